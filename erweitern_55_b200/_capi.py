@@ -1,0 +1,71 @@
+"""ctypes binding of libe55.so (include/e55.h).  Fails loudly when the CUDA library is missing."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libe55.so")
+
+E55_OK = 0
+E55_ERR_INVALID, E55_ERR_CUDA, E55_ERR_NO_WEIGHTS, E55_ERR_UNSUPPORTED, E55_ERR_NO_DEVICE = -1, -2, -3, -4, -5
+PRECISION_FP32, PRECISION_BF16_TC = 0, 1
+
+_f32p = C.POINTER(C.c_float)
+_ctx = C.c_void_p
+
+# name -> (restype, argtypes); every symbol include/e55.h declares
+SIGNATURES = {
+    "e55_version": (C.c_int, []),
+    "e55_create": (C.c_int, [C.POINTER(_ctx), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "e55_destroy": (None, [_ctx]),
+    "e55_last_error": (C.c_char_p, [_ctx]),
+    "e55_set_weights": (C.c_int, [_ctx, C.c_int, C.POINTER(_f32p), C.POINTER(C.POINTER(C.c_int64)), C.POINTER(C.c_int)]),
+    "e55_set_precision": (C.c_int, [_ctx, C.c_int]),
+    "e55_get_precision": (C.c_int, [_ctx, C.POINTER(C.c_int)]),
+    "e55_predict": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "e55_predict_device": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "e55_predict_masked": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "e55_predict_masked_device": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "e55_sync": (C.c_int, [_ctx]),
+    "e55_stream": (C.c_int, [_ctx, C.POINTER(C.c_void_p)]),
+    "e55_launch_count": (C.c_int, [_ctx, C.POINTER(C.c_int64)]),
+    "e55_debug_trunk": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_void_p]),
+    "e55_selftest_umma": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "e55_bench_umma": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+}
+
+_lib = None
+
+
+class E55Error(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"libe55 error {code}: {message}")
+        self.code = code
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def load():
+    """Load libe55.so once.  There is no fallback: a missing library is an ImportError."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise ImportError(
+            f"{_LIB_PATH} is missing: build it with `make -C erweitern_55_b200/csrc` "
+            "(or `python -c 'import __graft_entry__ as g; g.build()'`); there is no CPU fallback")
+    lib = C.CDLL(_LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(ctx, rc):
+    if rc != E55_OK:
+        msg = load().e55_last_error(ctx)
+        raise E55Error(rc, msg.decode("utf-8", "replace") if msg else "")

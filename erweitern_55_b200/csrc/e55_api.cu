@@ -1,0 +1,595 @@
+// libe55.so -- C ABI of the B200-native policy/value evaluator (see include/e55.h).
+// Host side: context, Keras weight-list parsing, BatchNorm folding, weight images, launch plumbing.
+#include "../../include/e55.h"
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "e55_fp32.cuh"
+#include "e55_tc.cuh"
+#include "e55_umma_test.cuh"
+
+namespace {
+
+constexpr int kSq = 25;
+constexpr int kPolicyCh = 69;
+constexpr int kValueHidden = 128;
+constexpr double kBnEps = 1e-3;  // Keras BatchNormalization default epsilon
+
+thread_local std::string g_create_error;
+
+struct ConvF32 {
+  float* w = nullptr;  // [taps][cin][cout], BN folded
+  float* b = nullptr;  // [cout]
+  int cin = 0, cout = 0, taps = 0;
+};
+
+}  // namespace
+
+struct e55_ctx {
+  int device = 0, blocks = 0, filters = 0, in_planes = 0;
+  int capacity = 0;
+  int precision = E55_PRECISION_BF16_TC;
+  bool has_weights = false;
+  int64_t launches = 0;
+  cudaStream_t stream = nullptr;
+  mutable std::mutex mu;
+  mutable std::string err;
+
+  // fp32 weight images
+  std::vector<ConvF32> convs;  // stem, 2 per block, policy conv (all 3x3)
+  ConvF32 policy_out;          // 1x1 -> 69
+  float* value_w = nullptr;    // [filters] folded value conv
+  float value_b = 0.f;
+  float* fc1_k = nullptr;      // [25][128]
+  float* fc1_b = nullptr;      // [128]
+  float* fc2_k = nullptr;      // [128]
+  float fc2_b = 0.f;
+
+  // tensor-core path state
+  e55::tc::State tc;
+
+  // device work buffers (sized for `capacity` positions)
+  float* d_in = nullptr;
+  float* d_act[3] = {nullptr, nullptr, nullptr};
+  float* d_policy = nullptr;
+  float* d_value = nullptr;
+  float* d_probs = nullptr;
+  uint8_t* d_mask = nullptr;
+};
+
+namespace {
+
+int fail(const e55_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg; else g_create_error = msg;
+  return code;
+}
+
+#define E55_CUDA(ctx, expr)                                                                    \
+  do {                                                                                         \
+    cudaError_t e__ = (expr);                                                                  \
+    if (e__ != cudaSuccess)                                                                    \
+      return fail(ctx, E55_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));     \
+  } while (0)
+
+void free_conv(ConvF32& c) {
+  cudaFree(c.w); cudaFree(c.b);
+  c = ConvF32();
+}
+
+void free_weights(e55_ctx* c) {
+  for (auto& cv : c->convs) free_conv(cv);
+  c->convs.clear();
+  free_conv(c->policy_out);
+  cudaFree(c->value_w); cudaFree(c->fc1_k); cudaFree(c->fc1_b); cudaFree(c->fc2_k);
+  c->value_w = c->fc1_k = c->fc1_b = c->fc2_k = nullptr;
+  e55::tc::free_weights(c->tc);
+  c->has_weights = false;
+}
+
+void free_buffers(e55_ctx* c) {
+  cudaFree(c->d_in);
+  for (auto& p : c->d_act) { cudaFree(p); p = nullptr; }
+  cudaFree(c->d_policy); cudaFree(c->d_value); cudaFree(c->d_probs); cudaFree(c->d_mask);
+  c->d_in = c->d_policy = c->d_value = c->d_probs = nullptr;
+  c->d_mask = nullptr;
+  e55::tc::free_buffers(c->tc);
+  c->capacity = 0;
+}
+
+int ensure_capacity(e55_ctx* c, int n) {
+  if (n <= c->capacity) return E55_OK;
+  E55_CUDA(c, cudaStreamSynchronize(c->stream));
+  free_buffers(c);
+  int cap = 64;
+  while (cap < n) cap *= 2;
+  const size_t act = static_cast<size_t>(cap) * c->filters * kSq * sizeof(float);
+  E55_CUDA(c, cudaMalloc(&c->d_in, static_cast<size_t>(cap) * c->in_planes * kSq * sizeof(float)));
+  for (auto& p : c->d_act) E55_CUDA(c, cudaMalloc(&p, act));
+  E55_CUDA(c, cudaMalloc(&c->d_policy, static_cast<size_t>(cap) * kPolicyCh * kSq * sizeof(float)));
+  E55_CUDA(c, cudaMalloc(&c->d_value, static_cast<size_t>(cap) * sizeof(float)));
+  E55_CUDA(c, cudaMalloc(&c->d_probs, static_cast<size_t>(cap) * kPolicyCh * kSq * sizeof(float)));
+  E55_CUDA(c, cudaMalloc(&c->d_mask, static_cast<size_t>(cap) * kPolicyCh * kSq));
+  cudaError_t e = e55::tc::alloc_buffers(c->tc, cap);
+  if (e != cudaSuccess) return fail(c, E55_ERR_CUDA, std::string("tc buffers: ") + cudaGetErrorString(e));
+  c->capacity = cap;
+  return E55_OK;
+}
+
+// ---- Keras weight list -> named layers ----------------------------------------------------------
+struct Tensor {
+  const float* data;
+  std::vector<int64_t> shape;
+  int64_t numel() const { int64_t n = 1; for (auto s : shape) n *= s; return n; }
+};
+struct BnRef { const float *gamma = nullptr, *beta = nullptr, *mean = nullptr, *var = nullptr; int c = 0; };
+struct LayerRef {
+  enum Kind { CONV, DENSE } kind;
+  Tensor kernel, bias;
+  BnRef bn;  // c == 0 when no BatchNorm follows
+};
+
+// Groups the flat list into conv/dense layers, each with the BatchNorm quadruple that follows it.
+bool group_layers(const std::vector<Tensor>& ts, std::vector<LayerRef>& out, std::string& why) {
+  size_t i = 0;
+  while (i < ts.size()) {
+    const Tensor& k = ts[i];
+    if (k.shape.size() == 4 || k.shape.size() == 2) {
+      if (i + 1 >= ts.size() || ts[i + 1].shape.size() != 1 || ts[i + 1].shape[0] != k.shape.back()) {
+        why = "kernel tensor " + std::to_string(i) + " is not followed by its bias";
+        return false;
+      }
+      LayerRef l;
+      l.kind = k.shape.size() == 4 ? LayerRef::CONV : LayerRef::DENSE;
+      l.kernel = k; l.bias = ts[i + 1];
+      out.push_back(l);
+      i += 2;
+    } else if (k.shape.size() == 1) {
+      if (i + 3 >= ts.size()) { why = "truncated BatchNorm group at tensor " + std::to_string(i); return false; }
+      const int64_t c = k.shape[0];
+      for (int j = 1; j < 4; ++j)
+        if (ts[i + j].shape.size() != 1 || ts[i + j].shape[0] != c) {
+          why = "BatchNorm group at tensor " + std::to_string(i) + " has inconsistent shapes";
+          return false;
+        }
+      // attach to the most recent conv with matching channel count that has no BN yet
+      bool attached = false;
+      for (size_t j = out.size(); j-- > 0;) {
+        if (out[j].kind == LayerRef::CONV && out[j].bn.c == 0 && out[j].kernel.shape[3] == c) {
+          out[j].bn = BnRef{ts[i].data, ts[i + 1].data, ts[i + 2].data, ts[i + 3].data, static_cast<int>(c)};
+          attached = true;
+          break;
+        }
+      }
+      if (!attached) { why = "BatchNorm group at tensor " + std::to_string(i) + " has no convolution"; return false; }
+      i += 4;
+    } else {
+      why = "tensor " + std::to_string(i) + " has unsupported rank";
+      return false;
+    }
+  }
+  return true;
+}
+
+// Fold inference BN into conv (double math): w'[t][ci][co] = w*s[co], b' = (b-mean)*s + beta,
+// s = gamma / sqrt(var + eps).   Keras HWIO flattening == [tap][ci][co].
+void fold(const LayerRef& l, std::vector<float>& w, std::vector<float>& b) {
+  const int64_t cout = l.kernel.shape.back();
+  const int64_t rows = l.kernel.numel() / cout;
+  w.resize(rows * cout);
+  b.resize(cout);
+  std::vector<double> s(cout, 1.0);
+  if (l.bn.c)
+    for (int64_t o = 0; o < cout; ++o) s[o] = static_cast<double>(l.bn.gamma[o]) / std::sqrt(static_cast<double>(l.bn.var[o]) + kBnEps);
+  for (int64_t r = 0; r < rows; ++r)
+    for (int64_t o = 0; o < cout; ++o) w[r * cout + o] = static_cast<float>(static_cast<double>(l.kernel.data[r * cout + o]) * s[o]);
+  for (int64_t o = 0; o < cout; ++o) {
+    double v = l.bias.data[o];
+    if (l.bn.c) v = (v - l.bn.mean[o]) * s[o] + l.bn.beta[o];
+    b[o] = static_cast<float>(v);
+  }
+}
+
+cudaError_t upload(float** dst, const std::vector<float>& src) {
+  cudaError_t e = cudaMalloc(dst, src.size() * sizeof(float));
+  if (e != cudaSuccess) return e;
+  return cudaMemcpy(*dst, src.data(), src.size() * sizeof(float), cudaMemcpyHostToDevice);
+}
+
+// ---- fp32 forward -------------------------------------------------------------------------------
+int launch_conv3x3(e55_ctx* c, const ConvF32& cv, const float* in, const float* res, float* out, int n, int relu) {
+  if (n <= 148) {
+    e55::fp32::conv3x3_kernel<1><<<n, cv.cout, 0, c->stream>>>(in, cv.w, cv.b, res, out, n, cv.cin, cv.cout, relu);
+  } else {
+    e55::fp32::conv3x3_kernel<4><<<(n + 3) / 4, cv.cout, 0, c->stream>>>(in, cv.w, cv.b, res, out, n, cv.cin, cv.cout, relu);
+  }
+  ++c->launches;
+  E55_CUDA(c, cudaGetLastError());
+  return E55_OK;
+}
+
+// trunk_out (optional) receives a pointer to the trunk output buffer.
+int forward_fp32(e55_ctx* c, const float* d_planes, int n, float* d_policy, float* d_value, const float** trunk_out) {
+  float* x = c->d_act[0];
+  float* y = c->d_act[1];
+  float* z = c->d_act[2];
+  int rc = launch_conv3x3(c, c->convs[0], d_planes, nullptr, x, n, 1);  // network.py:92-95
+  if (rc) return rc;
+  for (int b = 0; b < c->blocks; ++b) {                                 // network.py:98-99,124-146
+    if ((rc = launch_conv3x3(c, c->convs[1 + 2 * b], x, nullptr, y, n, 1))) return rc;
+    if ((rc = launch_conv3x3(c, c->convs[2 + 2 * b], y, x, z, n, 1))) return rc;
+    float* t = x; x = z; z = t;
+  }
+  if (trunk_out) *trunk_out = x;
+  if ((rc = launch_conv3x3(c, c->convs[1 + 2 * c->blocks], x, nullptr, y, n, 1))) return rc;  // network.py:102-105
+  const size_t act_smem = static_cast<size_t>(c->filters) * kSq * sizeof(float);
+  e55::fp32::policy_out_kernel<<<n, 256, act_smem, c->stream>>>(y, c->policy_out.w, c->policy_out.b, d_policy,
+                                                                c->filters, kPolicyCh);
+  ++c->launches;
+  E55_CUDA(c, cudaGetLastError());
+  e55::fp32::value_head_kernel<<<n, 128, act_smem, c->stream>>>(x, c->value_w, c->value_b, c->fc1_k, c->fc1_b,
+                                                                c->fc2_k, c->fc2_b, d_value, c->filters);
+  ++c->launches;
+  E55_CUDA(c, cudaGetLastError());
+  return E55_OK;
+}
+
+int forward(e55_ctx* c, const float* d_planes, int n, float* d_policy, float* d_value) {
+  if (c->precision == E55_PRECISION_FP32) return forward_fp32(c, d_planes, n, d_policy, d_value, nullptr);
+  std::string why;
+  int launched = 0;
+  cudaError_t e = e55::tc::forward(c->tc, d_planes, n, d_policy, d_value, c->stream, &launched, &why);
+  c->launches += launched;
+  if (e != cudaSuccess) return fail(c, E55_ERR_CUDA, "tensor-core forward: " + why + ": " + cudaGetErrorString(e));
+  if (!why.empty()) return fail(c, E55_ERR_UNSUPPORTED, why);
+  return E55_OK;
+}
+
+int check_predict_args(e55_ctx* c, const void* a, const void* b, const void* d, int n) {
+  if (!c) return E55_ERR_INVALID;
+  if (!a || !b || !d) return fail(c, E55_ERR_INVALID, "null buffer");
+  if (n <= 0) return fail(c, E55_ERR_INVALID, "batch size must be >= 1");
+  if (!c->has_weights) return fail(c, E55_ERR_NO_WEIGHTS, "predict called before e55_set_weights");
+  return E55_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int e55_version(void) { return 1; }
+
+const char* e55_last_error(const e55_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int e55_create(e55_ctx** out, int device, int blocks, int filters, int in_planes, int max_batch) {
+  if (!out) return fail(nullptr, E55_ERR_INVALID, "out is null");
+  *out = nullptr;
+  if (blocks < 0 || blocks > 64 || in_planes < 1 || in_planes > 4096 || max_batch < 1)
+    return fail(nullptr, E55_ERR_INVALID, "bad architecture arguments");
+  if (filters != 128 && filters != 256)
+    return fail(nullptr, E55_ERR_UNSUPPORTED, "filters must be 128 or 256");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, E55_ERR_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(nullptr, E55_ERR_INVALID, "device index out of range");
+  cudaDeviceProp prop;
+  E55_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(nullptr, E55_ERR_NO_DEVICE, std::string("device is not sm_100 (Blackwell B200): ") + prop.name);
+  E55_CUDA(nullptr, cudaSetDevice(device));
+  e55_ctx* c = new (std::nothrow) e55_ctx();
+  if (!c) return fail(nullptr, E55_ERR_INVALID, "out of host memory");
+  c->device = device; c->blocks = blocks; c->filters = filters; c->in_planes = in_planes;
+  e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete c; return fail(nullptr, E55_ERR_CUDA, cudaGetErrorString(e)); }
+  e55::tc::init(c->tc, blocks, filters, in_planes, prop.multiProcessorCount);
+  int rc = ensure_capacity(c, max_batch);
+  if (rc != E55_OK) { g_create_error = c->err; e55_destroy(c); return rc; }
+  *out = c;
+  return E55_OK;
+}
+
+void e55_destroy(e55_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  free_weights(c);
+  free_buffers(c);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int e55_set_weights(e55_ctx* c, int n_tensors, const float* const* data, const int64_t* const* shapes,
+                    const int* ndims) {
+  if (!c) return E55_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!data || !shapes || !ndims || n_tensors <= 0) return fail(c, E55_ERR_INVALID, "null weight list");
+  std::vector<Tensor> ts(n_tensors);
+  for (int i = 0; i < n_tensors; ++i) {
+    if (!data[i] || !shapes[i] || ndims[i] < 1 || ndims[i] > 4)
+      return fail(c, E55_ERR_INVALID, "weight tensor " + std::to_string(i) + " is malformed");
+    ts[i].data = data[i];
+    ts[i].shape.assign(shapes[i], shapes[i] + ndims[i]);
+  }
+  std::vector<LayerRef> layers;
+  std::string why;
+  if (!group_layers(ts, layers, why)) return fail(c, E55_ERR_INVALID, why);
+
+  // trunk: the first 1 + 2*blocks convolutions, in order (network.py:92-99)
+  const int n_trunk = 1 + 2 * c->blocks;
+  if (static_cast<int>(layers.size()) != n_trunk + 5)
+    return fail(c, E55_ERR_INVALID, "expected " + std::to_string(n_trunk + 5) + " conv/dense layers, got " +
+                                        std::to_string(layers.size()));
+  const int F = c->filters;
+  auto is_conv = [](const LayerRef& l, int kh, int64_t cin, int64_t cout, bool bn) {
+    return l.kind == LayerRef::CONV && l.kernel.shape[0] == kh && l.kernel.shape[1] == kh &&
+           l.kernel.shape[2] == cin && l.kernel.shape[3] == cout && (l.bn.c != 0) == bn;
+  };
+  for (int i = 0; i < n_trunk; ++i)
+    if (!is_conv(layers[i], 3, i == 0 ? c->in_planes : F, F, true))
+      return fail(c, E55_ERR_INVALID, "trunk convolution " + std::to_string(i) + " has the wrong shape or no BatchNorm");
+  // heads: identified by shape, any interleaving (Keras orders them by graph depth)
+  const LayerRef *value_conv = nullptr, *policy_conv = nullptr, *policy_out = nullptr, *fc1 = nullptr, *fc2 = nullptr;
+  for (size_t i = n_trunk; i < layers.size(); ++i) {
+    const LayerRef& l = layers[i];
+    if (is_conv(l, 1, F, 1, true) && !value_conv) value_conv = &l;
+    else if (is_conv(l, 3, F, F, true) && !policy_conv) policy_conv = &l;
+    else if (is_conv(l, 1, F, kPolicyCh, false) && !policy_out) policy_out = &l;
+    else if (l.kind == LayerRef::DENSE && l.kernel.shape[0] == kSq && l.kernel.shape[1] == kValueHidden && !fc1) fc1 = &l;
+    else if (l.kind == LayerRef::DENSE && l.kernel.shape[0] == kValueHidden && l.kernel.shape[1] == 1 && !fc2) fc2 = &l;
+    else return fail(c, E55_ERR_INVALID, "unrecognised head layer at position " + std::to_string(i));
+  }
+  if (!value_conv || !policy_conv || !policy_out || !fc1 || !fc2)
+    return fail(c, E55_ERR_INVALID, "a head layer is missing from the weight list");
+
+  E55_CUDA(c, cudaSetDevice(c->device));
+  E55_CUDA(c, cudaStreamSynchronize(c->stream));
+  free_weights(c);
+
+  std::vector<float> w, b;
+  std::vector<std::vector<float>> conv_w, conv_b;  // kept for the tensor-core packer
+  auto add_conv3 = [&](const LayerRef& l) -> cudaError_t {
+    fold(l, w, b);
+    ConvF32 cv;
+    cv.cin = static_cast<int>(l.kernel.shape[2]); cv.cout = static_cast<int>(l.kernel.shape[3]); cv.taps = 9;
+    cudaError_t e = upload(&cv.w, w);
+    if (e == cudaSuccess) e = upload(&cv.b, b);
+    c->convs.push_back(cv);
+    conv_w.push_back(w); conv_b.push_back(b);
+    return e;
+  };
+  for (int i = 0; i < n_trunk; ++i) E55_CUDA(c, add_conv3(layers[i]));
+  E55_CUDA(c, add_conv3(*policy_conv));
+
+  std::vector<float> pw, pb;
+  fold(*policy_out, pw, pb);
+  c->policy_out.cin = F; c->policy_out.cout = kPolicyCh; c->policy_out.taps = 1;
+  E55_CUDA(c, upload(&c->policy_out.w, pw));
+  E55_CUDA(c, upload(&c->policy_out.b, pb));
+
+  std::vector<float> vw, vb;
+  fold(*value_conv, vw, vb);
+  E55_CUDA(c, upload(&c->value_w, vw));
+  c->value_b = vb[0];
+  std::vector<float> k1(fc1->kernel.data, fc1->kernel.data + kSq * kValueHidden);
+  std::vector<float> b1(fc1->bias.data, fc1->bias.data + kValueHidden);
+  std::vector<float> k2(fc2->kernel.data, fc2->kernel.data + kValueHidden);
+  E55_CUDA(c, upload(&c->fc1_k, k1));
+  E55_CUDA(c, upload(&c->fc1_b, b1));
+  E55_CUDA(c, upload(&c->fc2_k, k2));
+  c->fc2_b = fc2->bias.data[0];
+
+  e55::tc::HeadWeights hw{pw.data(), pb.data(), c->value_w, c->value_b, c->fc1_k, c->fc1_b, c->fc2_k, c->fc2_b};
+  cudaError_t e = e55::tc::set_weights(c->tc, conv_w, conv_b, hw);
+  if (e != cudaSuccess) return fail(c, E55_ERR_CUDA, std::string("tensor-core weight image: ") + cudaGetErrorString(e));
+  c->has_weights = true;
+  return E55_OK;
+}
+
+int e55_set_precision(e55_ctx* c, int precision) {
+  if (!c) return E55_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (precision != E55_PRECISION_FP32 && precision != E55_PRECISION_BF16_TC)
+    return fail(c, E55_ERR_INVALID, "unknown precision");
+  if (precision == E55_PRECISION_BF16_TC && !e55::tc::supported(c->tc))
+    return fail(c, E55_ERR_UNSUPPORTED, "the tcgen05 path supports filters == 128 only");
+  c->precision = precision;
+  return E55_OK;
+}
+
+int e55_get_precision(const e55_ctx* c, int* precision) {
+  if (!c || !precision) return E55_ERR_INVALID;
+  *precision = c->precision;
+  return E55_OK;
+}
+
+int e55_predict_device(e55_ctx* c, const float* d_planes, int n, float* d_policy, float* d_value) {
+  int rc = check_predict_args(c, d_planes, d_policy, d_value, n);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  E55_CUDA(c, cudaSetDevice(c->device));
+  if ((rc = ensure_capacity(c, n))) return rc;
+  return forward(c, d_planes, n, d_policy, d_value);
+}
+
+int e55_predict(e55_ctx* c, const float* planes, int n, float* policy, float* value) {
+  int rc = check_predict_args(c, planes, policy, value, n);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  E55_CUDA(c, cudaSetDevice(c->device));
+  if ((rc = ensure_capacity(c, n))) return rc;
+  const size_t in_bytes = static_cast<size_t>(n) * c->in_planes * kSq * sizeof(float);
+  E55_CUDA(c, cudaMemcpyAsync(c->d_in, planes, in_bytes, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = forward(c, c->d_in, n, c->d_policy, c->d_value))) return rc;
+  E55_CUDA(c, cudaMemcpyAsync(policy, c->d_policy, static_cast<size_t>(n) * kPolicyCh * kSq * sizeof(float),
+                              cudaMemcpyDeviceToHost, c->stream));
+  E55_CUDA(c, cudaMemcpyAsync(value, c->d_value, static_cast<size_t>(n) * sizeof(float), cudaMemcpyDeviceToHost,
+                              c->stream));
+  E55_CUDA(c, cudaStreamSynchronize(c->stream));
+  return E55_OK;
+}
+
+int e55_predict_masked_device(e55_ctx* c, const float* d_planes, const uint8_t* d_mask, int n, float* d_probs,
+                              float* d_value) {
+  int rc = check_predict_args(c, d_planes, d_probs, d_value, n);
+  if (rc) return rc;
+  if (!d_mask) return fail(c, E55_ERR_INVALID, "null legal mask");
+  std::lock_guard<std::mutex> lk(c->mu);
+  E55_CUDA(c, cudaSetDevice(c->device));
+  if ((rc = ensure_capacity(c, n))) return rc;
+  if ((rc = forward(c, d_planes, n, c->d_policy, d_value))) return rc;
+  e55::fp32::masked_softmax_kernel<<<n, 256, 0, c->stream>>>(c->d_policy, d_mask, d_probs, kPolicyCh * kSq);
+  ++c->launches;
+  E55_CUDA(c, cudaGetLastError());
+  return E55_OK;
+}
+
+int e55_predict_masked(e55_ctx* c, const float* planes, const uint8_t* mask, int n, float* probs, float* value) {
+  int rc = check_predict_args(c, planes, probs, value, n);
+  if (rc) return rc;
+  if (!mask) return fail(c, E55_ERR_INVALID, "null legal mask");
+  std::lock_guard<std::mutex> lk(c->mu);
+  E55_CUDA(c, cudaSetDevice(c->device));
+  if ((rc = ensure_capacity(c, n))) return rc;
+  const size_t pol = static_cast<size_t>(n) * kPolicyCh * kSq;
+  E55_CUDA(c, cudaMemcpyAsync(c->d_in, planes, static_cast<size_t>(n) * c->in_planes * kSq * sizeof(float),
+                              cudaMemcpyHostToDevice, c->stream));
+  E55_CUDA(c, cudaMemcpyAsync(c->d_mask, mask, pol, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = forward(c, c->d_in, n, c->d_policy, c->d_value))) return rc;
+  e55::fp32::masked_softmax_kernel<<<n, 256, 0, c->stream>>>(c->d_policy, c->d_mask, c->d_probs, kPolicyCh * kSq);
+  ++c->launches;
+  E55_CUDA(c, cudaGetLastError());
+  E55_CUDA(c, cudaMemcpyAsync(probs, c->d_probs, pol * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  E55_CUDA(c, cudaMemcpyAsync(value, c->d_value, static_cast<size_t>(n) * sizeof(float), cudaMemcpyDeviceToHost,
+                              c->stream));
+  E55_CUDA(c, cudaStreamSynchronize(c->stream));
+  return E55_OK;
+}
+
+int e55_sync(e55_ctx* c) {
+  if (!c) return E55_ERR_INVALID;
+  E55_CUDA(c, cudaStreamSynchronize(c->stream));
+  return E55_OK;
+}
+
+int e55_stream(e55_ctx* c, void** stream_out) {
+  if (!c || !stream_out) return E55_ERR_INVALID;
+  *stream_out = static_cast<void*>(c->stream);
+  return E55_OK;
+}
+
+int e55_launch_count(const e55_ctx* c, int64_t* count_out) {
+  if (!c || !count_out) return E55_ERR_INVALID;
+  *count_out = c->launches;
+  return E55_OK;
+}
+
+int e55_debug_trunk(e55_ctx* c, const float* planes, int n, float* trunk_out) {
+  int rc = check_predict_args(c, planes, trunk_out, trunk_out, n);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  E55_CUDA(c, cudaSetDevice(c->device));
+  if ((rc = ensure_capacity(c, n))) return rc;
+  E55_CUDA(c, cudaMemcpyAsync(c->d_in, planes, static_cast<size_t>(n) * c->in_planes * kSq * sizeof(float),
+                              cudaMemcpyHostToDevice, c->stream));
+  const float* trunk = nullptr;
+  if (c->precision == E55_PRECISION_FP32) {
+    if ((rc = forward_fp32(c, c->d_in, n, c->d_policy, c->d_value, &trunk))) return rc;
+  } else {
+    if ((rc = forward(c, c->d_in, n, c->d_policy, c->d_value))) return rc;
+    std::string why;
+    int launched = 0;
+    cudaError_t e = e55::tc::export_trunk(c->tc, n, c->d_act[0], c->stream, &launched, &why);
+    c->launches += launched;
+    if (e != cudaSuccess) return fail(c, E55_ERR_CUDA, "export trunk: " + why + ": " + cudaGetErrorString(e));
+    if (!why.empty()) return fail(c, E55_ERR_UNSUPPORTED, why);
+    trunk = c->d_act[0];
+  }
+  E55_CUDA(c, cudaMemcpyAsync(trunk_out, trunk, static_cast<size_t>(n) * c->filters * kSq * sizeof(float),
+                              cudaMemcpyDeviceToHost, c->stream));
+  E55_CUDA(c, cudaStreamSynchronize(c->stream));
+  return E55_OK;
+}
+
+int e55_selftest_umma(int device, int row_shift, float* max_abs_err_out) {
+  using namespace e55::ummatest;
+  if (!max_abs_err_out || row_shift < 0 || row_shift > 64) return fail(nullptr, E55_ERR_INVALID, "bad selftest arguments");
+  E55_CUDA(nullptr, cudaSetDevice(device));
+  std::vector<__nv_bfloat16> ha(kRowsA * kK), hb(kN * kK);
+  std::vector<float> fa(ha.size()), fb(hb.size());
+  uint32_t s = 12345u + row_shift;
+  auto rnd = [&]() { s = s * 1664525u + 1013904223u; return static_cast<float>((s >> 9) & 0xFF) / 128.f - 1.f; };
+  for (size_t i = 0; i < ha.size(); ++i) { ha[i] = __float2bfloat16(rnd()); fa[i] = __bfloat162float(ha[i]); }
+  for (size_t i = 0; i < hb.size(); ++i) { hb[i] = __float2bfloat16(rnd()); fb[i] = __bfloat162float(hb[i]); }
+  __nv_bfloat16 *da = nullptr, *db = nullptr;
+  float* dd = nullptr;
+  E55_CUDA(nullptr, cudaMalloc(&da, ha.size() * 2));
+  E55_CUDA(nullptr, cudaMalloc(&db, hb.size() * 2));
+  E55_CUDA(nullptr, cudaMalloc(&dd, kM * kN * 4));
+  E55_CUDA(nullptr, cudaMemcpy(da, ha.data(), ha.size() * 2, cudaMemcpyHostToDevice));
+  E55_CUDA(nullptr, cudaMemcpy(db, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice));
+  E55_CUDA(nullptr, cudaMemset(dd, 0xFF, kM * kN * 4));
+  const size_t smem = (kK / 8) * (kRowsA + kN) * 16;
+  E55_CUDA(nullptr, cudaFuncSetAttribute(selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  selftest_kernel<<<1, 128, smem>>>(da, db, dd, row_shift);
+  E55_CUDA(nullptr, cudaGetLastError());
+  E55_CUDA(nullptr, cudaDeviceSynchronize());
+  std::vector<float> hd(kM * kN);
+  E55_CUDA(nullptr, cudaMemcpy(hd.data(), dd, hd.size() * 4, cudaMemcpyDeviceToHost));
+  cudaFree(da); cudaFree(db); cudaFree(dd);
+  float worst = 0.f;
+  for (int m = 0; m < kM; ++m)
+    for (int n = 0; n < kN; ++n) {
+      double ref = 0.0;
+      for (int k = 0; k < kK; ++k) ref += static_cast<double>(fa[(m + row_shift) * kK + k]) * fb[n * kK + k];
+      const float err = std::fabs(hd[m * kN + n] - static_cast<float>(ref));
+      if (!(err <= worst)) worst = std::isnan(err) ? INFINITY : err;
+    }
+  *max_abs_err_out = worst;
+  return E55_OK;
+}
+
+int e55_bench_umma(int device, int n_dim, int iters, float* tflops_out) {
+  using namespace e55::ummatest;
+  if (!tflops_out || iters < 1 || (n_dim != 128 && n_dim != 256)) return fail(nullptr, E55_ERR_INVALID, "bad bench arguments");
+  E55_CUDA(nullptr, cudaSetDevice(device));
+  cudaDeviceProp prop;
+  E55_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
+  const int grid = prop.multiProcessorCount;
+  float* sink = nullptr;
+  E55_CUDA(nullptr, cudaMalloc(&sink, grid * sizeof(float)));
+  const size_t smem = 16 * (128 * 2 + 64) * 16 + 8 * static_cast<size_t>(n_dim) * 16;
+  cudaEvent_t e0, e1;
+  E55_CUDA(nullptr, cudaEventCreate(&e0));
+  E55_CUDA(nullptr, cudaEventCreate(&e1));
+  float ms = 0.f;
+  for (int rep = 0; rep < 2; ++rep) {
+    E55_CUDA(nullptr, cudaEventRecord(e0));
+    if (n_dim == 128) {
+      E55_CUDA(nullptr, cudaFuncSetAttribute(bench_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      bench_kernel<128><<<grid, 128, smem>>>(iters, sink);
+    } else {
+      E55_CUDA(nullptr, cudaFuncSetAttribute(bench_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      bench_kernel<256><<<grid, 128, smem>>>(iters, sink);
+    }
+    E55_CUDA(nullptr, cudaGetLastError());
+    E55_CUDA(nullptr, cudaEventRecord(e1));
+    E55_CUDA(nullptr, cudaEventSynchronize(e1));
+    E55_CUDA(nullptr, cudaEventElapsedTime(&ms, e0, e1));
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+  const double flops = 2.0 * 128.0 * n_dim * 16.0 * 144.0 * iters * grid;
+  *tflops_out = static_cast<float>(flops / (ms * 1e-3) / 1e12);
+  return E55_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,213 @@
+"""Drop-in ``Network`` for erweitern_55's search code, backed by libe55.so (sm_100a CUDA kernels).
+
+Mirrors the public surface of the reference class ``erweitern_55/network.py:16-286`` that ``mcts.py``,
+``selfplay.py``, ``usi.py``, ``client.py`` and ``train.py`` touch: ``predict`` (network.py:201-216),
+``get_input/get_inputs/zero_inputs`` (network.py:255-274,283-286), ``get_weights/set_weights``
+(network.py:228-243), ``load/save`` (network.py:218-226,245-253), ``iter`` (network.py:276-281),
+``step`` (network.py:148-199; training is out of scope and raises), attributes ``input_shape``,
+``network_type`` and ``model`` (``client.py:51`` calls ``nn.model.set_weights`` directly).
+TensorFlow is replaced by the C ABI in ``include/e55.h``; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from .weights import IN_PLANES, POLICY_SIZE, infer_arch, init_weights, weight_spec
+
+_PRECISIONS = {"fp32": _capi.PRECISION_FP32, "bf16": _capi.PRECISION_BF16_TC}
+
+
+def _parse_device(device):
+    if isinstance(device, int):
+        return device
+    d = str(device).lower()
+    if d in ("gpu", "cuda"):
+        return 0
+    if d.startswith("cuda:") or d.startswith("gpu:"):
+        return int(d.split(":", 1)[1])
+    raise ValueError(
+        f"device {device!r} is not supported: this build evaluates on a B200 only "
+        "(the reference's 'cpu'/'tpu' session configs, network.py:21-42, have no counterpart)")
+
+
+class _ModelShim:
+    """Stands in for ``Network.model`` (a keras.Model in the reference) for the calls callers make."""
+
+    def __init__(self, net):
+        self._net = net
+
+    def set_weights(self, weights):  # client.py:51
+        self._net.set_weights(weights)
+
+    def get_weights(self):
+        return self._net.get_weights()
+
+    def predict(self, images, batch_size=None, verbose=0, steps=None):  # network.py:213-214
+        return list(self._net.predict(images))
+
+
+class Network:
+    def __init__(self, device="gpu", blocks=7, filters=128, in_planes=IN_PLANES, max_batch=1024,
+                 precision="bf16", weights=None, seed=None):
+        self._lib = _capi.load()
+        self._device = _parse_device(device)
+        self.network_type = "AlphaZero"                 # network.py:84
+        self.input_shape = [in_planes, 5, 5]            # network.py:85
+        self._blocks, self._filters, self._in_planes = blocks, filters, in_planes
+        self._ctx = C.c_void_p()
+        self._iterations = 0
+        self._weights = None
+        rc = self._lib.e55_create(C.byref(self._ctx), self._device, blocks, filters, in_planes, max_batch)
+        if rc != _capi.E55_OK:
+            _capi.check(None, rc)
+        self.model = _ModelShim(self)
+        self.set_precision(precision)
+        if weights is None:
+            # the reference starts from Keras' random initialisers (network.py:50-53)
+            if seed is None:
+                seed = int(np.random.randint(0, 2**31 - 1))
+            weights = init_weights(blocks, filters, in_planes, seed=seed)
+        self.set_weights(weights)
+        # warm-up predict on a float64 random input, as the reference does (network.py:71-73)
+        self.predict(np.random.rand(*([1] + self.input_shape)))
+
+    # ---- lifecycle ---------------------------------------------------------------------------
+    def close(self):
+        ctx, self._ctx = self._ctx, C.c_void_p()
+        if ctx:
+            self._lib.e55_destroy(ctx)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        _capi.check(self._ctx, rc)
+
+    # ---- configuration -------------------------------------------------------------------------
+    def set_precision(self, precision):
+        if precision not in _PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}")
+        self._check(self._lib.e55_set_precision(self._ctx, _PRECISIONS[precision]))
+        self.precision = precision
+
+    # ---- weights (network.py:228-243) ----------------------------------------------------------
+    def get_weights(self):
+        return [w.copy() for w in self._weights]
+
+    def set_weights(self, weights):
+        ws = [np.ascontiguousarray(np.asarray(w, dtype=np.float32)) for w in weights]
+        blocks, filters, in_planes = infer_arch(ws)
+        if (blocks, filters, in_planes) != (self._blocks, self._filters, self._in_planes):
+            raise ValueError(f"weight list describes a {blocks}x{filters} tower on {in_planes} planes, "
+                             f"this Network is {self._blocks}x{self._filters} on {self._in_planes}")
+        n = len(ws)
+        data = (C.POINTER(C.c_float) * n)(*[w.ctypes.data_as(C.POINTER(C.c_float)) for w in ws])
+        shape_arrays = [(C.c_int64 * w.ndim)(*w.shape) for w in ws]
+        shapes = (C.POINTER(C.c_int64) * n)(*[C.cast(s, C.POINTER(C.c_int64)) for s in shape_arrays])
+        ndims = (C.c_int * n)(*[w.ndim for w in ws])
+        self._check(self._lib.e55_set_weights(self._ctx, n, data, shapes, ndims))
+        self._weights = ws
+
+    def load(self, filepath):
+        """Load weights saved by :meth:`save` (``.npz``).  Keras ``.h5`` files (network.py:226) need h5py,
+        which this environment lacks; convert them with ``np.savez(path, *model.get_weights())``."""
+        if str(filepath).endswith((".h5", ".hdf5")):
+            raise NotImplementedError("Keras HDF5 checkpoints are not readable here (no h5py); "
+                                      "export model.get_weights() to .npz")
+        with np.load(filepath) as z:
+            n = len([k for k in z.files if k.startswith("arr_")])
+            self.set_weights([z[f"arr_{i}"] for i in range(n)])
+            if "iterations" in z.files:
+                self._iterations = int(z["iterations"])
+
+    def save(self, filepath):
+        np.savez(filepath, *self._weights, iterations=np.int64(self._iterations))
+
+    # ---- inputs (network.py:255-274,283-286) ----------------------------------------------------
+    def get_input(self, position, dim_4=False):
+        shape = [1] + self.input_shape if dim_4 else self.input_shape
+        return np.reshape(position.to_alphazero_input(), shape)
+
+    def get_inputs(self, positions):
+        ins = np.zeros([len(positions)] + self.input_shape, dtype="float32")
+        for i, position in enumerate(positions):
+            ins[i] = self.get_input(position)
+        return ins
+
+    def zero_inputs(self, batch_size):
+        return np.zeros([batch_size] + self.input_shape, dtype="float32")
+
+    # ---- evaluation (network.py:201-216) --------------------------------------------------------
+    def _as_batch(self, images):
+        x = np.ascontiguousarray(np.asarray(images, dtype=np.float32))
+        if x.ndim != 4 or list(x.shape[1:]) != self.input_shape:
+            raise ValueError(f"expected images of shape [N,{self.input_shape[0]},5,5], got {list(x.shape)}")
+        if x.shape[0] == 0:
+            raise ValueError("empty batch")
+        return x
+
+    def predict(self, images):
+        """policy float32 ``[N,1725]`` raw logits, value float32 ``[N,1]`` (tanh); whole input = one batch."""
+        x = self._as_batch(images)
+        n = x.shape[0]
+        policy = np.empty((n, POLICY_SIZE), dtype=np.float32)
+        value = np.empty((n, 1), dtype=np.float32)
+        self._check(self._lib.e55_predict(self._ctx, x.ctypes.data, n, policy.ctypes.data, value.ctypes.data))
+        return policy, value
+
+    def predict_masked(self, images, legal_mask):
+        """Fused policy tail: softmax over legal moves (what minishogilib.MCTS.evaluate does with the
+        logits, mcts.py:60,105-106).  ``legal_mask`` uint8/bool ``[N,1725]``."""
+        x = self._as_batch(images)
+        n = x.shape[0]
+        m = np.ascontiguousarray(np.asarray(legal_mask).astype(np.uint8))
+        if m.shape != (n, POLICY_SIZE):
+            raise ValueError(f"legal_mask must have shape [{n},{POLICY_SIZE}]")
+        probs = np.empty((n, POLICY_SIZE), dtype=np.float32)
+        value = np.empty((n, 1), dtype=np.float32)
+        self._check(self._lib.e55_predict_masked(self._ctx, x.ctypes.data, m.ctypes.data, n,
+                                                 probs.ctypes.data, value.ctypes.data))
+        return probs, value
+
+    def predict_device(self, planes, policy, value):
+        """Device-resident variant: torch CUDA tensors (float32, contiguous); asynchronous on the context
+        stream -- call :meth:`sync` before reading the outputs from another stream."""
+        n = int(planes.shape[0])
+        self._check(self._lib.e55_predict_device(self._ctx, planes.data_ptr(), n, policy.data_ptr(), value.data_ptr()))
+
+    def debug_trunk(self, images):
+        x = self._as_batch(images)
+        out = np.empty((x.shape[0], self._filters, 5, 5), dtype=np.float32)
+        self._check(self._lib.e55_debug_trunk(self._ctx, x.ctypes.data, x.shape[0], out.ctypes.data))
+        return out
+
+    def sync(self):
+        self._check(self._lib.e55_sync(self._ctx))
+
+    def cuda_stream(self) -> int:
+        s = C.c_void_p()
+        self._check(self._lib.e55_stream(self._ctx, C.byref(s)))
+        return int(s.value or 0)
+
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        self._check(self._lib.e55_launch_count(self._ctx, C.byref(n)))
+        return int(n.value)
+
+    # ---- training (out of scope) ----------------------------------------------------------------
+    def iter(self):
+        return self._iterations
+
+    def step(self, train_images, policy_labels, value_labels, assertion=False):
+        raise NotImplementedError("training (network.py:148-199) is outside the accelerated path; "
+                                  "train with the reference and hand the weights over with set_weights()")
+
+
+def expected_weight_shapes(blocks=7, filters=128, in_planes=IN_PLANES):
+    return [s for _, s in weight_spec(blocks, filters, in_planes)]

@@ -1,0 +1,111 @@
+/*
+ * e55.h -- C ABI of the B200-native policy/value network evaluator (libe55.so).
+ *
+ * Drop-in boundary for ONE path of nyashiki/erweitern_55: the batched forward pass behind
+ * `Network.predict` (reference erweitern_55/network.py:201-216), i.e. the graph built by
+ * `_alphazero_network` / `_residual_block` (network.py:75-146), with weights exchanged in the Keras
+ * `get_weights()` list format (network.py:228-243).  In the reference this boundary is
+ * `keras.Model.predict` -> `tf.Session.run` (TensorFlow 1.15.2, not vendored); a maintainer binds
+ * these symbols with ctypes from network.py.
+ *
+ * Conventions: plain pointers and sizes only; the caller owns every in/out buffer; the library owns
+ * the context, device weights, staging buffers, streams and graphs.  Every function returns E55_OK (0)
+ * or a negative error code; the message is available through e55_last_error().  No C++ exception
+ * crosses the ABI.  One context = one GPU + one stream; calls on one context are serialised
+ * internally (any host thread may call); distinct contexts are independent (one per GPU for sharding).
+ * There is no CPU fallback: without a usable CUDA device e55_create() fails.
+ */
+#ifndef E55_H_
+#define E55_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct e55_ctx e55_ctx;
+
+enum {
+  E55_OK = 0,
+  E55_ERR_INVALID = -1,      /* bad argument / shape */
+  E55_ERR_CUDA = -2,         /* CUDA runtime error (message has the CUDA string) */
+  E55_ERR_NO_WEIGHTS = -3,   /* predict before set_weights */
+  E55_ERR_UNSUPPORTED = -4,  /* architecture not supported by the requested precision path */
+  E55_ERR_NO_DEVICE = -5     /* no CUDA device / device is not sm_100 */
+};
+
+enum {
+  E55_PRECISION_FP32 = 0,    /* CUDA-core fp32 path (same arithmetic type as the reference) */
+  E55_PRECISION_BF16_TC = 1  /* bf16 operands on tcgen05 tensor cores, fp32 accumulation */
+};
+
+/* Library ABI version (bumped on incompatible change). */
+int e55_version(void);
+
+/* Replaces Network.__init__ session/graph construction (network.py:17-69).  `blocks`, `filters`,
+ * `in_planes` describe the tower (reference defaults 7, 128, 266); `max_batch` is a sizing hint,
+ * larger batches grow the buffers on demand. */
+int e55_create(e55_ctx** out, int device, int blocks, int filters, int in_planes, int max_batch);
+void e55_destroy(e55_ctx* ctx);
+
+/* Message of the last failing call on `ctx` (or of the last failing e55_create on this thread when
+ * ctx is NULL).  Valid until the next call on the same ctx/thread. */
+const char* e55_last_error(const e55_ctx* ctx);
+
+/* Replaces Network.set_weights / model.set_weights (network.py:238-243; client.py:51).  Takes the
+ * Keras get_weights() list: n_tensors float32 arrays, shapes[i][0..ndims[i]).  Folds inference
+ * BatchNorm (eps 1e-3) into the preceding convolution, builds the fp32 and the bf16/UMMA weight
+ * images and uploads them. */
+int e55_set_weights(e55_ctx* ctx, int n_tensors, const float* const* data,
+                    const int64_t* const* shapes, const int* ndims);
+
+/* Select the arithmetic path used by the predict calls (default E55_PRECISION_BF16_TC). */
+int e55_set_precision(e55_ctx* ctx, int precision);
+int e55_get_precision(const e55_ctx* ctx, int* precision);
+
+/* Replaces Network.predict (network.py:201-216) for HOST buffers: planes float32 [n,in_planes,5,5]
+ * (NCHW) -> policy float32 [n,1725] raw logits (index c*25+y*5+x), value float32 [n,1] (tanh).
+ * The whole input is one batch.  Includes H2D and D2H copies; returns after the outputs are in the
+ * caller's buffers. */
+int e55_predict(e55_ctx* ctx, const float* planes, int n, float* policy, float* value);
+
+/* Same computation on DEVICE buffers, enqueued on the context stream; returns without
+ * synchronising (call e55_sync).  Buffers must stay valid until then. */
+int e55_predict_device(e55_ctx* ctx, const float* d_planes, int n, float* d_policy, float* d_value);
+
+/* Fused policy tail for the caller-side post-processing the reference leaves to
+ * minishogilib.MCTS.evaluate (mcts.py:59-60,103-106): probs = softmax over entries with
+ * legal_mask != 0 (others 0), legal_mask uint8 [n,1725]; value as in e55_predict. */
+int e55_predict_masked(e55_ctx* ctx, const float* planes, const uint8_t* legal_mask, int n,
+                       float* probs, float* value);
+int e55_predict_masked_device(e55_ctx* ctx, const float* d_planes, const uint8_t* d_legal_mask, int n,
+                              float* d_probs, float* d_value);
+
+/* Block until all work enqueued on the context stream has finished. */
+int e55_sync(e55_ctx* ctx);
+
+/* The cudaStream_t the context launches on (for CUDA-event timing by the caller). */
+int e55_stream(e55_ctx* ctx, void** stream_out);
+
+/* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
+int e55_launch_count(const e55_ctx* ctx, int64_t* count_out);
+
+/* Debug/verification: run the forward pass on device planes and copy the trunk output (input of the
+ * two heads, float32 [n,filters,5,5]) to the host. */
+int e55_debug_trunk(e55_ctx* ctx, const float* planes, int n, float* trunk_out);
+
+/* Hardware self-test of the tcgen05 operand addressing this library depends on: one 128x128x64 bf16
+ * UMMA from no-swizzle K-major shared-memory operands whose A descriptor start is displaced by
+ * `row_shift` rows (16-byte granularity), compared with a CPU product.  max_abs_err_out receives the
+ * largest deviation. */
+int e55_selftest_umma(int device, int row_shift, float* max_abs_err_out);
+
+/* Tensor-pipe micro-benchmark: every SM issues `iters` rounds of 72 back-to-back 128 x n_dim x 16
+ * UMMAs (n_dim 128 or 256) from shared memory; tflops_out receives the achieved dense bf16 rate. */
+int e55_bench_umma(int device, int n_dim, int iters, float* tflops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* E55_H_ */
