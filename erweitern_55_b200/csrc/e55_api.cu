@@ -493,28 +493,42 @@ int e55_launch_count(const e55_ctx* c, int64_t* count_out) {
   return E55_OK;
 }
 
-int e55_debug_trunk(e55_ctx* c, const float* planes, int n, float* trunk_out) {
-  int rc = check_predict_args(c, planes, trunk_out, trunk_out, n);
+int e55_debug_activations(e55_ctx* c, const float* planes, int n, int n_convs, float* act_out) {
+  int rc = check_predict_args(c, planes, act_out, act_out, n);
   if (rc) return rc;
+  if (n_convs < 1 || n_convs > 1 + 2 * c->blocks) return fail(c, E55_ERR_INVALID, "n_convs out of range");
   std::lock_guard<std::mutex> lk(c->mu);
   E55_CUDA(c, cudaSetDevice(c->device));
   if ((rc = ensure_capacity(c, n))) return rc;
   E55_CUDA(c, cudaMemcpyAsync(c->d_in, planes, static_cast<size_t>(n) * c->in_planes * kSq * sizeof(float),
                               cudaMemcpyHostToDevice, c->stream));
-  const float* trunk = nullptr;
+  const float* result = nullptr;
   if (c->precision == E55_PRECISION_FP32) {
-    if ((rc = forward_fp32(c, c->d_in, n, c->d_policy, c->d_value, &trunk))) return rc;
+    float* x = c->d_act[0];
+    float* y = c->d_act[1];
+    float* z = c->d_act[2];
+    if ((rc = launch_conv3x3(c, c->convs[0], c->d_in, nullptr, x, n, 1))) return rc;
+    result = x;
+    for (int i = 1; i < n_convs; ++i) {
+      if (i % 2 == 1) {
+        if ((rc = launch_conv3x3(c, c->convs[i], x, nullptr, y, n, 1))) return rc;
+        result = y;
+      } else {
+        if ((rc = launch_conv3x3(c, c->convs[i], y, x, z, n, 1))) return rc;
+        float* t = x; x = z; z = t;
+        result = x;
+      }
+    }
   } else {
-    if ((rc = forward(c, c->d_in, n, c->d_policy, c->d_value))) return rc;
     std::string why;
     int launched = 0;
-    cudaError_t e = e55::tc::export_trunk(c->tc, n, c->d_act[0], c->stream, &launched, &why);
+    cudaError_t e = e55::tc::debug_layers(c->tc, c->d_in, n, n_convs, c->d_act[0], c->stream, &launched, &why);
     c->launches += launched;
-    if (e != cudaSuccess) return fail(c, E55_ERR_CUDA, "export trunk: " + why + ": " + cudaGetErrorString(e));
+    if (e != cudaSuccess) return fail(c, E55_ERR_CUDA, "debug activations: " + why + ": " + cudaGetErrorString(e));
     if (!why.empty()) return fail(c, E55_ERR_UNSUPPORTED, why);
-    trunk = c->d_act[0];
+    result = c->d_act[0];
   }
-  E55_CUDA(c, cudaMemcpyAsync(trunk_out, trunk, static_cast<size_t>(n) * c->filters * kSq * sizeof(float),
+  E55_CUDA(c, cudaMemcpyAsync(act_out, result, static_cast<size_t>(n) * c->filters * kSq * sizeof(float),
                               cudaMemcpyDeviceToHost, c->stream));
   E55_CUDA(c, cudaStreamSynchronize(c->stream));
   return E55_OK;

@@ -1,28 +1,639 @@
-// Tensor-core (tcgen05) path -- placeholder until the tower kernel lands.
+// Tensor-core path: the whole network (stem, residual tower, policy conv, policy 1x1, value head) for
+// a batch of positions in ONE persistent, warp-specialised sm_100a kernel.
+//
+// Restates network.py:87-146 with BatchNorm folded into bf16 weights.  Every 3x3 convolution is an
+// implicit GEMM on tcgen05:  D[row, cout] += A[row + shift(tap), cin] * W[tap][cin, cout]
+//
+//   * rows  = squares of a "wide board": 4 positions side by side, each 5 squares + 1 zero column wide,
+//             5 board rows -> row = y*24 + p*6 + x  (120 rows, one UMMA M=128 tile).  A 3x3 tap is then
+//             the constant row displacement (dy*24 + dx); the zero columns and 25 zero guard rows
+//             above/below supply the 'same' padding.  M efficiency = 100/128.
+//   * A     = activations, bf16, resident in shared memory for the whole network, stored as 16 channel
+//             planes [plane = c/8][row][c%8]: the no-swizzle K-major UMMA layout with SBO = 128 B, in
+//             which rows are linear, so a tap is just start-address + shift*16 B (e55_selftest_umma).
+//   * B     = weights, bf16, pre-packed on the host into the same layout per (tap, 64-channel) chunk
+//             and streamed L2 -> smem by bulk TMA through an 8-stage mbarrier ring.
+//   * D     = fp32 accumulators in TMEM (128 lanes = rows, 128 columns = output channels).
+//
+// A CTA evaluates 8 positions per round as two independent 4-position groups A and B.  Both groups
+// consume the SAME weight stream (a ring stage is released after both have used it); the single MMA
+// thread gives group A priority, so A runs up to 7 chunks ahead of B and the epilogue of one group
+// (TMEM -> +bias (+residual) -> ReLU -> bf16 -> smem, in place) overlaps the other group's MMAs.
+// The residual operand never leaves registers: the epilogue thread that owns a row keeps its block
+// input as 64 packed bf16x2 registers.
+//
+// Warp roles (352 threads): warps 0-3 epilogue of group A (TMEM lane quadrant = warp%4), warps 4-7
+// epilogue of group B, warp 8 weight producer (TMA), warp 9 MMA issuer, warp 10 stem-input loader (TMA).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
 #include <string>
 #include <vector>
+
+#include "e55_ptx.cuh"
 
 namespace e55 {
 namespace tc {
 
+// ---- geometry -----------------------------------------------------------------------------------
+constexpr int kF = 128;                // tower width this kernel is specialised for
+constexpr int kPosPerGroup = 4;
+constexpr int kPosPerRound = 8;
+constexpr int kW = 24;                 // wide-board width
+constexpr int kRowsValid = 120;        // 5 * kW
+constexpr int kTile = 128;             // UMMA M
+constexpr int kGuard = 25;             // kW + 1
+constexpr int kRowsTotal = kGuard + kTile + kGuard + kTile + kGuard;  // 331
+constexpr int kPlanes = kF / 8;        // 16
+constexpr int kPlaneBytes = kRowsTotal * 16;
+constexpr int kActBytes = kPlanes * kPlaneBytes;                       // 84,736
+constexpr int kMaxStages = 8;
+constexpr int kStageBytes = 16384;     // one (tap, 64-channel) chunk of a 128-wide layer
+constexpr int kPolicyCh = 69;
+constexpr int kPolicyN = 80;           // policy 1x1 output channels padded to a legal UMMA N
+constexpr int kSq = 25;
+constexpr int kThreads = 352;
+constexpr int kTmemCols = 256;
+
+__host__ __device__ constexpr int group_origin_row(int g) { return kGuard + g * (kTile + kGuard); }
+
+enum : uint32_t { kFirstOfSlice = 1, kLastOfSlice = 2, kFirstOfLayer = 4, kLastOfLayer = 8 };
+enum : uint32_t { kRelu = 1, kHasRes = 2, kUpdRes = 4, kValueTap = 8, kFinal = 16 };
+
+struct alignas(16) Chunk {
+  uint32_t gofs;     // byte offset into the weight image
+  uint32_t bytes;    // nk * 2 * ndim * 16
+  int16_t shift;     // row displacement of the tap
+  uint8_t nk;        // K=16 steps in this chunk
+  uint8_t kplane;    // first activation plane (within the 16 resident planes)
+  uint8_t flags;
+  uint8_t layer;
+  uint8_t slice;
+  uint8_t ndim8;     // UMMA N / 8 of the layer
+};
+
+struct LayerInfo {
+  int chunk_begin, chunk_end;
+  int ndim;          // UMMA N
+  uint32_t flags;
+};
+
+struct Params {
+  const uint8_t* wimg;
+  const Chunk* chunks;
+  const LayerInfo* layers;
+  const float* bias;       // [nlayers][128]
+  const float* value_w;    // [128]
+  const float* fc1_k;      // [25][128]
+  const float* fc1_b;      // [128]
+  const float* fc2_k;      // [128]
+  float value_b, fc2_b;
+  const uint8_t* in_packed;  // [groups][in_planes8][120][16 B]
+  int in_planes8;            // ceil(in_planes / 16) * 2
+  int nslices;
+  int nstages;               // weight ring depth
+  int nchunks_total;         // chunks of the full network (size of the shared-memory chunk table)
+  int nlayers;               // layers of the full network (tower convs + policy conv + policy 1x1)
+  int nlayers_run;           // == nlayers, or fewer for a debug dump
+  int n;                     // positions
+  int nrounds;
+  float* policy;             // [n][1725]
+  float* value;              // [n]
+  uint4* dbg;                // [rounds*2][16][128] packed activations after layer nlayers_run-1
+};
+
+// ---- input packing: fp32 NCHW planes -> bf16 wide-board planes ------------------------------------
+// out[group][plane][row][8]: row = y*24 + p*6 + x, zero for the pad column, absent positions and the
+// channels beyond in_planes.  (network.py:255-274 builds the fp32 array this reads.)
+__global__ void __launch_bounds__(256)
+pack_input_kernel(const float* __restrict__ in, uint4* __restrict__ out, int n, int in_planes, int planes8) {
+  const int group = blockIdx.x;
+  for (int idx = threadIdx.x; idx < planes8 * kRowsValid; idx += blockDim.x) {
+    const int pl = idx / kRowsValid, r = idx % kRowsValid;
+    const int y = r / kW, p = (r % kW) / 6, x = r % 6;
+    const int pos = group * kPosPerGroup + p;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (x < 5 && pos < n) {
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int c = pl * 8 + e;
+        f[e] = c < in_planes ? in[(static_cast<size_t>(pos) * in_planes + c) * kSq + y * 5 + x] : 0.f;
+      }
+      v.x = ptx::pack_bf16x2(f[0], f[1]); v.y = ptx::pack_bf16x2(f[2], f[3]);
+      v.z = ptx::pack_bf16x2(f[4], f[5]); v.w = ptx::pack_bf16x2(f[6], f[7]);
+    }
+    out[(static_cast<size_t>(group) * planes8 + pl) * kRowsValid + r] = v;
+  }
+}
+
+// debug: packed activations [group][16][128 rows][8] bf16 -> fp32 NCHW [n][128][25]
+__global__ void unpack_debug_kernel(const uint4* __restrict__ dbg, float* __restrict__ out, int n) {
+  const int pos = blockIdx.x;
+  const int group = pos / kPosPerGroup, p = pos % kPosPerGroup;
+  for (int idx = threadIdx.x; idx < kPlanes * kSq; idx += blockDim.x) {
+    const int pl = idx / kSq, sq = idx % kSq;
+    const int r = (sq / 5) * kW + p * 6 + sq % 5;
+    const uint4 v = dbg[(static_cast<size_t>(group) * kPlanes + pl) * kTile + r];
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const uint32_t bits = (e & 1) ? (w[e >> 1] & 0xFFFF0000u) : (w[e >> 1] << 16);
+      out[(static_cast<size_t>(pos) * kF + pl * 8 + e) * kSq + sq] = __uint_as_float(bits);
+    }
+  }
+}
+
+__device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+
+// ---- the tower kernel ---------------------------------------------------------------------------
+struct SmemLayout {
+  static constexpr int ring = 0;
+  __host__ __device__ static constexpr int act(int nstages) { return ring + nstages * kStageBytes; }
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+tower_kernel(const Params prm) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* s_ring = smem + SmemLayout::ring;
+  uint8_t* s_act = smem + SmemLayout::act(prm.nstages);
+  float* s_bias = reinterpret_cast<float*>(s_act + kActBytes);
+  float* s_wv = s_bias + prm.nlayers * kF;
+  float* s_v = s_wv + kF;                       // [2 groups][4 positions][25]
+  float* s_part = s_v + 2 * kPosPerGroup * kSq;  // [2 groups][4 warps][4 positions]
+  Chunk* s_chunks = reinterpret_cast<Chunk*>(s_part + 32);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_chunks + prm.nchunks_total);
+  const uint32_t kStages = prm.nstages;
+  uint64_t* bar_full = bars;                    // [kStages]
+  uint64_t* bar_empty = bars + kStages;         // [kStages]
+  uint64_t* bar_tmem_full = bars + 2 * kStages;  // [2]
+  uint64_t* bar_act_ready = bar_tmem_full + 2;  // [2]
+  uint64_t* bar_in_full = bar_act_ready + 2;    // [2]
+  uint64_t* bar_in_empty = bar_in_full + 2;     // [2]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_in_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nl = prm.nlayers_run;
+  const uint32_t nchunks = prm.layers[nl - 1].chunk_end;
+
+  // ---- one-time setup -----------------------------------------------------------------------
+  for (int i = threadIdx.x; i < kActBytes / 16; i += kThreads)
+    reinterpret_cast<uint4*>(s_act)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = threadIdx.x; i < prm.nlayers * kF; i += kThreads) s_bias[i] = prm.bias[i];
+  for (int i = threadIdx.x; i < kF; i += kThreads) s_wv[i] = prm.value_w[i];
+  for (int i = threadIdx.x; i < prm.nchunks_total; i += kThreads) s_chunks[i] = prm.chunks[i];
+  if (threadIdx.x == 0) {
+    for (uint32_t s = 0; s < kStages; ++s) {
+      ptx::mbar_init(&bar_full[s], 1);
+      ptx::mbar_init(&bar_empty[s], 2);
+    }
+    for (int g = 0; g < 2; ++g) {
+      ptx::mbar_init(&bar_tmem_full[g], 1);
+      ptx::mbar_init(&bar_act_ready[g], 4);
+      ptx::mbar_init(&bar_in_full[g], 1);
+      ptx::mbar_init(&bar_in_empty[g], 1);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 9) ptx::tmem_alloc<kTmemCols>(s_tmem);
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 8) {
+    // ===== weight producer ===================================================================
+    if (lane == 0) {
+      uint32_t gc = 0;
+      for (int r = blockIdx.x; r < prm.nrounds; r += gridDim.x) {
+        for (uint32_t c = 0; c < nchunks; ++c, ++gc) {
+          const Chunk ch = s_chunks[c];
+          const uint32_t s = gc % kStages;
+          ptx::mbar_wait(&bar_empty[s], ((gc / kStages) & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(&bar_full[s], ch.bytes);
+          ptx::tma_bulk_g2s(s_ring + s * kStageBytes, prm.wimg + ch.gofs, ch.bytes, &bar_full[s]);
+        }
+      }
+    }
+  } else if (warp == 10) {
+    // ===== stem-input loader =================================================================
+    if (lane == 0) {
+      uint32_t k[2] = {0, 0};  // loads issued so far per group
+      for (int r = blockIdx.x; r < prm.nrounds; r += gridDim.x) {
+        for (int sl = 0; sl < prm.nslices; ++sl) {
+          const int pl0 = sl * kPlanes;
+          const int npl = min(kPlanes, prm.in_planes8 - pl0);
+          for (int g = 0; g < 2; ++g) {
+            if (r * kPosPerRound + g * kPosPerGroup >= prm.n) continue;
+            if (k[g] > 0) ptx::mbar_wait(&bar_in_empty[g], (k[g] - 1) & 1);
+            ptx::mbar_arrive_expect_tx(&bar_in_full[g], npl * kRowsValid * 16);
+            const uint8_t* src = prm.in_packed +
+                                 (static_cast<size_t>(r * 2 + g) * prm.in_planes8 + pl0) * (kRowsValid * 16);
+            for (int pl = 0; pl < npl; ++pl)
+              ptx::tma_bulk_g2s(s_act + pl * kPlaneBytes + group_origin_row(g) * 16,
+                                src + static_cast<size_t>(pl) * kRowsValid * 16, kRowsValid * 16, &bar_in_full[g]);
+            ++k[g];
+          }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ===== MMA issuer ========================================================================
+    if (lane == 0) {
+      const uint32_t act_addr = ptx::smem_u32(s_act);
+      const uint32_t ring_addr = ptx::smem_u32(s_ring);
+      uint32_t full_seen = 0, round_seq = 0;
+      for (int r = blockIdx.x; r < prm.nrounds; r += gridDim.x, ++round_seq) {
+        const bool has_b = r * kPosPerRound + kPosPerGroup < prm.n;
+        uint32_t pos[2] = {0u, has_b ? 0u : nchunks};
+        const uint32_t gbase = round_seq * nchunks;
+        while (pos[0] < nchunks || pos[1] < nchunks) {
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            if (pos[g] >= nchunks) continue;
+            const uint32_t c = pos[g];
+            const Chunk ch = s_chunks[c];
+            const uint32_t gc = gbase + c;
+            const uint32_t s = gc % kStages;
+            if (gc >= full_seen) {
+              if (!ptx::mbar_test_wait(&bar_full[s], (gc / kStages) & 1)) continue;
+              full_seen = gc + 1;
+            }
+            if (ch.flags & kFirstOfSlice) {
+              const uint32_t epoch = round_seq * nl + ch.layer;
+              if (ch.layer == 0) {
+                const uint32_t k = round_seq * prm.nslices + ch.slice;
+                if (!ptx::mbar_test_wait(&bar_in_full[g], k & 1)) continue;
+              }
+              if ((ch.flags & kFirstOfLayer) && epoch > 0) {
+                if (!ptx::mbar_test_wait(&bar_act_ready[g], (epoch - 1) & 1)) continue;
+              }
+            }
+            ptx::tc_fence_after_sync();
+            const int ndim = ch.ndim8 * 8;
+            const uint32_t idesc = ptx::umma_idesc_bf16_f32(kTile, ndim);
+            const uint32_t a0 = act_addr + ch.kplane * kPlaneBytes + (group_origin_row(g) + ch.shift) * 16;
+            const uint32_t b0 = ring_addr + s * kStageBytes;
+            const uint32_t d = tmem_base + g * kF;
+            for (int ks = 0; ks < ch.nk; ++ks) {
+              const uint64_t da = ptx::umma_desc_kmajor_noswz(a0 + ks * 2 * kPlaneBytes, kPlaneBytes, 128);
+              const uint64_t db = ptx::umma_desc_kmajor_noswz(b0 + ks * 2 * ndim * 16, ndim * 16, 128);
+              ptx::umma_bf16_ss(d, da, db, idesc, ((ch.flags & kFirstOfLayer) && ks == 0) ? 0u : 1u);
+            }
+            ptx::umma_commit(&bar_empty[s]);
+            if (!has_b) ptx::umma_commit(&bar_empty[s]);
+            if ((ch.flags & kLastOfSlice) && ch.layer == 0 && ch.slice + 1 < prm.nslices)
+              ptx::umma_commit(&bar_in_empty[g]);
+            if (ch.flags & kLastOfLayer) {
+              ptx::umma_commit(&bar_tmem_full[g]);
+              if (ch.layer == nl - 1) ptx::umma_commit(&bar_in_empty[g]);
+            }
+            pos[g] = c + 1;
+            if (g == 0) break;  // group A has priority: it runs ahead, B fills the gaps
+          }
+        }
+      }
+    }
+  } else {
+    // ===== epilogue warps (0-3: group A, 4-7: group B) ========================================
+    const int g = warp >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;                       // TMEM lane == tile row
+    const int by = row / kW, bp = (row % kW) / 6, bx = row % 6;
+    const bool row_valid = row < kRowsValid && bx < 5;
+    const int sq = by * 5 + bx;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * kF;
+    uint8_t* act_row = s_act + (group_origin_row(g) + row) * 16;
+    uint32_t res[kF / 2];                                // block input of this row, packed bf16x2
+#pragma unroll
+    for (int i = 0; i < kF / 2; ++i) res[i] = 0u;
+    uint32_t round_seq = 0;
+
+    for (int r = blockIdx.x; r < prm.nrounds; r += gridDim.x, ++round_seq) {
+      const int pos_base = r * kPosPerRound + g * kPosPerGroup;
+      if (pos_base >= prm.n) continue;
+      const int pos = pos_base + bp;
+      const bool out_valid = row_valid && pos < prm.n;
+      for (int L = 0; L < nl; ++L) {
+        const uint32_t epoch = round_seq * nl + L;
+        const uint32_t lf = prm.layers[L].flags;
+        const float* bias = s_bias + L * kF;
+        ptx::mbar_wait(&bar_tmem_full[g], epoch & 1);
+        ptx::tc_fence_after_sync();
+
+        if (!(lf & kFinal)) {
+          float vacc = 0.f;
+          const bool dump = prm.dbg != nullptr && L == nl - 1;
+#pragma unroll
+          for (int cb = 0; cb < 4; ++cb) {
+            uint32_t v[32];
+            ptx::tmem_ld_32x32b_x32(taddr + cb * 32, v);
+            ptx::tmem_ld_wait();
+            uint32_t o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float a = __uint_as_float(v[2 * j]) + bias[cb * 32 + 2 * j];
+              float b = __uint_as_float(v[2 * j + 1]) + bias[cb * 32 + 2 * j + 1];
+              if (lf & kHasRes) {
+                a += bf16lo(res[cb * 16 + j]);
+                b += bf16hi(res[cb * 16 + j]);
+              }
+              if (lf & kRelu) {
+                a = fmaxf(a, 0.f);
+                b = fmaxf(b, 0.f);
+              }
+              o[j] = ptx::pack_bf16x2(a, b);
+              if (lf & kUpdRes) res[cb * 16 + j] = o[j];
+              if (lf & kValueTap)
+                vacc += s_wv[cb * 32 + 2 * j] * bf16lo(o[j]) + s_wv[cb * 32 + 2 * j + 1] * bf16hi(o[j]);
+            }
+            if (row_valid) {
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const uint4 pk = make_uint4(o[4 * j4], o[4 * j4 + 1], o[4 * j4 + 2], o[4 * j4 + 3]);
+                *reinterpret_cast<uint4*>(act_row + (cb * 4 + j4) * kPlaneBytes) = pk;
+                if (dump) prm.dbg[(static_cast<size_t>(r * 2 + g) * kPlanes + cb * 4 + j4) * kTile + row] = pk;
+              }
+            }
+          }
+          if ((lf & kValueTap) && row_valid) s_v[(g * kPosPerGroup + bp) * kSq + sq] = fmaxf(vacc + prm.value_b, 0.f);
+        } else {
+          // policy 1x1 output: fp32 logits straight to HBM, index c*25 + sq (Flatten of NCHW)
+          float* dst = prm.policy + static_cast<size_t>(pos) * (kPolicyCh * kSq) + sq;
+#pragma unroll
+          for (int cb = 0; cb < 3; ++cb) {
+            uint32_t v[32];
+            ptx::tmem_ld_32x32b_x32(taddr + cb * 32, v);
+            ptx::tmem_ld_wait();
+            if (out_valid) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int c = cb * 32 + j;
+                if (c < kPolicyCh) dst[c * kSq] = __uint_as_float(v[j]) + bias[c];
+              }
+            }
+          }
+        }
+        ptx::tc_fence_before_sync();
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bar_act_ready[g]);
+      }
+
+      if (nl == prm.nlayers) {
+        // value head tail: Dense(25->128)+ReLU, Dense(128->1)+tanh (network.py:115-120), 128 threads/group
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+        const int j = row;  // hidden unit
+        float h[kPosPerGroup];
+        const float b1 = prm.fc1_b[j];
+#pragma unroll
+        for (int p = 0; p < kPosPerGroup; ++p) h[p] = b1;
+        for (int s = 0; s < kSq; ++s) {
+          const float kk = prm.fc1_k[s * kF + j];
+#pragma unroll
+          for (int p = 0; p < kPosPerGroup; ++p) h[p] = fmaf(s_v[(g * kPosPerGroup + p) * kSq + s], kk, h[p]);
+        }
+        const float k2 = prm.fc2_k[j];
+#pragma unroll
+        for (int p = 0; p < kPosPerGroup; ++p) {
+          float part = fmaxf(h[p], 0.f) * k2;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+          if (lane == 0) s_part[(g * 4 + q) * kPosPerGroup + p] = part;
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+        if (row < kPosPerGroup && pos_base + row < prm.n) {
+          float t = prm.fc2_b;
+#pragma unroll
+          for (int w4 = 0; w4 < 4; ++w4) t += s_part[(g * 4 + w4) * kPosPerGroup + row];
+          prm.value[pos_base + row] = tanhf(t);
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+      }
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 9) ptx::tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+// =================================================================================================
+// host side
+// =================================================================================================
 struct HeadWeights {
   const float* policy_w; const float* policy_b;   // host, folded [cin][69], [69]
   const float* d_value_w; float value_b;          // device [filters]
   const float* d_fc1_k; const float* d_fc1_b; const float* d_fc2_k; float fc2_b;  // device
 };
 
-struct State { int blocks = 0, filters = 0, in_planes = 0, sms = 0; };
+struct State {
+  int blocks = 0, filters = 0, in_planes = 0, sms = 0;
+  int nlayers = 0, nslices = 0, in_planes8 = 0;
+  int nstages = 0, nchunks = 0;
+  size_t smem_bytes = 0;
+  uint8_t* d_wimg = nullptr;
+  Chunk* d_chunks = nullptr;
+  LayerInfo* d_layers = nullptr;
+  float* d_bias = nullptr;
+  std::vector<LayerInfo> layers;
+  HeadWeights heads{};
+  uint8_t* d_in_packed = nullptr;
+  uint4* d_dbg = nullptr;
+  int capacity = 0;
+  bool attr_set = false;
+};
 
-inline void init(State& s, int blocks, int filters, int in_planes, int sms) { s.blocks = blocks; s.filters = filters; s.in_planes = in_planes; s.sms = sms; }
-inline bool supported(const State&) { return false; }
-inline void free_weights(State&) {}
-inline void free_buffers(State&) {}
-inline cudaError_t alloc_buffers(State&, int) { return cudaSuccess; }
-inline cudaError_t set_weights(State&, const std::vector<std::vector<float>>&, const std::vector<std::vector<float>>&, const HeadWeights&) { return cudaSuccess; }
-inline cudaError_t forward(State&, const float*, int, float*, float*, cudaStream_t, int*, std::string* why) { *why = "tensor-core path not built"; return cudaSuccess; }
-inline cudaError_t export_trunk(State&, int, float*, cudaStream_t, int*, std::string* why) { *why = "tensor-core path not built"; return cudaSuccess; }
+inline void init(State& s, int blocks, int filters, int in_planes, int sms) {
+  s.blocks = blocks; s.filters = filters; s.in_planes = in_planes; s.sms = sms;
+  s.nlayers = 1 + 2 * blocks + 2;
+  s.in_planes8 = ((in_planes + 15) / 16) * 2;
+  s.nslices = (s.in_planes8 + kPlanes - 1) / kPlanes;
+}
+
+inline bool supported(const State& s) { return s.filters == kF && s.nlayers <= 255; }
+
+inline void free_weights(State& s) {
+  cudaFree(s.d_wimg); cudaFree(s.d_chunks); cudaFree(s.d_layers); cudaFree(s.d_bias);
+  s.d_wimg = nullptr; s.d_chunks = nullptr; s.d_layers = nullptr; s.d_bias = nullptr;
+  s.layers.clear();
+}
+
+inline void free_buffers(State& s) {
+  cudaFree(s.d_in_packed); cudaFree(s.d_dbg);
+  s.d_in_packed = nullptr; s.d_dbg = nullptr; s.capacity = 0;
+}
+
+inline cudaError_t alloc_buffers(State& s, int cap) {
+  if (!supported(s)) return cudaSuccess;
+  free_buffers(s);
+  const size_t groups = (static_cast<size_t>(cap) + kPosPerGroup - 1) / kPosPerGroup + 1;
+  cudaError_t e = cudaMalloc(&s.d_in_packed, groups * s.in_planes8 * kRowsValid * 16);
+  if (e != cudaSuccess) return e;
+  e = cudaMalloc(&s.d_dbg, groups * kPlanes * kTile * sizeof(uint4));
+  if (e != cudaSuccess) return e;
+  s.capacity = cap;
+  return cudaSuccess;
+}
+
+inline uint16_t f32_to_bf16_rne(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return static_cast<uint16_t>(u >> 16);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>(u >> 16);
+}
+
+// conv_w[i]: folded fp32 [9][cin][128] for the stem, tower convs and the policy conv (in that order);
+// heads.policy_w: folded [128][69].
+inline cudaError_t set_weights(State& s, const std::vector<std::vector<float>>& conv_w,
+                               const std::vector<std::vector<float>>& conv_b, const HeadWeights& heads) {
+  if (!supported(s)) return cudaSuccess;
+  free_weights(s);
+  s.heads = heads;
+  std::vector<Chunk> chunks;
+  std::vector<uint16_t> img;
+  std::vector<float> bias(static_cast<size_t>(s.nlayers) * kF, 0.f);
+  s.layers.assign(s.nlayers, LayerInfo{});
+
+  auto emit = [&](int layer, int slice, int tap, int ntaps, int k0_total, int kplane, int nk, int ndim, int cin,
+                  int cout, const float* w, uint32_t flags) {
+    Chunk ch{};
+    ch.gofs = static_cast<uint32_t>(img.size() * 2);
+    ch.bytes = static_cast<uint32_t>(nk * 2 * ndim * 16);
+    ch.shift = static_cast<int16_t>(ntaps == 9 ? (tap / 3 - 1) * kW + (tap % 3 - 1) : 0);
+    ch.nk = static_cast<uint8_t>(nk);
+    ch.kplane = static_cast<uint8_t>(kplane);
+    ch.flags = static_cast<uint8_t>(flags);
+    ch.layer = static_cast<uint8_t>(layer);
+    ch.slice = static_cast<uint8_t>(slice);
+    ch.ndim8 = static_cast<uint8_t>(ndim / 8);
+    // image: [plane j][n][8 channels]
+    for (int j = 0; j < nk * 2; ++j)
+      for (int n = 0; n < ndim; ++n)
+        for (int e = 0; e < 8; ++e) {
+          const int ci = k0_total + j * 8 + e;
+          const float v = (ci < cin && n < cout) ? w[(static_cast<size_t>(tap) * cin + ci) * cout + n] : 0.f;
+          img.push_back(f32_to_bf16_rne(v));
+        }
+    chunks.push_back(ch);
+  };
+
+  for (int L = 0; L < s.nlayers; ++L) {
+    LayerInfo& li = s.layers[L];
+    li.chunk_begin = static_cast<int>(chunks.size());
+    const bool is_final = L == s.nlayers - 1;
+    const bool is_stem = L == 0;
+    const bool is_policy_conv = L == s.nlayers - 2;
+    const int cin = is_stem ? s.in_planes : kF;
+    const int cout = is_final ? kPolicyCh : kF;
+    const int ndim = is_final ? kPolicyN : kF;
+    const int ntaps = is_final ? 1 : 9;
+    const float* w = is_final ? heads.policy_w : conv_w[L].data();
+    const float* b = is_final ? heads.policy_b : conv_b[L].data();
+    for (int o = 0; o < cout; ++o) bias[static_cast<size_t>(L) * kF + o] = b[o];
+    li.ndim = ndim;
+    li.flags = 0;
+    if (is_final) li.flags = kFinal;
+    else if (is_stem) li.flags = kRelu | kUpdRes;
+    else if (is_policy_conv) li.flags = kRelu;
+    else if ((L - 1) % 2 == 0) li.flags = kRelu;                // first conv of a block
+    else li.flags = kRelu | kHasRes | kUpdRes;                  // second conv: relu(y + x)
+    if (L == s.nlayers - 3) li.flags |= kValueTap;              // trunk output feeds the value head
+    const int planes_total = is_stem ? s.in_planes8 : kPlanes;  // 8-channel planes of the input
+    const int nslices = (planes_total + kPlanes - 1) / kPlanes;
+    for (int sl = 0; sl < nslices; ++sl) {
+      const int pl0 = sl * kPlanes;
+      const int npl = std::min(kPlanes, planes_total - pl0);
+      const int nchunks_tap = (npl + 7) / 8;
+      for (int tap = 0; tap < ntaps; ++tap)
+        for (int kb = 0; kb < nchunks_tap; ++kb) {
+          const int nk = std::min(4, (npl - kb * 8) / 2);
+          uint32_t fl = 0;
+          const bool first_in_slice = tap == 0 && kb == 0, last_in_slice = tap == ntaps - 1 && kb == nchunks_tap - 1;
+          if (first_in_slice) fl |= kFirstOfSlice;
+          if (last_in_slice) fl |= kLastOfSlice;
+          if (first_in_slice && sl == 0) fl |= kFirstOfLayer;
+          if (last_in_slice && sl == nslices - 1) fl |= kLastOfLayer;
+          emit(L, sl, tap, ntaps, (pl0 + kb * 8) * 8, kb * 8, nk, ndim, cin, cout, w, fl);
+        }
+    }
+    li.chunk_end = static_cast<int>(chunks.size());
+  }
+
+  cudaError_t e;
+  if ((e = cudaMalloc(&s.d_wimg, img.size() * 2)) != cudaSuccess) return e;
+  if ((e = cudaMemcpy(s.d_wimg, img.data(), img.size() * 2, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&s.d_chunks, chunks.size() * sizeof(Chunk))) != cudaSuccess) return e;
+  if ((e = cudaMemcpy(s.d_chunks, chunks.data(), chunks.size() * sizeof(Chunk), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&s.d_layers, s.layers.size() * sizeof(LayerInfo))) != cudaSuccess) return e;
+  if ((e = cudaMemcpy(s.d_layers, s.layers.data(), s.layers.size() * sizeof(LayerInfo), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&s.d_bias, bias.size() * 4)) != cudaSuccess) return e;
+  if ((e = cudaMemcpy(s.d_bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+
+  s.nchunks = static_cast<int>(chunks.size());
+  const size_t fixed = kActBytes + static_cast<size_t>(s.nlayers) * kF * 4 + kF * 4 + 2 * kPosPerGroup * kSq * 4 + 32 * 4 +
+                       chunks.size() * sizeof(Chunk) + (2 * kMaxStages + 8) * 8 + 16;
+  s.nstages = static_cast<int>(std::min<size_t>(kMaxStages, (232448 - std::min<size_t>(fixed, 232448)) / kStageBytes));
+  s.smem_bytes = fixed + static_cast<size_t>(s.nstages) * kStageBytes;
+  s.attr_set = false;
+  return cudaSuccess;
+}
+
+// nlayers_run < nlayers: stop after that many layers and leave the packed activations in d_dbg.
+inline cudaError_t run(State& s, const float* d_planes, int n, float* d_policy, float* d_value, int nlayers_run,
+                       cudaStream_t stream, int* launched, std::string* why) {
+  if (!supported(s)) { *why = "the tcgen05 path supports filters == 128 only"; return cudaSuccess; }
+  if (s.nstages < 3) { *why = "network too deep for the shared-memory layer tables"; return cudaSuccess; }
+  if (!s.attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(s.smem_bytes));
+    if (e != cudaSuccess) { *why = "cudaFuncSetAttribute"; return e; }
+    s.attr_set = true;
+  }
+  const int groups = (n + kPosPerGroup - 1) / kPosPerGroup;
+  const int rounds = (n + kPosPerRound - 1) / kPosPerRound;
+  pack_input_kernel<<<rounds * 2, 256, 0, stream>>>(d_planes, reinterpret_cast<uint4*>(s.d_in_packed), n, s.in_planes, s.in_planes8);
+  ++*launched;
+  (void)groups;
+  Params p{};
+  p.wimg = s.d_wimg; p.chunks = s.d_chunks; p.layers = s.d_layers; p.bias = s.d_bias;
+  p.value_w = s.heads.d_value_w; p.fc1_k = s.heads.d_fc1_k; p.fc1_b = s.heads.d_fc1_b; p.fc2_k = s.heads.d_fc2_k;
+  p.value_b = s.heads.value_b; p.fc2_b = s.heads.fc2_b;
+  p.in_packed = s.d_in_packed; p.in_planes8 = s.in_planes8; p.nslices = s.nslices;
+  p.nstages = s.nstages; p.nchunks_total = s.nchunks;
+  p.nlayers = s.nlayers; p.nlayers_run = nlayers_run; p.n = n; p.nrounds = rounds;
+  p.policy = d_policy; p.value = d_value;
+  p.dbg = nlayers_run < s.nlayers ? s.d_dbg : nullptr;
+  const int grid = std::min(rounds, s.sms);
+  tower_kernel<<<grid, kThreads, s.smem_bytes, stream>>>(p);
+  ++*launched;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) *why = "tower_kernel launch";
+  return e;
+}
+
+inline cudaError_t forward(State& s, const float* d_planes, int n, float* d_policy, float* d_value,
+                           cudaStream_t stream, int* launched, std::string* why) {
+  return run(s, d_planes, n, d_policy, d_value, s.nlayers, stream, launched, why);
+}
+
+// Activations after `nconv` 3x3 convolutions (1 = stem ... 1+2*blocks = trunk) as fp32 NCHW.
+inline cudaError_t debug_layers(State& s, const float* d_planes, int n, int nconv, float* d_out_nchw,
+                                cudaStream_t stream, int* launched, std::string* why) {
+  cudaError_t e = run(s, d_planes, n, nullptr, nullptr, nconv, stream, launched, why);
+  if (e != cudaSuccess || !why->empty()) return e;
+  unpack_debug_kernel<<<n, 128, 0, stream>>>(s.d_dbg, d_out_nchw, n);
+  ++*launched;
+  e = cudaGetLastError();
+  if (e != cudaSuccess) *why = "unpack_debug_kernel launch";
+  return e;
+}
 
 }  // namespace tc
 }  // namespace e55

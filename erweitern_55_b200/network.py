@@ -181,10 +181,13 @@ class Network:
         n = int(planes.shape[0])
         self._check(self._lib.e55_predict_device(self._ctx, planes.data_ptr(), n, policy.data_ptr(), value.data_ptr()))
 
-    def debug_trunk(self, images):
+    def debug_activations(self, images, n_convs=None):
+        """Activations after the first ``n_convs`` 3x3 convolutions (default: trunk output)."""
         x = self._as_batch(images)
+        if n_convs is None:
+            n_convs = 1 + 2 * self._blocks
         out = np.empty((x.shape[0], self._filters, 5, 5), dtype=np.float32)
-        self._check(self._lib.e55_debug_trunk(self._ctx, x.ctypes.data, x.shape[0], out.ctypes.data))
+        self._check(self._lib.e55_debug_activations(self._ctx, x.ctypes.data, x.shape[0], n_convs, out.ctypes.data))
         return out
 
     def sync(self):

@@ -91,9 +91,10 @@ int e55_stream(e55_ctx* ctx, void** stream_out);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 int e55_launch_count(const e55_ctx* ctx, int64_t* count_out);
 
-/* Debug/verification: run the forward pass on device planes and copy the trunk output (input of the
- * two heads, float32 [n,filters,5,5]) to the host. */
-int e55_debug_trunk(e55_ctx* ctx, const float* planes, int n, float* trunk_out);
+/* Debug/verification: activations after the first `n_convs` 3x3 convolutions of the tower
+ * (1 = stem ... 1+2*blocks = trunk output, the input of both heads) as float32 [n,filters,5,5] on the
+ * host, computed by the currently selected precision path. */
+int e55_debug_activations(e55_ctx* ctx, const float* planes, int n, int n_convs, float* act_out);
 
 /* Hardware self-test of the tcgen05 operand addressing this library depends on: one 128x128x64 bf16
  * UMMA from no-swizzle K-major shared-memory operands whose A descriptor start is displaced by
