@@ -534,6 +534,19 @@ int e55_debug_activations(e55_ctx* c, const float* planes, int n, int n_convs, f
   return E55_OK;
 }
 
+int e55_debug_profile(e55_ctx* c, int enable, uint64_t* counters_out) {
+  if (!c) return E55_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  E55_CUDA(c, cudaSetDevice(c->device));
+  E55_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (counters_out && c->tc.d_prof)
+    E55_CUDA(c, cudaMemcpy(counters_out, c->tc.d_prof, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  if (enable && !c->tc.d_prof) E55_CUDA(c, cudaMalloc(&c->tc.d_prof, 16 * sizeof(uint64_t)));
+  if (!enable && c->tc.d_prof) { cudaFree(c->tc.d_prof); c->tc.d_prof = nullptr; }
+  if (c->tc.d_prof) E55_CUDA(c, cudaMemset(c->tc.d_prof, 0, 16 * sizeof(uint64_t)));
+  return E55_OK;
+}
+
 int e55_selftest_umma(int device, int row_shift, float* max_abs_err_out) {
   using namespace e55::ummatest;
   if (!max_abs_err_out || row_shift < 0 || row_shift > 64) return fail(nullptr, E55_ERR_INVALID, "bad selftest arguments");

@@ -50,29 +50,31 @@ constexpr int kRowsTotal = kGuard + kTile + kGuard + kTile + kGuard;  // 331
 constexpr int kPlanes = kF / 8;        // 16
 constexpr int kPlaneBytes = kRowsTotal * 16;
 constexpr int kActBytes = kPlanes * kPlaneBytes;                       // 84,736
-constexpr int kMaxStages = 8;
-constexpr int kStageBytes = 16384;     // one (tap, 64-channel) chunk of a 128-wide layer
+constexpr int kMaxStages = 4;
+constexpr int kStageBytes = 32768;     // one tap of a 128-wide layer: 8 K-steps x 128 x 16 x 2 B
 constexpr int kPolicyCh = 69;
 constexpr int kPolicyN = 80;           // policy 1x1 output channels padded to a legal UMMA N
 constexpr int kSq = 25;
-constexpr int kThreads = 352;
+constexpr int kThreads = 384;
 constexpr int kTmemCols = 256;
+constexpr uint32_t kDescHi = 8u | (1u << 14);  // SBO = 128 B, descriptor version 1, no swizzle
 
 __host__ __device__ constexpr int group_origin_row(int g) { return kGuard + g * (kTile + kGuard); }
 
 enum : uint32_t { kFirstOfSlice = 1, kLastOfSlice = 2, kFirstOfLayer = 4, kLastOfLayer = 8 };
 enum : uint32_t { kRelu = 1, kHasRes = 2, kUpdRes = 4, kValueTap = 8, kFinal = 16 };
 
+// One ring stage worth of weights: all K-steps of one tap of one input slice.
 struct alignas(16) Chunk {
   uint32_t gofs;     // byte offset into the weight image
   uint32_t bytes;    // nk * 2 * ndim * 16
-  int16_t shift;     // row displacement of the tap
+  int16_t a_off;     // A-descriptor displacement in 16 B units: kplane * rows + tap row shift
   uint8_t nk;        // K=16 steps in this chunk
-  uint8_t kplane;    // first activation plane (within the 16 resident planes)
+  uint8_t ndim8;     // UMMA N / 8 of the layer
   uint8_t flags;
   uint8_t layer;
   uint8_t slice;
-  uint8_t ndim8;     // UMMA N / 8 of the layer
+  uint8_t pad;
 };
 
 struct LayerInfo {
@@ -103,6 +105,7 @@ struct Params {
   float* policy;             // [n][1725]
   float* value;              // [n]
   uint4* dbg;                // [rounds*2][16][128] packed activations after layer nlayers_run-1
+  unsigned long long* prof;  // optional [16] cycle counters of CTA 0 (kProf instantiation only)
 };
 
 // ---- input packing: fp32 NCHW planes -> bf16 wide-board planes ------------------------------------
@@ -156,6 +159,65 @@ struct SmemLayout {
   __host__ __device__ static constexpr int act(int nstages) { return ring + nstages * kStageBytes; }
 };
 
+// D[tmem] (+)= A * B^T with descriptors given as (lo, hi) words.
+__device__ __forceinline__ void umma_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(kDescHi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// Epilogue of one 128x128 accumulator tile for the thread that owns `row`:
+// TMEM -> +bias (+residual) -> ReLU -> bf16 -> shared memory (in place: the next layer's A operand).
+template <bool kRes, bool kUpd, bool kVal>
+__device__ __forceinline__ float epilogue_tile(uint32_t taddr, const float* __restrict__ bias, uint8_t* act_row,
+                                               uint32_t (&res)[kF / 2], const float* __restrict__ s_wv,
+                                               bool row_valid, uint4* dbg_row) {
+  float vacc = 0.f;
+#pragma unroll
+  for (int cb = 0; cb < 4; ++cb) {
+    uint32_t v[32];
+    ptx::tmem_ld_32x32b_x32(taddr + cb * 32, v);
+    ptx::tmem_ld_wait();
+    uint32_t o[16];
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+      const float4 bb = *reinterpret_cast<const float4*>(bias + cb * 32 + j4 * 4);
+      float a0 = __uint_as_float(v[4 * j4 + 0]) + bb.x;
+      float a1 = __uint_as_float(v[4 * j4 + 1]) + bb.y;
+      float a2 = __uint_as_float(v[4 * j4 + 2]) + bb.z;
+      float a3 = __uint_as_float(v[4 * j4 + 3]) + bb.w;
+      if (kRes) {
+        const uint32_t r0 = res[cb * 16 + 2 * j4], r1 = res[cb * 16 + 2 * j4 + 1];
+        a0 += bf16lo(r0); a1 += bf16hi(r0); a2 += bf16lo(r1); a3 += bf16hi(r1);
+      }
+      a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f);
+      const uint32_t p0 = ptx::pack_bf16x2(a0, a1), p1 = ptx::pack_bf16x2(a2, a3);
+      o[2 * j4] = p0; o[2 * j4 + 1] = p1;
+      if (kUpd) { res[cb * 16 + 2 * j4] = p0; res[cb * 16 + 2 * j4 + 1] = p1; }
+      if (kVal) {
+        const float4 wv = *reinterpret_cast<const float4*>(s_wv + cb * 32 + j4 * 4);
+        vacc += wv.x * bf16lo(p0) + wv.y * bf16hi(p0) + wv.z * bf16lo(p1) + wv.w * bf16hi(p1);
+      }
+    }
+    if (row_valid) {
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const uint4 pk = make_uint4(o[4 * j4], o[4 * j4 + 1], o[4 * j4 + 2], o[4 * j4 + 3]);
+        *reinterpret_cast<uint4*>(act_row + (cb * 4 + j4) * kPlaneBytes) = pk;
+        if (dbg_row) dbg_row[(cb * 4 + j4) * kTile] = pk;
+      }
+    }
+  }
+  return vacc;
+}
+
+template <bool kProf>
 __global__ void __launch_bounds__(kThreads, 1)
 tower_kernel(const Params prm) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -167,13 +229,13 @@ tower_kernel(const Params prm) {
   float* s_part = s_v + 2 * kPosPerGroup * kSq;  // [2 groups][4 warps][4 positions]
   Chunk* s_chunks = reinterpret_cast<Chunk*>(s_part + 32);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_chunks + prm.nchunks_total);
-  const uint32_t kStages = prm.nstages;
-  uint64_t* bar_full = bars;                    // [kStages]
-  uint64_t* bar_empty = bars + kStages;         // [kStages]
-  uint64_t* bar_tmem_full = bars + 2 * kStages;  // [2]
-  uint64_t* bar_act_ready = bar_tmem_full + 2;  // [2]
-  uint64_t* bar_in_full = bar_act_ready + 2;    // [2]
-  uint64_t* bar_in_empty = bar_in_full + 2;     // [2]
+  const uint32_t nstages = prm.nstages;
+  uint64_t* bar_full = bars;                     // [nstages]
+  uint64_t* bar_empty = bars + kMaxStages;       // [nstages]
+  uint64_t* bar_tmem_full = bars + 2 * kMaxStages;  // [2]
+  uint64_t* bar_act_ready = bar_tmem_full + 2;   // [2]
+  uint64_t* bar_in_full = bar_act_ready + 2;     // [2]
+  uint64_t* bar_in_empty = bar_in_full + 2;      // [2]
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_in_empty + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -188,7 +250,7 @@ tower_kernel(const Params prm) {
   for (int i = threadIdx.x; i < kF; i += kThreads) s_wv[i] = prm.value_w[i];
   for (int i = threadIdx.x; i < prm.nchunks_total; i += kThreads) s_chunks[i] = prm.chunks[i];
   if (threadIdx.x == 0) {
-    for (uint32_t s = 0; s < kStages; ++s) {
+    for (uint32_t s = 0; s < nstages; ++s) {
       ptx::mbar_init(&bar_full[s], 1);
       ptx::mbar_init(&bar_empty[s], 2);
     }
@@ -210,16 +272,21 @@ tower_kernel(const Params prm) {
   if (warp == 8) {
     // ===== weight producer ===================================================================
     if (lane == 0) {
-      uint32_t gc = 0;
+      uint32_t s = 0, ph = 1;
+      long long t_wait = 0;
       for (int r = blockIdx.x; r < prm.nrounds; r += gridDim.x) {
-        for (uint32_t c = 0; c < nchunks; ++c, ++gc) {
+        for (uint32_t c = 0; c < nchunks; ++c) {
           const Chunk ch = s_chunks[c];
-          const uint32_t s = gc % kStages;
-          ptx::mbar_wait(&bar_empty[s], ((gc / kStages) & 1) ^ 1);
+          long long t0 = 0;
+          if (kProf) t0 = clock64();
+          ptx::mbar_wait(&bar_empty[s], ph);
+          if (kProf) t_wait += clock64() - t0;
           ptx::mbar_arrive_expect_tx(&bar_full[s], ch.bytes);
           ptx::tma_bulk_g2s(s_ring + s * kStageBytes, prm.wimg + ch.gofs, ch.bytes, &bar_full[s]);
+          if (++s == nstages) { s = 0; ph ^= 1; }
         }
       }
+      if (kProf && blockIdx.x == 0) prm.prof[8] = t_wait;
     }
   } else if (warp == 10) {
     // ===== stem-input loader =================================================================
@@ -243,62 +310,72 @@ tower_kernel(const Params prm) {
         }
       }
     }
-  } else if (warp == 9) {
-    // ===== MMA issuer ========================================================================
-    if (lane == 0) {
-      const uint32_t act_addr = ptx::smem_u32(s_act);
-      const uint32_t ring_addr = ptx::smem_u32(s_ring);
-      uint32_t full_seen = 0, round_seq = 0;
-      for (int r = blockIdx.x; r < prm.nrounds; r += gridDim.x, ++round_seq) {
-        const bool has_b = r * kPosPerRound + kPosPerGroup < prm.n;
-        uint32_t pos[2] = {0u, has_b ? 0u : nchunks};
-        const uint32_t gbase = round_seq * nchunks;
-        while (pos[0] < nchunks || pos[1] < nchunks) {
+  } else if (warp == 9 || warp == 11) {
+    // ===== MMA issuers: warp 9 drives group A, warp 11 group B (warp-uniform loop, one elected lane
+    // issues).  Both walk the same chunk sequence; a ring stage is released after both used it. =====
+    const int g = warp == 9 ? 0 : 1;
+    const uint32_t a_lo_base = ((ptx::smem_u32(s_act) + group_origin_row(g) * 16) >> 4) |
+                               (static_cast<uint32_t>(kPlaneBytes >> 4) << 16);
+    const uint32_t b_lo_base = ptx::smem_u32(s_ring) >> 4;
+    const uint32_t d = tmem_base + g * kF;
+    uint32_t s = 0, ph = 0, round_seq = 0;
+    long long t_start = 0, t_issue = 0, t_full = 0, t_act = 0;
+    if (kProf) t_start = clock64();
+    for (int r = blockIdx.x; r < prm.nrounds; r += gridDim.x, ++round_seq) {
+      const bool has_b = r * kPosPerRound + kPosPerGroup < prm.n;
+      if (g == 1 && !has_b) break;  // only the last round can lack group B
+      for (uint32_t c = 0; c < nchunks; ++c) {
+        const Chunk ch = s_chunks[c];
+        long long t0 = 0, t1 = 0, t2 = 0;
+        if (kProf) t0 = clock64();
+        ptx::mbar_wait(&bar_full[s], ph);
+        if (kProf) t1 = clock64();
+        if (ch.flags & kFirstOfSlice) {
+          const uint32_t epoch = round_seq * nl + ch.layer;
+          if (ch.layer == 0) ptx::mbar_wait(&bar_in_full[g], (round_seq * prm.nslices + ch.slice) & 1);
+          if ((ch.flags & kFirstOfLayer) && epoch > 0) ptx::mbar_wait(&bar_act_ready[g], (epoch - 1) & 1);
+        }
+        if (kProf) t2 = clock64();
+        ptx::tc_fence_after_sync();
+        if (ptx::elect_one()) {
+          const uint32_t ndim = ch.ndim8 * 8u;
+          const uint32_t idesc = ptx::umma_idesc_bf16_f32(kTile, ndim);
+          uint32_t a_lo = a_lo_base + static_cast<int>(ch.a_off);
+          uint32_t b_lo = (b_lo_base + s * (kStageBytes >> 4)) | (ndim << 16);
+          uint32_t acc = (ch.flags & kFirstOfLayer) ? 0u : 1u;
+          if (ch.nk == 8) {
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            if (pos[g] >= nchunks) continue;
-            const uint32_t c = pos[g];
-            const Chunk ch = s_chunks[c];
-            const uint32_t gc = gbase + c;
-            const uint32_t s = gc % kStages;
-            if (gc >= full_seen) {
-              if (!ptx::mbar_test_wait(&bar_full[s], (gc / kStages) & 1)) continue;
-              full_seen = gc + 1;
+            for (int ks = 0; ks < 8; ++ks) {
+              umma_lohi(d, a_lo, b_lo, idesc, acc);
+              acc = 1u;
+              a_lo += 2 * (kPlaneBytes >> 4);
+              b_lo += 2 * ndim;
             }
-            if (ch.flags & kFirstOfSlice) {
-              const uint32_t epoch = round_seq * nl + ch.layer;
-              if (ch.layer == 0) {
-                const uint32_t k = round_seq * prm.nslices + ch.slice;
-                if (!ptx::mbar_test_wait(&bar_in_full[g], k & 1)) continue;
-              }
-              if ((ch.flags & kFirstOfLayer) && epoch > 0) {
-                if (!ptx::mbar_test_wait(&bar_act_ready[g], (epoch - 1) & 1)) continue;
-              }
-            }
-            ptx::tc_fence_after_sync();
-            const int ndim = ch.ndim8 * 8;
-            const uint32_t idesc = ptx::umma_idesc_bf16_f32(kTile, ndim);
-            const uint32_t a0 = act_addr + ch.kplane * kPlaneBytes + (group_origin_row(g) + ch.shift) * 16;
-            const uint32_t b0 = ring_addr + s * kStageBytes;
-            const uint32_t d = tmem_base + g * kF;
+          } else {
             for (int ks = 0; ks < ch.nk; ++ks) {
-              const uint64_t da = ptx::umma_desc_kmajor_noswz(a0 + ks * 2 * kPlaneBytes, kPlaneBytes, 128);
-              const uint64_t db = ptx::umma_desc_kmajor_noswz(b0 + ks * 2 * ndim * 16, ndim * 16, 128);
-              ptx::umma_bf16_ss(d, da, db, idesc, ((ch.flags & kFirstOfLayer) && ks == 0) ? 0u : 1u);
+              umma_lohi(d, a_lo, b_lo, idesc, acc);
+              acc = 1u;
+              a_lo += 2 * (kPlaneBytes >> 4);
+              b_lo += 2 * ndim;
             }
-            ptx::umma_commit(&bar_empty[s]);
-            if (!has_b) ptx::umma_commit(&bar_empty[s]);
-            if ((ch.flags & kLastOfSlice) && ch.layer == 0 && ch.slice + 1 < prm.nslices)
-              ptx::umma_commit(&bar_in_empty[g]);
-            if (ch.flags & kLastOfLayer) {
-              ptx::umma_commit(&bar_tmem_full[g]);
-              if (ch.layer == nl - 1) ptx::umma_commit(&bar_in_empty[g]);
-            }
-            pos[g] = c + 1;
-            if (g == 0) break;  // group A has priority: it runs ahead, B fills the gaps
+          }
+          ptx::umma_commit(&bar_empty[s]);
+          if (!has_b) ptx::umma_commit(&bar_empty[s]);
+          if ((ch.flags & kLastOfSlice) && ch.layer == 0 && ch.slice + 1 < prm.nslices)
+            ptx::umma_commit(&bar_in_empty[g]);
+          if (ch.flags & kLastOfLayer) {
+            ptx::umma_commit(&bar_tmem_full[g]);
+            if (ch.layer == nl - 1) ptx::umma_commit(&bar_in_empty[g]);
           }
         }
+        __syncwarp();
+        if (++s == nstages) { s = 0; ph ^= 1; }
+        if (kProf) { t_full += t1 - t0; t_act += t2 - t1; t_issue += clock64() - t2; }
       }
+    }
+    if (kProf && blockIdx.x == 0 && lane == 0) {
+      unsigned long long* o = prm.prof + (g ? 4 : 0);
+      o[0] = clock64() - t_start; o[1] = t_issue; o[2] = t_full; o[3] = t_act;
     }
   } else {
     // ===== epilogue warps (0-3: group A, 4-7: group B) ========================================
@@ -314,6 +391,7 @@ tower_kernel(const Params prm) {
 #pragma unroll
     for (int i = 0; i < kF / 2; ++i) res[i] = 0u;
     uint32_t round_seq = 0;
+    long long t_wait = 0, t_work = 0;
 
     for (int r = blockIdx.x; r < prm.nrounds; r += gridDim.x, ++round_seq) {
       const int pos_base = r * kPosPerRound + g * kPosPerGroup;
@@ -324,45 +402,27 @@ tower_kernel(const Params prm) {
         const uint32_t epoch = round_seq * nl + L;
         const uint32_t lf = prm.layers[L].flags;
         const float* bias = s_bias + L * kF;
+        long long te0 = 0, te1 = 0;
+        if (kProf) te0 = clock64();
         ptx::mbar_wait(&bar_tmem_full[g], epoch & 1);
         ptx::tc_fence_after_sync();
+        if (kProf) te1 = clock64();
 
         if (!(lf & kFinal)) {
-          float vacc = 0.f;
-          const bool dump = prm.dbg != nullptr && L == nl - 1;
-#pragma unroll
-          for (int cb = 0; cb < 4; ++cb) {
-            uint32_t v[32];
-            ptx::tmem_ld_32x32b_x32(taddr + cb * 32, v);
-            ptx::tmem_ld_wait();
-            uint32_t o[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float a = __uint_as_float(v[2 * j]) + bias[cb * 32 + 2 * j];
-              float b = __uint_as_float(v[2 * j + 1]) + bias[cb * 32 + 2 * j + 1];
-              if (lf & kHasRes) {
-                a += bf16lo(res[cb * 16 + j]);
-                b += bf16hi(res[cb * 16 + j]);
-              }
-              if (lf & kRelu) {
-                a = fmaxf(a, 0.f);
-                b = fmaxf(b, 0.f);
-              }
-              o[j] = ptx::pack_bf16x2(a, b);
-              if (lf & kUpdRes) res[cb * 16 + j] = o[j];
-              if (lf & kValueTap)
-                vacc += s_wv[cb * 32 + 2 * j] * bf16lo(o[j]) + s_wv[cb * 32 + 2 * j + 1] * bf16hi(o[j]);
-            }
-            if (row_valid) {
-#pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4) {
-                const uint4 pk = make_uint4(o[4 * j4], o[4 * j4 + 1], o[4 * j4 + 2], o[4 * j4 + 3]);
-                *reinterpret_cast<uint4*>(act_row + (cb * 4 + j4) * kPlaneBytes) = pk;
-                if (dump) prm.dbg[(static_cast<size_t>(r * 2 + g) * kPlanes + cb * 4 + j4) * kTile + row] = pk;
-              }
-            }
+          uint4* dbg_row = (prm.dbg != nullptr && L == nl - 1)
+                               ? prm.dbg + static_cast<size_t>(r * 2 + g) * kPlanes * kTile + row : nullptr;
+          if (lf & kValueTap) {
+            float vacc;
+            if (lf & kHasRes) vacc = epilogue_tile<true, true, true>(taddr, bias, act_row, res, s_wv, row_valid, dbg_row);
+            else vacc = epilogue_tile<false, true, true>(taddr, bias, act_row, res, s_wv, row_valid, dbg_row);
+            if (row_valid) s_v[(g * kPosPerGroup + bp) * kSq + sq] = fmaxf(vacc + prm.value_b, 0.f);
+          } else if (lf & kHasRes) {
+            epilogue_tile<true, true, false>(taddr, bias, act_row, res, s_wv, row_valid, dbg_row);
+          } else if (lf & kUpdRes) {
+            epilogue_tile<false, true, false>(taddr, bias, act_row, res, s_wv, row_valid, dbg_row);
+          } else {
+            epilogue_tile<false, false, false>(taddr, bias, act_row, res, s_wv, row_valid, dbg_row);
           }
-          if ((lf & kValueTap) && row_valid) s_v[(g * kPosPerGroup + bp) * kSq + sq] = fmaxf(vacc + prm.value_b, 0.f);
         } else {
           // policy 1x1 output: fp32 logits straight to HBM, index c*25 + sq (Flatten of NCHW)
           float* dst = prm.policy + static_cast<size_t>(pos) * (kPolicyCh * kSq) + sq;
@@ -384,6 +444,7 @@ tower_kernel(const Params prm) {
         ptx::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&bar_act_ready[g]);
+        if (kProf) { t_wait += te1 - te0; t_work += clock64() - te1; }
       }
 
       if (nl == prm.nlayers) {
@@ -417,6 +478,10 @@ tower_kernel(const Params prm) {
         asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
       }
     }
+    if (kProf && blockIdx.x == 0 && (threadIdx.x & 127) == 0) {
+      prm.prof[10 + 2 * g] = t_wait;
+      prm.prof[11 + 2 * g] = t_work;
+    }
   }
 
   ptx::tc_fence_before_sync();
@@ -446,6 +511,7 @@ struct State {
   HeadWeights heads{};
   uint8_t* d_in_packed = nullptr;
   uint4* d_dbg = nullptr;
+  unsigned long long* d_prof = nullptr;  // set by e55_debug_profile
   int capacity = 0;
   bool attr_set = false;
 };
@@ -502,18 +568,17 @@ inline cudaError_t set_weights(State& s, const std::vector<std::vector<float>>& 
   std::vector<float> bias(static_cast<size_t>(s.nlayers) * kF, 0.f);
   s.layers.assign(s.nlayers, LayerInfo{});
 
-  auto emit = [&](int layer, int slice, int tap, int ntaps, int k0_total, int kplane, int nk, int ndim, int cin,
-                  int cout, const float* w, uint32_t flags) {
+  auto emit = [&](int layer, int slice, int tap, int ntaps, int k0_total, int nk, int ndim, int cin, int cout,
+                  const float* w, uint32_t flags) {
     Chunk ch{};
     ch.gofs = static_cast<uint32_t>(img.size() * 2);
     ch.bytes = static_cast<uint32_t>(nk * 2 * ndim * 16);
-    ch.shift = static_cast<int16_t>(ntaps == 9 ? (tap / 3 - 1) * kW + (tap % 3 - 1) : 0);
+    ch.a_off = static_cast<int16_t>(ntaps == 9 ? (tap / 3 - 1) * kW + (tap % 3 - 1) : 0);
     ch.nk = static_cast<uint8_t>(nk);
-    ch.kplane = static_cast<uint8_t>(kplane);
+    ch.ndim8 = static_cast<uint8_t>(ndim / 8);
     ch.flags = static_cast<uint8_t>(flags);
     ch.layer = static_cast<uint8_t>(layer);
     ch.slice = static_cast<uint8_t>(slice);
-    ch.ndim8 = static_cast<uint8_t>(ndim / 8);
     // image: [plane j][n][8 channels]
     for (int j = 0; j < nk * 2; ++j)
       for (int n = 0; n < ndim; ++n)
@@ -551,18 +616,14 @@ inline cudaError_t set_weights(State& s, const std::vector<std::vector<float>>& 
     for (int sl = 0; sl < nslices; ++sl) {
       const int pl0 = sl * kPlanes;
       const int npl = std::min(kPlanes, planes_total - pl0);
-      const int nchunks_tap = (npl + 7) / 8;
-      for (int tap = 0; tap < ntaps; ++tap)
-        for (int kb = 0; kb < nchunks_tap; ++kb) {
-          const int nk = std::min(4, (npl - kb * 8) / 2);
-          uint32_t fl = 0;
-          const bool first_in_slice = tap == 0 && kb == 0, last_in_slice = tap == ntaps - 1 && kb == nchunks_tap - 1;
-          if (first_in_slice) fl |= kFirstOfSlice;
-          if (last_in_slice) fl |= kLastOfSlice;
-          if (first_in_slice && sl == 0) fl |= kFirstOfLayer;
-          if (last_in_slice && sl == nslices - 1) fl |= kLastOfLayer;
-          emit(L, sl, tap, ntaps, (pl0 + kb * 8) * 8, kb * 8, nk, ndim, cin, cout, w, fl);
-        }
+      for (int tap = 0; tap < ntaps; ++tap) {
+        uint32_t fl = 0;
+        if (tap == 0) fl |= kFirstOfSlice;
+        if (tap == ntaps - 1) fl |= kLastOfSlice;
+        if (tap == 0 && sl == 0) fl |= kFirstOfLayer;
+        if (tap == ntaps - 1 && sl == nslices - 1) fl |= kLastOfLayer;
+        emit(L, sl, tap, ntaps, pl0 * 8, npl / 2, ndim, cin, cout, w, fl);
+      }
     }
     li.chunk_end = static_cast<int>(chunks.size());
   }
@@ -590,9 +651,10 @@ inline cudaError_t set_weights(State& s, const std::vector<std::vector<float>>& 
 inline cudaError_t run(State& s, const float* d_planes, int n, float* d_policy, float* d_value, int nlayers_run,
                        cudaStream_t stream, int* launched, std::string* why) {
   if (!supported(s)) { *why = "the tcgen05 path supports filters == 128 only"; return cudaSuccess; }
-  if (s.nstages < 3) { *why = "network too deep for the shared-memory layer tables"; return cudaSuccess; }
+  if (s.nstages < 2) { *why = "network too deep for the shared-memory layer tables"; return cudaSuccess; }
   if (!s.attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(s.smem_bytes));
+    cudaError_t e = cudaFuncSetAttribute(tower_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(s.smem_bytes));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tower_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(s.smem_bytes));
     if (e != cudaSuccess) { *why = "cudaFuncSetAttribute"; return e; }
     s.attr_set = true;
   }
@@ -610,8 +672,10 @@ inline cudaError_t run(State& s, const float* d_planes, int n, float* d_policy, 
   p.nlayers = s.nlayers; p.nlayers_run = nlayers_run; p.n = n; p.nrounds = rounds;
   p.policy = d_policy; p.value = d_value;
   p.dbg = nlayers_run < s.nlayers ? s.d_dbg : nullptr;
+  p.prof = s.d_prof;
   const int grid = std::min(rounds, s.sms);
-  tower_kernel<<<grid, kThreads, s.smem_bytes, stream>>>(p);
+  if (p.prof) tower_kernel<true><<<grid, kThreads, s.smem_bytes, stream>>>(p);
+  else tower_kernel<false><<<grid, kThreads, s.smem_bytes, stream>>>(p);
   ++*launched;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) *why = "tower_kernel launch";

@@ -96,6 +96,12 @@ int e55_launch_count(const e55_ctx* ctx, int64_t* count_out);
  * host, computed by the currently selected precision path. */
 int e55_debug_activations(e55_ctx* ctx, const float* planes, int n, int n_convs, float* act_out);
 
+/* Debug/profiling: switch the tower kernel's in-kernel cycle counters (CTA 0 only) on or off; when
+ * counters_out is non-NULL the 16 counters accumulated so far are copied out first, then reset.
+ * [0..3] group-A MMA issuer: total, issue, wait-for-weights, wait-for-activations cycles; [4..7] the
+ * same for group B; [8] weight producer wait; [10],[11] group-A epilogue wait / work; [12],[13] group B. */
+int e55_debug_profile(e55_ctx* ctx, int enable, uint64_t* counters_out);
+
 /* Hardware self-test of the tcgen05 operand addressing this library depends on: one 128x128x64 bf16
  * UMMA from no-swizzle K-major shared-memory operands whose A descriptor start is displaced by
  * `row_shift` rows (16-byte granularity), compared with a CPU product.  max_abs_err_out receives the

@@ -1,0 +1,24 @@
+"""In-kernel cycle counters of the tower kernel (CTA 0) for one forward of n positions."""
+import ctypes as C
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+from erweitern_55_b200 import synth, weights as W
+from erweitern_55_b200.network import Network
+
+w = W.init_weights()
+net = Network(precision="bf16", weights=w)
+for n in [int(a) for a in sys.argv[1:]] or [8, 256, 1024]:
+    x = torch.from_numpy(synth.synthetic_planes(n, seed=5)).cuda()
+    pd = torch.empty((n, 1725), device="cuda"); vd = torch.empty((n, 1), device="cuda")
+    net.predict_device(x, pd, vd); net.sync()
+    net._check(net._lib.e55_debug_profile(net._ctx, 1, None))
+    net.predict_device(x, pd, vd); net.sync()
+    out = (C.c_uint64 * 16)()
+    net._check(net._lib.e55_debug_profile(net._ctx, 0, out))
+    c = list(out)
+    print(f"n={n}: issuerA total={c[0]} issue={c[1]} wait_full={c[2]} wait_act={c[3]} | issuerB total={c[4]} issue={c[5]} "
+          f"wait_full={c[6]} wait_act={c[7]} | producer wait={c[8]} | epiA wait={c[10]} work={c[11]} | epiB wait={c[12]} work={c[13]}", flush=True)
