@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""Benchmark of the accelerated path: batched policy/value network evaluation (BASELINE.json metric
+"policy+value evals/sec (batch 1024)").
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--batch 1024] [--precision bf16]
+
+A step = one forward pass of the default 7x128 ResNet (network.py:75-146) over one batch of 1024
+synthetic positions with random-init weights (configs[1] of BASELINE.json).  Multi-GPU runs are launched
+with torchrun: one process per GPU, each evaluating its own batches (independent positions shard with no
+data-path collective -> weak scaling); NCCL is used only for the barrier and the max/sum of the results.
+
+The JSON line carries: `value` (device-resident inputs, CUDA-event time on the launching stream, max over
+ranks), `e2e` (same metric through the reference-facing host-buffer call e55_predict / Network.predict with
+pinned host inputs: H2D + kernels + D2H inside the timed region), `roofline` (dominant kernel vs the
+measured bf16 peak), `cpu_baseline` (the CPU oracle port on the box's host cores, bounded sample).
+`--impl reference` times the reference's CPU path stand-in (the oracle port; TensorFlow 1.15 cannot run
+here) with all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_POSITION = 126_368_256          # dense-convention FLOPs of the default net
+METRIC = "policy+value evals/sec (batch 1024)"
+UNIT = "evals/s"
+L2_BYTES = 126 * 1024 * 1024
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["bf16_tflops_sustained"]), "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
+    except Exception:
+        return 1590.0, "fallback 1.59 PFLOP/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons for one GPU while the timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for nme, val in zip(names, r[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        busy = [s for s in sm if s > 0.5 * max(sm)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def host_info():
+    model = "unknown"
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    return os.cpu_count() or 1, model
+
+
+def cpu_oracle_rate(batch, seconds, weights):
+    """evals/s of the CPU oracle port (torch fp32, all host threads) on repeated batches for ~`seconds`."""
+    import torch
+    from oracle import network_oracle as O
+    from erweitern_55_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    prep = O.prepare_torch(weights)
+    x = torch.from_numpy(synth.synthetic_planes(batch, seed=1000))
+    O.forward_prepared(prep, x)                       # warm-up
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        O.forward_prepared(prep, x)
+        reps += 1
+        dt = time.perf_counter() - t0
+        if dt >= seconds or reps >= 200:
+            break
+    return batch * reps / dt, cores, reps, dt
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's own CPU forward is TF 1.15 (absent); its stand-in is the oracle port."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import network_oracle as O
+    from erweitern_55_b200 import synth, weights as W
+    cores, model = host_info()
+    torch.set_num_threads(cores)
+    w = W.init_weights(seed=55)
+    prep = O.prepare_torch(w)
+    x = torch.from_numpy(synth.synthetic_planes(args.batch, seed=1000))
+    for _ in range(max(1, min(args.warmup, 2))):
+        O.forward_prepared(prep, x)
+    steps = min(args.steps, 40)                       # bounded: ~0.2-0.4 s per 1024-position step
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.forward_prepared(prep, x)
+    dt = time.perf_counter() - t0
+    val = args.batch * steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"default 7x128 ResNet forward, batch {args.batch}, random-init weights (configs[1])",
+                   "batch": args.batch, "host_cpu": model},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{steps} forward passes of batch {args.batch} (torch-CPU fp32 restatement of network.py; "
+                                   "TensorFlow 1.15 is not installable here)"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 50)")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from erweitern_55_b200 import sharding, synth, weights as W
+    from erweitern_55_b200.network import Network
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = args.batch
+    w = W.init_weights(seed=55)
+    net = Network(device=local_rank, precision=args.precision, weights=w, max_batch=B)
+    stream = torch.cuda.ExternalStream(net.cuda_stream(), device=dev)
+
+    # distinct input batches whose total size exceeds L2, used round-robin: every step reads HBM
+    in_bytes = B * 266 * 25 * 4
+    n_pool = max(2, -(-int(1.7 * L2_BYTES) // in_bytes))
+    pool = [torch.from_numpy(synth.synthetic_planes(B, seed=1000 + 16 * rank + i)).to(dev) for i in range(min(n_pool, 4))]
+    while len(pool) < n_pool:                          # cheap variety: roll the first batches along the batch axis
+        pool.append(torch.roll(pool[len(pool) % 4], shifts=len(pool), dims=0).contiguous())
+    policy = torch.empty((B, 1725), dtype=torch.float32, device=dev)
+    value = torch.empty((B, 1), dtype=torch.float32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident throughput ("value") ---------------------------------------------------
+    for i in range(args.warmup):
+        net.predict_device(pool[i % n_pool], policy, value)
+    net.sync()
+    barrier()
+    launches0 = net.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        t_wall0 = time.perf_counter()
+        e0.record(stream)
+        for i in range(args.steps):
+            net.predict_device(pool[i % n_pool], policy, value)
+        e1.record(stream)
+        net.sync()
+        t_wall = time.perf_counter() - t_wall0
+        launches = net.launch_count() - launches0
+        # a very short timed region ends before nvidia-smi's first sample: keep the same load running
+        # (untimed) until the sampler has seen it
+        if t_wall < 0.5:
+            t_end = time.perf_counter() + 0.5
+            while time.perf_counter() < t_end:
+                for i in range(16):
+                    net.predict_device(pool[i % n_pool], policy, value)
+                net.sync()
+    barrier()
+    dev_s = e0.elapsed_time(e1) * 1e-3
+    total_units, max_s = sharding.aggregate(B * args.steps, dev_s, device=dev)
+    value_rate = total_units / max_s
+
+    # ---- dominant kernel vs roofline (rank 0, CUDA events around the tower kernel) ----------------
+    roofline = None
+    if rank == 0 and args.precision == "bf16":
+        net.set_kernel_timing(True)
+        for i in range(min(args.steps, 100)):
+            net.predict_device(pool[i % n_pool], policy, value)
+        net.sync()
+        k_ms, k_n = net.kernel_timing()
+        net.set_kernel_timing(False)
+        peak, peak_src = measured_peaks()
+        achieved = B * FLOP_PER_POSITION / (k_ms / k_n * 1e-3) / 1e12
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "tower_kernel_dram_bytes.json")) as f:
+                traffic = json.load(f).get(f"batch_{B}")
+        except Exception:
+            pass
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "traffic": traffic, "kernel": "e55::tc::tower_kernel", "kernel_us": k_ms / k_n * 1e3,
+                    "flop_per_launch": B * FLOP_PER_POSITION, "peak_source": peak_src}
+
+    # ---- end-to-end through the host-buffer call (reference-facing Network.predict path) ----------
+    e2e_steps = args.e2e_steps or min(args.steps, 50)
+    host_pool = [torch.from_numpy(synth.synthetic_planes(B, seed=3000 + 16 * rank + i)).pin_memory() for i in range(3)]
+    host_policy = torch.empty((B, 1725), dtype=torch.float32).pin_memory()
+    host_value = torch.empty((B, 1), dtype=torch.float32).pin_memory()
+    lib, ctx = net._lib, net._ctx
+
+    def host_step(i):
+        net._check(lib.e55_predict(ctx, host_pool[i % 3].data_ptr(), B, host_policy.data_ptr(), host_value.data_ptr()))
+
+    for i in range(3):
+        host_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        host_step(i)
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    e2e_units, e2e_max = sharding.aggregate(B * e2e_steps, e2e_s, device=dev)
+    e2e = {"value": e2e_units / e2e_max, "unit": UNIT, "h2d_bytes_per_step": in_bytes,
+           "d2h_bytes_per_step": B * 1725 * 4 + B * 4, "steps": e2e_steps,
+           "timing": "host wall clock around blocking e55_predict calls (pinned host buffers), max over ranks"}
+
+    # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1:
+        rate, cores, reps, dt = cpu_oracle_rate(B, args.cpu_seconds, w)
+        cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{reps} forward passes of batch {B} in {dt:.1f} s (torch-CPU fp32 oracle port of network.py)"}
+
+    if rank == 0:
+        ncpu, model = host_info()
+        line = {
+            "metric": METRIC, "value": value_rate, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": max_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": f"default 7x128 ResNet forward (stem + 7 residual blocks + policy/value heads), batch {B} "
+                                   "per GPU, random-init weights (BASELINE.json configs[1])",
+                       "batch_per_gpu": B, "parallelism": f"replicas x{world} (independent positions, no collective)",
+                       "l2": f"inputs rotate over {n_pool} distinct device batches = {n_pool * in_bytes >> 20} MiB > 126 MiB L2",
+                       "flop_per_position": FLOP_PER_POSITION, "host_cpu": model, "host_cores": ncpu},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "wall_s": t_wall,
+        }
+        print(json.dumps(line), flush=True)
+    net.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

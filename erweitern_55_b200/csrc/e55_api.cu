@@ -56,6 +56,13 @@ struct e55_ctx {
   // tensor-core path state
   e55::tc::State tc;
 
+  // optional CUDA-event timing of the dominant kernel (e55_set_kernel_timing)
+  bool timing = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double timed_ms = 0.0;
+  int64_t timed_launches = 0;
+  bool ev_pending = false;
+
   // device work buffers (sized for `capacity` positions)
   float* d_in = nullptr;
   float* d_act[3] = {nullptr, nullptr, nullptr};
@@ -241,10 +248,31 @@ int forward_fp32(e55_ctx* c, const float* d_planes, int n, float* d_policy, floa
   return E55_OK;
 }
 
+// Folds the previous launch's event pair into the running total (events are reused, so this blocks
+// until that launch has finished; timing mode is for measurement runs only).
+int collect_timing(e55_ctx* c) {
+  if (!c->ev_pending) return E55_OK;
+  float ms = 0.f;
+  E55_CUDA(c, cudaEventSynchronize(c->ev1));
+  E55_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  c->timed_ms += ms;
+  ++c->timed_launches;
+  c->ev_pending = false;
+  return E55_OK;
+}
+
 int forward(e55_ctx* c, const float* d_planes, int n, float* d_policy, float* d_value) {
   if (c->precision == E55_PRECISION_FP32) return forward_fp32(c, d_planes, n, d_policy, d_value, nullptr);
   std::string why;
   int launched = 0;
+  if (c->timing) {
+    int rc = collect_timing(c);
+    if (rc) return rc;
+    c->tc.ev0 = c->ev0; c->tc.ev1 = c->ev1;
+    c->ev_pending = true;
+  } else {
+    c->tc.ev0 = c->tc.ev1 = nullptr;
+  }
   cudaError_t e = e55::tc::forward(c->tc, d_planes, n, d_policy, d_value, c->stream, &launched, &why);
   c->launches += launched;
   if (e != cudaSuccess) return fail(c, E55_ERR_CUDA, "tensor-core forward: " + why + ": " + cudaGetErrorString(e));
@@ -304,6 +332,8 @@ void e55_destroy(e55_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   free_weights(c);
   free_buffers(c);
+  if (c->ev0) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); }
+  if (c->tc.d_prof) cudaFree(c->tc.d_prof);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -531,6 +561,31 @@ int e55_debug_activations(e55_ctx* c, const float* planes, int n, int n_convs, f
   E55_CUDA(c, cudaMemcpyAsync(act_out, result, static_cast<size_t>(n) * c->filters * kSq * sizeof(float),
                               cudaMemcpyDeviceToHost, c->stream));
   E55_CUDA(c, cudaStreamSynchronize(c->stream));
+  return E55_OK;
+}
+
+int e55_set_kernel_timing(e55_ctx* c, int enable) {
+  if (!c) return E55_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  E55_CUDA(c, cudaSetDevice(c->device));
+  E55_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (enable && !c->ev0) {
+    E55_CUDA(c, cudaEventCreate(&c->ev0));
+    E55_CUDA(c, cudaEventCreate(&c->ev1));
+  }
+  c->timing = enable != 0;
+  c->timed_ms = 0.0; c->timed_launches = 0; c->ev_pending = false;
+  return E55_OK;
+}
+
+int e55_get_kernel_timing(e55_ctx* c, double* total_ms_out, int64_t* launches_out) {
+  if (!c || !total_ms_out || !launches_out) return E55_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  E55_CUDA(c, cudaSetDevice(c->device));
+  int rc = collect_timing(c);
+  if (rc) return rc;
+  *total_ms_out = c->timed_ms;
+  *launches_out = c->timed_launches;
   return E55_OK;
 }
 

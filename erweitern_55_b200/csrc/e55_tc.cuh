@@ -512,6 +512,7 @@ struct State {
   uint8_t* d_in_packed = nullptr;
   uint4* d_dbg = nullptr;
   unsigned long long* d_prof = nullptr;  // set by e55_debug_profile
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // when set, recorded around the tower kernel launch
   int capacity = 0;
   bool attr_set = false;
 };
@@ -674,8 +675,10 @@ inline cudaError_t run(State& s, const float* d_planes, int n, float* d_policy, 
   p.dbg = nlayers_run < s.nlayers ? s.d_dbg : nullptr;
   p.prof = s.d_prof;
   const int grid = std::min(rounds, s.sms);
+  if (s.ev0) cudaEventRecord(s.ev0, stream);
   if (p.prof) tower_kernel<true><<<grid, kThreads, s.smem_bytes, stream>>>(p);
   else tower_kernel<false><<<grid, kThreads, s.smem_bytes, stream>>>(p);
+  if (s.ev1) cudaEventRecord(s.ev1, stream);
   ++*launched;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) *why = "tower_kernel launch";

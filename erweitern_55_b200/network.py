@@ -198,6 +198,15 @@ class Network:
         self._check(self._lib.e55_stream(self._ctx, C.byref(s)))
         return int(s.value or 0)
 
+    def set_kernel_timing(self, enable: bool):
+        self._check(self._lib.e55_set_kernel_timing(self._ctx, 1 if enable else 0))
+
+    def kernel_timing(self):
+        """(total device ms of the dominant kernel, launches) since set_kernel_timing(True)."""
+        ms, n = C.c_double(), C.c_int64()
+        self._check(self._lib.e55_get_kernel_timing(self._ctx, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
     def launch_count(self) -> int:
         n = C.c_int64()
         self._check(self._lib.e55_launch_count(self._ctx, C.byref(n)))

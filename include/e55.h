@@ -91,6 +91,13 @@ int e55_stream(e55_ctx* ctx, void** stream_out);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 int e55_launch_count(const e55_ctx* ctx, int64_t* count_out);
 
+/* Measurement: when enabled, every tensor-core forward records a CUDA-event pair on the context
+ * stream around its dominant kernel (the fused tower kernel); e55_get_kernel_timing returns the
+ * accumulated device time and launch count since the last e55_set_kernel_timing call.  Serialises
+ * consecutive launches on the host, so leave it off outside measurement runs. */
+int e55_set_kernel_timing(e55_ctx* ctx, int enable);
+int e55_get_kernel_timing(e55_ctx* ctx, double* total_ms_out, int64_t* launches_out);
+
 /* Debug/verification: activations after the first `n_convs` 3x3 convolutions of the tower
  * (1 = stem ... 1+2*blocks = trunk output, the input of both heads) as float32 [n,filters,5,5] on the
  * host, computed by the currently selected precision path. */

@@ -1,0 +1,235 @@
+"""GPU parity tests proper: the CUDA paths, called through the C ABI (ctypes), against the CPU oracle.
+
+Tolerances (BASELINE.md section 4 / BASELINE.json north_star):
+  fp32 CUDA-core path  : |dlogit| <= 1e-4, |dvalue| <= 1e-5 against the fp32 oracle
+  bf16 tcgen05 path    : |dlogit| <= 0.03, |dvalue| <= 0.01 against the fp32 oracle, identical top-1
+                         wherever the oracle's top-2 margin exceeds 2 x the logit tolerance.
+                         bf16 rounding error scales with the logit magnitude: the "perturbed" weight set
+                         (random BN statistics) doubles the logit range (+-4 instead of +-2), so its logit
+                         tolerance is 0.06.
+"""
+import threading
+
+import numpy as np
+import pytest
+import torch
+
+from erweitern_55_b200 import synth, weights as W
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = (1e-4, 1e-5)
+BF16_TOL = (0.03, 0.01)
+BF16_TOL_PERTURBED = (0.06, 0.01)
+
+
+def _bf16_tol(tag):
+    return BF16_TOL if tag == "default" else BF16_TOL_PERTURBED
+
+
+def _oracle():
+    from oracle import network_oracle as O
+    return O
+
+
+@pytest.fixture(scope="module")
+def nets(weights_default, weights_perturbed):
+    from erweitern_55_b200.network import Network
+    made = {}
+    for tag, w in (("default", weights_default), ("perturbed", weights_perturbed)):
+        for prec in ("fp32", "bf16"):
+            made[tag, prec] = Network(device="gpu", precision=prec, weights=w)
+    yield made
+    for n in made.values():
+        n.close()
+
+
+def _check(p, v, po, vo, tol):
+    assert p.shape == po.shape and v.shape == vo.shape and p.dtype == np.float32 and v.dtype == np.float32
+    assert np.isfinite(p).all() and np.isfinite(v).all()
+    assert np.abs(p - po).max() <= tol[0], np.abs(p - po).max()
+    assert np.abs(v - vo).max() <= tol[1], np.abs(v - vo).max()
+    top2 = np.sort(po, axis=1)[:, -2:]
+    decisive = (top2[:, 1] - top2[:, 0]) > 2 * tol[0]
+    assert (p.argmax(1)[decisive] == po.argmax(1)[decisive]).all()
+    return float(decisive.mean())
+
+
+@pytest.mark.parametrize("tag", ["default", "perturbed"])
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 7, 8, 9, 16, 37, 64, 255])
+def test_predict_matches_oracle(nets, weights_default, weights_perturbed, tag, prec, n):
+    w = weights_default if tag == "default" else weights_perturbed
+    x = synth.synthetic_planes(n, seed=1000 + n)
+    p, v = nets[tag, prec].predict(x)
+    po, vo = _oracle().forward_torch(w, x)
+    _check(p, v, po, vo, FP32_TOL if prec == "fp32" else _bf16_tol(tag))
+
+
+@pytest.mark.parametrize("tag", ["default", "perturbed"])
+def test_golden_fixture(nets, golden, tag):
+    x = synth.synthetic_planes(int(golden["batch"]), seed=int(golden["input_seed"]))
+    p, v = nets[tag, "fp32"].predict(x)
+    _check(p, v, golden[f"{tag}_policy_f64"].astype(np.float32), golden[f"{tag}_value_f64"].astype(np.float32), FP32_TOL)
+    p, v = nets[tag, "bf16"].predict(x)
+    _check(p, v, golden[f"{tag}_policy_f64"].astype(np.float32), golden[f"{tag}_value_f64"].astype(np.float32), _bf16_tol(tag))
+    # the oracle's bf16 emulation (same rounding points, different accumulation order) stays as close
+    assert np.abs(p - golden[f"{tag}_policy_bf16"]).max() <= _bf16_tol(tag)[0]
+
+
+def test_trunk_activations_match_fp32_path(nets):
+    x = synth.synthetic_planes(11, seed=3)
+    for nconv in (1, 2, 3, 15):
+        a = nets["perturbed", "bf16"].debug_activations(x, nconv)
+        b = nets["perturbed", "fp32"].debug_activations(x, nconv)
+        assert np.abs(a - b).max() <= 0.02 * max(1.0, np.abs(b).max())
+
+
+def test_reference_call_conventions(nets):
+    """What mcts.py does with the result (mcts.py:57-60,101-106) and the float64 warm-up (network.py:72)."""
+    net = nets["default", "bf16"]
+    x64 = np.random.default_rng(0).random((1, 266, 5, 5))           # float64, batch 1
+    policy, value = net.predict(x64)
+    assert policy.shape == (1, 1725) and value.shape == (1, 1)
+    v = (value + 1) / 2
+    assert 0.0 <= float(v[0][0]) <= 1.0 and policy[0].shape == (1725,)
+    plist, vlist = net.model.predict(x64.tolist())                     # array-like input
+    np.testing.assert_array_equal(plist, policy)
+    with pytest.raises(ValueError):
+        net.predict(np.zeros((0, 266, 5, 5), dtype=np.float32))
+    with pytest.raises(ValueError):
+        net.predict(np.zeros((2, 265, 5, 5), dtype=np.float32))
+    z, vz = net.predict(net.zero_inputs(3))                            # all-zero planes: bias-only path
+    assert np.allclose(z[0], z[1]) and np.allclose(vz[0], vz[2])
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_batch_invariance_and_determinism(nets, prec):
+    """Size-independent properties at the headline batch: row i of a 1024 batch == the same position
+    evaluated alone or in another order; repeated calls are bit-identical."""
+    net = nets["perturbed", prec]
+    x = synth.synthetic_planes(1024, seed=77)
+    p, v = net.predict(x)
+    p2, v2 = net.predict(x)
+    assert np.array_equal(p, p2) and np.array_equal(v, v2)
+    perm = np.random.default_rng(1).permutation(1024)
+    pp, vp = net.predict(x[perm])
+    tol = 1e-5 if prec == "fp32" else 0.0   # tcgen05 path: a position's arithmetic does not depend on its slot
+    assert np.abs(pp - p[perm]).max() <= tol and np.abs(vp - v[perm]).max() <= tol
+    for i in (0, 5, 1023):
+        pi, vi = net.predict(x[i:i + 1])
+        assert np.abs(pi[0] - p[i]).max() <= max(tol, 1e-6) and abs(vi[0, 0] - v[i, 0]) <= max(tol, 1e-6)
+
+
+def test_large_batch_against_oracle_sample(nets, weights_default):
+    net = nets["default", "bf16"]
+    x = synth.synthetic_planes(4096, seed=9)
+    p, v = net.predict(x)
+    idx = np.arange(0, 4096, 97)
+    po, vo = _oracle().forward_torch(weights_default, x[idx])
+    _check(p[idx], v[idx], po, vo, BF16_TOL)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_masked_softmax_tail(nets, weights_default, prec):
+    O = _oracle()
+    n = 19
+    x = synth.synthetic_planes(n, seed=21)
+    m = synth.synthetic_legal_mask(n, seed=22)
+    m[3] = 0                                  # a row without legal moves
+    m[4] = 0; m[4, 100] = 1                   # a single legal move
+    probs, v = nets["default", prec].predict_masked(x, m)
+    p, v2 = nets["default", prec].predict(x)
+    np.testing.assert_array_equal(v, v2)
+    ref = O.masked_softmax(p, m)              # softmax of the SAME logits: tests the fused tail alone
+    assert np.abs(probs - ref).max() <= 2e-6
+    assert np.all(probs[m == 0] == 0) and np.all(probs[3] == 0) and probs[4, 100] == 1.0
+    po, _ = O.forward_torch(weights_default, x)
+    assert np.abs(probs - O.masked_softmax(po, m)).max() <= (1e-4 if prec == "fp32" else 0.03)
+
+
+def test_set_weights_roundtrip_and_swap(nets, weights_default, weights_perturbed, tmp_path):
+    from erweitern_55_b200.network import Network
+    net = Network(precision="bf16", weights=weights_default)
+    x = synth.synthetic_planes(6, seed=4)
+    p0, _ = net.predict(x)
+    got = net.get_weights()
+    assert len(got) == 108 and all(np.array_equal(a, b) for a, b in zip(got, weights_default))
+    net.model.set_weights(weights_perturbed)                           # client.py:51
+    p1, v1 = net.predict(x)
+    pr, vr = nets["perturbed", "bf16"].predict(x)
+    assert np.array_equal(p1, pr) and np.array_equal(v1, vr) and not np.array_equal(p0, p1)
+    path = str(tmp_path / "w.npz")
+    net.save(path)
+    net.set_weights(weights_default)
+    net.load(path)
+    p2, _ = net.predict(x)
+    assert np.array_equal(p2, p1)
+    with pytest.raises(ValueError):
+        net.set_weights(W.init_weights(blocks=2))
+    net.close()
+
+
+def test_predict_from_other_threads(nets):
+    """usi.py:146-148 calls predict from a ponder thread; contexts serialise internally."""
+    net = nets["default", "bf16"]
+    x = synth.synthetic_planes(16, seed=8)
+    want, _ = net.predict(x)
+    out, errs = [None] * 4, []
+
+    def work(i):
+        try:
+            for _ in range(5):
+                out[i] = net.predict(x)[0]
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs and all(np.array_equal(o, want) for o in out)
+
+
+def test_device_resident_api(nets):
+    net = nets["default", "bf16"]
+    x = synth.synthetic_planes(100, seed=12)
+    p, v = net.predict(x)
+    xd = torch.from_numpy(x).cuda()
+    pd = torch.empty((100, 1725), device="cuda")
+    vd = torch.empty((100, 1), device="cuda")
+    before = net.launch_count()
+    net.predict_device(xd, pd, vd)
+    net.sync()
+    assert net.launch_count() > before
+    assert np.array_equal(pd.cpu().numpy(), p) and np.array_equal(vd.cpu().numpy(), v)
+
+
+def test_small_and_scaled_architectures(weights_default):
+    """Other tower shapes: 2 blocks on the tcgen05 path; 256 filters on the fp32 path only."""
+    from erweitern_55_b200 import _capi
+    from erweitern_55_b200.network import Network
+    O = _oracle()
+    w2 = W.init_weights(blocks=2, filters=128, in_planes=40, seed=5, perturbed=True)
+    x = synth.synthetic_planes(9, seed=2, in_planes=40)
+    po, vo = O.forward_torch(w2, x)
+    for prec, tol in (("fp32", FP32_TOL), ("bf16", BF16_TOL_PERTURBED)):
+        net = Network(blocks=2, in_planes=40, precision=prec, weights=w2)
+        _check(*net.predict(x), po, vo, tol)
+        net.close()
+    w3 = W.init_weights(blocks=1, filters=256, seed=6, perturbed=True)
+    x = synth.synthetic_planes(5, seed=3)
+    net = Network(blocks=1, filters=256, precision="fp32", weights=w3)
+    _check(*net.predict(x), *O.forward_torch(w3, x), FP32_TOL)
+    with pytest.raises(_capi.E55Error):
+        net.set_precision("bf16")
+    net.close()
+
+
+def test_umma_addressing_selftest():
+    import ctypes as C
+    from erweitern_55_b200 import _capi
+    lib = _capi.load()
+    for shift in (0, 1, 7, 25, 49):
+        err = C.c_float(-1)
+        assert lib.e55_selftest_umma(0, shift, C.byref(err)) == 0
+        assert err.value == 0.0
