@@ -32,6 +32,7 @@ SIGNATURES = {
     "e55_debug_activations": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "e55_set_kernel_timing": (C.c_int, [_ctx, C.c_int]),
     "e55_get_kernel_timing": (C.c_int, [_ctx, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "e55_debug_set_lag": (C.c_int, [_ctx, C.c_int]),
     "e55_debug_profile": (C.c_int, [_ctx, C.c_int, C.POINTER(C.c_uint64)]),
     "e55_selftest_umma": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "e55_bench_umma": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),

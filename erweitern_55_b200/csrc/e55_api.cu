@@ -589,16 +589,25 @@ int e55_get_kernel_timing(e55_ctx* c, double* total_ms_out, int64_t* launches_ou
   return E55_OK;
 }
 
+int e55_debug_set_lag(e55_ctx* c, int lag) {
+  if (!c || lag < 0 || lag > 16) return E55_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  c->tc.lag = lag;
+  return E55_OK;
+}
+
+static constexpr size_t kProfWords = 16 + 8192 + 1024;
+
 int e55_debug_profile(e55_ctx* c, int enable, uint64_t* counters_out) {
   if (!c) return E55_ERR_INVALID;
   std::lock_guard<std::mutex> lk(c->mu);
   E55_CUDA(c, cudaSetDevice(c->device));
   E55_CUDA(c, cudaStreamSynchronize(c->stream));
   if (counters_out && c->tc.d_prof)
-    E55_CUDA(c, cudaMemcpy(counters_out, c->tc.d_prof, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-  if (enable && !c->tc.d_prof) E55_CUDA(c, cudaMalloc(&c->tc.d_prof, 16 * sizeof(uint64_t)));
+    E55_CUDA(c, cudaMemcpy(counters_out, c->tc.d_prof, kProfWords * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  if (enable && !c->tc.d_prof) E55_CUDA(c, cudaMalloc(&c->tc.d_prof, kProfWords * sizeof(uint64_t)));
   if (!enable && c->tc.d_prof) { cudaFree(c->tc.d_prof); c->tc.d_prof = nullptr; }
-  if (c->tc.d_prof) E55_CUDA(c, cudaMemset(c->tc.d_prof, 0, 16 * sizeof(uint64_t)));
+  if (c->tc.d_prof) E55_CUDA(c, cudaMemset(c->tc.d_prof, 0, kProfWords * sizeof(uint64_t)));
   return E55_OK;
 }
 

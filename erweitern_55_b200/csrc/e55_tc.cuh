@@ -50,13 +50,13 @@ constexpr int kRowsTotal = kGuard + kTile + kGuard + kTile + kGuard;  // 331
 constexpr int kPlanes = kF / 8;        // 16
 constexpr int kPlaneBytes = kRowsTotal * 16;
 constexpr int kActBytes = kPlanes * kPlaneBytes;                       // 84,736
-constexpr int kMaxStages = 4;
-constexpr int kStageBytes = 32768;     // one tap of a 128-wide layer: 8 K-steps x 128 x 16 x 2 B
+constexpr int kMaxStages = 5;
+constexpr int kStageBytes = 24576;     // one chunk: 3 taps (dx = -1,0,1) x 2 K-steps x 128 x 16 x 2 B
 constexpr int kPolicyCh = 69;
 constexpr int kPolicyN = 80;           // policy 1x1 output channels padded to a legal UMMA N
 constexpr int kSq = 25;
-constexpr int kThreads = 384;
-constexpr int kTmemCols = 256;
+constexpr int kThreads = 352;
+constexpr int kTmemCols = 512;         // 2 groups x 2 accumulators (layer parity) x 128 columns
 constexpr uint32_t kDescHi = 8u | (1u << 14);  // SBO = 128 B, descriptor version 1, no swizzle
 
 __host__ __device__ constexpr int group_origin_row(int g) { return kGuard + g * (kTile + kGuard); }
@@ -64,17 +64,19 @@ __host__ __device__ constexpr int group_origin_row(int g) { return kGuard + g * 
 enum : uint32_t { kFirstOfSlice = 1, kLastOfSlice = 2, kFirstOfLayer = 4, kLastOfLayer = 8 };
 enum : uint32_t { kRelu = 1, kHasRes = 2, kUpdRes = 4, kValueTap = 8, kFinal = 16 };
 
-// One ring stage worth of weights: all K-steps of one tap of one input slice.
+// One ring stage worth of weights: the taps of one board row (dx = -1,0,1; or the single tap of a 1x1
+// layer) for one 32-channel K block of one input slice.  Within a layer chunks are ordered K-block-major,
+// so the MMAs of K block kb only need activation planes 4kb..4kb+3 of the previous layer's epilogue.
 struct alignas(16) Chunk {
   uint32_t gofs;     // byte offset into the weight image
-  uint32_t bytes;    // nk * 2 * ndim * 16
-  int16_t a_off;     // A-descriptor displacement in 16 B units: kplane * rows + tap row shift
-  uint8_t nk;        // K=16 steps in this chunk
+  uint32_t bytes;    // ntaps * nk * 2 * ndim * 16
+  int16_t a_off;     // A-descriptor displacement in 16 B units: kplane * rows + dy * board width
+  uint8_t nk;        // K=16 steps per tap in this chunk
+  uint8_t ntaps;     // 3 (dx = -1,0,1) or 1
   uint8_t ndim8;     // UMMA N / 8 of the layer
-  uint8_t flags;
+  uint8_t flags;     // low 4 bits: first/last of slice/layer; high 4 bits: activation K blocks required
   uint8_t layer;
   uint8_t slice;
-  uint8_t pad;
 };
 
 struct LayerInfo {
@@ -93,10 +95,12 @@ struct Params {
   const float* fc1_b;      // [128]
   const float* fc2_k;      // [128]
   float value_b, fc2_b;
-  const uint8_t* in_packed;  // [groups][in_planes8][120][16 B]
-  int in_planes8;            // ceil(in_planes / 16) * 2
+  const float* planes;       // [n][in_planes][25] fp32 NCHW, as Network.get_inputs builds them
+  int in_planes;
+  int in_planes8;            // ceil(in_planes / 16) * 2: 8-channel planes incl. zero padding
   int nslices;
   int nstages;               // weight ring depth
+  int lag;                   // chunks group A is kept ahead of group B (0 = free running)
   int nchunks_total;         // chunks of the full network (size of the shared-memory chunk table)
   int nlayers;               // layers of the full network (tower convs + policy conv + policy 1x1)
   int nlayers_run;           // == nlayers, or fewer for a debug dump
@@ -107,31 +111,6 @@ struct Params {
   uint4* dbg;                // [rounds*2][16][128] packed activations after layer nlayers_run-1
   unsigned long long* prof;  // optional [16] cycle counters of CTA 0 (kProf instantiation only)
 };
-
-// ---- input packing: fp32 NCHW planes -> bf16 wide-board planes ------------------------------------
-// out[group][plane][row][8]: row = y*24 + p*6 + x, zero for the pad column, absent positions and the
-// channels beyond in_planes.  (network.py:255-274 builds the fp32 array this reads.)
-__global__ void __launch_bounds__(256)
-pack_input_kernel(const float* __restrict__ in, uint4* __restrict__ out, int n, int in_planes, int planes8) {
-  const int group = blockIdx.x;
-  for (int idx = threadIdx.x; idx < planes8 * kRowsValid; idx += blockDim.x) {
-    const int pl = idx / kRowsValid, r = idx % kRowsValid;
-    const int y = r / kW, p = (r % kW) / 6, x = r % 6;
-    const int pos = group * kPosPerGroup + p;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (x < 5 && pos < n) {
-      float f[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int c = pl * 8 + e;
-        f[e] = c < in_planes ? in[(static_cast<size_t>(pos) * in_planes + c) * kSq + y * 5 + x] : 0.f;
-      }
-      v.x = ptx::pack_bf16x2(f[0], f[1]); v.y = ptx::pack_bf16x2(f[2], f[3]);
-      v.z = ptx::pack_bf16x2(f[4], f[5]); v.w = ptx::pack_bf16x2(f[6], f[7]);
-    }
-    out[(static_cast<size_t>(group) * planes8 + pl) * kRowsValid + r] = v;
-  }
-}
 
 // debug: packed activations [group][16][128 rows][8] bf16 -> fp32 NCHW [n][128][25]
 __global__ void unpack_debug_kernel(const uint4* __restrict__ dbg, float* __restrict__ out, int n) {
@@ -175,29 +154,31 @@ __device__ __forceinline__ void umma_lohi(uint32_t tmem_d, uint32_t a_lo, uint32
 // Epilogue of one 128x128 accumulator tile for the thread that owns `row`:
 // TMEM -> +bias (+residual) -> ReLU -> bf16 -> shared memory (in place: the next layer's A operand).
 template <bool kRes, bool kUpd, bool kVal>
-__device__ __forceinline__ float epilogue_tile(uint32_t taddr, const float* __restrict__ bias, uint8_t* act_row,
-                                               uint32_t (&res)[kF / 2], const float* __restrict__ s_wv,
-                                               bool row_valid, uint4* dbg_row) {
+__device__ __forceinline__ float epilogue_half(uint32_t taddr, const float* __restrict__ bias, uint8_t* act_row,
+                                               uint32_t (&res)[kF / 4], const float* __restrict__ s_wv,
+                                               bool row_valid, uint4* dbg_row, uint64_t* bar_part, int lane) {
+  // taddr / bias / act_row / s_wv / dbg_row / bar_part already point at this thread's 64-channel half
   float vacc = 0.f;
+  uint32_t v[2][32];
+  ptx::tmem_ld_32x32b_x32(taddr, v[0]);
 #pragma unroll
-  for (int cb = 0; cb < 4; ++cb) {
-    uint32_t v[32];
-    ptx::tmem_ld_32x32b_x32(taddr + cb * 32, v);
+  for (int cb = 0; cb < 2; ++cb) {
     ptx::tmem_ld_wait();
+    if (cb < 1) ptx::tmem_ld_32x32b_x32(taddr + 32, v[1]);  // overlaps the math below
+    const uint32_t(&vv)[32] = v[cb & 1];
     uint32_t o[16];
 #pragma unroll
     for (int j4 = 0; j4 < 8; ++j4) {
       const float4 bb = *reinterpret_cast<const float4*>(bias + cb * 32 + j4 * 4);
-      float a0 = __uint_as_float(v[4 * j4 + 0]) + bb.x;
-      float a1 = __uint_as_float(v[4 * j4 + 1]) + bb.y;
-      float a2 = __uint_as_float(v[4 * j4 + 2]) + bb.z;
-      float a3 = __uint_as_float(v[4 * j4 + 3]) + bb.w;
+      float a0 = __uint_as_float(vv[4 * j4 + 0]) + bb.x;
+      float a1 = __uint_as_float(vv[4 * j4 + 1]) + bb.y;
+      float a2 = __uint_as_float(vv[4 * j4 + 2]) + bb.z;
+      float a3 = __uint_as_float(vv[4 * j4 + 3]) + bb.w;
       if (kRes) {
         const uint32_t r0 = res[cb * 16 + 2 * j4], r1 = res[cb * 16 + 2 * j4 + 1];
         a0 += bf16lo(r0); a1 += bf16hi(r0); a2 += bf16lo(r1); a3 += bf16hi(r1);
       }
-      a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f);
-      const uint32_t p0 = ptx::pack_bf16x2(a0, a1), p1 = ptx::pack_bf16x2(a2, a3);
+      const uint32_t p0 = ptx::pack_relu_bf16x2(a0, a1), p1 = ptx::pack_relu_bf16x2(a2, a3);
       o[2 * j4] = p0; o[2 * j4 + 1] = p1;
       if (kUpd) { res[cb * 16 + 2 * j4] = p0; res[cb * 16 + 2 * j4 + 1] = p1; }
       if (kVal) {
@@ -213,6 +194,11 @@ __device__ __forceinline__ float epilogue_tile(uint32_t taddr, const float* __re
         if (dbg_row) dbg_row[(cb * 4 + j4) * kTile] = pk;
       }
     }
+    // this 32-channel K block of the new activations is complete: the next layer's MMAs on it may start
+    ptx::tc_fence_before_sync();
+    ptx::fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&bar_part[cb]);
   }
   return vacc;
 }
@@ -225,18 +211,19 @@ tower_kernel(const Params prm) {
   uint8_t* s_act = smem + SmemLayout::act(prm.nstages);
   float* s_bias = reinterpret_cast<float*>(s_act + kActBytes);
   float* s_wv = s_bias + prm.nlayers * kF;
-  float* s_v = s_wv + kF;                       // [2 groups][4 positions][25]
-  float* s_part = s_v + 2 * kPosPerGroup * kSq;  // [2 groups][4 warps][4 positions]
+  float* s_v = s_wv + kF;                       // [2 groups][2 halves][4 positions][25]
+  float* s_part = s_v + 4 * kPosPerGroup * kSq;  // [2 groups][4 warps][4 positions]
   Chunk* s_chunks = reinterpret_cast<Chunk*>(s_part + 32);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_chunks + prm.nchunks_total);
   const uint32_t nstages = prm.nstages;
   uint64_t* bar_full = bars;                     // [nstages]
   uint64_t* bar_empty = bars + kMaxStages;       // [nstages]
   uint64_t* bar_tmem_full = bars + 2 * kMaxStages;  // [2]
-  uint64_t* bar_act_ready = bar_tmem_full + 2;   // [2]
-  uint64_t* bar_in_full = bar_act_ready + 2;     // [2]
+  uint64_t* bar_act_part = bar_tmem_full + 2;    // [2 groups][4 K blocks of 32 channels]
+  uint64_t* bar_in_full = bar_act_part + 8;      // [2]
   uint64_t* bar_in_empty = bar_in_full + 2;      // [2]
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_in_empty + 2);
+  volatile uint32_t* s_apos = s_tmem + 1;        // chunks issued so far by group A's issuer
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -250,14 +237,15 @@ tower_kernel(const Params prm) {
   for (int i = threadIdx.x; i < kF; i += kThreads) s_wv[i] = prm.value_w[i];
   for (int i = threadIdx.x; i < prm.nchunks_total; i += kThreads) s_chunks[i] = prm.chunks[i];
   if (threadIdx.x == 0) {
+    *s_apos = 0u;
     for (uint32_t s = 0; s < nstages; ++s) {
       ptx::mbar_init(&bar_full[s], 1);
       ptx::mbar_init(&bar_empty[s], 2);
     }
     for (int g = 0; g < 2; ++g) {
       ptx::mbar_init(&bar_tmem_full[g], 1);
-      ptx::mbar_init(&bar_act_ready[g], 4);
-      ptx::mbar_init(&bar_in_full[g], 1);
+      for (int kb = 0; kb < 4; ++kb) ptx::mbar_init(&bar_act_part[g * 4 + kb], 4);
+      ptx::mbar_init(&bar_in_full[g], 8);
       ptx::mbar_init(&bar_in_empty[g], 1);
     }
     ptx::fence_mbar_init();
@@ -288,76 +276,68 @@ tower_kernel(const Params prm) {
       }
       if (kProf && blockIdx.x == 0) prm.prof[8] = t_wait;
     }
-  } else if (warp == 10) {
-    // ===== stem-input loader =================================================================
-    if (lane == 0) {
-      uint32_t k[2] = {0, 0};  // loads issued so far per group
-      for (int r = blockIdx.x; r < prm.nrounds; r += gridDim.x) {
-        for (int sl = 0; sl < prm.nslices; ++sl) {
-          const int pl0 = sl * kPlanes;
-          const int npl = min(kPlanes, prm.in_planes8 - pl0);
-          for (int g = 0; g < 2; ++g) {
-            if (r * kPosPerRound + g * kPosPerGroup >= prm.n) continue;
-            if (k[g] > 0) ptx::mbar_wait(&bar_in_empty[g], (k[g] - 1) & 1);
-            ptx::mbar_arrive_expect_tx(&bar_in_full[g], npl * kRowsValid * 16);
-            const uint8_t* src = prm.in_packed +
-                                 (static_cast<size_t>(r * 2 + g) * prm.in_planes8 + pl0) * (kRowsValid * 16);
-            for (int pl = 0; pl < npl; ++pl)
-              ptx::tma_bulk_g2s(s_act + pl * kPlaneBytes + group_origin_row(g) * 16,
-                                src + static_cast<size_t>(pl) * kRowsValid * 16, kRowsValid * 16, &bar_in_full[g]);
-            ++k[g];
-          }
-        }
-      }
-    }
-  } else if (warp == 9 || warp == 11) {
-    // ===== MMA issuers: warp 9 drives group A, warp 11 group B (warp-uniform loop, one elected lane
+  } else if (warp == 9 || warp == 10) {
+    // ===== MMA issuers: warp 9 drives group A, warp 10 group B (warp-uniform loop, one elected lane
     // issues).  Both walk the same chunk sequence; a ring stage is released after both used it. =====
     const int g = warp == 9 ? 0 : 1;
     const uint32_t a_lo_base = ((ptx::smem_u32(s_act) + group_origin_row(g) * 16) >> 4) |
                                (static_cast<uint32_t>(kPlaneBytes >> 4) << 16);
     const uint32_t b_lo_base = ptx::smem_u32(s_ring) >> 4;
-    const uint32_t d = tmem_base + g * kF;
     uint32_t s = 0, ph = 0, round_seq = 0;
     long long t_start = 0, t_issue = 0, t_full = 0, t_act = 0;
     if (kProf) t_start = clock64();
     for (int r = blockIdx.x; r < prm.nrounds; r += gridDim.x, ++round_seq) {
       const bool has_b = r * kPosPerRound + kPosPerGroup < prm.n;
       if (g == 1 && !has_b) break;  // only the last round can lack group B
+      const uint32_t gbase = round_seq * nchunks;
       for (uint32_t c = 0; c < nchunks; ++c) {
         const Chunk ch = s_chunks[c];
         long long t0 = 0, t1 = 0, t2 = 0;
         if (kProf) t0 = clock64();
+        if (g == 1 && prm.lag > 0) {
+          // Keep group A `lag` chunks ahead so that one group's epilogue overlaps the other group's
+          // MMAs; once A has finished B's current layer (A is then in its own epilogue or further on)
+          // B runs freely to the end of that layer.
+          const uint32_t want = min(gbase + c + 1 + prm.lag, gbase + static_cast<uint32_t>(prm.layers[ch.layer].chunk_end));
+          while (*s_apos < want) {
+          }
+        }
         ptx::mbar_wait(&bar_full[s], ph);
         if (kProf) t1 = clock64();
-        if (ch.flags & kFirstOfSlice) {
-          const uint32_t epoch = round_seq * nl + ch.layer;
-          if (ch.layer == 0) ptx::mbar_wait(&bar_in_full[g], (round_seq * prm.nslices + ch.slice) & 1);
-          if ((ch.flags & kFirstOfLayer) && epoch > 0) ptx::mbar_wait(&bar_act_ready[g], (epoch - 1) & 1);
+        const uint32_t epoch = round_seq * nl + ch.layer;
+        if ((ch.flags & kFirstOfSlice) && ch.layer == 0)
+          ptx::mbar_wait(&bar_in_full[g], (round_seq * prm.nslices + ch.slice) & 1);
+        if ((ch.flags >> 4) && epoch > 0) {
+          // activation K blocks written by the previous layer's (progressive) epilogue
+#pragma unroll
+          for (int kb = 0; kb < 4; ++kb)
+            if ((ch.flags >> 4) & (1u << kb)) ptx::mbar_wait(&bar_act_part[g * 4 + kb], (epoch - 1) & 1);
         }
         if (kProf) t2 = clock64();
         ptx::tc_fence_after_sync();
         if (ptx::elect_one()) {
           const uint32_t ndim = ch.ndim8 * 8u;
           const uint32_t idesc = ptx::umma_idesc_bf16_f32(kTile, ndim);
-          uint32_t a_lo = a_lo_base + static_cast<int>(ch.a_off);
+          const uint32_t d = tmem_base + (g * 2 + (ch.layer & 1)) * kF;
+          const uint32_t a_chunk = a_lo_base + static_cast<int>(ch.a_off) - (ch.ntaps == 3 ? 1 : 0);
           uint32_t b_lo = (b_lo_base + s * (kStageBytes >> 4)) | (ndim << 16);
           uint32_t acc = (ch.flags & kFirstOfLayer) ? 0u : 1u;
-          if (ch.nk == 8) {
+          if (ch.ntaps == 3 && ch.nk == 2) {
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-              umma_lohi(d, a_lo, b_lo, idesc, acc);
-              acc = 1u;
-              a_lo += 2 * (kPlaneBytes >> 4);
-              b_lo += 2 * ndim;
-            }
+            for (int t = 0; t < 3; ++t)
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) {
+                umma_lohi(d, a_chunk + t + ks * 2 * (kPlaneBytes >> 4), b_lo, idesc, acc);
+                acc = 1u;
+                b_lo += 2 * ndim;
+              }
           } else {
-            for (int ks = 0; ks < ch.nk; ++ks) {
-              umma_lohi(d, a_lo, b_lo, idesc, acc);
-              acc = 1u;
-              a_lo += 2 * (kPlaneBytes >> 4);
-              b_lo += 2 * ndim;
-            }
+            for (int t = 0; t < ch.ntaps; ++t)
+              for (int ks = 0; ks < ch.nk; ++ks) {
+                umma_lohi(d, a_chunk + t + ks * 2 * (kPlaneBytes >> 4), b_lo, idesc, acc);
+                acc = 1u;
+                b_lo += 2 * ndim;
+              }
           }
           ptx::umma_commit(&bar_empty[s]);
           if (!has_b) ptx::umma_commit(&bar_empty[s]);
@@ -369,8 +349,16 @@ tower_kernel(const Params prm) {
           }
         }
         __syncwarp();
+        if (g == 0 && lane == 0) *s_apos = gbase + c + 1;
         if (++s == nstages) { s = 0; ph ^= 1; }
-        if (kProf) { t_full += t1 - t0; t_act += t2 - t1; t_issue += clock64() - t2; }
+        if (kProf) {
+          const long long t3 = clock64();
+          t_full += t1 - t0; t_act += t2 - t1; t_issue += t3 - t2;
+          if (blockIdx.x == 0 && lane == 0 && round_seq == 0 && c < 1024) {
+            unsigned long long* tr = prm.prof + 16 + g * 4096 + c * 4;
+            tr[0] = t0; tr[1] = t1; tr[2] = t2; tr[3] = t3;
+          }
+        }
       }
     }
     if (kProf && blockIdx.x == 0 && lane == 0) {
@@ -378,109 +366,175 @@ tower_kernel(const Params prm) {
       o[0] = clock64() - t_start; o[1] = t_issue; o[2] = t_full; o[3] = t_act;
     }
   } else {
-    // ===== epilogue warps (0-3: group A, 4-7: group B) ========================================
-    const int g = warp >> 2;
+    // ===== epilogue warps 0-7, shared by both groups: warp w owns TMEM lane quadrant w%4 (32 tile rows)
+    // and the 64-channel half w/4 of whichever group's accumulator is complete. =====================
     const int q = warp & 3;
+    const int h = warp >> 2;
     const int row = q * 32 + lane;                       // TMEM lane == tile row
     const int by = row / kW, bp = (row % kW) / 6, bx = row % 6;
     const bool row_valid = row < kRowsValid && bx < 5;
     const int sq = by * 5 + bx;
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * kF;
-    uint8_t* act_row = s_act + (group_origin_row(g) + row) * 16;
-    uint32_t res[kF / 2];                                // block input of this row, packed bf16x2
+    uint32_t res_a[kF / 4], res_b[kF / 4];               // block inputs of this row/half, packed bf16x2
 #pragma unroll
-    for (int i = 0; i < kF / 2; ++i) res[i] = 0u;
+    for (int i = 0; i < kF / 4; ++i) { res_a[i] = 0u; res_b[i] = 0u; }
     uint32_t round_seq = 0;
+    uint32_t slices_done[2] = {0u, 0u};
     long long t_wait = 0, t_work = 0;
 
     for (int r = blockIdx.x; r < prm.nrounds; r += gridDim.x, ++round_seq) {
-      const int pos_base = r * kPosPerRound + g * kPosPerGroup;
-      if (pos_base >= prm.n) continue;
-      const int pos = pos_base + bp;
-      const bool out_valid = row_valid && pos < prm.n;
-      for (int L = 0; L < nl; ++L) {
-        const uint32_t epoch = round_seq * nl + L;
-        const uint32_t lf = prm.layers[L].flags;
-        const float* bias = s_bias + L * kF;
+      const bool has_b = r * kPosPerRound + kPosPerGroup < prm.n;
+      int next_layer[2] = {0, has_b ? 0 : nl};
+      int next_slice[2] = {0, has_b ? 0 : prm.nslices};
+      while (next_layer[0] < nl || next_layer[1] < nl) {
         long long te0 = 0, te1 = 0;
         if (kProf) te0 = clock64();
-        ptx::mbar_wait(&bar_tmem_full[g], epoch & 1);
+        int g;
+        bool convert = false;
+        for (;;) {  // serve whichever event is ready first (group A preferred: it runs ahead)
+          if (next_layer[0] < nl && ptx::mbar_test_wait(&bar_tmem_full[0], (round_seq * nl + next_layer[0]) & 1)) { g = 0; break; }
+          if (next_layer[1] < nl && ptx::mbar_test_wait(&bar_tmem_full[1], (round_seq * nl + next_layer[1]) & 1)) { g = 1; break; }
+          // stem input: slice k of a group may be written once the MMAs that read slice k-1 are done
+          if (next_slice[0] < prm.nslices && (slices_done[0] == 0 || ptx::mbar_test_wait(&bar_in_empty[0], (slices_done[0] - 1) & 1))) { g = 0; convert = true; break; }
+          if (next_slice[1] < prm.nslices && (slices_done[1] == 0 || ptx::mbar_test_wait(&bar_in_empty[1], (slices_done[1] - 1) & 1))) { g = 1; convert = true; break; }
+        }
+        if (convert) {
+          // fp32 NCHW planes -> bf16 wide-board planes of this group (network.py:255-274 built the input):
+          // one item = 8 consecutive channels of one square of one position = one 16-byte row entry
+          const int sl = next_slice[g];
+          const int pl0 = sl * kPlanes;
+          const int npl = min(kPlanes, prm.in_planes8 - pl0);
+          const int pos0 = r * kPosPerRound + g * kPosPerGroup;
+          for (int it = threadIdx.x; it < kPosPerGroup * npl * kSq; it += 256) {
+            const int s_ = it % kSq, c8 = (it / kSq) % npl, p = it / (kSq * npl);
+            uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+            if (pos0 + p < prm.n) {
+              const float* src = prm.planes + (static_cast<size_t>(pos0 + p) * prm.in_planes + (pl0 + c8) * 8) * kSq + s_;
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = (pl0 + c8) * 8 + e < prm.in_planes ? __ldg(src + e * kSq) : 0.f;
+              pk = make_uint4(ptx::pack_bf16x2(f[0], f[1]), ptx::pack_bf16x2(f[2], f[3]),
+                              ptx::pack_bf16x2(f[4], f[5]), ptx::pack_bf16x2(f[6], f[7]));
+            }
+            const int rr = (s_ / 5) * kW + p * 6 + s_ % 5;
+            *reinterpret_cast<uint4*>(s_act + c8 * kPlaneBytes + (group_origin_row(g) + rr) * 16) = pk;
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&bar_in_full[g]);
+          next_slice[g] = sl + 1;
+          ++slices_done[g];
+          continue;
+        }
         ptx::tc_fence_after_sync();
         if (kProf) te1 = clock64();
+        const int L = next_layer[g];
+        next_layer[g] = L + 1;
+        const uint32_t lf = prm.layers[L].flags;
+        const float* bias = s_bias + L * kF + h * 64;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (g * 2 + (L & 1)) * kF + h * 64;
+        uint64_t* bar_part = &bar_act_part[g * 4 + h * 2];
+        const int pos_base = r * kPosPerRound + g * kPosPerGroup;
 
         if (!(lf & kFinal)) {
+          uint8_t* act_row = s_act + (h * 8) * kPlaneBytes + (group_origin_row(g) + row) * 16;
           uint4* dbg_row = (prm.dbg != nullptr && L == nl - 1)
-                               ? prm.dbg + static_cast<size_t>(r * 2 + g) * kPlanes * kTile + row : nullptr;
-          if (lf & kValueTap) {
-            float vacc;
-            if (lf & kHasRes) vacc = epilogue_tile<true, true, true>(taddr, bias, act_row, res, s_wv, row_valid, dbg_row);
-            else vacc = epilogue_tile<false, true, true>(taddr, bias, act_row, res, s_wv, row_valid, dbg_row);
-            if (row_valid) s_v[(g * kPosPerGroup + bp) * kSq + sq] = fmaxf(vacc + prm.value_b, 0.f);
-          } else if (lf & kHasRes) {
-            epilogue_tile<true, true, false>(taddr, bias, act_row, res, s_wv, row_valid, dbg_row);
-          } else if (lf & kUpdRes) {
-            epilogue_tile<false, true, false>(taddr, bias, act_row, res, s_wv, row_valid, dbg_row);
-          } else {
-            epilogue_tile<false, false, false>(taddr, bias, act_row, res, s_wv, row_valid, dbg_row);
+                               ? prm.dbg + (static_cast<size_t>(r * 2 + g) * kPlanes + h * 8) * kTile + row : nullptr;
+          const float* wv = s_wv + h * 64;
+          float vacc = 0.f;
+#define E55_EPI(RES)                                                                                          \
+          if (lf & kValueTap) {                                                                               \
+            if (lf & kHasRes) vacc = epilogue_half<true, true, true>(taddr, bias, act_row, RES, wv, row_valid, dbg_row, bar_part, lane);   \
+            else vacc = epilogue_half<false, true, true>(taddr, bias, act_row, RES, wv, row_valid, dbg_row, bar_part, lane);  \
+          } else if (lf & kHasRes) {                                                                          \
+            epilogue_half<true, true, false>(taddr, bias, act_row, RES, wv, row_valid, dbg_row, bar_part, lane);              \
+          } else if (lf & kUpdRes) {                                                                          \
+            epilogue_half<false, true, false>(taddr, bias, act_row, RES, wv, row_valid, dbg_row, bar_part, lane);             \
+          } else {                                                                                            \
+            epilogue_half<false, false, false>(taddr, bias, act_row, RES, wv, row_valid, dbg_row, bar_part, lane);            \
           }
+          if (g == 0) { E55_EPI(res_a) } else { E55_EPI(res_b) }
+#undef E55_EPI
+          // value 1x1 conv: this thread's half of the channel dot product (summed in the value tail)
+          if ((lf & kValueTap) && row_valid) s_v[((g * 2 + h) * kPosPerGroup + bp) * kSq + sq] = vacc;
         } else {
           // policy 1x1 output: fp32 logits straight to HBM, index c*25 + sq (Flatten of NCHW)
+          const int pos = pos_base + bp;
+          const bool out_valid = row_valid && pos < prm.n;
           float* dst = prm.policy + static_cast<size_t>(pos) * (kPolicyCh * kSq) + sq;
 #pragma unroll
-          for (int cb = 0; cb < 3; ++cb) {
+          for (int cb = 0; cb < 2; ++cb) {
+            if (h == 1 && cb == 1) break;  // channels 96.. do not exist (N = 80)
             uint32_t v[32];
             ptx::tmem_ld_32x32b_x32(taddr + cb * 32, v);
             ptx::tmem_ld_wait();
             if (out_valid) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
-                const int c = cb * 32 + j;
-                if (c < kPolicyCh) dst[c * kSq] = __uint_as_float(v[j]) + bias[c];
+                const int c = h * 64 + cb * 32 + j;
+                if (c < kPolicyCh) dst[c * kSq] = __uint_as_float(v[j]) + bias[cb * 32 + j];
               }
             }
           }
         }
-        ptx::tc_fence_before_sync();
-        ptx::fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&bar_act_ready[g]);
-        if (kProf) { t_wait += te1 - te0; t_work += clock64() - te1; }
+        if (lf & kFinal) {  // no activations written, but keep the per-layer barrier phases in step
+          ptx::tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) { ptx::mbar_arrive(&bar_part[0]); ptx::mbar_arrive(&bar_part[1]); }
+        }
+        if (kProf) {
+          const long long te2 = clock64();
+          t_wait += te1 - te0; t_work += te2 - te1;
+          if (blockIdx.x == 0 && threadIdx.x == 0 && round_seq == 0) {
+            unsigned long long* tr = prm.prof + 16 + 8192 + (g * nl + L) * 4;
+            tr[0] = te1; tr[1] = te2; tr[2] = g; tr[3] = L;
+          }
+        }
       }
 
       if (nl == prm.nlayers) {
-        // value head tail: Dense(25->128)+ReLU, Dense(128->1)+tanh (network.py:115-120), 128 threads/group
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
-        const int j = row;  // hidden unit
-        float h[kPosPerGroup];
-        const float b1 = prm.fc1_b[j];
+        // value head tail: ReLU(conv1x1) -> Dense(25->128)+ReLU -> Dense(128->1)+tanh (network.py:111-120);
+        // thread t: group t/128, hidden unit t%128
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int vg = threadIdx.x >> 7, j = threadIdx.x & 127;
+        if (vg == 0 || has_b) {
+          float hsum[kPosPerGroup];
+          const float b1 = prm.fc1_b[j];
 #pragma unroll
-        for (int p = 0; p < kPosPerGroup; ++p) h[p] = b1;
-        for (int s = 0; s < kSq; ++s) {
-          const float kk = prm.fc1_k[s * kF + j];
+          for (int p = 0; p < kPosPerGroup; ++p) hsum[p] = b1;
+          for (int s = 0; s < kSq; ++s) {
+            const float kk = prm.fc1_k[s * kF + j];
 #pragma unroll
-          for (int p = 0; p < kPosPerGroup; ++p) h[p] = fmaf(s_v[(g * kPosPerGroup + p) * kSq + s], kk, h[p]);
+            for (int p = 0; p < kPosPerGroup; ++p) {
+              const float v1 = fmaxf(s_v[((vg * 2 + 0) * kPosPerGroup + p) * kSq + s] +
+                                     s_v[((vg * 2 + 1) * kPosPerGroup + p) * kSq + s] + prm.value_b, 0.f);
+              hsum[p] = fmaf(v1, kk, hsum[p]);
+            }
+          }
+          const float k2 = prm.fc2_k[j];
+#pragma unroll
+          for (int p = 0; p < kPosPerGroup; ++p) {
+            float part = fmaxf(hsum[p], 0.f) * k2;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            if (lane == 0) s_part[(vg * 4 + (j >> 5)) * kPosPerGroup + p] = part;
+          }
         }
-        const float k2 = prm.fc2_k[j];
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (j < kPosPerGroup && (vg == 0 || has_b)) {
+          const int pos = r * kPosPerRound + vg * kPosPerGroup + j;
+          if (pos < prm.n) {
+            float t = prm.fc2_b;
 #pragma unroll
-        for (int p = 0; p < kPosPerGroup; ++p) {
-          float part = fmaxf(h[p], 0.f) * k2;
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-          if (lane == 0) s_part[(g * 4 + q) * kPosPerGroup + p] = part;
+            for (int w4 = 0; w4 < 4; ++w4) t += s_part[(vg * 4 + w4) * kPosPerGroup + j];
+            prm.value[pos] = tanhf(t);
+          }
         }
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
-        if (row < kPosPerGroup && pos_base + row < prm.n) {
-          float t = prm.fc2_b;
-#pragma unroll
-          for (int w4 = 0; w4 < 4; ++w4) t += s_part[(g * 4 + w4) * kPosPerGroup + row];
-          prm.value[pos_base + row] = tanhf(t);
-        }
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
     }
-    if (kProf && blockIdx.x == 0 && (threadIdx.x & 127) == 0) {
-      prm.prof[10 + 2 * g] = t_wait;
-      prm.prof[11 + 2 * g] = t_work;
+    if (kProf && blockIdx.x == 0 && threadIdx.x == 0) {
+      prm.prof[10] = t_wait;
+      prm.prof[11] = t_work;
     }
   }
 
@@ -502,6 +556,7 @@ struct State {
   int blocks = 0, filters = 0, in_planes = 0, sms = 0;
   int nlayers = 0, nslices = 0, in_planes8 = 0;
   int nstages = 0, nchunks = 0;
+  int lag = 1;
   size_t smem_bytes = 0;
   uint8_t* d_wimg = nullptr;
   Chunk* d_chunks = nullptr;
@@ -509,7 +564,6 @@ struct State {
   float* d_bias = nullptr;
   std::vector<LayerInfo> layers;
   HeadWeights heads{};
-  uint8_t* d_in_packed = nullptr;
   uint4* d_dbg = nullptr;
   unsigned long long* d_prof = nullptr;  // set by e55_debug_profile
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // when set, recorded around the tower kernel launch
@@ -533,17 +587,15 @@ inline void free_weights(State& s) {
 }
 
 inline void free_buffers(State& s) {
-  cudaFree(s.d_in_packed); cudaFree(s.d_dbg);
-  s.d_in_packed = nullptr; s.d_dbg = nullptr; s.capacity = 0;
+  cudaFree(s.d_dbg);
+  s.d_dbg = nullptr; s.capacity = 0;
 }
 
 inline cudaError_t alloc_buffers(State& s, int cap) {
   if (!supported(s)) return cudaSuccess;
   free_buffers(s);
   const size_t groups = (static_cast<size_t>(cap) + kPosPerGroup - 1) / kPosPerGroup + 1;
-  cudaError_t e = cudaMalloc(&s.d_in_packed, groups * s.in_planes8 * kRowsValid * 16);
-  if (e != cudaSuccess) return e;
-  e = cudaMalloc(&s.d_dbg, groups * kPlanes * kTile * sizeof(uint4));
+  cudaError_t e = cudaMalloc(&s.d_dbg, groups * kPlanes * kTile * sizeof(uint4));
   if (e != cudaSuccess) return e;
   s.capacity = cap;
   return cudaSuccess;
@@ -569,25 +621,29 @@ inline cudaError_t set_weights(State& s, const std::vector<std::vector<float>>& 
   std::vector<float> bias(static_cast<size_t>(s.nlayers) * kF, 0.f);
   s.layers.assign(s.nlayers, LayerInfo{});
 
-  auto emit = [&](int layer, int slice, int tap, int ntaps, int k0_total, int nk, int ndim, int cin, int cout,
-                  const float* w, uint32_t flags) {
+  // chunk = (layer, slice, K block kb of <= 32 channels, board row dy): ntaps taps x nk K-steps
+  auto emit = [&](int layer, int slice, int tap0, int ntaps, int total_taps, int ch0, int kplane, int nk, int ndim,
+                  int cin, int cout, const float* w, uint32_t flags, uint32_t need) {
     Chunk ch{};
     ch.gofs = static_cast<uint32_t>(img.size() * 2);
-    ch.bytes = static_cast<uint32_t>(nk * 2 * ndim * 16);
-    ch.a_off = static_cast<int16_t>(ntaps == 9 ? (tap / 3 - 1) * kW + (tap % 3 - 1) : 0);
+    ch.bytes = static_cast<uint32_t>(ntaps * nk * 2 * ndim * 16);
+    const int dy = total_taps == 9 ? tap0 / 3 - 1 : 0;
+    ch.a_off = static_cast<int16_t>(kplane * kRowsTotal + dy * kW);
     ch.nk = static_cast<uint8_t>(nk);
+    ch.ntaps = static_cast<uint8_t>(ntaps);
     ch.ndim8 = static_cast<uint8_t>(ndim / 8);
-    ch.flags = static_cast<uint8_t>(flags);
+    ch.flags = static_cast<uint8_t>(flags | (need << 4));
     ch.layer = static_cast<uint8_t>(layer);
     ch.slice = static_cast<uint8_t>(slice);
-    // image: [plane j][n][8 channels]
-    for (int j = 0; j < nk * 2; ++j)
-      for (int n = 0; n < ndim; ++n)
-        for (int e = 0; e < 8; ++e) {
-          const int ci = k0_total + j * 8 + e;
-          const float v = (ci < cin && n < cout) ? w[(static_cast<size_t>(tap) * cin + ci) * cout + n] : 0.f;
-          img.push_back(f32_to_bf16_rne(v));
-        }
+    // image: [tap][plane j][n][8 channels]
+    for (int t = 0; t < ntaps; ++t)
+      for (int j = 0; j < nk * 2; ++j)
+        for (int n = 0; n < ndim; ++n)
+          for (int e = 0; e < 8; ++e) {
+            const int ci = ch0 + j * 8 + e;
+            const float v = (ci < cin && n < cout) ? w[(static_cast<size_t>(tap0 + t) * cin + ci) * cout + n] : 0.f;
+            img.push_back(f32_to_bf16_rne(v));
+          }
     chunks.push_back(ch);
   };
 
@@ -600,7 +656,6 @@ inline cudaError_t set_weights(State& s, const std::vector<std::vector<float>>& 
     const int cin = is_stem ? s.in_planes : kF;
     const int cout = is_final ? kPolicyCh : kF;
     const int ndim = is_final ? kPolicyN : kF;
-    const int ntaps = is_final ? 1 : 9;
     const float* w = is_final ? heads.policy_w : conv_w[L].data();
     const float* b = is_final ? heads.policy_b : conv_b[L].data();
     for (int o = 0; o < cout; ++o) bias[static_cast<size_t>(L) * kF + o] = b[o];
@@ -617,13 +672,27 @@ inline cudaError_t set_weights(State& s, const std::vector<std::vector<float>>& 
     for (int sl = 0; sl < nslices; ++sl) {
       const int pl0 = sl * kPlanes;
       const int npl = std::min(kPlanes, planes_total - pl0);
-      for (int tap = 0; tap < ntaps; ++tap) {
-        uint32_t fl = 0;
-        if (tap == 0) fl |= kFirstOfSlice;
-        if (tap == ntaps - 1) fl |= kLastOfSlice;
-        if (tap == 0 && sl == 0) fl |= kFirstOfLayer;
-        if (tap == ntaps - 1 && sl == nslices - 1) fl |= kLastOfLayer;
-        emit(L, sl, tap, ntaps, pl0 * 8, npl / 2, ndim, cin, cout, w, fl);
+      if (is_final) {
+        // 1x1 conv: one chunk, all 8 K-steps, needs every activation K block
+        emit(L, sl, 0, 1, 1, 0, 0, npl / 2, ndim, cin, cout, w,
+             kFirstOfSlice | kLastOfSlice | kFirstOfLayer | kLastOfLayer, 0xFu);
+        continue;
+      }
+      const int nkb = (npl + 3) / 4;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int nk = std::min(2, (npl - kb * 4) / 2);
+        for (int dy = 0; dy < 3; ++dy) {
+          uint32_t fl = 0;
+          const bool first = kb == 0 && dy == 0, last = kb == nkb - 1 && dy == 2;
+          if (first) fl |= kFirstOfSlice;
+          if (last) fl |= kLastOfSlice;
+          if (first && sl == 0) fl |= kFirstOfLayer;
+          if (last && sl == nslices - 1) fl |= kLastOfLayer;
+          uint32_t need = 0;
+          if (!is_stem && dy == 0) need = 1u << kb;             // planes 4kb..4kb+3 of the previous epilogue
+          if (is_stem && first && sl == 0) need = 0xFu;          // previous round fully drained (TMEM + planes)
+          emit(L, sl, dy * 3, 3, 9, (pl0 + kb * 4) * 8, kb * 4, nk, ndim, cin, cout, w, fl, need);
+        }
       }
     }
     li.chunk_end = static_cast<int>(chunks.size());
@@ -640,8 +709,8 @@ inline cudaError_t set_weights(State& s, const std::vector<std::vector<float>>& 
   if ((e = cudaMemcpy(s.d_bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
 
   s.nchunks = static_cast<int>(chunks.size());
-  const size_t fixed = kActBytes + static_cast<size_t>(s.nlayers) * kF * 4 + kF * 4 + 2 * kPosPerGroup * kSq * 4 + 32 * 4 +
-                       chunks.size() * sizeof(Chunk) + (2 * kMaxStages + 8) * 8 + 16;
+  const size_t fixed = kActBytes + static_cast<size_t>(s.nlayers) * kF * 4 + kF * 4 + 4 * kPosPerGroup * kSq * 4 + 32 * 4 +
+                       chunks.size() * sizeof(Chunk) + (2 * kMaxStages + 16) * 8 + 16;
   s.nstages = static_cast<int>(std::min<size_t>(kMaxStages, (232448 - std::min<size_t>(fixed, 232448)) / kStageBytes));
   s.smem_bytes = fixed + static_cast<size_t>(s.nstages) * kStageBytes;
   s.attr_set = false;
@@ -659,17 +728,13 @@ inline cudaError_t run(State& s, const float* d_planes, int n, float* d_policy, 
     if (e != cudaSuccess) { *why = "cudaFuncSetAttribute"; return e; }
     s.attr_set = true;
   }
-  const int groups = (n + kPosPerGroup - 1) / kPosPerGroup;
   const int rounds = (n + kPosPerRound - 1) / kPosPerRound;
-  pack_input_kernel<<<rounds * 2, 256, 0, stream>>>(d_planes, reinterpret_cast<uint4*>(s.d_in_packed), n, s.in_planes, s.in_planes8);
-  ++*launched;
-  (void)groups;
   Params p{};
   p.wimg = s.d_wimg; p.chunks = s.d_chunks; p.layers = s.d_layers; p.bias = s.d_bias;
   p.value_w = s.heads.d_value_w; p.fc1_k = s.heads.d_fc1_k; p.fc1_b = s.heads.d_fc1_b; p.fc2_k = s.heads.d_fc2_k;
   p.value_b = s.heads.value_b; p.fc2_b = s.heads.fc2_b;
-  p.in_packed = s.d_in_packed; p.in_planes8 = s.in_planes8; p.nslices = s.nslices;
-  p.nstages = s.nstages; p.nchunks_total = s.nchunks;
+  p.planes = d_planes; p.in_planes = s.in_planes; p.in_planes8 = s.in_planes8; p.nslices = s.nslices;
+  p.nstages = s.nstages; p.nchunks_total = s.nchunks; p.lag = std::min(s.lag, s.nstages - 1);
   p.nlayers = s.nlayers; p.nlayers_run = nlayers_run; p.n = n; p.nrounds = rounds;
   p.policy = d_policy; p.value = d_value;
   p.dbg = nlayers_run < s.nlayers ? s.d_dbg : nullptr;

@@ -103,10 +103,15 @@ int e55_get_kernel_timing(e55_ctx* ctx, double* total_ms_out, int64_t* launches_
  * host, computed by the currently selected precision path. */
 int e55_debug_activations(e55_ctx* ctx, const float* planes, int n, int n_convs, float* act_out);
 
+/* Tuning: number of weight chunks the tower kernel keeps group A's MMA issuer ahead of group B's
+ * (0 = free running; clamped to ring depth - 1). */
+int e55_debug_set_lag(e55_ctx* ctx, int lag);
+
 /* Debug/profiling: switch the tower kernel's in-kernel cycle counters (CTA 0 only) on or off; when
- * counters_out is non-NULL the 16 counters accumulated so far are copied out first, then reset.
+ * counters_out is non-NULL the 9232 words (16 counters + per-chunk / per-event timestamps of the first
+ * round) accumulated so far are copied out first, then reset.
  * [0..3] group-A MMA issuer: total, issue, wait-for-weights, wait-for-activations cycles; [4..7] the
- * same for group B; [8] weight producer wait; [10],[11] group-A epilogue wait / work; [12],[13] group B. */
+ * same for group B; [8] weight producer wait; [10],[11] epilogue warp 0 wait / work. */
 int e55_debug_profile(e55_ctx* ctx, int enable, uint64_t* counters_out);
 
 /* Hardware self-test of the tcgen05 operand addressing this library depends on: one 128x128x64 bf16

@@ -11,6 +11,10 @@ from erweitern_55_b200.network import Network
 
 w = W.init_weights()
 net = Network(precision="bf16", weights=w)
+import os
+lag = int(os.environ.get("E55_LAG", "-1"))
+if lag >= 0:
+    net._check(net._lib.e55_debug_set_lag(net._ctx, lag))
 for n in [int(a) for a in sys.argv[1:]] or [8, 256, 1024]:
     x = torch.from_numpy(synth.synthetic_planes(n, seed=5)).cuda()
     pd = torch.empty((n, 1725), device="cuda"); vd = torch.empty((n, 1), device="cuda")
@@ -21,4 +25,17 @@ for n in [int(a) for a in sys.argv[1:]] or [8, 256, 1024]:
     net._check(net._lib.e55_debug_profile(net._ctx, 0, out))
     c = list(out)
     print(f"n={n}: issuerA total={c[0]} issue={c[1]} wait_full={c[2]} wait_act={c[3]} | issuerB total={c[4]} issue={c[5]} "
-          f"wait_full={c[6]} wait_act={c[7]} | producer wait={c[8]} | epiA wait={c[10]} work={c[11]} | epiB wait={c[12]} work={c[13]}", flush=True)
+          f"wait_full={c[6]} wait_act={c[7]} | producer wait={c[8]} | epi wait={c[10]} work={c[11]}", flush=True)
+    st = torch.cuda.ExternalStream(net.cuda_stream())
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        net.predict_device(x, pd, vd)
+    net.sync()
+    with torch.cuda.stream(st):
+        e0.record(st)
+        for _ in range(20):
+            net.predict_device(x, pd, vd)
+        e1.record(st)
+    net.sync()
+    ms = e0.elapsed_time(e1) / 20
+    print(f"   lag={lag} n={n}: {ms*1e3:.1f} us/forward  {n/ms*1e3:.0f} evals/s", flush=True)
