@@ -1,35 +1,46 @@
 // Tensor-core path: the whole network (stem, residual tower, policy conv, policy 1x1, value head) for
-// a batch of positions in ONE persistent, warp-specialised sm_100a kernel.
+// a batch of positions in ONE persistent, warp-specialised sm_100a kernel running on CTA pairs.
 //
 // Restates network.py:87-146 with BatchNorm folded into bf16 weights.  Every 3x3 convolution is an
 // implicit GEMM on tcgen05:  D[row, cout] += A[row + shift(tap), cin] * W[tap][cin, cout]
 //
 //   * rows  = squares of a "wide board": 4 positions side by side, each 5 squares + 1 zero column wide,
-//             5 board rows -> row = y*24 + p*6 + x  (120 rows, one UMMA M=128 tile).  A 3x3 tap is then
+//             5 board rows -> row = y*24 + p*6 + x  (120 rows, one 128-row UMMA tile).  A 3x3 tap is then
 //             the constant row displacement (dy*24 + dx); the zero columns and 25 zero guard rows
 //             above/below supply the 'same' padding.  M efficiency = 100/128.
 //   * A     = activations, bf16, resident in shared memory for the whole network, stored as 16 channel
 //             planes [plane = c/8][row][c%8]: the no-swizzle K-major UMMA layout with SBO = 128 B, in
 //             which rows are linear, so a tap is just start-address + shift*16 B (e55_selftest_umma).
-//   * B     = weights, bf16, pre-packed on the host into the same layout per (tap, 64-channel) chunk
-//             and streamed L2 -> smem by bulk TMA through an 8-stage mbarrier ring.
-//   * D     = fp32 accumulators in TMEM (128 lanes = rows, 128 columns = output channels).
+//   * B     = weights, bf16, pre-packed on the host into the same layout per chunk (board row of taps x
+//             32-channel K block) and streamed L2 -> smem by bulk TMA through a 10-stage mbarrier ring.
+//   * D     = fp32 accumulators in TMEM (128 lanes = rows, 128 columns = output channels), two per group
+//             (layer parity) so the next layer's MMAs start while the epilogue still drains the last one.
 //
-// A CTA evaluates 8 positions per round as two independent 4-position groups A and B.  Both groups
-// consume the SAME weight stream (a ring stage is released after both have used it); the single MMA
-// thread gives group A priority, so A runs up to 7 chunks ahead of B and the epilogue of one group
-// (TMEM -> +bias (+residual) -> ReLU -> bf16 -> smem, in place) overlaps the other group's MMAs.
-// The residual operand never leaves registers: the epilogue thread that owns a row keeps its block
-// input as 64 packed bf16x2 registers.
+// CTA pair (cta_group::2).  A 128x128x16 SS-mode UMMA issued by one CTA reads 4 KB of A and 4 KB of B per
+// 64 cycles = the full 128 B/clk of shared-memory bandwidth, so weight-ring writes and epilogue traffic
+// would steal tensor throughput.  Two CTAs therefore pair up: each holds (and streams) only HALF of every
+// weight chunk (64 of the 128 output channels) and the leader CTA issues M=256 UMMAs that cover one
+// 128-row tile of each CTA: 96 B/clk per SM, half the L2->SM weight traffic, twice the ring depth.
 //
-// Warp roles (352 threads): warps 0-3 epilogue of group A (TMEM lane quadrant = warp%4), warps 4-7
-// epilogue of group B, warp 8 weight producer (TMA), warp 9 MMA issuer, warp 10 stem-input loader (TMA).
+// Each CTA evaluates 8 positions per round as two independent 4-position groups A and B (so a pair does
+// 16 positions per round).  Both groups consume the SAME weight stream (a ring stage is released after
+// both used it); the epilogue of one group (TMEM -> +bias (+residual) -> ReLU -> bf16 -> smem, in place)
+// overlaps the other group's MMAs, and it is progressive: each finished 32-channel K block of the new
+// activations is signalled separately and the next layer's chunks are ordered K-block-major.
+// The residual operand never leaves registers: the thread that owns a row keeps its block input as packed
+// bf16x2 registers.  The fp32 -> bf16 conversion of the network input is fused (epilogue warps).
+//
+// Warp roles per CTA (352 threads): warps 0-7 epilogue + input conversion, shared by both groups (TMEM
+// lane quadrant = warp%4, 64-channel half = warp/4); warp 8 weight producer (bulk TMA, own half);
+// warps 9 / 10: in the leader CTA the MMA issuers of group A / B, in the peer CTA warp 9 relays
+// "my half of the stage has landed" to the leader.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include <algorithm>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -41,19 +52,19 @@ namespace tc {
 // ---- geometry -----------------------------------------------------------------------------------
 constexpr int kF = 128;                // tower width this kernel is specialised for
 constexpr int kPosPerGroup = 4;
-constexpr int kPosPerRound = 8;
+constexpr int kPosPerRound = 8;        // per CTA; a pair does 16
 constexpr int kW = 24;                 // wide-board width
 constexpr int kRowsValid = 120;        // 5 * kW
-constexpr int kTile = 128;             // UMMA M
+constexpr int kTile = 128;             // rows per CTA tile (UMMA M = 256 across the pair)
 constexpr int kGuard = 25;             // kW + 1
 constexpr int kRowsTotal = kGuard + kTile + kGuard + kTile + kGuard;  // 331
 constexpr int kPlanes = kF / 8;        // 16
 constexpr int kPlaneBytes = kRowsTotal * 16;
 constexpr int kActBytes = kPlanes * kPlaneBytes;                       // 84,736
-constexpr int kMaxStages = 5;
-constexpr int kStageBytes = 24576;     // one chunk: 3 taps (dx = -1,0,1) x 2 K-steps x 128 x 16 x 2 B
+constexpr int kMaxStages = 10;
+constexpr int kStageBytes = 12288;     // this CTA's half of a chunk: 3 taps x 2 K-steps x 64 x 16 x 2 B
 constexpr int kPolicyCh = 69;
-constexpr int kPolicyN = 80;           // policy 1x1 output channels padded to a legal UMMA N
+constexpr int kPolicyN = 96;           // policy 1x1 output channels padded (each CTA holds N/2 = 48 columns)
 constexpr int kSq = 25;
 constexpr int kThreads = 352;
 constexpr int kTmemCols = 512;         // 2 groups x 2 accumulators (layer parity) x 128 columns
@@ -67,9 +78,11 @@ enum : uint32_t { kRelu = 1, kHasRes = 2, kUpdRes = 4, kValueTap = 8, kFinal = 1
 // One ring stage worth of weights: the taps of one board row (dx = -1,0,1; or the single tap of a 1x1
 // layer) for one 32-channel K block of one input slice.  Within a layer chunks are ordered K-block-major,
 // so the MMAs of K block kb only need activation planes 4kb..4kb+3 of the previous layer's epilogue.
+// In the weight image the two 64-column halves of a chunk follow each other (CTA rank 0, then rank 1).
 struct alignas(16) Chunk {
   uint32_t gofs;     // byte offset into the weight image
-  uint32_t bytes;    // ntaps * nk * 2 * ndim * 16
+  uint16_t half16;   // bytes of one CTA's half, in 16 B units: ntaps * nk * 2 * (ndim/2)
+  uint16_t lend;     // chunk index one past the end of this chunk's layer
   int16_t a_off;     // A-descriptor displacement in 16 B units: kplane * rows + dy * board width
   uint8_t nk;        // K=16 steps per tap in this chunk
   uint8_t ntaps;     // 3 (dx = -1,0,1) or 1
@@ -105,11 +118,11 @@ struct Params {
   int nlayers;               // layers of the full network (tower convs + policy conv + policy 1x1)
   int nlayers_run;           // == nlayers, or fewer for a debug dump
   int n;                     // positions
-  int nrounds;
+  int nrounds;               // ceil(n / 8)
   float* policy;             // [n][1725]
   float* value;              // [n]
   uint4* dbg;                // [rounds*2][16][128] packed activations after layer nlayers_run-1
-  unsigned long long* prof;  // optional [16] cycle counters of CTA 0 (kProf instantiation only)
+  unsigned long long* prof;  // optional cycle counters / timeline of CTA 0 (kProf instantiation only)
 };
 
 // debug: packed activations [group][16][128 rows][8] bf16 -> fp32 NCHW [n][128][25]
@@ -132,32 +145,33 @@ __global__ void unpack_debug_kernel(const uint4* __restrict__ dbg, float* __rest
 __device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 
-// ---- the tower kernel ---------------------------------------------------------------------------
-struct SmemLayout {
-  static constexpr int ring = 0;
-  __host__ __device__ static constexpr int act(int nstages) { return ring + nstages * kStageBytes; }
-};
-
-// D[tmem] (+)= A * B^T with descriptors given as (lo, hi) words.
-__device__ __forceinline__ void umma_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+// D[tmem] (+)= A * B^T across the CTA pair (M = 256), descriptors given as (lo, hi) words.
+__device__ __forceinline__ void umma_pair(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\t"
       "mov.b64 da, {%1, %3};\n\t"
       "mov.b64 db, {%2, %3};\n\t"
       "setp.ne.b32 p, %5, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n" ::"r"(tmem_d),
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}\n" ::"r"(tmem_d),
       "r"(a_lo), "r"(b_lo), "r"(kDescHi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 
-// Epilogue of one 128x128 accumulator tile for the thread that owns `row`:
+// arrive on the leader CTA's copy of `bar` (plain local arrive when this CTA is the leader)
+__device__ __forceinline__ void arrive_on_leader(uint64_t* bar, uint32_t rank) {
+  if (rank == 0) ptx::mbar_arrive(bar);
+  else ptx::mbar_arrive_cluster(bar, 0);
+}
+
+// Epilogue of one 64-channel half of a 128x128 accumulator tile for the thread that owns `row`:
 // TMEM -> +bias (+residual) -> ReLU -> bf16 -> shared memory (in place: the next layer's A operand).
+// taddr / bias / act_row / s_wv / dbg_row / bar_part already point at this thread's half.
 template <bool kRes, bool kUpd, bool kVal>
 __device__ __forceinline__ float epilogue_half(uint32_t taddr, const float* __restrict__ bias, uint8_t* act_row,
                                                uint32_t (&res)[kF / 4], const float* __restrict__ s_wv,
-                                               bool row_valid, uint4* dbg_row, uint64_t* bar_part, int lane) {
-  // taddr / bias / act_row / s_wv / dbg_row / bar_part already point at this thread's 64-channel half
+                                               bool row_valid, uint4* dbg_row, uint64_t* bar_part, int lane,
+                                               uint32_t rank) {
   float vacc = 0.f;
   uint32_t v[2][32];
   ptx::tmem_ld_32x32b_x32(taddr, v[0]);
@@ -194,17 +208,22 @@ __device__ __forceinline__ float epilogue_half(uint32_t taddr, const float* __re
         if (dbg_row) dbg_row[(cb * 4 + j4) * kTile] = pk;
       }
     }
-    // this 32-channel K block of the new activations is complete: the next layer's MMAs on it may start
+    // this 32-channel K block of the new activations is complete: tell the leader's MMA issuer
     ptx::tc_fence_before_sync();
     ptx::fence_proxy_async_smem();
     __syncwarp();
-    if (lane == 0) ptx::mbar_arrive(&bar_part[cb]);
+    if (lane == 0) arrive_on_leader(&bar_part[cb], rank);
   }
   return vacc;
 }
 
+struct SmemLayout {
+  static constexpr int ring = 0;
+  __host__ __device__ static constexpr int act(int nstages) { return ring + nstages * kStageBytes; }
+};
+
 template <bool kProf>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 tower_kernel(const Params prm) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* s_ring = smem + SmemLayout::ring;
@@ -216,19 +235,23 @@ tower_kernel(const Params prm) {
   Chunk* s_chunks = reinterpret_cast<Chunk*>(s_part + 32);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_chunks + prm.nchunks_total);
   const uint32_t nstages = prm.nstages;
-  uint64_t* bar_full = bars;                     // [nstages]
-  uint64_t* bar_empty = bars + kMaxStages;       // [nstages]
-  uint64_t* bar_tmem_full = bars + 2 * kMaxStages;  // [2]
-  uint64_t* bar_act_part = bar_tmem_full + 2;    // [2 groups][4 K blocks of 32 channels]
-  uint64_t* bar_in_full = bar_act_part + 8;      // [2]
-  uint64_t* bar_in_empty = bar_in_full + 2;      // [2]
+  // identical layout in both CTAs (multicast commits and remote arrives address barriers by offset)
+  uint64_t* bar_full = bars;                          // [stages] stage landed (leader: both CTAs' halves)
+  uint64_t* bar_empty = bars + kMaxStages;            // [stages] both groups' MMAs on the stage are done
+  uint64_t* bar_tmem_full = bars + 2 * kMaxStages;    // [2] accumulator of a group complete
+  uint64_t* bar_act_part = bar_tmem_full + 2;         // [2][4] leader only: K block written by both CTAs
+  uint64_t* bar_in_full = bar_act_part + 8;           // [2] leader only: stem input slice written
+  uint64_t* bar_in_empty = bar_in_full + 2;           // [2] stem input planes may be overwritten
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_in_empty + 2);
-  volatile uint32_t* s_apos = s_tmem + 1;        // chunks issued so far by group A's issuer
+  volatile uint32_t* s_apos = s_tmem + 1;             // chunks issued so far by group A's issuer
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
   const int nl = prm.nlayers_run;
   const uint32_t nchunks = prm.layers[nl - 1].chunk_end;
+  const int pair0 = blockIdx.x >> 1, pair_stride = gridDim.x >> 1;
+  const int npair_rounds = (prm.nrounds + 1) >> 1;    // a pair-round = one round in each CTA
 
   // ---- one-time setup -----------------------------------------------------------------------
   for (int i = threadIdx.x; i < kActBytes / 16; i += kThreads)
@@ -239,46 +262,61 @@ tower_kernel(const Params prm) {
   if (threadIdx.x == 0) {
     *s_apos = 0u;
     for (uint32_t s = 0; s < nstages; ++s) {
-      ptx::mbar_init(&bar_full[s], 1);
+      ptx::mbar_init(&bar_full[s], rank == 0 ? 2 : 1);   // leader: own TMA + the peer's relay
       ptx::mbar_init(&bar_empty[s], 2);
     }
     for (int g = 0; g < 2; ++g) {
       ptx::mbar_init(&bar_tmem_full[g], 1);
-      for (int kb = 0; kb < 4; ++kb) ptx::mbar_init(&bar_act_part[g * 4 + kb], 4);
-      ptx::mbar_init(&bar_in_full[g], 8);
+      for (int kb = 0; kb < 4; ++kb) ptx::mbar_init(&bar_act_part[g * 4 + kb], 8);   // 4 warps x 2 CTAs
+      ptx::mbar_init(&bar_in_full[g], 16);                                           // 8 warps x 2 CTAs
       ptx::mbar_init(&bar_in_empty[g], 1);
     }
     ptx::fence_mbar_init();
   }
-  if (warp == 9) ptx::tmem_alloc<kTmemCols>(s_tmem);
+  if (warp == 9) ptx::tmem_alloc_2sm<kTmemCols>(s_tmem);
   ptx::fence_proxy_async_smem();
   ptx::tc_fence_before_sync();
   __syncthreads();
+  ptx::cluster_sync();   // the peer's barriers are initialised before anyone arrives on them remotely
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *s_tmem;
 
   if (warp == 8) {
-    // ===== weight producer ===================================================================
+    // ===== weight producer: this CTA's half (64 output channels) of every chunk ==================
     if (lane == 0) {
       uint32_t s = 0, ph = 1;
       long long t_wait = 0;
-      for (int r = blockIdx.x; r < prm.nrounds; r += gridDim.x) {
+      for (int pr = pair0; pr < npair_rounds; pr += pair_stride) {
         for (uint32_t c = 0; c < nchunks; ++c) {
           const Chunk ch = s_chunks[c];
           long long t0 = 0;
           if (kProf) t0 = clock64();
           ptx::mbar_wait(&bar_empty[s], ph);
           if (kProf) t_wait += clock64() - t0;
-          ptx::mbar_arrive_expect_tx(&bar_full[s], ch.bytes);
-          ptx::tma_bulk_g2s(s_ring + s * kStageBytes, prm.wimg + ch.gofs, ch.bytes, &bar_full[s]);
+          const uint32_t bytes = static_cast<uint32_t>(ch.half16) * 16u;
+          ptx::mbar_arrive_expect_tx(&bar_full[s], bytes);
+          ptx::tma_bulk_g2s(s_ring + s * kStageBytes, prm.wimg + ch.gofs + rank * bytes, bytes, &bar_full[s]);
           if (++s == nstages) { s = 0; ph ^= 1; }
         }
       }
       if (kProf && blockIdx.x == 0) prm.prof[8] = t_wait;
     }
-  } else if (warp == 9 || warp == 10) {
-    // ===== MMA issuers: warp 9 drives group A, warp 10 group B (warp-uniform loop, one elected lane
-    // issues).  Both walk the same chunk sequence; a ring stage is released after both used it. =====
+  } else if (warp == 9 && rank == 1) {
+    // ===== peer CTA: relay "my half of stage s has landed" to the leader's issuers ==================
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0;
+      for (int pr = pair0; pr < npair_rounds; pr += pair_stride) {
+        for (uint32_t c = 0; c < nchunks; ++c) {
+          ptx::mbar_wait(&bar_full[s], ph);
+          ptx::mbar_arrive_cluster(&bar_full[s], 0);
+          if (++s == nstages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if ((warp == 9 || warp == 10) && rank == 0) {
+    // ===== MMA issuers (leader CTA): warp 9 drives group A, warp 10 group B, for BOTH CTAs' tiles
+    // (cta_group::2, M = 256).  Warp-uniform loop, one elected lane issues.  Both walk the same chunk
+    // sequence; a ring stage is released (in both CTAs) after both groups used it. ==================
     const int g = warp == 9 ? 0 : 1;
     const uint32_t a_lo_base = ((ptx::smem_u32(s_act) + group_origin_row(g) * 16) >> 4) |
                                (static_cast<uint32_t>(kPlaneBytes >> 4) << 16);
@@ -286,9 +324,9 @@ tower_kernel(const Params prm) {
     uint32_t s = 0, ph = 0, round_seq = 0;
     long long t_start = 0, t_issue = 0, t_full = 0, t_act = 0;
     if (kProf) t_start = clock64();
-    for (int r = blockIdx.x; r < prm.nrounds; r += gridDim.x, ++round_seq) {
-      const bool has_b = r * kPosPerRound + kPosPerGroup < prm.n;
-      if (g == 1 && !has_b) break;  // only the last round can lack group B
+    for (int pr = pair0; pr < npair_rounds; pr += pair_stride, ++round_seq) {
+      const bool has_b = pr * 2 * kPosPerRound + kPosPerGroup < prm.n;
+      if (g == 1 && !has_b) break;  // only the last pair-round can lack group B
       const uint32_t gbase = round_seq * nchunks;
       for (uint32_t c = 0; c < nchunks; ++c) {
         const Chunk ch = s_chunks[c];
@@ -296,56 +334,56 @@ tower_kernel(const Params prm) {
         if (kProf) t0 = clock64();
         if (g == 1 && prm.lag > 0) {
           // Keep group A `lag` chunks ahead so that one group's epilogue overlaps the other group's
-          // MMAs; once A has finished B's current layer (A is then in its own epilogue or further on)
-          // B runs freely to the end of that layer.
-          const uint32_t want = min(gbase + c + 1 + prm.lag, gbase + static_cast<uint32_t>(prm.layers[ch.layer].chunk_end));
+          // MMAs; once A has finished B's current layer B runs freely to the end of that layer.
+          const uint32_t want = min(gbase + c + 1 + prm.lag, gbase + static_cast<uint32_t>(ch.lend));
           while (*s_apos < want) {
           }
         }
-        ptx::mbar_wait(&bar_full[s], ph);
+        ptx::mbar_wait_cluster(&bar_full[s], ph);
         if (kProf) t1 = clock64();
         const uint32_t epoch = round_seq * nl + ch.layer;
         if ((ch.flags & kFirstOfSlice) && ch.layer == 0)
-          ptx::mbar_wait(&bar_in_full[g], (round_seq * prm.nslices + ch.slice) & 1);
+          ptx::mbar_wait_cluster(&bar_in_full[g], (round_seq * prm.nslices + ch.slice) & 1);
         if ((ch.flags >> 4) && epoch > 0) {
-          // activation K blocks written by the previous layer's (progressive) epilogue
+          // activation K blocks written by the previous layer's (progressive) epilogue in both CTAs
 #pragma unroll
           for (int kb = 0; kb < 4; ++kb)
-            if ((ch.flags >> 4) & (1u << kb)) ptx::mbar_wait(&bar_act_part[g * 4 + kb], (epoch - 1) & 1);
+            if ((ch.flags >> 4) & (1u << kb)) ptx::mbar_wait_cluster(&bar_act_part[g * 4 + kb], (epoch - 1) & 1);
         }
         if (kProf) t2 = clock64();
         ptx::tc_fence_after_sync();
         if (ptx::elect_one()) {
           const uint32_t ndim = ch.ndim8 * 8u;
-          const uint32_t idesc = ptx::umma_idesc_bf16_f32(kTile, ndim);
+          const uint32_t idesc = ptx::umma_idesc_bf16_f32(2 * kTile, ndim);
           const uint32_t d = tmem_base + (g * 2 + (ch.layer & 1)) * kF;
           const uint32_t a_chunk = a_lo_base + static_cast<int>(ch.a_off) - (ch.ntaps == 3 ? 1 : 0);
-          uint32_t b_lo = (b_lo_base + s * (kStageBytes >> 4)) | (ndim << 16);
+          const uint32_t b_step = ndim;                          // 2 planes x (ndim/2 rows) x 16 B, in 16 B units
+          uint32_t b_lo = (b_lo_base + s * (kStageBytes >> 4)) | ((ndim >> 1) << 16);   // LBO = (ndim/2) x 16 B
           uint32_t acc = (ch.flags & kFirstOfLayer) ? 0u : 1u;
           if (ch.ntaps == 3 && ch.nk == 2) {
 #pragma unroll
             for (int t = 0; t < 3; ++t)
 #pragma unroll
               for (int ks = 0; ks < 2; ++ks) {
-                umma_lohi(d, a_chunk + t + ks * 2 * (kPlaneBytes >> 4), b_lo, idesc, acc);
+                umma_pair(d, a_chunk + t + ks * 2 * (kPlaneBytes >> 4), b_lo, idesc, acc);
                 acc = 1u;
-                b_lo += 2 * ndim;
+                b_lo += b_step;
               }
           } else {
             for (int t = 0; t < ch.ntaps; ++t)
               for (int ks = 0; ks < ch.nk; ++ks) {
-                umma_lohi(d, a_chunk + t + ks * 2 * (kPlaneBytes >> 4), b_lo, idesc, acc);
+                umma_pair(d, a_chunk + t + ks * 2 * (kPlaneBytes >> 4), b_lo, idesc, acc);
                 acc = 1u;
-                b_lo += 2 * ndim;
+                b_lo += b_step;
               }
           }
-          ptx::umma_commit(&bar_empty[s]);
-          if (!has_b) ptx::umma_commit(&bar_empty[s]);
+          ptx::umma_commit_2sm(&bar_empty[s], 3);
+          if (!has_b) ptx::umma_commit_2sm(&bar_empty[s], 3);
           if ((ch.flags & kLastOfSlice) && ch.layer == 0 && ch.slice + 1 < prm.nslices)
-            ptx::umma_commit(&bar_in_empty[g]);
+            ptx::umma_commit_2sm(&bar_in_empty[g], 3);
           if (ch.flags & kLastOfLayer) {
-            ptx::umma_commit(&bar_tmem_full[g]);
-            if (ch.layer == nl - 1) ptx::umma_commit(&bar_in_empty[g]);
+            ptx::umma_commit_2sm(&bar_tmem_full[g], 3);
+            if (ch.layer == nl - 1) ptx::umma_commit_2sm(&bar_in_empty[g], 3);
           }
         }
         __syncwarp();
@@ -365,9 +403,10 @@ tower_kernel(const Params prm) {
       unsigned long long* o = prm.prof + (g ? 4 : 0);
       o[0] = clock64() - t_start; o[1] = t_issue; o[2] = t_full; o[3] = t_act;
     }
-  } else {
+  } else if (warp < 8) {
     // ===== epilogue warps 0-7, shared by both groups: warp w owns TMEM lane quadrant w%4 (32 tile rows)
-    // and the 64-channel half w/4 of whichever group's accumulator is complete. =====================
+    // and the 64-channel half w/4 of whichever group's accumulator is complete; they also convert the
+    // fp32 network input into the bf16 wide-board planes (stem input slices). =======================
     const int q = warp & 3;
     const int h = warp >> 2;
     const int row = q * 32 + lane;                       // TMEM lane == tile row
@@ -381,8 +420,9 @@ tower_kernel(const Params prm) {
     uint32_t slices_done[2] = {0u, 0u};
     long long t_wait = 0, t_work = 0;
 
-    for (int r = blockIdx.x; r < prm.nrounds; r += gridDim.x, ++round_seq) {
-      const bool has_b = r * kPosPerRound + kPosPerGroup < prm.n;
+    for (int pr = pair0; pr < npair_rounds; pr += pair_stride, ++round_seq) {
+      const int r = pr * 2 + static_cast<int>(rank);     // this CTA's round (may lie past the batch: all absent)
+      const bool has_b = pr * 2 * kPosPerRound + kPosPerGroup < prm.n;
       int next_layer[2] = {0, has_b ? 0 : nl};
       int next_slice[2] = {0, has_b ? 0 : prm.nslices};
       while (next_layer[0] < nl || next_layer[1] < nl) {
@@ -420,7 +460,7 @@ tower_kernel(const Params prm) {
           }
           ptx::fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&bar_in_full[g]);
+          if (lane == 0) arrive_on_leader(&bar_in_full[g], rank);
           next_slice[g] = sl + 1;
           ++slices_done[g];
           continue;
@@ -437,20 +477,20 @@ tower_kernel(const Params prm) {
 
         if (!(lf & kFinal)) {
           uint8_t* act_row = s_act + (h * 8) * kPlaneBytes + (group_origin_row(g) + row) * 16;
-          uint4* dbg_row = (prm.dbg != nullptr && L == nl - 1)
+          uint4* dbg_row = (prm.dbg != nullptr && L == nl - 1 && pos_base < prm.n)
                                ? prm.dbg + (static_cast<size_t>(r * 2 + g) * kPlanes + h * 8) * kTile + row : nullptr;
           const float* wv = s_wv + h * 64;
           float vacc = 0.f;
 #define E55_EPI(RES)                                                                                          \
           if (lf & kValueTap) {                                                                               \
-            if (lf & kHasRes) vacc = epilogue_half<true, true, true>(taddr, bias, act_row, RES, wv, row_valid, dbg_row, bar_part, lane);   \
-            else vacc = epilogue_half<false, true, true>(taddr, bias, act_row, RES, wv, row_valid, dbg_row, bar_part, lane);  \
+            if (lf & kHasRes) vacc = epilogue_half<true, true, true>(taddr, bias, act_row, RES, wv, row_valid, dbg_row, bar_part, lane, rank);   \
+            else vacc = epilogue_half<false, true, true>(taddr, bias, act_row, RES, wv, row_valid, dbg_row, bar_part, lane, rank);  \
           } else if (lf & kHasRes) {                                                                          \
-            epilogue_half<true, true, false>(taddr, bias, act_row, RES, wv, row_valid, dbg_row, bar_part, lane);              \
+            epilogue_half<true, true, false>(taddr, bias, act_row, RES, wv, row_valid, dbg_row, bar_part, lane, rank);              \
           } else if (lf & kUpdRes) {                                                                          \
-            epilogue_half<false, true, false>(taddr, bias, act_row, RES, wv, row_valid, dbg_row, bar_part, lane);             \
+            epilogue_half<false, true, false>(taddr, bias, act_row, RES, wv, row_valid, dbg_row, bar_part, lane, rank);             \
           } else {                                                                                            \
-            epilogue_half<false, false, false>(taddr, bias, act_row, RES, wv, row_valid, dbg_row, bar_part, lane);            \
+            epilogue_half<false, false, false>(taddr, bias, act_row, RES, wv, row_valid, dbg_row, bar_part, lane, rank);            \
           }
           if (g == 0) { E55_EPI(res_a) } else { E55_EPI(res_b) }
 #undef E55_EPI
@@ -463,7 +503,7 @@ tower_kernel(const Params prm) {
           float* dst = prm.policy + static_cast<size_t>(pos) * (kPolicyCh * kSq) + sq;
 #pragma unroll
           for (int cb = 0; cb < 2; ++cb) {
-            if (h == 1 && cb == 1) break;  // channels 96.. do not exist (N = 80)
+            if (h == 1 && cb == 1) break;  // channels 96.. do not exist
             uint32_t v[32];
             ptx::tmem_ld_32x32b_x32(taddr + cb * 32, v);
             ptx::tmem_ld_wait();
@@ -475,11 +515,10 @@ tower_kernel(const Params prm) {
               }
             }
           }
-        }
-        if (lf & kFinal) {  // no activations written, but keep the per-layer barrier phases in step
+          // no activations written, but keep the per-layer barrier phases in step
           ptx::tc_fence_before_sync();
           __syncwarp();
-          if (lane == 0) { ptx::mbar_arrive(&bar_part[0]); ptx::mbar_arrive(&bar_part[1]); }
+          if (lane == 0) { arrive_on_leader(&bar_part[0], rank); arrive_on_leader(&bar_part[1], rank); }
         }
         if (kProf) {
           const long long te2 = clock64();
@@ -538,9 +577,11 @@ tower_kernel(const Params prm) {
     }
   }
 
+  // neither CTA may exit (or free TMEM) while the other can still signal its barriers / read its smem
   ptx::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 9) ptx::tmem_dealloc<kTmemCols>(tmem_base);
+  ptx::cluster_sync();
+  if (warp == 9) ptx::tmem_dealloc_2sm<kTmemCols>(tmem_base);
 }
 
 // =================================================================================================
@@ -594,7 +635,7 @@ inline void free_buffers(State& s) {
 inline cudaError_t alloc_buffers(State& s, int cap) {
   if (!supported(s)) return cudaSuccess;
   free_buffers(s);
-  const size_t groups = (static_cast<size_t>(cap) + kPosPerGroup - 1) / kPosPerGroup + 1;
+  const size_t groups = (static_cast<size_t>(cap) + kPosPerGroup - 1) / kPosPerGroup + 4;
   cudaError_t e = cudaMalloc(&s.d_dbg, groups * kPlanes * kTile * sizeof(uint4));
   if (e != cudaSuccess) return e;
   s.capacity = cap;
@@ -621,12 +662,13 @@ inline cudaError_t set_weights(State& s, const std::vector<std::vector<float>>& 
   std::vector<float> bias(static_cast<size_t>(s.nlayers) * kF, 0.f);
   s.layers.assign(s.nlayers, LayerInfo{});
 
-  // chunk = (layer, slice, K block kb of <= 32 channels, board row dy): ntaps taps x nk K-steps
+  // chunk = (layer, slice, K block kb of <= 32 channels, board row dy): ntaps taps x nk K-steps.
+  // image: [half: cout 0..ndim/2-1 | ndim/2..ndim-1][tap][plane j][n within half][8 channels]
   auto emit = [&](int layer, int slice, int tap0, int ntaps, int total_taps, int ch0, int kplane, int nk, int ndim,
                   int cin, int cout, const float* w, uint32_t flags, uint32_t need) {
     Chunk ch{};
     ch.gofs = static_cast<uint32_t>(img.size() * 2);
-    ch.bytes = static_cast<uint32_t>(ntaps * nk * 2 * ndim * 16);
+    ch.half16 = static_cast<uint16_t>(ntaps * nk * 2 * (ndim / 2));
     const int dy = total_taps == 9 ? tap0 / 3 - 1 : 0;
     ch.a_off = static_cast<int16_t>(kplane * kRowsTotal + dy * kW);
     ch.nk = static_cast<uint8_t>(nk);
@@ -635,15 +677,16 @@ inline cudaError_t set_weights(State& s, const std::vector<std::vector<float>>& 
     ch.flags = static_cast<uint8_t>(flags | (need << 4));
     ch.layer = static_cast<uint8_t>(layer);
     ch.slice = static_cast<uint8_t>(slice);
-    // image: [tap][plane j][n][8 channels]
-    for (int t = 0; t < ntaps; ++t)
-      for (int j = 0; j < nk * 2; ++j)
-        for (int n = 0; n < ndim; ++n)
-          for (int e = 0; e < 8; ++e) {
-            const int ci = ch0 + j * 8 + e;
-            const float v = (ci < cin && n < cout) ? w[(static_cast<size_t>(tap0 + t) * cin + ci) * cout + n] : 0.f;
-            img.push_back(f32_to_bf16_rne(v));
-          }
+    for (int half = 0; half < 2; ++half)
+      for (int t = 0; t < ntaps; ++t)
+        for (int j = 0; j < nk * 2; ++j)
+          for (int nn = 0; nn < ndim / 2; ++nn)
+            for (int e = 0; e < 8; ++e) {
+              const int ci = ch0 + j * 8 + e;
+              const int n = half * (ndim / 2) + nn;
+              const float v = (ci < cin && n < cout) ? w[(static_cast<size_t>(tap0 + t) * cin + ci) * cout + n] : 0.f;
+              img.push_back(f32_to_bf16_rne(v));
+            }
     chunks.push_back(ch);
   };
 
@@ -696,6 +739,7 @@ inline cudaError_t set_weights(State& s, const std::vector<std::vector<float>>& 
       }
     }
     li.chunk_end = static_cast<int>(chunks.size());
+    for (int c = li.chunk_begin; c < li.chunk_end; ++c) chunks[c].lend = static_cast<uint16_t>(li.chunk_end);
   }
 
   cudaError_t e;
@@ -710,7 +754,7 @@ inline cudaError_t set_weights(State& s, const std::vector<std::vector<float>>& 
 
   s.nchunks = static_cast<int>(chunks.size());
   const size_t fixed = kActBytes + static_cast<size_t>(s.nlayers) * kF * 4 + kF * 4 + 4 * kPosPerGroup * kSq * 4 + 32 * 4 +
-                       chunks.size() * sizeof(Chunk) + (2 * kMaxStages + 16) * 8 + 16;
+                       chunks.size() * sizeof(Chunk) + (3 * kMaxStages + 16) * 8 + 16;
   s.nstages = static_cast<int>(std::min<size_t>(kMaxStages, (232448 - std::min<size_t>(fixed, 232448)) / kStageBytes));
   s.smem_bytes = fixed + static_cast<size_t>(s.nstages) * kStageBytes;
   s.attr_set = false;
@@ -721,7 +765,7 @@ inline cudaError_t set_weights(State& s, const std::vector<std::vector<float>>& 
 inline cudaError_t run(State& s, const float* d_planes, int n, float* d_policy, float* d_value, int nlayers_run,
                        cudaStream_t stream, int* launched, std::string* why) {
   if (!supported(s)) { *why = "the tcgen05 path supports filters == 128 only"; return cudaSuccess; }
-  if (s.nstages < 2) { *why = "network too deep for the shared-memory layer tables"; return cudaSuccess; }
+  if (s.nstages < 3) { *why = "network too deep for the shared-memory layer tables"; return cudaSuccess; }
   if (!s.attr_set) {
     cudaError_t e = cudaFuncSetAttribute(tower_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(s.smem_bytes));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tower_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(s.smem_bytes));
@@ -734,12 +778,13 @@ inline cudaError_t run(State& s, const float* d_planes, int n, float* d_policy, 
   p.value_w = s.heads.d_value_w; p.fc1_k = s.heads.d_fc1_k; p.fc1_b = s.heads.d_fc1_b; p.fc2_k = s.heads.d_fc2_k;
   p.value_b = s.heads.value_b; p.fc2_b = s.heads.fc2_b;
   p.planes = d_planes; p.in_planes = s.in_planes; p.in_planes8 = s.in_planes8; p.nslices = s.nslices;
-  p.nstages = s.nstages; p.nchunks_total = s.nchunks; p.lag = std::min(s.lag, s.nstages - 1);
+  p.nstages = s.nstages; p.nchunks_total = s.nchunks; p.lag = std::min(s.lag, s.nstages - 2);
   p.nlayers = s.nlayers; p.nlayers_run = nlayers_run; p.n = n; p.nrounds = rounds;
   p.policy = d_policy; p.value = d_value;
   p.dbg = nlayers_run < s.nlayers ? s.d_dbg : nullptr;
   p.prof = s.d_prof;
-  const int grid = std::min(rounds, s.sms);
+  const int pairs = std::min((rounds + 1) / 2, std::max(1, s.sms / 2));
+  const int grid = 2 * pairs;
   if (s.ev0) cudaEventRecord(s.ev0, stream);
   if (p.prof) tower_kernel<true><<<grid, kThreads, s.smem_bytes, stream>>>(p);
   else tower_kernel<false><<<grid, kThreads, s.smem_bytes, stream>>>(p);

@@ -21,7 +21,7 @@ for n in [int(a) for a in sys.argv[1:]] or [8, 256, 1024]:
     net.predict_device(x, pd, vd); net.sync()
     net._check(net._lib.e55_debug_profile(net._ctx, 1, None))
     net.predict_device(x, pd, vd); net.sync()
-    out = (C.c_uint64 * 16)()
+    out = (C.c_uint64 * (16 + 8192 + 1024))()
     net._check(net._lib.e55_debug_profile(net._ctx, 0, out))
     c = list(out)
     print(f"n={n}: issuerA total={c[0]} issue={c[1]} wait_full={c[2]} wait_act={c[3]} | issuerB total={c[4]} issue={c[5]} "

@@ -25,10 +25,17 @@ ia = ia[ia[:, 0] > 0]; ib = ib[ib[:, 0] > 0]; ep = ep[ep[:, 0] > 0]
 t0 = min(ia[0, 0], ib[0, 0])
 print("chunks", len(ia), len(ib), "events", len(ep))
 print("issuer A: total", ia[-1, 3] - t0, " B:", ib[-1, 3] - t0)
-def fmt(r): return " ".join(f"{v - t0:7d}" for v in r)
-nch = len(ia)
-for c in list(range(0, 40)) + list(range(nch - 16, nch)):
-    print(f"c={c:3d} A[{fmt(ia[c])}] dWaitFull={ia[c,1]-ia[c,0]:5d} dWaitAct={ia[c,2]-ia[c,1]:5d} dIssue={ia[c,3]-ia[c,2]:5d} | B[{fmt(ib[c])}] dWF={ib[c,1]-ib[c,0]:5d} dWA={ib[c,2]-ib[c,1]:5d} dI={ib[c,3]-ib[c,2]:5d}")
+def stats(name, ia):
+    cad = np.diff(ia[:, 0])
+    print(f"{name}: cadence median={np.median(cad):.0f} mean={cad.mean():.0f} | waitFull med={np.median(ia[:,1]-ia[:,0]):.0f} sum={np.sum(ia[:,1]-ia[:,0])} "
+          f"| waitAct med={np.median(ia[:,2]-ia[:,1]):.0f} sum={np.sum(ia[:,2]-ia[:,1])} | issue med={np.median(ia[:,3]-ia[:,2]):.0f} sum={np.sum(ia[:,3]-ia[:,2])} "
+          f"| loop med={np.median(ia[1:,0]-ia[:-1,3]):.0f} sum={np.sum(ia[1:,0]-ia[:-1,3])}")
+stats("A", ia); stats("B", ib)
+big = [(c, int(ia[c,1]-ia[c,0]), int(ia[c,2]-ia[c,1])) for c in range(len(ia)) if ia[c,2]-ia[c,0] > 1000]
+print("A stalls >1000 (chunk, waitFull, waitAct):", big[:40])
+big = [(c, int(ib[c,1]-ib[c,0]), int(ib[c,2]-ib[c,1])) for c in range(len(ib)) if ib[c,2]-ib[c,0] > 1000]
+print("B stalls >1000:", big[:40])
 ep = ep[np.argsort(ep[:, 0])]
-for e in ep[:24]:
-    print(f"epi g={e[2]} L={e[3]:2d} ready={e[0]-t0:7d} done={e[1]-t0:7d} dur={e[1]-e[0]}")
+print("epilogue durations: median", np.median(ep[:,1]-ep[:,0]), "max", (ep[:,1]-ep[:,0]).max())
+for c in range(36, 64):
+    print(f"c={c:3d} A t0={ia[c,0]-t0:7d} wF={ia[c,1]-ia[c,0]:5d} wA={ia[c,2]-ia[c,1]:5d} is={ia[c,3]-ia[c,2]:5d} | B t0={ib[c,0]-t0:7d} wF={ib[c,1]-ib[c,0]:5d} wA={ib[c,2]-ib[c,1]:5d} is={ib[c,3]-ib[c,2]:5d}")
