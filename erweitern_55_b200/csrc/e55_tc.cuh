@@ -61,8 +61,8 @@ constexpr int kRowsTotal = kGuard + kTile + kGuard + kTile + kGuard;  // 331
 constexpr int kPlanes = kF / 8;        // 16
 constexpr int kPlaneBytes = kRowsTotal * 16;
 constexpr int kActBytes = kPlanes * kPlaneBytes;                       // 84,736
-constexpr int kMaxStages = 10;
-constexpr int kStageBytes = 12288;     // this CTA's half of a chunk: 3 taps x 2 K-steps x 64 x 16 x 2 B
+constexpr int kMaxStages = 5;
+constexpr int kStageBytes = 24576;     // this CTA's half of a chunk: 3 taps x 2 K blocks x 2 K-steps x 64 x 16 x 2 B
 constexpr int kPolicyCh = 69;
 constexpr int kPolicyN = 96;           // policy 1x1 output channels padded (each CTA holds N/2 = 48 columns)
 constexpr int kSq = 25;
@@ -76,20 +76,21 @@ enum : uint32_t { kFirstOfSlice = 1, kLastOfSlice = 2, kFirstOfLayer = 4, kLastO
 enum : uint32_t { kRelu = 1, kHasRes = 2, kUpdRes = 4, kValueTap = 8, kFinal = 16 };
 
 // One ring stage worth of weights: the taps of one board row (dx = -1,0,1; or the single tap of a 1x1
-// layer) for one 32-channel K block of one input slice.  Within a layer chunks are ordered K-block-major,
-// so the MMAs of K block kb only need activation planes 4kb..4kb+3 of the previous layer's epilogue.
+// layer) for a pair of 32-channel K blocks of one input slice.  The epilogue finishes K blocks 0 and 2
+// first (first 32 channels of each 64-channel half), then 1 and 3, so a layer's chunks come in that
+// order: {0,2} x 3 board rows, then {1,3} x 3 board rows; each chunk only needs "its" K blocks.
 // In the weight image the two 64-column halves of a chunk follow each other (CTA rank 0, then rank 1).
 struct alignas(16) Chunk {
   uint32_t gofs;     // byte offset into the weight image
-  uint16_t half16;   // bytes of one CTA's half, in 16 B units: ntaps * nk * 2 * (ndim/2)
+  uint16_t half16;   // bytes of one CTA's half, in 16 B units
   uint16_t lend;     // chunk index one past the end of this chunk's layer
-  int16_t a_off;     // A-descriptor displacement in 16 B units: kplane * rows + dy * board width
-  uint8_t nk;        // K=16 steps per tap in this chunk
+  int16_t a_off;     // A-descriptor displacement in 16 B units: first plane * rows + dy * board width
+  uint8_t nk0;       // K=16 steps per tap on the first K block (planes a_off..)
+  uint8_t nk1;       // K=16 steps per tap on the second K block, 8 planes further on (0 = none)
   uint8_t ntaps;     // 3 (dx = -1,0,1) or 1
   uint8_t ndim8;     // UMMA N / 8 of the layer
   uint8_t flags;     // low 4 bits: first/last of slice/layer; high 4 bits: activation K blocks required
   uint8_t layer;
-  uint8_t slice;
 };
 
 struct LayerInfo {
@@ -321,7 +322,7 @@ tower_kernel(const Params prm) {
     const uint32_t a_lo_base = ((ptx::smem_u32(s_act) + group_origin_row(g) * 16) >> 4) |
                                (static_cast<uint32_t>(kPlaneBytes >> 4) << 16);
     const uint32_t b_lo_base = ptx::smem_u32(s_ring) >> 4;
-    uint32_t s = 0, ph = 0, round_seq = 0;
+    uint32_t s = 0, ph = 0, round_seq = 0, stem_slices = 0;
     long long t_start = 0, t_issue = 0, t_full = 0, t_act = 0;
     if (kProf) t_start = clock64();
     for (int pr = pair0; pr < npair_rounds; pr += pair_stride, ++round_seq) {
@@ -342,8 +343,10 @@ tower_kernel(const Params prm) {
         ptx::mbar_wait_cluster(&bar_full[s], ph);
         if (kProf) t1 = clock64();
         const uint32_t epoch = round_seq * nl + ch.layer;
-        if ((ch.flags & kFirstOfSlice) && ch.layer == 0)
-          ptx::mbar_wait_cluster(&bar_in_full[g], (round_seq * prm.nslices + ch.slice) & 1);
+        if ((ch.flags & kFirstOfSlice) && ch.layer == 0) {
+          ptx::mbar_wait_cluster(&bar_in_full[g], stem_slices & 1);
+          ++stem_slices;
+        }
         if ((ch.flags >> 4) && epoch > 0) {
           // activation K blocks written by the previous layer's (progressive) epilogue in both CTAs
 #pragma unroll
@@ -360,26 +363,34 @@ tower_kernel(const Params prm) {
           const uint32_t b_step = ndim;                          // 2 planes x (ndim/2 rows) x 16 B, in 16 B units
           uint32_t b_lo = (b_lo_base + s * (kStageBytes >> 4)) | ((ndim >> 1) << 16);   // LBO = (ndim/2) x 16 B
           uint32_t acc = (ch.flags & kFirstOfLayer) ? 0u : 1u;
-          if (ch.ntaps == 3 && ch.nk == 2) {
+          constexpr uint32_t kStepK = 2 * (kPlaneBytes >> 4);    // one K=16 step = 2 planes
+          constexpr uint32_t kBlock2 = 8 * (kPlaneBytes >> 4);   // second K block of the chunk: 8 planes on
+          if (ch.ntaps == 3 && ch.nk0 == 2 && ch.nk1 == 2) {
 #pragma unroll
             for (int t = 0; t < 3; ++t)
 #pragma unroll
-              for (int ks = 0; ks < 2; ++ks) {
-                umma_pair(d, a_chunk + t + ks * 2 * (kPlaneBytes >> 4), b_lo, idesc, acc);
+              for (int k4 = 0; k4 < 4; ++k4) {
+                umma_pair(d, a_chunk + t + (k4 >> 1) * kBlock2 + (k4 & 1) * kStepK, b_lo, idesc, acc);
                 acc = 1u;
                 b_lo += b_step;
               }
           } else {
-            for (int t = 0; t < ch.ntaps; ++t)
-              for (int ks = 0; ks < ch.nk; ++ks) {
-                umma_pair(d, a_chunk + t + ks * 2 * (kPlaneBytes >> 4), b_lo, idesc, acc);
+            for (int t = 0; t < ch.ntaps; ++t) {
+              for (int ks = 0; ks < ch.nk0; ++ks) {
+                umma_pair(d, a_chunk + t + ks * kStepK, b_lo, idesc, acc);
                 acc = 1u;
                 b_lo += b_step;
               }
+              for (int ks = 0; ks < ch.nk1; ++ks) {
+                umma_pair(d, a_chunk + t + kBlock2 + ks * kStepK, b_lo, idesc, acc);
+                acc = 1u;
+                b_lo += b_step;
+              }
+            }
           }
           ptx::umma_commit_2sm(&bar_empty[s], 3);
           if (!has_b) ptx::umma_commit_2sm(&bar_empty[s], 3);
-          if ((ch.flags & kLastOfSlice) && ch.layer == 0 && ch.slice + 1 < prm.nslices)
+          if ((ch.flags & kLastOfSlice) && ch.layer == 0 && !(ch.flags & kLastOfLayer))
             ptx::umma_commit_2sm(&bar_in_empty[g], 3);
           if (ch.flags & kLastOfLayer) {
             ptx::umma_commit_2sm(&bar_tmem_full[g], 3);
@@ -444,19 +455,32 @@ tower_kernel(const Params prm) {
           const int pl0 = sl * kPlanes;
           const int npl = min(kPlanes, prm.in_planes8 - pl0);
           const int pos0 = r * kPosPerRound + g * kPosPerGroup;
-          for (int it = threadIdx.x; it < kPosPerGroup * npl * kSq; it += 256) {
-            const int s_ = it % kSq, c8 = (it / kSq) % npl, p = it / (kSq * npl);
-            uint4 pk = make_uint4(0u, 0u, 0u, 0u);
-            if (pos0 + p < prm.n) {
-              const float* src = prm.planes + (static_cast<size_t>(pos0 + p) * prm.in_planes + (pl0 + c8) * 8) * kSq + s_;
-              float f[8];
+          const int nitems = kPosPerGroup * npl * kSq;
+          for (int it0 = threadIdx.x; it0 < nitems; it0 += 256 * 4) {
+            float f[4][8];
+            // phase 1: issue every global load of up to 4 items before touching any result
 #pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = (pl0 + c8) * 8 + e < prm.in_planes ? __ldg(src + e * kSq) : 0.f;
-              pk = make_uint4(ptx::pack_bf16x2(f[0], f[1]), ptx::pack_bf16x2(f[2], f[3]),
-                              ptx::pack_bf16x2(f[4], f[5]), ptx::pack_bf16x2(f[6], f[7]));
+            for (int u = 0; u < 4; ++u) {
+              const int it = it0 + u * 256;
+              const int s_ = it % kSq, c8 = (it / kSq) % npl, p = it / (kSq * npl);
+              const bool live = it < nitems && pos0 + p < prm.n;
+              const float* src = prm.planes + (static_cast<size_t>(pos0 + p) * prm.in_planes + (pl0 + c8) * 8) * kSq + s_;
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                f[u][e] = (live && (pl0 + c8) * 8 + e < prm.in_planes) ? __ldg(src + e * kSq) : 0.f;
             }
-            const int rr = (s_ / 5) * kW + p * 6 + s_ % 5;
-            *reinterpret_cast<uint4*>(s_act + c8 * kPlaneBytes + (group_origin_row(g) + rr) * 16) = pk;
+            // phase 2: pack and store
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int it = it0 + u * 256;
+              if (it < nitems) {
+                const int s_ = it % kSq, c8 = (it / kSq) % npl, p = it / (kSq * npl);
+                const uint4 pk = make_uint4(ptx::pack_bf16x2(f[u][0], f[u][1]), ptx::pack_bf16x2(f[u][2], f[u][3]),
+                                            ptx::pack_bf16x2(f[u][4], f[u][5]), ptx::pack_bf16x2(f[u][6], f[u][7]));
+                const int rr = (s_ / 5) * kW + p * 6 + s_ % 5;
+                *reinterpret_cast<uint4*>(s_act + c8 * kPlaneBytes + (group_origin_row(g) + rr) * 16) = pk;
+              }
+            }
           }
           ptx::fence_proxy_async_smem();
           __syncwarp();
@@ -662,31 +686,34 @@ inline cudaError_t set_weights(State& s, const std::vector<std::vector<float>>& 
   std::vector<float> bias(static_cast<size_t>(s.nlayers) * kF, 0.f);
   s.layers.assign(s.nlayers, LayerInfo{});
 
-  // chunk = (layer, slice, K block kb of <= 32 channels, board row dy): ntaps taps x nk K-steps.
-  // image: [half: cout 0..ndim/2-1 | ndim/2..ndim-1][tap][plane j][n within half][8 channels]
-  auto emit = [&](int layer, int slice, int tap0, int ntaps, int total_taps, int ch0, int kplane, int nk, int ndim,
-                  int cin, int cout, const float* w, uint32_t flags, uint32_t need) {
+  // chunk = (layer, slice, K-block set, board row dy): ntaps taps x (nk0 + nk1) K-steps, MMA order
+  // (tap, K block, K-step).  image: [half: cout 0..ndim/2-1 | ndim/2..ndim-1][tap][K block][plane j][n][8]
+  struct KB { int ch0; int nk; };  // first input channel and K-steps of a K block
+  auto emit = [&](int layer, int tap0, int ntaps, int dy, int first_plane, KB k0, KB k1, int ndim, int cin, int cout,
+                  const float* w, uint32_t flags, uint32_t need) {
     Chunk ch{};
     ch.gofs = static_cast<uint32_t>(img.size() * 2);
-    ch.half16 = static_cast<uint16_t>(ntaps * nk * 2 * (ndim / 2));
-    const int dy = total_taps == 9 ? tap0 / 3 - 1 : 0;
-    ch.a_off = static_cast<int16_t>(kplane * kRowsTotal + dy * kW);
-    ch.nk = static_cast<uint8_t>(nk);
+    ch.half16 = static_cast<uint16_t>(ntaps * (k0.nk + k1.nk) * 2 * (ndim / 2));
+    ch.a_off = static_cast<int16_t>(first_plane * kRowsTotal + dy * kW);
+    ch.nk0 = static_cast<uint8_t>(k0.nk);
+    ch.nk1 = static_cast<uint8_t>(k1.nk);
     ch.ntaps = static_cast<uint8_t>(ntaps);
     ch.ndim8 = static_cast<uint8_t>(ndim / 8);
     ch.flags = static_cast<uint8_t>(flags | (need << 4));
     ch.layer = static_cast<uint8_t>(layer);
-    ch.slice = static_cast<uint8_t>(slice);
     for (int half = 0; half < 2; ++half)
       for (int t = 0; t < ntaps; ++t)
-        for (int j = 0; j < nk * 2; ++j)
-          for (int nn = 0; nn < ndim / 2; ++nn)
-            for (int e = 0; e < 8; ++e) {
-              const int ci = ch0 + j * 8 + e;
-              const int n = half * (ndim / 2) + nn;
-              const float v = (ci < cin && n < cout) ? w[(static_cast<size_t>(tap0 + t) * cin + ci) * cout + n] : 0.f;
-              img.push_back(f32_to_bf16_rne(v));
-            }
+        for (int blk = 0; blk < 2; ++blk) {
+          const KB& k = blk ? k1 : k0;
+          for (int j = 0; j < k.nk * 2; ++j)
+            for (int nn = 0; nn < ndim / 2; ++nn)
+              for (int e = 0; e < 8; ++e) {
+                const int ci = k.ch0 + j * 8 + e;
+                const int n = half * (ndim / 2) + nn;
+                const float v = (ci < cin && n < cout) ? w[(static_cast<size_t>(tap0 + t) * cin + ci) * cout + n] : 0.f;
+                img.push_back(f32_to_bf16_rne(v));
+              }
+        }
     chunks.push_back(ch);
   };
 
@@ -715,28 +742,36 @@ inline cudaError_t set_weights(State& s, const std::vector<std::vector<float>>& 
     for (int sl = 0; sl < nslices; ++sl) {
       const int pl0 = sl * kPlanes;
       const int npl = std::min(kPlanes, planes_total - pl0);
+      const bool first_sl = sl == 0, last_sl = sl == nslices - 1;
       if (is_final) {
-        // 1x1 conv: one chunk, all 8 K-steps, needs every activation K block
-        emit(L, sl, 0, 1, 1, 0, 0, npl / 2, ndim, cin, cout, w,
+        // 1x1 conv: one chunk, all 8 K-steps over planes 0..15, needs every activation K block
+        emit(L, 0, 1, 0, 0, KB{0, npl / 2}, KB{0, 0}, ndim, cin, cout, w,
              kFirstOfSlice | kLastOfSlice | kFirstOfLayer | kLastOfLayer, 0xFu);
         continue;
       }
-      const int nkb = (npl + 3) / 4;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int nk = std::min(2, (npl - kb * 4) / 2);
+      // K-block sets of this slice, in issue order
+      struct Set { int plane; KB k0, k1; uint32_t need; };
+      std::vector<Set> sets;
+      if (npl == kPlanes) {
+        for (int pi = 0; pi < 2; ++pi)
+          sets.push_back(Set{pi * 4, KB{(pl0 + pi * 4) * 8, 2}, KB{(pl0 + pi * 4 + 8) * 8, 2}, (1u << pi) | (1u << (pi + 2))});
+      } else {
+        for (int kb = 0; kb * 4 < npl; ++kb)
+          sets.push_back(Set{kb * 4, KB{(pl0 + kb * 4) * 8, std::min(2, (npl - kb * 4) / 2)}, KB{0, 0}, 1u << kb});
+      }
+      for (size_t si = 0; si < sets.size(); ++si)
         for (int dy = 0; dy < 3; ++dy) {
           uint32_t fl = 0;
-          const bool first = kb == 0 && dy == 0, last = kb == nkb - 1 && dy == 2;
+          const bool first = si == 0 && dy == 0, last = si + 1 == sets.size() && dy == 2;
           if (first) fl |= kFirstOfSlice;
           if (last) fl |= kLastOfSlice;
-          if (first && sl == 0) fl |= kFirstOfLayer;
-          if (last && sl == nslices - 1) fl |= kLastOfLayer;
+          if (first && first_sl) fl |= kFirstOfLayer;
+          if (last && last_sl) fl |= kLastOfLayer;
           uint32_t need = 0;
-          if (!is_stem && dy == 0) need = 1u << kb;             // planes 4kb..4kb+3 of the previous epilogue
-          if (is_stem && first && sl == 0) need = 0xFu;          // previous round fully drained (TMEM + planes)
-          emit(L, sl, dy * 3, 3, 9, (pl0 + kb * 4) * 8, kb * 4, nk, ndim, cin, cout, w, fl, need);
+          if (!is_stem && dy == 0) need = sets[si].need;          // K blocks written by the previous epilogue
+          if (is_stem && first && first_sl) need = 0xFu;           // previous round fully drained (TMEM + planes)
+          emit(L, dy * 3, 3, dy - 1, sets[si].plane, sets[si].k0, sets[si].k1, ndim, cin, cout, w, fl, need);
         }
-      }
     }
     li.chunk_end = static_cast<int>(chunks.size());
     for (int c = li.chunk_begin; c < li.chunk_end; ++c) chunks[c].lend = static_cast<uint16_t>(li.chunk_end);
@@ -754,7 +789,7 @@ inline cudaError_t set_weights(State& s, const std::vector<std::vector<float>>& 
 
   s.nchunks = static_cast<int>(chunks.size());
   const size_t fixed = kActBytes + static_cast<size_t>(s.nlayers) * kF * 4 + kF * 4 + 4 * kPosPerGroup * kSq * 4 + 32 * 4 +
-                       chunks.size() * sizeof(Chunk) + (3 * kMaxStages + 16) * 8 + 16;
+                       chunks.size() * sizeof(Chunk) + (2 * kMaxStages + 16) * 8 + 16;
   s.nstages = static_cast<int>(std::min<size_t>(kMaxStages, (232448 - std::min<size_t>(fixed, 232448)) / kStageBytes));
   s.smem_bytes = fixed + static_cast<size_t>(s.nstages) * kStageBytes;
   s.attr_set = false;
