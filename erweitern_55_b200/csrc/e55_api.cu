@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -40,6 +41,11 @@ struct e55_ctx {
   bool has_weights = false;
   int64_t launches = 0;
   cudaStream_t stream = nullptr;
+  // host-buffer predict pipeline: chunks of the batch go H2D -> kernels -> D2H on rotating side streams
+  static constexpr int kPipeStreams = 4;
+  cudaStream_t pipe_stream[kPipeStreams] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t pipe_done[kPipeStreams] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t pipe_start = nullptr;
   mutable std::mutex mu;
   mutable std::string err;
 
@@ -261,6 +267,17 @@ int collect_timing(e55_ctx* c) {
   return E55_OK;
 }
 
+int forward_tc_on(e55_ctx* c, cudaStream_t stream, const float* d_planes, int n, float* d_policy, float* d_value) {
+  std::string why;
+  int launched = 0;
+  c->tc.ev0 = c->tc.ev1 = nullptr;
+  cudaError_t e = e55::tc::forward(c->tc, d_planes, n, d_policy, d_value, stream, &launched, &why);
+  c->launches += launched;
+  if (e != cudaSuccess) return fail(c, E55_ERR_CUDA, "tensor-core forward: " + why + ": " + cudaGetErrorString(e));
+  if (!why.empty()) return fail(c, E55_ERR_UNSUPPORTED, why);
+  return E55_OK;
+}
+
 int forward(e55_ctx* c, const float* d_planes, int n, float* d_policy, float* d_value) {
   if (c->precision == E55_PRECISION_FP32) return forward_fp32(c, d_planes, n, d_policy, d_value, nullptr);
   std::string why;
@@ -319,6 +336,12 @@ int e55_create(e55_ctx** out, int device, int blocks, int filters, int in_planes
   c->device = device; c->blocks = blocks; c->filters = filters; c->in_planes = in_planes;
   e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete c; return fail(nullptr, E55_ERR_CUDA, cudaGetErrorString(e)); }
+  for (int i = 0; i < e55_ctx::kPipeStreams && e == cudaSuccess; ++i) {
+    e = cudaStreamCreateWithFlags(&c->pipe_stream[i], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->pipe_done[i], cudaEventDisableTiming);
+  }
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->pipe_start, cudaEventDisableTiming);
+  if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); e55_destroy(c); return E55_ERR_CUDA; }
   e55::tc::init(c->tc, blocks, filters, in_planes, prop.multiProcessorCount);
   int rc = ensure_capacity(c, max_batch);
   if (rc != E55_OK) { g_create_error = c->err; e55_destroy(c); return rc; }
@@ -334,6 +357,11 @@ void e55_destroy(e55_ctx* c) {
   free_buffers(c);
   if (c->ev0) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); }
   if (c->tc.d_prof) cudaFree(c->tc.d_prof);
+  for (int i = 0; i < e55_ctx::kPipeStreams; ++i) {
+    if (c->pipe_stream[i]) { cudaStreamSynchronize(c->pipe_stream[i]); cudaStreamDestroy(c->pipe_stream[i]); }
+    if (c->pipe_done[i]) cudaEventDestroy(c->pipe_done[i]);
+  }
+  if (c->pipe_start) cudaEventDestroy(c->pipe_start);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -457,6 +485,32 @@ int e55_predict(e55_ctx* c, const float* planes, int n, float* policy, float* va
   std::lock_guard<std::mutex> lk(c->mu);
   E55_CUDA(c, cudaSetDevice(c->device));
   if ((rc = ensure_capacity(c, n))) return rc;
+  // Large batches on the tensor-core path: split into chunks that travel H2D -> kernel -> D2H on rotating
+  // side streams, so PCIe transfers in both directions overlap each other and the kernels (which then run
+  // concurrently on disjoint SMs).  The step stays one logical batch: every position is independent.
+  constexpr int kChunk = 256;
+  if (c->precision == E55_PRECISION_BF16_TC && !c->timing && n >= 2 * kChunk) {
+    E55_CUDA(c, cudaEventRecord(c->pipe_start, c->stream));
+    const size_t in_pp = static_cast<size_t>(c->in_planes) * kSq, pol_pp = static_cast<size_t>(kPolicyCh) * kSq;
+    int used = 0;
+    for (int off = 0, i = 0; off < n; off += kChunk, ++i) {
+      const int m = std::min(kChunk, n - off);
+      cudaStream_t st = c->pipe_stream[i % e55_ctx::kPipeStreams];
+      if (i < e55_ctx::kPipeStreams) { E55_CUDA(c, cudaStreamWaitEvent(st, c->pipe_start, 0)); used = i + 1; }
+      E55_CUDA(c, cudaMemcpyAsync(c->d_in + off * in_pp, planes + off * in_pp, m * in_pp * sizeof(float),
+                                  cudaMemcpyHostToDevice, st));
+      if ((rc = forward_tc_on(c, st, c->d_in + off * in_pp, m, c->d_policy + off * pol_pp, c->d_value + off))) return rc;
+      E55_CUDA(c, cudaMemcpyAsync(policy + off * pol_pp, c->d_policy + off * pol_pp, m * pol_pp * sizeof(float),
+                                  cudaMemcpyDeviceToHost, st));
+      E55_CUDA(c, cudaMemcpyAsync(value + off, c->d_value + off, m * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < used; ++i) {
+      E55_CUDA(c, cudaEventRecord(c->pipe_done[i], c->pipe_stream[i]));
+      E55_CUDA(c, cudaStreamWaitEvent(c->stream, c->pipe_done[i], 0));
+    }
+    E55_CUDA(c, cudaStreamSynchronize(c->stream));
+    return E55_OK;
+  }
   const size_t in_bytes = static_cast<size_t>(n) * c->in_planes * kSq * sizeof(float);
   E55_CUDA(c, cudaMemcpyAsync(c->d_in, planes, in_bytes, cudaMemcpyHostToDevice, c->stream));
   if ((rc = forward(c, c->d_in, n, c->d_policy, c->d_value))) return rc;

@@ -243,7 +243,8 @@ tower_kernel(const Params prm) {
   uint64_t* bar_act_part = bar_tmem_full + 2;         // [2][4] leader only: K block written by both CTAs
   uint64_t* bar_in_full = bar_act_part + 8;           // [2] leader only: stem input slice written
   uint64_t* bar_in_empty = bar_in_full + 2;           // [2] stem input planes may be overwritten
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_in_empty + 2);
+  uint64_t* bar_v = bar_in_empty + 2;                 // [2] value-conv partials of a group written by all 8 warps
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_v + 2);
   volatile uint32_t* s_apos = s_tmem + 1;             // chunks issued so far by group A's issuer
 
   const int warp = threadIdx.x >> 5;
@@ -254,6 +255,8 @@ tower_kernel(const Params prm) {
   const int pair0 = blockIdx.x >> 1, pair_stride = gridDim.x >> 1;
   const int npair_rounds = (prm.nrounds + 1) >> 1;    // a pair-round = one round in each CTA
 
+  long long t_entry = 0;
+  if (kProf) t_entry = clock64();
   // ---- one-time setup -----------------------------------------------------------------------
   for (int i = threadIdx.x; i < kActBytes / 16; i += kThreads)
     reinterpret_cast<uint4*>(s_act)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -271,8 +274,16 @@ tower_kernel(const Params prm) {
       for (int kb = 0; kb < 4; ++kb) ptx::mbar_init(&bar_act_part[g * 4 + kb], 8);   // 4 warps x 2 CTAs
       ptx::mbar_init(&bar_in_full[g], 16);                                           // 8 warps x 2 CTAs
       ptx::mbar_init(&bar_in_empty[g], 1);
+      ptx::mbar_init(&bar_v[g], 8);
     }
     ptx::fence_mbar_init();
+  }
+  {  // pull this CTA's first round of network input into L2 while the setup completes
+    const int r0 = pair0 * 2 + static_cast<int>(rank);
+    const size_t first = static_cast<size_t>(r0) * kPosPerRound * prm.in_planes * kSq;
+    const size_t last = min(static_cast<size_t>(r0 + 1) * kPosPerRound, static_cast<size_t>(prm.n)) * prm.in_planes * kSq;
+    for (size_t i = first + threadIdx.x * 32; i < last; i += kThreads * 32)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(prm.planes + i));
   }
   if (warp == 9) ptx::tmem_alloc_2sm<kTmemCols>(s_tmem);
   ptx::fence_proxy_async_smem();
@@ -281,6 +292,7 @@ tower_kernel(const Params prm) {
   ptx::cluster_sync();   // the peer's barriers are initialised before anyone arrives on them remotely
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *s_tmem;
+  if (kProf && blockIdx.x == 0 && threadIdx.x == 0) { prm.prof[12] = t_entry; prm.prof[13] = clock64(); }
 
   if (warp == 8) {
     // ===== weight producer: this CTA's half (64 output channels) of every chunk ==================
@@ -413,6 +425,7 @@ tower_kernel(const Params prm) {
     if (kProf && blockIdx.x == 0 && lane == 0) {
       unsigned long long* o = prm.prof + (g ? 4 : 0);
       o[0] = clock64() - t_start; o[1] = t_issue; o[2] = t_full; o[3] = t_act;
+      if (g == 0) prm.prof[9] = t_start;
     }
   } else if (warp < 8) {
     // ===== epilogue warps 0-7, shared by both groups: warp w owns TMEM lane quadrant w%4 (32 tile rows)
@@ -436,17 +449,71 @@ tower_kernel(const Params prm) {
       const bool has_b = pr * 2 * kPosPerRound + kPosPerGroup < prm.n;
       int next_layer[2] = {0, has_b ? 0 : nl};
       int next_slice[2] = {0, has_b ? 0 : prm.nslices};
-      while (next_layer[0] < nl || next_layer[1] < nl) {
+      // the value-head tail of group g is run by warp 4g once all 8 warps have written their partials
+      const bool do_value = nl == prm.nlayers;
+      bool fc_pending[2] = {do_value && warp == 0, do_value && warp == 4 && has_b};
+      if (pr + pair_stride < npair_rounds) {  // pull the next round's network input into L2
+        const int rn = (pr + pair_stride) * 2 + static_cast<int>(rank);
+        const size_t first = static_cast<size_t>(rn) * kPosPerRound * prm.in_planes * kSq;
+        const size_t last = min(static_cast<size_t>(rn + 1) * kPosPerRound, static_cast<size_t>(prm.n)) * prm.in_planes * kSq;
+        for (size_t i = first + threadIdx.x * 32; i < last; i += 256 * 32)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(prm.planes + i));
+      }
+      while (next_layer[0] < nl || next_layer[1] < nl || fc_pending[0] || fc_pending[1]) {
         long long te0 = 0, te1 = 0;
         if (kProf) te0 = clock64();
         int g;
-        bool convert = false;
+        bool convert = false, value_fc = false;
         for (;;) {  // serve whichever event is ready first (group A preferred: it runs ahead)
           if (next_layer[0] < nl && ptx::mbar_test_wait(&bar_tmem_full[0], (round_seq * nl + next_layer[0]) & 1)) { g = 0; break; }
           if (next_layer[1] < nl && ptx::mbar_test_wait(&bar_tmem_full[1], (round_seq * nl + next_layer[1]) & 1)) { g = 1; break; }
           // stem input: slice k of a group may be written once the MMAs that read slice k-1 are done
           if (next_slice[0] < prm.nslices && (slices_done[0] == 0 || ptx::mbar_test_wait(&bar_in_empty[0], (slices_done[0] - 1) & 1))) { g = 0; convert = true; break; }
           if (next_slice[1] < prm.nslices && (slices_done[1] == 0 || ptx::mbar_test_wait(&bar_in_empty[1], (slices_done[1] - 1) & 1))) { g = 1; convert = true; break; }
+          if (fc_pending[0] && ptx::mbar_test_wait(&bar_v[0], round_seq & 1)) { g = 0; value_fc = true; break; }
+          if (fc_pending[1] && ptx::mbar_test_wait(&bar_v[1], round_seq & 1)) { g = 1; value_fc = true; break; }
+        }
+        if (value_fc) {
+          // value head tail of group g on one warp: ReLU(conv1x1) -> Dense(25->128)+ReLU -> Dense(128->1)+tanh
+          // (network.py:111-120).  Lane l owns hidden units l, l+32, l+64, l+96.
+          fc_pending[g] = false;
+          float hsum[4][kPosPerGroup];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float b1 = prm.fc1_b[lane + 32 * i];
+#pragma unroll
+            for (int p = 0; p < kPosPerGroup; ++p) hsum[i][p] = b1;
+          }
+          for (int s_ = 0; s_ < kSq; ++s_) {
+            float v1[kPosPerGroup];
+#pragma unroll
+            for (int p = 0; p < kPosPerGroup; ++p)
+              v1[p] = fmaxf(s_v[((g * 2 + 0) * kPosPerGroup + p) * kSq + s_] +
+                            s_v[((g * 2 + 1) * kPosPerGroup + p) * kSq + s_] + prm.value_b, 0.f);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float kk = __ldg(prm.fc1_k + s_ * kF + lane + 32 * i);
+#pragma unroll
+              for (int p = 0; p < kPosPerGroup; ++p) hsum[i][p] = fmaf(v1[p], kk, hsum[i][p]);
+            }
+          }
+          float part[kPosPerGroup] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float k2 = __ldg(prm.fc2_k + lane + 32 * i);
+#pragma unroll
+            for (int p = 0; p < kPosPerGroup; ++p) part[p] = fmaf(fmaxf(hsum[i][p], 0.f), k2, part[p]);
+          }
+#pragma unroll
+          for (int p = 0; p < kPosPerGroup; ++p)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part[p] += __shfl_xor_sync(0xffffffffu, part[p], o);
+          const int pos = r * kPosPerRound + g * kPosPerGroup + lane;
+          if (lane < kPosPerGroup && pos < prm.n) {
+            const float t = lane == 0 ? part[0] : lane == 1 ? part[1] : lane == 2 ? part[2] : part[3];
+            prm.value[pos] = tanhf(t + prm.fc2_b);
+          }
+          continue;
         }
         if (convert) {
           // fp32 NCHW planes -> bf16 wide-board planes of this group (network.py:255-274 built the input):
@@ -519,7 +586,11 @@ tower_kernel(const Params prm) {
           if (g == 0) { E55_EPI(res_a) } else { E55_EPI(res_b) }
 #undef E55_EPI
           // value 1x1 conv: this thread's half of the channel dot product (summed in the value tail)
-          if ((lf & kValueTap) && row_valid) s_v[((g * 2 + h) * kPosPerGroup + bp) * kSq + sq] = vacc;
+          if (lf & kValueTap) {
+            if (row_valid) s_v[((g * 2 + h) * kPosPerGroup + bp) * kSq + sq] = vacc;
+            __syncwarp();
+            if (lane == 0 && do_value) ptx::mbar_arrive(&bar_v[g]);
+          }
         } else {
           // policy 1x1 output: fp32 logits straight to HBM, index c*25 + sq (Flatten of NCHW)
           const int pos = pos_base + bp;
@@ -554,46 +625,6 @@ tower_kernel(const Params prm) {
         }
       }
 
-      if (nl == prm.nlayers) {
-        // value head tail: ReLU(conv1x1) -> Dense(25->128)+ReLU -> Dense(128->1)+tanh (network.py:111-120);
-        // thread t: group t/128, hidden unit t%128
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const int vg = threadIdx.x >> 7, j = threadIdx.x & 127;
-        if (vg == 0 || has_b) {
-          float hsum[kPosPerGroup];
-          const float b1 = prm.fc1_b[j];
-#pragma unroll
-          for (int p = 0; p < kPosPerGroup; ++p) hsum[p] = b1;
-          for (int s = 0; s < kSq; ++s) {
-            const float kk = prm.fc1_k[s * kF + j];
-#pragma unroll
-            for (int p = 0; p < kPosPerGroup; ++p) {
-              const float v1 = fmaxf(s_v[((vg * 2 + 0) * kPosPerGroup + p) * kSq + s] +
-                                     s_v[((vg * 2 + 1) * kPosPerGroup + p) * kSq + s] + prm.value_b, 0.f);
-              hsum[p] = fmaf(v1, kk, hsum[p]);
-            }
-          }
-          const float k2 = prm.fc2_k[j];
-#pragma unroll
-          for (int p = 0; p < kPosPerGroup; ++p) {
-            float part = fmaxf(hsum[p], 0.f) * k2;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-            if (lane == 0) s_part[(vg * 4 + (j >> 5)) * kPosPerGroup + p] = part;
-          }
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (j < kPosPerGroup && (vg == 0 || has_b)) {
-          const int pos = r * kPosPerRound + vg * kPosPerGroup + j;
-          if (pos < prm.n) {
-            float t = prm.fc2_b;
-#pragma unroll
-            for (int w4 = 0; w4 < 4; ++w4) t += s_part[(vg * 4 + w4) * kPosPerGroup + j];
-            prm.value[pos] = tanhf(t);
-          }
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-      }
     }
     if (kProf && blockIdx.x == 0 && threadIdx.x == 0) {
       prm.prof[10] = t_wait;
@@ -604,8 +635,10 @@ tower_kernel(const Params prm) {
   // neither CTA may exit (or free TMEM) while the other can still signal its barriers / read its smem
   ptx::tc_fence_before_sync();
   __syncthreads();
+  if (kProf && blockIdx.x == 0 && threadIdx.x == 0) prm.prof[14] = clock64();
   ptx::cluster_sync();
   if (warp == 9) ptx::tmem_dealloc_2sm<kTmemCols>(tmem_base);
+  if (kProf && blockIdx.x == 0 && threadIdx.x == 0) prm.prof[15] = clock64();
 }
 
 // =================================================================================================
@@ -789,7 +822,7 @@ inline cudaError_t set_weights(State& s, const std::vector<std::vector<float>>& 
 
   s.nchunks = static_cast<int>(chunks.size());
   const size_t fixed = kActBytes + static_cast<size_t>(s.nlayers) * kF * 4 + kF * 4 + 4 * kPosPerGroup * kSq * 4 + 32 * 4 +
-                       chunks.size() * sizeof(Chunk) + (2 * kMaxStages + 16) * 8 + 16;
+                       chunks.size() * sizeof(Chunk) + (2 * kMaxStages + 18) * 8 + 16;
   s.nstages = static_cast<int>(std::min<size_t>(kMaxStages, (232448 - std::min<size_t>(fixed, 232448)) / kStageBytes));
   s.smem_bytes = fixed + static_cast<size_t>(s.nstages) * kStageBytes;
   s.attr_set = false;

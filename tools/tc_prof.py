@@ -26,6 +26,8 @@ for n in [int(a) for a in sys.argv[1:]] or [8, 256, 1024]:
     c = list(out)
     print(f"n={n}: issuerA total={c[0]} issue={c[1]} wait_full={c[2]} wait_act={c[3]} | issuerB total={c[4]} issue={c[5]} "
           f"wait_full={c[6]} wait_act={c[7]} | producer wait={c[8]} | epi wait={c[10]} work={c[11]}", flush=True)
+    print(f"   kernel timeline (cycles from entry): setup done={c[13]-c[12]} issuerA start={c[9]-c[12]} issuerA end={c[9]+c[0]-c[12]} "
+          f"all roles done={c[14]-c[12]} exit={c[15]-c[12]}", flush=True)
     st = torch.cuda.ExternalStream(net.cuda_stream())
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     for _ in range(3):
