@@ -119,7 +119,8 @@ struct Params {
   int nlayers;               // layers of the full network (tower convs + policy conv + policy 1x1)
   int nlayers_run;           // == nlayers, or fewer for a debug dump
   int n;                     // positions
-  int nrounds;               // ceil(n / 8)
+  int nrounds;               // ceil(n / pos_per_round)
+  int pos_per_round;         // 8 (groups A and B), or 4 (group A only: latency mode for small batches)
   float* policy;             // [n][1725]
   float* value;              // [n]
   uint4* dbg;                // [rounds*2][16][128] packed activations after layer nlayers_run-1
@@ -280,8 +281,8 @@ tower_kernel(const Params prm) {
   }
   {  // pull this CTA's first round of network input into L2 while the setup completes
     const int r0 = pair0 * 2 + static_cast<int>(rank);
-    const size_t first = static_cast<size_t>(r0) * kPosPerRound * prm.in_planes * kSq;
-    const size_t last = min(static_cast<size_t>(r0 + 1) * kPosPerRound, static_cast<size_t>(prm.n)) * prm.in_planes * kSq;
+    const size_t first = static_cast<size_t>(r0) * prm.pos_per_round * prm.in_planes * kSq;
+    const size_t last = min(static_cast<size_t>(r0 + 1) * prm.pos_per_round, static_cast<size_t>(prm.n)) * prm.in_planes * kSq;
     for (size_t i = first + threadIdx.x * 32; i < last; i += kThreads * 32)
       asm volatile("prefetch.global.L2 [%0];" ::"l"(prm.planes + i));
   }
@@ -338,7 +339,7 @@ tower_kernel(const Params prm) {
     long long t_start = 0, t_issue = 0, t_full = 0, t_act = 0;
     if (kProf) t_start = clock64();
     for (int pr = pair0; pr < npair_rounds; pr += pair_stride, ++round_seq) {
-      const bool has_b = pr * 2 * kPosPerRound + kPosPerGroup < prm.n;
+      const bool has_b = prm.pos_per_round == kPosPerRound && pr * 2 * kPosPerRound + kPosPerGroup < prm.n;
       if (g == 1 && !has_b) break;  // only the last pair-round can lack group B
       const uint32_t gbase = round_seq * nchunks;
       for (uint32_t c = 0; c < nchunks; ++c) {
@@ -446,7 +447,7 @@ tower_kernel(const Params prm) {
 
     for (int pr = pair0; pr < npair_rounds; pr += pair_stride, ++round_seq) {
       const int r = pr * 2 + static_cast<int>(rank);     // this CTA's round (may lie past the batch: all absent)
-      const bool has_b = pr * 2 * kPosPerRound + kPosPerGroup < prm.n;
+      const bool has_b = prm.pos_per_round == kPosPerRound && pr * 2 * kPosPerRound + kPosPerGroup < prm.n;
       int next_layer[2] = {0, has_b ? 0 : nl};
       int next_slice[2] = {0, has_b ? 0 : prm.nslices};
       // the value-head tail of group g is run by warp 4g once all 8 warps have written their partials
@@ -454,8 +455,8 @@ tower_kernel(const Params prm) {
       bool fc_pending[2] = {do_value && warp == 0, do_value && warp == 4 && has_b};
       if (pr + pair_stride < npair_rounds) {  // pull the next round's network input into L2
         const int rn = (pr + pair_stride) * 2 + static_cast<int>(rank);
-        const size_t first = static_cast<size_t>(rn) * kPosPerRound * prm.in_planes * kSq;
-        const size_t last = min(static_cast<size_t>(rn + 1) * kPosPerRound, static_cast<size_t>(prm.n)) * prm.in_planes * kSq;
+        const size_t first = static_cast<size_t>(rn) * prm.pos_per_round * prm.in_planes * kSq;
+        const size_t last = min(static_cast<size_t>(rn + 1) * prm.pos_per_round, static_cast<size_t>(prm.n)) * prm.in_planes * kSq;
         for (size_t i = first + threadIdx.x * 32; i < last; i += 256 * 32)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(prm.planes + i));
       }
@@ -508,7 +509,7 @@ tower_kernel(const Params prm) {
           for (int p = 0; p < kPosPerGroup; ++p)
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) part[p] += __shfl_xor_sync(0xffffffffu, part[p], o);
-          const int pos = r * kPosPerRound + g * kPosPerGroup + lane;
+          const int pos = r * prm.pos_per_round + g * kPosPerGroup + lane;
           if (lane < kPosPerGroup && pos < prm.n) {
             const float t = lane == 0 ? part[0] : lane == 1 ? part[1] : lane == 2 ? part[2] : part[3];
             prm.value[pos] = tanhf(t + prm.fc2_b);
@@ -521,7 +522,7 @@ tower_kernel(const Params prm) {
           const int sl = next_slice[g];
           const int pl0 = sl * kPlanes;
           const int npl = min(kPlanes, prm.in_planes8 - pl0);
-          const int pos0 = r * kPosPerRound + g * kPosPerGroup;
+          const int pos0 = r * prm.pos_per_round + g * kPosPerGroup;
           const int nitems = kPosPerGroup * npl * kSq;
           for (int it0 = threadIdx.x; it0 < nitems; it0 += 256 * 4) {
             float f[4][8];
@@ -564,12 +565,12 @@ tower_kernel(const Params prm) {
         const float* bias = s_bias + L * kF + h * 64;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (g * 2 + (L & 1)) * kF + h * 64;
         uint64_t* bar_part = &bar_act_part[g * 4 + h * 2];
-        const int pos_base = r * kPosPerRound + g * kPosPerGroup;
+        const int pos_base = r * prm.pos_per_round + g * kPosPerGroup;
 
         if (!(lf & kFinal)) {
           uint8_t* act_row = s_act + (h * 8) * kPlaneBytes + (group_origin_row(g) + row) * 16;
           uint4* dbg_row = (prm.dbg != nullptr && L == nl - 1 && pos_base < prm.n)
-                               ? prm.dbg + (static_cast<size_t>(r * 2 + g) * kPlanes + h * 8) * kTile + row : nullptr;
+                               ? prm.dbg + (static_cast<size_t>(pos_base / kPosPerGroup) * kPlanes + h * 8) * kTile + row : nullptr;
           const float* wv = s_wv + h * 64;
           float vacc = 0.f;
 #define E55_EPI(RES)                                                                                          \
@@ -840,14 +841,16 @@ inline cudaError_t run(State& s, const float* d_planes, int n, float* d_policy, 
     if (e != cudaSuccess) { *why = "cudaFuncSetAttribute"; return e; }
     s.attr_set = true;
   }
-  const int rounds = (n + kPosPerRound - 1) / kPosPerRound;
+  // latency mode: while the batch fits the machine with one 4-position group per CTA, leave group B out
+  const int ppr = n <= kPosPerGroup * 2 * std::max(1, s.sms / 2) ? kPosPerGroup : kPosPerRound;
+  const int rounds = (n + ppr - 1) / ppr;
   Params p{};
   p.wimg = s.d_wimg; p.chunks = s.d_chunks; p.layers = s.d_layers; p.bias = s.d_bias;
   p.value_w = s.heads.d_value_w; p.fc1_k = s.heads.d_fc1_k; p.fc1_b = s.heads.d_fc1_b; p.fc2_k = s.heads.d_fc2_k;
   p.value_b = s.heads.value_b; p.fc2_b = s.heads.fc2_b;
   p.planes = d_planes; p.in_planes = s.in_planes; p.in_planes8 = s.in_planes8; p.nslices = s.nslices;
   p.nstages = s.nstages; p.nchunks_total = s.nchunks; p.lag = std::min(s.lag, s.nstages - 2);
-  p.nlayers = s.nlayers; p.nlayers_run = nlayers_run; p.n = n; p.nrounds = rounds;
+  p.nlayers = s.nlayers; p.nlayers_run = nlayers_run; p.n = n; p.nrounds = rounds; p.pos_per_round = ppr;
   p.policy = d_policy; p.value = d_value;
   p.dbg = nlayers_run < s.nlayers ? s.d_dbg : nullptr;
   p.prof = s.d_prof;
