@@ -33,6 +33,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_POSITION = 126_368_256          # dense-convention FLOPs of the default net
+
+
+def flop_per_position(blocks, filters, in_planes=266):
+    """Dense-convention FLOPs of one forward pass: 126 368 256 for 7x128, 1 240 685 056 for 20x256."""
+    conv = lambda cin, cout, k: 2 * 25 * cout * cin * k * k
+    return (conv(in_planes, filters, 3) + (2 * blocks + 1) * conv(filters, filters, 3) + conv(filters, 69, 1)
+            + conv(filters, 1, 1) + 2 * 25 * 128 + 2 * 128)
 METRIC = "policy+value evals/sec (batch 1024)"
 UNIT = "evals/s"
 L2_BYTES = 126 * 1024 * 1024
@@ -137,7 +144,7 @@ def run_reference(args, rank, world):
     from erweitern_55_b200 import synth, weights as W
     cores, model = host_info()
     torch.set_num_threads(cores)
-    w = W.init_weights(seed=55)
+    w = W.init_weights(blocks=args.blocks, filters=args.filters, seed=55)
     prep = O.prepare_torch(w)
     x = torch.from_numpy(synth.synthetic_planes(args.batch, seed=1000))
     for _ in range(max(1, min(args.warmup, 2))):
@@ -171,6 +178,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--blocks", type=int, default=7, help="residual blocks (20 with --filters 256 = BASELINE configs[4])")
+    ap.add_argument("--filters", type=int, default=128, choices=[128, 256])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 50)")
     args = ap.parse_args()
@@ -199,8 +208,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     B = args.batch
-    w = W.init_weights(seed=55)
-    net = Network(device=local_rank, precision=args.precision, weights=w, max_batch=B)
+    w = W.init_weights(blocks=args.blocks, filters=args.filters, seed=55)
+    flops = flop_per_position(args.blocks, args.filters)
+    net = Network(device=local_rank, blocks=args.blocks, filters=args.filters, precision=args.precision, weights=w, max_batch=B)
     stream = torch.cuda.ExternalStream(net.cuda_stream(), device=dev)
 
     # distinct input batches whose total size exceeds L2, used round-robin: every step reads HBM
@@ -256,16 +266,16 @@ def main():
         k_ms, k_n = net.kernel_timing()
         net.set_kernel_timing(False)
         peak, peak_src = measured_peaks()
-        achieved = B * FLOP_PER_POSITION / (k_ms / k_n * 1e-3) / 1e12
+        achieved = B * flops / (k_ms / k_n * 1e-3) / 1e12
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "tower_kernel_dram_bytes.json")) as f:
-                traffic = json.load(f).get(f"batch_{B}")
+                traffic = json.load(f).get(f"batch_{B}" if (args.blocks, args.filters) == (7, 128) else f"batch_{B}_{args.blocks}x{args.filters}")
         except Exception:
             pass
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "traffic": traffic, "kernel": "e55::tc::tower_kernel", "kernel_us": k_ms / k_n * 1e3,
-                    "flop_per_launch": B * FLOP_PER_POSITION, "peak_source": peak_src}
+                    "flop_per_launch": B * flops, "peak_source": peak_src}
 
     # ---- end-to-end through the host-buffer call (reference-facing Network.predict path) ----------
     e2e_steps = args.e2e_steps or min(args.steps, 50)
@@ -303,11 +313,12 @@ def main():
             "metric": METRIC, "value": value_rate, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": max_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": f"default 7x128 ResNet forward (stem + 7 residual blocks + policy/value heads), batch {B} "
-                                   "per GPU, random-init weights (BASELINE.json configs[1])",
+            "config": {"workload": (f"default 7x128 ResNet forward (stem + 7 residual blocks + policy/value heads), batch {B} "
+                                    "per GPU, random-init weights (BASELINE.json configs[1])") if (args.blocks, args.filters) == (7, 128)
+                       else f"scaled tower {args.blocks}x{args.filters} forward, batch {B} per GPU, random-init weights (BASELINE.json configs[4])",
                        "batch_per_gpu": B, "parallelism": f"replicas x{world} (independent positions, no collective)",
                        "l2": f"inputs rotate over {n_pool} distinct device batches = {n_pool * in_bytes >> 20} MiB > 126 MiB L2",
-                       "flop_per_position": FLOP_PER_POSITION, "host_cpu": model, "host_cores": ncpu},
+                       "flop_per_position": flops, "host_cpu": model, "host_cores": ncpu},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "wall_s": t_wall,
         }

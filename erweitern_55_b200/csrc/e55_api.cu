@@ -459,7 +459,7 @@ int e55_set_precision(e55_ctx* c, int precision) {
   if (precision != E55_PRECISION_FP32 && precision != E55_PRECISION_BF16_TC)
     return fail(c, E55_ERR_INVALID, "unknown precision");
   if (precision == E55_PRECISION_BF16_TC && !e55::tc::supported(c->tc))
-    return fail(c, E55_ERR_UNSUPPORTED, "the tcgen05 path supports filters == 128 only");
+    return fail(c, E55_ERR_UNSUPPORTED, "the tcgen05 path supports 128 or 256 filters");
   c->precision = precision;
   return E55_OK;
 }

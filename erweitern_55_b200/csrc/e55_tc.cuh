@@ -50,29 +50,41 @@ namespace e55 {
 namespace tc {
 
 // ---- geometry -----------------------------------------------------------------------------------
-constexpr int kF = 128;                // tower width this kernel is specialised for
 constexpr int kPosPerGroup = 4;
 constexpr int kPosPerRound = 8;        // per CTA; a pair does 16
 constexpr int kW = 24;                 // wide-board width
 constexpr int kRowsValid = 120;        // 5 * kW
 constexpr int kTile = 128;             // rows per CTA tile (UMMA M = 256 across the pair)
 constexpr int kGuard = 25;             // kW + 1
-constexpr int kRowsTotal = kGuard + kTile + kGuard + kTile + kGuard;  // 331
-constexpr int kPlanes = kF / 8;        // 16
-constexpr int kPlaneBytes = kRowsTotal * 16;
-constexpr int kActBytes = kPlanes * kPlaneBytes;                       // 84,736
+constexpr int kValueHidden = 128;      // Dense(25 -> 128) of the value head (network.py:116-117)
+
+// Per-tower-width geometry.  F = 128 (reference net): two 4-position groups per CTA.  F = 256 (scaled tower,
+// BASELINE.json configs[4]): one group per CTA (the activations of a second one would not fit), N = 256.
+template <int F>
+struct Geo {
+  static_assert(F == 128 || F == 256, "tower width must be 128 or 256");
+  static constexpr int kGroups = F == 128 ? 2 : 1;
+  static constexpr int kPlanes = F / 8;                                   // 8-channel activation planes
+  static constexpr int kRowsTotal = kGuard + kGroups * (kTile + kGuard);  // 331 / 178
+  static constexpr int kPlaneBytes = kRowsTotal * 16;
+  static constexpr int kActBytes = kPlanes * kPlaneBytes;                 // 84,736 / 91,136
+  static constexpr int kKBlocks = F / 32;                                 // 32-channel activation K blocks
+  static constexpr int kHalfCh = F / 2;                                   // channels per epilogue thread
+  static constexpr int kCb = kHalfCh / 32;                                // 32-column TMEM loads per thread
+  static constexpr bool kBiasInSmem = F == 128;                           // 43 x 256 biases do not fit
+};
 constexpr int kMaxStages = 5;
 constexpr int kStageBytes = 24576;     // this CTA's half of a chunk: 3 taps x 2 K blocks x 2 K-steps x 64 x 16 x 2 B
 constexpr int kPolicyCh = 69;
 constexpr int kPolicyN = 96;           // policy 1x1 output channels padded (each CTA holds N/2 = 48 columns)
 constexpr int kSq = 25;
 constexpr int kThreads = 352;
-constexpr int kTmemCols = 512;         // 2 groups x 2 accumulators (layer parity) x 128 columns
+constexpr int kTmemCols = 512;         // groups x 2 accumulators (layer parity) x F columns
 constexpr uint32_t kDescHi = 8u | (1u << 14);  // SBO = 128 B, descriptor version 1, no swizzle
 
 __host__ __device__ constexpr int group_origin_row(int g) { return kGuard + g * (kTile + kGuard); }
 
-enum : uint32_t { kFirstOfSlice = 1, kLastOfSlice = 2, kFirstOfLayer = 4, kLastOfLayer = 8 };
+enum : uint32_t { kFirstOfSlice = 1, kLastOfSlice = 2, kFirstOfLayer = 4, kLastOfLayer = 8, kSingleTap = 16 };
 enum : uint32_t { kRelu = 1, kHasRes = 2, kUpdRes = 4, kValueTap = 8, kFinal = 16 };
 
 // One ring stage worth of weights: the taps of one board row (dx = -1,0,1; or the single tap of a 1x1
@@ -86,10 +98,10 @@ struct alignas(16) Chunk {
   uint16_t lend;     // chunk index one past the end of this chunk's layer
   int16_t a_off;     // A-descriptor displacement in 16 B units: first plane * rows + dy * board width
   uint8_t nk0;       // K=16 steps per tap on the first K block (planes a_off..)
-  uint8_t nk1;       // K=16 steps per tap on the second K block, 8 planes further on (0 = none)
-  uint8_t ntaps;     // 3 (dx = -1,0,1) or 1
+  uint8_t nk1;       // K=16 steps per tap on the second K block, half the planes further on (0 = none)
+  uint8_t need;      // bit kb: activation K block kb of the previous layer must be written before this chunk
   uint8_t ndim8;     // UMMA N / 8 of the layer
-  uint8_t flags;     // low 4 bits: first/last of slice/layer; high 4 bits: activation K blocks required
+  uint8_t flags;     // bits 0-3: first/last of slice/layer; bit 4: single tap (1x1 layer) instead of dx = -1,0,1
   uint8_t layer;
 };
 
@@ -103,8 +115,8 @@ struct Params {
   const uint8_t* wimg;
   const Chunk* chunks;
   const LayerInfo* layers;
-  const float* bias;       // [nlayers][128]
-  const float* value_w;    // [128]
+  const float* bias;       // [nlayers][F]
+  const float* value_w;    // [F]
   const float* fc1_k;      // [25][128]
   const float* fc1_b;      // [128]
   const float* fc2_k;      // [128]
@@ -128,9 +140,10 @@ struct Params {
 };
 
 // debug: packed activations [group][16][128 rows][8] bf16 -> fp32 NCHW [n][128][25]
-__global__ void unpack_debug_kernel(const uint4* __restrict__ dbg, float* __restrict__ out, int n) {
+__global__ void unpack_debug_kernel(const uint4* __restrict__ dbg, float* __restrict__ out, int n, int filters) {
   const int pos = blockIdx.x;
   const int group = pos / kPosPerGroup, p = pos % kPosPerGroup;
+  const int kPlanes = filters / 8;
   for (int idx = threadIdx.x; idx < kPlanes * kSq; idx += blockDim.x) {
     const int pl = idx / kSq, sq = idx % kSq;
     const int r = (sq / 5) * kW + p * 6 + sq % 5;
@@ -139,7 +152,7 @@ __global__ void unpack_debug_kernel(const uint4* __restrict__ dbg, float* __rest
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const uint32_t bits = (e & 1) ? (w[e >> 1] & 0xFFFF0000u) : (w[e >> 1] << 16);
-      out[(static_cast<size_t>(pos) * kF + pl * 8 + e) * kSq + sq] = __uint_as_float(bits);
+      out[(static_cast<size_t>(pos) * filters + pl * 8 + e) * kSq + sq] = __uint_as_float(bits);
     }
   }
 }
@@ -166,21 +179,22 @@ __device__ __forceinline__ void arrive_on_leader(uint64_t* bar, uint32_t rank) {
   else ptx::mbar_arrive_cluster(bar, 0);
 }
 
-// Epilogue of one 64-channel half of a 128x128 accumulator tile for the thread that owns `row`:
+// Epilogue of one half (F/2 channels) of a 128 x F accumulator tile for the thread that owns `row`:
 // TMEM -> +bias (+residual) -> ReLU -> bf16 -> shared memory (in place: the next layer's A operand).
 // taddr / bias / act_row / s_wv / dbg_row / bar_part already point at this thread's half.
-template <bool kRes, bool kUpd, bool kVal>
+template <int F, bool kRes, bool kUpd, bool kVal>
 __device__ __forceinline__ float epilogue_half(uint32_t taddr, const float* __restrict__ bias, uint8_t* act_row,
-                                               uint32_t (&res)[kF / 4], const float* __restrict__ s_wv,
+                                               uint32_t (&res)[F / 4], const float* __restrict__ s_wv,
                                                bool row_valid, uint4* dbg_row, uint64_t* bar_part, int lane,
                                                uint32_t rank) {
+  using G = Geo<F>;
   float vacc = 0.f;
   uint32_t v[2][32];
   ptx::tmem_ld_32x32b_x32(taddr, v[0]);
 #pragma unroll
-  for (int cb = 0; cb < 2; ++cb) {
+  for (int cb = 0; cb < G::kCb; ++cb) {
     ptx::tmem_ld_wait();
-    if (cb < 1) ptx::tmem_ld_32x32b_x32(taddr + 32, v[1]);  // overlaps the math below
+    if (cb + 1 < G::kCb) ptx::tmem_ld_32x32b_x32(taddr + (cb + 1) * 32, v[(cb + 1) & 1]);  // overlaps the math below
     const uint32_t(&vv)[32] = v[cb & 1];
     uint32_t o[16];
 #pragma unroll
@@ -206,7 +220,7 @@ __device__ __forceinline__ float epilogue_half(uint32_t taddr, const float* __re
 #pragma unroll
       for (int j4 = 0; j4 < 4; ++j4) {
         const uint4 pk = make_uint4(o[4 * j4], o[4 * j4 + 1], o[4 * j4 + 2], o[4 * j4 + 3]);
-        *reinterpret_cast<uint4*>(act_row + (cb * 4 + j4) * kPlaneBytes) = pk;
+        *reinterpret_cast<uint4*>(act_row + (cb * 4 + j4) * G::kPlaneBytes) = pk;
         if (dbg_row) dbg_row[(cb * 4 + j4) * kTile] = pk;
       }
     }
@@ -224,24 +238,26 @@ struct SmemLayout {
   __host__ __device__ static constexpr int act(int nstages) { return ring + nstages * kStageBytes; }
 };
 
-template <bool kProf>
+template <int F, bool kProf>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 tower_kernel(const Params prm) {
+  using G = Geo<F>;
+  constexpr int kPlanes = G::kPlanes;
+  constexpr int kPlaneBytes = G::kPlaneBytes;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* s_ring = smem + SmemLayout::ring;
   uint8_t* s_act = smem + SmemLayout::act(prm.nstages);
-  float* s_bias = reinterpret_cast<float*>(s_act + kActBytes);
-  float* s_wv = s_bias + prm.nlayers * kF;
-  float* s_v = s_wv + kF;                       // [2 groups][2 halves][4 positions][25]
-  float* s_part = s_v + 4 * kPosPerGroup * kSq;  // [2 groups][4 warps][4 positions]
-  Chunk* s_chunks = reinterpret_cast<Chunk*>(s_part + 32);
+  float* s_bias = reinterpret_cast<float*>(s_act + G::kActBytes);   // [nlayers][F] when it fits (F = 128)
+  float* s_wv = s_bias + (G::kBiasInSmem ? prm.nlayers * F : 0);
+  float* s_v = s_wv + F;                         // [2 groups][2 halves][4 positions][25]
+  Chunk* s_chunks = reinterpret_cast<Chunk*>(s_v + 4 * kPosPerGroup * kSq);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_chunks + prm.nchunks_total);
   const uint32_t nstages = prm.nstages;
   // identical layout in both CTAs (multicast commits and remote arrives address barriers by offset)
   uint64_t* bar_full = bars;                          // [stages] stage landed (leader: both CTAs' halves)
   uint64_t* bar_empty = bars + kMaxStages;            // [stages] both groups' MMAs on the stage are done
   uint64_t* bar_tmem_full = bars + 2 * kMaxStages;    // [2] accumulator of a group complete
-  uint64_t* bar_act_part = bar_tmem_full + 2;         // [2][4] leader only: K block written by both CTAs
+  uint64_t* bar_act_part = bar_tmem_full + 2;         // [groups][F/32 / groups... 8 in all] leader only: K block written by both CTAs
   uint64_t* bar_in_full = bar_act_part + 8;           // [2] leader only: stem input slice written
   uint64_t* bar_in_empty = bar_in_full + 2;           // [2] stem input planes may be overwritten
   uint64_t* bar_v = bar_in_empty + 2;                 // [2] value-conv partials of a group written by all 8 warps
@@ -259,10 +275,12 @@ tower_kernel(const Params prm) {
   long long t_entry = 0;
   if (kProf) t_entry = clock64();
   // ---- one-time setup -----------------------------------------------------------------------
-  for (int i = threadIdx.x; i < kActBytes / 16; i += kThreads)
+  for (int i = threadIdx.x; i < G::kActBytes / 16; i += kThreads)
     reinterpret_cast<uint4*>(s_act)[i] = make_uint4(0u, 0u, 0u, 0u);
-  for (int i = threadIdx.x; i < prm.nlayers * kF; i += kThreads) s_bias[i] = prm.bias[i];
-  for (int i = threadIdx.x; i < kF; i += kThreads) s_wv[i] = prm.value_w[i];
+  if (G::kBiasInSmem)
+    for (int i = threadIdx.x; i < prm.nlayers * F; i += kThreads) s_bias[i] = prm.bias[i];
+  for (int i = threadIdx.x; i < F; i += kThreads) s_wv[i] = prm.value_w[i];
+  const float* bias_base = G::kBiasInSmem ? s_bias : prm.bias;
   for (int i = threadIdx.x; i < prm.nchunks_total; i += kThreads) s_chunks[i] = prm.chunks[i];
   if (threadIdx.x == 0) {
     *s_apos = 0u;
@@ -270,9 +288,9 @@ tower_kernel(const Params prm) {
       ptx::mbar_init(&bar_full[s], rank == 0 ? 2 : 1);   // leader: own TMA + the peer's relay
       ptx::mbar_init(&bar_empty[s], 2);
     }
+    for (int kb = 0; kb < 8; ++kb) ptx::mbar_init(&bar_act_part[kb], 8);               // 4 warps x 2 CTAs
     for (int g = 0; g < 2; ++g) {
       ptx::mbar_init(&bar_tmem_full[g], 1);
-      for (int kb = 0; kb < 4; ++kb) ptx::mbar_init(&bar_act_part[g * 4 + kb], 8);   // 4 warps x 2 CTAs
       ptx::mbar_init(&bar_in_full[g], 16);                                           // 8 warps x 2 CTAs
       ptx::mbar_init(&bar_in_empty[g], 1);
       ptx::mbar_init(&bar_v[g], 8);
@@ -327,7 +345,7 @@ tower_kernel(const Params prm) {
         }
       }
     }
-  } else if ((warp == 9 || warp == 10) && rank == 0) {
+  } else if ((warp == 9 || (warp == 10 && G::kGroups == 2)) && rank == 0) {
     // ===== MMA issuers (leader CTA): warp 9 drives group A, warp 10 group B, for BOTH CTAs' tiles
     // (cta_group::2, M = 256).  Warp-uniform loop, one elected lane issues.  Both walk the same chunk
     // sequence; a ring stage is released (in both CTAs) after both groups used it. ==================
@@ -339,7 +357,7 @@ tower_kernel(const Params prm) {
     long long t_start = 0, t_issue = 0, t_full = 0, t_act = 0;
     if (kProf) t_start = clock64();
     for (int pr = pair0; pr < npair_rounds; pr += pair_stride, ++round_seq) {
-      const bool has_b = prm.pos_per_round == kPosPerRound && pr * 2 * kPosPerRound + kPosPerGroup < prm.n;
+      const bool has_b = G::kGroups == 2 && prm.pos_per_round == kPosPerRound && pr * 2 * kPosPerRound + kPosPerGroup < prm.n;
       if (g == 1 && !has_b) break;  // only the last pair-round can lack group B
       const uint32_t gbase = round_seq * nchunks;
       for (uint32_t c = 0; c < nchunks; ++c) {
@@ -360,25 +378,26 @@ tower_kernel(const Params prm) {
           ptx::mbar_wait_cluster(&bar_in_full[g], stem_slices & 1);
           ++stem_slices;
         }
-        if ((ch.flags >> 4) && epoch > 0) {
+        if (ch.need && epoch > 0) {
           // activation K blocks written by the previous layer's (progressive) epilogue in both CTAs
 #pragma unroll
-          for (int kb = 0; kb < 4; ++kb)
-            if ((ch.flags >> 4) & (1u << kb)) ptx::mbar_wait_cluster(&bar_act_part[g * 4 + kb], (epoch - 1) & 1);
+          for (int kb = 0; kb < G::kKBlocks; ++kb)
+            if (ch.need & (1u << kb)) ptx::mbar_wait_cluster(&bar_act_part[g * 4 + kb], (epoch - 1) & 1);
         }
         if (kProf) t2 = clock64();
         ptx::tc_fence_after_sync();
         if (ptx::elect_one()) {
           const uint32_t ndim = ch.ndim8 * 8u;
           const uint32_t idesc = ptx::umma_idesc_bf16_f32(2 * kTile, ndim);
-          const uint32_t d = tmem_base + (g * 2 + (ch.layer & 1)) * kF;
-          const uint32_t a_chunk = a_lo_base + static_cast<int>(ch.a_off) - (ch.ntaps == 3 ? 1 : 0);
+          const uint32_t d = tmem_base + (g * 2 + (ch.layer & 1)) * F;
+          const int ntaps = (ch.flags & kSingleTap) ? 1 : 3;
+          const uint32_t a_chunk = a_lo_base + static_cast<int>(ch.a_off) - (ntaps == 3 ? 1 : 0);
           const uint32_t b_step = ndim;                          // 2 planes x (ndim/2 rows) x 16 B, in 16 B units
           uint32_t b_lo = (b_lo_base + s * (kStageBytes >> 4)) | ((ndim >> 1) << 16);   // LBO = (ndim/2) x 16 B
           uint32_t acc = (ch.flags & kFirstOfLayer) ? 0u : 1u;
           constexpr uint32_t kStepK = 2 * (kPlaneBytes >> 4);    // one K=16 step = 2 planes
-          constexpr uint32_t kBlock2 = 8 * (kPlaneBytes >> 4);   // second K block of the chunk: 8 planes on
-          if (ch.ntaps == 3 && ch.nk0 == 2 && ch.nk1 == 2) {
+          constexpr uint32_t kBlock2 = (kPlanes / 2) * (kPlaneBytes >> 4);   // second K block: half the planes on
+          if (ntaps == 3 && ch.nk0 == 2 && ch.nk1 == 2) {
 #pragma unroll
             for (int t = 0; t < 3; ++t)
 #pragma unroll
@@ -387,8 +406,17 @@ tower_kernel(const Params prm) {
                 acc = 1u;
                 b_lo += b_step;
               }
+          } else if (ntaps == 3 && ch.nk0 == 2 && ch.nk1 == 0) {
+#pragma unroll
+            for (int t = 0; t < 3; ++t)
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) {
+                umma_pair(d, a_chunk + t + ks * kStepK, b_lo, idesc, acc);
+                acc = 1u;
+                b_lo += b_step;
+              }
           } else {
-            for (int t = 0; t < ch.ntaps; ++t) {
+            for (int t = 0; t < ntaps; ++t) {
               for (int ks = 0; ks < ch.nk0; ++ks) {
                 umma_pair(d, a_chunk + t + ks * kStepK, b_lo, idesc, acc);
                 acc = 1u;
@@ -438,16 +466,18 @@ tower_kernel(const Params prm) {
     const int by = row / kW, bp = (row % kW) / 6, bx = row % 6;
     const bool row_valid = row < kRowsValid && bx < 5;
     const int sq = by * 5 + bx;
-    uint32_t res_a[kF / 4], res_b[kF / 4];               // block inputs of this row/half, packed bf16x2
+    uint32_t res_a[F / 4], res_b[G::kGroups == 2 ? F / 4 : 1];   // block inputs of this row/half, packed bf16x2
 #pragma unroll
-    for (int i = 0; i < kF / 4; ++i) { res_a[i] = 0u; res_b[i] = 0u; }
+    for (int i = 0; i < F / 4; ++i) res_a[i] = 0u;
+#pragma unroll
+    for (int i = 0; i < (G::kGroups == 2 ? F / 4 : 1); ++i) res_b[i] = 0u;
     uint32_t round_seq = 0;
     uint32_t slices_done[2] = {0u, 0u};
     long long t_wait = 0, t_work = 0;
 
     for (int pr = pair0; pr < npair_rounds; pr += pair_stride, ++round_seq) {
       const int r = pr * 2 + static_cast<int>(rank);     // this CTA's round (may lie past the batch: all absent)
-      const bool has_b = prm.pos_per_round == kPosPerRound && pr * 2 * kPosPerRound + kPosPerGroup < prm.n;
+      const bool has_b = G::kGroups == 2 && prm.pos_per_round == kPosPerRound && pr * 2 * kPosPerRound + kPosPerGroup < prm.n;
       int next_layer[2] = {0, has_b ? 0 : nl};
       int next_slice[2] = {0, has_b ? 0 : prm.nslices};
       // the value-head tail of group g is run by warp 4g once all 8 warps have written their partials
@@ -493,7 +523,7 @@ tower_kernel(const Params prm) {
                             s_v[((g * 2 + 1) * kPosPerGroup + p) * kSq + s_] + prm.value_b, 0.f);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float kk = __ldg(prm.fc1_k + s_ * kF + lane + 32 * i);
+              const float kk = __ldg(prm.fc1_k + s_ * kValueHidden + lane + 32 * i);
 #pragma unroll
               for (int p = 0; p < kPosPerGroup; ++p) hsum[i][p] = fmaf(v1[p], kk, hsum[i][p]);
             }
@@ -562,29 +592,29 @@ tower_kernel(const Params prm) {
         const int L = next_layer[g];
         next_layer[g] = L + 1;
         const uint32_t lf = prm.layers[L].flags;
-        const float* bias = s_bias + L * kF + h * 64;
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (g * 2 + (L & 1)) * kF + h * 64;
-        uint64_t* bar_part = &bar_act_part[g * 4 + h * 2];
+        const float* bias = bias_base + L * F + h * G::kHalfCh;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (g * 2 + (L & 1)) * F + h * G::kHalfCh;
+        uint64_t* bar_part = &bar_act_part[g * 4 + h * G::kCb];
         const int pos_base = r * prm.pos_per_round + g * kPosPerGroup;
 
         if (!(lf & kFinal)) {
-          uint8_t* act_row = s_act + (h * 8) * kPlaneBytes + (group_origin_row(g) + row) * 16;
+          uint8_t* act_row = s_act + (h * (G::kHalfCh / 8)) * kPlaneBytes + (group_origin_row(g) + row) * 16;
           uint4* dbg_row = (prm.dbg != nullptr && L == nl - 1 && pos_base < prm.n)
-                               ? prm.dbg + (static_cast<size_t>(pos_base / kPosPerGroup) * kPlanes + h * 8) * kTile + row : nullptr;
-          const float* wv = s_wv + h * 64;
+                               ? prm.dbg + (static_cast<size_t>(pos_base / kPosPerGroup) * kPlanes + h * (G::kHalfCh / 8)) * kTile + row : nullptr;
+          const float* wv = s_wv + h * G::kHalfCh;
           float vacc = 0.f;
 #define E55_EPI(RES)                                                                                          \
           if (lf & kValueTap) {                                                                               \
-            if (lf & kHasRes) vacc = epilogue_half<true, true, true>(taddr, bias, act_row, RES, wv, row_valid, dbg_row, bar_part, lane, rank);   \
-            else vacc = epilogue_half<false, true, true>(taddr, bias, act_row, RES, wv, row_valid, dbg_row, bar_part, lane, rank);  \
+            if (lf & kHasRes) vacc = epilogue_half<F, true, true, true>(taddr, bias, act_row, RES, wv, row_valid, dbg_row, bar_part, lane, rank);   \
+            else vacc = epilogue_half<F, false, true, true>(taddr, bias, act_row, RES, wv, row_valid, dbg_row, bar_part, lane, rank);  \
           } else if (lf & kHasRes) {                                                                          \
-            epilogue_half<true, true, false>(taddr, bias, act_row, RES, wv, row_valid, dbg_row, bar_part, lane, rank);              \
+            epilogue_half<F, true, true, false>(taddr, bias, act_row, RES, wv, row_valid, dbg_row, bar_part, lane, rank);              \
           } else if (lf & kUpdRes) {                                                                          \
-            epilogue_half<false, true, false>(taddr, bias, act_row, RES, wv, row_valid, dbg_row, bar_part, lane, rank);             \
+            epilogue_half<F, false, true, false>(taddr, bias, act_row, RES, wv, row_valid, dbg_row, bar_part, lane, rank);             \
           } else {                                                                                            \
-            epilogue_half<false, false, false>(taddr, bias, act_row, RES, wv, row_valid, dbg_row, bar_part, lane, rank);            \
+            epilogue_half<F, false, false, false>(taddr, bias, act_row, RES, wv, row_valid, dbg_row, bar_part, lane, rank);            \
           }
-          if (g == 0) { E55_EPI(res_a) } else { E55_EPI(res_b) }
+          if (G::kGroups == 1 || g == 0) { E55_EPI(res_a) } else if constexpr (G::kGroups == 2) { E55_EPI(res_b) }
 #undef E55_EPI
           // value 1x1 conv: this thread's half of the channel dot product (summed in the value tail)
           if (lf & kValueTap) {
@@ -598,15 +628,15 @@ tower_kernel(const Params prm) {
           const bool out_valid = row_valid && pos < prm.n;
           float* dst = prm.policy + static_cast<size_t>(pos) * (kPolicyCh * kSq) + sq;
 #pragma unroll
-          for (int cb = 0; cb < 2; ++cb) {
-            if (h == 1 && cb == 1) break;  // channels 96.. do not exist
+          for (int cb = 0; cb < G::kCb; ++cb) {
+            if (h * G::kHalfCh + cb * 32 >= kPolicyN) break;  // columns beyond the padded policy width do not exist
             uint32_t v[32];
             ptx::tmem_ld_32x32b_x32(taddr + cb * 32, v);
             ptx::tmem_ld_wait();
             if (out_valid) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
-                const int c = h * 64 + cb * 32 + j;
+                const int c = h * G::kHalfCh + cb * 32 + j;
                 if (c < kPolicyCh) dst[c * kSq] = __uint_as_float(v[j]) + bias[cb * 32 + j];
               }
             }
@@ -614,7 +644,8 @@ tower_kernel(const Params prm) {
           // no activations written, but keep the per-layer barrier phases in step
           ptx::tc_fence_before_sync();
           __syncwarp();
-          if (lane == 0) { arrive_on_leader(&bar_part[0], rank); arrive_on_leader(&bar_part[1], rank); }
+          if (lane == 0)
+            for (int cb = 0; cb < G::kCb; ++cb) arrive_on_leader(&bar_part[cb], rank);
         }
         if (kProf) {
           const long long te2 = clock64();
@@ -674,10 +705,18 @@ inline void init(State& s, int blocks, int filters, int in_planes, int sms) {
   s.blocks = blocks; s.filters = filters; s.in_planes = in_planes; s.sms = sms;
   s.nlayers = 1 + 2 * blocks + 2;
   s.in_planes8 = ((in_planes + 15) / 16) * 2;
-  s.nslices = (s.in_planes8 + kPlanes - 1) / kPlanes;
+  const int planes = filters / 8;
+  s.nslices = planes > 0 ? (s.in_planes8 + planes - 1) / planes : 0;
 }
 
-inline bool supported(const State& s) { return s.filters == kF && s.nlayers <= 255; }
+inline bool supported(const State& s) { return (s.filters == 128 || s.filters == 256) && s.nlayers <= 255; }
+
+struct HostGeo { int groups, planes, rows_total, act_bytes, kblocks; bool bias_in_smem; };
+inline HostGeo host_geo(int filters) {
+  if (filters == 128)
+    return HostGeo{Geo<128>::kGroups, Geo<128>::kPlanes, Geo<128>::kRowsTotal, Geo<128>::kActBytes, Geo<128>::kKBlocks, Geo<128>::kBiasInSmem};
+  return HostGeo{Geo<256>::kGroups, Geo<256>::kPlanes, Geo<256>::kRowsTotal, Geo<256>::kActBytes, Geo<256>::kKBlocks, Geo<256>::kBiasInSmem};
+}
 
 inline void free_weights(State& s) {
   cudaFree(s.d_wimg); cudaFree(s.d_chunks); cudaFree(s.d_layers); cudaFree(s.d_bias);
@@ -694,7 +733,7 @@ inline cudaError_t alloc_buffers(State& s, int cap) {
   if (!supported(s)) return cudaSuccess;
   free_buffers(s);
   const size_t groups = (static_cast<size_t>(cap) + kPosPerGroup - 1) / kPosPerGroup + 4;
-  cudaError_t e = cudaMalloc(&s.d_dbg, groups * kPlanes * kTile * sizeof(uint4));
+  cudaError_t e = cudaMalloc(&s.d_dbg, groups * (s.filters / 8) * kTile * sizeof(uint4));
   if (e != cudaSuccess) return e;
   s.capacity = cap;
   return cudaSuccess;
@@ -715,9 +754,12 @@ inline cudaError_t set_weights(State& s, const std::vector<std::vector<float>>& 
   if (!supported(s)) return cudaSuccess;
   free_weights(s);
   s.heads = heads;
+  const int F = s.filters;
+  const HostGeo geo = host_geo(F);
+  const int kPlanes = geo.planes;
   std::vector<Chunk> chunks;
   std::vector<uint16_t> img;
-  std::vector<float> bias(static_cast<size_t>(s.nlayers) * kF, 0.f);
+  std::vector<float> bias(static_cast<size_t>(s.nlayers) * F, 0.f);
   s.layers.assign(s.nlayers, LayerInfo{});
 
   // chunk = (layer, slice, K-block set, board row dy): ntaps taps x (nk0 + nk1) K-steps, MMA order
@@ -728,12 +770,12 @@ inline cudaError_t set_weights(State& s, const std::vector<std::vector<float>>& 
     Chunk ch{};
     ch.gofs = static_cast<uint32_t>(img.size() * 2);
     ch.half16 = static_cast<uint16_t>(ntaps * (k0.nk + k1.nk) * 2 * (ndim / 2));
-    ch.a_off = static_cast<int16_t>(first_plane * kRowsTotal + dy * kW);
+    ch.a_off = static_cast<int16_t>(first_plane * geo.rows_total + dy * kW);
     ch.nk0 = static_cast<uint8_t>(k0.nk);
     ch.nk1 = static_cast<uint8_t>(k1.nk);
-    ch.ntaps = static_cast<uint8_t>(ntaps);
+    ch.need = static_cast<uint8_t>(need);
     ch.ndim8 = static_cast<uint8_t>(ndim / 8);
-    ch.flags = static_cast<uint8_t>(flags | (need << 4));
+    ch.flags = static_cast<uint8_t>(flags | (ntaps == 1 ? kSingleTap : 0u));
     ch.layer = static_cast<uint8_t>(layer);
     for (int half = 0; half < 2; ++half)
       for (int t = 0; t < ntaps; ++t)
@@ -757,12 +799,12 @@ inline cudaError_t set_weights(State& s, const std::vector<std::vector<float>>& 
     const bool is_final = L == s.nlayers - 1;
     const bool is_stem = L == 0;
     const bool is_policy_conv = L == s.nlayers - 2;
-    const int cin = is_stem ? s.in_planes : kF;
-    const int cout = is_final ? kPolicyCh : kF;
-    const int ndim = is_final ? kPolicyN : kF;
+    const int cin = is_stem ? s.in_planes : F;
+    const int cout = is_final ? kPolicyCh : F;
+    const int ndim = is_final ? kPolicyN : F;
     const float* w = is_final ? heads.policy_w : conv_w[L].data();
     const float* b = is_final ? heads.policy_b : conv_b[L].data();
-    for (int o = 0; o < cout; ++o) bias[static_cast<size_t>(L) * kF + o] = b[o];
+    for (int o = 0; o < cout; ++o) bias[static_cast<size_t>(L) * F + o] = b[o];
     li.ndim = ndim;
     li.flags = 0;
     if (is_final) li.flags = kFinal;
@@ -778,17 +820,25 @@ inline cudaError_t set_weights(State& s, const std::vector<std::vector<float>>& 
       const int npl = std::min(kPlanes, planes_total - pl0);
       const bool first_sl = sl == 0, last_sl = sl == nslices - 1;
       if (is_final) {
-        // 1x1 conv: one chunk, all 8 K-steps over planes 0..15, needs every activation K block
+        // 1x1 conv: one chunk, every K-step over all planes, needs every activation K block
         emit(L, 0, 1, 0, 0, KB{0, npl / 2}, KB{0, 0}, ndim, cin, cout, w,
-             kFirstOfSlice | kLastOfSlice | kFirstOfLayer | kLastOfLayer, 0xFu);
+             kFirstOfSlice | kLastOfSlice | kFirstOfLayer | kLastOfLayer, (1u << geo.kblocks) - 1u);
         continue;
       }
-      // K-block sets of this slice, in issue order
+      // K-block sets of this slice, in the order in which the previous layer's epilogue finishes them
+      // (its two thread halves work through their K blocks in parallel)
       struct Set { int plane; KB k0, k1; uint32_t need; };
       std::vector<Set> sets;
-      if (npl == kPlanes) {
-        for (int pi = 0; pi < 2; ++pi)
-          sets.push_back(Set{pi * 4, KB{(pl0 + pi * 4) * 8, 2}, KB{(pl0 + pi * 4 + 8) * 8, 2}, (1u << pi) | (1u << (pi + 2))});
+      const int hk = geo.kblocks / 2;  // K blocks per epilogue half
+      if (npl == kPlanes && F == 128) {
+        for (int pi = 0; pi < hk; ++pi)   // two K blocks per chunk: {pi, pi + hk}
+          sets.push_back(Set{pi * 4, KB{(pl0 + pi * 4) * 8, 2}, KB{(pl0 + (pi + hk) * 4) * 8, 2}, (1u << pi) | (1u << (pi + hk))});
+      } else if (npl == kPlanes) {
+        for (int pi = 0; pi < hk; ++pi)   // one K block per chunk (N = 256 fills the stage): pi, pi + hk, ...
+          for (int hh = 0; hh < 2; ++hh) {
+            const int kb = pi + hh * hk;
+            sets.push_back(Set{kb * 4, KB{(pl0 + kb * 4) * 8, 2}, KB{0, 0}, 1u << kb});
+          }
       } else {
         for (int kb = 0; kb * 4 < npl; ++kb)
           sets.push_back(Set{kb * 4, KB{(pl0 + kb * 4) * 8, std::min(2, (npl - kb * 4) / 2)}, KB{0, 0}, 1u << kb});
@@ -803,7 +853,7 @@ inline cudaError_t set_weights(State& s, const std::vector<std::vector<float>>& 
           if (last && last_sl) fl |= kLastOfLayer;
           uint32_t need = 0;
           if (!is_stem && dy == 0) need = sets[si].need;          // K blocks written by the previous epilogue
-          if (is_stem && first && first_sl) need = 0xFu;           // previous round fully drained (TMEM + planes)
+          if (is_stem && first && first_sl) need = (1u << geo.kblocks) - 1u;   // previous round fully drained
           emit(L, dy * 3, 3, dy - 1, sets[si].plane, sets[si].k0, sets[si].k1, ndim, cin, cout, w, fl, need);
         }
     }
@@ -822,8 +872,8 @@ inline cudaError_t set_weights(State& s, const std::vector<std::vector<float>>& 
   if ((e = cudaMemcpy(s.d_bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
 
   s.nchunks = static_cast<int>(chunks.size());
-  const size_t fixed = kActBytes + static_cast<size_t>(s.nlayers) * kF * 4 + kF * 4 + 4 * kPosPerGroup * kSq * 4 + 32 * 4 +
-                       chunks.size() * sizeof(Chunk) + (2 * kMaxStages + 18) * 8 + 16;
+  const size_t fixed = geo.act_bytes + (geo.bias_in_smem ? static_cast<size_t>(s.nlayers) * F * 4 : 0) + F * 4 +
+                       4 * kPosPerGroup * kSq * 4 + chunks.size() * sizeof(Chunk) + (2 * kMaxStages + 18) * 8 + 16;
   s.nstages = static_cast<int>(std::min<size_t>(kMaxStages, (232448 - std::min<size_t>(fixed, 232448)) / kStageBytes));
   s.smem_bytes = fixed + static_cast<size_t>(s.nstages) * kStageBytes;
   s.attr_set = false;
@@ -833,16 +883,21 @@ inline cudaError_t set_weights(State& s, const std::vector<std::vector<float>>& 
 // nlayers_run < nlayers: stop after that many layers and leave the packed activations in d_dbg.
 inline cudaError_t run(State& s, const float* d_planes, int n, float* d_policy, float* d_value, int nlayers_run,
                        cudaStream_t stream, int* launched, std::string* why) {
-  if (!supported(s)) { *why = "the tcgen05 path supports filters == 128 only"; return cudaSuccess; }
+  if (!supported(s)) { *why = "the tcgen05 path supports 128 or 256 filters"; return cudaSuccess; }
   if (s.nstages < 3) { *why = "network too deep for the shared-memory layer tables"; return cudaSuccess; }
   if (!s.attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tower_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(s.smem_bytes));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tower_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(s.smem_bytes));
+    const int sm = static_cast<int>(s.smem_bytes);
+    cudaError_t e = s.filters == 128
+        ? cudaFuncSetAttribute(tower_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm)
+        : cudaFuncSetAttribute(tower_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    if (e == cudaSuccess)
+      e = s.filters == 128 ? cudaFuncSetAttribute(tower_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm)
+                           : cudaFuncSetAttribute(tower_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
     if (e != cudaSuccess) { *why = "cudaFuncSetAttribute"; return e; }
     s.attr_set = true;
   }
   // latency mode: while the batch fits the machine with one 4-position group per CTA, leave group B out
-  const int ppr = n <= kPosPerGroup * 2 * std::max(1, s.sms / 2) ? kPosPerGroup : kPosPerRound;
+  const int ppr = (s.filters != 128 || n <= kPosPerGroup * 2 * std::max(1, s.sms / 2)) ? kPosPerGroup : kPosPerRound;
   const int rounds = (n + ppr - 1) / ppr;
   Params p{};
   p.wimg = s.d_wimg; p.chunks = s.d_chunks; p.layers = s.d_layers; p.bias = s.d_bias;
@@ -857,8 +912,13 @@ inline cudaError_t run(State& s, const float* d_planes, int n, float* d_policy, 
   const int pairs = std::min((rounds + 1) / 2, std::max(1, s.sms / 2));
   const int grid = 2 * pairs;
   if (s.ev0) cudaEventRecord(s.ev0, stream);
-  if (p.prof) tower_kernel<true><<<grid, kThreads, s.smem_bytes, stream>>>(p);
-  else tower_kernel<false><<<grid, kThreads, s.smem_bytes, stream>>>(p);
+  if (s.filters == 128) {
+    if (p.prof) tower_kernel<128, true><<<grid, kThreads, s.smem_bytes, stream>>>(p);
+    else tower_kernel<128, false><<<grid, kThreads, s.smem_bytes, stream>>>(p);
+  } else {
+    if (p.prof) tower_kernel<256, true><<<grid, kThreads, s.smem_bytes, stream>>>(p);
+    else tower_kernel<256, false><<<grid, kThreads, s.smem_bytes, stream>>>(p);
+  }
   if (s.ev1) cudaEventRecord(s.ev1, stream);
   ++*launched;
   cudaError_t e = cudaGetLastError();
@@ -876,7 +936,7 @@ inline cudaError_t debug_layers(State& s, const float* d_planes, int n, int ncon
                                 cudaStream_t stream, int* launched, std::string* why) {
   cudaError_t e = run(s, d_planes, n, nullptr, nullptr, nconv, stream, launched, why);
   if (e != cudaSuccess || !why->empty()) return e;
-  unpack_debug_kernel<<<n, 128, 0, stream>>>(s.d_dbg, d_out_nchw, n);
+  unpack_debug_kernel<<<n, 128, 0, stream>>>(s.d_dbg, d_out_nchw, n, s.filters);
   ++*launched;
   e = cudaGetLastError();
   if (e != cudaSuccess) *why = "unpack_debug_kernel launch";

@@ -205,8 +205,8 @@ def test_device_resident_api(nets):
 
 
 def test_small_and_scaled_architectures(weights_default):
-    """Other tower shapes: 2 blocks on the tcgen05 path; 256 filters on the fp32 path only."""
-    from erweitern_55_b200 import _capi
+    """Other tower shapes on both paths: 2 blocks x 128 filters on 40 input planes, 2 blocks x 256 filters
+    (the width of BASELINE.json configs[4]; the tcgen05 kernel has a 256-filter instantiation)."""
     from erweitern_55_b200.network import Network
     O = _oracle()
     w2 = W.init_weights(blocks=2, filters=128, in_planes=40, seed=5, perturbed=True)
@@ -216,12 +216,38 @@ def test_small_and_scaled_architectures(weights_default):
         net = Network(blocks=2, in_planes=40, precision=prec, weights=w2)
         _check(*net.predict(x), po, vo, tol)
         net.close()
-    w3 = W.init_weights(blocks=1, filters=256, seed=6, perturbed=True)
-    x = synth.synthetic_planes(5, seed=3)
-    net = Network(blocks=1, filters=256, precision="fp32", weights=w3)
-    _check(*net.predict(x), *O.forward_torch(w3, x), FP32_TOL)
-    with pytest.raises(_capi.E55Error):
-        net.set_precision("bf16")
+    w3 = W.init_weights(blocks=2, filters=256, seed=6, perturbed=True)
+    for n in (1, 5, 37):
+        x = synth.synthetic_planes(n, seed=3 + n)
+        po, vo = O.forward_torch(w3, x)
+        for prec, tol in (("fp32", FP32_TOL), ("bf16", BF16_TOL_PERTURBED)):
+            net = Network(blocks=2, filters=256, precision=prec, weights=w3)
+            _check(*net.predict(x), po, vo, tol)
+            if prec == "bf16":
+                a = net.debug_activations(x, 5)
+                net.set_precision("fp32")
+                b = net.debug_activations(x, 5)
+                assert np.abs(a - b).max() <= 0.02 * max(1.0, np.abs(b).max())
+            net.close()
+
+
+def test_scaled_tower_20x256():
+    """BASELINE.json configs[4]: 20 residual blocks x 256 filters.  With Keras-default init (identity BN) the
+    activations of a 43-layer tower grow, so the bf16 tolerance is stated relative to the logit scale:
+    |dlogit| <= 1 % of max|logit| (the 7x128 net's 0.03 is 1.5 % of its +-2 range), |dvalue| <= 0.03."""
+    from erweitern_55_b200.network import Network
+    O = _oracle()
+    w = W.init_weights(blocks=20, filters=256, seed=55)
+    x = synth.synthetic_planes(24, seed=31)
+    po, vo = O.forward_torch(w, x)
+    net = Network(blocks=20, filters=256, precision="bf16", weights=w)
+    p, v = net.predict(x)
+    scale = float(np.abs(po).max())
+    assert np.abs(p - po).max() <= 0.01 * scale, (np.abs(p - po).max(), scale)
+    assert np.abs(v - vo).max() <= 0.03
+    top2 = np.sort(po, axis=1)[:, -2:]
+    decisive = (top2[:, 1] - top2[:, 0]) > 0.02 * scale
+    assert (p.argmax(1)[decisive] == po.argmax(1)[decisive]).all()
     net.close()
 
 
