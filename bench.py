@@ -329,6 +329,7 @@ def main():
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     net.close()
     if world > 1:
         dist.destroy_process_group()

@@ -258,9 +258,9 @@ tower_kernel(const Params prm) {
   uint64_t* bar_empty = bars + kMaxStages;            // [stages] both groups' MMAs on the stage are done
   uint64_t* bar_tmem_full = bars + 2 * kMaxStages;    // [2] accumulator of a group complete
   uint64_t* bar_act_part = bar_tmem_full + 2;         // [groups][F/32 / groups... 8 in all] leader only: K block written by both CTAs
-  uint64_t* bar_in_full = bar_act_part + 8;           // [2] leader only: stem input slice written
-  uint64_t* bar_in_empty = bar_in_full + 2;           // [2] stem input planes may be overwritten
-  uint64_t* bar_v = bar_in_empty + 2;                 // [2] value-conv partials of a group written by all 8 warps
+  uint64_t* bar_in_full = bar_act_part + 8;           // [2 groups][2 plane halves] leader only: stem input slice written
+  uint64_t* bar_in_empty = bar_in_full + 4;           // [2][2] that half of the planes may be overwritten
+  uint64_t* bar_v = bar_in_empty + 4;                 // [2] value-conv partials of a group written by all 8 warps
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_v + 2);
   volatile uint32_t* s_apos = s_tmem + 1;             // chunks issued so far by group A's issuer
 
@@ -291,8 +291,10 @@ tower_kernel(const Params prm) {
     for (int kb = 0; kb < 8; ++kb) ptx::mbar_init(&bar_act_part[kb], 8);               // 4 warps x 2 CTAs
     for (int g = 0; g < 2; ++g) {
       ptx::mbar_init(&bar_tmem_full[g], 1);
-      ptx::mbar_init(&bar_in_full[g], 16);                                           // 8 warps x 2 CTAs
-      ptx::mbar_init(&bar_in_empty[g], 1);
+      for (int hh = 0; hh < 2; ++hh) {
+        ptx::mbar_init(&bar_in_full[g * 2 + hh], 16);                                // 8 warps x 2 CTAs
+        ptx::mbar_init(&bar_in_empty[g * 2 + hh], 1);
+      }
       ptx::mbar_init(&bar_v[g], 8);
     }
     ptx::fence_mbar_init();
@@ -353,7 +355,7 @@ tower_kernel(const Params prm) {
     const uint32_t a_lo_base = ((ptx::smem_u32(s_act) + group_origin_row(g) * 16) >> 4) |
                                (static_cast<uint32_t>(kPlaneBytes >> 4) << 16);
     const uint32_t b_lo_base = ptx::smem_u32(s_ring) >> 4;
-    uint32_t s = 0, ph = 0, round_seq = 0, stem_slices = 0;
+    uint32_t s = 0, ph = 0, round_seq = 0, stem_idx = 0, stem_full[2] = {0u, 0u};
     long long t_start = 0, t_issue = 0, t_full = 0, t_act = 0;
     if (kProf) t_start = clock64();
     for (int pr = pair0; pr < npair_rounds; pr += pair_stride, ++round_seq) {
@@ -375,8 +377,11 @@ tower_kernel(const Params prm) {
         if (kProf) t1 = clock64();
         const uint32_t epoch = round_seq * nl + ch.layer;
         if ((ch.flags & kFirstOfSlice) && ch.layer == 0) {
-          ptx::mbar_wait_cluster(&bar_in_full[g], stem_slices & 1);
-          ++stem_slices;
+          // stem input slices alternate between the two halves of the activation planes
+          if (ch.flags & kFirstOfLayer) stem_idx = 0;
+          const uint32_t hh = stem_idx & 1;
+          ptx::mbar_wait_cluster(&bar_in_full[g * 2 + hh], stem_full[hh] & 1);
+          ++stem_full[hh];
         }
         if (ch.need && epoch > 0) {
           // activation K blocks written by the previous layer's (progressive) epilogue in both CTAs
@@ -431,13 +436,17 @@ tower_kernel(const Params prm) {
           }
           ptx::umma_commit_2sm(&bar_empty[s], 3);
           if (!has_b) ptx::umma_commit_2sm(&bar_empty[s], 3);
-          if ((ch.flags & kLastOfSlice) && ch.layer == 0 && !(ch.flags & kLastOfLayer))
-            ptx::umma_commit_2sm(&bar_in_empty[g], 3);
+          if ((ch.flags & kLastOfSlice) && ch.layer == 0 && stem_idx + 2 < static_cast<uint32_t>(prm.nslices))
+            ptx::umma_commit_2sm(&bar_in_empty[g * 2 + (stem_idx & 1)], 3);   // a later slice reuses this half
           if (ch.flags & kLastOfLayer) {
             ptx::umma_commit_2sm(&bar_tmem_full[g], 3);
-            if (ch.layer == nl - 1) ptx::umma_commit_2sm(&bar_in_empty[g], 3);
+            if (ch.layer == nl - 1) {   // round end: both halves are free for the next round's input
+              ptx::umma_commit_2sm(&bar_in_empty[g * 2 + 0], 3);
+              ptx::umma_commit_2sm(&bar_in_empty[g * 2 + 1], 3);
+            }
           }
         }
+        if ((ch.flags & kLastOfSlice) && ch.layer == 0) ++stem_idx;
         __syncwarp();
         if (g == 0 && lane == 0) *s_apos = gbase + c + 1;
         if (++s == nstages) { s = 0; ph ^= 1; }
@@ -472,7 +481,7 @@ tower_kernel(const Params prm) {
 #pragma unroll
     for (int i = 0; i < (G::kGroups == 2 ? F / 4 : 1); ++i) res_b[i] = 0u;
     uint32_t round_seq = 0;
-    uint32_t slices_done[2] = {0u, 0u};
+    uint32_t conv_cnt[4] = {0u, 0u, 0u, 0u};             // input slices written so far per (group, plane half)
     long long t_wait = 0, t_work = 0;
 
     for (int pr = pair0; pr < npair_rounds; pr += pair_stride, ++round_seq) {
@@ -498,9 +507,21 @@ tower_kernel(const Params prm) {
         for (;;) {  // serve whichever event is ready first (group A preferred: it runs ahead)
           if (next_layer[0] < nl && ptx::mbar_test_wait(&bar_tmem_full[0], (round_seq * nl + next_layer[0]) & 1)) { g = 0; break; }
           if (next_layer[1] < nl && ptx::mbar_test_wait(&bar_tmem_full[1], (round_seq * nl + next_layer[1]) & 1)) { g = 1; break; }
-          // stem input: slice k of a group may be written once the MMAs that read slice k-1 are done
-          if (next_slice[0] < prm.nslices && (slices_done[0] == 0 || ptx::mbar_test_wait(&bar_in_empty[0], (slices_done[0] - 1) & 1))) { g = 0; convert = true; break; }
-          if (next_slice[1] < prm.nslices && (slices_done[1] == 0 || ptx::mbar_test_wait(&bar_in_empty[1], (slices_done[1] - 1) & 1))) { g = 1; convert = true; break; }
+          // stem input: slice k goes to plane half k&1 once the MMAs that read that half's previous slice are done
+          // (the group that is further behind with its input goes first, so neither starves the other)
+          {
+            const int g0 = next_slice[1] < next_slice[0] ? 1 : 0;
+            bool found = false;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const int gg = g0 ^ k;
+              if (next_slice[gg] < prm.nslices) {
+                const int b = gg * 2 + (next_slice[gg] & 1);
+                if (conv_cnt[b] == 0 || ptx::mbar_test_wait(&bar_in_empty[b], (conv_cnt[b] - 1) & 1)) { g = gg; convert = true; found = true; break; }
+              }
+            }
+            if (found) break;
+          }
           if (fc_pending[0] && ptx::mbar_test_wait(&bar_v[0], round_seq & 1)) { g = 0; value_fc = true; break; }
           if (fc_pending[1] && ptx::mbar_test_wait(&bar_v[1], round_seq & 1)) { g = 1; value_fc = true; break; }
         }
@@ -550,8 +571,10 @@ tower_kernel(const Params prm) {
           // fp32 NCHW planes -> bf16 wide-board planes of this group (network.py:255-274 built the input):
           // one item = 8 consecutive channels of one square of one position = one 16-byte row entry
           const int sl = next_slice[g];
-          const int pl0 = sl * kPlanes;
-          const int npl = min(kPlanes, prm.in_planes8 - pl0);
+          constexpr int kSlicePlanes = kPlanes / 2;
+          const int hh = sl & 1;
+          const int pl0 = sl * kSlicePlanes;                       // first input plane (8 channels each) of the slice
+          const int npl = min(kSlicePlanes, prm.in_planes8 - pl0);
           const int pos0 = r * prm.pos_per_round + g * kPosPerGroup;
           const int nitems = kPosPerGroup * npl * kSq;
           for (int it0 = threadIdx.x; it0 < nitems; it0 += 256 * 4) {
@@ -576,15 +599,15 @@ tower_kernel(const Params prm) {
                 const uint4 pk = make_uint4(ptx::pack_bf16x2(f[u][0], f[u][1]), ptx::pack_bf16x2(f[u][2], f[u][3]),
                                             ptx::pack_bf16x2(f[u][4], f[u][5]), ptx::pack_bf16x2(f[u][6], f[u][7]));
                 const int rr = (s_ / 5) * kW + p * 6 + s_ % 5;
-                *reinterpret_cast<uint4*>(s_act + c8 * kPlaneBytes + (group_origin_row(g) + rr) * 16) = pk;
+                *reinterpret_cast<uint4*>(s_act + (hh * kSlicePlanes + c8) * kPlaneBytes + (group_origin_row(g) + rr) * 16) = pk;
               }
             }
           }
           ptx::fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) arrive_on_leader(&bar_in_full[g], rank);
+          if (lane == 0) arrive_on_leader(&bar_in_full[g * 2 + hh], rank);
           next_slice[g] = sl + 1;
-          ++slices_done[g];
+          ++conv_cnt[g * 2 + hh];
           continue;
         }
         ptx::tc_fence_after_sync();
@@ -705,8 +728,8 @@ inline void init(State& s, int blocks, int filters, int in_planes, int sms) {
   s.blocks = blocks; s.filters = filters; s.in_planes = in_planes; s.sms = sms;
   s.nlayers = 1 + 2 * blocks + 2;
   s.in_planes8 = ((in_planes + 15) / 16) * 2;
-  const int planes = filters / 8;
-  s.nslices = planes > 0 ? (s.in_planes8 + planes - 1) / planes : 0;
+  const int slice_planes = filters / 16;   // stem input slices fill half of the activation planes, alternating
+  s.nslices = slice_planes > 0 ? (s.in_planes8 + slice_planes - 1) / slice_planes : 0;
 }
 
 inline bool supported(const State& s) { return (s.filters == 128 || s.filters == 256) && s.nlayers <= 255; }
@@ -814,10 +837,12 @@ inline cudaError_t set_weights(State& s, const std::vector<std::vector<float>>& 
     else li.flags = kRelu | kHasRes | kUpdRes;                  // second conv: relu(y + x)
     if (L == s.nlayers - 3) li.flags |= kValueTap;              // trunk output feeds the value head
     const int planes_total = is_stem ? s.in_planes8 : kPlanes;  // 8-channel planes of the input
-    const int nslices = (planes_total + kPlanes - 1) / kPlanes;
+    const int slice_planes = is_stem ? kPlanes / 2 : kPlanes;   // stem: double-buffered half-plane slices
+    const int nslices = (planes_total + slice_planes - 1) / slice_planes;
     for (int sl = 0; sl < nslices; ++sl) {
-      const int pl0 = sl * kPlanes;
-      const int npl = std::min(kPlanes, planes_total - pl0);
+      const int pl0 = sl * slice_planes;                          // first input plane of the slice
+      const int npl = std::min(slice_planes, planes_total - pl0);
+      const int base = is_stem ? (sl & 1) * slice_planes : 0;     // activation plane the slice starts at
       const bool first_sl = sl == 0, last_sl = sl == nslices - 1;
       if (is_final) {
         // 1x1 conv: one chunk, every K-step over all planes, needs every activation K block
@@ -830,7 +855,12 @@ inline cudaError_t set_weights(State& s, const std::vector<std::vector<float>>& 
       struct Set { int plane; KB k0, k1; uint32_t need; };
       std::vector<Set> sets;
       const int hk = geo.kblocks / 2;  // K blocks per epilogue half
-      if (npl == kPlanes && F == 128) {
+      if (is_stem && F == 128) {
+        sets.push_back(Set{base, KB{pl0 * 8, npl / 2}, KB{0, 0}, 0u});   // <= 4 K-steps over <= 8 consecutive planes
+      } else if (is_stem) {
+        for (int kb = 0; kb * 4 < npl; ++kb)
+          sets.push_back(Set{base + kb * 4, KB{(pl0 + kb * 4) * 8, std::min(2, (npl - kb * 4) / 2)}, KB{0, 0}, 0u});
+      } else if (npl == kPlanes && F == 128) {
         for (int pi = 0; pi < hk; ++pi)   // two K blocks per chunk: {pi, pi + hk}
           sets.push_back(Set{pi * 4, KB{(pl0 + pi * 4) * 8, 2}, KB{(pl0 + (pi + hk) * 4) * 8, 2}, (1u << pi) | (1u << (pi + hk))});
       } else if (npl == kPlanes) {
@@ -873,7 +903,7 @@ inline cudaError_t set_weights(State& s, const std::vector<std::vector<float>>& 
 
   s.nchunks = static_cast<int>(chunks.size());
   const size_t fixed = geo.act_bytes + (geo.bias_in_smem ? static_cast<size_t>(s.nlayers) * F * 4 : 0) + F * 4 +
-                       4 * kPosPerGroup * kSq * 4 + chunks.size() * sizeof(Chunk) + (2 * kMaxStages + 18) * 8 + 16;
+                       4 * kPosPerGroup * kSq * 4 + chunks.size() * sizeof(Chunk) + (2 * kMaxStages + 22) * 8 + 16;
   s.nstages = static_cast<int>(std::min<size_t>(kMaxStages, (232448 - std::min<size_t>(fixed, 232448)) / kStageBytes));
   s.smem_bytes = fixed + static_cast<size_t>(s.nstages) * kStageBytes;
   s.attr_set = false;

@@ -37,5 +37,5 @@ big = [(c, int(ib[c,1]-ib[c,0]), int(ib[c,2]-ib[c,1])) for c in range(len(ib)) i
 print("B stalls >1000:", big[:40])
 ep = ep[np.argsort(ep[:, 0])]
 print("epilogue durations: median", np.median(ep[:,1]-ep[:,0]), "max", (ep[:,1]-ep[:,0]).max())
-for c in range(36, 64):
+for c in list(range(0, 24)) + list(range(36, 44)):
     print(f"c={c:3d} A t0={ia[c,0]-t0:7d} wF={ia[c,1]-ia[c,0]:5d} wA={ia[c,2]-ia[c,1]:5d} is={ia[c,3]-ia[c,2]:5d} | B t0={ib[c,0]-t0:7d} wF={ib[c,1]-ib[c,0]:5d} wA={ib[c,2]-ib[c,1]:5d} is={ib[c,3]-ib[c,2]:5d}")
