@@ -304,6 +304,30 @@ def main():
            "d2h_bytes_per_step": B * 1725 * 4 + B * 4, "steps": e2e_steps,
            "timing": "host wall clock around blocking e55_predict calls (pinned host buffers), max over ranks"}
 
+    # ---- same call with the compact input format (e55_predict_packed; not the reference's format) ---
+    from erweitern_55_b200 import packing
+    packed = [packing.pack_planes(hp.numpy()) for hp in host_pool]
+    pk_bits = [torch.from_numpy(b.view(np.int32)).pin_memory() for b, _ in packed]
+    pk_scale = [torch.from_numpy(sc).pin_memory() for _, sc in packed]
+
+    def packed_step(i):
+        net._check(lib.e55_predict_packed(ctx, pk_bits[i % 3].data_ptr(), pk_scale[i % 3].data_ptr(), B,
+                                          host_policy.data_ptr(), host_value.data_ptr()))
+
+    for i in range(3):
+        packed_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        packed_step(i)
+    pk_s = time.perf_counter() - t0
+    barrier()
+    pk_units, pk_max = sharding.aggregate(B * e2e_steps, pk_s, device=dev)
+    e2e_packed = {"value": pk_units / pk_max, "unit": UNIT, "h2d_bytes_per_step": B * 266 * 8,
+                  "d2h_bytes_per_step": B * 1725 * 4 + B * 4, "steps": e2e_steps,
+                  "note": "e55_predict_packed: bit-packed planes (8 B/plane) instead of the reference's float32 planes; "
+                          "identical outputs; not the drop-in input format, reported beside e2e"}
+
     # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------------
     cpu_baseline = None
     if rank == 0 and world == 1:
@@ -323,7 +347,7 @@ def main():
                        "batch_per_gpu": B, "parallelism": f"replicas x{world} (independent positions, no collective)",
                        "l2": f"inputs rotate over {n_pool} distinct device batches = {n_pool * in_bytes >> 20} MiB > 126 MiB L2",
                        "flop_per_position": flops, "host_cpu": model, "host_cores": ncpu},
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
+            "e2e": e2e, "e2e_packed": e2e_packed, "gpu_launches": launches, "clocks": clocks.summary(),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "wall_s": t_wall,
         }
         sys.stdout.flush()

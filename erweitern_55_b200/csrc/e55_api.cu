@@ -76,6 +76,8 @@ struct e55_ctx {
   float* d_value = nullptr;
   float* d_probs = nullptr;
   uint8_t* d_mask = nullptr;
+  uint32_t* d_bits = nullptr;   // packed input staging: [capacity][in_planes]
+  float* d_scale = nullptr;
 };
 
 namespace {
@@ -111,8 +113,9 @@ void free_buffers(e55_ctx* c) {
   cudaFree(c->d_in);
   for (auto& p : c->d_act) { cudaFree(p); p = nullptr; }
   cudaFree(c->d_policy); cudaFree(c->d_value); cudaFree(c->d_probs); cudaFree(c->d_mask);
-  c->d_in = c->d_policy = c->d_value = c->d_probs = nullptr;
-  c->d_mask = nullptr;
+  cudaFree(c->d_bits); cudaFree(c->d_scale);
+  c->d_in = c->d_policy = c->d_value = c->d_probs = c->d_scale = nullptr;
+  c->d_mask = nullptr; c->d_bits = nullptr;
   e55::tc::free_buffers(c->tc);
   c->capacity = 0;
 }
@@ -130,6 +133,8 @@ int ensure_capacity(e55_ctx* c, int n) {
   E55_CUDA(c, cudaMalloc(&c->d_value, static_cast<size_t>(cap) * sizeof(float)));
   E55_CUDA(c, cudaMalloc(&c->d_probs, static_cast<size_t>(cap) * kPolicyCh * kSq * sizeof(float)));
   E55_CUDA(c, cudaMalloc(&c->d_mask, static_cast<size_t>(cap) * kPolicyCh * kSq));
+  E55_CUDA(c, cudaMalloc(&c->d_bits, static_cast<size_t>(cap) * c->in_planes * sizeof(uint32_t)));
+  E55_CUDA(c, cudaMalloc(&c->d_scale, static_cast<size_t>(cap) * c->in_planes * sizeof(float)));
   cudaError_t e = e55::tc::alloc_buffers(c->tc, cap);
   if (e != cudaSuccess) return fail(c, E55_ERR_CUDA, std::string("tc buffers: ") + cudaGetErrorString(e));
   c->capacity = cap;
@@ -291,6 +296,29 @@ int forward(e55_ctx* c, const float* d_planes, int n, float* d_policy, float* d_
     c->tc.ev0 = c->tc.ev1 = nullptr;
   }
   cudaError_t e = e55::tc::forward(c->tc, d_planes, n, d_policy, d_value, c->stream, &launched, &why);
+  c->launches += launched;
+  if (e != cudaSuccess) return fail(c, E55_ERR_CUDA, "tensor-core forward: " + why + ": " + cudaGetErrorString(e));
+  if (!why.empty()) return fail(c, E55_ERR_UNSUPPORTED, why);
+  return E55_OK;
+}
+
+// Forward from packed device input on `stream`: the tcgen05 kernel expands the bits itself; the fp32 path
+// expands them into the context's plane buffer first (main stream only).
+int forward_packed_on(e55_ctx* c, cudaStream_t stream, const uint32_t* d_bits, const float* d_scale, int n, int plane_off,
+                      float* d_policy, float* d_value) {
+  if (c->precision == E55_PRECISION_FP32) {
+    const size_t total = static_cast<size_t>(n) * c->in_planes * kSq;
+    float* planes = c->d_in + static_cast<size_t>(plane_off) * c->in_planes * kSq;
+    e55::fp32::unpack_planes_kernel<<<static_cast<unsigned>(std::min<size_t>((total + 255) / 256, 4096)), 256, 0, stream>>>(
+        d_bits, d_scale, planes, total);
+    ++c->launches;
+    E55_CUDA(c, cudaGetLastError());
+    return forward_fp32(c, planes, n, d_policy, d_value, nullptr);
+  }
+  std::string why;
+  int launched = 0;
+  c->tc.ev0 = c->tc.ev1 = nullptr;
+  cudaError_t e = e55::tc::forward_packed(c->tc, d_bits, d_scale, n, d_policy, d_value, stream, &launched, &why);
   c->launches += launched;
   if (e != cudaSuccess) return fail(c, E55_ERR_CUDA, "tensor-core forward: " + why + ": " + cudaGetErrorString(e));
   if (!why.empty()) return fail(c, E55_ERR_UNSUPPORTED, why);
@@ -492,6 +520,7 @@ int e55_predict(e55_ctx* c, const float* planes, int n, float* policy, float* va
   if (c->precision == E55_PRECISION_BF16_TC && !c->timing && n >= 2 * kChunk) {
     E55_CUDA(c, cudaEventRecord(c->pipe_start, c->stream));
     const size_t in_pp = static_cast<size_t>(c->in_planes) * kSq, pol_pp = static_cast<size_t>(kPolicyCh) * kSq;
+    c->tc.throughput_rounds = true;   // chunk kernels run side by side: keep each on few SMs
     int used = 0;
     for (int off = 0, i = 0; off < n; off += kChunk, ++i) {
       const int m = std::min(kChunk, n - off);
@@ -504,6 +533,7 @@ int e55_predict(e55_ctx* c, const float* planes, int n, float* policy, float* va
                                   cudaMemcpyDeviceToHost, st));
       E55_CUDA(c, cudaMemcpyAsync(value + off, c->d_value + off, m * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
+    c->tc.throughput_rounds = false;
     for (int i = 0; i < used; ++i) {
       E55_CUDA(c, cudaEventRecord(c->pipe_done[i], c->pipe_stream[i]));
       E55_CUDA(c, cudaStreamWaitEvent(c->stream, c->pipe_done[i], 0));
@@ -518,6 +548,51 @@ int e55_predict(e55_ctx* c, const float* planes, int n, float* policy, float* va
                               cudaMemcpyDeviceToHost, c->stream));
   E55_CUDA(c, cudaMemcpyAsync(value, c->d_value, static_cast<size_t>(n) * sizeof(float), cudaMemcpyDeviceToHost,
                               c->stream));
+  E55_CUDA(c, cudaStreamSynchronize(c->stream));
+  return E55_OK;
+}
+
+int e55_predict_packed_device(e55_ctx* c, const uint32_t* d_bits, const float* d_scale, int n, float* d_policy,
+                              float* d_value) {
+  int rc = check_predict_args(c, d_bits, d_policy, d_value, n);
+  if (rc) return rc;
+  if (!d_scale) return fail(c, E55_ERR_INVALID, "null scale buffer");
+  std::lock_guard<std::mutex> lk(c->mu);
+  E55_CUDA(c, cudaSetDevice(c->device));
+  if ((rc = ensure_capacity(c, n))) return rc;
+  return forward_packed_on(c, c->stream, d_bits, d_scale, n, 0, d_policy, d_value);
+}
+
+int e55_predict_packed(e55_ctx* c, const uint32_t* bits, const float* scale, int n, float* policy, float* value) {
+  int rc = check_predict_args(c, bits, policy, value, n);
+  if (rc) return rc;
+  if (!scale) return fail(c, E55_ERR_INVALID, "null scale buffer");
+  std::lock_guard<std::mutex> lk(c->mu);
+  E55_CUDA(c, cudaSetDevice(c->device));
+  if ((rc = ensure_capacity(c, n))) return rc;
+  const size_t in_pp = static_cast<size_t>(c->in_planes), pol_pp = static_cast<size_t>(kPolicyCh) * kSq;
+  constexpr int kChunk = 256;
+  const bool pipelined = c->precision == E55_PRECISION_BF16_TC && n >= 2 * kChunk;
+  const int step = pipelined ? kChunk : n;
+  if (pipelined) E55_CUDA(c, cudaEventRecord(c->pipe_start, c->stream));
+  c->tc.throughput_rounds = pipelined;   // chunk kernels run side by side: keep each on few SMs
+  int used = 0;
+  for (int off = 0, i = 0; off < n; off += step, ++i) {
+    const int m = std::min(step, n - off);
+    cudaStream_t st = pipelined ? c->pipe_stream[i % e55_ctx::kPipeStreams] : c->stream;
+    if (pipelined && i < e55_ctx::kPipeStreams) { E55_CUDA(c, cudaStreamWaitEvent(st, c->pipe_start, 0)); used = i + 1; }
+    E55_CUDA(c, cudaMemcpyAsync(c->d_bits + off * in_pp, bits + off * in_pp, m * in_pp * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    E55_CUDA(c, cudaMemcpyAsync(c->d_scale + off * in_pp, scale + off * in_pp, m * in_pp * sizeof(float), cudaMemcpyHostToDevice, st));
+    if ((rc = forward_packed_on(c, st, c->d_bits + off * in_pp, c->d_scale + off * in_pp, m, off, c->d_policy + off * pol_pp,
+                                c->d_value + off))) return rc;
+    E55_CUDA(c, cudaMemcpyAsync(policy + off * pol_pp, c->d_policy + off * pol_pp, m * pol_pp * sizeof(float), cudaMemcpyDeviceToHost, st));
+    E55_CUDA(c, cudaMemcpyAsync(value + off, c->d_value + off, m * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  c->tc.throughput_rounds = false;
+  for (int i = 0; i < used; ++i) {
+    E55_CUDA(c, cudaEventRecord(c->pipe_done[i], c->pipe_stream[i]));
+    E55_CUDA(c, cudaStreamWaitEvent(c->stream, c->pipe_done[i], 0));
+  }
   E55_CUDA(c, cudaStreamSynchronize(c->stream));
   return E55_OK;
 }

@@ -131,6 +131,18 @@ value_head_kernel(const float* __restrict__ in, const float* __restrict__ wv, fl
   if (threadIdx.x == 0) value[n] = tanhf(s_part[0] + s_part[1] + s_part[2] + s_part[3] + b2);
 }
 
+// Packed planes -> fp32 NCHW planes: x[n][c][sq] = bit sq of bits[n][c] ? scale[n][c] : 0.
+__global__ void __launch_bounds__(256)
+unpack_planes_kernel(const uint32_t* __restrict__ bits, const float* __restrict__ scale, float* __restrict__ planes,
+                     size_t total /* n * in_planes * 25 */) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t nc = i / kSq;
+    const int sq = static_cast<int>(i % kSq);
+    planes[i] = ((bits[nc] >> sq) & 1u) ? scale[nc] : 0.f;
+  }
+}
+
 // probs = softmax over legal entries of one policy row; illegal entries 0 (all-illegal row -> zeros).
 // Warp-shuffle reductions for the row max and the row sum.  One block of 256 threads per position.
 __global__ void __launch_bounds__(256)

@@ -121,7 +121,9 @@ struct Params {
   const float* fc1_b;      // [128]
   const float* fc2_k;      // [128]
   float value_b, fc2_b;
-  const float* planes;       // [n][in_planes][25] fp32 NCHW, as Network.get_inputs builds them
+  const float* planes;       // [n][in_planes][25] fp32 NCHW, as Network.get_inputs builds them (or nullptr)
+  const uint32_t* bits;      // packed input instead of `planes`: [n][in_planes] occupancy bit per square ...
+  const float* scale;        // ... and [n][in_planes] value of the set squares of that plane
   int in_planes;
   int in_planes8;            // ceil(in_planes / 16) * 2: 8-channel planes incl. zero padding
   int nslices;
@@ -299,7 +301,7 @@ tower_kernel(const Params prm) {
     }
     ptx::fence_mbar_init();
   }
-  {  // pull this CTA's first round of network input into L2 while the setup completes
+  if (prm.planes != nullptr) {  // pull this CTA's first round of network input into L2 while the setup completes
     const int r0 = pair0 * 2 + static_cast<int>(rank);
     const size_t first = static_cast<size_t>(r0) * prm.pos_per_round * prm.in_planes * kSq;
     const size_t last = min(static_cast<size_t>(r0 + 1) * prm.pos_per_round, static_cast<size_t>(prm.n)) * prm.in_planes * kSq;
@@ -492,7 +494,7 @@ tower_kernel(const Params prm) {
       // the value-head tail of group g is run by warp 4g once all 8 warps have written their partials
       const bool do_value = nl == prm.nlayers;
       bool fc_pending[2] = {do_value && warp == 0, do_value && warp == 4 && has_b};
-      if (pr + pair_stride < npair_rounds) {  // pull the next round's network input into L2
+      if (prm.planes != nullptr && pr + pair_stride < npair_rounds) {  // pull the next round's network input into L2
         const int rn = (pr + pair_stride) * 2 + static_cast<int>(rank);
         const size_t first = static_cast<size_t>(rn) * prm.pos_per_round * prm.in_planes * kSq;
         const size_t last = min(static_cast<size_t>(rn + 1) * prm.pos_per_round, static_cast<size_t>(prm.n)) * prm.in_planes * kSq;
@@ -585,10 +587,22 @@ tower_kernel(const Params prm) {
               const int it = it0 + u * 256;
               const int s_ = it % kSq, c8 = (it / kSq) % npl, p = it / (kSq * npl);
               const bool live = it < nitems && pos0 + p < prm.n;
-              const float* src = prm.planes + (static_cast<size_t>(pos0 + p) * prm.in_planes + (pl0 + c8) * 8) * kSq + s_;
+              if (prm.bits == nullptr) {
+                const float* src = prm.planes + (static_cast<size_t>(pos0 + p) * prm.in_planes + (pl0 + c8) * 8) * kSq + s_;
 #pragma unroll
-              for (int e = 0; e < 8; ++e)
-                f[u][e] = (live && (pl0 + c8) * 8 + e < prm.in_planes) ? __ldg(src + e * kSq) : 0.f;
+                for (int e = 0; e < 8; ++e)
+                  f[u][e] = (live && (pl0 + c8) * 8 + e < prm.in_planes) ? __ldg(src + e * kSq) : 0.f;
+              } else {
+                // packed planes: x[c][sq] = bit sq of bits[c] ? scale[c] : 0
+                const size_t o = static_cast<size_t>(pos0 + p) * prm.in_planes + (pl0 + c8) * 8;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const bool ok = live && (pl0 + c8) * 8 + e < prm.in_planes;
+                  const uint32_t wbits = ok ? __ldg(prm.bits + o + e) : 0u;
+                  const float sc = ok ? __ldg(prm.scale + o + e) : 0.f;
+                  f[u][e] = ((wbits >> s_) & 1u) ? sc : 0.f;
+                }
+              }
             }
             // phase 2: pack and store
 #pragma unroll
@@ -710,6 +724,7 @@ struct State {
   int nlayers = 0, nslices = 0, in_planes8 = 0;
   int nstages = 0, nchunks = 0;
   int lag = 1;
+  bool throughput_rounds = false;   // set by callers that run several chunk kernels concurrently: never use latency mode
   size_t smem_bytes = 0;
   uint8_t* d_wimg = nullptr;
   Chunk* d_chunks = nullptr;
@@ -911,8 +926,10 @@ inline cudaError_t set_weights(State& s, const std::vector<std::vector<float>>& 
 }
 
 // nlayers_run < nlayers: stop after that many layers and leave the packed activations in d_dbg.
+struct PackedInput { const uint32_t* bits = nullptr; const float* scale = nullptr; };
+
 inline cudaError_t run(State& s, const float* d_planes, int n, float* d_policy, float* d_value, int nlayers_run,
-                       cudaStream_t stream, int* launched, std::string* why) {
+                       cudaStream_t stream, int* launched, std::string* why, PackedInput packed = PackedInput()) {
   if (!supported(s)) { *why = "the tcgen05 path supports 128 or 256 filters"; return cudaSuccess; }
   if (s.nstages < 3) { *why = "network too deep for the shared-memory layer tables"; return cudaSuccess; }
   if (!s.attr_set) {
@@ -927,13 +944,13 @@ inline cudaError_t run(State& s, const float* d_planes, int n, float* d_policy, 
     s.attr_set = true;
   }
   // latency mode: while the batch fits the machine with one 4-position group per CTA, leave group B out
-  const int ppr = (s.filters != 128 || n <= kPosPerGroup * 2 * std::max(1, s.sms / 2)) ? kPosPerGroup : kPosPerRound;
+  const int ppr = (s.filters != 128 || (!s.throughput_rounds && n <= kPosPerGroup * 2 * std::max(1, s.sms / 2))) ? kPosPerGroup : kPosPerRound;
   const int rounds = (n + ppr - 1) / ppr;
   Params p{};
   p.wimg = s.d_wimg; p.chunks = s.d_chunks; p.layers = s.d_layers; p.bias = s.d_bias;
   p.value_w = s.heads.d_value_w; p.fc1_k = s.heads.d_fc1_k; p.fc1_b = s.heads.d_fc1_b; p.fc2_k = s.heads.d_fc2_k;
   p.value_b = s.heads.value_b; p.fc2_b = s.heads.fc2_b;
-  p.planes = d_planes; p.in_planes = s.in_planes; p.in_planes8 = s.in_planes8; p.nslices = s.nslices;
+  p.planes = d_planes; p.bits = packed.bits; p.scale = packed.scale; p.in_planes = s.in_planes; p.in_planes8 = s.in_planes8; p.nslices = s.nslices;
   p.nstages = s.nstages; p.nchunks_total = s.nchunks; p.lag = std::min(s.lag, s.nstages - 2);
   p.nlayers = s.nlayers; p.nlayers_run = nlayers_run; p.n = n; p.nrounds = rounds; p.pos_per_round = ppr;
   p.policy = d_policy; p.value = d_value;
@@ -959,6 +976,11 @@ inline cudaError_t run(State& s, const float* d_planes, int n, float* d_policy, 
 inline cudaError_t forward(State& s, const float* d_planes, int n, float* d_policy, float* d_value,
                            cudaStream_t stream, int* launched, std::string* why) {
   return run(s, d_planes, n, d_policy, d_value, s.nlayers, stream, launched, why);
+}
+
+inline cudaError_t forward_packed(State& s, const uint32_t* d_bits, const float* d_scale, int n, float* d_policy,
+                                  float* d_value, cudaStream_t stream, int* launched, std::string* why) {
+  return run(s, nullptr, n, d_policy, d_value, s.nlayers, stream, launched, why, PackedInput{d_bits, d_scale});
 }
 
 // Activations after `nconv` 3x3 convolutions (1 = stem ... 1+2*blocks = trunk) as fp32 NCHW.

@@ -74,6 +74,15 @@ int e55_predict(e55_ctx* ctx, const float* planes, int n, float* policy, float* 
  * synchronising (call e55_sync).  Buffers must stay valid until then. */
 int e55_predict_device(e55_ctx* ctx, const float* d_planes, int n, float* d_policy, float* d_value);
 
+/* Compact input: the same evaluation from bit-packed planes, 8 bytes per plane
+ * instead of 100.  bits uint32 [n,in_planes]: bit sq (= y*5+x) set where the plane is non-zero; scale float32
+ * [n,in_planes]: the value those squares hold (1 for occupancy planes, the constant for count/ply planes), i.e.
+ * planes[n][c][sq] = (bits[n][c] >> sq) & 1 ? scale[n][c] : 0 of what Network.get_inputs builds
+ * (network.py:255-274).  Results are identical to e55_predict on the expanded planes. */
+int e55_predict_packed(e55_ctx* ctx, const uint32_t* bits, const float* scale, int n, float* policy, float* value);
+int e55_predict_packed_device(e55_ctx* ctx, const uint32_t* d_bits, const float* d_scale, int n, float* d_policy,
+                              float* d_value);
+
 /* Fused policy tail for the caller-side post-processing the reference leaves to
  * minishogilib.MCTS.evaluate (mcts.py:59-60,103-106): probs = softmax over entries with
  * legal_mask != 0 (others 0), legal_mask uint8 [n,1725]; value as in e55_predict. */

@@ -148,6 +148,35 @@ def test_masked_softmax_tail(nets, weights_default, prec):
     assert np.abs(probs - O.masked_softmax(po, m)).max() <= (1e-4 if prec == "fp32" else 0.03)
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("n", [1, 9, 300, 1024])
+def test_packed_input_is_identical_to_float_planes(nets, prec, n):
+    """e55_predict_packed must reproduce e55_predict bit for bit (same kernel arithmetic, different input format)."""
+    from erweitern_55_b200 import packing
+    net = nets["perturbed", prec]
+    x = synth.synthetic_planes(n, seed=50 + n)
+    bits, scale = packing.pack_planes(x)
+    p, v = net.predict(x)
+    pp, vp = net.predict_packed(bits, scale)
+    assert np.array_equal(p, pp) and np.array_equal(v, vp)
+    with pytest.raises(ValueError):
+        net.predict_packed(bits[:, :10], scale[:, :10])
+
+
+def test_pickled_weight_wire_format(nets, weights_perturbed):
+    """The client/trainer exchange weights as a pickled get_weights() list (train.py:50, client.py:47-51)."""
+    import pickle
+    from erweitern_55_b200.network import Network
+    blob = pickle.dumps(weights_perturbed, protocol=4)
+    net = Network(precision="bf16", seed=1)
+    net.load_pickled_weights(blob)
+    x = synth.synthetic_planes(5, seed=77)
+    assert np.array_equal(net.predict(x)[0], nets["perturbed", "bf16"].predict(x)[0])
+    again = pickle.loads(net.dump_pickled_weights())
+    assert all(np.array_equal(a, b) for a, b in zip(again, weights_perturbed))
+    net.close()
+
+
 def test_set_weights_roundtrip_and_swap(nets, weights_default, weights_perturbed, tmp_path):
     from erweitern_55_b200.network import Network
     net = Network(precision="bf16", weights=weights_default)

@@ -77,3 +77,20 @@ def test_shard_ranges_partition_the_batch():
             assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in parts]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_pack_planes_roundtrip_and_rejection():
+    from erweitern_55_b200 import packing
+    x = synth.synthetic_planes(7, seed=9)
+    bits, scale = packing.pack_planes(x)
+    assert bits.shape == (7, 266) and bits.dtype == np.uint32 and scale.shape == (7, 266) and scale.dtype == np.float32
+    assert bits.max() < (1 << 25)
+    np.testing.assert_array_equal(packing.unpack_planes(bits, scale), x)
+    assert np.all(bits[:, 0][x[:, 0, 0, 0] == 1] == (1 << 25) - 1)          # constant plane: every square set
+    assert np.array_equal(scale[:, 1], x[:, 1, 0, 0])                        # ply plane keeps its value
+    bad = x.copy()
+    bad[0, 5, 0, 0], bad[0, 5, 0, 1] = 0.25, 0.5
+    with pytest.raises(ValueError):
+        packing.pack_planes(bad)
+    with pytest.raises(ValueError):
+        packing.pack_planes(np.zeros((2, 3, 4, 5)))
