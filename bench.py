@@ -178,6 +178,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--selfplay-workers", type=int, default=128, help="0 = skip the synthetic self-play load")
+    ap.add_argument("--selfplay-moves", type=int, default=4)
     ap.add_argument("--blocks", type=int, default=7, help="residual blocks (20 with --filters 256 = BASELINE configs[4])")
     ap.add_argument("--filters", type=int, default=128, choices=[128, 256])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -328,6 +330,23 @@ def main():
                   "note": "e55_predict_packed: bit-packed planes (8 B/plane) instead of the reference's float32 planes; "
                           "identical outputs; not the drop-in input format, reported beside e2e"}
 
+    # ---- synthetic self-play load through the cross-game aggregation service (tree ops excluded) -------
+    selfplay = None
+    if args.selfplay_workers > 0 and args.precision == "bf16":
+        net.start_service(max_batch=B, max_wait_us=200)
+        net.bench_selfplay(workers=args.selfplay_workers, moves=1, simulations=160, leaf_batch=16)   # warm-up
+        barrier()
+        mv, ev, mb = net.bench_selfplay(workers=args.selfplay_workers, moves=args.selfplay_moves, simulations=800, leaf_batch=16)
+        barrier()
+        net.stop_service()
+        tot_ev, _ = sharding.aggregate(ev, 1.0, device=dev)
+        tot_mv, _ = sharding.aggregate(mv, 1.0, device=dev)
+        selfplay = {"moves_per_s": tot_mv, "evals_per_s": tot_ev, "mean_gpu_batch_rank0": mb,
+                    "workers_per_gpu": args.selfplay_workers, "simulations_per_move": 800, "leaf_batch": 16,
+                    "note": "synthetic: host threads drive the network like mcts.MCTS.run (1 root + 800/16 leaf batches per "
+                            "move, mcts.py:57-58,70,91-106) on random bit-packed positions through e55_service_predict_packed; "
+                            "tree operations and move generation (minishogilib, absent) are not included"}
+
     # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------------
     cpu_baseline = None
     if rank == 0 and world == 1:
@@ -347,7 +366,7 @@ def main():
                        "batch_per_gpu": B, "parallelism": f"replicas x{world} (independent positions, no collective)",
                        "l2": f"inputs rotate over {n_pool} distinct device batches = {n_pool * in_bytes >> 20} MiB > 126 MiB L2",
                        "flop_per_position": flops, "host_cpu": model, "host_cores": ncpu},
-            "e2e": e2e, "e2e_packed": e2e_packed, "gpu_launches": launches, "clocks": clocks.summary(),
+            "e2e": e2e, "e2e_packed": e2e_packed, "selfplay_synthetic": selfplay, "gpu_launches": launches, "clocks": clocks.summary(),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "wall_s": t_wall,
         }
         sys.stdout.flush()

@@ -28,6 +28,13 @@ SIGNATURES = {
     "e55_predict_packed_device": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "e55_predict_masked": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "e55_predict_masked_device": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "e55_service_start": (C.c_int, [_ctx, C.c_int, C.c_int]),
+    "e55_service_stop": (C.c_int, [_ctx]),
+    "e55_service_predict": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "e55_service_predict_packed": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "e55_service_stats": (C.c_int, [_ctx, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "e55_bench_selfplay": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double),
+                                     C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "e55_sync": (C.c_int, [_ctx]),
     "e55_stream": (C.c_int, [_ctx, C.POINTER(C.c_void_p)]),
     "e55_launch_count": (C.c_int, [_ctx, C.POINTER(C.c_int64)]),

@@ -6,7 +6,11 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
+#include <condition_variable>
+#include <thread>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -34,7 +38,10 @@ struct ConvF32 {
 
 }  // namespace
 
+struct e55_service;
+
 struct e55_ctx {
+  e55_service* service = nullptr;   // cross-game leaf aggregation (e55_service.inl)
   int device = 0, blocks = 0, filters = 0, in_planes = 0;
   int capacity = 0;
   int precision = E55_PRECISION_BF16_TC;
@@ -380,6 +387,7 @@ int e55_create(e55_ctx** out, int device, int blocks, int filters, int in_planes
 void e55_destroy(e55_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  e55_service_stop(c);
   if (c->stream) cudaStreamSynchronize(c->stream);
   free_weights(c);
   free_buffers(c);
@@ -813,3 +821,5 @@ int e55_bench_umma(int device, int n_dim, int iters, float* tflops_out) {
 }
 
 }  // extern "C"
+
+#include "e55_service.inl"

@@ -60,6 +60,7 @@ class Network:
         self._ctx = C.c_void_p()
         self._iterations = 0
         self._weights = None
+        self._service_cap = 0
         rc = self._lib.e55_create(C.byref(self._ctx), self._device, blocks, filters, in_planes, max_batch)
         if rc != _capi.E55_OK:
             _capi.check(None, rc)
@@ -168,13 +169,37 @@ class Network:
         return x
 
     def predict(self, images):
-        """policy float32 ``[N,1725]`` raw logits, value float32 ``[N,1]`` (tanh); whole input = one batch."""
+        """policy float32 ``[N,1725]`` raw logits, value float32 ``[N,1]`` (tanh); whole input = one batch.
+        While the aggregation service runs (:meth:`start_service`) calls from many threads are coalesced."""
         x = self._as_batch(images)
         n = x.shape[0]
         policy = np.empty((n, POLICY_SIZE), dtype=np.float32)
         value = np.empty((n, 1), dtype=np.float32)
-        self._check(self._lib.e55_predict(self._ctx, x.ctypes.data, n, policy.ctypes.data, value.ctypes.data))
+        fn = self._lib.e55_service_predict if (self._service_cap and n <= self._service_cap) else self._lib.e55_predict
+        self._check(fn(self._ctx, x.ctypes.data, n, policy.ctypes.data, value.ctypes.data))
         return policy, value
+
+    # ---- cross-game leaf aggregation --------------------------------------------------------------
+    def start_service(self, max_batch=1024, max_wait_us=200):
+        """Coalesce predict() calls of many search threads (one per game) into large GPU batches."""
+        self._check(self._lib.e55_service_start(self._ctx, max_batch, max_wait_us))
+        self._service_cap = max_batch
+
+    def stop_service(self):
+        self._service_cap = 0
+        self._check(self._lib.e55_service_stop(self._ctx))
+
+    def service_stats(self):
+        b, p = C.c_int64(), C.c_int64()
+        self._check(self._lib.e55_service_stats(self._ctx, C.byref(b), C.byref(p)))
+        return int(b.value), int(p.value)
+
+    def bench_selfplay(self, workers, moves, simulations=800, leaf_batch=16):
+        """Synthetic self-play load on the running service -> (moves/s, evals/s, mean GPU batch)."""
+        m, e, mb = C.c_double(), C.c_double(), C.c_double()
+        self._check(self._lib.e55_bench_selfplay(self._ctx, workers, moves, simulations, leaf_batch,
+                                                 C.byref(m), C.byref(e), C.byref(mb)))
+        return float(m.value), float(e.value), float(mb.value)
 
     def predict_packed(self, bits, scale):
         """Same evaluation from bit-packed planes (:mod:`erweitern_55_b200.packing`): ``bits`` uint32 ``[N,C]``,
@@ -186,8 +211,8 @@ class Network:
         n = b.shape[0]
         policy = np.empty((n, POLICY_SIZE), dtype=np.float32)
         value = np.empty((n, 1), dtype=np.float32)
-        self._check(self._lib.e55_predict_packed(self._ctx, b.ctypes.data, sc.ctypes.data, n,
-                                                 policy.ctypes.data, value.ctypes.data))
+        fn = self._lib.e55_service_predict_packed if (self._service_cap and n <= self._service_cap) else self._lib.e55_predict_packed
+        self._check(fn(self._ctx, b.ctypes.data, sc.ctypes.data, n, policy.ctypes.data, value.ctypes.data))
         return policy, value
 
     def predict_masked(self, images, legal_mask):

@@ -91,6 +91,24 @@ int e55_predict_masked(e55_ctx* ctx, const float* planes, const uint8_t* legal_m
 int e55_predict_masked_device(e55_ctx* ctx, const float* d_planes, const uint8_t* d_legal_mask, int n,
                               float* d_probs, float* d_value);
 
+/* Cross-game leaf aggregation (the per-GPU "inference stream" of a self-play shard): after
+ * e55_service_start, any number of host threads may call the blocking e55_service_predict[_packed] with
+ * the small batches mcts.py produces (root 1, leaves 16; mcts.py:57-58,91-106); a dispatcher thread coalesces
+ * them into forwards of up to max_batch positions (a batch is dispatched when full, when a request does not
+ * fit, or max_wait_us after its first request).  Results equal e55_predict[_packed] on the same positions. */
+int e55_service_start(e55_ctx* ctx, int max_batch, int max_wait_us);
+int e55_service_stop(e55_ctx* ctx);
+int e55_service_predict(e55_ctx* ctx, const float* planes, int n, float* policy, float* value);
+int e55_service_predict_packed(e55_ctx* ctx, const uint32_t* bits, const float* scale, int n, float* policy,
+                               float* value);
+int e55_service_stats(e55_ctx* ctx, int64_t* batches_out, int64_t* positions_out);
+
+/* Synthetic self-play load on the running service, tree operations excluded: `workers` host threads each play
+ * `moves` moves the way mcts.MCTS.run drives the network (one root evaluation, then simulations/leaf_batch
+ * evaluations of leaf_batch positions; mcts.py:57-58,70,91-106) on random bit-packed positions. */
+int e55_bench_selfplay(e55_ctx* ctx, int workers, int moves, int simulations, int leaf_batch,
+                       double* moves_per_s_out, double* evals_per_s_out, double* mean_batch_out);
+
 /* Block until all work enqueued on the context stream has finished. */
 int e55_sync(e55_ctx* ctx);
 

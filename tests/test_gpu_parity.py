@@ -219,6 +219,45 @@ def test_predict_from_other_threads(nets):
     assert not errs and all(np.array_equal(o, want) for o in out)
 
 
+def test_aggregation_service_matches_direct_predict(weights_default):
+    """Many 'games' (threads) submit root (1) and leaf (16) batches; the service coalesces them into large GPU
+    batches; every caller gets exactly what a direct predict of its own positions returns."""
+    from erweitern_55_b200 import packing
+    from erweitern_55_b200.network import Network
+    net = Network(precision="bf16", weights=weights_default)
+    games = 24
+    xs = [synth.synthetic_planes(16, seed=900 + g) for g in range(games)]
+    want = [net.predict(x) for x in xs]
+    want1 = [net.predict(x[:1]) for x in xs]
+    net.start_service(max_batch=256, max_wait_us=300)
+    got, got1, gotp, errs = [None] * games, [None] * games, [None] * games, []
+
+    def game(g):
+        try:
+            for _ in range(3):
+                got1[g] = net.predict(xs[g][:1])                       # root evaluation, mcts.py:57-58
+                got[g] = net.predict(xs[g])                            # leaf batch, mcts.py:101-102
+                gotp[g] = net.predict_packed(*packing.pack_planes(xs[g]))
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    ts = [threading.Thread(target=game, args=(g,)) for g in range(games)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    batches, positions = net.service_stats()
+    net.stop_service()
+    assert not errs
+    assert positions == games * 3 * (1 + 16 + 16) and batches < games * 9      # requests really were coalesced
+    for g in range(games):
+        for a, b in ((got[g], want[g]), (got1[g], want1[g]), (gotp[g], want[g])):
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    p, v = net.predict(xs[0])                                          # direct path works again after stop
+    assert np.array_equal(p, want[0][0])
+    m, e, mb = (net.start_service(1024, 200), net.bench_selfplay(workers=32, moves=1, simulations=64, leaf_batch=16))[1]
+    assert m > 0 and e > 0 and mb > 1
+    net.close()                                                        # destroy stops a running service
+
+
 def test_device_resident_api(nets):
     net = nets["default", "bf16"]
     x = synth.synthetic_planes(100, seed=12)
