@@ -12,7 +12,7 @@
 //             planes [plane = c/8][row][c%8]: the no-swizzle K-major UMMA layout with SBO = 128 B, in
 //             which rows are linear, so a tap is just start-address + shift*16 B (e55_selftest_umma).
 //   * B     = weights, bf16, pre-packed on the host into the same layout per chunk (board row of taps x
-//             32-channel K block) and streamed L2 -> smem by bulk TMA through a 10-stage mbarrier ring.
+//             pair of 32-channel K blocks) and streamed L2 -> smem by bulk TMA through a 5-stage mbarrier ring.
 //   * D     = fp32 accumulators in TMEM (128 lanes = rows, 128 columns = output channels), two per group
 //             (layer parity) so the next layer's MMAs start while the epilogue still drains the last one.
 //
@@ -107,7 +107,7 @@ struct alignas(16) Chunk {
 
 struct LayerInfo {
   int chunk_begin, chunk_end;
-  int ndim;          // UMMA N
+  int ndim;          // UMMA N (host-side bookkeeping; the kernel reads Chunk::ndim8)
   uint32_t flags;
 };
 
@@ -259,7 +259,7 @@ tower_kernel(const Params prm) {
   uint64_t* bar_full = bars;                          // [stages] stage landed (leader: both CTAs' halves)
   uint64_t* bar_empty = bars + kMaxStages;            // [stages] both groups' MMAs on the stage are done
   uint64_t* bar_tmem_full = bars + 2 * kMaxStages;    // [2] accumulator of a group complete
-  uint64_t* bar_act_part = bar_tmem_full + 2;         // [groups][F/32 / groups... 8 in all] leader only: K block written by both CTAs
+  uint64_t* bar_act_part = bar_tmem_full + 2;         // [8] leader only: activation K block (group*4 + kb) written by both CTAs
   uint64_t* bar_in_full = bar_act_part + 8;           // [2 groups][2 plane halves] leader only: stem input slice written
   uint64_t* bar_in_empty = bar_in_full + 4;           // [2][2] that half of the planes may be overwritten
   uint64_t* bar_v = bar_in_empty + 4;                 // [2] value-conv partials of a group written by all 8 warps
@@ -723,7 +723,7 @@ struct State {
   int blocks = 0, filters = 0, in_planes = 0, sms = 0;
   int nlayers = 0, nslices = 0, in_planes8 = 0;
   int nstages = 0, nchunks = 0;
-  int lag = 1;
+  int lag = 0;                      // free-running groups measured fastest (tools/tc_prof.py, E55_LAG)
   bool throughput_rounds = false;   // set by callers that run several chunk kernels concurrently: never use latency mode
   size_t smem_bytes = 0;
   uint8_t* d_wimg = nullptr;
