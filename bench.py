@@ -353,6 +353,17 @@ def main():
         rate, cores, reps, dt = cpu_oracle_rate(B, args.cpu_seconds, w)
         cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": f"{reps} forward passes of batch {B} in {dt:.1f} s (torch-CPU fp32 oracle port of network.py)"}
+        # BASELINE.json configs[0]: the batches mcts.py / usi.py really use (root 1, leaves 16), CPU vs this library
+        small = {}
+        for nb in (1, 16, 64):
+            r_cpu, _, _, _ = cpu_oracle_rate(nb, 1.0, w)
+            xs = synth.synthetic_planes(nb, seed=77)
+            net.predict(xs)
+            t0 = time.perf_counter()
+            for _ in range(200):
+                net.predict(xs)
+            small[str(nb)] = {"cpu_port_evals_per_s": r_cpu, "b200_predict_evals_per_s": nb * 200 / (time.perf_counter() - t0)}
+        cpu_baseline["small_batches"] = small
 
     if rank == 0:
         ncpu, model = host_info()
