@@ -331,14 +331,26 @@ def main():
                           "identical outputs; not the drop-in input format, reported beside e2e"}
 
     # ---- synthetic self-play load through the cross-game aggregation service (tree ops excluded) -------
-    selfplay = None
+    selfplay = selfplay_real = None
     if args.selfplay_workers > 0 and args.precision == "bf16":
         net.start_service(max_batch=B, max_wait_us=200)
         net.bench_selfplay(workers=args.selfplay_workers, moves=1, simulations=160, leaf_batch=16)   # warm-up
         barrier()
         mv, ev, mb = net.bench_selfplay(workers=args.selfplay_workers, moves=args.selfplay_moves, simulations=800, leaf_batch=16)
         barrier()
+        # real self-play: native minishogi engine + MCTS (800 simulations, leaf batch 16, 7-ply mate search)
+        real = net.selfplay(threads=args.selfplay_workers, total_moves=args.selfplay_workers * args.selfplay_moves,
+                            simulations=800, leaf_batch=16, mate_depth=7, seed=1 + rank)
+        barrier()
         net.stop_service()
+        real_mv, _ = sharding.aggregate(real["moves_per_s"], 1.0, device=dev)
+        real_ev, _ = sharding.aggregate(real["evals_per_s"], 1.0, device=dev)
+        selfplay_real = {"moves_per_s": real_mv, "evals_per_s": real_ev, "games_rank0": real["games"],
+                         "mean_gpu_batch_rank0": real["mean_gpu_batch"], "threads_per_gpu": args.selfplay_workers,
+                         "simulations_per_move": 800, "leaf_batch": 16, "mate_search_plies": 7,
+                         "note": "native C++ minishogi engine + batched PUCT search (csrc/minishogi.hpp, mcts.hpp) playing whole "
+                                 "games from the start position with random-init weights through the evaluation service; "
+                                 "rules pinned by the reference's 17 KATs, input encoding / policy index are this repo's own"}
         tot_ev, _ = sharding.aggregate(ev, 1.0, device=dev)
         tot_mv, _ = sharding.aggregate(mv, 1.0, device=dev)
         selfplay = {"moves_per_s": tot_mv, "evals_per_s": tot_ev, "mean_gpu_batch_rank0": mb,
@@ -377,7 +389,7 @@ def main():
                        "batch_per_gpu": B, "parallelism": f"replicas x{world} (independent positions, no collective)",
                        "l2": f"inputs rotate over {n_pool} distinct device batches = {n_pool * in_bytes >> 20} MiB > 126 MiB L2",
                        "flop_per_position": flops, "host_cpu": model, "host_cores": ncpu},
-            "e2e": e2e, "e2e_packed": e2e_packed, "selfplay_synthetic": selfplay, "gpu_launches": launches, "clocks": clocks.summary(),
+            "e2e": e2e, "e2e_packed": e2e_packed, "selfplay": selfplay_real, "selfplay_synthetic": selfplay, "gpu_launches": launches, "clocks": clocks.summary(),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "wall_s": t_wall,
         }
         sys.stdout.flush()

@@ -47,6 +47,29 @@ SIGNATURES = {
     "e55_bench_umma": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
 }
 
+class SelfplayStats(C.Structure):
+    _fields_ = [("seconds", C.c_double), ("moves", C.c_long), ("evals", C.c_long), ("games", C.c_long),
+                ("mean_game_plies", C.c_double), ("mean_gpu_batch", C.c_double)]
+
+
+_pos = C.c_void_p
+SIGNATURES.update({
+    "e55_pos_create": (_pos, []),
+    "e55_pos_destroy": (None, [_pos]),
+    "e55_pos_copy": (_pos, [_pos]),
+    "e55_pos_set_sfen": (C.c_int, [_pos, C.c_char_p]),
+    "e55_pos_sfen": (C.c_int, [_pos, C.c_char_p, C.c_int]),
+    "e55_pos_side_to_move": (C.c_int, [_pos]),
+    "e55_pos_ply": (C.c_int, [_pos]),
+    "e55_pos_generate_moves": (C.c_int, [_pos, C.c_char_p, C.c_int]),
+    "e55_pos_do_move": (C.c_int, [_pos, C.c_char_p]),
+    "e55_pos_is_repetition": (C.c_int, [_pos, C.POINTER(C.c_int)]),
+    "e55_pos_solve_checkmate_dfs": (C.c_int, [_pos, C.c_int, C.c_char_p, C.c_int]),
+    "e55_pos_encode_packed": (C.c_int, [_pos, C.c_void_p, C.c_void_p]),
+    "e55_pos_policy_index": (C.c_int, [_pos, C.c_char_p]),
+    "e55_selfplay_run": (C.c_int, [_ctx, C.c_int, C.c_long, C.c_int, C.c_int, C.c_int, C.c_uint64, C.POINTER(SelfplayStats)]),
+})
+
 _lib = None
 
 

@@ -823,3 +823,4 @@ int e55_bench_umma(int device, int n_dim, int iters, float* tflops_out) {
 }  // extern "C"
 
 #include "e55_service.inl"
+#include "e55_game.inl"

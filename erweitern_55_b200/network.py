@@ -194,6 +194,16 @@ class Network:
         self._check(self._lib.e55_service_stats(self._ctx, C.byref(b), C.byref(p)))
         return int(b.value), int(p.value)
 
+    def selfplay(self, threads, total_moves, simulations=800, leaf_batch=16, mate_depth=7, seed=1):
+        """Real self-play on the running service with the native minishogi engine + MCTS (``selfplay.run``'s loop,
+        selfplay.py:10-113): returns a dict of moves, evals, games, seconds, mean game length and mean GPU batch."""
+        st = _capi.SelfplayStats()
+        self._check(self._lib.e55_selfplay_run(self._ctx, threads, total_moves, simulations, leaf_batch, mate_depth,
+                                               seed, C.byref(st)))
+        return {"seconds": st.seconds, "moves": st.moves, "evals": st.evals, "games": st.games,
+                "mean_game_plies": st.mean_game_plies, "mean_gpu_batch": st.mean_gpu_batch,
+                "moves_per_s": st.moves / st.seconds, "evals_per_s": st.evals / st.seconds}
+
     def bench_selfplay(self, workers, moves, simulations=800, leaf_batch=16):
         """Synthetic self-play load on the running service -> (moves/s, evals/s, mean GPU batch)."""
         m, e, mb = C.c_double(), C.c_double(), C.c_double()

@@ -109,6 +109,40 @@ int e55_service_stats(e55_ctx* ctx, int64_t* batches_out, int64_t* positions_out
 int e55_bench_selfplay(e55_ctx* ctx, int workers, int moves, int simulations, int leaf_batch,
                        double* moves_per_s_out, double* evals_per_s_out, double* mean_batch_out);
 
+/* ---- native minishogi engine + self-play -----------------------------------------
+ * Counterpart of the external Rust library minishogilib v0.6.12 the reference drives from Python
+ * (selfplay.py:11-36,78; mcts.py:27-110; tests/test_checkmate.py, tests/test_repetition.py).  Moves and
+ * positions travel as SFEN/USI strings ("5e4d", "3d4e+", "G*1d"). */
+typedef struct e55_pos e55_pos;
+e55_pos* e55_pos_create(void);                                  /* Position(); starts at the initial position */
+void e55_pos_destroy(e55_pos* pos);
+e55_pos* e55_pos_copy(const e55_pos* pos);                      /* Position.copy(True) */
+int e55_pos_set_sfen(e55_pos* pos, const char* sfen);           /* "board side hands n [moves m1 m2 ...]" */
+int e55_pos_sfen(const e55_pos* pos, char* buf, int buflen);
+int e55_pos_side_to_move(const e55_pos* pos);                   /* 0 = first player (black), 1 = second */
+int e55_pos_ply(const e55_pos* pos);
+int e55_pos_generate_moves(e55_pos* pos, char* buf, int buflen); /* legal moves, space separated; returns count */
+int e55_pos_do_move(e55_pos* pos, const char* move);            /* E55_ERR_INVALID if the move is not legal */
+int e55_pos_is_repetition(const e55_pos* pos, int out3[3]);     /* (is_repetition, my_check_rep, op_check_rep) */
+int e55_pos_solve_checkmate_dfs(e55_pos* pos, int depth, char* move_buf, int buflen);  /* 1 = mate found */
+int e55_pos_encode_packed(const e55_pos* pos, uint32_t* bits, float* scale);   /* 266-plane input, packed */
+int e55_pos_policy_index(e55_pos* pos, const char* move);       /* index of a legal move in the 1725 logits */
+
+typedef struct e55_selfplay_stats {
+  double seconds;          /* wall time of the run */
+  long moves;              /* game plies played (each = 1 root evaluation + `simulations` simulations, or a mate move) */
+  long evals;              /* positions sent through the network */
+  long games;              /* games finished */
+  double mean_game_plies;
+  double mean_gpu_batch;   /* positions per GPU forward as coalesced by the evaluation service */
+} e55_selfplay_stats;
+
+/* Self-play on the running evaluation service: `threads` host threads each play whole games the way
+ * selfplay.run does (selfplay.py:10-113; mate search of `mate_depth` plies, MCTS of `simulations` simulations in
+ * batches of `leaf_batch`, sampling for the first 10 plies) until `total_moves` plies have been played. */
+int e55_selfplay_run(e55_ctx* ctx, int threads, long total_moves, int simulations, int leaf_batch, int mate_depth,
+                     uint64_t seed, e55_selfplay_stats* stats_out);
+
 /* Block until all work enqueued on the context stream has finished. */
 int e55_sync(e55_ctx* ctx);
 

@@ -258,6 +258,39 @@ def test_aggregation_service_matches_direct_predict(weights_default):
     net.close()                                                        # destroy stops a running service
 
 
+def test_native_selfplay_and_python_search_loop(weights_default):
+    """The engine + MCTS + evaluation service end to end, and the reference's own search-loop shape in Python:
+    positions -> get_inputs -> predict -> legal-move priors (mcts.py:91-106) with the native Position class."""
+    from erweitern_55_b200.minishogi import Position
+    from erweitern_55_b200.network import Network
+    net = Network(precision="bf16", weights=weights_default)
+    positions = []
+    p = Position()
+    rng = np.random.default_rng(3)
+    for _ in range(16):
+        moves = p.generate_moves()
+        if not moves:
+            break
+        p.do_move(moves[int(rng.integers(len(moves)))])
+        positions.append(p.copy(True))
+    nninputs = net.get_inputs(positions)                                # network.py:260-274
+    policy, value = net.predict(nninputs)
+    value = (value + 1) / 2                                             # mcts.py:103
+    bits = np.stack([q.to_packed_input()[0] for q in positions]); scale = np.stack([q.to_packed_input()[1] for q in positions])
+    pp, vp = net.predict_packed(bits, scale)
+    assert np.array_equal(pp, policy) and np.all((0 <= value) & (value <= 1))
+    for b, q in enumerate(positions):
+        idx = [q.policy_index(m) for m in q.generate_moves()]
+        if idx:
+            pri = np.exp(policy[b, idx] - policy[b, idx].max())
+            assert np.isfinite(pri).all() and pri.sum() > 0
+    net.start_service(max_batch=512, max_wait_us=200)
+    st = net.selfplay(threads=16, total_moves=48, simulations=64, leaf_batch=16, mate_depth=3, seed=7)
+    net.stop_service()
+    assert st["moves"] >= 40 and st["evals"] > st["moves"] * 40 and st["mean_gpu_batch"] > 4
+    net.close()
+
+
 def test_device_resident_api(nets):
     net = nets["default", "bf16"]
     x = synth.synthetic_planes(100, seed=12)
