@@ -179,7 +179,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--selfplay-workers", type=int, default=128, help="0 = skip the synthetic self-play load")
-    ap.add_argument("--selfplay-moves", type=int, default=4)
+    ap.add_argument("--selfplay-moves", type=int, default=8, help="moves per worker thread in the self-play runs")
     ap.add_argument("--blocks", type=int, default=7, help="residual blocks (20 with --filters 256 = BASELINE configs[4])")
     ap.add_argument("--filters", type=int, default=128, choices=[128, 256])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

@@ -41,7 +41,7 @@ struct SelfplayWorker {
   std::vector<float> scale, policy, value;
   std::vector<mshogi::Selection> sels;
   std::vector<mshogi::Position> leaf_pos;
-  std::vector<std::vector<mshogi::Move>> leaf_moves;
+  std::vector<mshogi::MoveList> leaf_moves;
   std::vector<int> eval_slot;
   mshogi::Mcts tree;
 
@@ -57,7 +57,7 @@ struct SelfplayWorker {
   bool search(mshogi::Position& root_pos, int& chosen, std::mt19937_64& rng) {
     using namespace mshogi;
     tree.clear();
-    std::vector<Move> root_moves;
+    MoveList root_moves;
     float tv;
     Position scratch = root_pos;
     if (Mcts::terminal_value(scratch, root_moves, tv)) return false;
@@ -117,7 +117,7 @@ struct SelfplayWorker {
         if (!have) {
           int chosen = 0;
           if (!search(pos, chosen, rng)) break;                                           // terminal position
-          next = tree.nodes[0].edges[chosen].move;
+          next = tree.edges_of(tree.nodes[0])[chosen].move;
         }
         pos.do_move(next);
         moves_done->fetch_add(1);

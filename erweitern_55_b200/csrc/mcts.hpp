@@ -24,7 +24,8 @@ struct Edge {
 };
 
 struct Node {
-  std::vector<Edge> edges;
+  int32_t first_edge = 0;       // edges live in one pool per tree: [first_edge, first_edge + n_edges)
+  int32_t n_edges = 0;
   bool expanded = false;
   bool terminal = false;
   float terminal_value = 0.f;   // for the side to move at this node
@@ -42,12 +43,15 @@ class Mcts {
  public:
   float c_puct = 1.25f;
   std::vector<Node> nodes;
+  std::vector<Edge> edges;      // pool; cleared, not freed, between searches
 
-  void clear() { nodes.clear(); nodes.emplace_back(); }
+  void clear() { nodes.clear(); edges.clear(); nodes.emplace_back(); }
+  Edge* edges_of(const Node& nd) { return edges.data() + nd.first_edge; }
+  const Edge* edges_of(const Node& nd) const { return edges.data() + nd.first_edge; }
   int32_t root() const { return 0; }
 
   // Terminal test in the reference's order (selfplay.py:17-31): perpetual check, repetition, no moves.
-  static bool terminal_value(Position& pos, std::vector<Move>& moves, float& v) {
+  static bool terminal_value(Position& pos, MoveList& moves, float& v) {
     bool rep, my_check, op_check;
     pos.is_repetition(rep, my_check, op_check);
     if (my_check) { v = 0.f; return true; }                        // the perpetual checker (side to move) loses
@@ -64,29 +68,30 @@ class Mcts {
     sel.duplicate_of = -1;
     int32_t node = 0;
     for (;;) {
-      Node& nd = nodes[node];
+      const Node nd = nodes[node];        // by value: nodes may grow below
       if (!nd.expanded || nd.terminal) break;
+      Edge* ed = edges.data() + nd.first_edge;
       int total = 0;
-      for (const Edge& e : nd.edges) total += e.n + e.vloss;
+      for (int i = 0; i < nd.n_edges; ++i) total += ed[i].n + ed[i].vloss;
       const float sq = std::sqrt(static_cast<float>(total) + 1e-8f);
       int best = 0;
       float best_score = -1e30f;
-      for (int i = 0; i < static_cast<int>(nd.edges.size()); ++i) {
-        const Edge& e = nd.edges[i];
+      for (int i = 0; i < nd.n_edges; ++i) {
+        const Edge& e = ed[i];
         const int n = e.n + e.vloss;
         const float q = n > 0 ? e.w / static_cast<float>(n) : 0.f;   // virtual losses count as visits worth 0
         const float score = q + c_puct * e.prior * sq / (1.f + static_cast<float>(n));
         if (score > best_score) { best_score = score; best = i; }
       }
-      Edge& e = nd.edges[best];
+      Edge& e = ed[best];
       ++e.vloss;
       sel.path.emplace_back(node, best);
       pos.do_move(e.move);
       if (e.child < 0) {
         e.child = static_cast<int32_t>(nodes.size());
-        nodes.emplace_back();             // invalidates nd / e: do not touch them below
+        nodes.emplace_back();
       }
-      node = nodes[sel.path.back().first].edges[best].child;
+      node = e.child;
     }
     sel.leaf = node;
     Node& leaf = nodes[node];
@@ -97,21 +102,25 @@ class Mcts {
   }
 
   // Expand a leaf: priors = softmax over the logits of the legal moves.  `policy` is the network's 1725 logits.
-  void evaluate(int32_t node, Position& pos, std::vector<Move>& moves, const float* policy, float value01) {
+  void evaluate(int32_t node, Position& pos, const MoveList& moves, const float* policy, float value01) {
     Node& nd = nodes[node];
     nd.pending = -1;
     if (nd.expanded || nd.terminal) return;
     nd.value = value01;
-    nd.edges.resize(moves.size());
+    nd.first_edge = static_cast<int32_t>(edges.size());
+    nd.n_edges = moves.size();
+    edges.resize(edges.size() + moves.size());
+    Edge* ed = edges.data() + nd.first_edge;
     float mx = -1e30f;
-    for (size_t i = 0; i < moves.size(); ++i) {
-      nd.edges[i].move = moves[i];
-      nd.edges[i].prior = policy[policy_index(moves[i], pos.side)];
-      mx = std::max(mx, nd.edges[i].prior);
+    for (int i = 0; i < moves.size(); ++i) {
+      ed[i] = Edge();
+      ed[i].move = moves.m[i];
+      ed[i].prior = policy[policy_index(moves.m[i], pos.side)];
+      mx = std::max(mx, ed[i].prior);
     }
     float sum = 0.f;
-    for (Edge& e : nd.edges) { e.prior = std::exp(e.prior - mx); sum += e.prior; }
-    for (Edge& e : nd.edges) e.prior /= sum;
+    for (int i = 0; i < moves.size(); ++i) { ed[i].prior = std::exp(ed[i].prior - mx); sum += ed[i].prior; }
+    for (int i = 0; i < moves.size(); ++i) ed[i].prior /= sum;
     nd.expanded = true;
   }
   void set_terminal(int32_t node, float v) {
@@ -126,7 +135,7 @@ class Mcts {
     float v = value01;
     for (int i = static_cast<int>(sel.path.size()) - 1; i >= 0; --i) {
       v = 1.f - v;
-      Edge& e = nodes[sel.path[i].first].edges[sel.path[i].second];
+      Edge& e = edges[nodes[sel.path[i].first].first_edge + sel.path[i].second];
       --e.vloss;
       ++e.n;
       e.w += v;
@@ -134,21 +143,21 @@ class Mcts {
   }
 
   int best_edge() const {
-    const Node& r = nodes[0];
+    const Edge* ed = edges_of(nodes[0]);
     int best = 0;
-    for (int i = 1; i < static_cast<int>(r.edges.size()); ++i)
-      if (r.edges[i].n > r.edges[best].n) best = i;
+    for (int i = 1; i < nodes[0].n_edges; ++i)
+      if (ed[i].n > ed[best].n) best = i;
     return best;
   }
   template <class Rng>
   int sample_edge(Rng& rng) const {   // proportional to visit counts (temperature 1, selfplay.py:65-66)
-    const Node& r = nodes[0];
+    const Edge* ed = edges_of(nodes[0]);
     long total = 0;
-    for (const Edge& e : r.edges) total += e.n;
+    for (int i = 0; i < nodes[0].n_edges; ++i) total += ed[i].n;
     if (total <= 0) return best_edge();
     long pick = static_cast<long>(std::uniform_int_distribution<long>(0, total - 1)(rng));
-    for (int i = 0; i < static_cast<int>(r.edges.size()); ++i) {
-      pick -= r.edges[i].n;
+    for (int i = 0; i < nodes[0].n_edges; ++i) {
+      pick -= ed[i].n;
       if (pick < 0) return i;
     }
     return best_edge();

@@ -87,6 +87,16 @@ inline uint32_t slide_mask(PieceType t) {
   }
 }
 
+struct MoveList {                    // no position has anywhere near 256 legal moves on a 5x5 board
+  Move m[256];
+  int n = 0;
+  void push(const Move& mv) { if (n < 256) m[n++] = mv; }
+  const Move* begin() const { return m; }
+  const Move* end() const { return m + n; }
+  bool empty() const { return n == 0; }
+  int size() const { return n; }
+};
+
 struct Snapshot {                    // what the input encoder needs of a past position
   int8_t board[kSquares];           // type | color << 4
   int8_t hand[2][kHandTypes];
@@ -99,6 +109,7 @@ class Position {
   int8_t hand[2][kHandTypes];
   int side = BLACK;
   int ply = 0;
+  int8_t king_sq[2] = {-1, -1};      // cached king squares (-1: no king, as in some test positions)
   // history for repetition / encoding
   std::vector<uint64_t> hashes;      // hash after each ply (index 0 = initial position)
   std::vector<uint8_t> gave_check;   // gave_check[i]: the move leading to hashes[i] gave check (index 0 unused)
@@ -114,6 +125,7 @@ class Position {
     memset(board, 0, sizeof(board));
     memset(hand, 0, sizeof(hand));
     side = BLACK; ply = 0;
+    king_sq[0] = king_sq[1] = -1;
     hashes.clear(); gave_check.clear(); snaps.clear();
   }
 
@@ -137,6 +149,7 @@ class Position {
         if (promo) t = promote(t);
         promo = false;
         board[sq_of(r, c)] = make_piece(t, color);
+        if (t == KING) king_sq[color] = static_cast<int8_t>(sq_of(r, c));
         ++c;
       }
     }
@@ -254,11 +267,7 @@ class Position {
     }
     return false;
   }
-  int king_square(int color) const {
-    for (int s = 0; s < kSquares; ++s)
-      if (board[s] == make_piece(KING, color)) return s;
-    return -1;
-  }
+  int king_square(int color) const { return king_sq[color]; }
   bool in_check(int color) const {
     const int k = king_square(color);
     return k >= 0 && attacked_by(k, color ^ 1);
@@ -274,6 +283,7 @@ class Position {
       if (m.captured) ++hand[us][hand_index(unpromote(static_cast<PieceType>(m.captured)))];
       board[m.to] = make_piece(m.promotes ? promote(static_cast<PieceType>(m.piece)) : m.piece, us);
       board[m.from] = 0;
+      if (m.piece == KING) king_sq[us] = m.to;
     }
     side ^= 1;
   }
@@ -285,6 +295,7 @@ class Position {
       ++hand[us][hand_index(static_cast<PieceType>(m.piece))];
     } else {
       board[m.from] = make_piece(m.piece, us);
+      if (m.piece == KING) king_sq[us] = m.from;
       board[m.to] = m.captured ? make_piece(m.captured, us ^ 1) : 0;
       if (m.captured) --hand[us][hand_index(unpromote(static_cast<PieceType>(m.captured)))];
     }
@@ -304,23 +315,42 @@ class Position {
   // ---- move generation ------------------------------------------------------------------------
   // Fully legal moves of the side to move (own king never left in check; nifu, last-rank pawn and
   // pawn-drop-mate excluded).
-  void generate_moves(std::vector<Move>& out) {
-    out.clear();
-    std::vector<Move> pseudo;
+  void generate_moves(MoveList& out) {
+    out.n = 0;
+    MoveList pseudo;
     pseudo_moves(pseudo);
     const int us = side;
+    const int ksq = king_sq[us];
+    const bool checked = ksq >= 0 && attacked_by(ksq, us ^ 1);
+    const int opp_k = king_sq[us ^ 1];
     for (const Move& m : pseudo) {
+      // Playing the move and testing for check is only needed when it could expose the king: we are in
+      // check, the king itself moves, or the piece leaves a line through the king (possible pin).  A pawn
+      // drop is additionally played out when it checks the enemy king (pawn-drop mate is illegal).
+      bool test = checked || ksq < 0 || m.piece == KING;
+      if (!test && !m.is_drop()) {
+        const int dr = rank_of(m.from) - rank_of(ksq), dc = col_of(m.from) - col_of(ksq);
+        test = dr == 0 || dc == 0 || dr == dc || dr == -dc;
+      }
+      const bool pawn_drop_check = m.is_drop() && m.piece == PAWN && opp_k >= 0 && col_of(opp_k) == col_of(m.to) &&
+                                   rank_of(opp_k) == rank_of(m.to) + (us == BLACK ? -1 : 1);
+      if (!test && !pawn_drop_check) { out.push(m); continue; }
       apply(m);
       bool ok = !in_check(us);
-      if (ok && m.is_drop() && m.piece == PAWN && in_check(side) && !has_legal_move()) ok = false;  // uchifuzume
+      if (ok && pawn_drop_check && !has_legal_move()) ok = false;  // uchifuzume
       revert(m);
-      if (ok) out.push_back(m);
+      if (ok) out.push(m);
     }
+  }
+  void generate_moves(std::vector<Move>& out) {
+    MoveList l;
+    generate_moves(l);
+    out.assign(l.begin(), l.end());
   }
   std::vector<Move> generate_moves() { std::vector<Move> v; generate_moves(v); return v; }
 
   bool has_legal_move() {
-    std::vector<Move> pseudo;
+    MoveList pseudo;
     pseudo_moves(pseudo);
     const int us = side;
     for (const Move& m : pseudo) {
@@ -404,7 +434,7 @@ class Position {
     snaps.push_back(sn);
   }
 
-  void pseudo_moves(std::vector<Move>& out) const {
+  void pseudo_moves(MoveList& out) const {
     const int us = side;
     const int sgn = us == BLACK ? 1 : -1;
     const int far = us == BLACK ? 0 : kN - 1;  // promotion rank
@@ -426,8 +456,8 @@ class Position {
           m.from = static_cast<int8_t>(s); m.to = static_cast<int8_t>(to); m.piece = static_cast<int8_t>(t);
           m.captured = static_cast<int8_t>(type_of(q));
           const bool zone = rank_of(s) == far || rr == far;
-          if (can_promote(t) && zone) { Move pm = m; pm.promotes = 1; out.push_back(pm); }
-          if (!(t == PAWN && rr == far)) out.push_back(m);  // a pawn on the last rank must promote
+          if (can_promote(t) && zone) { Move pm = m; pm.promotes = 1; out.push(pm); }
+          if (!(t == PAWN && rr == far)) out.push(m);  // a pawn on the last rank must promote
           if (q || !slide) break;
           rr += dr; cc += dc;
         }
@@ -447,13 +477,13 @@ class Position {
         }
         Move m;
         m.from = -1; m.to = static_cast<int8_t>(to); m.piece = static_cast<int8_t>(t);
-        out.push_back(m);
+        out.push(m);
       }
     }
   }
 
   bool mate_attack(int depth, Move* best) {
-    std::vector<Move> moves;
+    MoveList moves;
     generate_moves(moves);
     for (const Move& m : moves) {
       apply(m);
@@ -466,7 +496,7 @@ class Position {
   }
   // true iff the side to move (in check) is mated within `depth` further plies whatever it plays
   bool mate_defend(int depth) {
-    std::vector<Move> moves;
+    MoveList moves;
     generate_moves(moves);
     if (moves.empty()) return true;
     if (depth <= 1) return false;
