@@ -52,13 +52,26 @@ class SelfplayStats(C.Structure):
                 ("mean_game_plies", C.c_double), ("mean_gpu_batch", C.c_double)]
 
 
+GAME_SINK = C.CFUNCTYPE(None, C.c_void_p, C.c_char_p)
+
+
+class SelfplayConfig(C.Structure):
+    _fields_ = [("threads", C.c_int), ("total_moves", C.c_long), ("simulations", C.c_int), ("leaf_batch", C.c_int),
+                ("mate_depth", C.c_int), ("reuse_tree", C.c_int), ("use_dirichlet", C.c_int),
+                ("sampling_moves", C.c_int), ("max_moves", C.c_int), ("seed", C.c_uint64),
+                ("sink", GAME_SINK), ("sink_user", C.c_void_p)]
+
+
 _pos = C.c_void_p
+_mcts = C.c_void_p
 SIGNATURES.update({
+    "e55_get_arch": (C.c_int, [_ctx, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "e55_pos_create": (_pos, []),
     "e55_pos_destroy": (None, [_pos]),
     "e55_pos_copy": (_pos, [_pos]),
     "e55_pos_set_sfen": (C.c_int, [_pos, C.c_char_p]),
     "e55_pos_sfen": (C.c_int, [_pos, C.c_char_p, C.c_int]),
+    "e55_pos_print": (C.c_int, [_pos, C.c_char_p, C.c_int]),
     "e55_pos_side_to_move": (C.c_int, [_pos]),
     "e55_pos_ply": (C.c_int, [_pos]),
     "e55_pos_generate_moves": (C.c_int, [_pos, C.c_char_p, C.c_int]),
@@ -66,7 +79,33 @@ SIGNATURES.update({
     "e55_pos_is_repetition": (C.c_int, [_pos, C.POINTER(C.c_int)]),
     "e55_pos_solve_checkmate_dfs": (C.c_int, [_pos, C.c_int, C.c_char_p, C.c_int]),
     "e55_pos_encode_packed": (C.c_int, [_pos, C.c_void_p, C.c_void_p]),
+    "e55_pos_encode_packed_batch": (C.c_int, [C.POINTER(_pos), C.c_int, C.c_void_p, C.c_void_p]),
     "e55_pos_policy_index": (C.c_int, [_pos, C.c_char_p]),
+    "e55_mcts_create": (_mcts, [C.c_double]),
+    "e55_mcts_destroy": (None, [_mcts]),
+    "e55_mcts_clear": (C.c_int, [_mcts]),
+    "e55_mcts_configure": (C.c_int, [_mcts, C.c_float, C.c_float, C.c_float, C.c_uint64]),
+    "e55_mcts_set_root": (C.c_int, [_mcts, _pos, C.c_int]),
+    "e55_mcts_expanded": (C.c_int, [_mcts, C.c_int]),
+    "e55_mcts_evaluate": (C.c_int, [_mcts, C.c_int, _pos, C.c_void_p, C.c_float]),
+    "e55_mcts_add_noise": (C.c_int, [_mcts, C.c_int]),
+    "e55_mcts_select_leaf": (C.c_int, [_mcts, C.c_int, _pos, C.c_int]),
+    "e55_mcts_backpropagate": (C.c_int, [_mcts, C.c_int]),
+    "e55_mcts_get_usage": (C.c_double, [_mcts]),
+    "e55_mcts_get_nodes": (C.c_int, [_mcts]),
+    "e55_mcts_get_playouts": (C.c_int, [_mcts, C.c_int, C.c_int]),
+    "e55_mcts_best_move": (C.c_int, [_mcts, C.c_int, C.c_char_p, C.c_int]),
+    "e55_mcts_softmax_sample": (C.c_int, [_mcts, C.c_int, C.c_float, C.c_char_p, C.c_int]),
+    "e55_mcts_softmax_sample_among_top_moves": (C.c_int, [_mcts, C.c_int, C.c_float, C.c_float, C.c_char_p, C.c_int]),
+    "e55_mcts_info": (C.c_int, [_mcts, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_float)]),
+    "e55_mcts_dump": (C.c_int, [_mcts, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_float),
+                                C.c_char_p, C.c_int, C.POINTER(C.c_int), C.c_int]),
+    "e55_mcts_describe": (C.c_int, [_mcts, C.c_int, C.c_char_p, C.c_int]),
+    "e55_mcts_visualize": (C.c_int, [_mcts, C.c_int, C.c_int, C.c_char_p, C.c_int]),
+    "e55_mcts_search_root": (C.c_int, [_mcts, _ctx, _pos, C.c_int, C.c_int, C.c_int]),
+    "e55_mcts_search_batches": (C.c_int, [_mcts, _ctx, _pos, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "e55_selfplay_default_config": (None, [C.POINTER(SelfplayConfig)]),
+    "e55_selfplay_run_ex": (C.c_int, [_ctx, C.POINTER(SelfplayConfig), C.POINTER(SelfplayStats)]),
     "e55_selfplay_run": (C.c_int, [_ctx, C.c_int, C.c_long, C.c_int, C.c_int, C.c_int, C.c_uint64, C.POINTER(SelfplayStats)]),
 })
 

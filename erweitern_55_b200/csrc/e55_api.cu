@@ -654,6 +654,12 @@ int e55_stream(e55_ctx* c, void** stream_out) {
   return E55_OK;
 }
 
+int e55_get_arch(const e55_ctx* c, int* blocks_out, int* filters_out, int* in_planes_out) {
+  if (!c || !blocks_out || !filters_out || !in_planes_out) return E55_ERR_INVALID;
+  *blocks_out = c->blocks; *filters_out = c->filters; *in_planes_out = c->in_planes;
+  return E55_OK;
+}
+
 int e55_launch_count(const e55_ctx* c, int64_t* count_out) {
   if (!c || !count_out) return E55_ERR_INVALID;
   *count_out = c->launches;
@@ -823,4 +829,3 @@ int e55_bench_umma(int device, int n_dim, int iters, float* tflops_out) {
 }  // extern "C"
 
 #include "e55_service.inl"
-#include "e55_game.inl"

@@ -103,6 +103,13 @@ struct Snapshot {                    // what the input encoder needs of a past p
   uint8_t rep_count;                // occurrences of that position up to then (1..)
 };
 
+struct HistoryEntry {                // one per position of the game so far (index 0 = the position set_sfen gave)
+  uint64_t hash;
+  Snapshot snap;
+  uint8_t gave_check;               // the move leading here gave check (index 0: unused)
+  Move move;                        // the move leading here (index 0: unused)
+};
+
 class Position {
  public:
   int8_t board[kSquares];            // 0 = empty, else type | (color << 4)
@@ -110,10 +117,7 @@ class Position {
   int side = BLACK;
   int ply = 0;
   int8_t king_sq[2] = {-1, -1};      // cached king squares (-1: no king, as in some test positions)
-  // history for repetition / encoding
-  std::vector<uint64_t> hashes;      // hash after each ply (index 0 = initial position)
-  std::vector<uint8_t> gave_check;   // gave_check[i]: the move leading to hashes[i] gave check (index 0 unused)
-  std::vector<Snapshot> snaps;       // one per entry of `hashes`
+  std::vector<HistoryEntry> hist;    // history for repetition / encoding / tree reuse; hist[ply] = current position
 
   Position() { set_start_position(); }
 
@@ -126,7 +130,7 @@ class Position {
     memset(hand, 0, sizeof(hand));
     side = BLACK; ply = 0;
     king_sq[0] = king_sq[1] = -1;
-    hashes.clear(); gave_check.clear(); snaps.clear();
+    hist.clear();
   }
 
   void set_start_position() { set_sfen("rbsgk/4p/5/P4/KGSBR b - 1"); }
@@ -171,7 +175,7 @@ class Position {
     }
     while (i < sfen.size() && sfen[i] == ' ') ++i;
     while (i < sfen.size() && sfen[i] != ' ') ++i;  // move number (the reference always restarts ply at 0)
-    push_history(false);
+    push_history(false, Move());
     // optional move list
     size_t m = sfen.find("moves", i);
     if (m != std::string::npos) {
@@ -220,6 +224,26 @@ class Position {
         }
     s += h.empty() ? "-" : h;
     s += " " + std::to_string(ply + 1);
+    return s;
+  }
+
+  std::string pretty() const {       // Position.print(): the board as text, White's home rank on top
+    static const char* kLetters = " KGSBRPSBRP";
+    std::string s = "  5  4  3  2  1\n";
+    for (int r = 0; r < kN; ++r) {
+      for (int c = 0; c < kN; ++c) {
+        const int8_t p = board[sq_of(r, c)];
+        if (!p) { s += "  ."; continue; }
+        const int t = type_of(p);
+        s += ' ';
+        s += t >= PRO_SILVER ? '+' : ' ';
+        s += color_of(p) == WHITE ? static_cast<char>(kLetters[t] - 'A' + 'a') : kLetters[t];
+      }
+      s += "  ";
+      s += static_cast<char>('a' + r);
+      s += '\n';
+    }
+    s += "sfen " + sfen() + "\nply " + std::to_string(ply) + (side == BLACK ? " (first player to move)\n" : " (second player to move)\n");
     return s;
   }
 
@@ -304,10 +328,10 @@ class Position {
   void do_move(const Move& m) {
     apply(m);
     ++ply;
-    push_history(in_check(side));
+    push_history(in_check(side), m);
   }
   void undo_move(const Move& m) {
-    hashes.pop_back(); gave_check.pop_back(); snaps.pop_back();
+    hist.pop_back();
     --ply;
     revert(m);
   }
@@ -368,11 +392,12 @@ class Position {
   // of those occurrences gave check, that side is the perpetual checker.
   void is_repetition(bool& rep, bool& my_check, bool& op_check) const {
     rep = my_check = op_check = false;
-    const int last = static_cast<int>(hashes.size()) - 1;
-    const uint64_t h = hashes[last];
+    const int last = static_cast<int>(hist.size()) - 1;
+    if (hist[last].snap.rep_count < 4) return;
+    const uint64_t h = hist[last].hash;
     int count = 0, first = last;
     for (int i = last; i >= 0; i -= 2)
-      if (hashes[i] == h) { ++count; first = i; }
+      if (hist[i].hash == h) { ++count; first = i; }
     if (count < 4) return;
     rep = true;
     // moves leading to positions first+1 .. last; the move to position i was made by the side NOT to move at i
@@ -380,19 +405,13 @@ class Position {
     bool any_mine = false, any_theirs = false;
     for (int i = first + 1; i <= last; ++i) {
       const bool mover_is_me = ((last - i) & 1) == 1;  // position `last` has me to move; the move into it was theirs
-      if (mover_is_me) { any_mine = true; mine = mine && gave_check[i]; }
-      else { any_theirs = true; theirs = theirs && gave_check[i]; }
+      if (mover_is_me) { any_mine = true; mine = mine && hist[i].gave_check; }
+      else { any_theirs = true; theirs = theirs && hist[i].gave_check; }
     }
     my_check = any_mine && mine;
     op_check = any_theirs && theirs;
   }
-  int repetition_count() const {
-    const int last = static_cast<int>(hashes.size()) - 1;
-    int count = 0;
-    for (int i = last; i >= 0; i -= 2)
-      if (hashes[i] == hashes[last]) ++count;
-    return count;
-  }
+  int repetition_count() const { return hist.back().snap.rep_count; }
 
   // ---- mate search (tests/test_checkmate.py) ----------------------------------------------------
   // Depth-limited AND/OR search over checking sequences: the side to move must check on every move.
@@ -400,7 +419,7 @@ class Position {
     return depth > 0 && mate_attack(depth, &best);
   }
 
-  uint64_t hash() const { return hashes.back(); }
+  uint64_t hash() const { return hist.back().hash; }
 
  private:
   static PieceType letter_type(char ch) {
@@ -423,15 +442,18 @@ class Position {
       for (int k = 0; k < kHandTypes; ++k) h ^= mix(4096 + (c * kHandTypes + k) * 8 + hand[c][k]);
     return h;
   }
-  void push_history(bool check) {
-    hashes.push_back(compute_hash());
-    gave_check.push_back(check ? 1 : 0);
-    Snapshot sn;
-    memcpy(sn.board, board, sizeof(board));
-    memcpy(sn.hand, hand, sizeof(hand));
-    const int c = repetition_count();
-    sn.rep_count = static_cast<uint8_t>(c > 255 ? 255 : c);
-    snaps.push_back(sn);
+  void push_history(bool check, const Move& m) {
+    HistoryEntry e;
+    e.hash = compute_hash();
+    e.gave_check = check ? 1 : 0;
+    e.move = m;
+    memcpy(e.snap.board, board, sizeof(board));
+    memcpy(e.snap.hand, hand, sizeof(hand));
+    int c = 1;                                          // occurrences of this position so far (same side to move)
+    for (int i = static_cast<int>(hist.size()) - 2; i >= 0; i -= 2)
+      if (hist[i].hash == e.hash) { c += hist[i].snap.rep_count; break; }   // the latest earlier occurrence knows the rest
+    e.snap.rep_count = static_cast<uint8_t>(c > 255 ? 255 : c);
+    hist.push_back(e);
   }
 
   void pseudo_moves(MoveList& out) const {
@@ -525,11 +547,11 @@ inline void encode_packed(const Position& pos, uint32_t* bits, float* scale) {
   for (int c = 0; c < kInputPlanes; ++c) { bits[c] = 0u; scale[c] = 1.f; }
   const int me = pos.side;
   const uint32_t all = (1u << kSquares) - 1u;
-  const int last = static_cast<int>(pos.snaps.size()) - 1;
+  const int last = static_cast<int>(pos.hist.size()) - 1;
   for (int t = 0; t < kHistory; ++t) {
     const int idx = last - t;
     if (idx < 0) break;
-    const Snapshot& sn = pos.snaps[idx];
+    const Snapshot& sn = pos.hist[idx].snap;
     const int base = t * kPlanesPerStep;
     for (int s = 0; s < kSquares; ++s) {
       const int8_t p = sn.board[s];

@@ -150,6 +150,12 @@ class Network:
         shape = [1] + self.input_shape if dim_4 else self.input_shape
         return np.reshape(position.to_alphazero_input(), shape)
 
+    def predict_positions(self, positions):
+        """``predict(get_inputs(positions))`` without the float planes: positions of this package's engine are encoded
+        bit-packed in one native call (identical results, 12.5x fewer bytes over PCIe)."""
+        from .minishogi import encode_packed_batch
+        return self.predict_packed(*encode_packed_batch(positions))
+
     def get_inputs(self, positions):
         ins = np.zeros([len(positions)] + self.input_shape, dtype="float32")
         for i, position in enumerate(positions):
@@ -194,15 +200,14 @@ class Network:
         self._check(self._lib.e55_service_stats(self._ctx, C.byref(b), C.byref(p)))
         return int(b.value), int(p.value)
 
-    def selfplay(self, threads, total_moves, simulations=800, leaf_batch=16, mate_depth=7, seed=1):
+    def selfplay(self, threads, total_moves, simulations=800, leaf_batch=16, mate_depth=7, seed=1, **kw):
         """Real self-play on the running service with the native minishogi engine + MCTS (``selfplay.run``'s loop,
-        selfplay.py:10-113): returns a dict of moves, evals, games, seconds, mean game length and mean GPU batch."""
-        st = _capi.SelfplayStats()
-        self._check(self._lib.e55_selfplay_run(self._ctx, threads, total_moves, simulations, leaf_batch, mate_depth,
-                                               seed, C.byref(st)))
-        return {"seconds": st.seconds, "moves": st.moves, "evals": st.evals, "games": st.games,
-                "mean_game_plies": st.mean_game_plies, "mean_gpu_batch": st.mean_gpu_batch,
-                "moves_per_s": st.moves / st.seconds, "evals_per_s": st.evals / st.seconds}
+        selfplay.py:10-113, with client.py's search settings): a dict of moves, evals, games, seconds, mean game length
+        and mean GPU batch.  See :func:`erweitern_55_b200.selfplay.run_many` for the game records."""
+        from . import selfplay as _selfplay
+        stats, _ = _selfplay.run_many(self, threads, total_moves, simulations, leaf_batch, mate_depth, seed=seed,
+                                      records=False, **kw)
+        return stats
 
     def bench_selfplay(self, workers, moves, simulations=800, leaf_batch=16):
         """Synthetic self-play load on the running service -> (moves/s, evals/s, mean GPU batch)."""

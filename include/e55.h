@@ -109,24 +109,61 @@ int e55_service_stats(e55_ctx* ctx, int64_t* batches_out, int64_t* positions_out
 int e55_bench_selfplay(e55_ctx* ctx, int workers, int moves, int simulations, int leaf_batch,
                        double* moves_per_s_out, double* evals_per_s_out, double* mean_batch_out);
 
-/* ---- native minishogi engine + self-play -----------------------------------------
+/* Tower shape the context was created with (e55_create arguments). */
+int e55_get_arch(const e55_ctx* ctx, int* blocks_out, int* filters_out, int* in_planes_out);
+
+/* ---- native minishogi engine, search tree and self-play -------------------
  * Counterpart of the external Rust library minishogilib v0.6.12 the reference drives from Python
- * (selfplay.py:11-36,78; mcts.py:27-110; tests/test_checkmate.py, tests/test_repetition.py).  Moves and
- * positions travel as SFEN/USI strings ("5e4d", "3d4e+", "G*1d"). */
+ * (selfplay.py:11-36,78; mcts.py:27-205; usi.py:39-140; tests/test_checkmate.py, tests/test_repetition.py).
+ * Moves and positions travel as SFEN/USI strings ("5e4d", "3d4e+", "G*1d"); move lists are space separated. */
 typedef struct e55_pos e55_pos;
 e55_pos* e55_pos_create(void);                                  /* Position(); starts at the initial position */
 void e55_pos_destroy(e55_pos* pos);
 e55_pos* e55_pos_copy(const e55_pos* pos);                      /* Position.copy(True) */
 int e55_pos_set_sfen(e55_pos* pos, const char* sfen);           /* "board side hands n [moves m1 m2 ...]" */
 int e55_pos_sfen(const e55_pos* pos, char* buf, int buflen);
+int e55_pos_print(const e55_pos* pos, char* buf, int buflen);   /* Position.print(): board as text */
 int e55_pos_side_to_move(const e55_pos* pos);                   /* 0 = first player (black), 1 = second */
 int e55_pos_ply(const e55_pos* pos);
-int e55_pos_generate_moves(e55_pos* pos, char* buf, int buflen); /* legal moves, space separated; returns count */
+int e55_pos_generate_moves(e55_pos* pos, char* buf, int buflen); /* legal moves; returns count */
 int e55_pos_do_move(e55_pos* pos, const char* move);            /* E55_ERR_INVALID if the move is not legal */
 int e55_pos_is_repetition(const e55_pos* pos, int out3[3]);     /* (is_repetition, my_check_rep, op_check_rep) */
 int e55_pos_solve_checkmate_dfs(e55_pos* pos, int depth, char* move_buf, int buflen);  /* 1 = mate found */
 int e55_pos_encode_packed(const e55_pos* pos, uint32_t* bits, float* scale);   /* 266-plane input, packed */
+int e55_pos_encode_packed_batch(const e55_pos* const* pos, int n, uint32_t* bits, float* scale);  /* Network.get_inputs */
 int e55_pos_policy_index(e55_pos* pos, const char* move);       /* index of a legal move in the 1725 logits */
+
+/* minishogilib.MCTS as mcts.py drives it (mcts.py:27-205).  Nodes are small integers valid until the next
+ * set_root/clear; the root is node 0.  One tree serves one search at a time. */
+typedef struct e55_mcts e55_mcts;
+e55_mcts* e55_mcts_create(double memory_gb);                    /* minishogilib.MCTS(memory_size), mcts.py:27 */
+void e55_mcts_destroy(e55_mcts* m);
+int e55_mcts_clear(e55_mcts* m);
+int e55_mcts_configure(e55_mcts* m, float c_puct, float dirichlet_alpha, float dirichlet_eps, uint64_t seed);
+int e55_mcts_set_root(e55_mcts* m, const e55_pos* pos, int reuse_tree);                    /* -> root node, mcts.py:50 */
+int e55_mcts_expanded(const e55_mcts* m, int node);                                        /* mcts.py:56 */
+int e55_mcts_evaluate(e55_mcts* m, int node, e55_pos* pos, const float* policy, float value01);  /* mcts.py:60,105 */
+int e55_mcts_add_noise(e55_mcts* m, int node);                                             /* mcts.py:64 */
+int e55_mcts_select_leaf(e55_mcts* m, int node, e55_pos* pos, int forced_playouts);        /* -> leaf node; pos advanced, mcts.py:97 */
+int e55_mcts_backpropagate(e55_mcts* m, int leaf);                                         /* mcts.py:110 */
+double e55_mcts_get_usage(const e55_mcts* m);                                              /* mcts.py:72 */
+int e55_mcts_get_nodes(const e55_mcts* m);                                                 /* mcts.py:116 */
+int e55_mcts_get_playouts(const e55_mcts* m, int node, int child_sum);                     /* mcts.py:88 */
+int e55_mcts_best_move(e55_mcts* m, int node, char* buf, int buflen);                      /* 1 = move written, 0 = no children */
+int e55_mcts_softmax_sample(e55_mcts* m, int node, float temperature, char* buf, int buflen);
+int e55_mcts_softmax_sample_among_top_moves(e55_mcts* m, int node, float away, float temperature, char* buf, int buflen);
+int e55_mcts_info(const e55_mcts* m, int node, char* pv_buf, int buflen, float* q_out);    /* -> pv length, mcts.py:114 */
+int e55_mcts_dump(const e55_mcts* m, int node, int target_pruning, int remove_zeros, int* sum_n_out, float* q_out,
+                  char* moves_buf, int buflen, int* counts, int max_counts);               /* -> entries, mcts.py:187 */
+int e55_mcts_describe(const e55_mcts* m, int node, char* buf, int buflen);                 /* MCTS.print / debug */
+int e55_mcts_visualize(const e55_mcts* m, int node, int node_num, char* buf, int buflen);  /* dot, mcts.py:205 */
+/* The two halves of MCTS.run done natively on a network context (packed inputs, no Python per leaf):
+ * search_root = set the root, evaluate it if needed, add noise (mcts.py:49-64); returns 1 for a terminal root.
+ * search_batches = n_batches iterations of select / ONE network call / expand / back up (mcts.py:91-110);
+ * returns the simulations done.  use_service routes the calls through the evaluation service. */
+int e55_mcts_search_root(e55_mcts* m, e55_ctx* ctx, const e55_pos* pos, int reuse_tree, int use_dirichlet, int use_service);
+int e55_mcts_search_batches(e55_mcts* m, e55_ctx* ctx, const e55_pos* pos, int n_batches, int leaf_batch,
+                            int forced_playouts, int use_service);
 
 typedef struct e55_selfplay_stats {
   double seconds;          /* wall time of the run */
@@ -137,9 +174,29 @@ typedef struct e55_selfplay_stats {
   double mean_gpu_batch;   /* positions per GPU forward as coalesced by the evaluation service */
 } e55_selfplay_stats;
 
+/* Receives one finished game as text: "winner W ply P\n" then one line per ply
+ * "<move> <sum_N> <Q> <k> <m1> <n1> ... <mk> <nk>" (gamerecord.py:3-9).  Calls are serialised. */
+typedef void (*e55_game_sink)(void* user, const char* record);
+
+typedef struct e55_selfplay_config {
+  int threads;             /* host threads, one game each at a time */
+  long total_moves;        /* stop after this many plies in total */
+  int simulations;         /* per move (client.py:29: 800) */
+  int leaf_batch;          /* leaves per network call (client.py:28: 16) */
+  int mate_depth;          /* solve_checkmate_dfs depth before each search, 0 = off (selfplay.py:36: 7) */
+  int reuse_tree;          /* client.py:32 */
+  int use_dirichlet;       /* client.py:31 */
+  int sampling_moves;      /* plies sampled from the visit counts (selfplay.py:10: 10) */
+  int max_moves;           /* selfplay.py:10: 512 */
+  uint64_t seed;
+  e55_game_sink sink;      /* optional: game records */
+  void* sink_user;
+} e55_selfplay_config;
+void e55_selfplay_default_config(e55_selfplay_config* cfg);
+
 /* Self-play on the running evaluation service: `threads` host threads each play whole games the way
- * selfplay.run does (selfplay.py:10-113; mate search of `mate_depth` plies, MCTS of `simulations` simulations in
- * batches of `leaf_batch`, sampling for the first 10 plies) until `total_moves` plies have been played. */
+ * selfplay.run does (selfplay.py:10-113) with client.py's search settings until `total_moves` plies have been played. */
+int e55_selfplay_run_ex(e55_ctx* ctx, const e55_selfplay_config* cfg, e55_selfplay_stats* stats_out);
 int e55_selfplay_run(e55_ctx* ctx, int threads, long total_moves, int simulations, int leaf_batch, int mate_depth,
                      uint64_t seed, e55_selfplay_stats* stats_out);
 

@@ -291,6 +291,78 @@ def test_native_selfplay_and_python_search_loop(weights_default):
     net.close()
 
 
+class _ReferenceStyleNetwork:
+    """Only the reference's three calls (get_input / get_inputs / predict), so mcts.MCTS.run takes its leaf-by-leaf
+    Python path (mcts.py:91-110) instead of the native batch step."""
+
+    def __init__(self, net):
+        self.get_input, self.get_inputs, self.predict = net.get_input, net.get_inputs, net.predict
+
+
+def test_native_search_equals_the_reference_style_python_loop(weights_perturbed):
+    """mcts.MCTS.run on the native batch step (bit-packed inputs, one C call per leaf batch) builds exactly the tree
+    the reference's Python loop builds with the same Network: same visit counts, same principal variation."""
+    from erweitern_55_b200 import mcts
+    from erweitern_55_b200.minishogi import Position
+    from erweitern_55_b200.network import Network
+    net = Network(precision="bf16", weights=weights_perturbed)
+    results = []
+    for nn in (net, _ReferenceStyleNetwork(net)):
+        cfg = mcts.Config()
+        cfg.simulation_num = 256
+        search = mcts.MCTS(cfg)
+        p = Position()
+        dumps = []
+        for _ in range(3):                                              # three moves: tree reuse included
+            root = search.run(p, nn)
+            dumps.append((search.dump(root), [m.sfen() for m in search.mcts.info(root)[0]]))
+            p.do_move(search.best_move(root))
+        results.append(dumps)
+    assert results[0] == results[1]
+    assert results[0][0][0][0] == 256 and results[0][1][0][0] >= 256    # reused subtree adds to the next search
+    pp, vp = net.predict_positions([p])
+    pf, vf = net.predict(net.get_inputs([p]))
+    assert np.array_equal(pp, pf) and np.array_equal(vp, vf)
+    net.close()
+
+
+def test_selfplay_records_and_usi_on_the_gpu(weights_default):
+    import io
+    from erweitern_55_b200 import mcts, selfplay, usi
+    from erweitern_55_b200.minishogi import Move, Position
+    from erweitern_55_b200.network import Network
+    net = Network(precision="bf16", weights=weights_default)
+    # one game through the reference-shaped selfplay.run (native batch step underneath)
+    cfg = mcts.Config()
+    cfg.simulation_num = 64
+    cfg.use_dirichlet = True
+    rec = selfplay.run(net, mcts.MCTS(cfg), max_moves=12)
+    assert rec.ply == len(rec.sfen_kif) == len(rec.mcts_result) > 4
+    # many games on the native driver, records through the sink
+    net.start_service(max_batch=512, max_wait_us=200)
+    stats, games = selfplay.run_many(net, threads=16, total_moves=400, simulations=32, leaf_batch=16, mate_depth=3,
+                                     max_moves=20, seed=11)
+    net.stop_service()
+    assert stats["games"] == len(games) >= 8 and stats["mean_gpu_batch"] > 4
+    for g in games:
+        q = Position()
+        for move, (sum_n, qv, visits) in zip(g.sfen_kif, g.mcts_result):
+            assert move in {m.sfen() for m in q.generate_moves()} and sum_n == sum(n for _, n in visits)
+            q.do_move(Move(move))
+    # USI in latency mode on the direct (non-service) path
+    out = io.StringIO()
+    engine = usi.USI(nn=net, stdout=out, stdin=io.StringIO(
+        "usi\nisready\nposition startpos moves 5d5c\ngo btime 2000 wtime 2000 byoyomi 0\nquit\n"))
+    engine.start()
+    lines = out.getvalue().splitlines()
+    best = [l.split()[1] for l in lines if l.startswith("bestmove")]
+    start = Position(); start.do_move(Move("5d5c"))
+    assert len(best) == 1 and best[0] in {m.sfen() for m in start.generate_moves()}
+    nodes = [int(l.split()[4]) for l in lines if l.startswith("info depth")]
+    assert nodes and nodes[-1] > 2000                                   # 200 ms of batch-16 forwards at ~100 us each
+    net.close()
+
+
 def test_device_resident_api(nets):
     net = nets["default", "bf16"]
     x = synth.synthetic_planes(100, seed=12)
