@@ -26,6 +26,8 @@ SIGNATURES = {
     "e55_predict_device": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "e55_predict_packed": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "e55_predict_packed_device": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "e55_predict_packed_moves": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "e55_service_predict_packed_moves": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "e55_predict_masked": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "e55_predict_masked_device": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "e55_service_start": (C.c_int, [_ctx, C.c_int, C.c_int]),

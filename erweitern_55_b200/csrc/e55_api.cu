@@ -85,6 +85,11 @@ struct e55_ctx {
   uint8_t* d_mask = nullptr;
   uint32_t* d_bits = nullptr;   // packed input staging: [capacity][in_planes]
   float* d_scale = nullptr;
+  // compact legal-move tail (e55_predict_packed_moves): CSR move lists and their priors
+  static constexpr int kMovesPerPosition = 128;   // capacity per position on average; a single position may use more
+  int32_t* d_move_off = nullptr;   // [capacity + 1]
+  uint16_t* d_move_idx = nullptr;  // [capacity * kMovesPerPosition]
+  float* d_priors = nullptr;       // [capacity * kMovesPerPosition]
 };
 
 namespace {
@@ -121,6 +126,8 @@ void free_buffers(e55_ctx* c) {
   for (auto& p : c->d_act) { cudaFree(p); p = nullptr; }
   cudaFree(c->d_policy); cudaFree(c->d_value); cudaFree(c->d_probs); cudaFree(c->d_mask);
   cudaFree(c->d_bits); cudaFree(c->d_scale);
+  cudaFree(c->d_move_off); cudaFree(c->d_move_idx); cudaFree(c->d_priors);
+  c->d_move_off = nullptr; c->d_move_idx = nullptr; c->d_priors = nullptr;
   c->d_in = c->d_policy = c->d_value = c->d_probs = c->d_scale = nullptr;
   c->d_mask = nullptr; c->d_bits = nullptr;
   e55::tc::free_buffers(c->tc);
@@ -142,6 +149,9 @@ int ensure_capacity(e55_ctx* c, int n) {
   E55_CUDA(c, cudaMalloc(&c->d_mask, static_cast<size_t>(cap) * kPolicyCh * kSq));
   E55_CUDA(c, cudaMalloc(&c->d_bits, static_cast<size_t>(cap) * c->in_planes * sizeof(uint32_t)));
   E55_CUDA(c, cudaMalloc(&c->d_scale, static_cast<size_t>(cap) * c->in_planes * sizeof(float)));
+  E55_CUDA(c, cudaMalloc(&c->d_move_off, (static_cast<size_t>(cap) + 1) * sizeof(int32_t)));
+  E55_CUDA(c, cudaMalloc(&c->d_move_idx, static_cast<size_t>(cap) * e55_ctx::kMovesPerPosition * sizeof(uint16_t)));
+  E55_CUDA(c, cudaMalloc(&c->d_priors, static_cast<size_t>(cap) * e55_ctx::kMovesPerPosition * sizeof(float)));
   cudaError_t e = e55::tc::alloc_buffers(c->tc, cap);
   if (e != cudaSuccess) return fail(c, E55_ERR_CUDA, std::string("tc buffers: ") + cudaGetErrorString(e));
   c->capacity = cap;
@@ -601,6 +611,36 @@ int e55_predict_packed(e55_ctx* c, const uint32_t* bits, const float* scale, int
     E55_CUDA(c, cudaEventRecord(c->pipe_done[i], c->pipe_stream[i]));
     E55_CUDA(c, cudaStreamWaitEvent(c->stream, c->pipe_done[i], 0));
   }
+  E55_CUDA(c, cudaStreamSynchronize(c->stream));
+  return E55_OK;
+}
+
+int e55_predict_packed_moves(e55_ctx* c, const uint32_t* bits, const float* scale, int n, const int32_t* move_offset,
+                             const uint16_t* move_index, float* priors, float* value) {
+  int rc = check_predict_args(c, bits, priors, value, n);
+  if (rc) return rc;
+  if (!scale || !move_offset || !move_index) return fail(c, E55_ERR_INVALID, "null buffer");
+  const int total = move_offset[n];
+  if (move_offset[0] != 0 || total < 0) return fail(c, E55_ERR_INVALID, "move_offset must start at 0 and be non-decreasing");
+  for (int i = 0; i < n; ++i)
+    if (move_offset[i + 1] < move_offset[i]) return fail(c, E55_ERR_INVALID, "move_offset must start at 0 and be non-decreasing");
+  for (int j = 0; j < total; ++j)
+    if (move_index[j] >= kPolicyCh * kSq) return fail(c, E55_ERR_INVALID, "move index outside the 1725 policy entries");
+  std::lock_guard<std::mutex> lk(c->mu);
+  E55_CUDA(c, cudaSetDevice(c->device));
+  if ((rc = ensure_capacity(c, std::max(n, (total + e55_ctx::kMovesPerPosition - 1) / e55_ctx::kMovesPerPosition)))) return rc;
+  const size_t w = static_cast<size_t>(n) * c->in_planes;
+  E55_CUDA(c, cudaMemcpyAsync(c->d_bits, bits, w * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  E55_CUDA(c, cudaMemcpyAsync(c->d_scale, scale, w * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  E55_CUDA(c, cudaMemcpyAsync(c->d_move_off, move_offset, (static_cast<size_t>(n) + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  if (total) E55_CUDA(c, cudaMemcpyAsync(c->d_move_idx, move_index, static_cast<size_t>(total) * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
+  if ((rc = forward_packed_on(c, c->stream, c->d_bits, c->d_scale, n, 0, c->d_policy, c->d_value))) return rc;
+  e55::legal_priors_kernel<<<(n + 7) / 8, 256, 0, c->stream>>>(c->d_policy, c->d_move_off, c->d_move_idx, c->d_priors, n,
+                                                                    kPolicyCh * kSq);
+  ++c->launches;
+  E55_CUDA(c, cudaGetLastError());
+  if (total) E55_CUDA(c, cudaMemcpyAsync(priors, c->d_priors, static_cast<size_t>(total) * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  E55_CUDA(c, cudaMemcpyAsync(value, c->d_value, static_cast<size_t>(n) * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   E55_CUDA(c, cudaStreamSynchronize(c->stream));
   return E55_OK;
 }

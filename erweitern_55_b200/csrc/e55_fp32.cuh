@@ -188,4 +188,28 @@ masked_softmax_kernel(const float* __restrict__ logits, const uint8_t* __restric
 }
 
 }  // namespace fp32
+// Legal-move policy tail in compact form: for position p the logits at index[offset[p] .. offset[p+1]) (the policy
+// indices of its legal moves, at most a few dozen of the 1725) are soft-maxed and written to priors at the same
+// offsets -- what minishogilib.MCTS.evaluate does with a policy row (mcts.py:60,105-106), without moving the other
+// ~1700 logits to the host.  One warp per position, warp-shuffle max/sum reductions.
+__global__ void __launch_bounds__(256)
+legal_priors_kernel(const float* __restrict__ logits, const int32_t* __restrict__ offset, const uint16_t* __restrict__ index,
+                    float* __restrict__ priors, int n, int width) {
+  const int lane = threadIdx.x & 31;
+  const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (p >= n) return;
+  const int beg = offset[p], end = offset[p + 1];
+  const float* row = logits + static_cast<size_t>(p) * width;
+  float m = -INFINITY;
+  for (int j = beg + lane; j < end; j += 32) m = fmaxf(m, row[index[j]]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float sum = 0.f;
+  for (int j = beg + lane; j < end; j += 32) sum += __expf(row[index[j]] - m);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = sum > 0.f ? 1.f / sum : 0.f;
+  for (int j = beg + lane; j < end; j += 32) priors[j] = __expf(row[index[j]] - m) * inv;
+}
+
 }  // namespace e55

@@ -22,7 +22,9 @@ struct e55_mcts {
   mshogi::Mcts tree;
   // scratch of the native search steps (e55_mcts_search_root / e55_mcts_search_batches)
   std::vector<uint32_t> bits;
-  std::vector<float> scale, policy, value;
+  std::vector<float> scale, priors, value;
+  std::vector<int32_t> move_off;
+  std::vector<uint16_t> move_idx;
   std::vector<int32_t> leaf;
   std::vector<mshogi::Position> leaf_pos;
   std::vector<mshogi::MoveList> leaf_moves;
@@ -59,7 +61,9 @@ bool is_default_net(e55_ctx* ctx) {
 // ---- one search = what mcts.MCTS.run does for one move (mcts.py:32-138) ---------------------------------------
 struct SearchScratch {
   std::vector<uint32_t>* bits;
-  std::vector<float>*scale, *policy, *value;
+  std::vector<float>*scale, *priors, *value;
+  std::vector<int32_t>* move_off;
+  std::vector<uint16_t>* move_idx;
   std::vector<int32_t>* leaf;
   std::vector<mshogi::Position>* leaf_pos;
   std::vector<mshogi::MoveList>* leaf_moves;
@@ -68,7 +72,9 @@ struct SearchScratch {
     if (static_cast<int>(leaf->size()) >= leaf_batch) return;
     bits->resize(static_cast<size_t>(leaf_batch) * kInputPlanes);
     scale->resize(bits->size());
-    policy->resize(static_cast<size_t>(leaf_batch) * kPolicySize);
+    priors->resize(static_cast<size_t>(leaf_batch) * 256);     // MoveList holds at most 256 moves
+    move_idx->resize(priors->size());
+    move_off->resize(static_cast<size_t>(leaf_batch) + 1);
     value->resize(leaf_batch);
     leaf->resize(leaf_batch);
     leaf_pos->resize(leaf_batch);
@@ -81,10 +87,12 @@ struct Evaluator {
   e55_ctx* ctx;
   bool use_service;
   long evals = 0;
-  int operator()(const uint32_t* bits, const float* scale, int n, float* policy, float* value) {
+  // priors[j] = softmax over the logits at move_idx[move_off[i] .. move_off[i+1]) of position i, computed on the GPU
+  int operator()(const uint32_t* bits, const float* scale, int n, const int32_t* move_off, const uint16_t* move_idx,
+                 float* priors, float* value) {
     evals += n;
-    return use_service ? e55_service_predict_packed(ctx, bits, scale, n, policy, value)
-                       : e55_predict_packed(ctx, bits, scale, n, policy, value);
+    return use_service ? e55_service_predict_packed_moves(ctx, bits, scale, n, move_off, move_idx, priors, value)
+                       : e55_predict_packed_moves(ctx, bits, scale, n, move_off, move_idx, priors, value);
   }
 };
 
@@ -104,9 +112,11 @@ int search_root(mshogi::Mcts& tree, SearchScratch& s, Evaluator& nn, const mshog
       tree.set_terminal(root, tv);
     } else {
       encode_packed(root_pos, s.bits->data(), s.scale->data());
-      const int rc = nn(s.bits->data(), s.scale->data(), 1, s.policy->data(), s.value->data());
+      (*s.move_off)[0] = 0; (*s.move_off)[1] = moves.size();
+      for (int i = 0; i < moves.size(); ++i) (*s.move_idx)[i] = static_cast<uint16_t>(policy_index(moves.m[i], root_pos.side));
+      const int rc = nn(s.bits->data(), s.scale->data(), 1, s.move_off->data(), s.move_idx->data(), s.priors->data(), s.value->data());
       if (rc != E55_OK) return rc;
-      tree.expand_from_logits(root, root_pos.side, moves, s.policy->data(), ((*s.value)[0] + 1.f) * 0.5f);
+      tree.expand_from_priors(root, moves, s.priors->data(), ((*s.value)[0] + 1.f) * 0.5f);
     }
   }
   if (tree.nodes[root].terminal) return 1;
@@ -124,8 +134,11 @@ int search_batches(mshogi::Mcts& tree, SearchScratch& s, Evaluator& nn, const ms
   std::vector<Position>& leaf_pos = *s.leaf_pos;
   std::vector<MoveList>& leaf_moves = *s.leaf_moves;
   std::vector<int>& eval_slot = *s.eval_slot;
+  int32_t* move_off = s.move_off->data();
+  uint16_t* move_idx = s.move_idx->data();
   for (int it = 0; it < n_batches; ++it) {
     int n_eval = 0;
+    move_off[0] = 0;
     for (int b = 0; b < leaf_batch; ++b) {
       leaf_pos[b] = root_pos;
       leaf[b] = tree.select_leaf(0, leaf_pos[b], forced_playouts);
@@ -136,16 +149,19 @@ int search_batches(mshogi::Mcts& tree, SearchScratch& s, Evaluator& nn, const ms
       eval_slot[b] = n_eval;
       encode_packed(leaf_pos[b], s.bits->data() + static_cast<size_t>(n_eval) * kInputPlanes,
                     s.scale->data() + static_cast<size_t>(n_eval) * kInputPlanes);
+      const MoveList& lm = leaf_moves[b];                       // the policy entries of the legal moves go along
+      uint16_t* idx = move_idx + move_off[n_eval];
+      for (int i = 0; i < lm.size(); ++i) idx[i] = static_cast<uint16_t>(policy_index(lm.m[i], leaf_pos[b].side));
+      move_off[n_eval + 1] = move_off[n_eval] + lm.size();
       ++n_eval;
     }
     if (n_eval > 0) {
-      const int rc = nn(s.bits->data(), s.scale->data(), n_eval, s.policy->data(), s.value->data());
+      const int rc = nn(s.bits->data(), s.scale->data(), n_eval, move_off, move_idx, s.priors->data(), s.value->data());
       if (rc != E55_OK) return rc;
     }
     for (int b = 0; b < leaf_batch; ++b)
       if (eval_slot[b] >= 0)
-        tree.expand_from_logits(leaf[b], leaf_pos[b].side, leaf_moves[b],
-                                s.policy->data() + static_cast<size_t>(eval_slot[b]) * kPolicySize,
+        tree.expand_from_priors(leaf[b], leaf_moves[b], s.priors->data() + move_off[eval_slot[b]],
                                 ((*s.value)[eval_slot[b]] + 1.f) * 0.5f);
     for (int b = 0; b < leaf_batch; ++b) tree.backpropagate(leaf[b]);
   }
@@ -172,7 +188,7 @@ struct SelfplayWorker {
   void run() {
     using namespace mshogi;
     const e55_selfplay_config& cfg = sh->cfg;
-    SearchScratch s{&m.bits, &m.scale, &m.policy, &m.value, &m.leaf, &m.leaf_pos, &m.leaf_moves, &m.eval_slot};
+    SearchScratch s{&m.bits, &m.scale, &m.priors, &m.value, &m.move_off, &m.move_idx, &m.leaf, &m.leaf_pos, &m.leaf_moves, &m.eval_slot};
     Evaluator nn{sh->ctx, true};
     m.tree.rng.seed(seed);
     const int n_batches = (cfg.simulations + cfg.leaf_batch - 1) / cfg.leaf_batch;
@@ -427,7 +443,7 @@ int e55_mcts_visualize(const e55_mcts* m, int node, int node_num, char* buf, int
 
 int e55_mcts_search_root(e55_mcts* m, e55_ctx* ctx, const e55_pos* pos, int reuse_tree, int use_dirichlet, int use_service) {
   if (!m || !ctx || !pos || !is_default_net(ctx)) return E55_ERR_INVALID;
-  SearchScratch s{&m->bits, &m->scale, &m->policy, &m->value, &m->leaf, &m->leaf_pos, &m->leaf_moves, &m->eval_slot};
+  SearchScratch s{&m->bits, &m->scale, &m->priors, &m->value, &m->move_off, &m->move_idx, &m->leaf, &m->leaf_pos, &m->leaf_moves, &m->eval_slot};
   Evaluator nn{ctx, use_service != 0};
   return search_root(m->tree, s, nn, pos->p, reuse_tree != 0, use_dirichlet != 0);
 }
@@ -437,7 +453,7 @@ int e55_mcts_search_batches(e55_mcts* m, e55_ctx* ctx, const e55_pos* pos, int n
   if (!m || !ctx || !pos || n_batches < 1 || leaf_batch < 1 || leaf_batch > 4096 || !is_default_net(ctx)) return E55_ERR_INVALID;
   const mshogi::Node& root = m->tree.nodes[0];
   if (!root.expanded || root.terminal) return E55_ERR_INVALID;   // e55_mcts_search_root first
-  SearchScratch s{&m->bits, &m->scale, &m->policy, &m->value, &m->leaf, &m->leaf_pos, &m->leaf_moves, &m->eval_slot};
+  SearchScratch s{&m->bits, &m->scale, &m->priors, &m->value, &m->move_off, &m->move_idx, &m->leaf, &m->leaf_pos, &m->leaf_moves, &m->eval_slot};
   Evaluator nn{ctx, use_service != 0};
   const int rc = search_batches(m->tree, s, nn, pos->p, n_batches, leaf_batch, forced_playouts != 0);
   return rc != E55_OK ? rc : n_batches * leaf_batch;

@@ -15,8 +15,12 @@ struct ServiceBatch {
   float* scale = nullptr;
   float* policy = nullptr;      // [cap][1725]
   float* value = nullptr;       // [cap]
-  int kind = 0;                 // 0 = empty, 1 = float planes, 2 = packed
+  int32_t* move_off = nullptr;  // [cap + 1]              (packed + legal-move requests: CSR move lists)
+  uint16_t* move_idx = nullptr; // [cap * kMovesPerPosition]
+  float* priors = nullptr;      // [cap * kMovesPerPosition]
+  int kind = 0;                 // 0 = empty, 1 = float planes, 2 = packed, 3 = packed + legal moves -> priors
   int reserved = 0;             // positions handed out
+  int moves_reserved = 0;       // move slots handed out (kind 3)
   std::atomic<int> filled{0};   // positions whose input copy has finished
   std::atomic<int> readers{0};              // requests that still have to fetch their output
   std::atomic<uint64_t> generation{0};      // bumped when the batch's results are ready (futex-style wait/notify)
@@ -57,9 +61,23 @@ int service_forward(e55_ctx* c, ServiceBatch& b) {
     const size_t w = static_cast<size_t>(n) * c->in_planes;
     E55_CUDA(c, cudaMemcpyAsync(c->d_bits, b.bits, w * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     E55_CUDA(c, cudaMemcpyAsync(c->d_scale, b.scale, w * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    if (b.kind == 3) {
+      b.move_off[n] = b.moves_reserved;
+      E55_CUDA(c, cudaMemcpyAsync(c->d_move_off, b.move_off, (static_cast<size_t>(n) + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+      if (b.moves_reserved)
+        E55_CUDA(c, cudaMemcpyAsync(c->d_move_idx, b.move_idx, static_cast<size_t>(b.moves_reserved) * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
+    }
     if ((rc = forward_packed_on(c, c->stream, c->d_bits, c->d_scale, n, 0, c->d_policy, c->d_value))) return rc;
   }
-  E55_CUDA(c, cudaMemcpyAsync(b.policy, c->d_policy, pol * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  if (b.kind == 3) {   // only the legal moves' priors travel back
+    e55::legal_priors_kernel<<<(n + 7) / 8, 256, 0, c->stream>>>(c->d_policy, c->d_move_off, c->d_move_idx, c->d_priors, n, kPolicyCh * kSq);
+    ++c->launches;
+    E55_CUDA(c, cudaGetLastError());
+    if (b.moves_reserved)
+      E55_CUDA(c, cudaMemcpyAsync(b.priors, c->d_priors, static_cast<size_t>(b.moves_reserved) * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  } else {
+    E55_CUDA(c, cudaMemcpyAsync(b.policy, c->d_policy, pol * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  }
   E55_CUDA(c, cudaMemcpyAsync(b.value, c->d_value, static_cast<size_t>(n) * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   E55_CUDA(c, cudaStreamSynchronize(c->stream));
   return E55_OK;
@@ -82,7 +100,7 @@ void service_loop(e55_ctx* c) {
     lk.unlock();
     for (int r; (r = next.readers.load(std::memory_order_acquire)) != 0;) next.readers.wait(r);
     lk.lock();
-    next.kind = 0; next.reserved = 0; next.filled.store(0);
+    next.kind = 0; next.reserved = 0; next.moves_reserved = 0; next.filled.store(0);
     b.in_flight = true;
     s->open ^= 1;
     s->cv_space.notify_all();
@@ -99,25 +117,30 @@ void service_loop(e55_ctx* c) {
   }
 }
 
-// Blocking aggregated predict: kind 1 (planes) or 2 (bits + scale).
+// Blocking aggregated predict: kind 1 (planes), 2 (bits + scale) or 3 (bits + scale + legal-move lists; `policy`
+// then receives the priors of those moves, move_offset[n] floats).
 int service_predict(e55_ctx* c, int kind, const float* planes, const uint32_t* bits, const float* scale, int n,
-                    float* policy, float* value) {
+                    float* policy, float* value, const int32_t* move_offset = nullptr, const uint16_t* move_index = nullptr) {
   e55_service* s = c->service;
   auto fail_locked = [&](int code, const char* msg) {   // many threads call in: serialise the error string
     std::lock_guard<std::mutex> g(c->mu);
     return fail(c, code, msg);
   };
   if (!s) return fail_locked(E55_ERR_INVALID, "evaluation service is not running (e55_service_start)");
-  if (n <= 0 || !policy || !value || (kind == 1 ? !planes : (!bits || !scale)))
+  if (n <= 0 || !policy || !value || (kind == 1 ? !planes : (!bits || !scale)) || (kind == 3 && (!move_offset || !move_index)))
     return fail_locked(E55_ERR_INVALID, "bad service request");
   if (n > s->cap) return fail_locked(E55_ERR_INVALID, "request larger than the service batch");
+  const int total = kind == 3 ? move_offset[n] : 0;
+  if (kind == 3 && (move_offset[0] != 0 || total < 0 || total > s->cap * e55_ctx::kMovesPerPosition))
+    return fail_locked(E55_ERR_INVALID, "bad move lists in service request");
   if (!c->has_weights) return fail_locked(E55_ERR_NO_WEIGHTS, "predict called before e55_set_weights");
   std::unique_lock<std::mutex> lk(s->m);
   ServiceBatch* b = nullptr;
   for (;;) {
     if (s->stop) { lk.unlock(); return fail_locked(E55_ERR_INVALID, "evaluation service stopped"); }
     b = &s->batch[s->open];
-    if (!b->in_flight && (b->kind == 0 || b->kind == kind) && b->reserved + n <= s->cap) break;
+    if (!b->in_flight && (b->kind == 0 || b->kind == kind) && b->reserved + n <= s->cap &&
+        b->moves_reserved + total <= s->cap * e55_ctx::kMovesPerPosition) break;
     if (b->reserved > 0) s->force_close = true;   // the open batch cannot take this request: dispatch it now
     s->cv_submit.notify_one();
     s->cv_space.wait(lk);
@@ -125,6 +148,8 @@ int service_predict(e55_ctx* c, int kind, const float* planes, const uint32_t* b
   const int off = b->reserved;
   if (off == 0) { b->kind = kind; b->first_arrival = std::chrono::steady_clock::now(); }
   b->reserved += n;
+  const int moff = b->moves_reserved;
+  b->moves_reserved += total;
   b->readers.fetch_add(1, std::memory_order_relaxed);
   const uint64_t gen = b->generation.load(std::memory_order_relaxed);
   s->cv_submit.notify_one();
@@ -136,13 +161,19 @@ int service_predict(e55_ctx* c, int kind, const float* planes, const uint32_t* b
   } else {
     memcpy(b->bits + off * ip, bits, static_cast<size_t>(n) * ip * sizeof(uint32_t));
     memcpy(b->scale + off * ip, scale, static_cast<size_t>(n) * ip * sizeof(float));
+    if (kind == 3) {
+      for (int i = 0; i < n; ++i) b->move_off[off + i] = moff + move_offset[i];
+      for (int j = 0; j < total; ++j)     // an index outside the policy row would read foreign memory: clamp it
+        b->move_idx[moff + j] = move_index[j] < kPolicyCh * kSq ? move_index[j] : static_cast<uint16_t>(kPolicyCh * kSq - 1);
+    }
   }
   b->filled.fetch_add(n, std::memory_order_release);
 
   while (b->generation.load(std::memory_order_acquire) == gen) b->generation.wait(gen);
   const int rc = b->status;
   if (rc == E55_OK) {
-    memcpy(policy, b->policy + static_cast<size_t>(off) * kPolicyCh * kSq, static_cast<size_t>(n) * kPolicyCh * kSq * sizeof(float));
+    if (kind == 3) memcpy(policy, b->priors + moff, static_cast<size_t>(total) * sizeof(float));
+    else memcpy(policy, b->policy + static_cast<size_t>(off) * kPolicyCh * kSq, static_cast<size_t>(n) * kPolicyCh * kSq * sizeof(float));
     memcpy(value, b->value + off, static_cast<size_t>(n) * sizeof(float));
   }
   if (b->readers.fetch_sub(1, std::memory_order_release) == 1) b->readers.notify_all();
@@ -152,6 +183,7 @@ int service_predict(e55_ctx* c, int kind, const float* planes, const uint32_t* b
 void service_free(e55_service* s) {
   for (auto& b : s->batch) {
     cudaFreeHost(b.planes); cudaFreeHost(b.bits); cudaFreeHost(b.scale); cudaFreeHost(b.policy); cudaFreeHost(b.value);
+    cudaFreeHost(b.move_off); cudaFreeHost(b.move_idx); cudaFreeHost(b.priors);
   }
   delete s;
 }
@@ -179,6 +211,9 @@ int e55_service_start(e55_ctx* c, int max_batch, int max_wait_us) {
     if (e == cudaSuccess) e = cudaMallocHost(&b.scale, max_batch * ip * sizeof(float));
     if (e == cudaSuccess) e = cudaMallocHost(&b.policy, static_cast<size_t>(max_batch) * kPolicyCh * kSq * sizeof(float));
     if (e == cudaSuccess) e = cudaMallocHost(&b.value, max_batch * sizeof(float));
+    if (e == cudaSuccess) e = cudaMallocHost(&b.move_off, (static_cast<size_t>(max_batch) + 1) * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMallocHost(&b.move_idx, static_cast<size_t>(max_batch) * e55_ctx::kMovesPerPosition * sizeof(uint16_t));
+    if (e == cudaSuccess) e = cudaMallocHost(&b.priors, static_cast<size_t>(max_batch) * e55_ctx::kMovesPerPosition * sizeof(float));
     if (e != cudaSuccess) { service_free(s); return fail(c, E55_ERR_CUDA, std::string("pinned staging: ") + cudaGetErrorString(e)); }
   }
   c->service = s;
@@ -210,6 +245,12 @@ int e55_service_predict(e55_ctx* c, const float* planes, int n, float* policy, f
 int e55_service_predict_packed(e55_ctx* c, const uint32_t* bits, const float* scale, int n, float* policy, float* value) {
   if (!c) return E55_ERR_INVALID;
   return service_predict(c, 2, nullptr, bits, scale, n, policy, value);
+}
+
+int e55_service_predict_packed_moves(e55_ctx* c, const uint32_t* bits, const float* scale, int n, const int32_t* move_offset,
+                                     const uint16_t* move_index, float* priors, float* value) {
+  if (!c) return E55_ERR_INVALID;
+  return service_predict(c, 3, nullptr, bits, scale, n, priors, value, move_offset, move_index);
 }
 
 int e55_service_stats(e55_ctx* c, int64_t* batches_out, int64_t* positions_out) {

@@ -13,9 +13,12 @@
 // perpetual check loses.  The network input encoding and the policy index (to_alphazero_input, and the move
 // indexing inside minishogilib.MCTS.evaluate) are NOT visible in the reference tree; they are restated here
 // as documented below and are "parity unpinned" against minishogilib.
+//
+// Representation: a 25-bit bitboard per (colour, piece type) beside the mailbox board.  Legal moves are generated
+// directly (checkers, pins and king-danger squares from attack tables) instead of by make/unmake trials; the hash
+// is an incrementally updated Zobrist key.
 #pragma once
 #include <algorithm>
-#include <array>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -28,6 +31,8 @@ enum Color : int { BLACK = 0, WHITE = 1 };
 enum PieceType : int { EMPTY = 0, KING, GOLD, SILVER, BISHOP, ROOK, PAWN, PRO_SILVER, HORSE, DRAGON, TOKIN, PIECE_TYPES };
 constexpr int kHandTypes = 5;  // GOLD, SILVER, BISHOP, ROOK, PAWN
 constexpr PieceType kHandPiece[kHandTypes] = {GOLD, SILVER, BISHOP, ROOK, PAWN};
+using Bitboard = uint32_t;     // bit sq = rank * 5 + col
+constexpr Bitboard kAllSquares = (1u << kSquares) - 1u;
 
 inline int hand_index(PieceType t) {  // unpromoted type -> hand slot
   switch (t) { case GOLD: return 0; case SILVER: return 1; case BISHOP: return 2; case ROOK: return 3; case PAWN: return 4; default: return -1; }
@@ -44,6 +49,9 @@ inline bool can_promote(PieceType t) { return t == SILVER || t == BISHOP || t ==
 inline int sq_of(int rank, int col) { return rank * kN + col; }
 inline int rank_of(int sq) { return sq / kN; }
 inline int col_of(int sq) { return sq % kN; }
+inline int lsb(Bitboard b) { return __builtin_ctz(b); }
+inline int msb(Bitboard b) { return 31 - __builtin_clz(b); }
+inline int pop_lsb(Bitboard& b) { const int s = __builtin_ctz(b); b &= b - 1; return s; }
 
 struct Move {
   int8_t from = -1;      // -1: drop
@@ -86,6 +94,84 @@ inline uint32_t slide_mask(PieceType t) {
     default: return 0;
   }
 }
+constexpr uint32_t kRookDirs = (1u << 0) | (1u << 2) | (1u << 4) | (1u << 6);
+constexpr uint32_t kBishopDirs = (1u << 1) | (1u << 3) | (1u << 5) | (1u << 7);
+
+// ---- attack tables (built once) ------------------------------------------------------------------------------
+struct Tables {
+  Bitboard step_to[2][PIECE_TYPES][kSquares];   // squares a (colour, type) piece standing on sq steps to
+  Bitboard step_from[2][PIECE_TYPES][kSquares]; // squares from which a (colour, type) piece steps onto sq
+  Bitboard ray[8][kSquares];                    // all squares from sq in absolute direction d (N = towards rank 0)
+  Bitboard between[kSquares][kSquares];         // squares strictly between two aligned squares (else 0)
+  Bitboard line[kSquares][kSquares];            // the whole line through two aligned squares incl. both (else 0)
+  Bitboard file_mask[kN];
+  Bitboard rank_mask[kN];
+  uint64_t zob_piece[kSquares][32];
+  uint64_t zob_hand[2][kHandTypes][4];
+  uint64_t zob_side[2];
+
+  static uint64_t mix(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull; x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+  }
+  Tables() {
+    memset(static_cast<void*>(this), 0, sizeof(*this));
+    auto on = [](int r, int c) { return r >= 0 && r < kN && c >= 0 && c < kN; };
+    for (int s = 0; s < kSquares; ++s) {
+      const int r = rank_of(s), c = col_of(s);
+      for (int d = 0; d < 8; ++d) {
+        int rr = r + kDirR[d], cc = c + kDirC[d];
+        Bitboard acc = 0;
+        while (on(rr, cc)) {
+          const int t = sq_of(rr, cc);
+          between[s][t] = acc;
+          acc |= 1u << t;
+          rr += kDirR[d]; cc += kDirC[d];
+        }
+        ray[d][s] = acc;
+      }
+      for (int color = 0; color < 2; ++color)
+        for (int t = 1; t < PIECE_TYPES; ++t) {
+          const uint32_t steps = step_mask(static_cast<PieceType>(t));
+          for (int d = 0; d < 8; ++d) {
+            if (!(steps >> d & 1)) continue;
+            const int rr = r + kDirR[d] * (color == BLACK ? 1 : -1), cc = c + kDirC[d];
+            if (on(rr, cc)) step_to[color][t][s] |= 1u << sq_of(rr, cc);
+          }
+        }
+      file_mask[c] |= 1u << s;
+      rank_mask[r] |= 1u << s;
+    }
+    for (int color = 0; color < 2; ++color)
+      for (int t = 1; t < PIECE_TYPES; ++t)
+        for (int s = 0; s < kSquares; ++s)
+          for (Bitboard b = step_to[color][t][s]; b;) step_from[color][t][pop_lsb(b)] |= 1u << s;
+    for (int a = 0; a < kSquares; ++a)
+      for (int d = 0; d < 8; ++d)
+        for (Bitboard b = ray[d][a]; b;) line[a][pop_lsb(b)] = ray[d][a] | ray[(d + 4) & 7][a] | (1u << a);
+    for (int s = 0; s < kSquares; ++s)
+      for (int p = 1; p < 32; ++p) zob_piece[s][p] = mix(static_cast<uint64_t>(s) * 64 + static_cast<uint64_t>(p));
+    for (int c = 0; c < 2; ++c)
+      for (int k = 0; k < kHandTypes; ++k)
+        for (int n = 1; n < 4; ++n) zob_hand[c][k][n] = mix(4096 + static_cast<uint64_t>((c * kHandTypes + k) * 8 + n));
+    zob_side[BLACK] = 0x1234567ull; zob_side[WHITE] = 0x7654321ull;
+  }
+};
+inline const Tables& tables() { static const Tables t; return t; }
+
+// Squares attacked by a slider on `sq` along the directions in `dirs` (bit d), given the occupancy.
+inline Bitboard slide_attacks(const Tables& T, int sq, Bitboard occ, uint32_t dirs) {
+  Bitboard att = 0;
+  for (int d = (dirs & 1) ? 0 : 1; d < 8; d += 2) {     // the four rook or the four bishop directions
+    const Bitboard r = T.ray[d][sq];
+    const Bitboard blockers = r & occ;
+    if (!blockers) { att |= r; continue; }
+    // directions 2 (E), 3 (SE), 4 (S), 5 (SW) run towards higher square numbers
+    const int b = (d >= 2 && d <= 5) ? lsb(blockers) : msb(blockers);
+    att |= r ^ T.ray[d][b];
+  }
+  return att;
+}
 
 struct MoveList {                    // no position has anywhere near 256 legal moves on a 5x5 board
   Move m[256];
@@ -98,7 +184,7 @@ struct MoveList {                    // no position has anywhere near 256 legal 
 };
 
 struct Snapshot {                    // what the input encoder needs of a past position
-  int8_t board[kSquares];           // type | color << 4
+  Bitboard pieces[2][PIECE_TYPES - 1];   // [colour][type - 1]
   int8_t hand[2][kHandTypes];
   uint8_t rep_count;                // occurrences of that position up to then (1..)
 };
@@ -114,6 +200,7 @@ class Position {
  public:
   int8_t board[kSquares];            // 0 = empty, else type | (color << 4)
   int8_t hand[2][kHandTypes];
+  Bitboard bb[2][PIECE_TYPES];       // [colour][type]; index 0 = all pieces of that colour
   int side = BLACK;
   int ply = 0;
   int8_t king_sq[2] = {-1, -1};      // cached king squares (-1: no king, as in some test positions)
@@ -128,6 +215,7 @@ class Position {
   void clear() {
     memset(board, 0, sizeof(board));
     memset(hand, 0, sizeof(hand));
+    memset(bb, 0, sizeof(bb));
     side = BLACK; ply = 0;
     king_sq[0] = king_sq[1] = -1;
     hist.clear();
@@ -152,8 +240,7 @@ class Position {
         if (t == EMPTY || r >= kN || c >= kN) return false;
         if (promo) t = promote(t);
         promo = false;
-        board[sq_of(r, c)] = make_piece(t, color);
-        if (t == KING) king_sq[color] = static_cast<int8_t>(sq_of(r, c));
+        put(sq_of(r, c), t, color);
         ++c;
       }
     }
@@ -175,7 +262,7 @@ class Position {
     }
     while (i < sfen.size() && sfen[i] == ' ') ++i;
     while (i < sfen.size() && sfen[i] != ' ') ++i;  // move number (the reference always restarts ply at 0)
-    push_history(false, Move());
+    push_history(compute_hash(), false, Move());
     // optional move list
     size_t m = sfen.find("moves", i);
     if (m != std::string::npos) {
@@ -271,26 +358,22 @@ class Position {
   }
 
   // ---- attacks -------------------------------------------------------------------------------
-  bool attacked_by(int sq, int by) const {
-    const int r = rank_of(sq), c = col_of(sq);
-    const int sgn = by == BLACK ? 1 : -1;  // BLACK's forward is -rank
-    for (int d = 0; d < 8; ++d) {
-      // a piece of `by` standing at sq - dir attacks sq if it can step/slide in dir
-      const int dr = kDirR[d] * sgn, dc = kDirC[d];
-      int rr = r - dr, cc = c - dc;
-      if (rr < 0 || rr >= kN || cc < 0 || cc >= kN) continue;
-      int8_t p = board[sq_of(rr, cc)];
-      if (p && color_of(p) == by && ((step_mask(static_cast<PieceType>(type_of(p))) | slide_mask(static_cast<PieceType>(type_of(p)))) >> d & 1)) return true;
-      // sliders further away
-      while (!p) {
-        rr -= dr; cc -= dc;
-        if (rr < 0 || rr >= kN || cc < 0 || cc >= kN) break;
-        p = board[sq_of(rr, cc)];
-        if (p) { if (color_of(p) == by && (slide_mask(static_cast<PieceType>(type_of(p))) >> d & 1)) return true; break; }
-      }
-    }
-    return false;
+  Bitboard occupied() const { return bb[BLACK][0] | bb[WHITE][0]; }
+
+  // Pieces of colour `by` that attack `sq`, with `occ` as the blocking set (pass a modified occupancy to look
+  // through a piece that is about to move).
+  Bitboard attackers_to(int sq, int by, Bitboard occ) const {
+    const Tables& T = tables();
+    const Bitboard* b = bb[by];
+    Bitboard att = (T.step_from[by][PAWN][sq] & b[PAWN]) | (T.step_from[by][SILVER][sq] & b[SILVER]) |
+                   (T.step_from[by][GOLD][sq] & (b[GOLD] | b[PRO_SILVER] | b[TOKIN])) |
+                   (T.step_from[by][KING][sq] & (b[KING] | b[HORSE] | b[DRAGON]));
+    const Bitboard rooks = b[ROOK] | b[DRAGON], bishops = b[BISHOP] | b[HORSE];
+    if (rooks) att |= slide_attacks(T, sq, occ, kRookDirs) & rooks;
+    if (bishops) att |= slide_attacks(T, sq, occ, kBishopDirs) & bishops;
+    return att;
   }
+  bool attacked_by(int sq, int by) const { return attackers_to(sq, by, occupied()) != 0; }
   int king_square(int color) const { return king_sq[color]; }
   bool in_check(int color) const {
     const int k = king_square(color);
@@ -301,13 +384,15 @@ class Position {
   void apply(const Move& m) {
     const int us = side;
     if (m.is_drop()) {
-      board[m.to] = make_piece(m.piece, us);
+      put(m.to, m.piece, us);
       --hand[us][hand_index(static_cast<PieceType>(m.piece))];
     } else {
-      if (m.captured) ++hand[us][hand_index(unpromote(static_cast<PieceType>(m.captured)))];
-      board[m.to] = make_piece(m.promotes ? promote(static_cast<PieceType>(m.piece)) : m.piece, us);
-      board[m.from] = 0;
-      if (m.piece == KING) king_sq[us] = m.to;
+      if (m.captured) {
+        lift(m.to, m.captured, us ^ 1);
+        ++hand[us][hand_index(unpromote(static_cast<PieceType>(m.captured)))];
+      }
+      lift(m.from, m.piece, us);
+      put(m.to, m.promotes ? promote(static_cast<PieceType>(m.piece)) : m.piece, us);
     }
     side ^= 1;
   }
@@ -315,20 +400,23 @@ class Position {
     side ^= 1;
     const int us = side;
     if (m.is_drop()) {
-      board[m.to] = 0;
+      lift(m.to, m.piece, us);
       ++hand[us][hand_index(static_cast<PieceType>(m.piece))];
     } else {
-      board[m.from] = make_piece(m.piece, us);
-      if (m.piece == KING) king_sq[us] = m.from;
-      board[m.to] = m.captured ? make_piece(m.captured, us ^ 1) : 0;
-      if (m.captured) --hand[us][hand_index(unpromote(static_cast<PieceType>(m.captured)))];
+      lift(m.to, m.promotes ? promote(static_cast<PieceType>(m.piece)) : m.piece, us);
+      put(m.from, m.piece, us);
+      if (m.captured) {
+        put(m.to, m.captured, us ^ 1);
+        --hand[us][hand_index(unpromote(static_cast<PieceType>(m.captured)))];
+      }
     }
   }
 
   void do_move(const Move& m) {
+    const uint64_t h = hash_after(m);
     apply(m);
     ++ply;
-    push_history(in_check(side), m);
+    push_history(h, in_check(side), m);
   }
   void undo_move(const Move& m) {
     hist.pop_back();
@@ -339,53 +427,14 @@ class Position {
   // ---- move generation ------------------------------------------------------------------------
   // Fully legal moves of the side to move (own king never left in check; nifu, last-rank pawn and
   // pawn-drop-mate excluded).
-  void generate_moves(MoveList& out) {
-    out.n = 0;
-    MoveList pseudo;
-    pseudo_moves(pseudo);
-    const int us = side;
-    const int ksq = king_sq[us];
-    const bool checked = ksq >= 0 && attacked_by(ksq, us ^ 1);
-    const int opp_k = king_sq[us ^ 1];
-    for (const Move& m : pseudo) {
-      // Playing the move and testing for check is only needed when it could expose the king: we are in
-      // check, the king itself moves, or the piece leaves a line through the king (possible pin).  A pawn
-      // drop is additionally played out when it checks the enemy king (pawn-drop mate is illegal).
-      bool test = checked || ksq < 0 || m.piece == KING;
-      if (!test && !m.is_drop()) {
-        const int dr = rank_of(m.from) - rank_of(ksq), dc = col_of(m.from) - col_of(ksq);
-        test = dr == 0 || dc == 0 || dr == dc || dr == -dc;
-      }
-      const bool pawn_drop_check = m.is_drop() && m.piece == PAWN && opp_k >= 0 && col_of(opp_k) == col_of(m.to) &&
-                                   rank_of(opp_k) == rank_of(m.to) + (us == BLACK ? -1 : 1);
-      if (!test && !pawn_drop_check) { out.push(m); continue; }
-      apply(m);
-      bool ok = !in_check(us);
-      if (ok && pawn_drop_check && !has_legal_move()) ok = false;  // uchifuzume
-      revert(m);
-      if (ok) out.push(m);
-    }
-  }
+  void generate_moves(MoveList& out) { out.n = 0; generate<false>(&out); }
   void generate_moves(std::vector<Move>& out) {
     MoveList l;
     generate_moves(l);
     out.assign(l.begin(), l.end());
   }
   std::vector<Move> generate_moves() { std::vector<Move> v; generate_moves(v); return v; }
-
-  bool has_legal_move() {
-    MoveList pseudo;
-    pseudo_moves(pseudo);
-    const int us = side;
-    for (const Move& m : pseudo) {
-      apply(m);
-      bool ok = !in_check(us);
-      if (ok && m.is_drop() && m.piece == PAWN && in_check(side) && !has_legal_move()) ok = false;
-      revert(m);
-      if (ok) return true;
-    }
-    return false;
-  }
+  bool has_legal_move() { return generate<true>(nullptr); }
 
   // ---- repetition (tests/test_repetition.py) -----------------------------------------------------
   // The position has now occurred four times -> repetition.  If every move one side made since the first
@@ -395,10 +444,9 @@ class Position {
     const int last = static_cast<int>(hist.size()) - 1;
     if (hist[last].snap.rep_count < 4) return;
     const uint64_t h = hist[last].hash;
-    int count = 0, first = last;
+    int first = last;
     for (int i = last; i >= 0; i -= 2)
-      if (hist[i].hash == h) { ++count; first = i; }
-    if (count < 4) return;
+      if (hist[i].hash == h) first = i;
     rep = true;
     // moves leading to positions first+1 .. last; the move to position i was made by the side NOT to move at i
     bool mine = true, theirs = true;   // "mine" = side to move now
@@ -421,6 +469,15 @@ class Position {
 
   uint64_t hash() const { return hist.back().hash; }
 
+  uint64_t compute_hash() const {
+    const Tables& T = tables();
+    uint64_t h = T.zob_side[side];
+    for (int s = 0; s < kSquares; ++s) h ^= T.zob_piece[s][board[s] & 31];
+    for (int c = 0; c < 2; ++c)
+      for (int k = 0; k < kHandTypes; ++k) h ^= T.zob_hand[c][k][hand[c][k] & 3];
+    return h;
+  }
+
  private:
   static PieceType letter_type(char ch) {
     switch (ch) {
@@ -430,78 +487,138 @@ class Position {
     }
   }
 
-  static uint64_t mix(uint64_t x) {
-    x += 0x9E3779B97F4A7C15ull; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull; x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
-    return x ^ (x >> 31);
+  void put(int sq, int type, int color) {
+    board[sq] = make_piece(type, color);
+    bb[color][type] |= 1u << sq;
+    bb[color][0] |= 1u << sq;
+    if (type == KING) king_sq[color] = static_cast<int8_t>(sq);
   }
-  uint64_t compute_hash() const {
-    uint64_t h = side == BLACK ? 0x1234567ull : 0x7654321ull;
-    for (int s = 0; s < kSquares; ++s)
-      if (board[s]) h ^= mix(static_cast<uint64_t>(s) * 64 + static_cast<uint8_t>(board[s]));
-    for (int c = 0; c < 2; ++c)
-      for (int k = 0; k < kHandTypes; ++k) h ^= mix(4096 + (c * kHandTypes + k) * 8 + hand[c][k]);
-    return h;
-  }
-  void push_history(bool check, const Move& m) {
-    HistoryEntry e;
-    e.hash = compute_hash();
-    e.gave_check = check ? 1 : 0;
-    e.move = m;
-    memcpy(e.snap.board, board, sizeof(board));
-    memcpy(e.snap.hand, hand, sizeof(hand));
-    int c = 1;                                          // occurrences of this position so far (same side to move)
-    for (int i = static_cast<int>(hist.size()) - 2; i >= 0; i -= 2)
-      if (hist[i].hash == e.hash) { c += hist[i].snap.rep_count; break; }   // the latest earlier occurrence knows the rest
-    e.snap.rep_count = static_cast<uint8_t>(c > 255 ? 255 : c);
-    hist.push_back(e);
+  void lift(int sq, int type, int color) {
+    board[sq] = 0;
+    bb[color][type] &= ~(1u << sq);
+    bb[color][0] &= ~(1u << sq);
   }
 
-  void pseudo_moves(MoveList& out) const {
+  // Key of the position after `m` (called before apply).
+  uint64_t hash_after(const Move& m) const {
+    const Tables& T = tables();
     const int us = side;
-    const int sgn = us == BLACK ? 1 : -1;
-    const int far = us == BLACK ? 0 : kN - 1;  // promotion rank
-    for (int s = 0; s < kSquares; ++s) {
-      const int8_t p = board[s];
-      if (!p || color_of(p) != us) continue;
-      const PieceType t = static_cast<PieceType>(type_of(p));
-      const uint32_t steps = step_mask(t), slides = slide_mask(t);
-      for (int d = 0; d < 8; ++d) {
-        const bool slide = slides >> d & 1;
-        if (!slide && !(steps >> d & 1)) continue;
-        const int dr = kDirR[d] * sgn, dc = kDirC[d];
-        int rr = rank_of(s) + dr, cc = col_of(s) + dc;
-        while (rr >= 0 && rr < kN && cc >= 0 && cc < kN) {
-          const int to = sq_of(rr, cc);
-          const int8_t q = board[to];
-          if (q && color_of(q) == us) break;
-          Move m;
-          m.from = static_cast<int8_t>(s); m.to = static_cast<int8_t>(to); m.piece = static_cast<int8_t>(t);
-          m.captured = static_cast<int8_t>(type_of(q));
-          const bool zone = rank_of(s) == far || rr == far;
-          if (can_promote(t) && zone) { Move pm = m; pm.promotes = 1; out.push(pm); }
-          if (!(t == PAWN && rr == far)) out.push(m);  // a pawn on the last rank must promote
-          if (q || !slide) break;
-          rr += dr; cc += dc;
-        }
+    uint64_t h = hist.back().hash ^ T.zob_side[BLACK] ^ T.zob_side[WHITE];
+    if (m.is_drop()) {
+      const int k = hand_index(static_cast<PieceType>(m.piece));
+      h ^= T.zob_hand[us][k][hand[us][k] & 3] ^ T.zob_hand[us][k][(hand[us][k] - 1) & 3];
+      h ^= T.zob_piece[m.to][make_piece(m.piece, us) & 31];
+    } else {
+      if (m.captured) {
+        const int k = hand_index(unpromote(static_cast<PieceType>(m.captured)));
+        h ^= T.zob_piece[m.to][make_piece(m.captured, us ^ 1) & 31];
+        h ^= T.zob_hand[us][k][hand[us][k] & 3] ^ T.zob_hand[us][k][(hand[us][k] + 1) & 3];
+      }
+      h ^= T.zob_piece[m.from][make_piece(m.piece, us) & 31];
+      h ^= T.zob_piece[m.to][make_piece(m.promotes ? promote(static_cast<PieceType>(m.piece)) : m.piece, us) & 31];
+    }
+    return h;
+  }
+
+  void push_history(uint64_t h, bool check, const Move& m) {
+    hist.emplace_back();
+    HistoryEntry& e = hist.back();
+    e.hash = h;
+    e.gave_check = check ? 1 : 0;
+    e.move = m;
+    for (int c = 0; c < 2; ++c)
+      for (int t = 1; t < PIECE_TYPES; ++t) e.snap.pieces[c][t - 1] = bb[c][t];
+    memcpy(e.snap.hand, hand, sizeof(hand));
+    int c = 1;                                          // occurrences of this position so far (same side to move)
+    for (int i = static_cast<int>(hist.size()) - 3; i >= 0; i -= 2)
+      if (hist[i].hash == h) { c += hist[i].snap.rep_count; break; }   // the latest earlier occurrence knows the rest
+    e.snap.rep_count = static_cast<uint8_t>(c > 255 ? 255 : c);
+  }
+
+  static void emit(MoveList* out, int from, int to, PieceType t, int captured, bool promo_zone, int far_rank) {
+    Move m;
+    m.from = static_cast<int8_t>(from); m.to = static_cast<int8_t>(to); m.piece = static_cast<int8_t>(t);
+    m.captured = static_cast<int8_t>(captured);
+    if (promo_zone && can_promote(t)) { Move pm = m; pm.promotes = 1; out->push(pm); }
+    if (!(t == PAWN && rank_of(to) == far_rank)) out->push(m);       // a pawn on the last rank must promote
+  }
+
+  // Legal move generation.  kAny: stop at the first legal move and return true (`out` is not used).
+  template <bool kAny>
+  bool generate(MoveList* out) {
+    const Tables& T = tables();
+    const int us = side, them = us ^ 1;
+    const int far = us == BLACK ? 0 : kN - 1;      // promotion rank
+    const Bitboard own = bb[us][0], occ = occupied();
+    const int ksq = king_sq[us];
+    Bitboard checkers = 0, pinned = 0;
+    Bitboard target_mask = kAllSquares;            // where non-king pieces may land (blocks / captures when in check)
+    if (ksq >= 0) {
+      checkers = attackers_to(ksq, them, occ);
+      // pins: an enemy slider aligned with the king with exactly one piece, ours, in between
+      const Bitboard rooks = bb[them][ROOK] | bb[them][DRAGON], bishops = bb[them][BISHOP] | bb[them][HORSE];
+      Bitboard snipers = 0;
+      if (rooks) snipers |= slide_attacks(T, ksq, 0, kRookDirs) & rooks;
+      if (bishops) snipers |= slide_attacks(T, ksq, 0, kBishopDirs) & bishops;
+      while (snipers) {
+        const Bitboard b = T.between[ksq][pop_lsb(snipers)] & occ;
+        if (b && !(b & (b - 1)) && (b & own)) pinned |= b;
+      }
+      if (checkers) {
+        if (checkers & (checkers - 1)) target_mask = 0;                                   // double check: king moves only
+        else target_mask = checkers | T.between[ksq][lsb(checkers)];
+      }
+      // king moves: the destination must not be attacked once the king has left its square
+      for (Bitboard dst = T.step_to[us][KING][ksq] & ~own; dst;) {
+        const int to = pop_lsb(dst);
+        if (attackers_to(to, them, occ ^ (1u << ksq))) continue;
+        if (kAny) return true;
+        emit(out, ksq, to, KING, type_of(board[to]), false, far);
       }
     }
-    for (int k = 0; k < kHandTypes; ++k) {
-      if (!hand[us][k]) continue;
-      const PieceType t = kHandPiece[k];
-      for (int to = 0; to < kSquares; ++to) {
-        if (board[to]) continue;
-        if (t == PAWN) {
-          if (rank_of(to) == far) continue;
-          bool nifu = false;
-          for (int r = 0; r < kN; ++r)
-            if (board[sq_of(r, col_of(to))] == make_piece(PAWN, us)) nifu = true;
-          if (nifu) continue;
+    if (target_mask) {
+      for (Bitboard pcs = own & ~bb[us][KING]; pcs;) {
+        const int from = pop_lsb(pcs);
+        const PieceType t = static_cast<PieceType>(type_of(board[from]));
+        Bitboard dst = T.step_to[us][t][from];
+        const uint32_t slides = slide_mask(t);
+        if (slides) dst |= slide_attacks(T, from, occ, slides);
+        dst &= ~own & target_mask;
+        if (pinned >> from & 1) dst &= T.line[ksq][from];
+        if (kAny) { if (dst) return true; continue; }    // (a pawn reaching the last rank still has its promotion)
+        const bool from_zone = rank_of(from) == far;
+        while (dst) {
+          const int to = pop_lsb(dst);
+          emit(out, from, to, t, type_of(board[to]), from_zone || rank_of(to) == far, far);
         }
-        Move m;
-        m.from = -1; m.to = static_cast<int8_t>(to); m.piece = static_cast<int8_t>(t);
-        out.push(m);
       }
+      // drops: onto empty squares (only interpositions when in check)
+      const Bitboard empties = ~occ & kAllSquares & target_mask;
+      if (empties)
+        for (int k = 0; k < kHandTypes; ++k) {
+          if (!hand[us][k]) continue;
+          const PieceType t = kHandPiece[k];
+          Bitboard dst = empties;
+          if (t == PAWN) {
+            dst &= ~T.rank_mask[far];                                                       // not onto the last rank
+            for (Bitboard p = bb[us][PAWN]; p;) dst &= ~T.file_mask[col_of(pop_lsb(p))];    // nifu
+          }
+          while (dst) {
+            const int to = pop_lsb(dst);
+            Move m;
+            m.from = -1; m.to = static_cast<int8_t>(to); m.piece = static_cast<int8_t>(t);
+            if (t == PAWN && king_sq[them] >= 0 && (T.step_to[us][PAWN][to] >> king_sq[them] & 1)) {
+              apply(m);                                                    // pawn-drop check: illegal if it is mate
+              const bool mate = !has_legal_move();
+              revert(m);
+              if (mate) continue;
+            }
+            if (kAny) return true;
+            out->push(m);
+          }
+        }
     }
+    return kAny ? false : out->n > 0;
   }
 
   bool mate_attack(int depth, Move* best) {
@@ -518,10 +635,10 @@ class Position {
   }
   // true iff the side to move (in check) is mated within `depth` further plies whatever it plays
   bool mate_defend(int depth) {
+    if (depth <= 1) return !has_legal_move();
     MoveList moves;
     generate_moves(moves);
     if (moves.empty()) return true;
-    if (depth <= 1) return false;
     for (const Move& m : moves) {
       apply(m);
       const bool still = mate_attack(depth - 1, nullptr);
@@ -543,32 +660,38 @@ class Position {
 // plane, erweitern_55_b200/packing.py) is exact.
 constexpr int kInputPlanes = 266, kHistory = 8, kPlanesPerStep = 33;
 
+inline Bitboard rotate180(Bitboard b) {   // square s -> 24 - s
+  b = ((b >> 1) & 0x55555555u) | ((b & 0x55555555u) << 1);
+  b = ((b >> 2) & 0x33333333u) | ((b & 0x33333333u) << 2);
+  b = ((b >> 4) & 0x0F0F0F0Fu) | ((b & 0x0F0F0F0Fu) << 4);
+  return __builtin_bswap32(b) >> 7;
+}
+
 inline void encode_packed(const Position& pos, uint32_t* bits, float* scale) {
-  for (int c = 0; c < kInputPlanes; ++c) { bits[c] = 0u; scale[c] = 1.f; }
+  memset(bits, 0, kInputPlanes * sizeof(uint32_t));
+  for (int c = 0; c < kInputPlanes; ++c) scale[c] = 1.f;
   const int me = pos.side;
-  const uint32_t all = (1u << kSquares) - 1u;
   const int last = static_cast<int>(pos.hist.size()) - 1;
   for (int t = 0; t < kHistory; ++t) {
     const int idx = last - t;
     if (idx < 0) break;
     const Snapshot& sn = pos.hist[idx].snap;
-    const int base = t * kPlanesPerStep;
-    for (int s = 0; s < kSquares; ++s) {
-      const int8_t p = sn.board[s];
-      if (!p) continue;
-      const int sq = me == BLACK ? s : kSquares - 1 - s;
-      const int type = Position::type_of(p), color = Position::color_of(p);
-      bits[base + (color == me ? 0 : 10) + (type - 1)] |= 1u << sq;
+    uint32_t* b = bits + t * kPlanesPerStep;
+    float* sc = scale + t * kPlanesPerStep;
+    if (me == BLACK) {
+      for (int k = 0; k < 10; ++k) { b[k] = sn.pieces[BLACK][k]; b[10 + k] = sn.pieces[WHITE][k]; }
+    } else {
+      for (int k = 0; k < 10; ++k) { b[k] = rotate180(sn.pieces[WHITE][k]); b[10 + k] = rotate180(sn.pieces[BLACK][k]); }
     }
     const int rc = sn.rep_count >= 3 ? 3 : sn.rep_count;
-    if (rc >= 1) bits[base + 20 + rc - 1] = all;
+    if (rc >= 1) b[20 + rc - 1] = kAllSquares;
     for (int k = 0; k < kHandTypes; ++k) {
-      if (sn.hand[me][k]) { bits[base + 23 + k] = all; scale[base + 23 + k] = sn.hand[me][k] / 2.f; }
-      if (sn.hand[me ^ 1][k]) { bits[base + 28 + k] = all; scale[base + 28 + k] = sn.hand[me ^ 1][k] / 2.f; }
+      if (sn.hand[me][k]) { b[23 + k] = kAllSquares; sc[23 + k] = sn.hand[me][k] / 2.f; }
+      if (sn.hand[me ^ 1][k]) { b[28 + k] = kAllSquares; sc[28 + k] = sn.hand[me ^ 1][k] / 2.f; }
     }
   }
-  if (me == WHITE) bits[264] = all;
-  if (pos.ply > 0) { bits[265] = all; scale[265] = static_cast<float>(pos.ply > 512 ? 512 : pos.ply) / 512.f; }
+  if (me == WHITE) bits[264] = kAllSquares;
+  if (pos.ply > 0) { bits[265] = kAllSquares; scale[265] = static_cast<float>(pos.ply > 512 ? 512 : pos.ply) / 512.f; }
 }
 
 // ---- policy index (restated): 69 move planes x 25 squares, side to move's perspective --------------

@@ -230,6 +230,28 @@ class Network:
         self._check(fn(self._ctx, b.ctypes.data, sc.ctypes.data, n, policy.ctypes.data, value.ctypes.data))
         return policy, value
 
+    def predict_packed_moves(self, bits, scale, move_offset, move_index):
+        """Compact legal-move tail: ``move_index[move_offset[i]:move_offset[i+1]]`` are the policy indices of position
+        ``i``'s legal moves; returns ``(priors, value)`` with ``priors`` the flat float32 array of the per-position
+        softmax over exactly those logits (what ``minishogilib.MCTS.evaluate`` derives from a policy row,
+        mcts.py:60,105-106) -- a few dozen floats per position cross PCIe instead of 1725."""
+        b = np.ascontiguousarray(np.asarray(bits, dtype=np.uint32))
+        sc = np.ascontiguousarray(np.asarray(scale, dtype=np.float32))
+        off = np.ascontiguousarray(np.asarray(move_offset, dtype=np.int32))
+        idx = np.ascontiguousarray(np.asarray(move_index, dtype=np.uint16))
+        if b.ndim != 2 or b.shape[1] != self._in_planes or sc.shape != b.shape or b.shape[0] == 0:
+            raise ValueError(f"expected bits and scale of shape [N,{self._in_planes}]")
+        n = b.shape[0]
+        if off.shape != (n + 1,) or off[0] != 0 or int(off[-1]) != idx.shape[0]:
+            raise ValueError("move_offset must have N+1 entries from 0 to len(move_index)")
+        priors = np.empty(idx.shape[0], dtype=np.float32)
+        value = np.empty((n, 1), dtype=np.float32)
+        fn = (self._lib.e55_service_predict_packed_moves if (self._service_cap and n <= self._service_cap)
+              else self._lib.e55_predict_packed_moves)
+        self._check(fn(self._ctx, b.ctypes.data, sc.ctypes.data, n, off.ctypes.data, idx.ctypes.data,
+                       priors.ctypes.data, value.ctypes.data))
+        return priors, value
+
     def predict_masked(self, images, legal_mask):
         """Fused policy tail: softmax over legal moves (what minishogilib.MCTS.evaluate does with the
         logits, mcts.py:60,105-106).  ``legal_mask`` uint8/bool ``[N,1725]``."""

@@ -83,6 +83,14 @@ int e55_predict_packed(e55_ctx* ctx, const uint32_t* bits, const float* scale, i
 int e55_predict_packed_device(e55_ctx* ctx, const uint32_t* d_bits, const float* d_scale, int n, float* d_policy,
                               float* d_value);
 
+/* Compact legal-move policy tail (the north star's fused legal-move-masked softmax, in the form a search wants it):
+ * for position i the caller lists the policy indices of its legal moves in move_index[move_offset[i] ..
+ * move_offset[i+1]) (move_offset int32 [n+1], starting at 0); priors[j] receives softmax over exactly those logits
+ * -- what minishogilib.MCTS.evaluate computes from a policy row (mcts.py:60,105-106) -- so only a few dozen floats
+ * per position cross PCIe instead of 1725.  value float32 [n] as in e55_predict. */
+int e55_predict_packed_moves(e55_ctx* ctx, const uint32_t* bits, const float* scale, int n, const int32_t* move_offset,
+                             const uint16_t* move_index, float* priors, float* value);
+
 /* Fused policy tail for the caller-side post-processing the reference leaves to
  * minishogilib.MCTS.evaluate (mcts.py:59-60,103-106): probs = softmax over entries with
  * legal_mask != 0 (others 0), legal_mask uint8 [n,1725]; value as in e55_predict. */
@@ -101,6 +109,8 @@ int e55_service_stop(e55_ctx* ctx);
 int e55_service_predict(e55_ctx* ctx, const float* planes, int n, float* policy, float* value);
 int e55_service_predict_packed(e55_ctx* ctx, const uint32_t* bits, const float* scale, int n, float* policy,
                                float* value);
+int e55_service_predict_packed_moves(e55_ctx* ctx, const uint32_t* bits, const float* scale, int n,
+                                     const int32_t* move_offset, const uint16_t* move_index, float* priors, float* value);
 int e55_service_stats(e55_ctx* ctx, int64_t* batches_out, int64_t* positions_out);
 
 /* Synthetic self-play load on the running service, tree operations excluded: `workers` host threads each play

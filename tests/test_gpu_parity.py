@@ -291,6 +291,65 @@ def test_native_selfplay_and_python_search_loop(weights_default):
     net.close()
 
 
+def test_legal_move_priors_match_the_host_softmax(weights_perturbed):
+    """e55_predict_packed_moves: softmax over the legal moves' logits on the GPU == the same softmax of the logits
+    predict_packed returns, directly and through the evaluation service; ragged and empty move lists included."""
+    from erweitern_55_b200.minishogi import Position, encode_packed_batch
+    from erweitern_55_b200.network import Network
+    net = Network(precision="bf16", weights=weights_perturbed)
+    rng = np.random.default_rng(9)
+    positions, p = [], Position()
+    while len(positions) < 40:
+        moves = p.generate_moves()
+        if not moves or p.get_ply() > 30:
+            p = Position()
+            continue
+        p.do_move(moves[int(rng.integers(len(moves)))])
+        positions.append(p.copy(True))
+    lists = [[q.policy_index(m) for m in q.generate_moves()] for q in positions]
+    lists[3] = []                                                       # a position without moves gets no priors
+    lists[7] = list(range(0, 1725, 7))                                  # a long list (247 entries)
+    off = np.concatenate([[0], np.cumsum([len(l) for l in lists])]).astype(np.int32)
+    idx = np.array([i for l in lists for i in l], dtype=np.uint16)
+    bits, scale = encode_packed_batch(positions)
+    logits, value = net.predict_packed(bits, scale)
+
+    def check(priors, v):
+        assert np.array_equal(v, value)
+        for b, l in enumerate(lists):
+            got = priors[off[b]:off[b + 1]]
+            if not l:
+                continue
+            e = np.exp(logits[b, l].astype(np.float64) - logits[b, l].max())
+            assert np.abs(got - e / e.sum()).max() < 2e-6 and abs(got.sum() - 1) < 1e-5
+
+    check(*net.predict_packed_moves(bits, scale, off, idx))
+    net.set_precision("fp32")
+    lf, vf = net.predict_packed(bits, scale)
+    pf, _ = net.predict_packed_moves(bits, scale, off, idx)
+    e = np.exp(lf[0, lists[0]] - lf[0, lists[0]].max())
+    assert np.abs(pf[:len(lists[0])] - e / e.sum()).max() < 2e-6
+    net.set_precision("bf16")
+    net.start_service(max_batch=64, max_wait_us=100)
+    out, errs = {}, []
+
+    def worker(lo, hi):
+        try:
+            o = off[lo:hi + 1] - off[lo]
+            out[lo] = net.predict_packed_moves(bits[lo:hi], scale[lo:hi], o, idx[off[lo]:off[hi]])
+        except Exception as ex:  # pragma: no cover
+            errs.append(ex)
+    ts = [threading.Thread(target=worker, args=(lo, min(lo + 6, 40))) for lo in range(0, 40, 6)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    net.stop_service()
+    assert not errs
+    check(np.concatenate([out[lo][0] for lo in sorted(out)]), np.concatenate([out[lo][1] for lo in sorted(out)]))
+    with pytest.raises(Exception):
+        net.predict_packed_moves(bits[:1], scale[:1], np.array([0, 1], np.int32), np.array([1725], np.uint16))
+    net.close()
+
+
 class _ReferenceStyleNetwork:
     """Only the reference's three calls (get_input / get_inputs / predict), so mcts.MCTS.run takes its leaf-by-leaf
     Python path (mcts.py:91-110) instead of the native batch step."""
@@ -318,7 +377,13 @@ def test_native_search_equals_the_reference_style_python_loop(weights_perturbed)
             dumps.append((search.dump(root), [m.sfen() for m in search.mcts.info(root)[0]]))
             p.do_move(search.best_move(root))
         results.append(dumps)
-    assert results[0] == results[1]
+    # the native step takes its priors from the GPU's legal-move softmax (__expf), the Python loop from the host's
+    # exp: the same search up to last-bit prior differences, which can only flip near-ties
+    for (dn, pvn), (dp, pvp) in zip(*results):
+        assert dn[0] == dp[0] and abs(dn[1] - dp[1]) < 0.02
+        vn, vp = dict(dn[2]), dict(dp[2])
+        tv = sum(abs(vn.get(m, 0) - vp.get(m, 0)) for m in set(vn) | set(vp)) / (2 * dn[0])
+        assert tv < 0.1, tv
     assert results[0][0][0][0] == 256 and results[0][1][0][0] >= 256    # reused subtree adds to the next search
     pp, vp = net.predict_positions([p])
     pf, vf = net.predict(net.get_inputs([p]))
