@@ -179,7 +179,8 @@ def main():
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--selfplay-workers", type=int, default=128, help="0 = skip the synthetic self-play load")
-    ap.add_argument("--selfplay-moves", type=int, default=8, help="moves per worker thread in the self-play runs")
+    ap.add_argument("--selfplay-moves", type=int, default=8, help="moves per worker thread in the synthetic self-play run")
+    ap.add_argument("--selfplay-total-moves", type=int, default=16000, help="plies played per GPU in the real self-play run")
     ap.add_argument("--blocks", type=int, default=7, help="residual blocks (20 with --filters 256 = BASELINE configs[4])")
     ap.add_argument("--filters", type=int, default=128, choices=[128, 256])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -339,18 +340,26 @@ def main():
         mv, ev, mb = net.bench_selfplay(workers=args.selfplay_workers, moves=args.selfplay_moves, simulations=800, leaf_batch=16)
         barrier()
         # real self-play: native minishogi engine + MCTS (800 simulations, leaf batch 16, 7-ply mate search)
-        real = net.selfplay(threads=args.selfplay_workers, total_moves=args.selfplay_workers * args.selfplay_moves,
-                            simulations=800, leaf_batch=16, mate_depth=7, seed=1 + rank)
+        # one worker thread per host core of this rank's share, minus two for the service's dispatcher / completer
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+        sp_threads = max(2, (os.cpu_count() or 4) // max(1, local_world) - 2)
+        net.selfplay(threads=sp_threads, total_moves=512, simulations=160, leaf_batch=16, mate_depth=7, seed=99 + rank)   # warm-up
+        barrier()
+        real = net.selfplay(threads=sp_threads, total_moves=args.selfplay_total_moves, simulations=800, leaf_batch=16,
+                            mate_depth=7, seed=1 + rank, games_per_thread=16)
         barrier()
         net.stop_service()
         real_mv, _ = sharding.aggregate(real["moves_per_s"], 1.0, device=dev)
         real_ev, _ = sharding.aggregate(real["evals_per_s"], 1.0, device=dev)
         selfplay_real = {"moves_per_s": real_mv, "evals_per_s": real_ev, "games_rank0": real["games"],
-                         "mean_gpu_batch_rank0": real["mean_gpu_batch"], "threads_per_gpu": args.selfplay_workers,
+                         "mean_gpu_batch_rank0": real["mean_gpu_batch"], "threads_per_gpu": sp_threads, "games_in_flight_per_gpu": sp_threads * 16,
+                         "mean_game_plies_rank0": real["mean_game_plies"],
                          "simulations_per_move": 800, "leaf_batch": 16, "mate_search_plies": 7,
                          "note": "native C++ minishogi engine + batched PUCT search (csrc/minishogi.hpp, mcts.hpp) playing whole "
-                                 "games from the start position with random-init weights through the evaluation service; "
-                                 "rules pinned by the reference's 17 KATs, input encoding / policy index are this repo's own"}
+                                 "games from the start position with random-init weights (client.py's settings: tree reuse, "
+                                 "Dirichlet noise) on the asynchronous evaluation service with GPU-side legal-move softmax "
+                                 "(e55_service_submit_packed_moves); rules pinned by the reference's 17 KATs, input encoding / "
+                                 "policy index are this repo's own"}
         tot_ev, _ = sharding.aggregate(ev, 1.0, device=dev)
         tot_mv, _ = sharding.aggregate(mv, 1.0, device=dev)
         selfplay = {"moves_per_s": tot_mv, "evals_per_s": tot_ev, "mean_gpu_batch_rank0": mb,

@@ -7,6 +7,7 @@ import os
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libe55.so")
 
 E55_OK = 0
+E55_PENDING = 1
 E55_ERR_INVALID, E55_ERR_CUDA, E55_ERR_NO_WEIGHTS, E55_ERR_UNSUPPORTED, E55_ERR_NO_DEVICE = -1, -2, -3, -4, -5
 PRECISION_FP32, PRECISION_BF16_TC = 0, 1
 
@@ -28,6 +29,8 @@ SIGNATURES = {
     "e55_predict_packed_device": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "e55_predict_packed_moves": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "e55_service_predict_packed_moves": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "e55_service_submit_packed_moves": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "e55_service_fetch": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "e55_predict_masked": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "e55_predict_masked_device": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "e55_service_start": (C.c_int, [_ctx, C.c_int, C.c_int]),
@@ -58,7 +61,7 @@ GAME_SINK = C.CFUNCTYPE(None, C.c_void_p, C.c_char_p)
 
 
 class SelfplayConfig(C.Structure):
-    _fields_ = [("threads", C.c_int), ("total_moves", C.c_long), ("simulations", C.c_int), ("leaf_batch", C.c_int),
+    _fields_ = [("threads", C.c_int), ("games_per_thread", C.c_int), ("total_moves", C.c_long), ("simulations", C.c_int), ("leaf_batch", C.c_int),
                 ("mate_depth", C.c_int), ("reuse_tree", C.c_int), ("use_dirichlet", C.c_int),
                 ("sampling_moves", C.c_int), ("max_moves", C.c_int), ("seed", C.c_uint64),
                 ("sink", GAME_SINK), ("sink_user", C.c_void_p)]

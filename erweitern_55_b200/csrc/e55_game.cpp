@@ -2,8 +2,12 @@
 // Host-only translation unit (g++): it reaches the network through the public C ABI of include/e55.h only.
 #include "../../include/e55.h"
 
+#include <sys/resource.h>
+
 #include <atomic>
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -59,6 +63,9 @@ bool is_default_net(e55_ctx* ctx) {
 }
 
 // ---- one search = what mcts.MCTS.run does for one move (mcts.py:32-138) ---------------------------------------
+// Each step is split into a "prepare" half that leaves a network request in the scratch buffers and a "finish" half
+// that consumes the answer, so that a caller can either run them back to back around a blocking predict
+// (e55_mcts_search_*) or keep many games in flight from one thread (the self-play worker below).
 struct SearchScratch {
   std::vector<uint32_t>* bits;
   std::vector<float>*scale, *priors, *value;
@@ -68,6 +75,9 @@ struct SearchScratch {
   std::vector<mshogi::Position>* leaf_pos;
   std::vector<mshogi::MoveList>* leaf_moves;
   std::vector<int>* eval_slot;
+  explicit SearchScratch(e55_mcts& m)
+      : bits(&m.bits), scale(&m.scale), priors(&m.priors), value(&m.value), move_off(&m.move_off), move_idx(&m.move_idx),
+        leaf(&m.leaf), leaf_pos(&m.leaf_pos), leaf_moves(&m.leaf_moves), eval_slot(&m.eval_slot) {}
   void size_for(int leaf_batch) {
     if (static_cast<int>(leaf->size()) >= leaf_batch) return;
     bits->resize(static_cast<size_t>(leaf_batch) * kInputPlanes);
@@ -83,51 +93,42 @@ struct SearchScratch {
   }
 };
 
-struct Evaluator {
-  e55_ctx* ctx;
-  bool use_service;
-  long evals = 0;
-  // priors[j] = softmax over the logits at move_idx[move_off[i] .. move_off[i+1]) of position i, computed on the GPU
-  int operator()(const uint32_t* bits, const float* scale, int n, const int32_t* move_off, const uint16_t* move_idx,
-                 float* priors, float* value) {
-    evals += n;
-    return use_service ? e55_service_predict_packed_moves(ctx, bits, scale, n, move_off, move_idx, priors, value)
-                       : e55_predict_packed_moves(ctx, bits, scale, n, move_off, move_idx, priors, value);
-  }
-};
+// priors[j] = softmax over the logits at move_idx[move_off[i] .. move_off[i+1]) of position i, computed on the GPU
+int evaluate_request(e55_ctx* ctx, bool use_service, SearchScratch& s, int n) {
+  return use_service
+             ? e55_service_predict_packed_moves(ctx, s.bits->data(), s.scale->data(), n, s.move_off->data(), s.move_idx->data(),
+                                                s.priors->data(), s.value->data())
+             : e55_predict_packed_moves(ctx, s.bits->data(), s.scale->data(), n, s.move_off->data(), s.move_idx->data(),
+                                        s.priors->data(), s.value->data());
+}
 
-// Step 1 + 2 of MCTS.run: set the root, evaluate it when it is not expanded yet, add noise (mcts.py:49-64).
-// Returns E55_OK, or 1 when the root is a terminal position (nothing to search).
-int search_root(mshogi::Mcts& tree, SearchScratch& s, Evaluator& nn, const mshogi::Position& root_pos, bool reuse_tree,
-                bool use_dirichlet) {
+enum RootStatus { kRootNeedsEval = 0, kRootTerminal = 1, kRootReady = 2 };
+
+// Step 1 of MCTS.run: set the root (mcts.py:49-50).  kRootNeedsEval: a one-position request is in the scratch.
+RootStatus prepare_root(mshogi::Mcts& tree, SearchScratch& s, const mshogi::Position& root_pos, bool reuse_tree) {
   using namespace mshogi;
   s.size_for(1);
   const int32_t root = tree.set_root(root_pos, reuse_tree);
   const Node& nd = tree.nodes[root];
-  if (!nd.expanded && !nd.terminal) {
-    Position scratch = root_pos;
-    MoveList moves;
-    float tv;
-    if (Mcts::terminal_value(scratch, moves, tv)) {
-      tree.set_terminal(root, tv);
-    } else {
-      encode_packed(root_pos, s.bits->data(), s.scale->data());
-      (*s.move_off)[0] = 0; (*s.move_off)[1] = moves.size();
-      for (int i = 0; i < moves.size(); ++i) (*s.move_idx)[i] = static_cast<uint16_t>(policy_index(moves.m[i], root_pos.side));
-      const int rc = nn(s.bits->data(), s.scale->data(), 1, s.move_off->data(), s.move_idx->data(), s.priors->data(), s.value->data());
-      if (rc != E55_OK) return rc;
-      tree.expand_from_priors(root, moves, s.priors->data(), ((*s.value)[0] + 1.f) * 0.5f);
-    }
-  }
-  if (tree.nodes[root].terminal) return 1;
-  if (use_dirichlet) tree.add_noise(root);
-  return E55_OK;
+  if (nd.terminal) return kRootTerminal;
+  if (nd.expanded) return kRootReady;
+  Position scratch = root_pos;
+  MoveList& moves = (*s.leaf_moves)[0];
+  float tv;
+  if (Mcts::terminal_value(scratch, moves, tv)) { tree.set_terminal(root, tv); return kRootTerminal; }
+  encode_packed(root_pos, s.bits->data(), s.scale->data());
+  (*s.move_off)[0] = 0; (*s.move_off)[1] = moves.size();
+  for (int i = 0; i < moves.size(); ++i) (*s.move_idx)[i] = static_cast<uint16_t>(policy_index(moves.m[i], root_pos.side));
+  return kRootNeedsEval;
+}
+// Step 2 (mcts.py:55-60): expand the root from the answer.
+void finish_root(mshogi::Mcts& tree, SearchScratch& s) {
+  tree.expand_from_priors(0, (*s.leaf_moves)[0], s.priors->data(), ((*s.value)[0] + 1.f) * 0.5f);
 }
 
-// `n_batches` iterations of MCTS.run's main loop (mcts.py:91-110): select leaf_batch leaves with virtual loss,
-// evaluate the new ones in ONE network call, expand, back up.
-int search_batches(mshogi::Mcts& tree, SearchScratch& s, Evaluator& nn, const mshogi::Position& root_pos, int n_batches,
-                   int leaf_batch, bool forced_playouts) {
+// First half of one iteration of MCTS.run's main loop (mcts.py:91-102): select leaf_batch leaves with virtual loss
+// and encode the new ones.  Returns the number of positions in the request (0: nothing to evaluate).
+int prepare_batch(mshogi::Mcts& tree, SearchScratch& s, const mshogi::Position& root_pos, int leaf_batch, bool forced_playouts) {
   using namespace mshogi;
   s.size_for(leaf_batch);
   std::vector<int32_t>& leaf = *s.leaf;
@@ -136,114 +137,248 @@ int search_batches(mshogi::Mcts& tree, SearchScratch& s, Evaluator& nn, const ms
   std::vector<int>& eval_slot = *s.eval_slot;
   int32_t* move_off = s.move_off->data();
   uint16_t* move_idx = s.move_idx->data();
-  for (int it = 0; it < n_batches; ++it) {
-    int n_eval = 0;
-    move_off[0] = 0;
-    for (int b = 0; b < leaf_batch; ++b) {
-      leaf_pos[b] = root_pos;
-      leaf[b] = tree.select_leaf(0, leaf_pos[b], forced_playouts);
-      eval_slot[b] = -1;
-      if (!tree.claim(leaf[b])) continue;                       // expanded, terminal, or a duplicate in this batch
-      float v;
-      if (Mcts::terminal_value(leaf_pos[b], leaf_moves[b], v)) { tree.set_terminal(leaf[b], v); continue; }
-      eval_slot[b] = n_eval;
-      encode_packed(leaf_pos[b], s.bits->data() + static_cast<size_t>(n_eval) * kInputPlanes,
-                    s.scale->data() + static_cast<size_t>(n_eval) * kInputPlanes);
-      const MoveList& lm = leaf_moves[b];                       // the policy entries of the legal moves go along
-      uint16_t* idx = move_idx + move_off[n_eval];
-      for (int i = 0; i < lm.size(); ++i) idx[i] = static_cast<uint16_t>(policy_index(lm.m[i], leaf_pos[b].side));
-      move_off[n_eval + 1] = move_off[n_eval] + lm.size();
-      ++n_eval;
-    }
-    if (n_eval > 0) {
-      const int rc = nn(s.bits->data(), s.scale->data(), n_eval, move_off, move_idx, s.priors->data(), s.value->data());
-      if (rc != E55_OK) return rc;
-    }
-    for (int b = 0; b < leaf_batch; ++b)
-      if (eval_slot[b] >= 0)
-        tree.expand_from_priors(leaf[b], leaf_moves[b], s.priors->data() + move_off[eval_slot[b]],
-                                ((*s.value)[eval_slot[b]] + 1.f) * 0.5f);
-    for (int b = 0; b < leaf_batch; ++b) tree.backpropagate(leaf[b]);
+  int n_eval = 0;
+  move_off[0] = 0;
+  for (int b = 0; b < leaf_batch; ++b) {
+    leaf_pos[b] = root_pos;
+    leaf[b] = tree.select_leaf(0, leaf_pos[b], forced_playouts);
+    eval_slot[b] = -1;
+    if (!tree.claim(leaf[b])) continue;                       // expanded, terminal, or a duplicate in this batch
+    float v;
+    if (Mcts::terminal_value(leaf_pos[b], leaf_moves[b], v)) { tree.set_terminal(leaf[b], v); continue; }
+    eval_slot[b] = n_eval;
+    encode_packed(leaf_pos[b], s.bits->data() + static_cast<size_t>(n_eval) * kInputPlanes,
+                  s.scale->data() + static_cast<size_t>(n_eval) * kInputPlanes);
+    const MoveList& lm = leaf_moves[b];                       // the policy entries of the legal moves go along
+    uint16_t* idx = move_idx + move_off[n_eval];
+    for (int i = 0; i < lm.size(); ++i) idx[i] = static_cast<uint16_t>(policy_index(lm.m[i], leaf_pos[b].side));
+    move_off[n_eval + 1] = move_off[n_eval] + lm.size();
+    ++n_eval;
   }
-  return E55_OK;
+  return n_eval;
+}
+// Second half (mcts.py:103-110): expand the evaluated leaves, back every selection up.
+void finish_batch(mshogi::Mcts& tree, SearchScratch& s, int leaf_batch) {
+  const int32_t* move_off = s.move_off->data();
+  for (int b = 0; b < leaf_batch; ++b) {
+    const int slot = (*s.eval_slot)[b];
+    if (slot >= 0)
+      tree.expand_from_priors((*s.leaf)[b], (*s.leaf_moves)[b], s.priors->data() + move_off[slot], ((*s.value)[slot] + 1.f) * 0.5f);
+  }
+  for (int b = 0; b < leaf_batch; ++b) tree.backpropagate((*s.leaf)[b]);
 }
 
 // ---- self-play ---------------------------------------------------------------------------------------------------
-// One game the way selfplay.run plays it (selfplay.py:10-113) under client.py's search settings (client.py:27-35):
-// repetition / no-move termination, optional mate search, otherwise `simulations` simulations in batches of
-// `leaf_batch` through the evaluation service; the first `sampling_moves` plies sample from the visit counts.
+// Games are played the way selfplay.run plays them (selfplay.py:10-113) under client.py's search settings
+// (client.py:27-35): repetition / no-move termination, optional mate search, otherwise `simulations` simulations in
+// batches of `leaf_batch`; the first `sampling_moves` plies sample from the visit counts.  The games are small state
+// machines over the asynchronous evaluation service, kept in one pool that all host threads work through: a thread
+// takes whichever game can advance (its answer has arrived, or it has CPU work to do), so a core never sleeps on a
+// network call while any game has work, and only sleeps -- on the oldest outstanding request -- when none has.
 struct SelfplayShared {
   e55_ctx* ctx;
   e55_selfplay_config cfg;
+  std::vector<struct SelfplayGame> games;      // the pool (threads x games_per_thread)
+  std::atomic<uint64_t> submit_seq{0};
   std::atomic<long> moves_left{0}, moves_done{0}, evals_done{0}, games_done{0}, plies_in_finished_games{0};
   std::atomic<int> failures{0};
   std::mutex sink_mu;
 };
 
+struct SelfplayGame {
+  enum State { kNewMove, kSubmitRoot, kWaitRoot, kSelect, kSubmitBatch, kWaitBatch, kStopped };
+  std::atomic<State> state{kNewMove};   // written only by the thread holding `busy`; others read it to skip the game
+  mshogi::Position pos;
+  e55_mcts m{0.2};
+  e55_ticket ticket{};
+  uint64_t seq = 0;                  // order of the outstanding request among all games (batches complete in order)
+  std::atomic_flag busy = ATOMIC_FLAG_INIT;   // a thread is working on this game
+  int batches_left = 0, n_eval = 0, plies = 0, winner = 2;
+  std::string record;
+  std::vector<std::pair<mshogi::Move, int>> visits;
+  SelfplayGame() = default;
+  SelfplayGame(SelfplayGame&&) noexcept {}   // only to let std::vector size the pool; games never move afterwards
+};
+
 struct SelfplayWorker {
   SelfplayShared* sh = nullptr;
-  uint64_t seed = 0;
-  e55_mcts m{0.2};
+  int index = 0;
+  long evals = 0;
 
-  void run() {
+  void start_game(SelfplayGame& g) {
+    g.pos.set_start_position();
+    g.m.tree.clear();
+    g.record.clear();
+    g.winner = 2; g.plies = 0;
+    g.state = SelfplayGame::kNewMove;
+  }
+  void end_game(SelfplayGame& g) {
+    sh->games_done.fetch_add(1);
+    sh->plies_in_finished_games.fetch_add(g.pos.ply);
+    if (sh->cfg.sink) {
+      g.record = "winner " + std::to_string(g.winner) + " ply " + std::to_string(g.pos.ply) + "\n" + g.record;
+      std::lock_guard<std::mutex> lk(sh->sink_mu);
+      sh->cfg.sink(sh->cfg.sink_user, g.record.c_str());
+    }
+    if (sh->moves_left.load() > 0 && sh->failures.load() == 0) start_game(g);
+    else g.state = SelfplayGame::kStopped;
+  }
+  void play(SelfplayGame& g, const mshogi::Move& mv) {
+    g.pos.do_move(mv);
+    ++g.plies;
+    sh->moves_done.fetch_add(1);
+    g.state = SelfplayGame::kNewMove;
+  }
+  int submit(SelfplayGame& g, SearchScratch& s, int n, bool may_block) {
+    const int rc = e55_service_submit_packed_moves(sh->ctx, s.bits->data(), s.scale->data(), n, s.move_off->data(),
+                                                   s.move_idx->data(), may_block ? 1 : 0, &g.ticket);
+    if (rc == E55_OK) { evals += n; g.seq = sh->submit_seq.fetch_add(1, std::memory_order_relaxed); }
+    else if (rc != E55_PENDING) { sh->failures.fetch_add(1); g.state = SelfplayGame::kStopped; }
+    return rc;
+  }
+
+  // Advance one game as far as it goes without waiting.  Returns true if anything happened.
+  bool step(SelfplayGame& g, bool block) {
     using namespace mshogi;
     const e55_selfplay_config& cfg = sh->cfg;
-    SearchScratch s{&m.bits, &m.scale, &m.priors, &m.value, &m.move_off, &m.move_idx, &m.leaf, &m.leaf_pos, &m.leaf_moves, &m.eval_slot};
-    Evaluator nn{sh->ctx, true};
-    m.tree.rng.seed(seed);
-    const int n_batches = (cfg.simulations + cfg.leaf_batch - 1) / cfg.leaf_batch;
-    std::string record;
-    std::vector<std::pair<Move, int>> visits;
-    while (sh->moves_left.load() > 0 && sh->failures.load() == 0) {
-      Position pos;
-      pos.set_start_position();
-      m.tree.clear();
-      int winner = 2;
-      record.clear();
-      for (int mv = 0; mv < cfg.max_moves; ++mv) {
-        bool rep, my_check, op_check;                                            // selfplay.py:17-26
-        pos.is_repetition(rep, my_check, op_check);
-        if (my_check) { winner = 1 - pos.side; break; }
-        if (op_check) { winner = pos.side; break; }
-        if (rep) { winner = 1; break; }
-        MoveList legal;
-        pos.generate_moves(legal);
-        if (legal.empty()) { winner = 1 - pos.side; break; }                    // selfplay.py:28-31
-        if (sh->moves_left.fetch_sub(1) <= 0) { sh->evals_done.fetch_add(nn.evals); return; }   // move budget exhausted mid-game
-        Move next;
-        bool mate = cfg.mate_depth > 0 && pos.solve_checkmate_dfs(cfg.mate_depth, next);   // selfplay.py:35-42
-        if (mate) {
-          m.tree.clear();
-          if (cfg.sink) record += next.sfen() + " 1 1.0 1 " + next.sfen() + " 1\n";     // selfplay.py:82-84
-        } else {
-          int rc = search_root(m.tree, s, nn, pos, cfg.reuse_tree != 0, cfg.use_dirichlet != 0);
-          if (rc == E55_OK) rc = search_batches(m.tree, s, nn, pos, n_batches, cfg.leaf_batch, false);
-          if (rc != E55_OK) { sh->failures.fetch_add(1); sh->evals_done.fetch_add(nn.evals); return; }
-          const int chosen = pos.ply < cfg.sampling_moves ? m.tree.sample_edge(0, 1.f) : m.tree.best_edge(0);
-          next = m.tree.edges_of(m.tree.nodes[0])[chosen].move;
-          if (cfg.sink) {                                                       // search.dump(root), selfplay.py:89
-            int sum_n;
-            float q;
-            m.tree.dump(0, false, true, sum_n, q, visits);
-            record += next.sfen() + " " + std::to_string(sum_n) + " " + std::to_string(q) + " " + std::to_string(visits.size());
-            for (const auto& v : visits) record += " " + v.first.sfen() + " " + std::to_string(v.second);
-            record += "\n";
+    SearchScratch s(g.m);
+    bool progressed = false;
+    for (;;) {
+      switch (g.state.load(std::memory_order_relaxed)) {
+        case SelfplayGame::kStopped:
+          return progressed;
+        case SelfplayGame::kNewMove: {
+          progressed = true;
+          bool rep, my_check, op_check;                                          // selfplay.py:17-26
+          g.pos.is_repetition(rep, my_check, op_check);
+          if (my_check) { g.winner = 1 - g.pos.side; end_game(g); break; }
+          if (op_check) { g.winner = g.pos.side; end_game(g); break; }
+          if (rep) { g.winner = 1; end_game(g); break; }
+          if (!g.pos.has_legal_move()) { g.winner = 1 - g.pos.side; end_game(g); break; }   // selfplay.py:28-31
+          if (g.plies >= cfg.max_moves) { end_game(g); break; }
+          if (sh->failures.load() || sh->moves_left.fetch_sub(1) <= 0) { g.state = SelfplayGame::kStopped; break; }   // budget spent mid-game
+          Move mate_move;
+          if (cfg.mate_depth > 0 && g.pos.solve_checkmate_dfs(cfg.mate_depth, mate_move)) {  // selfplay.py:35-42
+            g.m.tree.clear();
+            if (cfg.sink) g.record += mate_move.sfen() + " 1 1.0 1 " + mate_move.sfen() + " 1\n";   // selfplay.py:82-84
+            play(g, mate_move);
+            break;
           }
+          g.batches_left = (cfg.simulations + cfg.leaf_batch - 1) / cfg.leaf_batch;
+          const RootStatus rs = prepare_root(g.m.tree, s, g.pos, cfg.reuse_tree != 0);
+          if (rs == kRootNeedsEval) { g.state = SelfplayGame::kSubmitRoot; break; }
+          if (cfg.use_dirichlet) g.m.tree.add_noise(0);
+          g.state = SelfplayGame::kSelect;
+          break;
         }
-        pos.do_move(next);
-        sh->moves_done.fetch_add(1);
+        case SelfplayGame::kSubmitRoot: {
+          const int rc = submit(g, s, 1, block);
+          if (rc == E55_PENDING) return progressed;
+          if (rc == E55_OK) { g.state = SelfplayGame::kWaitRoot; progressed = true; }
+          break;
+        }
+        case SelfplayGame::kWaitRoot: {
+          const int rc = e55_service_fetch(sh->ctx, &g.ticket, s.priors->data(), s.value->data(), block ? 1 : 0);
+          if (rc == E55_PENDING) return progressed;
+          if (rc != E55_OK) { sh->failures.fetch_add(1); g.state = SelfplayGame::kStopped; break; }
+          progressed = true;
+          finish_root(g.m.tree, s);
+          if (cfg.use_dirichlet) g.m.tree.add_noise(0);
+          g.state = SelfplayGame::kSelect;
+          break;
+        }
+        case SelfplayGame::kSelect: {
+          progressed = true;
+          if (g.batches_left == 0) {                                             // selfplay.py:63-68
+            const int chosen = g.pos.ply < cfg.sampling_moves ? g.m.tree.sample_edge(0, 1.f) : g.m.tree.best_edge(0);
+            const Move next = g.m.tree.edges_of(g.m.tree.nodes[0])[chosen].move;
+            if (cfg.sink) {                                                      // search.dump(root), selfplay.py:89
+              int sum_n;
+              float q;
+              g.m.tree.dump(0, false, true, sum_n, q, g.visits);
+              g.record += next.sfen() + " " + std::to_string(sum_n) + " " + std::to_string(q) + " " + std::to_string(g.visits.size());
+              for (const auto& v : g.visits) g.record += " " + v.first.sfen() + " " + std::to_string(v.second);
+              g.record += "\n";
+            }
+            play(g, next);
+            break;
+          }
+          --g.batches_left;
+          g.n_eval = prepare_batch(g.m.tree, s, g.pos, cfg.leaf_batch, false);
+          if (g.n_eval == 0) { finish_batch(g.m.tree, s, cfg.leaf_batch); break; }
+          g.state = SelfplayGame::kSubmitBatch;
+          break;
+        }
+        case SelfplayGame::kSubmitBatch: {
+          const int rc = submit(g, s, g.n_eval, block);
+          if (rc == E55_PENDING) return progressed;
+          if (rc == E55_OK) { g.state = SelfplayGame::kWaitBatch; progressed = true; }
+          break;
+        }
+        case SelfplayGame::kWaitBatch: {
+          const int rc = e55_service_fetch(sh->ctx, &g.ticket, s.priors->data(), s.value->data(), block ? 1 : 0);
+          if (rc == E55_PENDING) return progressed;
+          if (rc != E55_OK) { sh->failures.fetch_add(1); g.state = SelfplayGame::kStopped; break; }
+          progressed = true;
+          finish_batch(g.m.tree, s, cfg.leaf_batch);
+          g.state = SelfplayGame::kSelect;
+          break;
+        }
       }
-      sh->evals_done.fetch_add(nn.evals);
-      nn.evals = 0;
-      sh->games_done.fetch_add(1);
-      sh->plies_in_finished_games.fetch_add(pos.ply);
-      if (cfg.sink) {
-        record = "winner " + std::to_string(winner) + " ply " + std::to_string(pos.ply) + "\n" + record;
-        std::lock_guard<std::mutex> lk(sh->sink_mu);
-        cfg.sink(cfg.sink_user, record.c_str());
+      block = false;   // at most one blocking call per step
+      if (g.state == SelfplayGame::kWaitRoot || g.state == SelfplayGame::kWaitBatch) return progressed;   // let the others run
+    }
+  }
+
+  void run() {
+    std::vector<SelfplayGame>& games = sh->games;
+    const size_t n_games = games.size();
+    // Each thread has a home range of the pool (its games stay warm in its cache); only when none of those can
+    // advance does it look through everybody else's for one that can.
+    const size_t per = n_games / static_cast<size_t>(sh->cfg.threads);
+    const size_t start = per * static_cast<size_t>(index);
+    const size_t home_n = index + 1 == sh->cfg.threads ? n_games - start : per;
+    for (;;) {
+      bool any_alive = false, progressed = false;
+      for (size_t i = 0; i < n_games; ++i) {
+        if (i == home_n && progressed) break;                           // home games moved: stay home
+        SelfplayGame& g = games[(start + i) % n_games];
+        if (g.state == SelfplayGame::kStopped) continue;
+        any_alive = true;
+        if (g.busy.test_and_set(std::memory_order_acquire)) continue;   // another thread has it
+        const bool moved = step(g, false);
+        g.busy.clear(std::memory_order_release);
+        progressed |= moved;
+        if (moved && i >= home_n) break;                                // helped out once: back to the home range
+      }
+      if (!any_alive) break;
+      if (progressed) continue;
+      // Nothing could move: sleep on the oldest outstanding answer that no other thread is sleeping on (the service
+      // always completes it), or -- holding no ticket at all -- on room for a request that did not fit.
+      SelfplayGame* oldest = nullptr;
+      for (size_t i = 0; i < n_games; ++i) {
+        SelfplayGame& g = games[(start + i) % n_games];
+        if (g.state != SelfplayGame::kWaitRoot && g.state != SelfplayGame::kWaitBatch && g.state != SelfplayGame::kSubmitRoot &&
+            g.state != SelfplayGame::kSubmitBatch) continue;
+        if (g.busy.test_and_set(std::memory_order_acquire)) continue;
+        const bool waiting = g.state == SelfplayGame::kWaitRoot || g.state == SelfplayGame::kWaitBatch;
+        const bool better = !oldest || (waiting && (oldest->state == SelfplayGame::kSubmitRoot || oldest->state == SelfplayGame::kSubmitBatch ||
+                                                    g.seq < oldest->seq));
+        if (better && (waiting || !oldest)) {
+          if (oldest) oldest->busy.clear(std::memory_order_release);
+          oldest = &g;
+        } else {
+          g.busy.clear(std::memory_order_release);
+        }
+      }
+      if (oldest) {
+        step(*oldest, true);
+        oldest->busy.clear(std::memory_order_release);
+      } else {
+        std::this_thread::sleep_for(std::chrono::microseconds(30));   // every candidate is in another thread's hands
       }
     }
-    sh->evals_done.fetch_add(nn.evals);
+    sh->evals_done.fetch_add(evals);   // (a game only stops between moves, so no ticket is left unfetched)
   }
 };
 
@@ -443,9 +578,16 @@ int e55_mcts_visualize(const e55_mcts* m, int node, int node_num, char* buf, int
 
 int e55_mcts_search_root(e55_mcts* m, e55_ctx* ctx, const e55_pos* pos, int reuse_tree, int use_dirichlet, int use_service) {
   if (!m || !ctx || !pos || !is_default_net(ctx)) return E55_ERR_INVALID;
-  SearchScratch s{&m->bits, &m->scale, &m->priors, &m->value, &m->move_off, &m->move_idx, &m->leaf, &m->leaf_pos, &m->leaf_moves, &m->eval_slot};
-  Evaluator nn{ctx, use_service != 0};
-  return search_root(m->tree, s, nn, pos->p, reuse_tree != 0, use_dirichlet != 0);
+  SearchScratch s(*m);
+  const RootStatus rs = prepare_root(m->tree, s, pos->p, reuse_tree != 0);
+  if (rs == kRootTerminal) return 1;
+  if (rs == kRootNeedsEval) {
+    const int rc = evaluate_request(ctx, use_service != 0, s, 1);
+    if (rc != E55_OK) return rc;
+    finish_root(m->tree, s);
+  }
+  if (use_dirichlet) m->tree.add_noise(0);
+  return E55_OK;
 }
 
 int e55_mcts_search_batches(e55_mcts* m, e55_ctx* ctx, const e55_pos* pos, int n_batches, int leaf_batch,
@@ -453,26 +595,41 @@ int e55_mcts_search_batches(e55_mcts* m, e55_ctx* ctx, const e55_pos* pos, int n
   if (!m || !ctx || !pos || n_batches < 1 || leaf_batch < 1 || leaf_batch > 4096 || !is_default_net(ctx)) return E55_ERR_INVALID;
   const mshogi::Node& root = m->tree.nodes[0];
   if (!root.expanded || root.terminal) return E55_ERR_INVALID;   // e55_mcts_search_root first
-  SearchScratch s{&m->bits, &m->scale, &m->priors, &m->value, &m->move_off, &m->move_idx, &m->leaf, &m->leaf_pos, &m->leaf_moves, &m->eval_slot};
-  Evaluator nn{ctx, use_service != 0};
-  const int rc = search_batches(m->tree, s, nn, pos->p, n_batches, leaf_batch, forced_playouts != 0);
-  return rc != E55_OK ? rc : n_batches * leaf_batch;
+  SearchScratch s(*m);
+  for (int it = 0; it < n_batches; ++it) {
+    const int n_eval = prepare_batch(m->tree, s, pos->p, leaf_batch, forced_playouts != 0);
+    if (n_eval > 0) {
+      const int rc = evaluate_request(ctx, use_service != 0, s, n_eval);
+      if (rc != E55_OK) return rc;
+    }
+    finish_batch(m->tree, s, leaf_batch);
+  }
+  return n_batches * leaf_batch;
 }
 
 // ---- self-play -----------------------------------------------------------------------------------------------
 void e55_selfplay_default_config(e55_selfplay_config* cfg) {
   if (!cfg) return;
   memset(cfg, 0, sizeof(*cfg));
-  cfg->threads = 1; cfg->total_moves = 1;
+  cfg->total_moves = 1;
   cfg->simulations = 800; cfg->leaf_batch = 16;          // client.py:28-29
   cfg->mate_depth = 7;                                   // selfplay.py:36
   cfg->reuse_tree = 1; cfg->use_dirichlet = 1;           // client.py:31-32
   cfg->sampling_moves = 10; cfg->max_moves = 512;        // selfplay.py:10
+  cfg->threads = 0; cfg->games_per_thread = 0;           // chosen from the core count
   cfg->seed = 1;
 }
 
-int e55_selfplay_run_ex(e55_ctx* c, const e55_selfplay_config* cfg, e55_selfplay_stats* out) {
-  if (!c || !cfg || !out || cfg->threads < 1 || cfg->total_moves < 1 || cfg->simulations < 1 || cfg->leaf_batch < 1 ||
+int e55_selfplay_run_ex(e55_ctx* c, const e55_selfplay_config* cfg_in, e55_selfplay_stats* out) {
+  if (!c || !cfg_in || !out) return E55_ERR_INVALID;
+  e55_selfplay_config resolved = *cfg_in;
+  if (resolved.threads <= 0) {   // leave two cores to the service's dispatcher and completer threads
+    const int hw = static_cast<int>(std::thread::hardware_concurrency());
+    resolved.threads = hw > 3 ? hw - 2 : 1;
+  }
+  if (resolved.games_per_thread <= 0) resolved.games_per_thread = 16;
+  const e55_selfplay_config* cfg = &resolved;
+  if (cfg->total_moves < 1 || cfg->simulations < 1 || cfg->leaf_batch < 1 ||
       cfg->leaf_batch > 256 || cfg->mate_depth < 0 || cfg->max_moves < 1)
     return E55_ERR_INVALID;
   int64_t b0 = 0, p0 = 0, b1 = 0, p1 = 0;
@@ -481,16 +638,31 @@ int e55_selfplay_run_ex(e55_ctx* c, const e55_selfplay_config* cfg, e55_selfplay
   SelfplayShared sh;
   sh.ctx = c; sh.cfg = *cfg;
   sh.moves_left.store(cfg->total_moves);
+  sh.games = std::vector<SelfplayGame>(static_cast<size_t>(cfg->threads) * static_cast<size_t>(cfg->games_per_thread));
+  for (size_t i = 0; i < sh.games.size(); ++i) {
+    sh.games[i].m.tree.rng.seed(cfg->seed * 0x9E3779B97F4A7C15ull + i);
+    sh.games[i].pos.set_start_position();
+  }
   std::vector<SelfplayWorker> workers(cfg->threads);
   std::vector<std::thread> th;
   const auto t0 = std::chrono::steady_clock::now();
+  rusage ru0{};
+  getrusage(RUSAGE_SELF, &ru0);
   for (int i = 0; i < cfg->threads; ++i) {
     workers[i].sh = &sh;
-    workers[i].seed = cfg->seed * 0x9E3779B97F4A7C15ull + static_cast<uint64_t>(i);
+    workers[i].index = i;
     th.emplace_back([&workers, i] { workers[i].run(); });
   }
   for (auto& t : th) t.join();
   out->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (getenv("E55_SERVICE_TRACE")) {
+    rusage ru1{};
+    getrusage(RUSAGE_SELF, &ru1);
+    auto secs = [](const timeval& a, const timeval& b) { return static_cast<double>(b.tv_sec - a.tv_sec) + 1e-6 * static_cast<double>(b.tv_usec - a.tv_usec); };
+    fprintf(stderr, "[e55 selfplay] %.2f s wall, process CPU: %.2f s user + %.2f s system = %.1f cores busy; %ld voluntary + %ld involuntary context switches\n",
+            out->seconds, secs(ru0.ru_utime, ru1.ru_utime), secs(ru0.ru_stime, ru1.ru_stime),
+            (secs(ru0.ru_utime, ru1.ru_utime) + secs(ru0.ru_stime, ru1.ru_stime)) / out->seconds, ru1.ru_nvcsw - ru0.ru_nvcsw, ru1.ru_nivcsw - ru0.ru_nivcsw);
+  }
   e55_service_stats(c, &b1, &p1);
   out->moves = sh.moves_done.load(); out->evals = sh.evals_done.load(); out->games = sh.games_done.load();
   out->mean_game_plies = out->games ? static_cast<double>(sh.plies_in_finished_games.load()) / static_cast<double>(out->games) : 0.0;

@@ -131,14 +131,16 @@ def random_play(max_moves=512, stop_with_checkmate=False, trim_checkmate=False):
     return record
 
 
-def run_many(nn, threads, total_moves, simulations=800, leaf_batch=16, mate_depth=7, reuse_tree=True,
-             use_dirichlet=True, num_sampling_moves=10, max_moves=512, seed=1, records=True):
-    """Play games on ``threads`` host threads until ``total_moves`` plies were played; the evaluation service of
-    ``nn`` must be running (``nn.start_service``).  Returns ``(stats dict, [GameRecord of each finished game])``."""
+def run_many(nn, threads=0, total_moves=1000, simulations=800, leaf_batch=16, mate_depth=7, reuse_tree=True,
+             use_dirichlet=True, num_sampling_moves=10, max_moves=512, seed=1, records=True, games_per_thread=0):
+    """Play games on ``threads`` host threads (0: cores - 2) working through a pool of ``threads x games_per_thread``
+    games (0: 16 per thread) kept in flight on the asynchronous evaluation service, until ``total_moves`` plies were played; the service of ``nn`` must be running
+    (``nn.start_service``).  Returns ``(stats dict, [GameRecord of each finished game])``."""
     lib = _capi.load()
     cfg = _capi.SelfplayConfig()
     lib.e55_selfplay_default_config(C.byref(cfg))
     cfg.threads, cfg.total_moves, cfg.simulations, cfg.leaf_batch = threads, total_moves, simulations, leaf_batch
+    cfg.games_per_thread = games_per_thread
     cfg.mate_depth, cfg.reuse_tree, cfg.use_dirichlet = mate_depth, int(reuse_tree), int(use_dirichlet)
     cfg.sampling_moves, cfg.max_moves, cfg.seed = num_sampling_moves, max_moves, seed
     games = []

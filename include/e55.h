@@ -27,6 +27,7 @@ extern "C" {
 typedef struct e55_ctx e55_ctx;
 
 enum {
+  E55_PENDING = 1,           /* asynchronous service calls only: no room right now / result not ready yet */
   E55_OK = 0,
   E55_ERR_INVALID = -1,      /* bad argument / shape */
   E55_ERR_CUDA = -2,         /* CUDA runtime error (message has the CUDA string) */
@@ -111,6 +112,18 @@ int e55_service_predict_packed(e55_ctx* ctx, const uint32_t* bits, const float* 
                                float* value);
 int e55_service_predict_packed_moves(e55_ctx* ctx, const uint32_t* bits, const float* scale, int n,
                                      const int32_t* move_offset, const uint16_t* move_index, float* priors, float* value);
+/* Asynchronous form, so that ONE host thread can keep many games in flight: submit copies the request into the
+ * open batch and returns a ticket at once (E55_PENDING if there is no room and may_block is 0); fetch copies the
+ * priors (move_offset[n] floats) and values out and releases the ticket (E55_PENDING if the batch has not finished
+ * and wait is 0).  Every ticket must be fetched exactly once, before e55_service_stop. */
+typedef struct e55_ticket {
+  int32_t batch, off, moff, n, total, kind;
+  uint64_t gen;
+} e55_ticket;
+int e55_service_submit_packed_moves(e55_ctx* ctx, const uint32_t* bits, const float* scale, int n,
+                                    const int32_t* move_offset, const uint16_t* move_index, int may_block,
+                                    e55_ticket* ticket_out);
+int e55_service_fetch(e55_ctx* ctx, const e55_ticket* ticket, float* priors, float* value, int wait);
 int e55_service_stats(e55_ctx* ctx, int64_t* batches_out, int64_t* positions_out);
 
 /* Synthetic self-play load on the running service, tree operations excluded: `workers` host threads each play
@@ -189,7 +202,8 @@ typedef struct e55_selfplay_stats {
 typedef void (*e55_game_sink)(void* user, const char* record);
 
 typedef struct e55_selfplay_config {
-  int threads;             /* host threads, one game each at a time */
+  int threads;             /* host threads; 0 = cores - 2 (the service's dispatcher and completer need the rest) */
+  int games_per_thread;    /* games per thread in the shared pool kept in flight on the asynchronous service; 0 = 16 */
   long total_moves;        /* stop after this many plies in total */
   int simulations;         /* per move (client.py:29: 800) */
   int leaf_batch;          /* leaves per network call (client.py:28: 16) */
@@ -204,8 +218,9 @@ typedef struct e55_selfplay_config {
 } e55_selfplay_config;
 void e55_selfplay_default_config(e55_selfplay_config* cfg);
 
-/* Self-play on the running evaluation service: `threads` host threads each play whole games the way
- * selfplay.run does (selfplay.py:10-113) with client.py's search settings until `total_moves` plies have been played. */
+/* Self-play on the running evaluation service: `threads` host threads work through a pool of threads x
+ * games_per_thread games, each played the way selfplay.run does (selfplay.py:10-113) with client.py's search
+ * settings, until `total_moves` plies have been played. */
 int e55_selfplay_run_ex(e55_ctx* ctx, const e55_selfplay_config* cfg, e55_selfplay_stats* stats_out);
 int e55_selfplay_run(e55_ctx* ctx, int threads, long total_moves, int simulations, int leaf_batch, int mate_depth,
                      uint64_t seed, e55_selfplay_stats* stats_out);

@@ -347,6 +347,30 @@ def test_legal_move_priors_match_the_host_softmax(weights_perturbed):
     check(np.concatenate([out[lo][0] for lo in sorted(out)]), np.concatenate([out[lo][1] for lo in sorted(out)]))
     with pytest.raises(Exception):
         net.predict_packed_moves(bits[:1], scale[:1], np.array([0, 1], np.int32), np.array([1725], np.uint16))
+    # asynchronous form: several tickets in flight from ONE thread, fetched out of order
+    import ctypes as C
+    from erweitern_55_b200 import _capi
+    lib = _capi.load()
+    net.start_service(max_batch=16, max_wait_us=100)
+    tickets, spans = [], [(0, 10), (10, 16), (16, 33), (33, 40)]          # 17 > what is left of the first batch of 16
+    for lo, hi in spans:
+        t = (C.c_uint8 * 32)()
+        o = np.ascontiguousarray(off[lo:hi + 1] - off[lo])
+        rc = lib.e55_service_submit_packed_moves(net._ctx, bits[lo:hi].ctypes.data, scale[lo:hi].ctypes.data, hi - lo,
+                                                 o.ctypes.data, idx[off[lo]:off[hi]].ctypes.data, 1, t)
+        assert rc == (_capi.E55_OK if hi - lo <= 16 else _capi.E55_ERR_INVALID)
+        tickets.append(t if rc == 0 else None)
+    got = {}
+    for k in (3, 0, 1):
+        lo, hi = spans[k]
+        pr = np.empty(off[hi] - off[lo], np.float32); va = np.empty((hi - lo, 1), np.float32)
+        assert lib.e55_service_fetch(net._ctx, tickets[k], pr.ctypes.data, va.ctypes.data, 1) == 0
+        got[k] = (pr, va)
+    net.stop_service()
+    ref_p, ref_v = net.predict_packed_moves(bits, scale, off, idx)
+    for k in (0, 1, 3):
+        lo, hi = spans[k]
+        assert np.array_equal(got[k][0], ref_p[off[lo]:off[hi]]) and np.array_equal(got[k][1], ref_v[lo:hi])
     net.close()
 
 
@@ -405,9 +429,11 @@ def test_selfplay_records_and_usi_on_the_gpu(weights_default):
     assert rec.ply == len(rec.sfen_kif) == len(rec.mcts_result) > 4
     # many games on the native driver, records through the sink
     net.start_service(max_batch=512, max_wait_us=200)
-    stats, games = selfplay.run_many(net, threads=16, total_moves=400, simulations=32, leaf_batch=16, mate_depth=3,
-                                     max_moves=20, seed=11)
+    stats, games = selfplay.run_many(net, threads=4, games_per_thread=8, total_moves=400, simulations=32, leaf_batch=16,
+                                     mate_depth=3, max_moves=20, seed=11)
+    auto, _ = selfplay.run_many(net, total_moves=200, simulations=32, max_moves=20, records=False)   # thread counts from the cores
     net.stop_service()
+    assert auto["moves"] >= 150
     assert stats["games"] == len(games) >= 8 and stats["mean_gpu_batch"] > 4
     for g in games:
         q = Position()

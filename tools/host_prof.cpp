@@ -6,6 +6,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <vector>
 
 #include "../include/e55.h"
 
@@ -48,6 +50,30 @@ int e55_predict_packed_moves(e55_ctx* c, const uint32_t* bits, const float* s, i
                              float* priors, float* value) {
   return e55_service_predict_packed_moves(c, bits, s, n, off, idx, priors, value);
 }
+// asynchronous form: answered at once, handed over at fetch
+struct Pending { std::vector<float> priors, value; };
+static std::mutex g_mu;
+static std::vector<Pending*> g_pending;
+int e55_service_submit_packed_moves(e55_ctx* c, const uint32_t* bits, const float* s, int n, const int32_t* off, const uint16_t* idx,
+                                    int, e55_ticket* t) {
+  Pending* p = new Pending{std::vector<float>(off[n]), std::vector<float>(n)};
+  e55_service_predict_packed_moves(c, bits, s, n, off, idx, p->priors.data(), p->value.data());
+  std::lock_guard<std::mutex> lk(g_mu);
+  int slot = -1;
+  for (size_t i = 0; i < g_pending.size(); ++i) if (!g_pending[i]) { slot = static_cast<int>(i); break; }
+  if (slot < 0) { slot = static_cast<int>(g_pending.size()); g_pending.push_back(nullptr); }
+  g_pending[slot] = p;
+  t->batch = slot; t->n = n; t->total = off[n];
+  return 0;
+}
+int e55_service_fetch(e55_ctx*, const e55_ticket* t, float* priors, float* value, int) {
+  Pending* p;
+  { std::lock_guard<std::mutex> lk(g_mu); p = g_pending[t->batch]; g_pending[t->batch] = nullptr; }
+  memcpy(priors, p->priors.data(), sizeof(float) * p->priors.size());
+  memcpy(value, p->value.data(), sizeof(float) * p->value.size());
+  delete p;
+  return 0;
+}
 int e55_get_arch(const e55_ctx*, int* b, int* f, int* ip) { *b = 7; *f = 128; *ip = 266; return 0; }
 int e55_service_stats(e55_ctx*, int64_t* b, int64_t* p) { *b = g_calls; *p = g_positions; return 0; }
 }
@@ -60,6 +86,7 @@ int main(int argc, char** argv) {
   e55_selfplay_config cfg;
   e55_selfplay_default_config(&cfg);
   cfg.threads = threads; cfg.total_moves = moves; cfg.mate_depth = mate; cfg.simulations = sims;
+  cfg.games_per_thread = argc > 5 ? atoi(argv[5]) : 1;
   e55_selfplay_stats st;
   const int rc = e55_selfplay_run_ex(reinterpret_cast<e55_ctx*>(0x1), &cfg, &st);
   printf("rc %d: %ld moves, %ld evals, %ld games (%.1f plies) in %.3f s -> %.1f moves/s, %.2f us/eval, %.2f ms/move/thread\n", rc,
