@@ -12,6 +12,7 @@
 #include <condition_variable>
 #include <thread>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -342,6 +343,13 @@ int forward_packed_on(e55_ctx* c, cudaStream_t stream, const uint32_t* d_bits, c
   return E55_OK;
 }
 
+// Chunk size of the pipelined host-buffer predict: full chunks while much is left, then halves (multiples of 64).
+int pipe_chunk(int left, int chunk) {
+  if (left > chunk + chunk / 2) return std::min(chunk, left);
+  const int half = std::max(64, ((left / 2 + 63) / 64) * 64);
+  return half >= left ? left : half;
+}
+
 int check_predict_args(e55_ctx* c, const void* a, const void* b, const void* d, int n) {
   if (!c) return E55_ERR_INVALID;
   if (!a || !b || !d) return fail(c, E55_ERR_INVALID, "null buffer");
@@ -538,20 +546,25 @@ int e55_predict(e55_ctx* c, const float* planes, int n, float* policy, float* va
   if (c->precision == E55_PRECISION_BF16_TC && !c->timing && n >= 2 * kChunk) {
     E55_CUDA(c, cudaEventRecord(c->pipe_start, c->stream));
     const size_t in_pp = static_cast<size_t>(c->in_planes) * kSq, pol_pp = static_cast<size_t>(kPolicyCh) * kSq;
-    c->tc.throughput_rounds = true;   // chunk kernels run side by side: keep each on few SMs
     int used = 0;
-    for (int off = 0, i = 0; off < n; off += kChunk, ++i) {
-      const int m = std::min(kChunk, n - off);
+    for (int off = 0, i = 0; off < n; ++i) {
+      // The H2D copy is the serial resource (26.6 KB per position): full chunks while much is left, then halving
+      // chunks, so that what remains after the last byte has arrived -- one kernel and one read-back -- is short.
+      const int left = n - off;
+      const int m = pipe_chunk(left, kChunk);
       cudaStream_t st = c->pipe_stream[i % e55_ctx::kPipeStreams];
       if (i < e55_ctx::kPipeStreams) { E55_CUDA(c, cudaStreamWaitEvent(st, c->pipe_start, 0)); used = i + 1; }
       E55_CUDA(c, cudaMemcpyAsync(c->d_in + off * in_pp, planes + off * in_pp, m * in_pp * sizeof(float),
                                   cudaMemcpyHostToDevice, st));
-      if ((rc = forward_tc_on(c, st, c->d_in + off * in_pp, m, c->d_policy + off * pol_pp, c->d_value + off))) return rc;
+      c->tc.throughput_rounds = m >= kChunk;   // full chunks run side by side on few SMs each; the short tail spreads out
+      rc = forward_tc_on(c, st, c->d_in + off * in_pp, m, c->d_policy + off * pol_pp, c->d_value + off);
+      c->tc.throughput_rounds = false;
+      if (rc) return rc;
       E55_CUDA(c, cudaMemcpyAsync(policy + off * pol_pp, c->d_policy + off * pol_pp, m * pol_pp * sizeof(float),
                                   cudaMemcpyDeviceToHost, st));
       E55_CUDA(c, cudaMemcpyAsync(value + off, c->d_value + off, m * sizeof(float), cudaMemcpyDeviceToHost, st));
+      off += m;
     }
-    c->tc.throughput_rounds = false;
     for (int i = 0; i < used; ++i) {
       E55_CUDA(c, cudaEventRecord(c->pipe_done[i], c->pipe_stream[i]));
       E55_CUDA(c, cudaStreamWaitEvent(c->stream, c->pipe_done[i], 0));
