@@ -126,16 +126,18 @@ class Network:
         return pickle.dumps(self.get_weights(), protocol=4)
 
     def load(self, filepath):
-        """Load weights saved by :meth:`save` (``.npz``) or a pickled ``get_weights()`` list (``.pkl``).  Keras
-        ``.h5`` files (network.py:226) need h5py, which this environment lacks; convert them with
-        ``np.savez(path, *model.get_weights())``."""
-        if str(filepath).endswith((".pkl", ".pickle")):
+        """Load weights from a Keras HDF5 file (``.h5`` / ``.hdf5``: what the reference's ``save`` writes with
+        ``keras.Model.save``, network.py:245-253, or a ``save_weights`` file; read by :mod:`erweitern_55_b200.hdf5`,
+        optimizer state ignored), from :meth:`save`'s ``.npz``, or from a pickled ``get_weights()`` list (``.pkl``)."""
+        path = str(filepath)
+        if path.endswith((".pkl", ".pickle")):
             with open(filepath, "rb") as f:
                 self.load_pickled_weights(f.read())
             return
-        if str(filepath).endswith((".h5", ".hdf5")):
-            raise NotImplementedError("Keras HDF5 checkpoints are not readable here (no h5py); "
-                                      "export model.get_weights() to .npz")
+        if path.endswith((".h5", ".hdf5", ".keras")):
+            from . import hdf5
+            self.set_weights(hdf5.read_keras_weights(filepath))
+            return
         with np.load(filepath) as z:
             n = len([k for k in z.files if k.startswith("arr_")])
             self.set_weights([z[f"arr_{i}"] for i in range(n)])
@@ -143,6 +145,14 @@ class Network:
                 self._iterations = int(z["iterations"])
 
     def save(self, filepath):
+        """``.h5`` / ``.hdf5``: a Keras ``save_weights``-layout HDF5 file (``model.load_weights`` reads it in the
+        reference; there is no optimizer state or model config to store); otherwise ``.npz``."""
+        path = str(filepath)
+        if path.endswith((".h5", ".hdf5")):
+            from . import hdf5
+            from .weights import keras_layers
+            hdf5.write_keras_weights(filepath, self._weights, keras_layers(self._blocks, self._filters, self._in_planes))
+            return
         np.savez(filepath, *self._weights, iterations=np.int64(self._iterations))
 
     # ---- inputs (network.py:255-274,283-286) ----------------------------------------------------

@@ -60,6 +60,24 @@ def weight_spec(blocks: int = 7, filters: int = 128, in_planes: int = IN_PLANES)
     return spec
 
 
+def keras_layers(blocks: int = 7, filters: int = 128, in_planes: int = IN_PLANES):
+    """``[(layer_name, [weight_name, ...]), ...]`` covering :func:`weight_spec` in order, with the names tf.keras
+    gives the layers of ``network.py:88-120`` (``conv2d``, ``conv2d_1``, ..., ``batch_normalization``, ..., ``dense``,
+    ``dense_1``) -- the groups and datasets of a Keras weight file."""
+    counters = {"conv2d": 0, "batch_normalization": 0, "dense": 0}
+    layers, last = [], None
+    for name, shape in weight_spec(blocks, filters, in_planes):
+        layer, part = name.rsplit("/", 1)
+        if layer != last:
+            kind = "batch_normalization" if part == "gamma" else ("conv2d" if len(shape) == 4 else "dense")
+            keras_name = kind if counters[kind] == 0 else f"{kind}_{counters[kind]}"
+            counters[kind] += 1
+            layers.append((keras_name, []))
+            last = layer
+        layers[-1][1].append(f"{layers[-1][0]}/{part}:0")
+    return layers
+
+
 def num_params(blocks: int = 7, filters: int = 128, in_planes: int = IN_PLANES) -> int:
     return int(sum(int(np.prod(s)) for _, s in weight_spec(blocks, filters, in_planes)))
 

@@ -194,6 +194,11 @@ def test_set_weights_roundtrip_and_swap(nets, weights_default, weights_perturbed
     net.load(path)
     p2, _ = net.predict(x)
     assert np.array_equal(p2, p1)
+    h5 = str(tmp_path / "iter_0.h5")                                  # the reference's checkpoint format (train.py:45)
+    net.save(h5)
+    net.set_weights(weights_default)
+    net.load(h5)
+    assert np.array_equal(net.predict(x)[0], p1)
     with pytest.raises(ValueError):
         net.set_weights(W.init_weights(blocks=2))
     net.close()
