@@ -63,6 +63,7 @@ class Mcts {
 
   void clear() {
     nodes.clear(); edges.clear(); nodes.emplace_back();
+    if (nodes.capacity() < 4096) { nodes.reserve(4096); edges.reserve(65536); }   // one 800-simulation search without regrowth
     root_ply_ = -1; root_hash_ = game_hash_ = 0;
   }
   int32_t root() const { return 0; }
