@@ -18,6 +18,7 @@
 #include <string>
 #include <vector>
 
+#include "e55_host.h"
 #include "e55_fp32.cuh"
 #include "e55_tc.cuh"
 #include "e55_umma_test.cuh"
@@ -50,9 +51,9 @@ struct e55_ctx {
   int64_t launches = 0;
   cudaStream_t stream = nullptr;
   // host-buffer predict pipeline: chunks of the batch go H2D -> kernels -> D2H on rotating side streams
-  static constexpr int kPipeStreams = 4;
-  cudaStream_t pipe_stream[kPipeStreams] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t pipe_done[kPipeStreams] = {nullptr, nullptr, nullptr, nullptr};
+  static constexpr int kPipeStreams = 8;
+  cudaStream_t pipe_stream[kPipeStreams] = {};
+  cudaEvent_t pipe_done[kPipeStreams] = {};
   cudaEvent_t pipe_start = nullptr;
   mutable std::mutex mu;
   mutable std::string err;
@@ -86,6 +87,12 @@ struct e55_ctx {
   uint8_t* d_mask = nullptr;
   uint32_t* d_bits = nullptr;   // packed input staging: [capacity][in_planes]
   float* d_scale = nullptr;
+  // host-side input compaction for e55_predict (e55_host.cpp): thread pool + pinned staging of the packed form
+  int host_threads = -1;           // -1: chosen from the core count on first use; 0: off
+  e55host::Packer* packer = nullptr;
+  uint32_t* h_bits = nullptr;      // pinned [h_cap][in_planes]
+  float* h_scale = nullptr;
+  int h_cap = 0;
   // compact legal-move tail (e55_predict_packed_moves): CSR move lists and their priors
   static constexpr int kMovesPerPosition = 128;   // capacity per position on average; a single position may use more
   int32_t* d_move_off = nullptr;   // [capacity + 1]
@@ -350,6 +357,32 @@ int pipe_chunk(int left, int chunk) {
   return half >= left ? left : half;
 }
 
+// The packing pool and pinned staging for `n` positions (null: compaction is off or unavailable).
+e55host::Packer* host_packer(e55_ctx* c, int n) {
+  if (c->host_threads < 0) {
+    int t = static_cast<int>(std::thread::hardware_concurrency()) - 2;
+    if (const char* env = getenv("E55_HOST_THREADS")) t = atoi(env);
+    c->host_threads = std::max(0, std::min(t, 14));
+  }
+  if (c->host_threads == 0) return nullptr;
+  if (c->packer && e55host::packer_threads(c->packer) != c->host_threads) { e55host::packer_destroy(c->packer); c->packer = nullptr; }
+  if (!c->packer) c->packer = e55host::packer_create(c->host_threads);
+  if (c->packer && n > c->h_cap) {
+    cudaFreeHost(c->h_bits); cudaFreeHost(c->h_scale);
+    c->h_bits = nullptr; c->h_scale = nullptr; c->h_cap = 0;
+    int cap = 256;
+    while (cap < n) cap *= 2;
+    const size_t w = static_cast<size_t>(cap) * c->in_planes;
+    if (cudaMallocHost(&c->h_bits, w * sizeof(uint32_t)) != cudaSuccess || cudaMallocHost(&c->h_scale, w * sizeof(float)) != cudaSuccess) {
+      cudaFreeHost(c->h_bits); c->h_bits = nullptr; c->h_scale = nullptr;
+      cudaGetLastError();
+      return nullptr;
+    }
+    c->h_cap = cap;
+  }
+  return c->packer;
+}
+
 int check_predict_args(e55_ctx* c, const void* a, const void* b, const void* d, int n) {
   if (!c) return E55_ERR_INVALID;
   if (!a || !b || !d) return fail(c, E55_ERR_INVALID, "null buffer");
@@ -407,6 +440,8 @@ void e55_destroy(e55_ctx* c) {
   cudaSetDevice(c->device);
   e55_service_stop(c);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  e55host::packer_destroy(c->packer);
+  cudaFreeHost(c->h_bits); cudaFreeHost(c->h_scale);
   free_weights(c);
   free_buffers(c);
   if (c->ev0) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); }
@@ -543,6 +578,43 @@ int e55_predict(e55_ctx* c, const float* planes, int n, float* policy, float* va
   // side streams, so PCIe transfers in both directions overlap each other and the kernels (which then run
   // concurrently on disjoint SMs).  The step stays one logical batch: every position is independent.
   constexpr int kChunk = 256;
+  // Large batches on the tensor-core path, with host threads to spare: the planes are bit-packed on the host chunk
+  // by chunk (exactly; e55_host.cpp) while earlier chunks are already on the GPU, so 2 128 instead of 26 600 bytes per
+  // position cross PCIe.  A chunk that is not exactly representable travels as float planes.
+  e55host::Packer* packer = (c->precision == E55_PRECISION_BF16_TC && !c->timing && n >= kChunk) ? host_packer(c, n) : nullptr;
+  if (packer) {
+    e55host::packer_start(packer, planes, n, c->in_planes, c->h_bits, c->h_scale);
+    cudaError_t e = cudaEventRecord(c->pipe_start, c->stream);
+    const size_t ip = static_cast<size_t>(c->in_planes), in_pp = ip * kSq, pol_pp = static_cast<size_t>(kPolicyCh) * kSq;
+    int used = 0;
+    rc = E55_OK;
+    for (int off = 0, i = 0; off < n && e == cudaSuccess && rc == E55_OK; ++i) {
+      const int m = std::min(kChunk, n - off);   // a one-group-per-CTA kernel of 64 CTAs; two run side by side
+      const bool exact = e55host::packer_wait_range(packer, off, m);
+      cudaStream_t st = c->pipe_stream[i % e55_ctx::kPipeStreams];
+      if (i < e55_ctx::kPipeStreams) { e = cudaStreamWaitEvent(st, c->pipe_start, 0); used = i + 1; }
+      if (exact) {
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_bits + off * ip, c->h_bits + off * ip, m * ip * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_scale + off * ip, c->h_scale + off * ip, m * ip * sizeof(float), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) rc = forward_packed_on(c, st, c->d_bits + off * ip, c->d_scale + off * ip, m, off, c->d_policy + off * pol_pp, c->d_value + off);
+      } else {
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_in + off * in_pp, planes + off * in_pp, m * in_pp * sizeof(float), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) rc = forward_tc_on(c, st, c->d_in + off * in_pp, m, c->d_policy + off * pol_pp, c->d_value + off);
+      }
+      if (e == cudaSuccess && rc == E55_OK) e = cudaMemcpyAsync(policy + off * pol_pp, c->d_policy + off * pol_pp, m * pol_pp * sizeof(float), cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess && rc == E55_OK) e = cudaMemcpyAsync(value + off, c->d_value + off, m * sizeof(float), cudaMemcpyDeviceToHost, st);
+      off += m;
+    }
+    for (int i = 0; i < used && e == cudaSuccess; ++i) {
+      e = cudaEventRecord(c->pipe_done[i], c->pipe_stream[i]);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(c->stream, c->pipe_done[i], 0);
+    }
+    e55host::packer_finish(packer);   // the pool reads the caller's planes: it must be done before we return, whatever happened
+    if (rc != E55_OK) return rc;
+    E55_CUDA(c, e);
+    E55_CUDA(c, cudaStreamSynchronize(c->stream));
+    return E55_OK;
+  }
   if (c->precision == E55_PRECISION_BF16_TC && !c->timing && n >= 2 * kChunk) {
     E55_CUDA(c, cudaEventRecord(c->pipe_start, c->stream));
     const size_t in_pp = static_cast<size_t>(c->in_planes) * kSq, pol_pp = static_cast<size_t>(kPolicyCh) * kSq;
@@ -604,12 +676,10 @@ int e55_predict_packed(e55_ctx* c, const uint32_t* bits, const float* scale, int
   const size_t in_pp = static_cast<size_t>(c->in_planes), pol_pp = static_cast<size_t>(kPolicyCh) * kSq;
   constexpr int kChunk = 256;
   const bool pipelined = c->precision == E55_PRECISION_BF16_TC && n >= 2 * kChunk;
-  const int step = pipelined ? kChunk : n;
   if (pipelined) E55_CUDA(c, cudaEventRecord(c->pipe_start, c->stream));
-  c->tc.throughput_rounds = pipelined;   // chunk kernels run side by side: keep each on few SMs
   int used = 0;
-  for (int off = 0, i = 0; off < n; off += step, ++i) {
-    const int m = std::min(step, n - off);
+  for (int off = 0, i = 0, m = 0; off < n; off += m, ++i) {
+    m = pipelined ? pipe_chunk(n - off, kChunk) : n;   // one-group-per-CTA kernels of <= 256 positions, two at a time
     cudaStream_t st = pipelined ? c->pipe_stream[i % e55_ctx::kPipeStreams] : c->stream;
     if (pipelined && i < e55_ctx::kPipeStreams) { E55_CUDA(c, cudaStreamWaitEvent(st, c->pipe_start, 0)); used = i + 1; }
     E55_CUDA(c, cudaMemcpyAsync(c->d_bits + off * in_pp, bits + off * in_pp, m * in_pp * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
@@ -619,7 +689,6 @@ int e55_predict_packed(e55_ctx* c, const uint32_t* bits, const float* scale, int
     E55_CUDA(c, cudaMemcpyAsync(policy + off * pol_pp, c->d_policy + off * pol_pp, m * pol_pp * sizeof(float), cudaMemcpyDeviceToHost, st));
     E55_CUDA(c, cudaMemcpyAsync(value + off, c->d_value + off, m * sizeof(float), cudaMemcpyDeviceToHost, st));
   }
-  c->tc.throughput_rounds = false;
   for (int i = 0; i < used; ++i) {
     E55_CUDA(c, cudaEventRecord(c->pipe_done[i], c->pipe_stream[i]));
     E55_CUDA(c, cudaStreamWaitEvent(c->stream, c->pipe_done[i], 0));
@@ -704,6 +773,14 @@ int e55_sync(e55_ctx* c) {
 int e55_stream(e55_ctx* c, void** stream_out) {
   if (!c || !stream_out) return E55_ERR_INVALID;
   *stream_out = static_cast<void*>(c->stream);
+  return E55_OK;
+}
+
+int e55_set_host_threads(e55_ctx* c, int threads) {
+  if (!c || threads < -1 || threads > 256) return E55_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  c->host_threads = threads;
+  if (threads == 0) { e55host::packer_destroy(c->packer); c->packer = nullptr; }
   return E55_OK;
 }
 

@@ -1,0 +1,22 @@
+// Host-side helpers of libe55.so that are plain C++ (compiled by g++, see e55_host.cpp).
+#pragma once
+#include <cstdint>
+
+namespace e55host {
+
+struct Packer;   // thread pool that bit-packs float planes (exactly, or reports that it cannot)
+
+Packer* packer_create(int threads);
+void packer_destroy(Packer* p);
+int packer_threads(const Packer* p);
+// Pack planes [n][in_planes][25] into bits/scale [n][in_planes] in the background, front to back.
+void packer_start(Packer* p, const float* planes, int n, int in_planes, uint32_t* bits, float* scale);
+// Block until positions [first, first + count) are done; false if one of them is not exactly representable
+// (some plane holds two different non-zero values).
+bool packer_wait_range(Packer* p, int first, int count);
+// Block until every worker has left the job started last.
+void packer_finish(Packer* p);
+// Same packing on the calling thread.
+bool pack_planes_inline(const float* planes, int n, int in_planes, uint32_t* bits, float* scale);
+
+}  // namespace e55host

@@ -68,8 +68,14 @@ int e55_get_precision(const e55_ctx* ctx, int* precision);
 /* Replaces Network.predict (network.py:201-216) for HOST buffers: planes float32 [n,in_planes,5,5]
  * (NCHW) -> policy float32 [n,1725] raw logits (index c*25+y*5+x), value float32 [n,1] (tanh).
  * The whole input is one batch.  Includes H2D and D2H copies; returns after the outputs are in the
- * caller's buffers. */
+ * caller's buffers.  Batches of 256 and more are pipelined in chunks (host-side bit-packing of the planes by a
+ * small thread pool -> copy -> kernel -> read-back overlap across chunks; see e55_set_host_threads). */
 int e55_predict(e55_ctx* ctx, const float* planes, int n, float* policy, float* value);
+
+/* Host threads e55_predict may use to bit-pack large float-plane batches before the copy (exact: a chunk whose
+ * planes are not "one value or zero" travels as floats; results are identical either way).  -1 = chosen from the
+ * core count (default; E55_HOST_THREADS overrides), 0 = off: the planes cross PCIe as they are. */
+int e55_set_host_threads(e55_ctx* ctx, int threads);
 
 /* Same computation on DEVICE buffers, enqueued on the context stream; returns without
  * synchronising (call e55_sync).  Buffers must stay valid until then. */

@@ -459,6 +459,32 @@ def test_selfplay_records_and_usi_on_the_gpu(weights_default):
     net.close()
 
 
+def test_host_side_packing_is_invisible(weights_perturbed):
+    """e55_predict bit-packs large float-plane batches on a host thread pool before the copy (e55_host.cpp): outputs are
+    bit-identical to the plain float path, also when some chunk cannot be packed exactly and travels as floats."""
+    from erweitern_55_b200.network import Network
+    net = Network(precision="bf16", weights=weights_perturbed, max_batch=1024)
+    lib = net._lib
+    x = synth.synthetic_planes(1000, seed=77)                          # ragged: not a multiple of the chunk
+    lib.e55_set_host_threads(net._ctx, 0)
+    p0, v0 = net.predict(x)
+    for threads in (1, 4, -1):
+        lib.e55_set_host_threads(net._ctx, threads)
+        for _ in range(2):
+            p1, v1 = net.predict(x)
+            assert np.array_equal(p0, p1) and np.array_equal(v0, v1)
+    y = x.copy()
+    y[300, 5, 2, 2], y[300, 5, 3, 3] = 0.25, 0.75                      # two different non-zero values in one plane
+    y[999, 265] = np.linspace(0.0, 1.0, 25, dtype=np.float32).reshape(5, 5)
+    y[5, 7, 0, 0] = -0.0                                               # negative zero is still zero
+    lib.e55_set_host_threads(net._ctx, 0)
+    q0, w0 = net.predict(y)
+    lib.e55_set_host_threads(net._ctx, 4)
+    q1, w1 = net.predict(y)
+    assert np.array_equal(q0, q1) and np.array_equal(w0, w1) and not np.array_equal(q0[300], p0[300])
+    net.close()
+
+
 def test_device_resident_api(nets):
     net = nets["default", "bf16"]
     x = synth.synthetic_planes(100, seed=12)

@@ -22,3 +22,7 @@ bits, scale = packing.pack_planes(x.numpy())
 bt = torch.from_numpy(bits.astype(np.int32)).pin_memory(); st = torch.from_numpy(scale).pin_memory()
 e = t(lambda: lib.e55_predict_packed(ctx, bt.data_ptr(), st.data_ptr(), B, pol.data_ptr(), val.data_ptr()), 50)
 print(f"e55_predict_packed: {e*1e6:.0f} us/step = {B/e/1e6:.2f} M evals/s")
+for threads in (0, 4, 8, 12, 14, 16):
+    lib.e55_set_host_threads(ctx, threads)
+    e = t(lambda: lib.e55_predict(ctx, x.data_ptr(), B, pol.data_ptr(), val.data_ptr()), 50)
+    print(f"e55_predict, {threads:2d} packing threads: {e*1e6:.0f} us/step = {B/e/1e6:.2f} M evals/s")
