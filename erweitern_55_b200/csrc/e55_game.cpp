@@ -87,6 +87,7 @@ struct SearchScratch {
     move_off->resize(static_cast<size_t>(leaf_batch) + 1);
     value->resize(leaf_batch);
     leaf->resize(leaf_batch);
+    leaf_pos->clear();                                           // (forked scratch positions must not be copied around)
     leaf_pos->resize(leaf_batch);
     leaf_moves->resize(leaf_batch);
     eval_slot->resize(leaf_batch);
@@ -140,7 +141,7 @@ int prepare_batch(mshogi::Mcts& tree, SearchScratch& s, const mshogi::Position& 
   int n_eval = 0;
   move_off[0] = 0;
   for (int b = 0; b < leaf_batch; ++b) {
-    leaf_pos[b] = root_pos;
+    leaf_pos[b].fork_from(root_pos);                          // shares the root's history, owns only the path below it
     leaf[b] = tree.select_leaf(0, leaf_pos[b], forced_playouts);
     eval_slot[b] = -1;
     if (!tree.claim(leaf[b])) continue;                       // expanded, terminal, or a duplicate in this batch

@@ -44,6 +44,7 @@ struct Node {
   bool expanded = false;
   bool terminal = false;
   bool claimed = false;         // selected, not yet evaluated, in the current leaf batch (native driver only)
+  bool in_check = false;        // known once expanded: the side to move here is in check (= the move into it checks)
 };
 
 class Mcts {
@@ -78,15 +79,15 @@ class Mcts {
   // The root for `pos`.  With reuse_tree, when `pos` continues the game the current root belongs to, the subtree
   // reached by the moves played since is kept (compacted to the front of the pools); otherwise the tree is emptied.
   int32_t set_root(const Position& pos, bool reuse_tree) {
-    if (reuse_tree && root_ply_ >= 0 && pos.ply >= root_ply_ && static_cast<int>(pos.hist.size()) == pos.ply + 1 &&
-        pos.hist[0].hash == game_hash_ && pos.hist[root_ply_].hash == root_hash_) {
+    if (reuse_tree && root_ply_ >= 0 && pos.ply >= root_ply_ && pos.history_size() == pos.ply + 1 &&
+        pos.entry(0).hash == game_hash_ && pos.entry(root_ply_).hash == root_hash_) {
       int32_t node = 0;
       for (int i = root_ply_ + 1; i <= pos.ply && node >= 0; ++i) {
         const Node& nd = nodes[node];
         int32_t next = -1;
         if (nd.expanded && !nd.terminal)
           for (int e = 0; e < nd.n_edges; ++e)
-            if (edges[nd.first_edge + e].move == pos.hist[i].move) { next = edges[nd.first_edge + e].child; break; }
+            if (edges[nd.first_edge + e].move == pos.entry(i).move) { next = edges[nd.first_edge + e].child; break; }
         node = next;
       }
       if (node >= 0) {
@@ -96,7 +97,7 @@ class Mcts {
       }
     }
     clear();
-    root_ply_ = pos.ply; root_hash_ = pos.hash(); game_hash_ = pos.hist[0].hash;
+    root_ply_ = pos.ply; root_hash_ = pos.hash(); game_hash_ = pos.entry(0).hash;
     return 0;
   }
 
@@ -140,7 +141,8 @@ class Mcts {
       }
       Edge& e = ed[best];
       ++e.vloss;
-      pos.do_move(e.move);
+      // whether the move gives check is known from the child's expansion; only moves into new leaves have to look
+      pos.do_move(e.move, e.child >= 0 && nodes[e.child].expanded ? static_cast<int>(nodes[e.child].in_check) : -1);
       if (e.child < 0) {
         e.child = static_cast<int32_t>(nodes.size());
         nodes.emplace_back();
@@ -370,6 +372,7 @@ class Mcts {
     nd.value = value01;
     nd.first_edge = static_cast<int32_t>(edges.size());
     nd.n_edges = moves.size();
+    nd.in_check = moves.in_check;
     nd.expanded = true;
     edges.resize(edges.size() + moves.size());
     Edge* ed = edges.data() + nd.first_edge;
@@ -394,8 +397,8 @@ class Mcts {
   void compact(int32_t new_root) {
     std::vector<Node> nn;
     std::vector<Edge> ne;
-    nn.reserve(nodes.size() / 4 + 16);
-    ne.reserve(edges.size() / 4 + 64);
+    nn.reserve(std::max<size_t>(4096, nodes.size() / 2));      // room for the next search: no regrowth copies
+    ne.reserve(std::max<size_t>(65536, edges.size() / 2));
     std::vector<int32_t> old_of;           // new index -> old index
     old_of.push_back(new_root);
     nn.push_back(nodes[new_root]);

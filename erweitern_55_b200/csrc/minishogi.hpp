@@ -176,6 +176,7 @@ inline Bitboard slide_attacks(const Tables& T, int sq, Bitboard occ, uint32_t di
 struct MoveList {                    // no position has anywhere near 256 legal moves on a 5x5 board
   Move m[256];
   int n = 0;
+  bool in_check = false;             // set by generate_moves: the side to move is in check
   void push(const Move& mv) { if (n < 256) m[n++] = mv; }
   const Move* begin() const { return m; }
   const Move* end() const { return m + n; }
@@ -204,9 +205,33 @@ class Position {
   int side = BLACK;
   int ply = 0;
   int8_t king_sq[2] = {-1, -1};      // cached king squares (-1: no king, as in some test positions)
-  std::vector<HistoryEntry> hist;    // history for repetition / encoding / tree reuse; hist[ply] = current position
+  // History for repetition / encoding / tree reuse; entry(ply) = the current position.  A position made by fork_from()
+  // shares the other position's entries as a read-only prefix and owns only what it plays on top of them.
+  std::vector<HistoryEntry> hist;
+  const HistoryEntry* base_ = nullptr;
+  int base_n_ = 0;
 
   Position() { set_start_position(); }
+  Position(const Position& o) { *this = o; }
+  Position& operator=(const Position& o) {     // a copy owns its whole history
+    if (this == &o) return *this;
+    copy_board_from(o);
+    hist.clear();
+    hist.reserve(static_cast<size_t>(o.history_size()) + 8);
+    for (int i = 0; i < o.history_size(); ++i) hist.push_back(o.entry(i));
+    base_ = nullptr; base_n_ = 0;
+    return *this;
+  }
+  // Cheap copy for a search: valid while `root` is alive and unchanged; `root` must own its history.
+  void fork_from(const Position& root) {
+    copy_board_from(root);
+    hist.clear();
+    base_ = root.hist.data();
+    base_n_ = static_cast<int>(root.hist.size());
+  }
+  int history_size() const { return base_n_ + static_cast<int>(hist.size()); }
+  const HistoryEntry& entry(int i) const { return i < base_n_ ? base_[i] : hist[static_cast<size_t>(i - base_n_)]; }
+  const HistoryEntry& last_entry() const { return hist.empty() ? base_[base_n_ - 1] : hist.back(); }
 
   static int type_of(int8_t p) { return p & 15; }
   static int color_of(int8_t p) { return (p >> 4) & 1; }
@@ -219,6 +244,7 @@ class Position {
     side = BLACK; ply = 0;
     king_sq[0] = king_sq[1] = -1;
     hist.clear();
+    base_ = nullptr; base_n_ = 0;
   }
 
   void set_start_position() { set_sfen("rbsgk/4p/5/P4/KGSBR b - 1"); }
@@ -412,11 +438,12 @@ class Position {
     }
   }
 
-  void do_move(const Move& m) {
+  // gives_check: 1 / 0 when the caller already knows whether the move checks (a search tree does), -1 to find out.
+  void do_move(const Move& m, int gives_check = -1) {
     const uint64_t h = hash_after(m);
     apply(m);
     ++ply;
-    push_history(h, in_check(side), m);
+    push_history(h, gives_check < 0 ? in_check(side) : gives_check != 0, m);
   }
   void undo_move(const Move& m) {
     hist.pop_back();
@@ -427,7 +454,7 @@ class Position {
   // ---- move generation ------------------------------------------------------------------------
   // Fully legal moves of the side to move (own king never left in check; nifu, last-rank pawn and
   // pawn-drop-mate excluded).
-  void generate_moves(MoveList& out) { out.n = 0; generate<false>(&out); }
+  void generate_moves(MoveList& out) { out.n = 0; out.in_check = false; generate<false>(&out); }
   void generate_moves(std::vector<Move>& out) {
     MoveList l;
     generate_moves(l);
@@ -441,25 +468,25 @@ class Position {
   // of those occurrences gave check, that side is the perpetual checker.
   void is_repetition(bool& rep, bool& my_check, bool& op_check) const {
     rep = my_check = op_check = false;
-    const int last = static_cast<int>(hist.size()) - 1;
-    if (hist[last].snap.rep_count < 4) return;
-    const uint64_t h = hist[last].hash;
+    const int last = history_size() - 1;
+    if (entry(last).snap.rep_count < 4) return;
+    const uint64_t h = entry(last).hash;
     int first = last;
     for (int i = last; i >= 0; i -= 2)
-      if (hist[i].hash == h) first = i;
+      if (entry(i).hash == h) first = i;
     rep = true;
     // moves leading to positions first+1 .. last; the move to position i was made by the side NOT to move at i
     bool mine = true, theirs = true;   // "mine" = side to move now
     bool any_mine = false, any_theirs = false;
     for (int i = first + 1; i <= last; ++i) {
       const bool mover_is_me = ((last - i) & 1) == 1;  // position `last` has me to move; the move into it was theirs
-      if (mover_is_me) { any_mine = true; mine = mine && hist[i].gave_check; }
-      else { any_theirs = true; theirs = theirs && hist[i].gave_check; }
+      if (mover_is_me) { any_mine = true; mine = mine && entry(i).gave_check; }
+      else { any_theirs = true; theirs = theirs && entry(i).gave_check; }
     }
     my_check = any_mine && mine;
     op_check = any_theirs && theirs;
   }
-  int repetition_count() const { return hist.back().snap.rep_count; }
+  int repetition_count() const { return last_entry().snap.rep_count; }
 
   // ---- mate search (tests/test_checkmate.py) ----------------------------------------------------
   // Depth-limited AND/OR search over checking sequences: the side to move must check on every move.
@@ -467,7 +494,7 @@ class Position {
     return depth > 0 && mate_attack(depth, &best);
   }
 
-  uint64_t hash() const { return hist.back().hash; }
+  uint64_t hash() const { return last_entry().hash; }
 
   uint64_t compute_hash() const {
     const Tables& T = tables();
@@ -487,6 +514,14 @@ class Position {
     }
   }
 
+  void copy_board_from(const Position& o) {
+    memcpy(board, o.board, sizeof(board));
+    memcpy(hand, o.hand, sizeof(hand));
+    memcpy(bb, o.bb, sizeof(bb));
+    side = o.side; ply = o.ply;
+    king_sq[0] = o.king_sq[0]; king_sq[1] = o.king_sq[1];
+  }
+
   void put(int sq, int type, int color) {
     board[sq] = make_piece(type, color);
     bb[color][type] |= 1u << sq;
@@ -503,7 +538,7 @@ class Position {
   uint64_t hash_after(const Move& m) const {
     const Tables& T = tables();
     const int us = side;
-    uint64_t h = hist.back().hash ^ T.zob_side[BLACK] ^ T.zob_side[WHITE];
+    uint64_t h = last_entry().hash ^ T.zob_side[BLACK] ^ T.zob_side[WHITE];
     if (m.is_drop()) {
       const int k = hand_index(static_cast<PieceType>(m.piece));
       h ^= T.zob_hand[us][k][hand[us][k] & 3] ^ T.zob_hand[us][k][(hand[us][k] - 1) & 3];
@@ -530,8 +565,8 @@ class Position {
       for (int t = 1; t < PIECE_TYPES; ++t) e.snap.pieces[c][t - 1] = bb[c][t];
     memcpy(e.snap.hand, hand, sizeof(hand));
     int c = 1;                                          // occurrences of this position so far (same side to move)
-    for (int i = static_cast<int>(hist.size()) - 3; i >= 0; i -= 2)
-      if (hist[i].hash == h) { c += hist[i].snap.rep_count; break; }   // the latest earlier occurrence knows the rest
+    for (int i = history_size() - 3; i >= 0; i -= 2)
+      if (entry(i).hash == h) { c += entry(i).snap.rep_count; break; }   // the latest earlier occurrence knows the rest
     e.snap.rep_count = static_cast<uint8_t>(c > 255 ? 255 : c);
   }
 
@@ -544,13 +579,31 @@ class Position {
   }
 
   // Legal move generation.  kAny: stop at the first legal move and return true (`out` is not used).
-  template <bool kAny>
+  // kChecks: only moves that can give check -- a superset of the checking moves, in the order of the full list (the
+  // piece lands where its kind attacks the enemy king with our own men thought away, or leaves a line through that
+  // king); the mate search confirms each by playing it.
+  template <bool kAny, bool kChecks = false>
   bool generate(MoveList* out) {
     const Tables& T = tables();
     const int us = side, them = us ^ 1;
     const int far = us == BLACK ? 0 : kN - 1;      // promotion rank
     const Bitboard own = bb[us][0], occ = occupied();
     const int ksq = king_sq[us];
+    Bitboard zone[PIECE_TYPES] = {};               // kChecks: squares from which a piece of that type would attack their king
+    Bitboard king_lines = 0;                       // kChecks: lines through their king that one of our sliders could use
+    if (kChecks) {
+      const int ek = king_sq[them];
+      if (ek < 0) return false;
+      const Bitboard rook_rays = slide_attacks(T, ek, bb[them][0], kRookDirs), bishop_rays = slide_attacks(T, ek, bb[them][0], kBishopDirs);
+      zone[GOLD] = zone[PRO_SILVER] = zone[TOKIN] = T.step_from[us][GOLD][ek];
+      zone[SILVER] = T.step_from[us][SILVER][ek];
+      zone[PAWN] = T.step_from[us][PAWN][ek];
+      zone[BISHOP] = bishop_rays; zone[ROOK] = rook_rays;
+      zone[HORSE] = bishop_rays | T.step_from[us][KING][ek];
+      zone[DRAGON] = rook_rays | T.step_from[us][KING][ek];
+      if (bb[us][ROOK] | bb[us][DRAGON]) king_lines |= rook_rays;
+      if (bb[us][BISHOP] | bb[us][HORSE]) king_lines |= bishop_rays;
+    }
     Bitboard checkers = 0, pinned = 0;
     Bitboard target_mask = kAllSquares;            // where non-king pieces may land (blocks / captures when in check)
     if (ksq >= 0) {
@@ -564,12 +617,13 @@ class Position {
         const Bitboard b = T.between[ksq][pop_lsb(snipers)] & occ;
         if (b && !(b & (b - 1)) && (b & own)) pinned |= b;
       }
+      if (!kAny) out->in_check = checkers != 0;
       if (checkers) {
         if (checkers & (checkers - 1)) target_mask = 0;                                   // double check: king moves only
         else target_mask = checkers | T.between[ksq][lsb(checkers)];
       }
       // king moves: the destination must not be attacked once the king has left its square
-      for (Bitboard dst = T.step_to[us][KING][ksq] & ~own; dst;) {
+      for (Bitboard dst = (kChecks && !(king_lines >> ksq & 1)) ? 0 : T.step_to[us][KING][ksq] & ~own; dst;) {
         const int to = pop_lsb(dst);
         if (attackers_to(to, them, occ ^ (1u << ksq))) continue;
         if (kAny) return true;
@@ -585,6 +639,7 @@ class Position {
         if (slides) dst |= slide_attacks(T, from, occ, slides);
         dst &= ~own & target_mask;
         if (pinned >> from & 1) dst &= T.line[ksq][from];
+        if (kChecks && !(king_lines >> from & 1)) dst &= zone[t] | (can_promote(t) ? zone[promote(t)] : 0);
         if (kAny) { if (dst) return true; continue; }    // (a pawn reaching the last rank still has its promotion)
         const bool from_zone = rank_of(from) == far;
         while (dst) {
@@ -598,7 +653,7 @@ class Position {
         for (int k = 0; k < kHandTypes; ++k) {
           if (!hand[us][k]) continue;
           const PieceType t = kHandPiece[k];
-          Bitboard dst = empties;
+          Bitboard dst = kChecks ? empties & zone[t] : empties;
           if (t == PAWN) {
             dst &= ~T.rank_mask[far];                                                       // not onto the last rank
             for (Bitboard p = bb[us][PAWN]; p;) dst &= ~T.file_mask[col_of(pop_lsb(p))];    // nifu
@@ -623,7 +678,8 @@ class Position {
 
   bool mate_attack(int depth, Move* best) {
     MoveList moves;
-    generate_moves(moves);
+    moves.n = 0;
+    generate<false, true>(&moves);
     for (const Move& m : moves) {
       apply(m);
       bool mated = false;
@@ -671,11 +727,11 @@ inline void encode_packed(const Position& pos, uint32_t* bits, float* scale) {
   memset(bits, 0, kInputPlanes * sizeof(uint32_t));
   for (int c = 0; c < kInputPlanes; ++c) scale[c] = 1.f;
   const int me = pos.side;
-  const int last = static_cast<int>(pos.hist.size()) - 1;
+  const int last = pos.history_size() - 1;
   for (int t = 0; t < kHistory; ++t) {
     const int idx = last - t;
     if (idx < 0) break;
-    const Snapshot& sn = pos.hist[idx].snap;
+    const Snapshot& sn = pos.entry(idx).snap;
     uint32_t* b = bits + t * kPlanesPerStep;
     float* sc = scale + t * kPlanesPerStep;
     if (me == BLACK) {
