@@ -210,6 +210,17 @@ def main():
     os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # several ranks on one box: give each its own contiguous block of host cores, so the game threads, the packing
+    # pool and the service threads of one GPU neither migrate across sockets nor sit on another rank's cores
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+    my_cores = sorted(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else list(range(os.cpu_count() or 1))
+    if local_world > 1 and len(my_cores) >= 2 * local_world:
+        per = len(my_cores) // local_world
+        my_cores = my_cores[local_rank * per:(local_rank + 1) * per]
+        try:
+            os.sched_setaffinity(0, my_cores)
+        except OSError:
+            pass
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -235,33 +246,57 @@ def main():
         torch.cuda.synchronize(dev)
 
     # ---- device-resident throughput ("value") ---------------------------------------------------
-    for i in range(args.warmup):
-        net.predict_device(pool[i % n_pool], policy, value)
-    net.sync()
+    # Two forwards of batch 1024 are kept in flight on two contexts (= two streams), the way the evaluation service
+    # feeds the GPU: a 1024-position launch occupies 128 of the 148 SMs, the next one starts on the other 20 and on
+    # every SM the first one leaves.  Every step is still one whole batch-1024 forward; the one-in-flight number
+    # (kernels strictly one after the other) is reported beside it and is what `roofline` is measured on.
+    net_b = Network(device=local_rank, precision=args.precision, weights=w, max_batch=B, blocks=args.blocks, filters=args.filters)
+    lanes = [(net, policy, value, stream),
+             (net_b, torch.empty_like(policy), torch.empty_like(value), torch.cuda.ExternalStream(net_b.cuda_stream(), device=dev))]
+
+    def run_steps(n_steps, in_flight):
+        for i in range(n_steps):
+            nn_, p_, v_, _ = lanes[i % in_flight]
+            nn_.predict_device(pool[i % n_pool], p_, v_)
+
+    def timed_steps(n_steps, in_flight):
+        for nn_, _, _, _ in lanes:
+            nn_.sync()
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(in_flight)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(in_flight)]
+        for k in range(in_flight):
+            starts[k].record(lanes[k][3])
+        run_steps(n_steps, in_flight)
+        for k in range(in_flight):
+            ends[k].record(lanes[k][3])
+        for nn_, _, _, _ in lanes:
+            nn_.sync()
+        return max(a.elapsed_time(b) for a in starts for b in ends) * 1e-3
+
+    run_steps(args.warmup * 2, 2)
     barrier()
-    launches0 = net.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = net.launch_count() + net_b.launch_count()
     with ClockSampler(local_rank) as clocks:
         t_wall0 = time.perf_counter()
-        e0.record(stream)
-        for i in range(args.steps):
-            net.predict_device(pool[i % n_pool], policy, value)
-        e1.record(stream)
-        net.sync()
+        dev_s = timed_steps(args.steps, 2)
         t_wall = time.perf_counter() - t_wall0
-        launches = net.launch_count() - launches0
+        launches = net.launch_count() + net_b.launch_count() - launches0
         # a very short timed region ends before nvidia-smi's first sample: keep the same load running
         # (untimed) until the sampler has seen it
         if t_wall < 0.5:
             t_end = time.perf_counter() + 0.5
             while time.perf_counter() < t_end:
-                for i in range(16):
-                    net.predict_device(pool[i % n_pool], policy, value)
-                net.sync()
+                run_steps(32, 2)
+                net.sync(); net_b.sync()
     barrier()
-    dev_s = e0.elapsed_time(e1) * 1e-3
     total_units, max_s = sharding.aggregate(B * args.steps, dev_s, device=dev)
     value_rate = total_units / max_s
+    one_s = timed_steps(max(args.steps // 2, 1), 1)
+    barrier()
+    one_units, one_max = sharding.aggregate(B * max(args.steps // 2, 1), one_s, device=dev)
+    value_one_in_flight = one_units / one_max
+    net_b.close()
+    lanes = lanes[:1]
 
     # ---- dominant kernel vs roofline (rank 0, CUDA events around the tower kernel) ----------------
     roofline = None
@@ -295,7 +330,7 @@ def main():
         net._check(lib.e55_predict(ctx, host_pool[i % 3].data_ptr(), B, host_policy.data_ptr(), host_value.data_ptr()))
 
     def timed_host_steps():
-        for i in range(3):
+        for i in range(12):      # warm-up; in the library's automatic mode these calls also try both pipelines
             host_step(i)
         barrier()
         t0 = time.perf_counter()
@@ -307,19 +342,23 @@ def main():
         return units / t_max
 
     # this rank's share of the host cores, minus two, packs the float planes into bits before the copy (e55_host.cpp)
-    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
-    pack_threads = max(1, min(14, (os.cpu_count() or 4) // max(1, local_world) - 2))
+    import ctypes as C
     net._check(lib.e55_set_host_threads(ctx, 0))
     e2e_plain = timed_host_steps()
-    net._check(lib.e55_set_host_threads(ctx, pack_threads))
+    net._check(lib.e55_set_host_threads(ctx, -1))      # the default: the library picks the thread count and the pipeline
     e2e_value = timed_host_steps()
-    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 266 * 8,
+    pk_threads, pk_us, fl_us = C.c_int(), C.c_double(), C.c_double()
+    net._check(lib.e55_get_host_pipeline(ctx, C.byref(pk_threads), C.byref(pk_us), C.byref(fl_us)))
+    pack_threads, compacting = pk_threads.value, pk_us.value <= fl_us.value
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 266 * 8 if compacting else in_bytes,
+           "host_pipeline": "compacting" if compacting else "float", "us_per_position": {"compacting": pk_us.value, "float": fl_us.value},
            "d2h_bytes_per_step": B * 1725 * 4 + B * 4, "steps": e2e_steps, "host_input_bytes_per_step": in_bytes,
            "host_pack_threads": pack_threads, "value_without_host_packing": e2e_plain,
            "timing": "host wall clock around blocking e55_predict calls on pinned float32 [B,266,5,5] planes, max over ranks; "
-                     "the call bit-packs the planes on a host thread pool chunk by chunk (exact, results identical) so that "
-                     "h2d_bytes_per_step, not host_input_bytes_per_step, cross PCIe; value_without_host_packing is the same "
-                     "call with e55_set_host_threads(0)"}
+                     "in its default mode the call measures two pipelines and keeps the faster (host_pipeline): bit-packing the planes "
+                     "on a host thread pool chunk by chunk (exact, results identical; then h2d_bytes_per_step = 2 128 B per "
+                     "position cross PCIe instead of host_input_bytes_per_step) or sending the float planes as they are; "
+                     "value_without_host_packing is the same call with e55_set_host_threads(0)"}
 
     # ---- same call with the compact input format (e55_predict_packed; not the reference's format) ---
     from erweitern_55_b200 import packing
@@ -355,8 +394,7 @@ def main():
         barrier()
         # real self-play: native minishogi engine + MCTS (800 simulations, leaf batch 16, 7-ply mate search)
         # one worker thread per host core of this rank's share, minus two for the service's dispatcher / completer
-        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
-        sp_threads = max(2, (os.cpu_count() or 4) // max(1, local_world) - 2)
+        sp_threads = max(2, len(my_cores) - 2)
         net.selfplay(threads=sp_threads, total_moves=512, simulations=160, leaf_batch=16, mate_depth=7, seed=99 + rank)   # warm-up
         barrier()
         real = net.selfplay(threads=sp_threads, total_moves=args.selfplay_total_moves, simulations=800, leaf_batch=16,
@@ -410,9 +448,11 @@ def main():
                                     "per GPU, random-init weights (BASELINE.json configs[1])") if (args.blocks, args.filters) == (7, 128)
                        else f"scaled tower {args.blocks}x{args.filters} forward, batch {B} per GPU, random-init weights (BASELINE.json configs[4])",
                        "batch_per_gpu": B, "parallelism": f"replicas x{world} (independent positions, no collective)",
+                       "in_flight": "two batch-%d forwards in flight per GPU on two streams (as the evaluation service runs them); "
+                                    "value_one_in_flight = kernels strictly one after the other" % B,
                        "l2": f"inputs rotate over {n_pool} distinct device batches = {n_pool * in_bytes >> 20} MiB > 126 MiB L2",
-                       "flop_per_position": flops, "host_cpu": model, "host_cores": ncpu},
-            "e2e": e2e, "e2e_packed": e2e_packed, "selfplay": selfplay_real, "selfplay_synthetic": selfplay, "gpu_launches": launches, "clocks": clocks.summary(),
+                       "flop_per_position": flops, "host_cpu": model, "host_cores_per_rank": len(my_cores), "host_cores": ncpu},
+            "value_one_in_flight": value_one_in_flight, "e2e": e2e, "e2e_packed": e2e_packed, "selfplay": selfplay_real, "selfplay_synthetic": selfplay, "gpu_launches": launches, "clocks": clocks.summary(),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "wall_s": t_wall,
         }
         sys.stdout.flush()

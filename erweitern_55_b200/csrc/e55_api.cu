@@ -4,6 +4,7 @@
 
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <sched.h>
 
 #include <algorithm>
 #include <atomic>
@@ -89,6 +90,9 @@ struct e55_ctx {
   float* d_scale = nullptr;
   // host-side input compaction for e55_predict (e55_host.cpp): thread pool + pinned staging of the packed form
   int host_threads = -1;           // -1: chosen from the core count on first use; 0: off
+  bool host_auto = true;           // the caller left the choice to the library: measure both pipelines, use the faster
+  int64_t pipe_calls = 0;
+  double compact_us = 0.0, float_us = 0.0;   // running mean of microseconds per position of either pipeline
   e55host::Packer* packer = nullptr;
   uint32_t* h_bits = nullptr;      // pinned [h_cap][in_planes]
   float* h_scale = nullptr;
@@ -360,7 +364,10 @@ int pipe_chunk(int left, int chunk) {
 // The packing pool and pinned staging for `n` positions (null: compaction is off or unavailable).
 e55host::Packer* host_packer(e55_ctx* c, int n) {
   if (c->host_threads < 0) {
-    int t = static_cast<int>(std::thread::hardware_concurrency()) - 2;
+    cpu_set_t set;
+    int hw = static_cast<int>(std::thread::hardware_concurrency());
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) hw = CPU_COUNT(&set);   // the cores this process may actually use
+    int t = hw - 2;
     if (const char* env = getenv("E55_HOST_THREADS")) t = atoi(env);
     c->host_threads = std::max(0, std::min(t, 14));
   }
@@ -568,81 +575,100 @@ int e55_predict_device(e55_ctx* c, const float* d_planes, int n, float* d_policy
   return forward(c, d_planes, n, d_policy, d_value);
 }
 
+namespace {
+
+constexpr int kPipeChunk = 256;
+
+// Host-buffer predict, compacting pipeline: the planes are bit-packed on the host chunk by chunk (exactly;
+// e55_host.cpp) while earlier chunks are already on the GPU, so 2 128 instead of 26 600 bytes per position cross
+// PCIe.  A chunk that is not exactly representable travels as float planes.  Results equal the float pipeline's.
+int predict_compacting(e55_ctx* c, e55host::Packer* packer, const float* planes, int n, float* policy, float* value) {
+  e55host::packer_start(packer, planes, n, c->in_planes, c->h_bits, c->h_scale);
+  cudaError_t e = cudaEventRecord(c->pipe_start, c->stream);
+  const size_t ip = static_cast<size_t>(c->in_planes), in_pp = ip * kSq, pol_pp = static_cast<size_t>(kPolicyCh) * kSq;
+  int used = 0, rc = E55_OK;
+  for (int off = 0, i = 0; off < n && e == cudaSuccess && rc == E55_OK; ++i) {
+    const int m = std::min(kPipeChunk, n - off);   // a one-group-per-CTA kernel of 64 CTAs; two run side by side
+    const bool exact = e55host::packer_wait_range(packer, off, m);
+    cudaStream_t st = c->pipe_stream[i % e55_ctx::kPipeStreams];
+    if (i < e55_ctx::kPipeStreams) { e = cudaStreamWaitEvent(st, c->pipe_start, 0); used = i + 1; }
+    if (exact) {
+      if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_bits + off * ip, c->h_bits + off * ip, m * ip * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_scale + off * ip, c->h_scale + off * ip, m * ip * sizeof(float), cudaMemcpyHostToDevice, st);
+      if (e == cudaSuccess) rc = forward_packed_on(c, st, c->d_bits + off * ip, c->d_scale + off * ip, m, off, c->d_policy + off * pol_pp, c->d_value + off);
+    } else {
+      if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_in + off * in_pp, planes + off * in_pp, m * in_pp * sizeof(float), cudaMemcpyHostToDevice, st);
+      if (e == cudaSuccess) rc = forward_tc_on(c, st, c->d_in + off * in_pp, m, c->d_policy + off * pol_pp, c->d_value + off);
+    }
+    if (e == cudaSuccess && rc == E55_OK) e = cudaMemcpyAsync(policy + off * pol_pp, c->d_policy + off * pol_pp, m * pol_pp * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && rc == E55_OK) e = cudaMemcpyAsync(value + off, c->d_value + off, m * sizeof(float), cudaMemcpyDeviceToHost, st);
+    off += m;
+  }
+  for (int i = 0; i < used && e == cudaSuccess; ++i) {
+    e = cudaEventRecord(c->pipe_done[i], c->pipe_stream[i]);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(c->stream, c->pipe_done[i], 0);
+  }
+  e55host::packer_finish(packer);   // the pool reads the caller's planes: it must be done before we return, whatever happened
+  if (rc != E55_OK) return rc;
+  E55_CUDA(c, e);
+  E55_CUDA(c, cudaStreamSynchronize(c->stream));
+  return E55_OK;
+}
+
+// Host-buffer predict, float pipeline: chunks travel H2D -> kernel -> D2H on rotating side streams, so PCIe
+// transfers in both directions overlap each other and the kernels (which run side by side on disjoint SMs).
+int predict_float_pipeline(e55_ctx* c, const float* planes, int n, float* policy, float* value) {
+  E55_CUDA(c, cudaEventRecord(c->pipe_start, c->stream));
+  const size_t in_pp = static_cast<size_t>(c->in_planes) * kSq, pol_pp = static_cast<size_t>(kPolicyCh) * kSq;
+  int used = 0;
+  for (int off = 0, i = 0; off < n; ++i) {
+    // The H2D copy is the serial resource (26.6 KB per position): full chunks while much is left, then halving
+    // chunks, so that what remains after the last byte has arrived -- one kernel and one read-back -- is short.
+    const int m = pipe_chunk(n - off, kPipeChunk);
+    cudaStream_t st = c->pipe_stream[i % e55_ctx::kPipeStreams];
+    if (i < e55_ctx::kPipeStreams) { E55_CUDA(c, cudaStreamWaitEvent(st, c->pipe_start, 0)); used = i + 1; }
+    E55_CUDA(c, cudaMemcpyAsync(c->d_in + off * in_pp, planes + off * in_pp, m * in_pp * sizeof(float), cudaMemcpyHostToDevice, st));
+    c->tc.throughput_rounds = m >= kPipeChunk;   // full chunks run side by side on few SMs each; the short tail spreads out
+    const int rc = forward_tc_on(c, st, c->d_in + off * in_pp, m, c->d_policy + off * pol_pp, c->d_value + off);
+    c->tc.throughput_rounds = false;
+    if (rc) return rc;
+    E55_CUDA(c, cudaMemcpyAsync(policy + off * pol_pp, c->d_policy + off * pol_pp, m * pol_pp * sizeof(float), cudaMemcpyDeviceToHost, st));
+    E55_CUDA(c, cudaMemcpyAsync(value + off, c->d_value + off, m * sizeof(float), cudaMemcpyDeviceToHost, st));
+    off += m;
+  }
+  for (int i = 0; i < used; ++i) {
+    E55_CUDA(c, cudaEventRecord(c->pipe_done[i], c->pipe_stream[i]));
+    E55_CUDA(c, cudaStreamWaitEvent(c->stream, c->pipe_done[i], 0));
+  }
+  E55_CUDA(c, cudaStreamSynchronize(c->stream));
+  return E55_OK;
+}
+
+}  // namespace
+
 int e55_predict(e55_ctx* c, const float* planes, int n, float* policy, float* value) {
   int rc = check_predict_args(c, planes, policy, value, n);
   if (rc) return rc;
   std::lock_guard<std::mutex> lk(c->mu);
   E55_CUDA(c, cudaSetDevice(c->device));
   if ((rc = ensure_capacity(c, n))) return rc;
-  // Large batches on the tensor-core path: split into chunks that travel H2D -> kernel -> D2H on rotating
-  // side streams, so PCIe transfers in both directions overlap each other and the kernels (which then run
-  // concurrently on disjoint SMs).  The step stays one logical batch: every position is independent.
-  constexpr int kChunk = 256;
-  // Large batches on the tensor-core path, with host threads to spare: the planes are bit-packed on the host chunk
-  // by chunk (exactly; e55_host.cpp) while earlier chunks are already on the GPU, so 2 128 instead of 26 600 bytes per
-  // position cross PCIe.  A chunk that is not exactly representable travels as float planes.
-  e55host::Packer* packer = (c->precision == E55_PRECISION_BF16_TC && !c->timing && n >= kChunk) ? host_packer(c, n) : nullptr;
-  if (packer) {
-    e55host::packer_start(packer, planes, n, c->in_planes, c->h_bits, c->h_scale);
-    cudaError_t e = cudaEventRecord(c->pipe_start, c->stream);
-    const size_t ip = static_cast<size_t>(c->in_planes), in_pp = ip * kSq, pol_pp = static_cast<size_t>(kPolicyCh) * kSq;
-    int used = 0;
-    rc = E55_OK;
-    for (int off = 0, i = 0; off < n && e == cudaSuccess && rc == E55_OK; ++i) {
-      const int m = std::min(kChunk, n - off);   // a one-group-per-CTA kernel of 64 CTAs; two run side by side
-      const bool exact = e55host::packer_wait_range(packer, off, m);
-      cudaStream_t st = c->pipe_stream[i % e55_ctx::kPipeStreams];
-      if (i < e55_ctx::kPipeStreams) { e = cudaStreamWaitEvent(st, c->pipe_start, 0); used = i + 1; }
-      if (exact) {
-        if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_bits + off * ip, c->h_bits + off * ip, m * ip * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_scale + off * ip, c->h_scale + off * ip, m * ip * sizeof(float), cudaMemcpyHostToDevice, st);
-        if (e == cudaSuccess) rc = forward_packed_on(c, st, c->d_bits + off * ip, c->d_scale + off * ip, m, off, c->d_policy + off * pol_pp, c->d_value + off);
-      } else {
-        if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_in + off * in_pp, planes + off * in_pp, m * in_pp * sizeof(float), cudaMemcpyHostToDevice, st);
-        if (e == cudaSuccess) rc = forward_tc_on(c, st, c->d_in + off * in_pp, m, c->d_policy + off * pol_pp, c->d_value + off);
-      }
-      if (e == cudaSuccess && rc == E55_OK) e = cudaMemcpyAsync(policy + off * pol_pp, c->d_policy + off * pol_pp, m * pol_pp * sizeof(float), cudaMemcpyDeviceToHost, st);
-      if (e == cudaSuccess && rc == E55_OK) e = cudaMemcpyAsync(value + off, c->d_value + off, m * sizeof(float), cudaMemcpyDeviceToHost, st);
-      off += m;
+  if (c->precision == E55_PRECISION_BF16_TC && !c->timing && n >= 2 * kPipeChunk) {
+    // Large batch on the tensor-core path: one of the two pipelines.  Which one is faster depends on the host (cores
+    // and memory bandwidth to spare against the PCIe link), so unless the caller fixed the thread count the first
+    // calls try both and later ones take the faster, looking at the other again now and then.
+    e55host::Packer* packer = host_packer(c, n);
+    bool compact = packer != nullptr;
+    if (compact && c->host_auto) {
+      const int64_t k = c->pipe_calls++;
+      if (k < 8) compact = (k & 1) == 0;
+      else compact = (c->compact_us <= c->float_us) != (k % 128 == 0);
     }
-    for (int i = 0; i < used && e == cudaSuccess; ++i) {
-      e = cudaEventRecord(c->pipe_done[i], c->pipe_stream[i]);
-      if (e == cudaSuccess) e = cudaStreamWaitEvent(c->stream, c->pipe_done[i], 0);
-    }
-    e55host::packer_finish(packer);   // the pool reads the caller's planes: it must be done before we return, whatever happened
-    if (rc != E55_OK) return rc;
-    E55_CUDA(c, e);
-    E55_CUDA(c, cudaStreamSynchronize(c->stream));
-    return E55_OK;
-  }
-  if (c->precision == E55_PRECISION_BF16_TC && !c->timing && n >= 2 * kChunk) {
-    E55_CUDA(c, cudaEventRecord(c->pipe_start, c->stream));
-    const size_t in_pp = static_cast<size_t>(c->in_planes) * kSq, pol_pp = static_cast<size_t>(kPolicyCh) * kSq;
-    int used = 0;
-    for (int off = 0, i = 0; off < n; ++i) {
-      // The H2D copy is the serial resource (26.6 KB per position): full chunks while much is left, then halving
-      // chunks, so that what remains after the last byte has arrived -- one kernel and one read-back -- is short.
-      const int left = n - off;
-      const int m = pipe_chunk(left, kChunk);
-      cudaStream_t st = c->pipe_stream[i % e55_ctx::kPipeStreams];
-      if (i < e55_ctx::kPipeStreams) { E55_CUDA(c, cudaStreamWaitEvent(st, c->pipe_start, 0)); used = i + 1; }
-      E55_CUDA(c, cudaMemcpyAsync(c->d_in + off * in_pp, planes + off * in_pp, m * in_pp * sizeof(float),
-                                  cudaMemcpyHostToDevice, st));
-      c->tc.throughput_rounds = m >= kChunk;   // full chunks run side by side on few SMs each; the short tail spreads out
-      rc = forward_tc_on(c, st, c->d_in + off * in_pp, m, c->d_policy + off * pol_pp, c->d_value + off);
-      c->tc.throughput_rounds = false;
-      if (rc) return rc;
-      E55_CUDA(c, cudaMemcpyAsync(policy + off * pol_pp, c->d_policy + off * pol_pp, m * pol_pp * sizeof(float),
-                                  cudaMemcpyDeviceToHost, st));
-      E55_CUDA(c, cudaMemcpyAsync(value + off, c->d_value + off, m * sizeof(float), cudaMemcpyDeviceToHost, st));
-      off += m;
-    }
-    for (int i = 0; i < used; ++i) {
-      E55_CUDA(c, cudaEventRecord(c->pipe_done[i], c->pipe_stream[i]));
-      E55_CUDA(c, cudaStreamWaitEvent(c->stream, c->pipe_done[i], 0));
-    }
-    E55_CUDA(c, cudaStreamSynchronize(c->stream));
-    return E55_OK;
+    const auto t0 = std::chrono::steady_clock::now();
+    rc = compact ? predict_compacting(c, packer, planes, n, policy, value) : predict_float_pipeline(c, planes, n, policy, value);
+    const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / n;
+    double& avg = compact ? c->compact_us : c->float_us;
+    avg = avg == 0.0 ? us : 0.75 * avg + 0.25 * us;
+    return rc;
   }
   const size_t in_bytes = static_cast<size_t>(n) * c->in_planes * kSq * sizeof(float);
   E55_CUDA(c, cudaMemcpyAsync(c->d_in, planes, in_bytes, cudaMemcpyHostToDevice, c->stream));
@@ -674,7 +700,7 @@ int e55_predict_packed(e55_ctx* c, const uint32_t* bits, const float* scale, int
   E55_CUDA(c, cudaSetDevice(c->device));
   if ((rc = ensure_capacity(c, n))) return rc;
   const size_t in_pp = static_cast<size_t>(c->in_planes), pol_pp = static_cast<size_t>(kPolicyCh) * kSq;
-  constexpr int kChunk = 256;
+  constexpr int kChunk = kPipeChunk;
   const bool pipelined = c->precision == E55_PRECISION_BF16_TC && n >= 2 * kChunk;
   if (pipelined) E55_CUDA(c, cudaEventRecord(c->pipe_start, c->stream));
   int used = 0;
@@ -780,7 +806,18 @@ int e55_set_host_threads(e55_ctx* c, int threads) {
   if (!c || threads < -1 || threads > 256) return E55_ERR_INVALID;
   std::lock_guard<std::mutex> lk(c->mu);
   c->host_threads = threads;
+  c->host_auto = threads < 0;
+  c->pipe_calls = 0; c->compact_us = c->float_us = 0.0;
   if (threads == 0) { e55host::packer_destroy(c->packer); c->packer = nullptr; }
+  return E55_OK;
+}
+
+int e55_get_host_pipeline(e55_ctx* c, int* threads_out, double* compact_us_out, double* float_us_out) {
+  if (!c || !threads_out || !compact_us_out || !float_us_out) return E55_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  *threads_out = c->packer ? e55host::packer_threads(c->packer) : 0;
+  *compact_us_out = c->compact_us;
+  *float_us_out = c->float_us;
   return E55_OK;
 }
 

@@ -2,6 +2,7 @@
 // Host-only translation unit (g++): it reaches the network through the public C ABI of include/e55.h only.
 #include "../../include/e55.h"
 
+#include <sched.h>
 #include <sys/resource.h>
 
 #include <atomic>
@@ -625,7 +626,9 @@ int e55_selfplay_run_ex(e55_ctx* c, const e55_selfplay_config* cfg_in, e55_selfp
   if (!c || !cfg_in || !out) return E55_ERR_INVALID;
   e55_selfplay_config resolved = *cfg_in;
   if (resolved.threads <= 0) {   // leave two cores to the service's dispatcher and completer threads
-    const int hw = static_cast<int>(std::thread::hardware_concurrency());
+    cpu_set_t set;
+    int hw = static_cast<int>(std::thread::hardware_concurrency());
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) hw = CPU_COUNT(&set);   // the cores this process may actually use
     resolved.threads = hw > 3 ? hw - 2 : 1;
   }
   if (resolved.games_per_thread <= 0) resolved.games_per_thread = 16;

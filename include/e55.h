@@ -73,9 +73,14 @@ int e55_get_precision(const e55_ctx* ctx, int* precision);
 int e55_predict(e55_ctx* ctx, const float* planes, int n, float* policy, float* value);
 
 /* Host threads e55_predict may use to bit-pack large float-plane batches before the copy (exact: a chunk whose
- * planes are not "one value or zero" travels as floats; results are identical either way).  -1 = chosen from the
- * core count (default; E55_HOST_THREADS overrides), 0 = off: the planes cross PCIe as they are. */
+ * planes are not "one value or zero" travels as floats; results are identical either way).  -1 (default) = the
+ * library's choice: cores - 2 threads (at most 14; E55_HOST_THREADS overrides), and it measures both ways during
+ * the first calls and keeps the faster; n > 0 = always pack with n threads; 0 = off: the planes cross PCIe as they
+ * are. */
 int e55_set_host_threads(e55_ctx* ctx, int threads);
+/* What e55_predict measured: packing threads in use, and the running mean of microseconds per position of the
+ * compacting and of the float pipeline on large batches (0 = not tried yet). */
+int e55_get_host_pipeline(e55_ctx* ctx, int* threads_out, double* compact_us_out, double* float_us_out);
 
 /* Same computation on DEVICE buffers, enqueued on the context stream; returns without
  * synchronising (call e55_sync).  Buffers must stay valid until then. */
