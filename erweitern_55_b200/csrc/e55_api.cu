@@ -97,6 +97,9 @@ struct e55_ctx {
   uint32_t* h_bits = nullptr;      // pinned [h_cap][in_planes]
   float* h_scale = nullptr;
   int h_cap = 0;
+  // e55_predict_packed_moves: one pinned request block and one answer block per call, and their device twins
+  uint8_t *h_req = nullptr, *h_ans = nullptr, *d_req = nullptr, *d_ans = nullptr;
+  size_t req_cap = 0, ans_cap = 0;
   // compact legal-move tail (e55_predict_packed_moves): CSR move lists and their priors
   static constexpr int kMovesPerPosition = 128;   // capacity per position on average; a single position may use more
   int32_t* d_move_off = nullptr;   // [capacity + 1]
@@ -449,6 +452,7 @@ void e55_destroy(e55_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   e55host::packer_destroy(c->packer);
   cudaFreeHost(c->h_bits); cudaFreeHost(c->h_scale);
+  cudaFreeHost(c->h_req); cudaFreeHost(c->h_ans); cudaFree(c->d_req); cudaFree(c->d_ans);
   free_weights(c);
   free_buffers(c);
   if (c->ev0) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); }
@@ -736,20 +740,43 @@ int e55_predict_packed_moves(e55_ctx* c, const uint32_t* bits, const float* scal
     if (move_index[j] >= kPolicyCh * kSq) return fail(c, E55_ERR_INVALID, "move index outside the 1725 policy entries");
   std::lock_guard<std::mutex> lk(c->mu);
   E55_CUDA(c, cudaSetDevice(c->device));
-  if ((rc = ensure_capacity(c, std::max(n, (total + e55_ctx::kMovesPerPosition - 1) / e55_ctx::kMovesPerPosition)))) return rc;
+  if ((rc = ensure_capacity(c, n))) return rc;
+  // This is the call a single search makes for every leaf batch (latency matters): the whole request travels as ONE
+  // copy from a pinned staging block, the whole answer as ONE copy back.
+  auto up16 = [](size_t x) { return (x + 15) & ~size_t(15); };
   const size_t w = static_cast<size_t>(n) * c->in_planes;
-  E55_CUDA(c, cudaMemcpyAsync(c->d_bits, bits, w * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-  E55_CUDA(c, cudaMemcpyAsync(c->d_scale, scale, w * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-  E55_CUDA(c, cudaMemcpyAsync(c->d_move_off, move_offset, (static_cast<size_t>(n) + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-  if (total) E55_CUDA(c, cudaMemcpyAsync(c->d_move_idx, move_index, static_cast<size_t>(total) * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
-  if ((rc = forward_packed_on(c, c->stream, c->d_bits, c->d_scale, n, 0, c->d_policy, c->d_value))) return rc;
-  e55::legal_priors_kernel<<<(n + 7) / 8, 256, 0, c->stream>>>(c->d_policy, c->d_move_off, c->d_move_idx, c->d_priors, n,
-                                                                    kPolicyCh * kSq);
+  const size_t o_scale = up16(w * 4), o_off = o_scale + up16(w * 4), o_idx = o_off + up16((static_cast<size_t>(n) + 1) * 4);
+  const size_t in_bytes = o_idx + up16(static_cast<size_t>(total) * 2);
+  const size_t o_value = up16(static_cast<size_t>(total) * 4), out_bytes = o_value + up16(static_cast<size_t>(n) * 4);
+  if (in_bytes > c->req_cap || out_bytes > c->ans_cap) {
+    E55_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFreeHost(c->h_req); cudaFreeHost(c->h_ans); cudaFree(c->d_req); cudaFree(c->d_ans);
+    c->h_req = c->h_ans = c->d_req = c->d_ans = nullptr;
+    c->req_cap = c->ans_cap = 0;
+    const size_t rq = std::max<size_t>(2 * in_bytes, 1 << 16), an = std::max<size_t>(2 * out_bytes, 1 << 14);
+    E55_CUDA(c, cudaMallocHost(&c->h_req, rq));
+    E55_CUDA(c, cudaMallocHost(&c->h_ans, an));
+    E55_CUDA(c, cudaMalloc(&c->d_req, rq));
+    E55_CUDA(c, cudaMalloc(&c->d_ans, an));
+    c->req_cap = rq; c->ans_cap = an;
+  }
+  memcpy(c->h_req, bits, w * 4);
+  memcpy(c->h_req + o_scale, scale, w * 4);
+  memcpy(c->h_req + o_off, move_offset, (static_cast<size_t>(n) + 1) * 4);
+  memcpy(c->h_req + o_idx, move_index, static_cast<size_t>(total) * 2);
+  E55_CUDA(c, cudaMemcpyAsync(c->d_req, c->h_req, in_bytes, cudaMemcpyHostToDevice, c->stream));
+  float* d_priors = reinterpret_cast<float*>(c->d_ans);
+  float* d_value = reinterpret_cast<float*>(c->d_ans + o_value);
+  if ((rc = forward_packed_on(c, c->stream, reinterpret_cast<const uint32_t*>(c->d_req), reinterpret_cast<const float*>(c->d_req + o_scale), n, 0,
+                              c->d_policy, d_value))) return rc;
+  e55::legal_priors_kernel<<<(n + 7) / 8, 256, 0, c->stream>>>(c->d_policy, reinterpret_cast<const int32_t*>(c->d_req + o_off),
+                                                                    reinterpret_cast<const uint16_t*>(c->d_req + o_idx), d_priors, n, kPolicyCh * kSq);
   ++c->launches;
   E55_CUDA(c, cudaGetLastError());
-  if (total) E55_CUDA(c, cudaMemcpyAsync(priors, c->d_priors, static_cast<size_t>(total) * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-  E55_CUDA(c, cudaMemcpyAsync(value, c->d_value, static_cast<size_t>(n) * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  E55_CUDA(c, cudaMemcpyAsync(c->h_ans, c->d_ans, out_bytes, cudaMemcpyDeviceToHost, c->stream));
   E55_CUDA(c, cudaStreamSynchronize(c->stream));
+  memcpy(priors, c->h_ans, static_cast<size_t>(total) * 4);
+  memcpy(value, c->h_ans + o_value, static_cast<size_t>(n) * 4);
   return E55_OK;
 }
 

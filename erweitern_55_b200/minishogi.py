@@ -115,9 +115,9 @@ class Position:
         return bits, scale
 
     def to_alphazero_input(self):
-        """Flat 266*25 float list, as ``Network.get_input`` reshapes it (``network.py:255-258``)."""
+        """Flat 266*25 float32 sequence, as ``Network.get_input`` reshapes it (``network.py:255-258``)."""
         bits, scale = self.to_packed_input()
-        return unpack_planes(bits[None], scale[None]).reshape(-1).tolist()
+        return unpack_planes(bits[None], scale[None]).reshape(-1)
 
     def policy_index(self, move) -> int:
         s = move.sfen() if isinstance(move, Move) else str(move)

@@ -152,3 +152,18 @@ def test_network_input_and_policy_index():
     xw = np.asarray(w.to_alphazero_input(), dtype=np.float32).reshape(266, 5, 5)
     assert np.all(xw[264] == 1)
     assert xw[0].sum() == 1 and xw[0, 4, 0] == 1                   # own king appears bottom-left from its own side
+
+
+def test_get_inputs_fast_path_equals_the_reference_loop():
+    """Network.get_inputs on this package's positions (one native encode) == the reference's per-position loop over
+    to_alphazero_input() (network.py:255-274)."""
+    from erweitern_55_b200.network import Network
+    rng = random.Random(5)
+    positions, p = [], Position()
+    for _ in range(12):
+        moves = p.generate_moves()
+        p.do_move(rng.choice(moves))
+        positions.append(p.copy(True))
+    fast = Network.get_inputs.__get__(type("N", (), {"input_shape": [266, 5, 5]})())(positions)
+    slow = np.stack([np.reshape(q.to_alphazero_input(), [266, 5, 5]) for q in positions]).astype(np.float32)
+    assert fast.dtype == np.float32 and fast.shape == (12, 266, 5, 5) and np.array_equal(fast, slow)
