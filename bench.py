@@ -180,7 +180,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--selfplay-workers", type=int, default=128, help="0 = skip the synthetic self-play load")
     ap.add_argument("--selfplay-moves", type=int, default=8, help="moves per worker thread in the synthetic self-play run")
-    ap.add_argument("--selfplay-total-moves", type=int, default=16000, help="plies played per GPU in the real self-play run")
+    ap.add_argument("--selfplay-total-moves", type=int, default=24000, help="plies played per GPU in the real self-play run")
     ap.add_argument("--blocks", type=int, default=7, help="residual blocks (20 with --filters 256 = BASELINE configs[4])")
     ap.add_argument("--filters", type=int, default=128, choices=[128, 256])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -387,24 +387,27 @@ def main():
     # ---- synthetic self-play load through the cross-game aggregation service (tree ops excluded) -------
     selfplay = selfplay_real = None
     if args.selfplay_workers > 0 and args.precision == "bf16":
-        net.start_service(max_batch=B, max_wait_us=200)
+        # game threads = this rank's cores minus two (the service's dispatcher and completer); 12 games per thread and a
+        # service batch of ~74 positions per thread keep two batches' worth of leaves in flight (tools/selfplay_real_sweep.py)
+        sp_threads = max(2, len(my_cores) - 2)
+        sp_cap = min(B, max(256, 64 * round(74 * sp_threads / 64)))
+        net.start_service(max_batch=sp_cap, max_wait_us=200)
         net.bench_selfplay(workers=args.selfplay_workers, moves=1, simulations=160, leaf_batch=16)   # warm-up
         barrier()
         mv, ev, mb = net.bench_selfplay(workers=args.selfplay_workers, moves=args.selfplay_moves, simulations=800, leaf_batch=16)
         barrier()
         # real self-play: native minishogi engine + MCTS (800 simulations, leaf batch 16, 7-ply mate search)
         # one worker thread per host core of this rank's share, minus two for the service's dispatcher / completer
-        sp_threads = max(2, len(my_cores) - 2)
         net.selfplay(threads=sp_threads, total_moves=512, simulations=160, leaf_batch=16, mate_depth=7, seed=99 + rank)   # warm-up
         barrier()
         real = net.selfplay(threads=sp_threads, total_moves=args.selfplay_total_moves, simulations=800, leaf_batch=16,
-                            mate_depth=7, seed=1 + rank, games_per_thread=16)
+                            mate_depth=7, seed=1 + rank, games_per_thread=12)
         barrier()
         net.stop_service()
         real_mv, _ = sharding.aggregate(real["moves_per_s"], 1.0, device=dev)
         real_ev, _ = sharding.aggregate(real["evals_per_s"], 1.0, device=dev)
         selfplay_real = {"moves_per_s": real_mv, "evals_per_s": real_ev, "games_rank0": real["games"],
-                         "mean_gpu_batch_rank0": real["mean_gpu_batch"], "threads_per_gpu": sp_threads, "games_in_flight_per_gpu": sp_threads * 16,
+                         "mean_gpu_batch_rank0": real["mean_gpu_batch"], "threads_per_gpu": sp_threads, "games_in_flight_per_gpu": sp_threads * 12, "service_batch_cap": sp_cap,
                          "mean_game_plies_rank0": real["mean_game_plies"],
                          "simulations_per_move": 800, "leaf_batch": 16, "mate_search_plies": 7,
                          "note": "native C++ minishogi engine + batched PUCT search (csrc/minishogi.hpp, mcts.hpp) playing whole "

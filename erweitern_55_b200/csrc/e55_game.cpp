@@ -631,7 +631,7 @@ int e55_selfplay_run_ex(e55_ctx* c, const e55_selfplay_config* cfg_in, e55_selfp
     if (sched_getaffinity(0, sizeof(set), &set) == 0) hw = CPU_COUNT(&set);   // the cores this process may actually use
     resolved.threads = hw > 3 ? hw - 2 : 1;
   }
-  if (resolved.games_per_thread <= 0) resolved.games_per_thread = 16;
+  if (resolved.games_per_thread <= 0) resolved.games_per_thread = 12;   // enough to hide the GPU round trip, few enough to stay in cache
   const e55_selfplay_config* cfg = &resolved;
   if (cfg->total_moves < 1 || cfg->simulations < 1 || cfg->leaf_batch < 1 ||
       cfg->leaf_batch > 256 || cfg->mate_depth < 0 || cfg->max_moves < 1)

@@ -134,7 +134,7 @@ def random_play(max_moves=512, stop_with_checkmate=False, trim_checkmate=False):
 def run_many(nn, threads=0, total_moves=1000, simulations=800, leaf_batch=16, mate_depth=7, reuse_tree=True,
              use_dirichlet=True, num_sampling_moves=10, max_moves=512, seed=1, records=True, games_per_thread=0):
     """Play games on ``threads`` host threads (0: cores - 2) working through a pool of ``threads x games_per_thread``
-    games (0: 16 per thread) kept in flight on the asynchronous evaluation service, until ``total_moves`` plies were played; the service of ``nn`` must be running
+    games (0: 12 per thread; a service batch of about 74 positions per thread suits that) kept in flight on the asynchronous evaluation service, until ``total_moves`` plies were played; the service of ``nn`` must be running
     (``nn.start_service``).  Returns ``(stats dict, [GameRecord of each finished game])``."""
     lib = _capi.load()
     cfg = _capi.SelfplayConfig()
