@@ -293,7 +293,7 @@ struct SelfplayWorker {
           progressed = true;
           if (g.batches_left == 0) {                                             // selfplay.py:63-68
             const int chosen = g.pos.ply < cfg.sampling_moves ? g.m.tree.sample_edge(0, 1.f) : g.m.tree.best_edge(0);
-            const Move next = g.m.tree.edges_of(g.m.tree.nodes[0])[chosen].move;
+            const Move next = g.m.tree.edge_move(0, chosen);
             if (cfg.sink) {                                                      // search.dump(root), selfplay.py:89
               int sum_n;
               float q;
@@ -523,8 +523,7 @@ int e55_mcts_get_playouts(const e55_mcts* m, int node, int child_sum) {
 
 static int edge_move_out(e55_mcts* m, int node, int edge, char* buf, int buflen) {
   if (edge < 0) return 0;
-  const mshogi::Node& nd = m->tree.nodes[node];
-  return copy_out(m->tree.edges_of(nd)[edge].move.sfen(), buf, buflen) == E55_OK ? 1 : E55_ERR_INVALID;
+  return copy_out(m->tree.edge_move(node, edge).sfen(), buf, buflen) == E55_OK ? 1 : E55_ERR_INVALID;
 }
 
 int e55_mcts_best_move(e55_mcts* m, int node, char* buf, int buflen) {

@@ -25,14 +25,28 @@
 
 namespace mshogi {
 
+// 16 bytes per edge: the PUCT scan over a node's children walks these, and a search's working set is mostly edges.
+// (The child node index lives in a parallel array: only the chosen edge needs it.)
 struct Edge {
-  Move move;
   float prior = 0.f;
   float w = 0.f;        // sum of values from the perspective of the side to move at the parent
   int32_t n = 0;
-  int32_t vloss = 0;
-  int32_t child = -1;   // node index, -1 = not created yet
+  uint16_t mv = 0;      // the move, packed: from (31 = drop) | to << 5 | piece << 10 | promotes << 14
+  uint16_t vloss = 0;
+  static uint16_t pack(const Move& m) {
+    return static_cast<uint16_t>((m.is_drop() ? 31 : m.from) | (m.to << 5) | (m.piece << 10) | ((m.promotes ? 1 : 0) << 14));
+  }
+  Move move() const {   // `captured` is not stored: whoever plays the move reads it off the board
+    Move m;
+    const int from = mv & 31;
+    m.from = static_cast<int8_t>(from == 31 ? -1 : from);
+    m.to = static_cast<int8_t>((mv >> 5) & 31);
+    m.piece = static_cast<int8_t>((mv >> 10) & 15);
+    m.promotes = static_cast<int8_t>((mv >> 14) & 1);
+    return m;
+  }
 };
+static_assert(sizeof(Edge) == 16, "edge layout");
 
 struct Node {
   int32_t parent = -1;          // node index of the parent (-1: root)
@@ -56,6 +70,7 @@ class Mcts {
   size_t capacity_bytes = size_t(1) << 28;
   std::vector<Node> nodes;
   std::vector<Edge> edges;      // pool; cleared, not freed, between searches
+  std::vector<int32_t> child;   // per edge: node index, -1 = not created yet
   std::mt19937_64 rng{0x55ULL};
 
   Mcts() { clear(); }
@@ -63,16 +78,17 @@ class Mcts {
   void set_memory(double gb) { capacity_bytes = gb > 0 ? static_cast<size_t>(gb * 1073741824.0) : (size_t(1) << 28); }
 
   void clear() {
-    nodes.clear(); edges.clear(); nodes.emplace_back();
-    if (nodes.capacity() < 4096) { nodes.reserve(4096); edges.reserve(65536); }   // one 800-simulation search without regrowth
+    nodes.clear(); edges.clear(); child.clear(); nodes.emplace_back();
+    if (nodes.capacity() < 4096) { nodes.reserve(4096); edges.reserve(65536); child.reserve(65536); }   // one 800-simulation search without regrowth
     root_ply_ = -1; root_hash_ = game_hash_ = 0;
   }
   int32_t root() const { return 0; }
   bool valid(int32_t node) const { return node >= 0 && node < static_cast<int32_t>(nodes.size()); }
+  Move edge_move(int32_t node, int i) const { return edges[nodes[node].first_edge + i].move(); }
   Edge* edges_of(const Node& nd) { return edges.data() + nd.first_edge; }
   const Edge* edges_of(const Node& nd) const { return edges.data() + nd.first_edge; }
   double usage() const {
-    return static_cast<double>(nodes.size() * sizeof(Node) + edges.size() * sizeof(Edge)) / static_cast<double>(capacity_bytes);
+    return static_cast<double>(nodes.size() * sizeof(Node) + edges.size() * (sizeof(Edge) + sizeof(int32_t))) / static_cast<double>(capacity_bytes);
   }
   int node_count() const { return static_cast<int>(nodes.size()); }
 
@@ -87,7 +103,7 @@ class Mcts {
         int32_t next = -1;
         if (nd.expanded && !nd.terminal)
           for (int e = 0; e < nd.n_edges; ++e)
-            if (edges[nd.first_edge + e].move == pos.entry(i).move) { next = edges[nd.first_edge + e].child; break; }
+            if (edges[nd.first_edge + e].mv == Edge::pack(pos.entry(i).move)) { next = child[nd.first_edge + e]; break; }
         node = next;
       }
       if (node >= 0) {
@@ -140,16 +156,18 @@ class Mcts {
         }
       }
       Edge& e = ed[best];
-      ++e.vloss;
+      if (e.vloss < 0xFFFF) ++e.vloss;
+      int32_t& ch = child[nd.first_edge + best];
+      const Move mv = e.move();   // (do_move reads the captured piece off the board)
       // whether the move gives check is known from the child's expansion; only moves into new leaves have to look
-      pos.do_move(e.move, e.child >= 0 && nodes[e.child].expanded ? static_cast<int>(nodes[e.child].in_check) : -1);
-      if (e.child < 0) {
-        e.child = static_cast<int32_t>(nodes.size());
+      pos.do_move(mv, ch >= 0 && nodes[ch].expanded ? static_cast<int>(nodes[ch].in_check) : -1);
+      if (ch < 0) {
+        ch = static_cast<int32_t>(nodes.size());
         nodes.emplace_back();
         nodes.back().parent = node;
         nodes.back().parent_edge = nd.first_edge + best;
       }
-      node = e.child;
+      node = ch;
     }
     return node;
   }
@@ -280,8 +298,8 @@ class Mcts {
       const Edge& e = edges[nd.first_edge + b];
       if (e.n == 0) break;
       if (first) { q = e.w / static_cast<float>(e.n); first = false; }
-      pv.push_back(e.move);
-      node = e.child;
+      pv.push_back(e.move());
+      node = child[nd.first_edge + b];
     }
   }
 
@@ -317,7 +335,7 @@ class Mcts {
     }
     for (int i = 0; i < nd.n_edges; ++i) {
       sum_n += cnt[i];
-      if (cnt[i] > 0 || !remove_zeros) out.emplace_back(ed[i].move, cnt[i]);
+      if (cnt[i] > 0 || !remove_zeros) out.emplace_back(ed[i].move(), cnt[i]);
     }
   }
 
@@ -330,7 +348,7 @@ class Mcts {
     std::string s = "playouts " + std::to_string(playouts(node, true)) + " value " + std::to_string(nd.value) + "\n";
     for (int i : order) {
       char line[128];
-      snprintf(line, sizeof(line), "  %-6s N %6d  Q %.4f  P %.4f\n", ed[i].move.sfen().c_str(), ed[i].n,
+      snprintf(line, sizeof(line), "  %-6s N %6d  Q %.4f  P %.4f\n", ed[i].move().sfen().c_str(), ed[i].n,
                ed[i].n > 0 ? ed[i].w / static_cast<float>(ed[i].n) : 0.f, ed[i].prior);
       s += line;
     }
@@ -351,12 +369,12 @@ class Mcts {
       const Node& nd = nodes[cur];
       if (nd.parent >= 0 && cur != node) {
         const Edge& e = edges[nd.parent_edge];
-        s += "  n" + std::to_string(nd.parent) + " -> n" + std::to_string(cur) + " [label=\"" + e.move.sfen() + "\"];\n";
+        s += "  n" + std::to_string(nd.parent) + " -> n" + std::to_string(cur) + " [label=\"" + e.move().sfen() + "\"];\n";
       }
       s += "  n" + std::to_string(cur) + " [label=\"N " + std::to_string(nd.n) + "\\nV " + std::to_string(nd.value).substr(0, 5) + "\"];\n";
       if (nd.expanded && !nd.terminal)
         for (int i = 0; i < nd.n_edges; ++i)
-          if (edges[nd.first_edge + i].child >= 0 && edges[nd.first_edge + i].n > 0) frontier.push_back(edges[nd.first_edge + i].child);
+          if (child[nd.first_edge + i] >= 0 && edges[nd.first_edge + i].n > 0) frontier.push_back(child[nd.first_edge + i]);
     }
     return s + "}\n";
   }
@@ -375,8 +393,9 @@ class Mcts {
     nd.in_check = moves.in_check;
     nd.expanded = true;
     edges.resize(edges.size() + moves.size());
+    child.resize(edges.size(), -1);
     Edge* ed = edges.data() + nd.first_edge;
-    for (int i = 0; i < moves.size(); ++i) { ed[i] = Edge(); ed[i].move = moves.m[i]; }
+    for (int i = 0; i < moves.size(); ++i) { ed[i] = Edge(); ed[i].mv = Edge::pack(moves.m[i]); }
     return ed;
   }
 
@@ -397,8 +416,10 @@ class Mcts {
   void compact(int32_t new_root) {
     std::vector<Node> nn;
     std::vector<Edge> ne;
+    std::vector<int32_t> nc;
     nn.reserve(std::max<size_t>(4096, nodes.size() / 2));      // room for the next search: no regrowth copies
     ne.reserve(std::max<size_t>(65536, edges.size() / 2));
+    nc.reserve(ne.capacity());
     std::vector<int32_t> old_of;           // new index -> old index
     old_of.push_back(new_root);
     nn.push_back(nodes[new_root]);
@@ -412,19 +433,22 @@ class Mcts {
       for (int e = 0; e < src.n_edges; ++e) {
         Edge ed = edges[src.first_edge + e];
         ed.vloss = 0;
-        if (ed.child >= 0) {
-          const int32_t nc = static_cast<int32_t>(nn.size());
-          old_of.push_back(ed.child);
-          nn.push_back(nodes[ed.child]);
+        const int32_t old_child = child[src.first_edge + e];
+        int32_t new_child = -1;
+        if (old_child >= 0) {
+          new_child = static_cast<int32_t>(nn.size());
+          old_of.push_back(old_child);
+          nn.push_back(nodes[old_child]);
           nn.back().parent = static_cast<int32_t>(i);
           nn.back().parent_edge = first + e;
-          ed.child = nc;
         }
         ne.push_back(ed);
+        nc.push_back(new_child);
       }
     }
     nodes.swap(nn);
     edges.swap(ne);
+    child.swap(nc);
   }
 };
 

@@ -439,7 +439,9 @@ class Position {
   }
 
   // gives_check: 1 / 0 when the caller already knows whether the move checks (a search tree does), -1 to find out.
-  void do_move(const Move& m, int gives_check = -1) {
+  void do_move(const Move& mv, int gives_check = -1) {
+    Move m = mv;
+    if (!m.is_drop()) m.captured = static_cast<int8_t>(type_of(board[m.to]));   // whatever the caller knew: the board decides
     const uint64_t h = hash_after(m);
     apply(m);
     ++ply;
