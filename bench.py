@@ -178,7 +178,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--selfplay-workers", type=int, default=128, help="0 = skip the synthetic self-play load")
+    ap.add_argument("--selfplay-workers", type=int, default=1, help="0 = skip the self-play runs")
     ap.add_argument("--selfplay-moves", type=int, default=8, help="moves per worker thread in the synthetic self-play run")
     ap.add_argument("--selfplay-total-moves", type=int, default=24000, help="plies played per GPU in the real self-play run")
     ap.add_argument("--blocks", type=int, default=7, help="residual blocks (20 with --filters 256 = BASELINE configs[4])")
@@ -392,9 +392,9 @@ def main():
         sp_threads = max(2, len(my_cores) - 2)
         sp_cap = min(B, max(256, 64 * round(74 * sp_threads / 64)))
         net.start_service(max_batch=sp_cap, max_wait_us=200)
-        net.bench_selfplay(workers=args.selfplay_workers, moves=1, simulations=160, leaf_batch=16)   # warm-up
+        net.bench_selfplay(workers=sp_threads, moves=1, simulations=160, leaf_batch=16)   # warm-up
         barrier()
-        mv, ev, mb = net.bench_selfplay(workers=args.selfplay_workers, moves=args.selfplay_moves, simulations=800, leaf_batch=16)
+        mv, ev, mb = net.bench_selfplay(workers=sp_threads, moves=args.selfplay_moves * 40, simulations=800, leaf_batch=16)
         barrier()
         # real self-play: native minishogi engine + MCTS (800 simulations, leaf batch 16, 7-ply mate search)
         # one worker thread per host core of this rank's share, minus two for the service's dispatcher / completer
@@ -418,10 +418,10 @@ def main():
         tot_ev, _ = sharding.aggregate(ev, 1.0, device=dev)
         tot_mv, _ = sharding.aggregate(mv, 1.0, device=dev)
         selfplay = {"moves_per_s": tot_mv, "evals_per_s": tot_ev, "mean_gpu_batch_rank0": mb,
-                    "workers_per_gpu": args.selfplay_workers, "simulations_per_move": 800, "leaf_batch": 16,
-                    "note": "synthetic: host threads drive the network like mcts.MCTS.run (1 root + 800/16 leaf batches per "
-                            "move, mcts.py:57-58,70,91-106) on random bit-packed positions through e55_service_predict_packed; "
-                            "tree operations and move generation (minishogilib, absent) are not included"}
+                    "workers_per_gpu": sp_threads, "simulations_per_move": 800, "leaf_batch": 16,
+                    "note": "synthetic: what the evaluation service itself sustains -- host threads keep 16-position requests "
+                            "(bit-packed planes + 30 legal moves each, the shape mcts.MCTS.run produces, mcts.py:91-106) in flight on "
+                            "asynchronous tickets; no tree work, no move generation"}
 
     # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------------
     cpu_baseline = None

@@ -6,14 +6,14 @@
 // lock, copies its own input in and later its own output out (so host copies run on the callers' threads), and
 // holds a ticket in between; blocking calls wait on the batch's generation counter (futex-style), asynchronous
 // callers (e55_service_submit_packed_moves / e55_service_fetch) keep several tickets in flight from one thread.
-// Device side (tensor-core path): two device slots with their own stream and buffers, so the H2D copy of batch k+1
-// overlaps the tower kernel of batch k; a dispatcher thread closes and launches batches, a completer thread waits
+// Device side (tensor-core path): three device slots with their own stream and buffers, so the H2D copy of batch k+1
+// overlaps the tower kernel of batch k and the next kernel starts on the SMs the previous one leaves; a dispatcher thread closes and launches batches, a completer thread waits
 // for their events and wakes the readers.  The fp32 path runs one batch at a time on the context stream.
 
 namespace {
 
-constexpr int kStaging = 4;       // host staging batches in the ring
-constexpr int kDeviceSlots = 2;   // batches in flight on the GPU
+constexpr int kStaging = 5;       // host staging batches in the ring
+constexpr int kDeviceSlots = 3;   // batches in flight on the GPU
 
 enum BatchState { kFree = 0, kOpen, kClosed, kDone };
 
@@ -64,7 +64,7 @@ struct e55_service {
   ServiceBatch batch[kStaging];
   DeviceSlot slot[kDeviceSlots];
   int open = -1;                        // index of the batch currently accepting requests (-1: none free)
-  int inflight[kDeviceSlots] = {-1, -1};   // FIFO of launched batches
+  int inflight[kDeviceSlots] = {};         // FIFO of launched batches
   int n_inflight = 0, next_slot = 0;
   int cap = 0, max_wait_us = 0;
   int idle_min = 0;                     // an idle GPU takes a batch of at least this many positions at once
@@ -230,7 +230,7 @@ void service_complete_loop(e55_ctx* c) {
       s->last_complete = std::chrono::steady_clock::now();
       s->t_gpu += std::chrono::duration<double, std::micro>(s->last_complete - s->launched_at[s->inflight[0]]).count();
     }
-    s->inflight[0] = s->inflight[1];
+    for (int i = 1; i < s->n_inflight; ++i) s->inflight[i - 1] = s->inflight[i];
     --s->n_inflight;
     service_finish(s, b, rc);
     s->cv_slot.notify_one();
@@ -470,16 +470,18 @@ int e55_service_stats(e55_ctx* c, int64_t* batches_out, int64_t* positions_out) 
   return E55_OK;
 }
 
-// Synthetic self-play load (tree operations excluded): `workers` threads each play `moves` moves the way
-// mcts.MCTS.run drives the network -- one root evaluation of batch 1, then simulations / leaf_batch
-// evaluations of leaf_batch positions (mcts.py:57-58,70,91-106) -- on random packed positions, all through
-// the evaluation service.
+// Synthetic self-play load (tree operations excluded): what the evaluation service itself sustains.  `workers`
+// threads each keep `leaf_batch`-position requests of the kind the search sends (bit-packed planes + ~30 legal moves
+// per position, mcts.py:91-106) in flight on 48 asynchronous tickets per thread (enough to keep the GPU fed)
+// until every worker has had simulations / leaf_batch requests answered for each of its `moves` moves.
 int e55_bench_selfplay(e55_ctx* c, int workers, int moves, int simulations, int leaf_batch, double* moves_per_s_out,
                        double* evals_per_s_out, double* mean_batch_out) {
-  if (!c || workers < 1 || moves < 1 || simulations < 1 || leaf_batch < 1 || !moves_per_s_out || !evals_per_s_out || !mean_batch_out)
+  if (!c || workers < 1 || moves < 1 || simulations < 1 || leaf_batch < 1 || leaf_batch > 256 || !moves_per_s_out || !evals_per_s_out || !mean_batch_out)
     return E55_ERR_INVALID;
   if (!c->service) return fail(c, E55_ERR_INVALID, "evaluation service is not running");
   const int ip = c->in_planes;
+  constexpr int kMaxTickets = 64, kMovesPerPosition = 30;
+  const int kTickets = getenv("E55_BENCH_TICKETS") ? std::min(kMaxTickets, std::max(1, atoi(getenv("E55_BENCH_TICKETS")))) : 48;
   std::atomic<int> failures{0};
   int64_t b0 = 0, p0 = 0, b1 = 0, p1 = 0;
   e55_service_stats(c, &b0, &p0);
@@ -488,15 +490,42 @@ int e55_bench_selfplay(e55_ctx* c, int workers, int moves, int simulations, int 
   for (int w = 0; w < workers; ++w)
     th.emplace_back([&, w] {
       std::vector<uint32_t> bits(static_cast<size_t>(leaf_batch) * ip);
-      std::vector<float> scale(bits.size(), 1.f), policy(static_cast<size_t>(leaf_batch) * kPolicyCh * kSq), value(leaf_batch);
+      std::vector<float> scale(bits.size(), 1.f), priors(static_cast<size_t>(leaf_batch) * kMovesPerPosition), value(leaf_batch);
+      std::vector<int32_t> off(leaf_batch + 1);
+      std::vector<uint16_t> idx(priors.size());
       uint32_t x = 0x9E3779B9u * (w + 1);
       for (auto& v : bits) { x = x * 1664525u + 1013904223u; v = (x >> 7) & (x >> 13) & (x >> 19) & 0x1FFFFFFu; }  // ~12 % density
-      const int iters = (simulations + leaf_batch - 1) / leaf_batch;
-      for (int mv = 0; mv < moves && !failures.load(); ++mv) {
-        if (e55_service_predict_packed(c, bits.data(), scale.data(), 1, policy.data(), value.data()) != E55_OK) { ++failures; break; }
-        for (int it = 0; it < iters; ++it)
-          if (e55_service_predict_packed(c, bits.data(), scale.data(), leaf_batch, policy.data(), value.data()) != E55_OK) { ++failures; break; }
+      for (int i = 0; i <= leaf_batch; ++i) off[i] = i * kMovesPerPosition;
+      for (auto& v : idx) { x = x * 1664525u + 1013904223u; v = static_cast<uint16_t>((x >> 8) % (kPolicyCh * kSq)); }
+      const long requests = static_cast<long>(moves) * ((simulations + leaf_batch - 1) / leaf_batch);
+      Ticket tickets[kMaxTickets];
+      bool live[kMaxTickets] = {};
+      long sent = 0, answered = 0;
+      while (answered < requests && !failures.load()) {
+        bool progressed = false;
+        int oldest = -1;
+        for (int k = 0; k < kTickets; ++k) {
+          if (live[k]) {
+            const int rc = service_fetch(c, tickets[k], priors.data(), value.data(), false);
+            if (rc == E55_PENDING) { if (oldest < 0 || tickets[k].gen < tickets[oldest].gen) oldest = k; continue; }
+            if (rc != E55_OK) { ++failures; break; }
+            live[k] = false; ++answered; progressed = true;
+          }
+          if (!live[k] && sent < requests) {
+            const int rc = service_submit(c, 3, nullptr, bits.data(), scale.data(), leaf_batch, off.data(), idx.data(), false, &tickets[k]);
+            if (rc == E55_OK) { live[k] = true; ++sent; progressed = true; }
+            else if (rc != E55_PENDING) { ++failures; break; }
+          }
+        }
+        if (!progressed && oldest >= 0) {   // nothing moved: sleep on an outstanding answer
+          if (service_fetch(c, tickets[oldest], priors.data(), value.data(), true) != E55_OK) { ++failures; break; }
+          live[oldest] = false; ++answered;
+        } else if (!progressed) {
+          std::this_thread::yield();
+        }
       }
+      for (int k = 0; k < kTickets; ++k)     // every ticket has to be fetched
+        if (live[k]) service_fetch(c, tickets[k], priors.data(), value.data(), true);
     });
   for (auto& t : th) t.join();
   const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

@@ -137,9 +137,10 @@ int e55_service_submit_packed_moves(e55_ctx* ctx, const uint32_t* bits, const fl
 int e55_service_fetch(e55_ctx* ctx, const e55_ticket* ticket, float* priors, float* value, int wait);
 int e55_service_stats(e55_ctx* ctx, int64_t* batches_out, int64_t* positions_out);
 
-/* Synthetic self-play load on the running service, tree operations excluded: `workers` host threads each play
- * `moves` moves the way mcts.MCTS.run drives the network (one root evaluation, then simulations/leaf_batch
- * evaluations of leaf_batch positions; mcts.py:57-58,70,91-106) on random bit-packed positions. */
+/* Synthetic self-play load on the running service, tree operations excluded (what the service itself sustains):
+ * `workers` host threads each keep leaf_batch-position requests of the kind the search sends (bit-packed planes + 30
+ * legal moves per position; mcts.py:91-106) in flight on 48 asynchronous tickets until simulations/leaf_batch requests
+ * per move have been answered for `moves` moves. */
 int e55_bench_selfplay(e55_ctx* ctx, int workers, int moves, int simulations, int leaf_batch,
                        double* moves_per_s_out, double* evals_per_s_out, double* mean_batch_out);
 
