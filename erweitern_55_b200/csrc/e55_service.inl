@@ -36,6 +36,7 @@ struct ServiceBatch {
   std::atomic<uint64_t> generation{0};      // bumped when the batch's results are ready
   int status = 0;               // result code of the forward
   cudaEvent_t done = nullptr;
+  cudaEvent_t k0 = nullptr, k1 = nullptr;   // E55_SERVICE_TRACE: around the kernels of the batch
   std::chrono::steady_clock::time_point first_arrival;
 };
 
@@ -73,7 +74,9 @@ struct e55_service {
   int64_t n_batches = 0, n_positions = 0;
   // E55_SERVICE_TRACE=1: where a batch spends its time (microseconds, summed over batches; printed at stop)
   bool trace = false;
-  double t_fill = 0, t_slot = 0, t_copywait = 0, t_launch = 0, t_gpu = 0, t_idle = 0;
+  double t_fill = 0, t_slot = 0, t_copywait = 0, t_launch = 0, t_gpu = 0, t_idle = 0, t_kernels = 0, t_interval = 0;
+  int64_t n_kernels = 0;
+  cudaEvent_t prev_k1 = nullptr;
   std::chrono::steady_clock::time_point launched_at[kStaging], last_complete;
   int64_t closed_full = 0, closed_idle = 0, closed_timeout = 0, closed_forced = 0;
 };
@@ -108,6 +111,7 @@ int service_launch(e55_ctx* c, e55_service* s, ServiceBatch& b, int slot_index) 
       if (b.moves_reserved)
         E55_CUDA(c, cudaMemcpyAsync(d.move_idx, b.move_idx, static_cast<size_t>(b.moves_reserved) * sizeof(uint16_t), cudaMemcpyHostToDevice, d.stream));
     }
+    if (s->trace) cudaEventRecord(b.k0, d.stream);
     rc = forward_packed_on(c, d.stream, d.bits, d.scale, n, 0, d.policy, d.value);
   }
   if (rc) return rc;
@@ -115,6 +119,7 @@ int service_launch(e55_ctx* c, e55_service* s, ServiceBatch& b, int slot_index) 
     e55::legal_priors_kernel<<<(n + 7) / 8, 256, 0, d.stream>>>(d.policy, d.move_off, d.move_idx, d.priors, n, kPolicyCh * kSq);
     ++c->launches;
     E55_CUDA(c, cudaGetLastError());
+    if (s->trace) cudaEventRecord(b.k1, d.stream);
     if (b.moves_reserved)
       E55_CUDA(c, cudaMemcpyAsync(b.priors, d.priors, static_cast<size_t>(b.moves_reserved) * sizeof(float), cudaMemcpyDeviceToHost, d.stream));
   } else {
@@ -227,6 +232,10 @@ void service_complete_loop(e55_ctx* c) {
     }
     lk.lock();
     if (s->trace) {
+      float ms = 0.f;
+      if (b.kind == 3 && cudaEventElapsedTime(&ms, b.k0, b.k1) == cudaSuccess) { s->t_kernels += ms * 1e3; ++s->n_kernels; }
+      if (s->prev_k1 && b.kind == 3 && cudaEventElapsedTime(&ms, s->prev_k1, b.k1) == cudaSuccess) s->t_interval += ms * 1e3;
+      s->prev_k1 = b.kind == 3 ? b.k1 : nullptr;
       s->last_complete = std::chrono::steady_clock::now();
       s->t_gpu += std::chrono::duration<double, std::micro>(s->last_complete - s->launched_at[s->inflight[0]]).count();
     }
@@ -341,6 +350,8 @@ void service_free(e55_service* s) {
     cudaFreeHost(b.planes); cudaFreeHost(b.bits); cudaFreeHost(b.scale); cudaFreeHost(b.policy); cudaFreeHost(b.value);
     cudaFreeHost(b.move_off); cudaFreeHost(b.move_idx); cudaFreeHost(b.priors);
     if (b.done) cudaEventDestroy(b.done);
+    if (b.k0) cudaEventDestroy(b.k0);
+    if (b.k1) cudaEventDestroy(b.k1);
   }
   for (auto& d : s->slot) {
     cudaFree(d.planes); cudaFree(d.bits); cudaFree(d.scale); cudaFree(d.policy); cudaFree(d.value);
@@ -383,6 +394,8 @@ int e55_service_start(e55_ctx* c, int max_batch, int max_wait_us) {
     if (e == cudaSuccess) e = cudaMallocHost(&b.move_idx, moves * sizeof(uint16_t));
     if (e == cudaSuccess) e = cudaMallocHost(&b.priors, moves * sizeof(float));
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreate(&b.k0);
+    if (e == cudaSuccess) e = cudaEventCreate(&b.k1);
   }
   for (auto& d : s->slot) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
@@ -419,9 +432,10 @@ int e55_service_stop(e55_ctx* c) {
   if (s->trace && s->n_batches > 0) {
     const double nb = static_cast<double>(s->n_batches);
     fprintf(stderr, "[e55 service] %lld batches, mean %.1f positions; per batch (us): fill %.1f, wait for slot %.1f, wait for copies %.1f, "
-            "launch %.1f, launch->complete %.1f, GPU idle before launch %.1f; closed: %lld full, %lld idle-GPU, %lld timeout, %lld forced\n",
+            "launch %.1f, launch->complete %.1f, GPU idle before launch %.1f, kernels %.1f, between kernel ends %.1f; closed: %lld full, %lld idle-GPU, %lld timeout, %lld forced\n",
             static_cast<long long>(s->n_batches), static_cast<double>(s->n_positions) / nb, s->t_fill / nb, s->t_slot / nb, s->t_copywait / nb,
-            s->t_launch / nb, s->t_gpu / nb, s->t_idle / nb, static_cast<long long>(s->closed_full), static_cast<long long>(s->closed_idle),
+            s->t_launch / nb, s->t_gpu / nb, s->t_idle / nb, s->n_kernels ? s->t_kernels / s->n_kernels : 0.0, s->n_kernels ? s->t_interval / s->n_kernels : 0.0,
+            static_cast<long long>(s->closed_full), static_cast<long long>(s->closed_idle),
             static_cast<long long>(s->closed_timeout), static_cast<long long>(s->closed_forced));
   }
   c->service = nullptr;
