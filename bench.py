@@ -387,9 +387,9 @@ def main():
     # ---- synthetic self-play load through the cross-game aggregation service (tree ops excluded) -------
     selfplay = selfplay_real = None
     if args.selfplay_workers > 0 and args.precision == "bf16":
-        # game threads = this rank's cores minus two (the service's dispatcher and completer); 12 games per thread and a
+        # game threads = this rank's cores minus two (minus one on small hosts) for the service's threads; 12 games per thread and a
         # service batch of ~74 positions per thread keep two batches' worth of leaves in flight (tools/selfplay_real_sweep.py)
-        sp_threads = max(2, len(my_cores) - 2)
+        sp_threads = max(1, len(my_cores) - (2 if len(my_cores) > 12 else 1))
         sp_cap = min(B, max(256, 64 * round(74 * sp_threads / 64)))
         net.start_service(max_batch=sp_cap, max_wait_us=200)
         net.bench_selfplay(workers=sp_threads, moves=1, simulations=160, leaf_batch=16)   # warm-up

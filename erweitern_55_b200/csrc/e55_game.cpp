@@ -624,11 +624,11 @@ void e55_selfplay_default_config(e55_selfplay_config* cfg) {
 int e55_selfplay_run_ex(e55_ctx* c, const e55_selfplay_config* cfg_in, e55_selfplay_stats* out) {
   if (!c || !cfg_in || !out) return E55_ERR_INVALID;
   e55_selfplay_config resolved = *cfg_in;
-  if (resolved.threads <= 0) {   // leave two cores to the service's dispatcher and completer threads
+  if (resolved.threads <= 0) {   // leave room for the service's dispatcher and completer threads
     cpu_set_t set;
     int hw = static_cast<int>(std::thread::hardware_concurrency());
     if (sched_getaffinity(0, sizeof(set), &set) == 0) hw = CPU_COUNT(&set);   // the cores this process may actually use
-    resolved.threads = hw > 3 ? hw - 2 : 1;
+    resolved.threads = hw > 12 ? hw - 2 : (hw > 1 ? hw - 1 : 1);   // the service's two threads need about one core (a spinning completer beats a sleeping one)
   }
   if (resolved.games_per_thread <= 0) resolved.games_per_thread = 12;   // enough to hide the GPU round trip, few enough to stay in cache
   const e55_selfplay_config* cfg = &resolved;

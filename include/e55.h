@@ -214,7 +214,7 @@ typedef struct e55_selfplay_stats {
 typedef void (*e55_game_sink)(void* user, const char* record);
 
 typedef struct e55_selfplay_config {
-  int threads;             /* host threads; 0 = cores - 2 (the service's dispatcher and completer need the rest) */
+  int threads;             /* host threads; 0 = cores - 2 (cores - 1 on hosts of 12 cores or fewer): the service's threads need the rest */
   int games_per_thread;    /* games per thread in the shared pool kept in flight on the asynchronous service; 0 = 12
                               (best with a service batch of about 74 positions per thread: two batches' worth of leaves in flight) */
   long total_moves;        /* stop after this many plies in total */
