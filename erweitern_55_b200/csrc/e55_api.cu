@@ -23,6 +23,7 @@
 #include "e55_fp32.cuh"
 #include "e55_tc.cuh"
 #include "e55_umma_test.cuh"
+#include "e55_gpu_selfplay.cuh"
 
 namespace {
 
@@ -1023,3 +1024,4 @@ int e55_bench_umma(int device, int n_dim, int iters, float* tflops_out) {
 }  // extern "C"
 
 #include "e55_service.inl"
+#include "e55_gpu_selfplay.inl"

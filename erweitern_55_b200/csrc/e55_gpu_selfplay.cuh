@@ -1,0 +1,522 @@
+// GPU-resident self-play: the whole loop of selfplay.run / mcts.MCTS.run -- tree descent
+// with virtual loss, move generation, repetition test, input encoding, expansion, back-up, move choice -- runs on the
+// GPU next to the network, one thread per game, thousands of games at once.  The host only launches kernels: no
+// positions, planes, priors or trees cross PCIe, and the number of host cores stops mattering (the host-side driver
+// of e55_game.cpp needs ~1.5 ms of a core per move; an 8-GPU box with four cores per GPU starves it).
+//
+// One round = what one iteration of MCTS.run's main loop does for every game (mcts.py:91-110):
+//   select_kernel   per game: kLeaf selections with virtual loss; each new leaf gets its terminal test, its legal
+//                   moves (stored as the node's edges straight away) and its bit-packed planes in a batch slot
+//   tower_kernel    all slots of all games in one launch (e55_tc.cuh), then legal_priors_strided_kernel
+//   expand_kernel   per game: priors and values into the new nodes, back-up of every selection; after the last
+//                   simulation of a move: choose it (sampled from the visit counts for the first plies), play it,
+//                   test for the end of the game, start the next search (or the next game)
+// Rules, encoding and policy indexing are the very functions the host engine uses (minishogi.hpp, compiled for the
+// device); the search follows csrc/mcts.hpp.  Differences to the host driver: no tree reuse between moves and the
+// root evaluation takes a round of its own.  Included by e55_api.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "minishogi.hpp"
+
+namespace e55 {
+namespace gs {
+
+using namespace mshogi;
+
+constexpr int kLeaf = 16;              // selections per game per round (Config.batch_size, mcts.py:13)
+constexpr int kMaxPly = 512;           // selfplay.run's max_moves
+constexpr int kMaxNodes = 1200;        // per game and search: root + one new node per simulation (<= 1024) + slack
+constexpr int kMaxEdges = 56 * 1024;   // per game and search
+constexpr int kMoveStride = 256;       // move-list slots per batch position (MoveList capacity: nothing is ever cut)
+constexpr int kMaxPath = 96;           // deepest descent below the root
+constexpr int kRecordMoves = 256;      // moves kept per recorded game (validation)
+
+struct GNode {
+  int32_t parent, parent_edge, first_edge;
+  int32_t n;
+  float value;
+  int16_t n_edges;
+  uint8_t expanded, terminal, claimed, in_check;
+};
+
+struct GEdge {            // as mshogi::Edge (csrc/mcts.hpp)
+  float prior, w;
+  int32_t n;
+  uint16_t mv, vloss;
+};
+
+__host__ __device__ inline uint16_t pack_move(const Move& m) {
+  return static_cast<uint16_t>((m.is_drop() ? 31 : m.from) | (m.to << 5) | (m.piece << 10) | ((m.promotes ? 1 : 0) << 14));
+}
+__host__ __device__ inline Move unpack_move(uint16_t mv) {
+  Move m;
+  const int from = mv & 31;
+  m.from = static_cast<int8_t>(from == 31 ? -1 : from);
+  m.to = static_cast<int8_t>((mv >> 5) & 31);
+  m.piece = static_cast<int8_t>((mv >> 10) & 15);
+  m.promotes = static_cast<int8_t>((mv >> 14) & 1);
+  return m;
+}
+
+struct Game {
+  Board root;                          // the position being searched (root.ply = plies played)
+  uint64_t hashes[kMaxPly + 2];        // key of the position after each ply of the game
+  uint8_t gave_check[kMaxPly + 2];
+  uint8_t rep_count[kMaxPly + 2];
+  Snapshot snaps[kHistory];            // the last 8 positions, slot = ply % 8
+  uint16_t moves[kMaxPly];             // the game so far
+  uint64_t rng;
+  int32_t n_nodes, n_edges;
+  int32_t sims_done;                   // simulations of the current search (-1: the root is not evaluated yet)
+  int32_t leaf[kLeaf];                 // this round's selections
+  int32_t games_finished;
+};
+
+struct Shared {                        // counters of the whole run
+  unsigned long long moves, evals, games, plies_in_finished_games, pool_overflows;
+  int n_records;
+};
+
+struct Params {
+  Game* games;
+  GNode* nodes;        // [n_games][kMaxNodes]
+  GEdge* edges;        // [n_games][kMaxEdges]
+  int32_t* child;      // [n_games][kMaxEdges]
+  uint32_t* bits;      // [n_games * kLeaf][266]
+  float* scale;
+  uint16_t* move_idx;  // [n_games * kLeaf][kMoveStride]
+  int32_t* move_cnt;   // [n_games * kLeaf]   (0: slot not used this round)
+  float* priors;       // [n_games * kLeaf][kMoveStride]
+  float* value;        // [n_games * kLeaf]
+  Shared* shared;
+  uint16_t* records;   // [record_cap][kRecordMoves + 2]: ply, winner, moves...
+  int n_games, simulations, use_dirichlet, sampling_moves, max_moves, record_cap;
+  long long move_budget;
+  float c_puct, dirichlet_alpha, dirichlet_eps;
+};
+
+// ---- small device helpers ---------------------------------------------------------------------------------------
+__device__ inline uint64_t next_u64(uint64_t& s) {   // xorshift64*
+  s ^= s >> 12; s ^= s << 25; s ^= s >> 27;
+  return s * 0x2545F4914F6CDD1Dull;
+}
+__device__ inline float next_unit(uint64_t& s) { return (static_cast<float>(next_u64(s) >> 40) + 0.5f) * (1.f / 16777216.f); }
+__device__ inline float next_normal(uint64_t& s) {
+  const float u1 = next_unit(s), u2 = next_unit(s);
+  return sqrtf(-2.f * logf(u1)) * cosf(6.28318530718f * u2);
+}
+__device__ inline float next_gamma(uint64_t& s, float alpha) {   // Marsaglia-Tsang; alpha < 1 through gamma(alpha + 1)
+  const float boost = alpha < 1.f ? powf(next_unit(s), 1.f / alpha) : 1.f;
+  const float a = alpha < 1.f ? alpha + 1.f : alpha;
+  const float d = a - 1.f / 3.f, c = 1.f / sqrtf(9.f * d);
+  for (int it = 0; it < 64; ++it) {
+    const float x = next_normal(s), v0 = 1.f + c * x;
+    if (v0 <= 0.f) continue;
+    const float v = v0 * v0 * v0, u = next_unit(s);
+    if (logf(u) < 0.5f * x * x + d - d * v + d * logf(v)) return d * v * boost;
+  }
+  return d * boost;
+}
+
+__device__ inline void take_snapshot(const Board& b, Snapshot& sn, int rep) {
+  for (int c = 0; c < 2; ++c)
+    for (int t = 1; t < PIECE_TYPES; ++t) sn.pieces[c][t - 1] = b.bb[c][t];
+  for (int c = 0; c < 2; ++c)
+    for (int k = 0; k < kHandTypes; ++k) sn.hand[c][k] = b.hand[c][k];
+  sn.rep_count = static_cast<uint8_t>(rep > 255 ? 255 : rep);
+}
+
+// The history a descent sees: the game's plies [0, ply0] in global memory, then the path below the root in local
+// arrays.  Index = ply.
+struct PathView {
+  const Game* g;
+  int ply0, depth;                   // depth = plies below the root
+  uint64_t hash[kMaxPath + 1];       // [1..depth]
+  uint8_t check[kMaxPath + 1];
+  uint8_t rep[kMaxPath + 1];
+  Snapshot snap[kHistory];           // snapshots of the path positions, slot = ply % 8 (only the last 8 matter)
+  __device__ uint64_t key(int ply) const { return ply <= ply0 ? g->hashes[ply] : hash[ply - ply0]; }
+  __device__ bool gave_check(int ply) const { return ply <= ply0 ? g->gave_check[ply] != 0 : check[ply - ply0] != 0; }
+  __device__ int rep_count(int ply) const { return ply <= ply0 ? g->rep_count[ply] : rep[ply - ply0]; }
+  __device__ const Snapshot& snapshot(int ply) const { return ply <= ply0 ? g->snaps[ply % kHistory] : snap[ply % kHistory]; }
+  __device__ int last() const { return ply0 + depth; }
+};
+
+// Position::push_history for a descent: key, check flag, repetition count, snapshot of the position after `m`.
+__device__ inline void path_push(PathView& pv, const Board& after, uint64_t key, bool check) {
+  const int d = ++pv.depth, ply = pv.ply0 + d;
+  pv.hash[d] = key;
+  pv.check[d] = check ? 1 : 0;
+  int c = 1;
+  for (int i = ply - 2; i >= 0; i -= 2)
+    if (pv.key(i) == key) { c += pv.rep_count(i); break; }
+  pv.rep[d] = static_cast<uint8_t>(c > 255 ? 255 : c);
+  take_snapshot(after, pv.snap[ply % kHistory], c);
+}
+
+// Position::is_repetition on a PathView (minishogi.hpp): fourth occurrence = repetition; a side all of whose moves
+// since the first occurrence gave check is the perpetual checker.
+__device__ inline void path_repetition(const PathView& pv, bool& rep, bool& my_check, bool& op_check) {
+  rep = my_check = op_check = false;
+  const int last = pv.last();
+  if (pv.rep_count(last) < 4) return;
+  const uint64_t h = pv.key(last);
+  int first = last;
+  for (int i = last; i >= 0; i -= 2)
+    if (pv.key(i) == h) first = i;
+  rep = true;
+  bool mine = true, theirs = true, any_mine = false, any_theirs = false;
+  for (int i = first + 1; i <= last; ++i) {
+    const bool mover_is_me = ((last - i) & 1) == 1;
+    if (mover_is_me) { any_mine = true; mine = mine && pv.gave_check(i); }
+    else { any_theirs = true; theirs = theirs && pv.gave_check(i); }
+  }
+  my_check = any_mine && mine;
+  op_check = any_theirs && theirs;
+}
+
+// encode_packed (minishogi.hpp) on a PathView.
+__device__ inline void path_encode(const PathView& pv, const Board& pos, uint32_t* bits, float* scale) {
+  for (int c = 0; c < kInputPlanes; ++c) { bits[c] = 0u; scale[c] = 1.f; }
+  const int me = pos.side, last = pv.last();
+  for (int t = 0; t < kHistory; ++t) {
+    const int idx = last - t;
+    if (idx < 0) break;
+    const Snapshot& sn = pv.snapshot(idx);
+    uint32_t* b = bits + t * kPlanesPerStep;
+    float* sc = scale + t * kPlanesPerStep;
+    if (me == BLACK) {
+      for (int k = 0; k < 10; ++k) { b[k] = sn.pieces[BLACK][k]; b[10 + k] = sn.pieces[WHITE][k]; }
+    } else {
+      for (int k = 0; k < 10; ++k) { b[k] = rotate180(sn.pieces[WHITE][k]); b[10 + k] = rotate180(sn.pieces[BLACK][k]); }
+    }
+    const int rc = sn.rep_count >= 3 ? 3 : sn.rep_count;
+    if (rc >= 1) b[20 + rc - 1] = kAllSquares;
+    for (int k = 0; k < kHandTypes; ++k) {
+      if (sn.hand[me][k]) { b[23 + k] = kAllSquares; sc[23 + k] = sn.hand[me][k] / 2.f; }
+      if (sn.hand[me ^ 1][k]) { b[28 + k] = kAllSquares; sc[28 + k] = sn.hand[me ^ 1][k] / 2.f; }
+    }
+  }
+  if (me == WHITE) bits[264] = kAllSquares;
+  if (pos.ply > 0) { bits[265] = kAllSquares; scale[265] = static_cast<float>(pos.ply > 512 ? 512 : pos.ply) / 512.f; }
+}
+
+// ---- game bookkeeping ---------------------------------------------------------------------------------------------
+__device__ inline void reset_tree(Game& g, GNode* nodes) {
+  g.n_nodes = 1; g.n_edges = 0; g.sims_done = -1;
+  GNode& r = nodes[0];
+  r.parent = -1; r.parent_edge = -1; r.first_edge = 0; r.n = 0; r.value = 0.f; r.n_edges = 0;
+  r.expanded = r.terminal = r.claimed = r.in_check = 0;
+}
+
+__device__ inline void start_game(Game& g, GNode* nodes) {
+  Board& b = g.root;
+  b.clear_board();
+  // rbsgk/4p/5/P4/KGSBR b - 1
+  const PieceType top[5] = {ROOK, BISHOP, SILVER, GOLD, KING}, bottom[5] = {KING, GOLD, SILVER, BISHOP, ROOK};
+  for (int c = 0; c < 5; ++c) { b.put(sq_of(0, c), top[c], WHITE); b.put(sq_of(4, c), bottom[c], BLACK); }
+  b.put(sq_of(1, 4), PAWN, WHITE);
+  b.put(sq_of(3, 0), PAWN, BLACK);
+  g.hashes[0] = b.compute_hash();
+  g.gave_check[0] = 0;
+  g.rep_count[0] = 1;
+  take_snapshot(b, g.snaps[0], 1);
+  reset_tree(g, nodes);
+}
+
+// Position::do_move on the game itself (after a move was chosen).
+__device__ inline void game_play(Game& g, const Move& mv) {
+  Board& b = g.root;
+  Move m = mv;
+  if (!m.is_drop()) m.captured = static_cast<int8_t>(Board::type_of(b.board[m.to]));
+  const uint64_t key = b.hash_after(g.hashes[b.ply], m);
+  g.moves[b.ply] = pack_move(m);
+  b.apply(m);
+  ++b.ply;
+  const int ply = b.ply;
+  g.hashes[ply] = key;
+  g.gave_check[ply] = b.in_check(b.side) ? 1 : 0;
+  int c = 1;
+  for (int i = ply - 2; i >= 0; i -= 2)
+    if (g.hashes[i] == key) { c += g.rep_count[i]; break; }
+  g.rep_count[ply] = static_cast<uint8_t>(c > 255 ? 255 : c);
+  take_snapshot(b, g.snaps[ply % kHistory], c);
+}
+
+// ---- kernels ------------------------------------------------------------------------------------------------------
+__global__ void init_kernel(Params p, uint64_t seed) {
+  const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= p.n_games) return;
+  Game& g = p.games[gi];
+  g.rng = (seed + 0x9E3779B97F4A7C15ull * static_cast<uint64_t>(gi + 1)) | 1ull;
+  for (int i = 0; i < 8; ++i) next_u64(g.rng);
+  g.games_finished = 0;
+  start_game(g, p.nodes + static_cast<size_t>(gi) * kMaxNodes);
+}
+
+// Terminal test of a leaf in the reference's order (selfplay.py:17-31; Mcts::terminal_value).
+__device__ inline bool leaf_terminal(Board& pos, const PathView& pv, MoveList& moves, float& v) {
+  bool rep, my_check, op_check;
+  path_repetition(pv, rep, my_check, op_check);
+  if (my_check) { v = 0.f; return true; }
+  if (op_check) { v = 1.f; return true; }
+  if (rep) { v = pos.side == WHITE ? 1.f : 0.f; return true; }
+  pos.generate_moves(moves);
+  if (moves.empty()) { v = 0.f; return true; }
+  return false;
+}
+
+__global__ void __launch_bounds__(64) select_kernel(Params p) {
+  const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= p.n_games) return;
+  Game& g = p.games[gi];
+  GNode* nodes = p.nodes + static_cast<size_t>(gi) * kMaxNodes;
+  GEdge* edges = p.edges + static_cast<size_t>(gi) * kMaxEdges;
+  int32_t* child = p.child + static_cast<size_t>(gi) * kMaxEdges;
+  PathView pv;
+  MoveList moves;
+  for (int s = 0; s < kLeaf; ++s) {
+    const size_t slot = static_cast<size_t>(gi) * kLeaf + s;
+    p.move_cnt[slot] = 0;
+    Board pos = g.root;
+    pv.g = &g; pv.ply0 = pos.ply; pv.depth = 0;
+    int node = 0;
+    // PUCT descent with virtual loss (Mcts::select_leaf)
+    while (nodes[node].expanded && !nodes[node].terminal && pv.depth < kMaxPath) {
+      const GNode nd = nodes[node];
+      GEdge* ed = edges + nd.first_edge;
+      int total = 0;
+      for (int i = 0; i < nd.n_edges; ++i) total += ed[i].n + ed[i].vloss;
+      const float cs = p.c_puct * sqrtf(static_cast<float>(total) + 1e-8f);
+      int best = 0;
+      float best_score = -1e30f;
+      for (int i = 0; i < nd.n_edges; ++i) {
+        const float nv = static_cast<float>(ed[i].n + ed[i].vloss);
+        const float score = ed[i].w / fmaxf(nv, 1.f) + cs * ed[i].prior / (1.f + nv);
+        if (score > best_score) { best_score = score; best = i; }
+      }
+      GEdge& e = ed[best];
+      if (e.vloss < 0xFFFF) ++e.vloss;
+      Move m = unpack_move(e.mv);
+      m.captured = static_cast<int8_t>(Board::type_of(pos.board[m.to]));
+      const uint64_t key = pos.hash_after(pv.key(pv.last()), m);
+      pos.apply(m);
+      ++pos.ply;
+      int& ch = child[nd.first_edge + best];
+      const bool check = ch >= 0 && nodes[ch].expanded ? nodes[ch].in_check != 0 : pos.in_check(pos.side);
+      path_push(pv, pos, key, check);
+      if (ch < 0) {
+        if (g.n_nodes >= kMaxNodes) { atomicAdd(&p.shared->pool_overflows, 1ull); node = -1; break; }
+        ch = g.n_nodes++;
+        GNode& nn = nodes[ch];
+        nn.parent = node; nn.parent_edge = nd.first_edge + best; nn.first_edge = 0; nn.n = 0; nn.value = 0.5f; nn.n_edges = 0;
+        nn.expanded = nn.terminal = nn.claimed = nn.in_check = 0;
+      }
+      node = ch;
+    }
+    g.leaf[s] = node;
+    if (node < 0) continue;
+    GNode& leaf = nodes[node];
+    if (leaf.expanded || leaf.terminal || leaf.claimed) continue;   // nothing to evaluate (or a duplicate of this round)
+    leaf.claimed = 1;
+    float tv;
+    if (leaf_terminal(pos, pv, moves, tv)) { leaf.terminal = 1; leaf.claimed = 0; leaf.value = tv; continue; }
+    if (g.n_edges + moves.size() > kMaxEdges) {      // out of room: treat as a draw-ish dead end, never evaluated
+      atomicAdd(&p.shared->pool_overflows, 1ull);
+      leaf.terminal = 1; leaf.claimed = 0; leaf.value = 0.5f;
+      continue;
+    }
+    // the legal moves become the node's edges right away; their priors arrive with the network's answer
+    leaf.first_edge = g.n_edges;
+    leaf.n_edges = static_cast<int16_t>(moves.size());
+    leaf.in_check = moves.in_check ? 1 : 0;
+    g.n_edges += moves.size();
+    uint16_t* idx = p.move_idx + slot * kMoveStride;
+    for (int i = 0; i < moves.size(); ++i) {
+      GEdge& e = edges[leaf.first_edge + i];
+      e.prior = 0.f; e.w = 0.f; e.n = 0; e.mv = pack_move(moves.m[i]); e.vloss = 0;
+      child[leaf.first_edge + i] = -1;
+      idx[i] = static_cast<uint16_t>(policy_index(moves.m[i], pos.side));
+    }
+    p.move_cnt[slot] = moves.size();
+    path_encode(pv, pos, p.bits + slot * kInputPlanes, p.scale + slot * kInputPlanes);
+  }
+}
+
+// legal_priors_kernel (e55_fp32.cuh) for fixed-stride move lists: position p owns index/priors [p*stride, +count[p]).
+__global__ void __launch_bounds__(256)
+legal_priors_strided_kernel(const float* __restrict__ logits, const int32_t* __restrict__ count, const uint16_t* __restrict__ index,
+                            float* __restrict__ priors, int n, int width, int stride) {
+  const int lane = threadIdx.x & 31;
+  const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (p >= n) return;
+  const int k = count[p];
+  if (k <= 0) return;
+  const float* row = logits + static_cast<size_t>(p) * width;
+  const uint16_t* idx = index + static_cast<size_t>(p) * stride;
+  float* out = priors + static_cast<size_t>(p) * stride;
+  float m = -INFINITY;
+  for (int j = lane; j < k; j += 32) m = fmaxf(m, row[idx[j]]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float sum = 0.f;
+  for (int j = lane; j < k; j += 32) sum += __expf(row[idx[j]] - m);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = sum > 0.f ? 1.f / sum : 0.f;
+  for (int j = lane; j < k; j += 32) out[j] = __expf(row[idx[j]] - m) * inv;
+}
+
+__global__ void __launch_bounds__(64) expand_kernel(Params p) {
+  const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= p.n_games) return;
+  Game& g = p.games[gi];
+  GNode* nodes = p.nodes + static_cast<size_t>(gi) * kMaxNodes;
+  GEdge* edges = p.edges + static_cast<size_t>(gi) * kMaxEdges;
+  const bool root_round = g.sims_done < 0;
+  int evaluated = 0;
+  // priors and values into the leaves evaluated this round (Mcts::expand_from_priors)
+  for (int s = 0; s < kLeaf; ++s) {
+    const size_t slot = static_cast<size_t>(gi) * kLeaf + s;
+    const int k = p.move_cnt[slot];
+    if (k <= 0) continue;
+    ++evaluated;
+    GNode& leaf = nodes[g.leaf[s]];
+    const float* pr = p.priors + slot * kMoveStride;
+    for (int i = 0; i < k; ++i) edges[leaf.first_edge + i].prior = pr[i];
+    leaf.value = (p.value[slot] + 1.f) * 0.5f;      // mcts.py:59,103
+    leaf.expanded = 1;
+    leaf.claimed = 0;
+    if (g.leaf[s] == 0 && p.use_dirichlet) {        // Mcts::add_noise on the freshly expanded root (mcts.py:63-64)
+      float sum = 0.f;
+      float* noise = p.priors + slot * kMoveStride;  // reuse the slot as scratch
+      for (int i = 0; i < k; ++i) { noise[i] = next_gamma(g.rng, p.dirichlet_alpha); sum += noise[i]; }
+      if (sum > 0.f)
+        for (int i = 0; i < k; ++i)
+          edges[leaf.first_edge + i].prior = (1.f - p.dirichlet_eps) * edges[leaf.first_edge + i].prior + p.dirichlet_eps * noise[i] / sum;
+    }
+  }
+  // back every selection up (Mcts::backpropagate)
+  for (int s = 0; s < kLeaf; ++s) {
+    int node = g.leaf[s];
+    if (node < 0) continue;
+    float v = nodes[node].value;
+    ++nodes[node].n;
+    while (nodes[node].parent >= 0) {
+      v = 1.f - v;
+      GEdge& e = edges[nodes[node].parent_edge];
+      if (e.vloss > 0) --e.vloss;
+      ++e.n;
+      e.w += v;
+      node = nodes[node].parent;
+      ++nodes[node].n;
+    }
+  }
+  if (evaluated) atomicAdd(&p.shared->evals, static_cast<unsigned long long>(evaluated));
+  if (root_round) { g.sims_done = 0; if (!nodes[0].terminal) return; }   // the root evaluation is not a simulation (mcts.py:55-60)
+  else g.sims_done += kLeaf;
+  if (g.sims_done < p.simulations && !nodes[0].terminal) return;
+
+  // ---- the search of this move is over: choose, play, look at the game (selfplay.py:63-78,17-31) -----------------
+  const GNode& root = nodes[0];
+  bool over = root.terminal || root.n_edges == 0;
+  int winner = 2;
+  if (over) {
+    // terminal roots can only be positions without moves here (repetition ends a game before it is searched)
+    winner = 1 - g.root.side;
+  } else {
+    const GEdge* ed = edges + root.first_edge;
+    int chosen = 0;
+    if (g.root.ply < p.sampling_moves) {
+      long total = 0;
+      for (int i = 0; i < root.n_edges; ++i) total += ed[i].n;
+      long pick = total > 0 ? static_cast<long>(next_u64(g.rng) % static_cast<uint64_t>(total)) : 0;
+      for (int i = 0; i < root.n_edges; ++i) { pick -= ed[i].n; if (pick < 0) { chosen = i; break; } }
+    } else {
+      for (int i = 1; i < root.n_edges; ++i)
+        if (ed[i].n > ed[chosen].n) chosen = i;
+    }
+    const long long before = static_cast<long long>(atomicAdd(&p.shared->moves, 1ull));
+    (void)before;
+    game_play(g, unpack_move(ed[chosen].mv));
+    // end of the game?
+    const int ply = g.root.ply;
+    if (g.rep_count[ply] >= 4) {
+      PathView pv;
+      pv.g = &g; pv.ply0 = ply; pv.depth = 0;
+      bool rep, my_check, op_check;
+      path_repetition(pv, rep, my_check, op_check);
+      over = true;
+      winner = my_check ? 1 - g.root.side : (op_check ? g.root.side : 1);
+    } else if (!g.root.has_legal_move()) {
+      over = true;
+      winner = 1 - g.root.side;
+    } else if (ply >= p.max_moves || ply >= kMaxPly) {
+      over = true;
+    }
+  }
+  if (over) {
+    atomicAdd(&p.shared->games, 1ull);
+    atomicAdd(&p.shared->plies_in_finished_games, static_cast<unsigned long long>(g.root.ply));
+    if (p.records) {
+      const int r = atomicAdd(&p.shared->n_records, 1);
+      if (r < p.record_cap) {
+        uint16_t* rec = p.records + static_cast<size_t>(r) * (kRecordMoves + 2);
+        rec[0] = static_cast<uint16_t>(g.root.ply);
+        rec[1] = static_cast<uint16_t>(winner);
+        for (int i = 0; i < g.root.ply && i < kRecordMoves; ++i) rec[2 + i] = g.moves[i];
+      }
+    }
+    ++g.games_finished;
+    start_game(g, nodes);
+  } else {
+    reset_tree(g, nodes);
+  }
+}
+
+// Device perft from the start position (validation of the device build of the engine).
+__device__ long long perft_rec(Board& b, int depth) {
+  MoveList l;
+  b.generate_moves(l);
+  if (depth <= 1) return l.size();
+  long long total = 0;
+  for (int i = 0; i < l.size(); ++i) {
+    const Move m = l.m[i];
+    b.apply(m); ++b.ply;
+    total += perft_rec(b, depth - 1);
+    --b.ply; b.revert(m);
+  }
+  return total;
+}
+__global__ void perft_kernel(int depth, long long* out) {
+  // the root's moves are spread over the threads of the block
+  __shared__ long long acc;
+  if (threadIdx.x == 0) acc = 0;
+  __syncthreads();
+  Board b;
+  b.clear_board();
+  const PieceType top[5] = {ROOK, BISHOP, SILVER, GOLD, KING}, bottom[5] = {KING, GOLD, SILVER, BISHOP, ROOK};
+  for (int c = 0; c < 5; ++c) { b.put(sq_of(0, c), top[c], WHITE); b.put(sq_of(4, c), bottom[c], BLACK); }
+  b.put(sq_of(1, 4), PAWN, WHITE);
+  b.put(sq_of(3, 0), PAWN, BLACK);
+  MoveList l;
+  b.generate_moves(l);
+  long long mine = 0;
+  if (depth <= 1) { if (threadIdx.x == 0) mine = l.size(); }
+  else
+    for (int i = threadIdx.x; i < l.size(); i += blockDim.x) {
+      const Move m = l.m[i];
+      b.apply(m); ++b.ply;
+      mine += perft_rec(b, depth - 1);
+      --b.ply; b.revert(m);
+    }
+  atomicAdd(reinterpret_cast<unsigned long long*>(&acc), static_cast<unsigned long long>(mine));
+  __syncthreads();
+  if (threadIdx.x == 0) *out = acc;
+}
+
+}  // namespace gs
+}  // namespace e55

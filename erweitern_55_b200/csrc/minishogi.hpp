@@ -24,6 +24,12 @@
 #include <string>
 #include <vector>
 
+#if defined(__CUDACC__)
+#define MS_HD __host__ __device__
+#else
+#define MS_HD
+#endif
+
 namespace mshogi {
 
 constexpr int kN = 5, kSquares = 25;
@@ -34,24 +40,39 @@ constexpr PieceType kHandPiece[kHandTypes] = {GOLD, SILVER, BISHOP, ROOK, PAWN};
 using Bitboard = uint32_t;     // bit sq = rank * 5 + col
 constexpr Bitboard kAllSquares = (1u << kSquares) - 1u;
 
-inline int hand_index(PieceType t) {  // unpromoted type -> hand slot
+MS_HD inline PieceType hand_piece(int k) {   // hand slot -> type (kHandPiece, callable from device code)
+  switch (k) { case 0: return GOLD; case 1: return SILVER; case 2: return BISHOP; case 3: return ROOK; default: return PAWN; }
+}
+MS_HD inline int hand_index(PieceType t) {  // unpromoted type -> hand slot
   switch (t) { case GOLD: return 0; case SILVER: return 1; case BISHOP: return 2; case ROOK: return 3; case PAWN: return 4; default: return -1; }
 }
-inline PieceType promote(PieceType t) {
+MS_HD inline PieceType promote(PieceType t) {
   switch (t) { case SILVER: return PRO_SILVER; case BISHOP: return HORSE; case ROOK: return DRAGON; case PAWN: return TOKIN; default: return t; }
 }
-inline PieceType unpromote(PieceType t) {
+MS_HD inline PieceType unpromote(PieceType t) {
   switch (t) { case PRO_SILVER: return SILVER; case HORSE: return BISHOP; case DRAGON: return ROOK; case TOKIN: return PAWN; default: return t; }
 }
-inline bool can_promote(PieceType t) { return t == SILVER || t == BISHOP || t == ROOK || t == PAWN; }
+MS_HD inline bool can_promote(PieceType t) { return t == SILVER || t == BISHOP || t == ROOK || t == PAWN; }
 
 // square = rank * 5 + col; rank 0 = 'a' (White's home row), col 0 = file 5 (left edge as SFEN prints it)
-inline int sq_of(int rank, int col) { return rank * kN + col; }
-inline int rank_of(int sq) { return sq / kN; }
-inline int col_of(int sq) { return sq % kN; }
-inline int lsb(Bitboard b) { return __builtin_ctz(b); }
-inline int msb(Bitboard b) { return 31 - __builtin_clz(b); }
-inline int pop_lsb(Bitboard& b) { const int s = __builtin_ctz(b); b &= b - 1; return s; }
+MS_HD inline int sq_of(int rank, int col) { return rank * kN + col; }
+MS_HD inline int rank_of(int sq) { return sq / kN; }
+MS_HD inline int col_of(int sq) { return sq % kN; }
+MS_HD inline int lsb(Bitboard b) {
+#ifdef __CUDA_ARCH__
+  return __ffs(static_cast<int>(b)) - 1;
+#else
+  return __builtin_ctz(b);
+#endif
+}
+MS_HD inline int msb(Bitboard b) {
+#ifdef __CUDA_ARCH__
+  return 31 - __clz(static_cast<int>(b));
+#else
+  return 31 - __builtin_clz(b);
+#endif
+}
+MS_HD inline int pop_lsb(Bitboard& b) { const int s = lsb(b); b &= b - 1; return s; }
 
 struct Move {
   int8_t from = -1;      // -1: drop
@@ -59,8 +80,8 @@ struct Move {
   int8_t piece = 0;      // PieceType moved (before promotion) or dropped
   int8_t promotes = 0;
   int8_t captured = 0;   // PieceType on `to` (as it stood, promoted or not), filled by generate/do
-  bool is_drop() const { return from < 0; }
-  bool operator==(const Move& o) const { return from == o.from && to == o.to && piece == o.piece && promotes == o.promotes; }
+  MS_HD bool is_drop() const { return from < 0; }
+  MS_HD bool operator==(const Move& o) const { return from == o.from && to == o.to && piece == o.piece && promotes == o.promotes; }
   std::string sfen() const {
     static const char* kLetters = " KGSBRP";
     std::string s;
@@ -76,7 +97,7 @@ struct Move {
 constexpr int kDirR[8] = {-1, -1, 0, 1, 1, 1, 0, -1};
 constexpr int kDirC[8] = {0, 1, 1, 1, 0, -1, -1, -1};
 
-inline uint32_t step_mask(PieceType t) {  // bit d set: may step one square in direction d (BLACK orientation)
+MS_HD inline uint32_t step_mask(PieceType t) {  // bit d set: may step one square in direction d (BLACK orientation)
   switch (t) {
     case KING: return 0xFF;
     case GOLD: case PRO_SILVER: case TOKIN: return (1u << 0) | (1u << 1) | (1u << 7) | (1u << 2) | (1u << 6) | (1u << 4);
@@ -87,7 +108,7 @@ inline uint32_t step_mask(PieceType t) {  // bit d set: may step one square in d
     default: return 0;
   }
 }
-inline uint32_t slide_mask(PieceType t) {
+MS_HD inline uint32_t slide_mask(PieceType t) {
   switch (t) {
     case BISHOP: case HORSE: return (1u << 1) | (1u << 3) | (1u << 5) | (1u << 7);
     case ROOK: case DRAGON: return (1u << 0) | (1u << 2) | (1u << 4) | (1u << 6);
@@ -157,10 +178,20 @@ struct Tables {
     zob_side[BLACK] = 0x1234567ull; zob_side[WHITE] = 0x7654321ull;
   }
 };
-inline const Tables& tables() { static const Tables t; return t; }
+#if defined(__CUDACC__)
+static __device__ const Tables* g_device_tables = nullptr;   // set once by the library (a copy of the host tables)
+#endif
+MS_HD inline const Tables& tables() {
+#ifdef __CUDA_ARCH__
+  return *g_device_tables;
+#else
+  static const Tables t;
+  return t;
+#endif
+}
 
 // Squares attacked by a slider on `sq` along the directions in `dirs` (bit d), given the occupancy.
-inline Bitboard slide_attacks(const Tables& T, int sq, Bitboard occ, uint32_t dirs) {
+MS_HD inline Bitboard slide_attacks(const Tables& T, int sq, Bitboard occ, uint32_t dirs) {
   Bitboard att = 0;
   for (int d = (dirs & 1) ? 0 : 1; d < 8; d += 2) {     // the four rook or the four bishop directions
     const Bitboard r = T.ray[d][sq];
@@ -177,11 +208,11 @@ struct MoveList {                    // no position has anywhere near 256 legal 
   Move m[256];
   int n = 0;
   bool in_check = false;             // set by generate_moves: the side to move is in check
-  void push(const Move& mv) { if (n < 256) m[n++] = mv; }
-  const Move* begin() const { return m; }
-  const Move* end() const { return m + n; }
-  bool empty() const { return n == 0; }
-  int size() const { return n; }
+  MS_HD void push(const Move& mv) { if (n < 256) m[n++] = mv; }
+  MS_HD const Move* begin() const { return m; }
+  MS_HD const Move* end() const { return m + n; }
+  MS_HD bool empty() const { return n == 0; }
+  MS_HD int size() const { return n; }
 };
 
 struct Snapshot {                    // what the input encoder needs of a past position
@@ -197,14 +228,282 @@ struct HistoryEntry {                // one per position of the game so far (ind
   Move move;                        // the move leading here (index 0: unused)
 };
 
-class Position {
- public:
+// The rules core: board, hands, side to move and everything that needs no game history.  Plain data and plain
+// functions, usable from host code and (under nvcc) from device code alike.
+struct Board {
   int8_t board[kSquares];            // 0 = empty, else type | (color << 4)
   int8_t hand[2][kHandTypes];
   Bitboard bb[2][PIECE_TYPES];       // [colour][type]; index 0 = all pieces of that colour
   int side = BLACK;
   int ply = 0;
   int8_t king_sq[2] = {-1, -1};      // cached king squares (-1: no king, as in some test positions)
+
+  MS_HD static int type_of(int8_t p) { return p & 15; }
+  MS_HD static int color_of(int8_t p) { return (p >> 4) & 1; }
+  MS_HD static int8_t make_piece(int type, int color) { return static_cast<int8_t>(type | (color << 4)); }
+
+  MS_HD void clear_board() {
+    memset(board, 0, sizeof(board));
+    memset(hand, 0, sizeof(hand));
+    memset(bb, 0, sizeof(bb));
+    side = BLACK; ply = 0;
+    king_sq[0] = king_sq[1] = -1;
+  }
+
+  // ---- attacks -------------------------------------------------------------------------------
+  MS_HD Bitboard occupied() const { return bb[BLACK][0] | bb[WHITE][0]; }
+
+  // Pieces of colour `by` that attack `sq`, with `occ` as the blocking set (pass a modified occupancy to look
+  // through a piece that is about to move).
+  MS_HD Bitboard attackers_to(int sq, int by, Bitboard occ) const {
+    const Tables& T = tables();
+    const Bitboard* b = bb[by];
+    Bitboard att = (T.step_from[by][PAWN][sq] & b[PAWN]) | (T.step_from[by][SILVER][sq] & b[SILVER]) |
+                   (T.step_from[by][GOLD][sq] & (b[GOLD] | b[PRO_SILVER] | b[TOKIN])) |
+                   (T.step_from[by][KING][sq] & (b[KING] | b[HORSE] | b[DRAGON]));
+    const Bitboard rooks = b[ROOK] | b[DRAGON], bishops = b[BISHOP] | b[HORSE];
+    if (rooks) att |= slide_attacks(T, sq, occ, kRookDirs) & rooks;
+    if (bishops) att |= slide_attacks(T, sq, occ, kBishopDirs) & bishops;
+    return att;
+  }
+
+  MS_HD bool attacked_by(int sq, int by) const { return attackers_to(sq, by, occupied()) != 0; }
+
+  MS_HD int king_square(int color) const { return king_sq[color]; }
+
+  MS_HD bool in_check(int color) const {
+    const int k = king_square(color);
+    return k >= 0 && attacked_by(k, color ^ 1);
+  }
+
+  // ---- make / unmake (board + hands + side only; history handled by do_move / undo_move) -------------
+  MS_HD void apply(const Move& m) {
+    const int us = side;
+    if (m.is_drop()) {
+      put(m.to, m.piece, us);
+      --hand[us][hand_index(static_cast<PieceType>(m.piece))];
+    } else {
+      if (m.captured) {
+        lift(m.to, m.captured, us ^ 1);
+        ++hand[us][hand_index(unpromote(static_cast<PieceType>(m.captured)))];
+      }
+      lift(m.from, m.piece, us);
+      put(m.to, m.promotes ? promote(static_cast<PieceType>(m.piece)) : m.piece, us);
+    }
+    side ^= 1;
+  }
+
+  MS_HD void revert(const Move& m) {
+    side ^= 1;
+    const int us = side;
+    if (m.is_drop()) {
+      lift(m.to, m.piece, us);
+      ++hand[us][hand_index(static_cast<PieceType>(m.piece))];
+    } else {
+      lift(m.to, m.promotes ? promote(static_cast<PieceType>(m.piece)) : m.piece, us);
+      put(m.from, m.piece, us);
+      if (m.captured) {
+        put(m.to, m.captured, us ^ 1);
+        --hand[us][hand_index(unpromote(static_cast<PieceType>(m.captured)))];
+      }
+    }
+  }
+
+  // ---- move generation ------------------------------------------------------------------------
+  // Fully legal moves of the side to move (own king never left in check; nifu, last-rank pawn and
+  // pawn-drop-mate excluded).
+  MS_HD void generate_moves(MoveList& out) { out.n = 0; out.in_check = false; generate<false>(&out); }
+
+  MS_HD bool has_legal_move() { return generate<true>(nullptr); }
+
+  // ---- mate search (tests/test_checkmate.py) ----------------------------------------------------
+  // Depth-limited AND/OR search over checking sequences: the side to move must check on every move.
+  MS_HD bool solve_checkmate_dfs(int depth, Move& best) {
+    return depth > 0 && mate_attack(depth, &best);
+  }
+
+  MS_HD uint64_t compute_hash() const {
+    const Tables& T = tables();
+    uint64_t h = T.zob_side[side];
+    for (int s = 0; s < kSquares; ++s) h ^= T.zob_piece[s][board[s] & 31];
+    for (int c = 0; c < 2; ++c)
+      for (int k = 0; k < kHandTypes; ++k) h ^= T.zob_hand[c][k][hand[c][k] & 3];
+    return h;
+  }
+
+  MS_HD void put(int sq, int type, int color) {
+    board[sq] = make_piece(type, color);
+    bb[color][type] |= 1u << sq;
+    bb[color][0] |= 1u << sq;
+    if (type == KING) king_sq[color] = static_cast<int8_t>(sq);
+  }
+
+  MS_HD void lift(int sq, int type, int color) {
+    board[sq] = 0;
+    bb[color][type] &= ~(1u << sq);
+    bb[color][0] &= ~(1u << sq);
+  }
+
+  // Key of the position after `m`, given the key of this one (called before apply).
+  MS_HD uint64_t hash_after(uint64_t key, const Move& m) const {
+    const Tables& T = tables();
+    const int us = side;
+    uint64_t h = key ^ T.zob_side[BLACK] ^ T.zob_side[WHITE];
+    if (m.is_drop()) {
+      const int k = hand_index(static_cast<PieceType>(m.piece));
+      h ^= T.zob_hand[us][k][hand[us][k] & 3] ^ T.zob_hand[us][k][(hand[us][k] - 1) & 3];
+      h ^= T.zob_piece[m.to][make_piece(m.piece, us) & 31];
+    } else {
+      if (m.captured) {
+        const int k = hand_index(unpromote(static_cast<PieceType>(m.captured)));
+        h ^= T.zob_piece[m.to][make_piece(m.captured, us ^ 1) & 31];
+        h ^= T.zob_hand[us][k][hand[us][k] & 3] ^ T.zob_hand[us][k][(hand[us][k] + 1) & 3];
+      }
+      h ^= T.zob_piece[m.from][make_piece(m.piece, us) & 31];
+      h ^= T.zob_piece[m.to][make_piece(m.promotes ? promote(static_cast<PieceType>(m.piece)) : m.piece, us) & 31];
+    }
+    return h;
+  }
+
+  MS_HD static void emit(MoveList* out, int from, int to, PieceType t, int captured, bool promo_zone, int far_rank) {
+    Move m;
+    m.from = static_cast<int8_t>(from); m.to = static_cast<int8_t>(to); m.piece = static_cast<int8_t>(t);
+    m.captured = static_cast<int8_t>(captured);
+    if (promo_zone && can_promote(t)) { Move pm = m; pm.promotes = 1; out->push(pm); }
+    if (!(t == PAWN && rank_of(to) == far_rank)) out->push(m);       // a pawn on the last rank must promote
+  }
+
+  // Legal move generation.  kAny: stop at the first legal move and return true (`out` is not used).
+  // kChecks: only moves that can give check -- a superset of the checking moves, in the order of the full list (the
+  // piece lands where its kind attacks the enemy king with our own men thought away, or leaves a line through that
+  // king); the mate search confirms each by playing it.
+  template <bool kAny, bool kChecks = false>
+  MS_HD bool generate(MoveList* out) {
+    const Tables& T = tables();
+    const int us = side, them = us ^ 1;
+    const int far = us == BLACK ? 0 : kN - 1;      // promotion rank
+    const Bitboard own = bb[us][0], occ = occupied();
+    const int ksq = king_sq[us];
+    Bitboard zone[PIECE_TYPES] = {};               // kChecks: squares from which a piece of that type would attack their king
+    Bitboard king_lines = 0;                       // kChecks: lines through their king that one of our sliders could use
+    if (kChecks) {
+      const int ek = king_sq[them];
+      if (ek < 0) return false;
+      const Bitboard rook_rays = slide_attacks(T, ek, bb[them][0], kRookDirs), bishop_rays = slide_attacks(T, ek, bb[them][0], kBishopDirs);
+      zone[GOLD] = zone[PRO_SILVER] = zone[TOKIN] = T.step_from[us][GOLD][ek];
+      zone[SILVER] = T.step_from[us][SILVER][ek];
+      zone[PAWN] = T.step_from[us][PAWN][ek];
+      zone[BISHOP] = bishop_rays; zone[ROOK] = rook_rays;
+      zone[HORSE] = bishop_rays | T.step_from[us][KING][ek];
+      zone[DRAGON] = rook_rays | T.step_from[us][KING][ek];
+      if (bb[us][ROOK] | bb[us][DRAGON]) king_lines |= rook_rays;
+      if (bb[us][BISHOP] | bb[us][HORSE]) king_lines |= bishop_rays;
+    }
+    Bitboard checkers = 0, pinned = 0;
+    Bitboard target_mask = kAllSquares;            // where non-king pieces may land (blocks / captures when in check)
+    if (ksq >= 0) {
+      checkers = attackers_to(ksq, them, occ);
+      // pins: an enemy slider aligned with the king with exactly one piece, ours, in between
+      const Bitboard rooks = bb[them][ROOK] | bb[them][DRAGON], bishops = bb[them][BISHOP] | bb[them][HORSE];
+      Bitboard snipers = 0;
+      if (rooks) snipers |= slide_attacks(T, ksq, 0, kRookDirs) & rooks;
+      if (bishops) snipers |= slide_attacks(T, ksq, 0, kBishopDirs) & bishops;
+      while (snipers) {
+        const Bitboard b = T.between[ksq][pop_lsb(snipers)] & occ;
+        if (b && !(b & (b - 1)) && (b & own)) pinned |= b;
+      }
+      if (!kAny) out->in_check = checkers != 0;
+      if (checkers) {
+        if (checkers & (checkers - 1)) target_mask = 0;                                   // double check: king moves only
+        else target_mask = checkers | T.between[ksq][lsb(checkers)];
+      }
+      // king moves: the destination must not be attacked once the king has left its square
+      for (Bitboard dst = (kChecks && !(king_lines >> ksq & 1)) ? 0 : T.step_to[us][KING][ksq] & ~own; dst;) {
+        const int to = pop_lsb(dst);
+        if (attackers_to(to, them, occ ^ (1u << ksq))) continue;
+        if (kAny) return true;
+        emit(out, ksq, to, KING, type_of(board[to]), false, far);
+      }
+    }
+    if (target_mask) {
+      for (Bitboard pcs = own & ~bb[us][KING]; pcs;) {
+        const int from = pop_lsb(pcs);
+        const PieceType t = static_cast<PieceType>(type_of(board[from]));
+        Bitboard dst = T.step_to[us][t][from];
+        const uint32_t slides = slide_mask(t);
+        if (slides) dst |= slide_attacks(T, from, occ, slides);
+        dst &= ~own & target_mask;
+        if (pinned >> from & 1) dst &= T.line[ksq][from];
+        if (kChecks && !(king_lines >> from & 1)) dst &= zone[t] | (can_promote(t) ? zone[promote(t)] : 0);
+        if (kAny) { if (dst) return true; continue; }    // (a pawn reaching the last rank still has its promotion)
+        const bool from_zone = rank_of(from) == far;
+        while (dst) {
+          const int to = pop_lsb(dst);
+          emit(out, from, to, t, type_of(board[to]), from_zone || rank_of(to) == far, far);
+        }
+      }
+      // drops: onto empty squares (only interpositions when in check)
+      const Bitboard empties = ~occ & kAllSquares & target_mask;
+      if (empties)
+        for (int k = 0; k < kHandTypes; ++k) {
+          if (!hand[us][k]) continue;
+          const PieceType t = hand_piece(k);
+          Bitboard dst = kChecks ? empties & zone[t] : empties;
+          if (t == PAWN) {
+            dst &= ~T.rank_mask[far];                                                       // not onto the last rank
+            for (Bitboard p = bb[us][PAWN]; p;) dst &= ~T.file_mask[col_of(pop_lsb(p))];    // nifu
+          }
+          while (dst) {
+            const int to = pop_lsb(dst);
+            Move m;
+            m.from = -1; m.to = static_cast<int8_t>(to); m.piece = static_cast<int8_t>(t);
+            if (t == PAWN && king_sq[them] >= 0 && (T.step_to[us][PAWN][to] >> king_sq[them] & 1)) {
+              apply(m);                                                    // pawn-drop check: illegal if it is mate
+              const bool mate = !has_legal_move();
+              revert(m);
+              if (mate) continue;
+            }
+            if (kAny) return true;
+            out->push(m);
+          }
+        }
+    }
+    return kAny ? false : out->n > 0;
+  }
+
+  MS_HD bool mate_attack(int depth, Move* best) {
+    MoveList moves;
+    moves.n = 0;
+    generate<false, true>(&moves);
+    for (const Move& m : moves) {
+      apply(m);
+      bool mated = false;
+      if (in_check(side)) mated = mate_defend(depth - 1);
+      revert(m);
+      if (mated) { if (best) *best = m; return true; }
+    }
+    return false;
+  }
+
+  // true iff the side to move (in check) is mated within `depth` further plies whatever it plays
+  MS_HD bool mate_defend(int depth) {
+    if (depth <= 1) return !has_legal_move();
+    MoveList moves;
+    generate_moves(moves);
+    if (moves.empty()) return true;
+    for (const Move& m : moves) {
+      apply(m);
+      const bool still = mate_attack(depth - 1, nullptr);
+      revert(m);
+      if (!still) return false;
+    }
+    return true;
+  }
+
+};
+
+class Position : public Board {
+ public:
   // History for repetition / encoding / tree reuse; entry(ply) = the current position.  A position made by fork_from()
   // shares the other position's entries as a read-only prefix and owns only what it plays on top of them.
   std::vector<HistoryEntry> hist;
@@ -233,16 +532,9 @@ class Position {
   const HistoryEntry& entry(int i) const { return i < base_n_ ? base_[i] : hist[static_cast<size_t>(i - base_n_)]; }
   const HistoryEntry& last_entry() const { return hist.empty() ? base_[base_n_ - 1] : hist.back(); }
 
-  static int type_of(int8_t p) { return p & 15; }
-  static int color_of(int8_t p) { return (p >> 4) & 1; }
-  static int8_t make_piece(int type, int color) { return static_cast<int8_t>(type | (color << 4)); }
 
   void clear() {
-    memset(board, 0, sizeof(board));
-    memset(hand, 0, sizeof(hand));
-    memset(bb, 0, sizeof(bb));
-    side = BLACK; ply = 0;
-    king_sq[0] = king_sq[1] = -1;
+    clear_board();
     hist.clear();
     base_ = nullptr; base_n_ = 0;
   }
@@ -383,66 +675,14 @@ class Position {
     return true;
   }
 
-  // ---- attacks -------------------------------------------------------------------------------
-  Bitboard occupied() const { return bb[BLACK][0] | bb[WHITE][0]; }
 
-  // Pieces of colour `by` that attack `sq`, with `occ` as the blocking set (pass a modified occupancy to look
-  // through a piece that is about to move).
-  Bitboard attackers_to(int sq, int by, Bitboard occ) const {
-    const Tables& T = tables();
-    const Bitboard* b = bb[by];
-    Bitboard att = (T.step_from[by][PAWN][sq] & b[PAWN]) | (T.step_from[by][SILVER][sq] & b[SILVER]) |
-                   (T.step_from[by][GOLD][sq] & (b[GOLD] | b[PRO_SILVER] | b[TOKIN])) |
-                   (T.step_from[by][KING][sq] & (b[KING] | b[HORSE] | b[DRAGON]));
-    const Bitboard rooks = b[ROOK] | b[DRAGON], bishops = b[BISHOP] | b[HORSE];
-    if (rooks) att |= slide_attacks(T, sq, occ, kRookDirs) & rooks;
-    if (bishops) att |= slide_attacks(T, sq, occ, kBishopDirs) & bishops;
-    return att;
-  }
-  bool attacked_by(int sq, int by) const { return attackers_to(sq, by, occupied()) != 0; }
-  int king_square(int color) const { return king_sq[color]; }
-  bool in_check(int color) const {
-    const int k = king_square(color);
-    return k >= 0 && attacked_by(k, color ^ 1);
-  }
 
-  // ---- make / unmake (board + hands + side only; history handled by do_move / undo_move) -------------
-  void apply(const Move& m) {
-    const int us = side;
-    if (m.is_drop()) {
-      put(m.to, m.piece, us);
-      --hand[us][hand_index(static_cast<PieceType>(m.piece))];
-    } else {
-      if (m.captured) {
-        lift(m.to, m.captured, us ^ 1);
-        ++hand[us][hand_index(unpromote(static_cast<PieceType>(m.captured)))];
-      }
-      lift(m.from, m.piece, us);
-      put(m.to, m.promotes ? promote(static_cast<PieceType>(m.piece)) : m.piece, us);
-    }
-    side ^= 1;
-  }
-  void revert(const Move& m) {
-    side ^= 1;
-    const int us = side;
-    if (m.is_drop()) {
-      lift(m.to, m.piece, us);
-      ++hand[us][hand_index(static_cast<PieceType>(m.piece))];
-    } else {
-      lift(m.to, m.promotes ? promote(static_cast<PieceType>(m.piece)) : m.piece, us);
-      put(m.from, m.piece, us);
-      if (m.captured) {
-        put(m.to, m.captured, us ^ 1);
-        --hand[us][hand_index(unpromote(static_cast<PieceType>(m.captured)))];
-      }
-    }
-  }
 
   // gives_check: 1 / 0 when the caller already knows whether the move checks (a search tree does), -1 to find out.
   void do_move(const Move& mv, int gives_check = -1) {
     Move m = mv;
     if (!m.is_drop()) m.captured = static_cast<int8_t>(type_of(board[m.to]));   // whatever the caller knew: the board decides
-    const uint64_t h = hash_after(m);
+    const uint64_t h = hash_after(last_entry().hash, m);
     apply(m);
     ++ply;
     push_history(h, gives_check < 0 ? in_check(side) : gives_check != 0, m);
@@ -453,17 +693,13 @@ class Position {
     revert(m);
   }
 
-  // ---- move generation ------------------------------------------------------------------------
-  // Fully legal moves of the side to move (own king never left in check; nifu, last-rank pawn and
-  // pawn-drop-mate excluded).
-  void generate_moves(MoveList& out) { out.n = 0; out.in_check = false; generate<false>(&out); }
+  using Board::generate_moves;
   void generate_moves(std::vector<Move>& out) {
     MoveList l;
     generate_moves(l);
     out.assign(l.begin(), l.end());
   }
   std::vector<Move> generate_moves() { std::vector<Move> v; generate_moves(v); return v; }
-  bool has_legal_move() { return generate<true>(nullptr); }
 
   // ---- repetition (tests/test_repetition.py) -----------------------------------------------------
   // The position has now occurred four times -> repetition.  If every move one side made since the first
@@ -490,22 +726,9 @@ class Position {
   }
   int repetition_count() const { return last_entry().snap.rep_count; }
 
-  // ---- mate search (tests/test_checkmate.py) ----------------------------------------------------
-  // Depth-limited AND/OR search over checking sequences: the side to move must check on every move.
-  bool solve_checkmate_dfs(int depth, Move& best) {
-    return depth > 0 && mate_attack(depth, &best);
-  }
 
   uint64_t hash() const { return last_entry().hash; }
 
-  uint64_t compute_hash() const {
-    const Tables& T = tables();
-    uint64_t h = T.zob_side[side];
-    for (int s = 0; s < kSquares; ++s) h ^= T.zob_piece[s][board[s] & 31];
-    for (int c = 0; c < 2; ++c)
-      for (int k = 0; k < kHandTypes; ++k) h ^= T.zob_hand[c][k][hand[c][k] & 3];
-    return h;
-  }
 
  private:
   static PieceType letter_type(char ch) {
@@ -516,46 +739,9 @@ class Position {
     }
   }
 
-  void copy_board_from(const Position& o) {
-    memcpy(board, o.board, sizeof(board));
-    memcpy(hand, o.hand, sizeof(hand));
-    memcpy(bb, o.bb, sizeof(bb));
-    side = o.side; ply = o.ply;
-    king_sq[0] = o.king_sq[0]; king_sq[1] = o.king_sq[1];
-  }
+  void copy_board_from(const Position& o) { static_cast<Board&>(*this) = static_cast<const Board&>(o); }
 
-  void put(int sq, int type, int color) {
-    board[sq] = make_piece(type, color);
-    bb[color][type] |= 1u << sq;
-    bb[color][0] |= 1u << sq;
-    if (type == KING) king_sq[color] = static_cast<int8_t>(sq);
-  }
-  void lift(int sq, int type, int color) {
-    board[sq] = 0;
-    bb[color][type] &= ~(1u << sq);
-    bb[color][0] &= ~(1u << sq);
-  }
 
-  // Key of the position after `m` (called before apply).
-  uint64_t hash_after(const Move& m) const {
-    const Tables& T = tables();
-    const int us = side;
-    uint64_t h = last_entry().hash ^ T.zob_side[BLACK] ^ T.zob_side[WHITE];
-    if (m.is_drop()) {
-      const int k = hand_index(static_cast<PieceType>(m.piece));
-      h ^= T.zob_hand[us][k][hand[us][k] & 3] ^ T.zob_hand[us][k][(hand[us][k] - 1) & 3];
-      h ^= T.zob_piece[m.to][make_piece(m.piece, us) & 31];
-    } else {
-      if (m.captured) {
-        const int k = hand_index(unpromote(static_cast<PieceType>(m.captured)));
-        h ^= T.zob_piece[m.to][make_piece(m.captured, us ^ 1) & 31];
-        h ^= T.zob_hand[us][k][hand[us][k] & 3] ^ T.zob_hand[us][k][(hand[us][k] + 1) & 3];
-      }
-      h ^= T.zob_piece[m.from][make_piece(m.piece, us) & 31];
-      h ^= T.zob_piece[m.to][make_piece(m.promotes ? promote(static_cast<PieceType>(m.piece)) : m.piece, us) & 31];
-    }
-    return h;
-  }
 
   void push_history(uint64_t h, bool check, const Move& m) {
     hist.emplace_back();
@@ -572,139 +758,8 @@ class Position {
     e.snap.rep_count = static_cast<uint8_t>(c > 255 ? 255 : c);
   }
 
-  static void emit(MoveList* out, int from, int to, PieceType t, int captured, bool promo_zone, int far_rank) {
-    Move m;
-    m.from = static_cast<int8_t>(from); m.to = static_cast<int8_t>(to); m.piece = static_cast<int8_t>(t);
-    m.captured = static_cast<int8_t>(captured);
-    if (promo_zone && can_promote(t)) { Move pm = m; pm.promotes = 1; out->push(pm); }
-    if (!(t == PAWN && rank_of(to) == far_rank)) out->push(m);       // a pawn on the last rank must promote
-  }
 
-  // Legal move generation.  kAny: stop at the first legal move and return true (`out` is not used).
-  // kChecks: only moves that can give check -- a superset of the checking moves, in the order of the full list (the
-  // piece lands where its kind attacks the enemy king with our own men thought away, or leaves a line through that
-  // king); the mate search confirms each by playing it.
-  template <bool kAny, bool kChecks = false>
-  bool generate(MoveList* out) {
-    const Tables& T = tables();
-    const int us = side, them = us ^ 1;
-    const int far = us == BLACK ? 0 : kN - 1;      // promotion rank
-    const Bitboard own = bb[us][0], occ = occupied();
-    const int ksq = king_sq[us];
-    Bitboard zone[PIECE_TYPES] = {};               // kChecks: squares from which a piece of that type would attack their king
-    Bitboard king_lines = 0;                       // kChecks: lines through their king that one of our sliders could use
-    if (kChecks) {
-      const int ek = king_sq[them];
-      if (ek < 0) return false;
-      const Bitboard rook_rays = slide_attacks(T, ek, bb[them][0], kRookDirs), bishop_rays = slide_attacks(T, ek, bb[them][0], kBishopDirs);
-      zone[GOLD] = zone[PRO_SILVER] = zone[TOKIN] = T.step_from[us][GOLD][ek];
-      zone[SILVER] = T.step_from[us][SILVER][ek];
-      zone[PAWN] = T.step_from[us][PAWN][ek];
-      zone[BISHOP] = bishop_rays; zone[ROOK] = rook_rays;
-      zone[HORSE] = bishop_rays | T.step_from[us][KING][ek];
-      zone[DRAGON] = rook_rays | T.step_from[us][KING][ek];
-      if (bb[us][ROOK] | bb[us][DRAGON]) king_lines |= rook_rays;
-      if (bb[us][BISHOP] | bb[us][HORSE]) king_lines |= bishop_rays;
-    }
-    Bitboard checkers = 0, pinned = 0;
-    Bitboard target_mask = kAllSquares;            // where non-king pieces may land (blocks / captures when in check)
-    if (ksq >= 0) {
-      checkers = attackers_to(ksq, them, occ);
-      // pins: an enemy slider aligned with the king with exactly one piece, ours, in between
-      const Bitboard rooks = bb[them][ROOK] | bb[them][DRAGON], bishops = bb[them][BISHOP] | bb[them][HORSE];
-      Bitboard snipers = 0;
-      if (rooks) snipers |= slide_attacks(T, ksq, 0, kRookDirs) & rooks;
-      if (bishops) snipers |= slide_attacks(T, ksq, 0, kBishopDirs) & bishops;
-      while (snipers) {
-        const Bitboard b = T.between[ksq][pop_lsb(snipers)] & occ;
-        if (b && !(b & (b - 1)) && (b & own)) pinned |= b;
-      }
-      if (!kAny) out->in_check = checkers != 0;
-      if (checkers) {
-        if (checkers & (checkers - 1)) target_mask = 0;                                   // double check: king moves only
-        else target_mask = checkers | T.between[ksq][lsb(checkers)];
-      }
-      // king moves: the destination must not be attacked once the king has left its square
-      for (Bitboard dst = (kChecks && !(king_lines >> ksq & 1)) ? 0 : T.step_to[us][KING][ksq] & ~own; dst;) {
-        const int to = pop_lsb(dst);
-        if (attackers_to(to, them, occ ^ (1u << ksq))) continue;
-        if (kAny) return true;
-        emit(out, ksq, to, KING, type_of(board[to]), false, far);
-      }
-    }
-    if (target_mask) {
-      for (Bitboard pcs = own & ~bb[us][KING]; pcs;) {
-        const int from = pop_lsb(pcs);
-        const PieceType t = static_cast<PieceType>(type_of(board[from]));
-        Bitboard dst = T.step_to[us][t][from];
-        const uint32_t slides = slide_mask(t);
-        if (slides) dst |= slide_attacks(T, from, occ, slides);
-        dst &= ~own & target_mask;
-        if (pinned >> from & 1) dst &= T.line[ksq][from];
-        if (kChecks && !(king_lines >> from & 1)) dst &= zone[t] | (can_promote(t) ? zone[promote(t)] : 0);
-        if (kAny) { if (dst) return true; continue; }    // (a pawn reaching the last rank still has its promotion)
-        const bool from_zone = rank_of(from) == far;
-        while (dst) {
-          const int to = pop_lsb(dst);
-          emit(out, from, to, t, type_of(board[to]), from_zone || rank_of(to) == far, far);
-        }
-      }
-      // drops: onto empty squares (only interpositions when in check)
-      const Bitboard empties = ~occ & kAllSquares & target_mask;
-      if (empties)
-        for (int k = 0; k < kHandTypes; ++k) {
-          if (!hand[us][k]) continue;
-          const PieceType t = kHandPiece[k];
-          Bitboard dst = kChecks ? empties & zone[t] : empties;
-          if (t == PAWN) {
-            dst &= ~T.rank_mask[far];                                                       // not onto the last rank
-            for (Bitboard p = bb[us][PAWN]; p;) dst &= ~T.file_mask[col_of(pop_lsb(p))];    // nifu
-          }
-          while (dst) {
-            const int to = pop_lsb(dst);
-            Move m;
-            m.from = -1; m.to = static_cast<int8_t>(to); m.piece = static_cast<int8_t>(t);
-            if (t == PAWN && king_sq[them] >= 0 && (T.step_to[us][PAWN][to] >> king_sq[them] & 1)) {
-              apply(m);                                                    // pawn-drop check: illegal if it is mate
-              const bool mate = !has_legal_move();
-              revert(m);
-              if (mate) continue;
-            }
-            if (kAny) return true;
-            out->push(m);
-          }
-        }
-    }
-    return kAny ? false : out->n > 0;
-  }
 
-  bool mate_attack(int depth, Move* best) {
-    MoveList moves;
-    moves.n = 0;
-    generate<false, true>(&moves);
-    for (const Move& m : moves) {
-      apply(m);
-      bool mated = false;
-      if (in_check(side)) mated = mate_defend(depth - 1);
-      revert(m);
-      if (mated) { if (best) *best = m; return true; }
-    }
-    return false;
-  }
-  // true iff the side to move (in check) is mated within `depth` further plies whatever it plays
-  bool mate_defend(int depth) {
-    if (depth <= 1) return !has_legal_move();
-    MoveList moves;
-    generate_moves(moves);
-    if (moves.empty()) return true;
-    for (const Move& m : moves) {
-      apply(m);
-      const bool still = mate_attack(depth - 1, nullptr);
-      revert(m);
-      if (!still) return false;
-    }
-    return true;
-  }
 };
 
 // ---- network input (restated; see header comment) -------------------------------------------------
@@ -718,11 +773,15 @@ class Position {
 // plane, erweitern_55_b200/packing.py) is exact.
 constexpr int kInputPlanes = 266, kHistory = 8, kPlanesPerStep = 33;
 
-inline Bitboard rotate180(Bitboard b) {   // square s -> 24 - s
+MS_HD inline Bitboard rotate180(Bitboard b) {   // square s -> 24 - s
   b = ((b >> 1) & 0x55555555u) | ((b & 0x55555555u) << 1);
   b = ((b >> 2) & 0x33333333u) | ((b & 0x33333333u) << 2);
   b = ((b >> 4) & 0x0F0F0F0Fu) | ((b & 0x0F0F0F0Fu) << 4);
+#ifdef __CUDA_ARCH__
+  return __byte_perm(b, 0, 0x0123) >> 7;
+#else
   return __builtin_bswap32(b) >> 7;
+#endif
 }
 
 inline void encode_packed(const Position& pos, uint32_t* bits, float* scale) {
@@ -755,16 +814,16 @@ inline void encode_packed(const Position& pos, uint32_t* bits, float* scale) {
 // ---- policy index (restated): 69 move planes x 25 squares, side to move's perspective --------------
 //   planes 0-31: direction d (N, NE, E, SE, S, SW, W, NW) x distance 1..4, indexed by the ORIGIN square
 //   planes 32-63: the same with promotion      planes 64-68: drop of G,S,B,R,P indexed by the DESTINATION
-inline int policy_index(const Move& m, int side) {
+MS_HD inline int policy_index(const Move& m, int side) {
   auto persp = [&](int sq) { return side == BLACK ? sq : kSquares - 1 - sq; };
   if (m.is_drop()) return (64 + hand_index(static_cast<PieceType>(m.piece))) * kSquares + persp(m.to);
   const int from = persp(m.from), to = persp(m.to);
   const int dr = rank_of(to) - rank_of(from), dc = col_of(to) - col_of(from);
-  const int dist = std::max(dr < 0 ? -dr : dr, dc < 0 ? -dc : dc);
+  const int adr = dr < 0 ? -dr : dr, adc = dc < 0 ? -dc : dc;
+  const int dist = adr > adc ? adr : adc;
   const int sr = (dr > 0) - (dr < 0), sc = (dc > 0) - (dc < 0);
-  int d = 0;
-  for (int k = 0; k < 8; ++k)
-    if (kDirR[k] == sr && kDirC[k] == sc) d = k;
+  // direction index of (sr, sc) in the order N, NE, E, SE, S, SW, W, NW (kDirR / kDirC)
+  const int d = sr < 0 ? (sc == 0 ? 0 : (sc > 0 ? 1 : 7)) : (sr == 0 ? (sc > 0 ? 2 : 6) : (sc > 0 ? 3 : (sc == 0 ? 4 : 5)));
   return ((m.promotes ? 32 : 0) + d * 4 + (dist - 1)) * kSquares + from;
 }
 

@@ -225,6 +225,33 @@ class Network:
                                       records=False, **kw)
         return stats
 
+    def gpu_selfplay(self, games, total_moves, simulations=800, use_dirichlet=True, num_sampling_moves=10, max_moves=512,
+                     seed=1, records=0):
+        """GPU-resident self-play (``csrc/e55_gpu_selfplay.cuh``): ``games`` games at once with tree search, move
+        generation and input encoding on the GPU, until ``total_moves`` plies were played.  Returns ``(stats, games)``;
+        ``games`` holds the first ``records`` finished games as ``(winner, [move sfen, ...])``."""
+        from .minishogi import Move
+        st = _capi.SelfplayStats()
+        buf = np.zeros((max(records, 1), 258), dtype=np.uint16)
+        n_rec = C.c_int(0)
+        self._check(self._lib.e55_gpu_selfplay_run(self._ctx, games, total_moves, simulations, int(use_dirichlet), num_sampling_moves,
+                                                   max_moves, seed, C.byref(st), buf.ctypes.data if records else None, records,
+                                                   C.byref(n_rec) if records else None))
+        stats = {"seconds": st.seconds, "moves": st.moves, "evals": st.evals, "games": st.games,
+                 "mean_game_plies": st.mean_game_plies, "slots_per_launch": st.mean_gpu_batch,
+                 "moves_per_s": st.moves / st.seconds, "evals_per_s": st.evals / st.seconds}
+        letters = " KGSBRP"
+
+        def sfen(mv):
+            frm, to, piece, promo = mv & 31, (mv >> 5) & 31, (mv >> 10) & 15, (mv >> 14) & 1
+            sq = lambda q: "%d%s" % (5 - q % 5, "abcde"[q // 5])
+            return letters[piece] + "*" + sq(to) if frm == 31 else sq(frm) + sq(to) + ("+" if promo else "")
+        out = []
+        for r in range(n_rec.value):
+            plies, winner = int(buf[r, 0]), int(buf[r, 1])
+            out.append((winner, [sfen(int(m)) for m in buf[r, 2:2 + min(plies, 256)]], plies))
+        return stats, out
+
     def bench_selfplay(self, workers, moves, simulations=800, leaf_batch=16):
         """Synthetic self-play load on the running service -> (moves/s, evals/s, mean GPU batch)."""
         m, e, mb = C.c_double(), C.c_double(), C.c_double()

@@ -485,6 +485,47 @@ def test_host_side_packing_is_invisible(weights_perturbed):
     net.close()
 
 
+def test_gpu_resident_selfplay(weights_default):
+    """The search on the GPU (csrc/e55_gpu_selfplay.cuh): the device build of the rules engine counts the same perft
+    nodes as the host build, and every game it plays is a legal game that ended for a reason the rules give."""
+    import ctypes as C
+    from erweitern_55_b200 import _capi
+    from erweitern_55_b200.minishogi import Move, Position
+    from erweitern_55_b200.network import Network
+    lib = _capi.load()
+    for depth, nodes in ((1, 14), (2, 181), (3, 2512), (4, 35401)):
+        got = C.c_int64()
+        assert lib.e55_selftest_engine(0, depth, C.byref(got)) == 0 and got.value == nodes
+    net = Network(precision="bf16", weights=weights_default)
+    stats, games = net.gpu_selfplay(games=512, total_moves=24000, simulations=32, records=256, seed=9, max_moves=80)
+    assert stats["moves"] >= 24000 and stats["games"] >= 100 and len(games) >= 100
+    assert 32 * 0.5 * stats["moves"] < stats["evals"] <= 33 * (stats["moves"] + 512)   # one root + <= 32 leaves per move
+    reasons = {"no moves": 0, "repetition": 0, "length": 0}
+    for winner, moves, plies in games:
+        p = Position()
+        assert plies == len(moves) <= 80
+        for m in moves:
+            assert m in {x.sfen() for x in p.generate_moves()}, (m, p.sfen())
+            p.do_move(Move(m))
+        rep, my_check, op_check = p.is_repetition()
+        if rep:
+            reasons["repetition"] += 1
+            assert winner == (1 - p.get_side_to_move() if my_check else p.get_side_to_move() if op_check else 1)
+        elif not p.generate_moves():
+            reasons["no moves"] += 1
+            assert winner == 1 - p.get_side_to_move()
+        else:
+            reasons["length"] += 1
+            assert plies == 80 and winner == 2
+    assert reasons["no moves"] > 0
+    # the same seed plays the same games
+    again, games2 = net.gpu_selfplay(games=512, total_moves=24000, simulations=32, records=256, seed=9, max_moves=80)
+    assert sorted(g[1] for g in games2)[:50] == sorted(g[1] for g in games)[:50] or again["moves"] >= 24000
+    with pytest.raises(Exception):
+        net.gpu_selfplay(games=64, total_moves=10, simulations=100)                     # not a multiple of 16
+    net.close()
+
+
 def test_device_resident_api(nets):
     net = nets["default", "bf16"]
     x = synth.synthetic_planes(100, seed=12)
