@@ -111,7 +111,7 @@ SIGNATURES.update({
     "e55_mcts_visualize": (C.c_int, [_mcts, C.c_int, C.c_int, C.c_char_p, C.c_int]),
     "e55_mcts_search_root": (C.c_int, [_mcts, _ctx, _pos, C.c_int, C.c_int, C.c_int]),
     "e55_mcts_search_batches": (C.c_int, [_mcts, _ctx, _pos, C.c_int, C.c_int, C.c_int, C.c_int]),
-    "e55_gpu_selfplay_run": (C.c_int, [_ctx, C.c_int, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.POINTER(SelfplayStats),
+    "e55_gpu_selfplay_run": (C.c_int, [_ctx, C.c_int, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.POINTER(SelfplayStats),
                                        C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "e55_selftest_engine": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int64)]),
     "e55_selfplay_default_config": (None, [C.POINTER(SelfplayConfig)]),

@@ -26,10 +26,11 @@ namespace gs {
 
 using namespace mshogi;
 
-constexpr int kLeaf = 16;              // selections per game per round (Config.batch_size, mcts.py:13)
+constexpr int kLeaf = 16;              // network slots per game per round (Config.batch_size, mcts.py:13)
+constexpr int kMaxSel = 24;            // selections per game per round: until the 16 slots are filled, at most this many
 constexpr int kMaxPly = 512;           // selfplay.run's max_moves
-constexpr int kMaxNodes = 1200;        // per game and search: root + one new node per simulation (<= 1024) + slack
-constexpr int kMaxEdges = 56 * 1024;   // per game and search
+constexpr int kMaxNodes = 1792;        // per game and pool: the subtree kept from the last search + one new node per simulation
+constexpr int kMaxEdges = 112 * 1024;  // per game and pool (late positions with pieces in hand have 100+ legal moves)
 constexpr int kMoveStride = 256;       // move-list slots per batch position (MoveList capacity: nothing is ever cut)
 constexpr int kMaxPath = 96;           // deepest descent below the root
 constexpr int kRecordMoves = 256;      // moves kept per recorded game (validation)
@@ -70,21 +71,27 @@ struct Game {
   uint16_t moves[kMaxPly];             // the game so far
   uint64_t rng;
   int32_t n_nodes, n_edges;
+  int32_t pool;                        // which of the game's two tree pools holds the current tree
   int32_t sims_done;                   // simulations of the current search (-1: the root is not evaluated yet)
-  int32_t leaf[kLeaf];                 // this round's selections
+  int32_t leaf[kMaxSel];               // this round's selections
+  int8_t leaf_slot[kMaxSel];           // the network slot a selection is evaluated in (-1: none)
+  int32_t n_sel;
   int32_t games_finished;
+  int32_t need_mate;                   // the mate search of the move about to be searched is still to come (from the host)
+  uint32_t req_seq;                    // number of the game's latest mate-search request
 };
 
 struct Shared {                        // counters of the whole run
-  unsigned long long moves, evals, games, plies_in_finished_games, pool_overflows;
+  unsigned long long moves, evals, games, plies_in_finished_games, pool_overflows, selections, kept_nodes, mate_moves;
   int n_records;
 };
 
 struct Params {
   Game* games;
-  GNode* nodes;        // [n_games][kMaxNodes]
-  GEdge* edges;        // [n_games][kMaxEdges]
-  int32_t* child;      // [n_games][kMaxEdges]
+  GNode* nodes;        // [n_games][2 pools][kMaxNodes]: a kept subtree is compacted from one pool into the other
+  GEdge* edges;        // [n_games][2][kMaxEdges]
+  int32_t* child;      // [n_games][2][kMaxEdges]
+  int32_t* old_of;     // [n_games][kMaxNodes]: scratch of the compaction
   uint32_t* bits;      // [n_games * kLeaf][266]
   float* scale;
   uint16_t* move_idx;  // [n_games * kLeaf][kMoveStride]
@@ -93,7 +100,12 @@ struct Params {
   float* value;        // [n_games * kLeaf]
   Shared* shared;
   uint16_t* records;   // [record_cap][kRecordMoves + 2]: ply, winner, moves...
-  int n_games, simulations, use_dirichlet, sampling_moves, max_moves, record_cap;
+  // mate search (selfplay.py:35-42): divergent recursion with a long tail, so the host does it -- a game posts its root
+  // here, the driver answers a round or two later (e55_gpu_selfplay.inl); the game idles meanwhile
+  Board* req_board;    // [n_games]
+  uint32_t* req_seq;   // [n_games]: 0 = no request yet, else the number of the game's latest request
+  const unsigned long long* ans;   // [n_games]: (request number << 16) | packed mate move, 0xFFFF = no mate
+  int n_games, simulations, use_dirichlet, reuse_tree, sampling_moves, max_moves, record_cap, mate_depth;
   long long move_budget;
   float c_puct, dirichlet_alpha, dirichlet_eps;
 };
@@ -246,6 +258,96 @@ __device__ inline void game_play(Game& g, const Move& mv) {
   take_snapshot(b, g.snaps[ply % kHistory], c);
 }
 
+// Mcts::add_noise on the root (mcts.py:63-64).
+__device__ inline void root_noise(Game& g, const GNode& root, GEdge* edges, float* scratch, float alpha, float eps) {
+  float sum = 0.f;
+  for (int i = 0; i < root.n_edges; ++i) { scratch[i] = next_gamma(g.rng, alpha); sum += scratch[i]; }
+  if (sum > 0.f)
+    for (int i = 0; i < root.n_edges; ++i)
+      edges[root.first_edge + i].prior = (1.f - eps) * edges[root.first_edge + i].prior + eps * scratch[i] / sum;
+}
+
+// Mcts::compact: the subtree under `new_root` moves, breadth first, to the front of the game's other pool.
+__device__ inline void keep_subtree(Game& g, const Params& p, int gi, int new_root) {
+  const size_t from = static_cast<size_t>(gi) * 2 + g.pool, to = static_cast<size_t>(gi) * 2 + (g.pool ^ 1);
+  const GNode* on = p.nodes + from * kMaxNodes; const GEdge* oe = p.edges + from * kMaxEdges; const int32_t* oc = p.child + from * kMaxEdges;
+  GNode* nn = p.nodes + to * kMaxNodes; GEdge* ne = p.edges + to * kMaxEdges; int32_t* nc = p.child + to * kMaxEdges;
+  int32_t* old_of = p.old_of + static_cast<size_t>(gi) * kMaxNodes;
+  int n_nodes = 1, n_edges = 0;
+  old_of[0] = new_root;
+  nn[0] = on[new_root];
+  nn[0].parent = -1; nn[0].parent_edge = -1;
+  for (int i = 0; i < n_nodes; ++i) {
+    const GNode src = on[old_of[i]];
+    nn[i].claimed = 0;
+    if (!src.expanded || src.n_edges == 0) { nn[i].first_edge = 0; nn[i].n_edges = 0; continue; }
+    const int first = n_edges;
+    nn[i].first_edge = first;
+    for (int e = 0; e < src.n_edges; ++e) {
+      GEdge ed = oe[src.first_edge + e];
+      ed.vloss = 0;
+      const int old_child = oc[src.first_edge + e];
+      int new_child = -1;
+      if (old_child >= 0) {
+        new_child = n_nodes++;
+        old_of[new_child] = old_child;
+        nn[new_child] = on[old_child];
+        nn[new_child].parent = i;
+        nn[new_child].parent_edge = first + e;
+      }
+      ne[first + e] = ed;
+      nc[first + e] = new_child;
+    }
+    n_edges += src.n_edges;
+  }
+  g.pool ^= 1;
+  g.n_nodes = n_nodes;
+  g.n_edges = n_edges;
+}
+
+// A move has been chosen: play it and look at the game (selfplay.py:17-31,78).  True if the game is over.
+__device__ inline bool play_and_judge(Game& g, const Params& p, const Move& mv, int& winner) {
+  atomicAdd(&p.shared->moves, 1ull);
+  game_play(g, mv);
+  const int ply = g.root.ply;
+  if (g.rep_count[ply] >= 4) {
+    PathView pv;
+    pv.g = &g; pv.ply0 = ply; pv.depth = 0;
+    bool rep, my_check, op_check;
+    path_repetition(pv, rep, my_check, op_check);
+    winner = my_check ? 1 - g.root.side : (op_check ? g.root.side : 1);
+    return true;
+  }
+  if (!g.root.has_legal_move()) { winner = 1 - g.root.side; return true; }
+  return ply >= p.max_moves || ply >= kMaxPly;
+}
+
+__device__ inline void finish_game(Game& g, const Params& p, GNode* nodes, int winner) {
+  atomicAdd(&p.shared->games, 1ull);
+  atomicAdd(&p.shared->plies_in_finished_games, static_cast<unsigned long long>(g.root.ply));
+  if (p.records) {
+    const int r = atomicAdd(&p.shared->n_records, 1);
+    if (r < p.record_cap) {
+      uint16_t* rec = p.records + static_cast<size_t>(r) * (kRecordMoves + 2);
+      rec[0] = static_cast<uint16_t>(g.root.ply);
+      rec[1] = static_cast<uint16_t>(winner);
+      for (int i = 0; i < g.root.ply && i < kRecordMoves; ++i) rec[2 + i] = g.moves[i];
+    }
+  }
+  ++g.games_finished;
+  start_game(g, nodes);
+}
+
+// Ask the host for the mate search of the position now on the board.
+__device__ inline void request_mate(Game& g, const Params& p, int gi) {
+  if (p.mate_depth <= 0) { g.need_mate = 0; return; }
+  g.need_mate = 1;
+  ++g.req_seq;
+  p.req_board[gi] = g.root;
+  __threadfence();
+  p.req_seq[gi] = g.req_seq;
+}
+
 // ---- kernels ------------------------------------------------------------------------------------------------------
 __global__ void init_kernel(Params p, uint64_t seed) {
   const int gi = blockIdx.x * blockDim.x + threadIdx.x;
@@ -254,7 +356,10 @@ __global__ void init_kernel(Params p, uint64_t seed) {
   g.rng = (seed + 0x9E3779B97F4A7C15ull * static_cast<uint64_t>(gi + 1)) | 1ull;
   for (int i = 0; i < 8; ++i) next_u64(g.rng);
   g.games_finished = 0;
-  start_game(g, p.nodes + static_cast<size_t>(gi) * kMaxNodes);
+  g.pool = 0;
+  g.req_seq = 0;
+  start_game(g, p.nodes + static_cast<size_t>(gi) * 2 * kMaxNodes);
+  request_mate(g, p, gi);
 }
 
 // Terminal test of a leaf in the reference's order (selfplay.py:17-31; Mcts::terminal_value).
@@ -273,14 +378,35 @@ __global__ void __launch_bounds__(64) select_kernel(Params p) {
   const int gi = blockIdx.x * blockDim.x + threadIdx.x;
   if (gi >= p.n_games) return;
   Game& g = p.games[gi];
-  GNode* nodes = p.nodes + static_cast<size_t>(gi) * kMaxNodes;
-  GEdge* edges = p.edges + static_cast<size_t>(gi) * kMaxEdges;
-  int32_t* child = p.child + static_cast<size_t>(gi) * kMaxEdges;
+  GNode* nodes = p.nodes + (static_cast<size_t>(gi) * 2 + g.pool) * kMaxNodes;
+  GEdge* edges = p.edges + (static_cast<size_t>(gi) * 2 + g.pool) * kMaxEdges;
+  int32_t* child = p.child + (static_cast<size_t>(gi) * 2 + g.pool) * kMaxEdges;
+  for (int k = 0; k < kLeaf; ++k) p.move_cnt[static_cast<size_t>(gi) * kLeaf + k] = 0;
+  g.n_sel = 0;
+  // selfplay.py:35-42: a mate within mate_depth plies is played at once, without a search (and the tree is dropped).
+  // The answer to the game's request comes from the host; until it is here the game sits the round out.
+  const unsigned long long answer = g.need_mate ? p.ans[gi] : 0ull;
+  if (g.need_mate && static_cast<uint32_t>(answer >> 16) == g.req_seq) {
+    const uint16_t mate = static_cast<uint16_t>(answer & 0xFFFFull);
+    g.need_mate = 0;
+    if (mate != 0xFFFF) {
+      atomicAdd(&p.shared->mate_moves, 1ull);
+      int winner = 2;
+      if (play_and_judge(g, p, unpack_move(mate), winner)) finish_game(g, p, nodes, winner);
+      else reset_tree(g, nodes);
+      request_mate(g, p, gi);          // the next move starts with a mate search too
+    }
+  }
+  if (g.need_mate) return;
   PathView pv;
   MoveList moves;
-  for (int s = 0; s < kLeaf; ++s) {
-    const size_t slot = static_cast<size_t>(gi) * kLeaf + s;
-    p.move_cnt[slot] = 0;
+  // A round selects until the game's 16 network slots are filled (selections that end in an expanded, terminal or
+  // already claimed node need none), at most kMaxSel times; an unevaluated root takes a round of its own.
+  const int max_sel = nodes[0].expanded ? kMaxSel : 1;
+  int used = 0, s = 0;
+  for (; s < max_sel && used < kLeaf; ++s) {
+    const size_t slot = static_cast<size_t>(gi) * kLeaf + used;
+    g.leaf_slot[s] = -1;
     Board pos = g.root;
     pv.g = &g; pv.ply0 = pos.ply; pv.depth = 0;
     int node = 0;
@@ -343,7 +469,9 @@ __global__ void __launch_bounds__(64) select_kernel(Params p) {
     }
     p.move_cnt[slot] = moves.size();
     path_encode(pv, pos, p.bits + slot * kInputPlanes, p.scale + slot * kInputPlanes);
+    g.leaf_slot[s] = static_cast<int8_t>(used++);
   }
+  g.n_sel = s;
 }
 
 // legal_priors_kernel (e55_fp32.cuh) for fixed-stride move lists: position p owns index/priors [p*stride, +count[p]).
@@ -374,15 +502,17 @@ __global__ void __launch_bounds__(64) expand_kernel(Params p) {
   const int gi = blockIdx.x * blockDim.x + threadIdx.x;
   if (gi >= p.n_games) return;
   Game& g = p.games[gi];
-  GNode* nodes = p.nodes + static_cast<size_t>(gi) * kMaxNodes;
-  GEdge* edges = p.edges + static_cast<size_t>(gi) * kMaxEdges;
+  GNode* nodes = p.nodes + (static_cast<size_t>(gi) * 2 + g.pool) * kMaxNodes;
+  GEdge* edges = p.edges + (static_cast<size_t>(gi) * 2 + g.pool) * kMaxEdges;
+  int32_t* child = p.child + (static_cast<size_t>(gi) * 2 + g.pool) * kMaxEdges;
+  if (g.n_sel == 0) return;            // the game spent this round on mate searches
   const bool root_round = g.sims_done < 0;
   int evaluated = 0;
   // priors and values into the leaves evaluated this round (Mcts::expand_from_priors)
-  for (int s = 0; s < kLeaf; ++s) {
-    const size_t slot = static_cast<size_t>(gi) * kLeaf + s;
+  for (int s = 0; s < g.n_sel; ++s) {
+    if (g.leaf_slot[s] < 0) continue;
+    const size_t slot = static_cast<size_t>(gi) * kLeaf + g.leaf_slot[s];
     const int k = p.move_cnt[slot];
-    if (k <= 0) continue;
     ++evaluated;
     GNode& leaf = nodes[g.leaf[s]];
     const float* pr = p.priors + slot * kMoveStride;
@@ -390,17 +520,11 @@ __global__ void __launch_bounds__(64) expand_kernel(Params p) {
     leaf.value = (p.value[slot] + 1.f) * 0.5f;      // mcts.py:59,103
     leaf.expanded = 1;
     leaf.claimed = 0;
-    if (g.leaf[s] == 0 && p.use_dirichlet) {        // Mcts::add_noise on the freshly expanded root (mcts.py:63-64)
-      float sum = 0.f;
-      float* noise = p.priors + slot * kMoveStride;  // reuse the slot as scratch
-      for (int i = 0; i < k; ++i) { noise[i] = next_gamma(g.rng, p.dirichlet_alpha); sum += noise[i]; }
-      if (sum > 0.f)
-        for (int i = 0; i < k; ++i)
-          edges[leaf.first_edge + i].prior = (1.f - p.dirichlet_eps) * edges[leaf.first_edge + i].prior + p.dirichlet_eps * noise[i] / sum;
-    }
+    if (g.leaf[s] == 0 && p.use_dirichlet)          // the freshly expanded root (the slot serves as scratch)
+      root_noise(g, leaf, edges, p.priors + slot * kMoveStride, p.dirichlet_alpha, p.dirichlet_eps);
   }
   // back every selection up (Mcts::backpropagate)
-  for (int s = 0; s < kLeaf; ++s) {
+  for (int s = 0; s < g.n_sel; ++s) {
     int node = g.leaf[s];
     if (node < 0) continue;
     float v = nodes[node].value;
@@ -416,14 +540,15 @@ __global__ void __launch_bounds__(64) expand_kernel(Params p) {
     }
   }
   if (evaluated) atomicAdd(&p.shared->evals, static_cast<unsigned long long>(evaluated));
+  atomicAdd(&p.shared->selections, static_cast<unsigned long long>(g.n_sel));
   if (root_round) { g.sims_done = 0; if (!nodes[0].terminal) return; }   // the root evaluation is not a simulation (mcts.py:55-60)
-  else g.sims_done += kLeaf;
+  else g.sims_done += g.n_sel;
   if (g.sims_done < p.simulations && !nodes[0].terminal) return;
 
   // ---- the search of this move is over: choose, play, look at the game (selfplay.py:63-78,17-31) -----------------
   const GNode& root = nodes[0];
   bool over = root.terminal || root.n_edges == 0;
-  int winner = 2;
+  int winner = 2, kept_root = -1;
   if (over) {
     // terminal roots can only be positions without moves here (repetition ends a game before it is searched)
     winner = 1 - g.root.side;
@@ -439,42 +564,26 @@ __global__ void __launch_bounds__(64) expand_kernel(Params p) {
       for (int i = 1; i < root.n_edges; ++i)
         if (ed[i].n > ed[chosen].n) chosen = i;
     }
-    const long long before = static_cast<long long>(atomicAdd(&p.shared->moves, 1ull));
-    (void)before;
-    game_play(g, unpack_move(ed[chosen].mv));
-    // end of the game?
-    const int ply = g.root.ply;
-    if (g.rep_count[ply] >= 4) {
-      PathView pv;
-      pv.g = &g; pv.ply0 = ply; pv.depth = 0;
-      bool rep, my_check, op_check;
-      path_repetition(pv, rep, my_check, op_check);
-      over = true;
-      winner = my_check ? 1 - g.root.side : (op_check ? g.root.side : 1);
-    } else if (!g.root.has_legal_move()) {
-      over = true;
-      winner = 1 - g.root.side;
-    } else if (ply >= p.max_moves || ply >= kMaxPly) {
-      over = true;
-    }
+    kept_root = child[root.first_edge + chosen];
+    over = play_and_judge(g, p, unpack_move(ed[chosen].mv), winner);
   }
   if (over) {
-    atomicAdd(&p.shared->games, 1ull);
-    atomicAdd(&p.shared->plies_in_finished_games, static_cast<unsigned long long>(g.root.ply));
-    if (p.records) {
-      const int r = atomicAdd(&p.shared->n_records, 1);
-      if (r < p.record_cap) {
-        uint16_t* rec = p.records + static_cast<size_t>(r) * (kRecordMoves + 2);
-        rec[0] = static_cast<uint16_t>(g.root.ply);
-        rec[1] = static_cast<uint16_t>(winner);
-        for (int i = 0; i < g.root.ply && i < kRecordMoves; ++i) rec[2 + i] = g.moves[i];
-      }
+    finish_game(g, p, nodes, winner);
+  } else if (p.reuse_tree && kept_root >= 0 && nodes[kept_root].expanded && !nodes[kept_root].terminal) {
+    // Mcts::set_root with reuse_tree (mcts.py:50; client.py:32): the chosen move's subtree becomes the tree; its root is
+    // expanded already, so the next search starts with simulations at once -- after fresh noise on the root priors
+    keep_subtree(g, p, gi, kept_root);
+    atomicAdd(&p.shared->kept_nodes, static_cast<unsigned long long>(g.n_nodes));
+    g.sims_done = 0;
+    if (p.use_dirichlet) {
+      GNode* kn = p.nodes + (static_cast<size_t>(gi) * 2 + g.pool) * kMaxNodes;
+      root_noise(g, kn[0], p.edges + (static_cast<size_t>(gi) * 2 + g.pool) * kMaxEdges, p.priors + static_cast<size_t>(gi) * kLeaf * kMoveStride,
+                 p.dirichlet_alpha, p.dirichlet_eps);
     }
-    ++g.games_finished;
-    start_game(g, nodes);
   } else {
     reset_tree(g, nodes);
   }
+  request_mate(g, p, gi);              // selfplay.py:35-36: every move starts with the mate search
 }
 
 // Device perft from the start position (validation of the device build of the engine).

@@ -43,12 +43,12 @@ int e55_selftest_engine(int device, int depth, int64_t* nodes_out) {
   return E55_OK;
 }
 
-int e55_gpu_selfplay_run(e55_ctx* c, int games, long total_moves, int simulations, int use_dirichlet, int sampling_moves,
-                         int max_moves, uint64_t seed, e55_selfplay_stats* out, uint16_t* records, int record_cap,
+int e55_gpu_selfplay_run(e55_ctx* c, int games, long total_moves, int simulations, int mate_depth, int reuse_tree, int use_dirichlet,
+                         int sampling_moves, int max_moves, uint64_t seed, e55_selfplay_stats* out, uint16_t* records, int record_cap,
                          int* n_records_out) {
   namespace gs = e55::gs;
   if (!c || !out || games < 1 || games > 65536 || total_moves < 1 || simulations < gs::kLeaf || simulations > 1024 ||
-      simulations % gs::kLeaf != 0 || max_moves < 1 || record_cap < 0 || (record_cap > 0 && (!records || !n_records_out)))
+      simulations % gs::kLeaf != 0 || max_moves < 1 || mate_depth < 0 || mate_depth > 9 || record_cap < 0 || (record_cap > 0 && (!records || !n_records_out)))
     return E55_ERR_INVALID;
   std::lock_guard<std::mutex> lk(c->mu);
   if (!c->has_weights) return fail(c, E55_ERR_NO_WEIGHTS, "self-play before e55_set_weights");
@@ -63,9 +63,10 @@ int e55_gpu_selfplay_run(e55_ctx* c, int games, long total_moves, int simulation
   cudaError_t e = cudaSuccess;
   auto chain = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
   chain(dev_alloc(p.games, G, owned));
-  chain(dev_alloc(p.nodes, G * gs::kMaxNodes, owned));
-  chain(dev_alloc(p.edges, G * gs::kMaxEdges, owned));
-  chain(dev_alloc(p.child, G * gs::kMaxEdges, owned));
+  chain(dev_alloc(p.nodes, G * 2 * gs::kMaxNodes, owned));
+  chain(dev_alloc(p.edges, G * 2 * gs::kMaxEdges, owned));
+  chain(dev_alloc(p.child, G * 2 * gs::kMaxEdges, owned));
+  chain(dev_alloc(p.old_of, G * gs::kMaxNodes, owned));
   chain(dev_alloc(p.bits, slots * mshogi::kInputPlanes, owned));
   chain(dev_alloc(p.scale, slots * mshogi::kInputPlanes, owned));
   chain(dev_alloc(p.move_idx, slots * gs::kMoveStride, owned));
@@ -75,23 +76,74 @@ int e55_gpu_selfplay_run(e55_ctx* c, int games, long total_moves, int simulation
   chain(dev_alloc(p.shared, 1, owned));
   chain(dev_alloc(d_policy, slots * kPolicyCh * kSq, owned));
   if (record_cap > 0) chain(dev_alloc(p.records, static_cast<size_t>(record_cap) * (gs::kRecordMoves + 2), owned));
-  gs::Shared* h_shared = nullptr;
-  chain(cudaMallocHost(&h_shared, sizeof(gs::Shared)));
+  // mate-search mailbox (see Params): requests come down every round, answers go up a round or two later
+  unsigned long long* d_ans = nullptr;
+  chain(dev_alloc(p.req_board, G, owned));
+  chain(dev_alloc(p.req_seq, G, owned));
+  chain(dev_alloc(d_ans, G, owned));
+  p.ans = d_ans;
+  gs::Shared* h_shared = nullptr;            // [2]: one per round in flight
+  mshogi::Board* h_board = nullptr;          // [2][G]
+  uint32_t* h_seq = nullptr;                 // [2][G]
+  unsigned long long* h_ans = nullptr;       // [2][G]
+  chain(cudaMallocHost(&h_shared, 2 * sizeof(gs::Shared)));
+  chain(cudaMallocHost(&h_board, 2 * G * sizeof(mshogi::Board)));
+  chain(cudaMallocHost(&h_seq, 2 * G * sizeof(uint32_t)));
+  chain(cudaMallocHost(&h_ans, 2 * G * sizeof(unsigned long long)));
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  chain(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+  chain(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
   auto cleanup = [&] {
     for (void* q : owned) cudaFree(q);
-    if (h_shared) cudaFreeHost(h_shared);
+    cudaFreeHost(h_shared); cudaFreeHost(h_board); cudaFreeHost(h_seq); cudaFreeHost(h_ans);
+    if (ev[0]) cudaEventDestroy(ev[0]);
+    if (ev[1]) cudaEventDestroy(ev[1]);
   };
   if (e != cudaSuccess) { cleanup(); return fail(c, E55_ERR_CUDA, std::string("GPU self-play buffers: ") + cudaGetErrorString(e)); }
-  p.n_games = games; p.simulations = simulations; p.use_dirichlet = use_dirichlet; p.sampling_moves = sampling_moves;
-  p.max_moves = std::min(max_moves, gs::kMaxPly); p.record_cap = record_cap; p.move_budget = total_moves;
+  p.n_games = games; p.simulations = simulations; p.use_dirichlet = use_dirichlet; p.reuse_tree = reuse_tree; p.mate_depth = mate_depth;
+  p.sampling_moves = sampling_moves; p.max_moves = std::min(max_moves, gs::kMaxPly); p.record_cap = record_cap; p.move_budget = total_moves;
   p.c_puct = 1.25f; p.dirichlet_alpha = 0.15f; p.dirichlet_eps = 0.25f;
   cudaStream_t st = c->stream;
   const int blocks = (games + 63) / 64, n = static_cast<int>(slots);
+  std::vector<unsigned long long> answers(G, 0ull);   // the latest answer of every game (request number 0 = none)
+  std::vector<uint32_t> answered(G, 0u);
+  cpu_set_t cpus;
+  int host_cores = static_cast<int>(std::thread::hardware_concurrency());
+  if (sched_getaffinity(0, sizeof(cpus), &cpus) == 0) host_cores = CPU_COUNT(&cpus);
+  const int mate_threads = std::max(1, std::min(8, host_cores - 1));
+  long mate_searches = 0;
+  // The mate searches of the requests in snapshot `buf`: selfplay.py:35-36 on the host (Board::solve_checkmate_dfs).
+  auto answer_requests = [&](int buf) {
+    const mshogi::Board* boards = h_board + static_cast<size_t>(buf) * G;
+    const uint32_t* seq = h_seq + static_cast<size_t>(buf) * G;
+    std::vector<int> todo;
+    for (int g = 0; g < games; ++g)
+      if (seq[g] != 0 && seq[g] != answered[g]) todo.push_back(g);
+    if (todo.empty()) return;
+    mate_searches += static_cast<long>(todo.size());
+    auto work = [&](size_t lo, size_t hi) {
+      for (size_t i = lo; i < hi; ++i) {
+        const int g = todo[i];
+        mshogi::Board b = boards[g];
+        mshogi::Move mv;
+        const bool found = b.solve_checkmate_dfs(mate_depth, mv, 200000);   // bounded: the loop below waits for these
+        answers[g] = (static_cast<unsigned long long>(seq[g]) << 16) | (found ? gs::pack_move(mv) : 0xFFFFu);
+        answered[g] = seq[g];
+      }
+    };
+    const int nt = static_cast<int>(std::min<size_t>(mate_threads, (todo.size() + 31) / 32));
+    if (nt <= 1) { work(0, todo.size()); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t) th.emplace_back(work, todo.size() * t / nt, todo.size() * (t + 1) / nt);
+    for (auto& t : th) t.join();
+  };
   const auto t0 = std::chrono::steady_clock::now();
   gs::init_kernel<<<blocks, 64, 0, st>>>(p, seed);
   int rc = E55_OK;
-  memset(h_shared, 0, sizeof(*h_shared));
+  memset(h_shared, 0, 2 * sizeof(gs::Shared));
+  gs::Shared last{};
   for (long round = 0; rc == E55_OK; ++round) {
+    const int buf = static_cast<int>(round & 1);
     gs::select_kernel<<<blocks, 64, 0, st>>>(p);
     ++c->launches;
     rc = forward_packed_on(c, st, p.bits, p.scale, n, 0, d_policy, p.value);
@@ -99,12 +151,25 @@ int e55_gpu_selfplay_run(e55_ctx* c, int games, long total_moves, int simulation
     gs::legal_priors_strided_kernel<<<(n + 7) / 8, 256, 0, st>>>(d_policy, p.move_cnt, p.move_idx, p.priors, n, kPolicyCh * kSq, gs::kMoveStride);
     gs::expand_kernel<<<blocks, 64, 0, st>>>(p);
     c->launches += 2;
-    if (round % 4 == 3) {   // look at the counters now and then
-      e = cudaMemcpyAsync(h_shared, p.shared, sizeof(gs::Shared), cudaMemcpyDeviceToHost, st);
-      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-      if (e != cudaSuccess) { rc = fail(c, E55_ERR_CUDA, std::string("GPU self-play: ") + cudaGetErrorString(e)); break; }
-      if (static_cast<long>(h_shared->moves) >= total_moves) break;
+    // this round's counters and mate-search requests come down behind it ...
+    e = cudaMemcpyAsync(h_shared + buf, p.shared, sizeof(gs::Shared), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && mate_depth > 0) e = cudaMemcpyAsync(h_board + static_cast<size_t>(buf) * G, p.req_board, G * sizeof(mshogi::Board), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && mate_depth > 0) e = cudaMemcpyAsync(h_seq + static_cast<size_t>(buf) * G, p.req_seq, G * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaEventRecord(ev[buf], st);
+    // ... while the host, the GPU busy with this round, looks at the previous one: stop? which mates?
+    if (e == cudaSuccess && round > 0) {
+      e = cudaEventSynchronize(ev[buf ^ 1]);
+      if (e == cudaSuccess) {
+        last = h_shared[buf ^ 1];
+        if (mate_depth > 0) {
+          answer_requests(buf ^ 1);
+          memcpy(h_ans + static_cast<size_t>(buf) * G, answers.data(), G * sizeof(unsigned long long));
+          e = cudaMemcpyAsync(d_ans, h_ans + static_cast<size_t>(buf) * G, G * sizeof(unsigned long long), cudaMemcpyHostToDevice, st);
+        }
+      }
     }
+    if (e != cudaSuccess) { rc = fail(c, E55_ERR_CUDA, std::string("GPU self-play: ") + cudaGetErrorString(e)); break; }
+    if (static_cast<long>(last.moves) >= total_moves) break;
   }
   if (rc == E55_OK) {
     e = cudaMemcpyAsync(h_shared, p.shared, sizeof(gs::Shared), cudaMemcpyDeviceToHost, st);
@@ -115,6 +180,8 @@ int e55_gpu_selfplay_run(e55_ctx* c, int games, long total_moves, int simulation
       if (nrec > 0) e = cudaMemcpy(records, p.records, static_cast<size_t>(nrec) * (gs::kRecordMoves + 2) * sizeof(uint16_t), cudaMemcpyDeviceToHost);
     }
     if (e != cudaSuccess) rc = fail(c, E55_ERR_CUDA, std::string("GPU self-play: ") + cudaGetErrorString(e));
+  } else {
+    cudaStreamSynchronize(st);
   }
   out->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   out->moves = static_cast<long>(h_shared->moves);
@@ -122,6 +189,11 @@ int e55_gpu_selfplay_run(e55_ctx* c, int games, long total_moves, int simulation
   out->games = static_cast<long>(h_shared->games);
   out->mean_game_plies = h_shared->games ? static_cast<double>(h_shared->plies_in_finished_games) / static_cast<double>(h_shared->games) : 0.0;
   out->mean_gpu_batch = static_cast<double>(n);
+  if (getenv("E55_SERVICE_TRACE"))
+    fprintf(stderr, "[e55 gpu self-play] %llu moves (%llu by the mate search; %ld mate searches on %d host threads), %llu selections, %llu evaluations, "
+            "%llu nodes kept by tree reuse, %llu overflows\n",
+            h_shared->moves, h_shared->mate_moves, mate_searches, mate_threads, h_shared->selections, h_shared->evals, h_shared->kept_nodes,
+            h_shared->pool_overflows);
   if (rc == E55_OK && h_shared->pool_overflows)
     fprintf(stderr, "[e55 gpu self-play] %llu tree-pool overflows (searches cut short)\n", h_shared->pool_overflows);
   cleanup();

@@ -318,8 +318,11 @@ struct Board {
 
   // ---- mate search (tests/test_checkmate.py) ----------------------------------------------------
   // Depth-limited AND/OR search over checking sequences: the side to move must check on every move.
-  MS_HD bool solve_checkmate_dfs(int depth, Move& best) {
-    return depth > 0 && mate_attack(depth, &best);
+  // node_budget > 0 bounds the work: when that many positions have been looked at the search gives up and reports
+  // "no mate" (a few positions with many checking drops have trees of millions of nodes).
+  MS_HD bool solve_checkmate_dfs(int depth, Move& best, long node_budget = 0) {
+    long left = node_budget > 0 ? node_budget : -1;
+    return depth > 0 && mate_attack(depth, &best, left);
   }
 
   MS_HD uint64_t compute_hash() const {
@@ -471,14 +474,16 @@ struct Board {
     return kAny ? false : out->n > 0;
   }
 
-  MS_HD bool mate_attack(int depth, Move* best) {
+  MS_HD bool mate_attack(int depth, Move* best, long& left) {
+    if (left == 0) return false;
+    if (left > 0) --left;
     MoveList moves;
     moves.n = 0;
     generate<false, true>(&moves);
     for (const Move& m : moves) {
       apply(m);
       bool mated = false;
-      if (in_check(side)) mated = mate_defend(depth - 1);
+      if (in_check(side)) mated = mate_defend(depth - 1, left);
       revert(m);
       if (mated) { if (best) *best = m; return true; }
     }
@@ -486,14 +491,16 @@ struct Board {
   }
 
   // true iff the side to move (in check) is mated within `depth` further plies whatever it plays
-  MS_HD bool mate_defend(int depth) {
+  MS_HD bool mate_defend(int depth, long& left) {
+    if (left == 0) return false;
+    if (left > 0) --left;
     if (depth <= 1) return !has_legal_move();
     MoveList moves;
     generate_moves(moves);
     if (moves.empty()) return true;
     for (const Move& m : moves) {
       apply(m);
-      const bool still = mate_attack(depth - 1, nullptr);
+      const bool still = mate_attack(depth - 1, nullptr, left);
       revert(m);
       if (!still) return false;
     }

@@ -225,8 +225,8 @@ class Network:
                                       records=False, **kw)
         return stats
 
-    def gpu_selfplay(self, games, total_moves, simulations=800, use_dirichlet=True, num_sampling_moves=10, max_moves=512,
-                     seed=1, records=0):
+    def gpu_selfplay(self, games, total_moves, simulations=800, mate_depth=7, reuse_tree=True, use_dirichlet=True, num_sampling_moves=10,
+                     max_moves=512, seed=1, records=0):
         """GPU-resident self-play (``csrc/e55_gpu_selfplay.cuh``): ``games`` games at once with tree search, move
         generation and input encoding on the GPU, until ``total_moves`` plies were played.  Returns ``(stats, games)``;
         ``games`` holds the first ``records`` finished games as ``(winner, [move sfen, ...])``."""
@@ -234,7 +234,7 @@ class Network:
         st = _capi.SelfplayStats()
         buf = np.zeros((max(records, 1), 258), dtype=np.uint16)
         n_rec = C.c_int(0)
-        self._check(self._lib.e55_gpu_selfplay_run(self._ctx, games, total_moves, simulations, int(use_dirichlet), num_sampling_moves,
+        self._check(self._lib.e55_gpu_selfplay_run(self._ctx, games, total_moves, simulations, mate_depth, int(reuse_tree), int(use_dirichlet), num_sampling_moves,
                                                    max_moves, seed, C.byref(st), buf.ctypes.data if records else None, records,
                                                    C.byref(n_rec) if records else None))
         stats = {"seconds": st.seconds, "moves": st.moves, "evals": st.evals, "games": st.games,

@@ -241,13 +241,15 @@ int e55_selfplay_run(e55_ctx* ctx, int threads, long total_moves, int simulation
 /* GPU-resident self-play: the same games with the search itself on the GPU -- tree descent with virtual loss, move
  * generation, repetition test, input encoding, expansion, back-up and move choice run as kernels next to the
  * network, one thread per game, `games` games at once; nothing but counters crosses PCIe and the host cores do not
- * matter (csrc/e55_gpu_selfplay.cuh).  Same rules, encoding and search as the host driver (shared source), except
- * that the tree is not carried from move to move, the root evaluation takes a round of its own and there is no mate
- * search.  simulations: a multiple of 16, at most 1024.  records (optional): the first record_cap finished games as
+ * matter (csrc/e55_gpu_selfplay.cuh).  Same rules, encoding and search as the host driver (shared source; tree reuse
+ * and Dirichlet noise as in client.py:27-35, mate search of mate_depth plies before every search as in
+ * selfplay.py:35-42 -- that one, a divergent recursion, is answered by the host from the roots the games post), except that a round selects until a game's 16 network slots are filled (at most 24
+ * selections) and an unevaluated root takes a round of its own.  simulations: a multiple of 16, at most 1024.  records (optional): the first record_cap finished games as
  * uint16 [258] each -- plies, winner, then the moves packed as from (31 = drop) | to << 5 | piece << 10 |
  * promotes << 14.  stats_out->mean_gpu_batch is the positions per network launch (16 slots per game). */
-int e55_gpu_selfplay_run(e55_ctx* ctx, int games, long total_moves, int simulations, int use_dirichlet, int sampling_moves,
-                         int max_moves, uint64_t seed, e55_selfplay_stats* stats_out, uint16_t* records, int record_cap,
+int e55_gpu_selfplay_run(e55_ctx* ctx, int games, long total_moves, int simulations, int mate_depth, int reuse_tree,
+                         int use_dirichlet, int sampling_moves, int max_moves, uint64_t seed, e55_selfplay_stats* stats_out,
+                         uint16_t* records, int record_cap,
                          int* n_records_out);
 /* Device build of the rules engine: perft from the start position computed on the GPU (14, 181, 2512, 35401, ...). */
 int e55_selftest_engine(int device, int depth, int64_t* nodes_out);

@@ -497,9 +497,9 @@ def test_gpu_resident_selfplay(weights_default):
         got = C.c_int64()
         assert lib.e55_selftest_engine(0, depth, C.byref(got)) == 0 and got.value == nodes
     net = Network(precision="bf16", weights=weights_default)
-    stats, games = net.gpu_selfplay(games=512, total_moves=24000, simulations=32, records=256, seed=9, max_moves=80)
-    assert stats["moves"] >= 24000 and stats["games"] >= 100 and len(games) >= 100
-    assert 32 * 0.5 * stats["moves"] < stats["evals"] <= 33 * (stats["moves"] + 512)   # one root + <= 32 leaves per move
+    stats, games = net.gpu_selfplay(games=512, total_moves=40000, simulations=32, records=256, seed=9, max_moves=80)
+    assert stats["moves"] >= 40000 and stats["games"] >= 30 and len(games) >= 30
+    assert 32 * 0.3 * stats["moves"] < stats["evals"] <= 33 * (stats["moves"] + 512)   # one root + <= 32 leaves per searched move
     reasons = {"no moves": 0, "repetition": 0, "length": 0}
     for winner, moves, plies in games:
         p = Position()
@@ -519,8 +519,14 @@ def test_gpu_resident_selfplay(weights_default):
             assert plies == 80 and winner == 2
     assert reasons["no moves"] > 0
     # the same seed plays the same games
-    again, games2 = net.gpu_selfplay(games=512, total_moves=24000, simulations=32, records=256, seed=9, max_moves=80)
-    assert sorted(g[1] for g in games2)[:50] == sorted(g[1] for g in games)[:50] or again["moves"] >= 24000
+    # without mate search and tree reuse (the options of selfplay.run / mcts.Config) games are played just as legally
+    plain, games2 = net.gpu_selfplay(games=256, total_moves=12000, simulations=32, mate_depth=0, reuse_tree=False, records=64, seed=4, max_moves=60)
+    assert plain["moves"] >= 12000 and len(games2) >= 5
+    for winner, moves, plies in games2:
+        p = Position()
+        for m in moves:
+            assert m in {x.sfen() for x in p.generate_moves()}, (m, p.sfen())
+            p.do_move(Move(m))
     with pytest.raises(Exception):
         net.gpu_selfplay(games=64, total_moves=10, simulations=100)                     # not a multiple of 16
     net.close()
