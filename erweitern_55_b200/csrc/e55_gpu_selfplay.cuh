@@ -33,7 +33,7 @@ constexpr int kMaxNodes = 1792;        // per game and pool: the subtree kept fr
 constexpr int kMaxEdges = 112 * 1024;  // per game and pool (late positions with pieces in hand have 100+ legal moves)
 constexpr int kMoveStride = 256;       // move-list slots per batch position (MoveList capacity: nothing is ever cut)
 constexpr int kMaxPath = 96;           // deepest descent below the root
-constexpr int kRecordMoves = 256;      // moves kept per recorded game (validation)
+constexpr int kRecordWords = 16384;    // uint16 words of one game record (see finish_game)
 
 struct GNode {
   int32_t parent, parent_edge, first_edge;
@@ -77,6 +77,7 @@ struct Game {
   int8_t leaf_slot[kMaxSel];           // the network slot a selection is evaluated in (-1: none)
   int32_t n_sel;
   int32_t games_finished;
+  int32_t rec_words;                   // words of the game's record written so far
   int32_t need_mate;                   // the mate search of the move about to be searched is still to come (from the host)
   uint32_t req_seq;                    // number of the game's latest mate-search request
 };
@@ -99,7 +100,8 @@ struct Params {
   float* priors;       // [n_games * kLeaf][kMoveStride]
   float* value;        // [n_games * kLeaf]
   Shared* shared;
-  uint16_t* records;   // [record_cap][kRecordMoves + 2]: ply, winner, moves...
+  uint16_t* records;   // [record_cap][kRecordWords]: finished games, in the layout of finish_game
+  uint16_t* rec_buf;   // [n_games][kRecordWords]: the record of the game in progress (null: no records wanted)
   // mate search (selfplay.py:35-42): divergent recursion with a long tail, so the host does it -- a game posts its root
   // here, the driver answers a round or two later (e55_gpu_selfplay.inl); the game idles meanwhile
   Board* req_board;    // [n_games]
@@ -305,6 +307,34 @@ __device__ inline void keep_subtree(Game& g, const Params& p, int gi, int new_ro
   g.n_edges = n_edges;
 }
 
+// One ply of the game record, as selfplay.run keeps it (selfplay.py:80-92; gamerecord.py:5): the move, then
+// search.dump(root) = (sum_N, Q, [(move, N), ...]) -- four words (move, sum_N, Q * 65535, k) and k (move, N) pairs.
+// A mate-search move is (1, 1.0, [(move, 1)]).  A record that would not fit loses its visit lists (k = 0), not its moves.
+__device__ inline void record_ply(Game& g, const Params& p, int gi, uint16_t mv, const GNode* root, const GEdge* edges) {
+  if (!p.rec_buf) return;
+  uint16_t* rec = p.rec_buf + static_cast<size_t>(gi) * kRecordWords;
+  int w = g.rec_words;
+  if (w + 4 > kRecordWords - 4) return;
+  int k = 0, sum_n = 0;
+  float wsum = 0.f;
+  if (root)
+    for (int i = 0; i < root->n_edges; ++i) { const GEdge& e = edges[root->first_edge + i]; sum_n += e.n; wsum += e.w; k += e.n > 0; }
+  const bool fits = w + 4 + 2 * k <= kRecordWords - 4;
+  rec[w++] = mv;
+  rec[w++] = static_cast<uint16_t>(root ? (sum_n > 65535 ? 65535 : sum_n) : 1);
+  rec[w++] = static_cast<uint16_t>(root ? (sum_n > 0 ? wsum / static_cast<float>(sum_n) : root->value) * 65535.f + 0.5f : 65535.f);
+  if (!root) { rec[w++] = 1; rec[w++] = mv; rec[w++] = 1; }
+  else if (!fits) rec[w++] = 0;
+  else {
+    rec[w++] = static_cast<uint16_t>(k);
+    for (int i = 0; i < root->n_edges; ++i) {
+      const GEdge& e = edges[root->first_edge + i];
+      if (e.n > 0) { rec[w++] = e.mv; rec[w++] = static_cast<uint16_t>(e.n > 65535 ? 65535 : e.n); }
+    }
+  }
+  g.rec_words = w;
+}
+
 // A move has been chosen: play it and look at the game (selfplay.py:17-31,78).  True if the game is over.
 __device__ inline bool play_and_judge(Game& g, const Params& p, const Move& mv, int& winner) {
   atomicAdd(&p.shared->moves, 1ull);
@@ -322,18 +352,22 @@ __device__ inline bool play_and_judge(Game& g, const Params& p, const Move& mv, 
   return ply >= p.max_moves || ply >= kMaxPly;
 }
 
-__device__ inline void finish_game(Game& g, const Params& p, GNode* nodes, int winner) {
+__device__ inline void finish_game(Game& g, const Params& p, int gi, GNode* nodes, int winner) {
   atomicAdd(&p.shared->games, 1ull);
   atomicAdd(&p.shared->plies_in_finished_games, static_cast<unsigned long long>(g.root.ply));
-  if (p.records) {
+  if (p.records && p.rec_buf) {        // the finished game: [plies, winner, words, 0] + its plies (record_ply)
     const int r = atomicAdd(&p.shared->n_records, 1);
     if (r < p.record_cap) {
-      uint16_t* rec = p.records + static_cast<size_t>(r) * (kRecordMoves + 2);
-      rec[0] = static_cast<uint16_t>(g.root.ply);
-      rec[1] = static_cast<uint16_t>(winner);
-      for (int i = 0; i < g.root.ply && i < kRecordMoves; ++i) rec[2 + i] = g.moves[i];
+      uint16_t* out = p.records + static_cast<size_t>(r) * kRecordWords;
+      const uint16_t* rec = p.rec_buf + static_cast<size_t>(gi) * kRecordWords;
+      out[0] = static_cast<uint16_t>(g.root.ply);
+      out[1] = static_cast<uint16_t>(winner);
+      out[2] = static_cast<uint16_t>(g.rec_words);
+      out[3] = 0;
+      for (int i = 0; i < g.rec_words; ++i) out[4 + i] = rec[i];
     }
   }
+  g.rec_words = 0;
   ++g.games_finished;
   start_game(g, nodes);
 }
@@ -358,6 +392,7 @@ __global__ void init_kernel(Params p, uint64_t seed) {
   g.games_finished = 0;
   g.pool = 0;
   g.req_seq = 0;
+  g.rec_words = 0;
   start_game(g, p.nodes + static_cast<size_t>(gi) * 2 * kMaxNodes);
   request_mate(g, p, gi);
 }
@@ -392,7 +427,8 @@ __global__ void __launch_bounds__(64) select_kernel(Params p) {
     if (mate != 0xFFFF) {
       atomicAdd(&p.shared->mate_moves, 1ull);
       int winner = 2;
-      if (play_and_judge(g, p, unpack_move(mate), winner)) finish_game(g, p, nodes, winner);
+      record_ply(g, p, gi, mate, nullptr, nullptr);
+      if (play_and_judge(g, p, unpack_move(mate), winner)) finish_game(g, p, gi, nodes, winner);
       else reset_tree(g, nodes);
       request_mate(g, p, gi);          // the next move starts with a mate search too
     }
@@ -565,10 +601,11 @@ __global__ void __launch_bounds__(64) expand_kernel(Params p) {
         if (ed[i].n > ed[chosen].n) chosen = i;
     }
     kept_root = child[root.first_edge + chosen];
+    record_ply(g, p, gi, ed[chosen].mv, &root, edges);
     over = play_and_judge(g, p, unpack_move(ed[chosen].mv), winner);
   }
   if (over) {
-    finish_game(g, p, nodes, winner);
+    finish_game(g, p, gi, nodes, winner);
   } else if (p.reuse_tree && kept_root >= 0 && nodes[kept_root].expanded && !nodes[kept_root].terminal) {
     // Mcts::set_root with reuse_tree (mcts.py:50; client.py:32): the chosen move's subtree becomes the tree; its root is
     // expanded already, so the next search starts with simulations at once -- after fresh noise on the root priors

@@ -75,7 +75,10 @@ int e55_gpu_selfplay_run(e55_ctx* c, int games, long total_moves, int simulation
   chain(dev_alloc(p.value, slots, owned));
   chain(dev_alloc(p.shared, 1, owned));
   chain(dev_alloc(d_policy, slots * kPolicyCh * kSq, owned));
-  if (record_cap > 0) chain(dev_alloc(p.records, static_cast<size_t>(record_cap) * (gs::kRecordMoves + 2), owned));
+  if (record_cap > 0) {
+    chain(dev_alloc(p.records, static_cast<size_t>(record_cap) * gs::kRecordWords, owned));
+    chain(dev_alloc(p.rec_buf, G * gs::kRecordWords, owned));
+  }
   // mate-search mailbox (see Params): requests come down every round, answers go up a round or two later
   unsigned long long* d_ans = nullptr;
   chain(dev_alloc(p.req_board, G, owned));
@@ -177,7 +180,7 @@ int e55_gpu_selfplay_run(e55_ctx* c, int games, long total_moves, int simulation
     if (e == cudaSuccess && record_cap > 0) {
       const int nrec = std::min(h_shared->n_records, record_cap);
       *n_records_out = nrec;
-      if (nrec > 0) e = cudaMemcpy(records, p.records, static_cast<size_t>(nrec) * (gs::kRecordMoves + 2) * sizeof(uint16_t), cudaMemcpyDeviceToHost);
+      if (nrec > 0) e = cudaMemcpy(records, p.records, static_cast<size_t>(nrec) * gs::kRecordWords * sizeof(uint16_t), cudaMemcpyDeviceToHost);
     }
     if (e != cudaSuccess) rc = fail(c, E55_ERR_CUDA, std::string("GPU self-play: ") + cudaGetErrorString(e));
   } else {

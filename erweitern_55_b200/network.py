@@ -228,15 +228,18 @@ class Network:
     def gpu_selfplay(self, games, total_moves, simulations=800, mate_depth=7, reuse_tree=True, use_dirichlet=True, num_sampling_moves=10,
                      max_moves=512, seed=1, records=0):
         """GPU-resident self-play (``csrc/e55_gpu_selfplay.cuh``): ``games`` games at once with tree search, move
-        generation and input encoding on the GPU, until ``total_moves`` plies were played.  Returns ``(stats, games)``;
-        ``games`` holds the first ``records`` finished games as ``(winner, [move sfen, ...])``."""
-        from .minishogi import Move
+        generation and input encoding on the GPU (the host only answers the mate searches), until ``total_moves`` plies
+        were played.  Returns ``(stats, game_records)``; ``game_records`` holds the first ``records`` finished games as
+        :class:`erweitern_55_b200.gamerecord.GameRecord` -- what ``selfplay.run`` returns (selfplay.py:10-113)."""
+        import time
+        from .gamerecord import GameRecord
         st = _capi.SelfplayStats()
-        buf = np.zeros((max(records, 1), 258), dtype=np.uint16)
+        words = 16384
+        buf = np.zeros((max(records, 1), words), dtype=np.uint16)
         n_rec = C.c_int(0)
-        self._check(self._lib.e55_gpu_selfplay_run(self._ctx, games, total_moves, simulations, mate_depth, int(reuse_tree), int(use_dirichlet), num_sampling_moves,
-                                                   max_moves, seed, C.byref(st), buf.ctypes.data if records else None, records,
-                                                   C.byref(n_rec) if records else None))
+        self._check(self._lib.e55_gpu_selfplay_run(self._ctx, games, total_moves, simulations, mate_depth, int(reuse_tree), int(use_dirichlet),
+                                                   num_sampling_moves, max_moves, seed, C.byref(st), buf.ctypes.data if records else None,
+                                                   records, C.byref(n_rec) if records else None))
         stats = {"seconds": st.seconds, "moves": st.moves, "evals": st.evals, "games": st.games,
                  "mean_game_plies": st.mean_game_plies, "slots_per_launch": st.mean_gpu_batch,
                  "moves_per_s": st.moves / st.seconds, "evals_per_s": st.evals / st.seconds}
@@ -246,10 +249,22 @@ class Network:
             frm, to, piece, promo = mv & 31, (mv >> 5) & 31, (mv >> 10) & 15, (mv >> 14) & 1
             sq = lambda q: "%d%s" % (5 - q % 5, "abcde"[q // 5])
             return letters[piece] + "*" + sq(to) if frm == 31 else sq(frm) + sq(to) + ("+" if promo else "")
-        out = []
+        out, now = [], int(time.time())
         for r in range(n_rec.value):
-            plies, winner = int(buf[r, 0]), int(buf[r, 1])
-            out.append((winner, [sfen(int(m)) for m in buf[r, 2:2 + min(plies, 256)]], plies))
+            row = buf[r]
+            rec = GameRecord()
+            rec.winner, used, w = int(row[1]), int(row[2]), 4
+            while w < 4 + used:
+                mv, sum_n, q, k = int(row[w]), int(row[w + 1]), int(row[w + 2]) / 65535.0, int(row[w + 3])
+                visits = [(sfen(int(row[w + 4 + 2 * i])), int(row[w + 5 + 2 * i])) for i in range(k)]
+                w += 4 + 2 * k
+                rec.sfen_kif.append(sfen(mv))
+                rec.mcts_result.append((sum_n, q, visits))
+                rec.learning_target_plys.append(rec.ply)
+                rec.ply += 1
+            rec.timestamp = now
+            rec.complete = rec.ply == int(row[0])      # False if the record buffer was too small for this game
+            out.append(rec)
         return stats, out
 
     def bench_selfplay(self, workers, moves, simulations=800, leaf_batch=16):

@@ -501,31 +501,38 @@ def test_gpu_resident_selfplay(weights_default):
     assert stats["moves"] >= 40000 and stats["games"] >= 30 and len(games) >= 30
     assert 32 * 0.3 * stats["moves"] < stats["evals"] <= 33 * (stats["moves"] + 512)   # one root + <= 32 leaves per searched move
     reasons = {"no moves": 0, "repetition": 0, "length": 0}
-    for winner, moves, plies in games:
+    mates = 0
+    for rec in games:                                                   # GameRecord objects, as selfplay.run returns them
         p = Position()
-        assert plies == len(moves) <= 80
-        for m in moves:
-            assert m in {x.sfen() for x in p.generate_moves()}, (m, p.sfen())
+        assert rec.complete and rec.ply == len(rec.sfen_kif) == len(rec.mcts_result) <= 80
+        for m, (sum_n, q, visits) in zip(rec.sfen_kif, rec.mcts_result):
+            legal = {x.sfen() for x in p.generate_moves()}
+            assert m in legal and {v for v, _ in visits} <= legal and 0.0 <= q <= 1.0, (m, p.sfen())
+            assert sum_n == sum(n for _, n in visits) and dict(visits).get(m, 0) > 0
+            if (sum_n, visits) == (1, [(m, 1)]):                         # a mate-search move (selfplay.py:82-84)
+                mates += 1
+                assert p.solve_checkmate_dfs(7)[0]
+            else:
+                assert sum_n >= 32                                       # a full search (more when the tree was reused)
             p.do_move(Move(m))
         rep, my_check, op_check = p.is_repetition()
         if rep:
             reasons["repetition"] += 1
-            assert winner == (1 - p.get_side_to_move() if my_check else p.get_side_to_move() if op_check else 1)
+            assert rec.winner == (1 - p.get_side_to_move() if my_check else p.get_side_to_move() if op_check else 1)
         elif not p.generate_moves():
             reasons["no moves"] += 1
-            assert winner == 1 - p.get_side_to_move()
+            assert rec.winner == 1 - p.get_side_to_move()
         else:
             reasons["length"] += 1
-            assert plies == 80 and winner == 2
-    assert reasons["no moves"] > 0
-    # the same seed plays the same games
+            assert rec.ply == 80 and rec.winner == 2
+    assert reasons["no moves"] > 0 and mates > 0
     # without mate search and tree reuse (the options of selfplay.run / mcts.Config) games are played just as legally
     plain, games2 = net.gpu_selfplay(games=256, total_moves=12000, simulations=32, mate_depth=0, reuse_tree=False, records=64, seed=4, max_moves=60)
     assert plain["moves"] >= 12000 and len(games2) >= 5
-    for winner, moves, plies in games2:
+    for rec in games2:
         p = Position()
-        for m in moves:
-            assert m in {x.sfen() for x in p.generate_moves()}, (m, p.sfen())
+        for m, (sum_n, q, visits) in zip(rec.sfen_kif, rec.mcts_result):
+            assert m in {x.sfen() for x in p.generate_moves()} and 32 <= sum_n <= 56, (m, p.sfen(), sum_n)
             p.do_move(Move(m))
     with pytest.raises(Exception):
         net.gpu_selfplay(games=64, total_moves=10, simulations=100)                     # not a multiple of 16

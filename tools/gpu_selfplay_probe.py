@@ -12,16 +12,15 @@ net = Network(precision="bf16", weights=W.init_weights(seed=55))
 stats, games = net.gpu_selfplay(games=256, total_moves=3000, simulations=64, records=64, seed=3)
 print(stats, len(games), flush=True)
 bad = 0
-for winner, moves, plies in games:
+for rec in games:
     p = Position()
-    for m in moves:
+    for m in rec.sfen_kif:
         if m not in {x.sfen() for x in p.generate_moves()}:
             bad += 1; print("ILLEGAL", m, "in", p.sfen()); break
         p.do_move(Move(m))
     else:
-        if plies <= 256:
-            over = (not p.generate_moves()) or p.is_repetition()[0] or plies >= 512
-            if not over: bad += 1; print("game not over?", p.sfen(), winner, plies)
+        if not ((not p.generate_moves()) or p.is_repetition()[0] or rec.ply >= 512):
+            bad += 1; print("game not over?", p.sfen(), rec.winner, rec.ply)
 print("validated", len(games), "games, problems:", bad, flush=True)
 for g in (int(a) for a in sys.argv[1:]):
     stats, _ = net.gpu_selfplay(games=g, total_moves=max(2000, g * 4), simulations=800, seed=5)
