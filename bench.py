@@ -180,6 +180,8 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--selfplay-workers", type=int, default=1, help="0 = skip the self-play runs")
     ap.add_argument("--selfplay-moves", type=int, default=8, help="moves per worker thread in the synthetic self-play run")
+    ap.add_argument("--gpu-games", type=int, default=16384, help="games in flight per GPU in the GPU-resident self-play run (0 = skip)")
+    ap.add_argument("--gpu-plies", type=int, default=8, help="plies per game slot in the GPU-resident self-play run")
     ap.add_argument("--selfplay-total-moves", type=int, default=24000, help="plies played per GPU in the real self-play run")
     ap.add_argument("--blocks", type=int, default=7, help="residual blocks (20 with --filters 256 = BASELINE configs[4])")
     ap.add_argument("--filters", type=int, default=128, choices=[128, 256])
@@ -423,6 +425,26 @@ def main():
                             "(bit-packed planes + 30 legal moves each, the shape mcts.MCTS.run produces, mcts.py:91-106) in flight on "
                             "asynchronous tickets; no tree work, no move generation"}
 
+    # ---- GPU-resident self-play: the search itself on the GPU, no host game threads ---------------------------
+    selfplay_gpu = None
+    if args.selfplay_workers > 0 and args.precision == "bf16" and (args.blocks, args.filters) == (7, 128) and args.gpu_games > 0:
+        net.gpu_selfplay(games=args.gpu_games, total_moves=args.gpu_games, simulations=800, seed=77 + rank)   # warm-up
+        barrier()
+        gs, _ = net.gpu_selfplay(games=args.gpu_games, total_moves=args.gpu_games * args.gpu_plies, simulations=800, mate_depth=7,
+                                 seed=5 + rank)
+        barrier()
+        g_mv, _ = sharding.aggregate(gs["moves_per_s"], 1.0, device=dev)
+        g_ev, _ = sharding.aggregate(gs["evals_per_s"], 1.0, device=dev)
+        selfplay_gpu = {"moves_per_s": g_mv, "evals_per_s": g_ev, "games_in_flight_per_gpu": args.gpu_games,
+                        "plies_per_game_slot": args.gpu_plies, "games_finished_rank0": gs["games"],
+                        "mean_game_plies_rank0": gs["mean_game_plies"], "simulations_per_move": 800, "mate_search_plies": 7,
+                        "host_game_threads": 0,
+                        "note": "the same self-play with the search on the GPU (csrc/e55_gpu_selfplay.cuh): one thread per game does "
+                                "the PUCT descent with virtual loss, move generation, repetition test, input encoding, expansion, "
+                                "back-up and move choice between the network launches (16 slots per game per launch); tree reuse "
+                                "and Dirichlet noise as in client.py; the host only answers the 7-ply mate searches.  All games start "
+                                "together at ply 0, so a short run sees mostly openings (cheaper positions, few mates)"}
+
     # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------------
     cpu_baseline = None
     if rank == 0 and world == 1:
@@ -455,7 +477,7 @@ def main():
                                     "value_one_in_flight = kernels strictly one after the other" % B,
                        "l2": f"inputs rotate over {n_pool} distinct device batches = {n_pool * in_bytes >> 20} MiB > 126 MiB L2",
                        "flop_per_position": flops, "host_cpu": model, "host_cores_per_rank": len(my_cores), "host_cores": ncpu},
-            "value_one_in_flight": value_one_in_flight, "e2e": e2e, "e2e_packed": e2e_packed, "selfplay": selfplay_real, "selfplay_synthetic": selfplay, "gpu_launches": launches, "clocks": clocks.summary(),
+            "value_one_in_flight": value_one_in_flight, "e2e": e2e, "e2e_packed": e2e_packed, "selfplay": selfplay_real, "selfplay_gpu": selfplay_gpu, "selfplay_synthetic": selfplay, "gpu_launches": launches, "clocks": clocks.summary(),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "wall_s": t_wall,
         }
         sys.stdout.flush()
