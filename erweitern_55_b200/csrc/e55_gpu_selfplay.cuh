@@ -68,6 +68,7 @@ struct Game {
   uint8_t gave_check[kMaxPly + 2];
   uint8_t rep_count[kMaxPly + 2];
   Snapshot snaps[kHistory];            // the last 8 positions, slot = ply % 8
+  uint64_t seen[2][8];                 // 512-bit Bloom filter of the keys of the game, per side to move: "never seen" needs no scan
   uint16_t moves[kMaxPly];             // the game so far
   uint64_t rng;
   int32_t n_nodes, n_edges;
@@ -159,14 +160,23 @@ struct PathView {
   __device__ int last() const { return ply0 + depth; }
 };
 
+__device__ inline bool maybe_seen(const Game& g, int parity, uint64_t key) { return (g.seen[parity][(key >> 6) & 7] >> (key & 63)) & 1ull; }
+__device__ inline void mark_seen(Game& g, int parity, uint64_t key) { g.seen[parity][(key >> 6) & 7] |= 1ull << (key & 63); }
+
 // Position::push_history for a descent: key, check flag, repetition count, snapshot of the position after `m`.
 __device__ inline void path_push(PathView& pv, const Board& after, uint64_t key, bool check) {
   const int d = ++pv.depth, ply = pv.ply0 + d;
   pv.hash[d] = key;
   pv.check[d] = check ? 1 : 0;
   int c = 1;
-  for (int i = ply - 2; i >= 0; i -= 2)
-    if (pv.key(i) == key) { c += pv.rep_count(i); break; }
+  // earlier occurrences with the same side to move: first along the path (local), then -- only if the game's filter
+  // does not rule it out -- through the game's history
+  int i = ply - 2;
+  for (; i > pv.ply0; i -= 2)
+    if (pv.hash[i - pv.ply0] == key) { c += pv.rep[i - pv.ply0]; break; }
+  if (c == 1 && i <= pv.ply0 && maybe_seen(*pv.g, ply & 1, key))
+    for (; i >= 0; i -= 2)
+      if (pv.g->hashes[i] == key) { c += pv.g->rep_count[i]; break; }
   pv.rep[d] = static_cast<uint8_t>(c > 255 ? 255 : c);
   take_snapshot(after, pv.snap[ply % kHistory], c);
 }
@@ -235,6 +245,8 @@ __device__ inline void start_game(Game& g, GNode* nodes) {
   b.put(sq_of(1, 4), PAWN, WHITE);
   b.put(sq_of(3, 0), PAWN, BLACK);
   g.hashes[0] = b.compute_hash();
+  for (int k = 0; k < 8; ++k) g.seen[0][k] = g.seen[1][k] = 0ull;
+  mark_seen(g, 0, g.hashes[0]);
   g.gave_check[0] = 0;
   g.rep_count[0] = 1;
   take_snapshot(b, g.snaps[0], 1);
@@ -257,6 +269,7 @@ __device__ inline void game_play(Game& g, const Move& mv) {
   for (int i = ply - 2; i >= 0; i -= 2)
     if (g.hashes[i] == key) { c += g.rep_count[i]; break; }
   g.rep_count[ply] = static_cast<uint8_t>(c > 255 ? 255 : c);
+  mark_seen(g, ply & 1, key);
   take_snapshot(b, g.snaps[ply % kHistory], c);
 }
 

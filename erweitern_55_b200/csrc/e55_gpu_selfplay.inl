@@ -145,15 +145,35 @@ int e55_gpu_selfplay_run(e55_ctx* c, int games, long total_moves, int simulation
   int rc = E55_OK;
   memset(h_shared, 0, 2 * sizeof(gs::Shared));
   gs::Shared last{};
+  const bool trace = getenv("E55_SERVICE_TRACE") != nullptr;
+  cudaEvent_t te[5] = {};
+  double t_sel = 0, t_net = 0, t_pri = 0, t_exp = 0;
+  long t_rounds = 0;
+  if (trace) for (auto& x : te) cudaEventCreate(&x);
   for (long round = 0; rc == E55_OK; ++round) {
     const int buf = static_cast<int>(round & 1);
+    const bool timed = trace && round % 16 == 8;
+    if (timed) cudaEventRecord(te[0], st);
     gs::select_kernel<<<blocks, 64, 0, st>>>(p);
     ++c->launches;
+    if (timed) cudaEventRecord(te[1], st);
     rc = forward_packed_on(c, st, p.bits, p.scale, n, 0, d_policy, p.value);
     if (rc) break;
+    if (timed) cudaEventRecord(te[2], st);
     gs::legal_priors_strided_kernel<<<(n + 7) / 8, 256, 0, st>>>(d_policy, p.move_cnt, p.move_idx, p.priors, n, kPolicyCh * kSq, gs::kMoveStride);
+    if (timed) cudaEventRecord(te[3], st);
     gs::expand_kernel<<<blocks, 64, 0, st>>>(p);
     c->launches += 2;
+    if (timed) {
+      cudaEventRecord(te[4], st);
+      cudaEventSynchronize(te[4]);
+      float ms;
+      cudaEventElapsedTime(&ms, te[0], te[1]); t_sel += ms;
+      cudaEventElapsedTime(&ms, te[1], te[2]); t_net += ms;
+      cudaEventElapsedTime(&ms, te[2], te[3]); t_pri += ms;
+      cudaEventElapsedTime(&ms, te[3], te[4]); t_exp += ms;
+      ++t_rounds;
+    }
     // this round's counters and mate-search requests come down behind it ...
     e = cudaMemcpyAsync(h_shared + buf, p.shared, sizeof(gs::Shared), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && mate_depth > 0) e = cudaMemcpyAsync(h_board + static_cast<size_t>(buf) * G, p.req_board, G * sizeof(mshogi::Board), cudaMemcpyDeviceToHost, st);
@@ -192,7 +212,11 @@ int e55_gpu_selfplay_run(e55_ctx* c, int games, long total_moves, int simulation
   out->games = static_cast<long>(h_shared->games);
   out->mean_game_plies = h_shared->games ? static_cast<double>(h_shared->plies_in_finished_games) / static_cast<double>(h_shared->games) : 0.0;
   out->mean_gpu_batch = static_cast<double>(n);
-  if (getenv("E55_SERVICE_TRACE"))
+  if (trace && t_rounds)
+    fprintf(stderr, "[e55 gpu self-play] per round (ms): select %.2f, network %.2f, legal priors %.2f, expand %.2f\n", t_sel / t_rounds,
+            t_net / t_rounds, t_pri / t_rounds, t_exp / t_rounds);
+  if (trace) for (auto& x : te) cudaEventDestroy(x);
+  if (trace)
     fprintf(stderr, "[e55 gpu self-play] %llu moves (%llu by the mate search; %ld mate searches on %d host threads), %llu selections, %llu evaluations, "
             "%llu nodes kept by tree reuse, %llu overflows\n",
             h_shared->moves, h_shared->mate_moves, mate_searches, mate_threads, h_shared->selections, h_shared->evals, h_shared->kept_nodes,
