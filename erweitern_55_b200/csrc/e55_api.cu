@@ -945,7 +945,7 @@ int e55_debug_profile(e55_ctx* c, int enable, uint64_t* counters_out) {
     E55_CUDA(c, cudaMemcpy(counters_out, c->tc.d_prof, kProfWords * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   if (enable && !c->tc.d_prof) E55_CUDA(c, cudaMalloc(&c->tc.d_prof, kProfWords * sizeof(uint64_t)));
   if (!enable && c->tc.d_prof) { cudaFree(c->tc.d_prof); c->tc.d_prof = nullptr; }
-  if (c->tc.d_prof) E55_CUDA(c, cudaMemset(c->tc.d_prof, 0, kProfWords * sizeof(uint64_t)));
+  if (c->tc.d_prof) E55_CUDA(c, cudaMemsetAsync(c->tc.d_prof, 0, kProfWords * sizeof(uint64_t), c->stream));   // ordered with the kernels
   return E55_OK;
 }
 

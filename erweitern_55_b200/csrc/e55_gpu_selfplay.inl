@@ -18,10 +18,12 @@ cudaError_t device_engine_ready() {
   return g_engine_status;
 }
 
+// Zeroed device memory; the zeroing is ordered on `stream` like everything else the run does (a cudaMemset on the
+// default stream is not ordered against kernels on a non-blocking stream and could wipe what the first kernel wrote).
 template <class T>
-cudaError_t dev_alloc(T*& ptr, size_t count, std::vector<void*>& owned) {
+cudaError_t dev_alloc(T*& ptr, size_t count, std::vector<void*>& owned, cudaStream_t stream) {
   cudaError_t e = cudaMalloc(&ptr, count * sizeof(T));
-  if (e == cudaSuccess) { owned.push_back(ptr); e = cudaMemset(ptr, 0, count * sizeof(T)); }
+  if (e == cudaSuccess) { owned.push_back(ptr); e = cudaMemsetAsync(ptr, 0, count * sizeof(T), stream); }
   return e;
 }
 
@@ -62,28 +64,28 @@ int e55_gpu_selfplay_run(e55_ctx* c, int games, long total_moves, int simulation
   float* d_policy = nullptr;
   cudaError_t e = cudaSuccess;
   auto chain = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
-  chain(dev_alloc(p.games, G, owned));
-  chain(dev_alloc(p.nodes, G * 2 * gs::kMaxNodes, owned));
-  chain(dev_alloc(p.edges, G * 2 * gs::kMaxEdges, owned));
-  chain(dev_alloc(p.child, G * 2 * gs::kMaxEdges, owned));
-  chain(dev_alloc(p.old_of, G * gs::kMaxNodes, owned));
-  chain(dev_alloc(p.bits, slots * mshogi::kInputPlanes, owned));
-  chain(dev_alloc(p.scale, slots * mshogi::kInputPlanes, owned));
-  chain(dev_alloc(p.move_idx, slots * gs::kMoveStride, owned));
-  chain(dev_alloc(p.move_cnt, slots, owned));
-  chain(dev_alloc(p.priors, slots * gs::kMoveStride, owned));
-  chain(dev_alloc(p.value, slots, owned));
-  chain(dev_alloc(p.shared, 1, owned));
-  chain(dev_alloc(d_policy, slots * kPolicyCh * kSq, owned));
+  chain(dev_alloc(p.games, G, owned, c->stream));
+  chain(dev_alloc(p.nodes, G * 2 * gs::kMaxNodes, owned, c->stream));
+  chain(dev_alloc(p.edges, G * 2 * gs::kMaxEdges, owned, c->stream));
+  chain(dev_alloc(p.child, G * 2 * gs::kMaxEdges, owned, c->stream));
+  chain(dev_alloc(p.old_of, G * gs::kMaxNodes, owned, c->stream));
+  chain(dev_alloc(p.bits, slots * mshogi::kInputPlanes, owned, c->stream));
+  chain(dev_alloc(p.scale, slots * mshogi::kInputPlanes, owned, c->stream));
+  chain(dev_alloc(p.move_idx, slots * gs::kMoveStride, owned, c->stream));
+  chain(dev_alloc(p.move_cnt, slots, owned, c->stream));
+  chain(dev_alloc(p.priors, slots * gs::kMoveStride, owned, c->stream));
+  chain(dev_alloc(p.value, slots, owned, c->stream));
+  chain(dev_alloc(p.shared, 1, owned, c->stream));
+  chain(dev_alloc(d_policy, slots * kPolicyCh * kSq, owned, c->stream));
   if (record_cap > 0) {
-    chain(dev_alloc(p.records, static_cast<size_t>(record_cap) * gs::kRecordWords, owned));
-    chain(dev_alloc(p.rec_buf, G * gs::kRecordWords, owned));
+    chain(dev_alloc(p.records, static_cast<size_t>(record_cap) * gs::kRecordWords, owned, c->stream));
+    chain(dev_alloc(p.rec_buf, G * gs::kRecordWords, owned, c->stream));
   }
   // mate-search mailbox (see Params): requests come down every round, answers go up a round or two later
   unsigned long long* d_ans = nullptr;
-  chain(dev_alloc(p.req_board, G, owned));
-  chain(dev_alloc(p.req_seq, G, owned));
-  chain(dev_alloc(d_ans, G, owned));
+  chain(dev_alloc(p.req_board, G, owned, c->stream));
+  chain(dev_alloc(p.req_seq, G, owned, c->stream));
+  chain(dev_alloc(d_ans, G, owned, c->stream));
   p.ans = d_ans;
   gs::Shared* h_shared = nullptr;            // [2]: one per round in flight
   mshogi::Board* h_board = nullptr;          // [2][G]
@@ -145,6 +147,9 @@ int e55_gpu_selfplay_run(e55_ctx* c, int games, long total_moves, int simulation
   int rc = E55_OK;
   memset(h_shared, 0, 2 * sizeof(gs::Shared));
   gs::Shared last{};
+  bool stalled = false;
+  unsigned long long progress_moves = 0;
+  auto progress_at = std::chrono::steady_clock::now();
   const bool trace = getenv("E55_SERVICE_TRACE") != nullptr;
   cudaEvent_t te[5] = {};
   double t_sel = 0, t_net = 0, t_pri = 0, t_exp = 0;
@@ -181,9 +186,24 @@ int e55_gpu_selfplay_run(e55_ctx* c, int games, long total_moves, int simulation
     if (e == cudaSuccess) e = cudaEventRecord(ev[buf], st);
     // ... while the host, the GPU busy with this round, looks at the previous one: stop? which mates?
     if (e == cudaSuccess && round > 0) {
-      e = cudaEventSynchronize(ev[buf ^ 1]);
+      // (polled, with a deadline: a round takes tens of milliseconds; minutes mean something is wrong, and the caller
+      // should hear about it rather than wait for ever)
+      const auto wait_start = std::chrono::steady_clock::now();
+      while ((e = cudaEventQuery(ev[buf ^ 1])) == cudaErrorNotReady) {
+        if (std::chrono::steady_clock::now() - wait_start > std::chrono::seconds(60)) { stalled = true; break; }
+        std::this_thread::sleep_for(std::chrono::microseconds(50));
+      }
+      if (stalled) { cudaGetLastError(); rc = fail(c, E55_ERR_CUDA, "GPU self-play: a round did not finish within 60 s"); break; }
       if (e == cudaSuccess) {
         last = h_shared[buf ^ 1];
+        if (last.moves != progress_moves) { progress_moves = last.moves; progress_at = std::chrono::steady_clock::now(); }
+        else if (std::chrono::steady_clock::now() - progress_at > std::chrono::seconds(15)) {
+          fprintf(stderr, "[e55 gpu self-play] stalled after %ld rounds: %llu moves (%llu mate), %llu selections, %llu evaluations, %llu games, "
+                  "%ld mate searches answered, %llu overflows\n", round, last.moves, last.mate_moves, last.selections, last.evals, last.games,
+                  mate_searches, last.pool_overflows);
+          rc = fail(c, E55_ERR_CUDA, "GPU self-play: no move was played for 60 s");
+          break;
+        }
         if (mate_depth > 0) {
           answer_requests(buf ^ 1);
           memcpy(h_ans + static_cast<size_t>(buf) * G, answers.data(), G * sizeof(unsigned long long));
@@ -203,9 +223,10 @@ int e55_gpu_selfplay_run(e55_ctx* c, int games, long total_moves, int simulation
       if (nrec > 0) e = cudaMemcpy(records, p.records, static_cast<size_t>(nrec) * gs::kRecordWords * sizeof(uint16_t), cudaMemcpyDeviceToHost);
     }
     if (e != cudaSuccess) rc = fail(c, E55_ERR_CUDA, std::string("GPU self-play: ") + cudaGetErrorString(e));
-  } else {
+  } else if (!stalled) {
     cudaStreamSynchronize(st);
   }
+  if (stalled) return rc;   // the device may be hung: freeing the buffers would wait for it, so they are left behind
   out->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   out->moves = static_cast<long>(h_shared->moves);
   out->evals = static_cast<long>(h_shared->evals);
