@@ -428,17 +428,26 @@ def main():
     # ---- GPU-resident self-play: the search itself on the GPU, no host game threads ---------------------------
     selfplay_gpu = None
     if args.selfplay_workers > 0 and args.precision == "bf16" and (args.blocks, args.filters) == (7, 128) and args.gpu_games > 0:
-        net.gpu_selfplay(games=args.gpu_games, total_moves=args.gpu_games, simulations=800, seed=77 + rank)   # warm-up
+        # (this section is an extra beside the contract's numbers: a failure here is reported in the line, not fatal)
+        gs, gpu_error = {"moves_per_s": 0.0, "evals_per_s": 0.0, "games": 0, "mean_game_plies": 0.0}, None
+        try:
+            net.gpu_selfplay(games=args.gpu_games, total_moves=args.gpu_games, simulations=800, seed=77 + rank)   # warm-up
+        except Exception as exc:
+            gpu_error = str(exc)
         barrier()
-        gs, _ = net.gpu_selfplay(games=args.gpu_games, total_moves=args.gpu_games * args.gpu_plies, simulations=800, mate_depth=7,
-                                 seed=5 + rank)
+        if gpu_error is None:
+            try:
+                gs, _ = net.gpu_selfplay(games=args.gpu_games, total_moves=args.gpu_games * args.gpu_plies, simulations=800,
+                                         mate_depth=7, seed=5 + rank)
+            except Exception as exc:
+                gpu_error = str(exc)
         barrier()
         g_mv, _ = sharding.aggregate(gs["moves_per_s"], 1.0, device=dev)
         g_ev, _ = sharding.aggregate(gs["evals_per_s"], 1.0, device=dev)
         selfplay_gpu = {"moves_per_s": g_mv, "evals_per_s": g_ev, "games_in_flight_per_gpu": args.gpu_games,
                         "plies_per_game_slot": args.gpu_plies, "games_finished_rank0": gs["games"],
                         "mean_game_plies_rank0": gs["mean_game_plies"], "simulations_per_move": 800, "mate_search_plies": 7,
-                        "host_game_threads": 0,
+                        "host_game_threads": 0, "error_rank0": gpu_error,
                         "note": "the same self-play with the search on the GPU (csrc/e55_gpu_selfplay.cuh): one thread per game does "
                                 "the PUCT descent with virtual loss, move generation, repetition test, input encoding, expansion, "
                                 "back-up and move choice between the network launches (16 slots per game per launch); tree reuse "
