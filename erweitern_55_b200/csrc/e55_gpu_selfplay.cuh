@@ -108,7 +108,7 @@ struct Params {
   Board* req_board;    // [n_games]
   uint32_t* req_seq;   // [n_games]: 0 = no request yet, else the number of the game's latest request
   const unsigned long long* ans;   // [n_games]: (request number << 16) | packed mate move, 0xFFFF = no mate
-  int n_games, simulations, use_dirichlet, reuse_tree, sampling_moves, max_moves, record_cap, mate_depth;
+  int n_games, game0, simulations, use_dirichlet, reuse_tree, sampling_moves, max_moves, record_cap, mate_depth;   // game0: index of the cohort's first game in the run
   long long move_budget;
   float c_puct, dirichlet_alpha, dirichlet_eps;
 };
@@ -400,7 +400,7 @@ __global__ void init_kernel(Params p, uint64_t seed) {
   const int gi = blockIdx.x * blockDim.x + threadIdx.x;
   if (gi >= p.n_games) return;
   Game& g = p.games[gi];
-  g.rng = (seed + 0x9E3779B97F4A7C15ull * static_cast<uint64_t>(gi + 1)) | 1ull;
+  g.rng = (seed + 0x9E3779B97F4A7C15ull * static_cast<uint64_t>(p.game0 + gi + 1)) | 1ull;
   for (int i = 0; i < 8; ++i) next_u64(g.rng);
   g.games_finished = 0;
   g.pool = 0;

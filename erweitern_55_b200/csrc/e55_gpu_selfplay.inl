@@ -87,29 +87,65 @@ int e55_gpu_selfplay_run(e55_ctx* c, int games, long total_moves, int simulation
   chain(dev_alloc(p.req_seq, G, owned, c->stream));
   chain(dev_alloc(d_ans, G, owned, c->stream));
   p.ans = d_ans;
-  gs::Shared* h_shared = nullptr;            // [2]: one per round in flight
+  gs::Shared* h_shared = nullptr;            // [2 cohorts][2]: one per cohort and round in flight
   mshogi::Board* h_board = nullptr;          // [2][G]
   uint32_t* h_seq = nullptr;                 // [2][G]
   unsigned long long* h_ans = nullptr;       // [2][G]
-  chain(cudaMallocHost(&h_shared, 2 * sizeof(gs::Shared)));
+  chain(cudaMallocHost(&h_shared, 4 * sizeof(gs::Shared)));
   chain(cudaMallocHost(&h_board, 2 * G * sizeof(mshogi::Board)));
   chain(cudaMallocHost(&h_seq, 2 * G * sizeof(uint32_t)));
   chain(cudaMallocHost(&h_ans, 2 * G * sizeof(unsigned long long)));
-  cudaEvent_t ev[2] = {nullptr, nullptr};
-  chain(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
-  chain(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+  cudaEvent_t ev[2][2] = {};
+  cudaEvent_t ready = nullptr;
+  for (auto& pair : ev)
+    for (auto& x : pair) chain(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
+  chain(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+  const int sms_before = c->tc.sms;
   auto cleanup = [&] {
+    c->tc.sms = sms_before;
     for (void* q : owned) cudaFree(q);
     cudaFreeHost(h_shared); cudaFreeHost(h_board); cudaFreeHost(h_seq); cudaFreeHost(h_ans);
-    if (ev[0]) cudaEventDestroy(ev[0]);
-    if (ev[1]) cudaEventDestroy(ev[1]);
+    for (auto& pair : ev)
+      for (auto& x : pair) if (x) cudaEventDestroy(x);
+    if (ready) cudaEventDestroy(ready);
   };
   if (e != cudaSuccess) { cleanup(); return fail(c, E55_ERR_CUDA, std::string("GPU self-play buffers: ") + cudaGetErrorString(e)); }
-  p.n_games = games; p.simulations = simulations; p.use_dirichlet = use_dirichlet; p.reuse_tree = reuse_tree; p.mate_depth = mate_depth;
+  p.n_games = games; p.game0 = 0; p.simulations = simulations; p.use_dirichlet = use_dirichlet; p.reuse_tree = reuse_tree; p.mate_depth = mate_depth;
   p.sampling_moves = sampling_moves; p.max_moves = std::min(max_moves, gs::kMaxPly); p.record_cap = record_cap; p.move_budget = total_moves;
   p.c_puct = 1.25f; p.dirichlet_alpha = 0.15f; p.dirichlet_eps = 0.25f;
-  cudaStream_t st = c->stream;
-  const int blocks = (games + 63) / 64, n = static_cast<int>(slots);
+  // Two cohorts of games on two streams: while the network evaluates one cohort's leaves the search kernels of the other
+  // run beside it.  The tower kernel is a persistent kernel with one CTA per SM that leaves no room for anything else
+  // on its SMs, so for the run it gets 24 SMs fewer and the (latency-bound, small) search kernels get those
+  // (measured at 16384 games: 8.65 k moves/s with one cohort; 8.95 k / 9.18 k / 9.54 k / 9.42 k with 12 / 16 / 24 / 32 spare SMs).
+  const int want_cohorts = getenv("E55_GPU_COHORTS") ? atoi(getenv("E55_GPU_COHORTS")) : 0;   // 0: by size
+  const int n_cohorts = want_cohorts == 1 || games < 128 ? 1 : (want_cohorts == 2 || games >= 2048 ? 2 : 1);
+  const int spare_sms = getenv("E55_GPU_SPARE_SMS") ? atoi(getenv("E55_GPU_SPARE_SMS")) : 24;
+  if (n_cohorts == 2) c->tc.sms = std::max(2, sms_before - std::max(0, spare_sms));
+  const int pri_warps = getenv("E55_GPU_PRIORS_WARPS") ? std::max(1, std::min(8, atoi(getenv("E55_GPU_PRIORS_WARPS")))) : 8;
+  struct Cohort {
+    gs::Params p;
+    cudaStream_t st;
+    float* policy;
+    int g0, games, blocks, n;
+  } co[2];
+  for (int k = 0; k < n_cohorts; ++k) {
+    Cohort& q = co[k];
+    q.g0 = k == 0 ? 0 : games / 2;
+    q.games = n_cohorts == 1 ? games : (k == 0 ? games / 2 : games - games / 2);
+    q.blocks = (q.games + 63) / 64;
+    q.n = q.games * gs::kLeaf;
+    q.st = k == 0 ? c->stream : c->pipe_stream[0];
+    const size_t g0 = static_cast<size_t>(q.g0), s0 = g0 * gs::kLeaf;
+    q.p = p;
+    q.p.n_games = q.games; q.p.game0 = q.g0;
+    q.p.games += g0; q.p.nodes += g0 * 2 * gs::kMaxNodes; q.p.edges += g0 * 2 * gs::kMaxEdges; q.p.child += g0 * 2 * gs::kMaxEdges;
+    q.p.old_of += g0 * gs::kMaxNodes; q.p.bits += s0 * mshogi::kInputPlanes; q.p.scale += s0 * mshogi::kInputPlanes;
+    q.p.move_idx += s0 * gs::kMoveStride; q.p.move_cnt += s0; q.p.priors += s0 * gs::kMoveStride; q.p.value += s0;
+    if (q.p.rec_buf) q.p.rec_buf += g0 * gs::kRecordWords;
+    q.p.req_board += g0; q.p.req_seq += g0; q.p.ans += g0;
+    q.policy = d_policy + s0 * kPolicyCh * kSq;
+  }
+  const int n = static_cast<int>(slots);
   std::vector<unsigned long long> answers(G, 0ull);   // the latest answer of every game (request number 0 = none)
   std::vector<uint32_t> answered(G, 0u);
   cpu_set_t cpus;
@@ -117,12 +153,12 @@ int e55_gpu_selfplay_run(e55_ctx* c, int games, long total_moves, int simulation
   if (sched_getaffinity(0, sizeof(cpus), &cpus) == 0) host_cores = CPU_COUNT(&cpus);
   const int mate_threads = std::max(1, std::min(8, host_cores - 1));
   long mate_searches = 0;
-  // The mate searches of the requests in snapshot `buf`: selfplay.py:35-36 on the host (Board::solve_checkmate_dfs).
-  auto answer_requests = [&](int buf) {
+  // The mate searches of the requests of games [g0, g0 + count) in snapshot `buf`: selfplay.py:35-36 on the host.
+  auto answer_requests = [&](int buf, int g0, int count) {
     const mshogi::Board* boards = h_board + static_cast<size_t>(buf) * G;
     const uint32_t* seq = h_seq + static_cast<size_t>(buf) * G;
     std::vector<int> todo;
-    for (int g = 0; g < games; ++g)
+    for (int g = g0; g < g0 + count; ++g)
       if (seq[g] != 0 && seq[g] != answered[g]) todo.push_back(g);
     if (todo.empty()) return;
     mate_searches += static_cast<long>(todo.size());
@@ -143,9 +179,14 @@ int e55_gpu_selfplay_run(e55_ctx* c, int games, long total_moves, int simulation
     for (auto& t : th) t.join();
   };
   const auto t0 = std::chrono::steady_clock::now();
-  gs::init_kernel<<<blocks, 64, 0, st>>>(p, seed);
   int rc = E55_OK;
-  memset(h_shared, 0, 2 * sizeof(gs::Shared));
+  e = cudaEventRecord(ready, c->stream);            // the buffers are zeroed on the context stream: the second stream waits for that
+  for (int k = 0; k < n_cohorts && e == cudaSuccess; ++k) {
+    if (k > 0) e = cudaStreamWaitEvent(co[k].st, ready, 0);
+    gs::init_kernel<<<co[k].blocks, 64, 0, co[k].st>>>(co[k].p, seed);
+  }
+  if (e != cudaSuccess) rc = fail(c, E55_ERR_CUDA, std::string("GPU self-play: ") + cudaGetErrorString(e));
+  memset(h_shared, 0, 4 * sizeof(gs::Shared));
   gs::Shared last{};
   bool stalled = false;
   unsigned long long progress_moves = 0;
@@ -157,66 +198,74 @@ int e55_gpu_selfplay_run(e55_ctx* c, int games, long total_moves, int simulation
   if (trace) for (auto& x : te) cudaEventCreate(&x);
   for (long round = 0; rc == E55_OK; ++round) {
     const int buf = static_cast<int>(round & 1);
-    const bool timed = trace && round % 16 == 8;
-    if (timed) cudaEventRecord(te[0], st);
-    gs::select_kernel<<<blocks, 64, 0, st>>>(p);
-    ++c->launches;
-    if (timed) cudaEventRecord(te[1], st);
-    rc = forward_packed_on(c, st, p.bits, p.scale, n, 0, d_policy, p.value);
-    if (rc) break;
-    if (timed) cudaEventRecord(te[2], st);
-    gs::legal_priors_strided_kernel<<<(n + 7) / 8, 256, 0, st>>>(d_policy, p.move_cnt, p.move_idx, p.priors, n, kPolicyCh * kSq, gs::kMoveStride);
-    if (timed) cudaEventRecord(te[3], st);
-    gs::expand_kernel<<<blocks, 64, 0, st>>>(p);
-    c->launches += 2;
-    if (timed) {
-      cudaEventRecord(te[4], st);
-      cudaEventSynchronize(te[4]);
-      float ms;
-      cudaEventElapsedTime(&ms, te[0], te[1]); t_sel += ms;
-      cudaEventElapsedTime(&ms, te[1], te[2]); t_net += ms;
-      cudaEventElapsedTime(&ms, te[2], te[3]); t_pri += ms;
-      cudaEventElapsedTime(&ms, te[3], te[4]); t_exp += ms;
-      ++t_rounds;
+    for (int k = 0; k < n_cohorts && rc == E55_OK; ++k) {
+      Cohort& q = co[k];
+      cudaStream_t st = q.st;
+      const bool timed = trace && k == 0 && round % 16 == 8;
+      if (timed) cudaEventRecord(te[0], st);
+      gs::select_kernel<<<q.blocks, 64, 0, st>>>(q.p);
+      ++c->launches;
+      if (timed) cudaEventRecord(te[1], st);
+      rc = forward_packed_on(c, st, q.p.bits, q.p.scale, q.n, 0, q.policy, q.p.value);
+      if (rc) break;
+      if (timed) cudaEventRecord(te[2], st);
+      gs::legal_priors_strided_kernel<<<(q.n + pri_warps - 1) / pri_warps, pri_warps * 32, 0, st>>>(q.policy, q.p.move_cnt, q.p.move_idx, q.p.priors, q.n, kPolicyCh * kSq, gs::kMoveStride);
+      if (timed) cudaEventRecord(te[3], st);
+      gs::expand_kernel<<<q.blocks, 64, 0, st>>>(q.p);
+      c->launches += 2;
+      if (timed) {
+        cudaEventRecord(te[4], st);
+        cudaEventSynchronize(te[4]);
+        float ms;
+        cudaEventElapsedTime(&ms, te[0], te[1]); t_sel += ms;
+        cudaEventElapsedTime(&ms, te[1], te[2]); t_net += ms;
+        cudaEventElapsedTime(&ms, te[2], te[3]); t_pri += ms;
+        cudaEventElapsedTime(&ms, te[3], te[4]); t_exp += ms;
+        ++t_rounds;
+      }
+      // this round's counters and mate-search requests come down behind it ...
+      e = cudaMemcpyAsync(h_shared + 2 * k + buf, p.shared, sizeof(gs::Shared), cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess && mate_depth > 0)
+        e = cudaMemcpyAsync(h_board + static_cast<size_t>(buf) * G + q.g0, q.p.req_board, q.games * sizeof(mshogi::Board), cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess && mate_depth > 0)
+        e = cudaMemcpyAsync(h_seq + static_cast<size_t>(buf) * G + q.g0, q.p.req_seq, q.games * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaEventRecord(ev[k][buf], st);
+      if (e != cudaSuccess) rc = fail(c, E55_ERR_CUDA, std::string("GPU self-play: ") + cudaGetErrorString(e));
     }
-    // this round's counters and mate-search requests come down behind it ...
-    e = cudaMemcpyAsync(h_shared + buf, p.shared, sizeof(gs::Shared), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess && mate_depth > 0) e = cudaMemcpyAsync(h_board + static_cast<size_t>(buf) * G, p.req_board, G * sizeof(mshogi::Board), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess && mate_depth > 0) e = cudaMemcpyAsync(h_seq + static_cast<size_t>(buf) * G, p.req_seq, G * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaEventRecord(ev[buf], st);
     // ... while the host, the GPU busy with this round, looks at the previous one: stop? which mates?
-    if (e == cudaSuccess && round > 0) {
+    for (int k = 0; k < n_cohorts && rc == E55_OK && round > 0; ++k) {
+      Cohort& q = co[k];
       // (polled, with a deadline: a round takes tens of milliseconds; minutes mean something is wrong, and the caller
       // should hear about it rather than wait for ever)
       const auto wait_start = std::chrono::steady_clock::now();
-      while ((e = cudaEventQuery(ev[buf ^ 1])) == cudaErrorNotReady) {
+      while ((e = cudaEventQuery(ev[k][buf ^ 1])) == cudaErrorNotReady) {
         if (std::chrono::steady_clock::now() - wait_start > std::chrono::seconds(60)) { stalled = true; break; }
         std::this_thread::sleep_for(std::chrono::microseconds(50));
       }
       if (stalled) { cudaGetLastError(); rc = fail(c, E55_ERR_CUDA, "GPU self-play: a round did not finish within 60 s"); break; }
       if (e == cudaSuccess) {
-        last = h_shared[buf ^ 1];
+        if (h_shared[2 * k + (buf ^ 1)].moves >= last.moves) last = h_shared[2 * k + (buf ^ 1)];
         if (last.moves != progress_moves) { progress_moves = last.moves; progress_at = std::chrono::steady_clock::now(); }
-        else if (std::chrono::steady_clock::now() - progress_at > std::chrono::seconds(15)) {
+        else if (std::chrono::steady_clock::now() - progress_at > std::chrono::seconds(30)) {
           fprintf(stderr, "[e55 gpu self-play] stalled after %ld rounds: %llu moves (%llu mate), %llu selections, %llu evaluations, %llu games, "
                   "%ld mate searches answered, %llu overflows\n", round, last.moves, last.mate_moves, last.selections, last.evals, last.games,
                   mate_searches, last.pool_overflows);
-          rc = fail(c, E55_ERR_CUDA, "GPU self-play: no move was played for 60 s");
+          rc = fail(c, E55_ERR_CUDA, "GPU self-play: no move was played for 30 s");
           break;
         }
         if (mate_depth > 0) {
-          answer_requests(buf ^ 1);
-          memcpy(h_ans + static_cast<size_t>(buf) * G, answers.data(), G * sizeof(unsigned long long));
-          e = cudaMemcpyAsync(d_ans, h_ans + static_cast<size_t>(buf) * G, G * sizeof(unsigned long long), cudaMemcpyHostToDevice, st);
+          answer_requests(buf ^ 1, q.g0, q.games);
+          memcpy(h_ans + static_cast<size_t>(buf) * G + q.g0, answers.data() + q.g0, q.games * sizeof(unsigned long long));
+          e = cudaMemcpyAsync(d_ans + q.g0, h_ans + static_cast<size_t>(buf) * G + q.g0, q.games * sizeof(unsigned long long), cudaMemcpyHostToDevice, q.st);
         }
       }
+      if (e != cudaSuccess) rc = fail(c, E55_ERR_CUDA, std::string("GPU self-play: ") + cudaGetErrorString(e));
     }
-    if (e != cudaSuccess) { rc = fail(c, E55_ERR_CUDA, std::string("GPU self-play: ") + cudaGetErrorString(e)); break; }
     if (static_cast<long>(last.moves) >= total_moves) break;
   }
   if (rc == E55_OK) {
-    e = cudaMemcpyAsync(h_shared, p.shared, sizeof(gs::Shared), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    for (int k = 0; k < n_cohorts && e == cudaSuccess; ++k) e = cudaStreamSynchronize(co[k].st);
+    if (e == cudaSuccess) e = cudaMemcpy(h_shared, p.shared, sizeof(gs::Shared), cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && record_cap > 0) {
       const int nrec = std::min(h_shared->n_records, record_cap);
       *n_records_out = nrec;
@@ -224,9 +273,9 @@ int e55_gpu_selfplay_run(e55_ctx* c, int games, long total_moves, int simulation
     }
     if (e != cudaSuccess) rc = fail(c, E55_ERR_CUDA, std::string("GPU self-play: ") + cudaGetErrorString(e));
   } else if (!stalled) {
-    cudaStreamSynchronize(st);
+    for (int k = 0; k < n_cohorts; ++k) cudaStreamSynchronize(co[k].st);
   }
-  if (stalled) return rc;   // the device may be hung: freeing the buffers would wait for it, so they are left behind
+  if (stalled) { c->tc.sms = sms_before; return rc; }   // the device may be hung: freeing the buffers would wait for it, so they are left behind
   out->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   out->moves = static_cast<long>(h_shared->moves);
   out->evals = static_cast<long>(h_shared->evals);

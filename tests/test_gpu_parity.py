@@ -485,9 +485,12 @@ def test_host_side_packing_is_invisible(weights_perturbed):
     net.close()
 
 
-def test_gpu_resident_selfplay(weights_default):
+@pytest.mark.parametrize("cohorts", ["1", "2"])
+def test_gpu_resident_selfplay(weights_default, monkeypatch, cohorts):
     """The search on the GPU (csrc/e55_gpu_selfplay.cuh): the device build of the rules engine counts the same perft
-    nodes as the host build, and every game it plays is a legal game that ended for a reason the rules give."""
+    nodes as the host build, and every game it plays is a legal game that ended for a reason the rules give -- with
+    all games in one cohort and with two cohorts on two streams (the layout large runs use)."""
+    monkeypatch.setenv("E55_GPU_COHORTS", cohorts)
     import ctypes as C
     from erweitern_55_b200 import _capi
     from erweitern_55_b200.minishogi import Move, Position
