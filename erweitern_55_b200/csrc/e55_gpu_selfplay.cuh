@@ -43,7 +43,7 @@ struct GNode {
   uint8_t expanded, terminal, claimed, in_check;
 };
 
-struct GEdge {            // as mshogi::Edge (csrc/mcts.hpp)
+struct alignas(16) GEdge {            // as mshogi::Edge (csrc/mcts.hpp)
   float prior, w;
   int32_t n;
   uint16_t mv, vloss;
@@ -463,14 +463,17 @@ __global__ void __launch_bounds__(64) select_kernel(Params p) {
     while (nodes[node].expanded && !nodes[node].terminal && pv.depth < kMaxPath) {
       const GNode nd = nodes[node];
       GEdge* ed = edges + nd.first_edge;
+      // (an edge is one aligned 16-byte load: {prior, w, n, mv | vloss << 16})
+      const uint4* raw = reinterpret_cast<const uint4*>(ed);
       int total = 0;
-      for (int i = 0; i < nd.n_edges; ++i) total += ed[i].n + ed[i].vloss;
+      for (int i = 0; i < nd.n_edges; ++i) { const uint4 r = raw[i]; total += static_cast<int>(r.z) + static_cast<int>(r.w >> 16); }
       const float cs = p.c_puct * sqrtf(static_cast<float>(total) + 1e-8f);
       int best = 0;
       float best_score = -1e30f;
       for (int i = 0; i < nd.n_edges; ++i) {
-        const float nv = static_cast<float>(ed[i].n + ed[i].vloss);
-        const float score = ed[i].w / fmaxf(nv, 1.f) + cs * ed[i].prior / (1.f + nv);
+        const uint4 r = raw[i];
+        const float nv = static_cast<float>(static_cast<int>(r.z) + static_cast<int>(r.w >> 16));
+        const float score = __uint_as_float(r.y) / fmaxf(nv, 1.f) + cs * __uint_as_float(r.x) / (1.f + nv);
         if (score > best_score) { best_score = score; best = i; }
       }
       GEdge& e = ed[best];

@@ -117,6 +117,8 @@ int e55_gpu_selfplay_run(e55_ctx* c, int games, long total_moves, int simulation
   // run beside it.  The tower kernel is a persistent kernel with one CTA per SM that leaves no room for anything else
   // on its SMs, so for the run it gets 24 SMs fewer and the (latency-bound, small) search kernels get those
   // (measured at 16384 games: 8.65 k moves/s with one cohort; 8.95 k / 9.18 k / 9.54 k / 9.42 k with 12 / 16 / 24 / 32 spare SMs).
+  // Search blocks do not share an SM with a tower CTA even where registers and shared memory would allow it (tried with
+  // the tower's shared-memory carve-out on the search kernels: the two cohorts just run in lock step), hence spare SMs.
   const int want_cohorts = getenv("E55_GPU_COHORTS") ? atoi(getenv("E55_GPU_COHORTS")) : 0;   // 0: by size
   const int n_cohorts = want_cohorts == 1 || games < 128 ? 1 : (want_cohorts == 2 || games >= 2048 ? 2 : 1);
   const int spare_sms = getenv("E55_GPU_SPARE_SMS") ? atoi(getenv("E55_GPU_SPARE_SMS")) : 24;
@@ -196,23 +198,34 @@ int e55_gpu_selfplay_run(e55_ctx* c, int games, long total_moves, int simulation
   double t_sel = 0, t_net = 0, t_pri = 0, t_exp = 0;
   long t_rounds = 0;
   if (trace) for (auto& x : te) cudaEventCreate(&x);
+  // E55_GPU_TIMELINE=1: when each kernel of rounds 40..43 started and ended on either stream (no synchronisation in between)
+  constexpr long kTl0 = 40, kTlRounds = 4;
+  const bool timeline = getenv("E55_GPU_TIMELINE") != nullptr;
+  cudaEvent_t tl[kTlRounds][2][5] = {};
+  if (timeline) for (auto& a : tl) for (auto& b : a) for (auto& x : b) cudaEventCreate(&x);
   for (long round = 0; rc == E55_OK; ++round) {
     const int buf = static_cast<int>(round & 1);
     for (int k = 0; k < n_cohorts && rc == E55_OK; ++k) {
       Cohort& q = co[k];
       cudaStream_t st = q.st;
-      const bool timed = trace && k == 0 && round % 16 == 8;
+      const bool timed = trace && !timeline && k == 0 && round % 16 == 8;
+      cudaEvent_t* tle = timeline && round >= kTl0 && round < kTl0 + kTlRounds ? tl[round - kTl0][k] : nullptr;
       if (timed) cudaEventRecord(te[0], st);
+      if (tle) cudaEventRecord(tle[0], st);
       gs::select_kernel<<<q.blocks, 64, 0, st>>>(q.p);
       ++c->launches;
       if (timed) cudaEventRecord(te[1], st);
+      if (tle) cudaEventRecord(tle[1], st);
       rc = forward_packed_on(c, st, q.p.bits, q.p.scale, q.n, 0, q.policy, q.p.value);
       if (rc) break;
       if (timed) cudaEventRecord(te[2], st);
+      if (tle) cudaEventRecord(tle[2], st);
       gs::legal_priors_strided_kernel<<<(q.n + pri_warps - 1) / pri_warps, pri_warps * 32, 0, st>>>(q.policy, q.p.move_cnt, q.p.move_idx, q.p.priors, q.n, kPolicyCh * kSq, gs::kMoveStride);
       if (timed) cudaEventRecord(te[3], st);
+      if (tle) cudaEventRecord(tle[3], st);
       gs::expand_kernel<<<q.blocks, 64, 0, st>>>(q.p);
       c->launches += 2;
+      if (tle) cudaEventRecord(tle[4], st);
       if (timed) {
         cudaEventRecord(te[4], st);
         cudaEventSynchronize(te[4]);
@@ -282,6 +295,18 @@ int e55_gpu_selfplay_run(e55_ctx* c, int games, long total_moves, int simulation
   out->games = static_cast<long>(h_shared->games);
   out->mean_game_plies = h_shared->games ? static_cast<double>(h_shared->plies_in_finished_games) / static_cast<double>(h_shared->games) : 0.0;
   out->mean_gpu_batch = static_cast<double>(n);
+  if (timeline && rc == E55_OK) {
+    for (long r = 0; r < kTlRounds; ++r)
+      for (int k = 0; k < n_cohorts; ++k) {
+        float t[5] = {};
+        bool ok = true;
+        for (int i = 0; i < 5; ++i) ok &= cudaEventElapsedTime(&t[i], tl[0][0][0], tl[r][k][i]) == cudaSuccess;
+        if (ok) fprintf(stderr, "[e55 gpu self-play] round %ld cohort %d: select %.2f-%.2f, network -%.2f, priors -%.2f, expand -%.2f ms\n", kTl0 + r, k,
+                        t[0], t[1], t[2], t[3], t[4]);
+      }
+    cudaGetLastError();
+  }
+  if (timeline) for (auto& a : tl) for (auto& b : a) for (auto& x : b) cudaEventDestroy(x);
   if (trace && t_rounds)
     fprintf(stderr, "[e55 gpu self-play] per round (ms): select %.2f, network %.2f, legal priors %.2f, expand %.2f\n", t_sel / t_rounds,
             t_net / t_rounds, t_pri / t_rounds, t_exp / t_rounds);
