@@ -351,15 +351,23 @@ def main():
     e2e_value = timed_host_steps()
     pk_threads, pk_us, fl_us = C.c_int(), C.c_double(), C.c_double()
     net._check(lib.e55_get_host_pipeline(ctx, C.byref(pk_threads), C.byref(pk_us), C.byref(fl_us)))
-    pack_threads, compacting = pk_threads.value, pk_us.value <= fl_us.value
-    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 266 * 8 if compacting else in_bytes,
-           "host_pipeline": "compacting" if compacting else "float", "us_per_position": {"compacting": pk_us.value, "float": fl_us.value},
+    split_us = (C.c_double * 6)()
+    eighths = C.c_int()
+    net._check(lib.e55_get_host_split(ctx, C.byref(eighths), split_us))
+    shares = (0, 1, 2, 3, 4, 8)
+    best_share = min((u, sh) for u, sh in zip(split_us, shares) if u > 0)[1] if any(u > 0 for u in split_us) else 8
+    n_float = B if best_share == 8 else (B // 8 * best_share) // 64 * 64
+    pack_threads, compacting = pk_threads.value, best_share < 8
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": (B - n_float) * 266 * 8 + n_float * 266 * 25 * 4,
+           "host_pipeline": "float" if best_share == 8 else "compacting" if best_share == 0 else f"compacting, {best_share}/8 of the batch as floats",
+           "us_per_position": {f"{sh}/8 as floats": u for sh, u in zip(shares, split_us)},
            "d2h_bytes_per_step": B * 1725 * 4 + B * 4, "steps": e2e_steps, "host_input_bytes_per_step": in_bytes,
            "host_pack_threads": pack_threads, "value_without_host_packing": e2e_plain,
            "timing": "host wall clock around blocking e55_predict calls on pinned float32 [B,266,5,5] planes, max over ranks; "
-                     "in its default mode the call measures two pipelines and keeps the faster (host_pipeline): bit-packing the planes "
-                     "on a host thread pool chunk by chunk (exact, results identical; then h2d_bytes_per_step = 2 128 B per "
-                     "position cross PCIe instead of host_input_bytes_per_step) or sending the float planes as they are; "
+                     "in its default mode the call bit-packs the planes on a host thread pool chunk by chunk (exact, results identical; "
+                     "2 128 B per position cross PCIe instead of 26 600) and sends a share of the batch as float planes meanwhile "
+                     "(link and cores both busy); it measures the shares 0..4/8 and 8/8 in its first calls and keeps the fastest "
+                     "(host_pipeline, us_per_position; h2d_bytes_per_step is counted for that share); "
                      "value_without_host_packing is the same call with e55_set_host_threads(0)"}
 
     # ---- same call with the compact input format (e55_predict_packed; not the reference's format) ---

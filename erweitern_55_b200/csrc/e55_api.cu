@@ -93,7 +93,11 @@ struct e55_ctx {
   int host_threads = -1;           // -1: chosen from the core count on first use; 0: off
   bool host_auto = true;           // the caller left the choice to the library: measure both pipelines, use the faster
   int64_t pipe_calls = 0;
-  double compact_us = 0.0, float_us = 0.0;   // running mean of microseconds per position of either pipeline
+  static constexpr int kSplitLevels = 6;
+  static constexpr int kSplitEighths[kSplitLevels] = {0, 1, 2, 3, 4, 8};   // eighths of a large batch that travel as float planes
+  double split_us[kSplitLevels] = {};        // running mean of microseconds per position at each split
+  int split_samples[kSplitLevels] = {};
+  int split_level = 0;                       // the split of the latest large call
   e55host::Packer* packer = nullptr;
   uint32_t* h_bits = nullptr;      // pinned [h_cap][in_planes]
   float* h_scale = nullptr;
@@ -587,17 +591,20 @@ constexpr int kPipeChunk = 256;
 // Host-buffer predict, compacting pipeline: the planes are bit-packed on the host chunk by chunk (exactly;
 // e55_host.cpp) while earlier chunks are already on the GPU, so 2 128 instead of 26 600 bytes per position cross
 // PCIe.  A chunk that is not exactly representable travels as float planes.  Results equal the float pipeline's.
-int predict_compacting(e55_ctx* c, e55host::Packer* packer, const float* planes, int n, float* policy, float* value) {
-  e55host::packer_start(packer, planes, n, c->in_planes, c->h_bits, c->h_scale);
+// n_float > 0: the last n_float positions are not packed at all but sent as float planes in between the packed
+// chunks -- the copy engine moves them while the cores pack the rest, so both the PCIe link and the host cores
+// are busy for the whole call.
+int predict_compacting(e55_ctx* c, e55host::Packer* packer, const float* planes, int n, int n_float, float* policy, float* value) {
+  const int n_pack = n - n_float;
+  e55host::packer_start(packer, planes, n_pack, c->in_planes, c->h_bits, c->h_scale);
   cudaError_t e = cudaEventRecord(c->pipe_start, c->stream);
   const size_t ip = static_cast<size_t>(c->in_planes), in_pp = ip * kSq, pol_pp = static_cast<size_t>(kPolicyCh) * kSq;
-  int used = 0, rc = E55_OK;
-  for (int off = 0, i = 0; off < n && e == cudaSuccess && rc == E55_OK; ++i) {
-    const int m = std::min(kPipeChunk, n - off);   // a one-group-per-CTA kernel of 64 CTAs; two run side by side
-    const bool exact = e55host::packer_wait_range(packer, off, m);
-    cudaStream_t st = c->pipe_stream[i % e55_ctx::kPipeStreams];
-    if (i < e55_ctx::kPipeStreams) { e = cudaStreamWaitEvent(st, c->pipe_start, 0); used = i + 1; }
-    if (exact) {
+  int used = 0, rc = E55_OK, chunk = 0;
+  auto send = [&](int off, int m, bool packed) {
+    cudaStream_t st = c->pipe_stream[chunk % e55_ctx::kPipeStreams];
+    if (chunk < e55_ctx::kPipeStreams) { e = cudaStreamWaitEvent(st, c->pipe_start, 0); used = chunk + 1; }
+    ++chunk;
+    if (packed) {
       if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_bits + off * ip, c->h_bits + off * ip, m * ip * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
       if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_scale + off * ip, c->h_scale + off * ip, m * ip * sizeof(float), cudaMemcpyHostToDevice, st);
       if (e == cudaSuccess) rc = forward_packed_on(c, st, c->d_bits + off * ip, c->d_scale + off * ip, m, off, c->d_policy + off * pol_pp, c->d_value + off);
@@ -607,7 +614,22 @@ int predict_compacting(e55_ctx* c, e55host::Packer* packer, const float* planes,
     }
     if (e == cudaSuccess && rc == E55_OK) e = cudaMemcpyAsync(policy + off * pol_pp, c->d_policy + off * pol_pp, m * pol_pp * sizeof(float), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && rc == E55_OK) e = cudaMemcpyAsync(value + off, c->d_value + off, m * sizeof(float), cudaMemcpyDeviceToHost, st);
-    off += m;
+  };
+  constexpr int kFloatChunk = 128;   // 3.4 MB: ~65 us on the link, about what packing the next chunk takes
+  int off = 0, foff = n_pack;
+  while ((off < n_pack || foff < n) && e == cudaSuccess && rc == E55_OK) {
+    // the float share keeps step with the packed share (and goes first: nothing has to be waited for)
+    while (foff < n && e == cudaSuccess && rc == E55_OK &&
+           (off >= n_pack || static_cast<int64_t>(foff - n_pack) * n_pack <= static_cast<int64_t>(off) * n_float)) {
+      const int m = std::min(kFloatChunk, n - foff);
+      send(foff, m, false);
+      foff += m;
+    }
+    if (off < n_pack && e == cudaSuccess && rc == E55_OK) {
+      const int m = std::min(kPipeChunk, n_pack - off);   // a one-group-per-CTA kernel of 64 CTAs; two run side by side
+      send(off, m, e55host::packer_wait_range(packer, off, m));
+      off += m;
+    }
   }
   for (int i = 0; i < used && e == cudaSuccess; ++i) {
     e = cudaEventRecord(c->pipe_done[i], c->pipe_stream[i]);
@@ -658,21 +680,32 @@ int e55_predict(e55_ctx* c, const float* planes, int n, float* policy, float* va
   E55_CUDA(c, cudaSetDevice(c->device));
   if ((rc = ensure_capacity(c, n))) return rc;
   if (c->precision == E55_PRECISION_BF16_TC && !c->timing && n >= 2 * kPipeChunk) {
-    // Large batch on the tensor-core path: one of the two pipelines.  Which one is faster depends on the host (cores
-    // and memory bandwidth to spare against the PCIe link), so unless the caller fixed the thread count the first
-    // calls try both and later ones take the faster, looking at the other again now and then.
+    // Large batch on the tensor-core path: the cores pack one part of the batch, the rest travels as floats meanwhile.
+    // Which split is fastest depends on the host (cores and memory bandwidth to spare against the PCIe link), so
+    // unless the caller fixed the thread count the first calls try them all and later ones take the fastest,
+    // looking at its neighbours again now and then.
     e55host::Packer* packer = host_packer(c, n);
-    bool compact = packer != nullptr;
-    if (compact && c->host_auto) {
+    int level = packer ? 0 : e55_ctx::kSplitLevels - 1;   // index into kSplitEighths: how much of the batch travels as floats
+    if (packer && c->host_auto) {
       const int64_t k = c->pipe_calls++;
-      if (k < 8) compact = (k & 1) == 0;
-      else compact = (c->compact_us <= c->float_us) != (k % 128 == 0);
+      int best = 0;
+      for (int i = 1; i < e55_ctx::kSplitLevels; ++i)
+        if (c->split_us[i] < c->split_us[best]) best = i;
+      if (k < 2 * e55_ctx::kSplitLevels) level = static_cast<int>(k % e55_ctx::kSplitLevels);   // every split twice, ...
+      else if (k % 32 == 0) level = std::max(0, std::min(e55_ctx::kSplitLevels - 1, best + ((k / 32) % 2 ? 1 : -1)));   // ... a neighbour now and then, ...
+      else level = best;                                                                                            // ... else the fastest
     }
+    if (const char* env = packer ? getenv("E55_HOST_SPLIT") : nullptr)   // fixed share (eighths of the batch as floats), for measurements
+      for (int i = 0; i < e55_ctx::kSplitLevels; ++i)
+        if (e55_ctx::kSplitEighths[i] == atoi(env)) level = i;
+    const int eighths = e55_ctx::kSplitEighths[level];
+    const int n_float = eighths >= 8 ? n : (n / 8 * eighths) / 64 * 64;
     const auto t0 = std::chrono::steady_clock::now();
-    rc = compact ? predict_compacting(c, packer, planes, n, policy, value) : predict_float_pipeline(c, planes, n, policy, value);
+    rc = n_float >= n ? predict_float_pipeline(c, planes, n, policy, value) : predict_compacting(c, packer, planes, n, n_float, policy, value);
     const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / n;
-    double& avg = compact ? c->compact_us : c->float_us;
-    avg = avg == 0.0 ? us : 0.75 * avg + 0.25 * us;
+    double& avg = c->split_us[level];
+    avg = c->split_samples[level]++ < 2 ? us : 0.75 * avg + 0.25 * us;   // (the first call of a kind also pays for its set-up)
+    c->split_level = level;
     return rc;
   }
   const size_t in_bytes = static_cast<size_t>(n) * c->in_planes * kSq * sizeof(float);
@@ -835,7 +868,8 @@ int e55_set_host_threads(e55_ctx* c, int threads) {
   std::lock_guard<std::mutex> lk(c->mu);
   c->host_threads = threads;
   c->host_auto = threads < 0;
-  c->pipe_calls = 0; c->compact_us = c->float_us = 0.0;
+  c->pipe_calls = 0; c->split_level = 0;
+  for (int i = 0; i < e55_ctx::kSplitLevels; ++i) { c->split_us[i] = 0.0; c->split_samples[i] = 0; }
   if (threads == 0) { e55host::packer_destroy(c->packer); c->packer = nullptr; }
   return E55_OK;
 }
@@ -844,8 +878,20 @@ int e55_get_host_pipeline(e55_ctx* c, int* threads_out, double* compact_us_out, 
   if (!c || !threads_out || !compact_us_out || !float_us_out) return E55_ERR_INVALID;
   std::lock_guard<std::mutex> lk(c->mu);
   *threads_out = c->packer ? e55host::packer_threads(c->packer) : 0;
-  *compact_us_out = c->compact_us;
-  *float_us_out = c->float_us;
+  int best = 0;                                       // the fastest split that packs at all
+  for (int i = 1; i < e55_ctx::kSplitLevels - 1; ++i)
+    if (c->split_samples[i] && (!c->split_samples[best] || c->split_us[i] < c->split_us[best])) best = i;
+  *compact_us_out = c->split_us[best];
+  *float_us_out = c->split_us[e55_ctx::kSplitLevels - 1];
+  return E55_OK;
+}
+
+int e55_get_host_split(e55_ctx* c, int* float_eighths_out, double* us_per_position_out) {
+  if (!c || !float_eighths_out) return E55_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  *float_eighths_out = e55_ctx::kSplitEighths[c->split_level];
+  if (us_per_position_out)
+    for (int i = 0; i < e55_ctx::kSplitLevels; ++i) us_per_position_out[i] = c->split_us[i];
   return E55_OK;
 }
 

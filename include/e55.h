@@ -74,13 +74,19 @@ int e55_predict(e55_ctx* ctx, const float* planes, int n, float* policy, float* 
 
 /* Host threads e55_predict may use to bit-pack large float-plane batches before the copy (exact: a chunk whose
  * planes are not "one value or zero" travels as floats; results are identical either way).  -1 (default) = the
- * library's choice: cores - 2 threads (at most 14; E55_HOST_THREADS overrides), and it measures both ways during
- * the first calls and keeps the faster; n > 0 = always pack with n threads; 0 = off: the planes cross PCIe as they
+ * library's choice: cores - 2 threads (at most 14; E55_HOST_THREADS overrides), and during the first calls it
+ * measures how much of the batch to pack and how much to send as floats meanwhile (e55_get_host_split) and keeps
+ * the fastest; n > 0 = always pack with n threads; 0 = off: the planes cross PCIe as they
  * are. */
 int e55_set_host_threads(e55_ctx* ctx, int threads);
 /* What e55_predict measured: packing threads in use, and the running mean of microseconds per position of the
  * compacting and of the float pipeline on large batches (0 = not tried yet). */
 int e55_get_host_pipeline(e55_ctx* ctx, int* threads_out, double* compact_us_out, double* float_us_out);
+/* The compacting pipeline may leave a share of a large batch unpacked and send it as float planes in between the
+ * packed chunks (link and cores both busy).  float_eighths_out: that share, in eighths of the batch, at the latest
+ * large call (0 = all packed, 8 = the float pipeline); us_per_position_out (6 doubles, may be null): the running
+ * mean at the shares 0, 1, 2, 3, 4 and 8 eighths (0 = not tried). */
+int e55_get_host_split(e55_ctx* ctx, int* float_eighths_out, double* us_per_position_out);
 
 /* Same computation on DEVICE buffers, enqueued on the context stream; returns without
  * synchronising (call e55_sync).  Buffers must stay valid until then. */

@@ -468,20 +468,28 @@ def test_host_side_packing_is_invisible(weights_perturbed):
     x = synth.synthetic_planes(1000, seed=77)                          # ragged: not a multiple of the chunk
     lib.e55_set_host_threads(net._ctx, 0)
     p0, v0 = net.predict(x)
+    import ctypes as C
     for threads in (1, 4, -1):
         lib.e55_set_host_threads(net._ctx, threads)
-        for _ in range(2):
-            p1, v1 = net.predict(x)
+        shares = set()
+        for _ in range(14 if threads < 0 else 2):                      # the automatic mode tries every split of the batch
+            p1, v1 = net.predict(x)                                    # between packed chunks and float chunks first
             assert np.array_equal(p0, p1) and np.array_equal(v0, v1)
+            eighths = C.c_int()
+            assert lib.e55_get_host_split(net._ctx, C.byref(eighths), None) == 0
+            shares.add(eighths.value)
+        assert shares == ({0, 1, 2, 3, 4, 8} if threads < 0 else {0})
     y = x.copy()
     y[300, 5, 2, 2], y[300, 5, 3, 3] = 0.25, 0.75                      # two different non-zero values in one plane
     y[999, 265] = np.linspace(0.0, 1.0, 25, dtype=np.float32).reshape(5, 5)
     y[5, 7, 0, 0] = -0.0                                               # negative zero is still zero
     lib.e55_set_host_threads(net._ctx, 0)
     q0, w0 = net.predict(y)
-    lib.e55_set_host_threads(net._ctx, 4)
-    q1, w1 = net.predict(y)
-    assert np.array_equal(q0, q1) and np.array_equal(w0, w1) and not np.array_equal(q0[300], p0[300])
+    for threads, calls in ((4, 1), (-1, 12)):
+        lib.e55_set_host_threads(net._ctx, threads)
+        for _ in range(calls):
+            q1, w1 = net.predict(y)
+            assert np.array_equal(q0, q1) and np.array_equal(w0, w1) and not np.array_equal(q0[300], p0[300])
     net.close()
 
 
