@@ -1,6 +1,8 @@
 // Host-side profile of the self-play loop without a GPU: links e55_game.cpp against stub network entry points that
 // return cheap pseudo-random logits, so tree / move generation / mate search / encoding costs can be measured here.
 //   g++ -O3 -std=c++20 -march=x86-64-v3 -pthread -I. tools/host_prof.cpp erweitern_55_b200/csrc/e55_game.cpp -o /tmp/host_prof
+// The same build with -O1 -g -fsanitize=address,undefined or -fsanitize=thread is how the engine, the tree and the
+// pooled self-play driver were checked for memory errors and data races (clean on 20 000 moves, 6 threads).
 #include <atomic>
 #include <chrono>
 #include <cstdio>
@@ -83,6 +85,7 @@ int main(int argc, char** argv) {
   const long moves = argc > 2 ? atol(argv[2]) : 200;
   const int mate = argc > 3 ? atoi(argv[3]) : 7;
   const int sims = argc > 4 ? atoi(argv[4]) : 800;
+  { uint32_t b[266] = {}; float pol[1725], v; fill(b, 1, pol, &v); }   // the stub's logit table, before any worker thread looks at it
   e55_selfplay_config cfg;
   e55_selfplay_default_config(&cfg);
   cfg.threads = threads; cfg.total_moves = moves; cfg.mate_depth = mate; cfg.simulations = sims;
