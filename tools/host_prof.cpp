@@ -80,7 +80,92 @@ int e55_get_arch(const e55_ctx*, int* b, int* f, int* ip) { *b = 7; *f = 128; *i
 int e55_service_stats(e55_ctx*, int64_t* b, int64_t* p) { *b = g_calls; *p = g_positions; return 0; }
 }
 
+// `host_prof fuzz <games> [simulations]`: the position / tree API the Python classes bind (e55_pos_*, e55_mcts_*), driven
+// the way mcts.py drives minishogilib -- immediate mode, random policies, tree reuse -- with every query in between.
+// Meant for the sanitizer builds; returns non-zero on any inconsistency it sees itself.
+static int fuzz(int games, int sims) {
+  uint64_t rng = 0x55aa1234beefull;
+  auto rnd = [&] { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; return rng; };
+  std::vector<float> policy(1725);
+  std::vector<uint32_t> bits(266);
+  std::vector<float> scale(266);
+  char buf[16384], mv[16], sf[4096];
+  int counts[700];
+  long plies = 0, mates = 0, reps = 0;
+  e55_mcts* tree = e55_mcts_create(0.05);
+  e55_mcts_configure(tree, 1.25f, 0.15f, 0.25f, 7);
+  for (int g = 0; g < games; ++g) {
+    e55_pos* pos = e55_pos_create();
+    e55_mcts_clear(tree);
+    for (int ply = 0; ply < 200; ++ply) {
+      const int n_moves = e55_pos_generate_moves(pos, buf, sizeof(buf));
+      int rep[3];
+      e55_pos_is_repetition(pos, rep);
+      if (n_moves <= 0 || rep[0]) { reps += rep[0]; break; }
+      if (e55_pos_sfen(pos, sf, sizeof(sf)) != 0) return 10;
+      e55_pos* again = e55_pos_create();                       // SFEN -> the same position
+      if (e55_pos_set_sfen(again, sf) != 0) return 11;
+      char sf2[4096];
+      e55_pos_sfen(again, sf2, sizeof(sf2));
+      // (board, side and hands; the move number restarts: set_sfen counts plies from the position it is given)
+      if (strncmp(sf, sf2, strrchr(sf, ' ') - sf) != 0) {
+        fprintf(stderr, "sfen round trip: '%s' -> '%s'\n", sf, sf2);
+        return 12;
+      }
+      e55_pos_destroy(again);
+      e55_pos_encode_packed(pos, bits.data(), scale.data());
+      e55_pos_print(pos, buf, sizeof(buf));
+      if (e55_pos_solve_checkmate_dfs(pos, 3, mv, sizeof(mv)) == 1) {
+        ++mates;
+        if (e55_pos_do_move(pos, mv) != 0) return 13;
+        continue;
+      }
+      const int root = e55_mcts_set_root(tree, pos, (g & 1));
+      if (root < 0) return 14;
+      for (float& v : policy) v = static_cast<float>(rnd() % 2048) / 512.f - 2.f;
+      if (!e55_mcts_expanded(tree, root)) e55_mcts_evaluate(tree, root, pos, policy.data(), 0.5f);
+      e55_mcts_add_noise(tree, root);
+      for (int s = 0; s < sims; ++s) {
+        e55_pos* leaf_pos = e55_pos_copy(pos);
+        const int leaf = e55_mcts_select_leaf(tree, root, leaf_pos, s % 3 == 0);
+        if (leaf < 0) return 15;
+        if (!e55_mcts_expanded(tree, leaf)) {
+          for (int k = 0; k < 64; ++k) policy[rnd() % 1725] = static_cast<float>(rnd() % 2048) / 512.f - 2.f;
+          e55_mcts_evaluate(tree, leaf, leaf_pos, policy.data(), static_cast<float>(rnd() % 1000) / 999.f);
+        }
+        e55_mcts_backpropagate(tree, leaf);
+        e55_pos_destroy(leaf_pos);
+      }
+      float q;
+      int sum_n;
+      e55_mcts_info(tree, root, buf, sizeof(buf), &q);
+      e55_mcts_describe(tree, root, buf, sizeof(buf));
+      e55_mcts_visualize(tree, root, 20, buf, sizeof(buf));
+      const int entries = e55_mcts_dump(tree, root, ply & 1, 1, &sum_n, &q, buf, sizeof(buf), counts, 700);
+      if (entries <= 0 || e55_mcts_get_playouts(tree, root, 1) < sims || e55_mcts_get_nodes(tree) <= 0 || e55_mcts_get_usage(tree) < 0) return 16;
+      int ok;
+      switch (rnd() % 3) {
+        case 0: ok = e55_mcts_best_move(tree, root, mv, sizeof(mv)); break;
+        case 1: ok = e55_mcts_softmax_sample(tree, root, 1.0f, mv, sizeof(mv)); break;
+        default: ok = e55_mcts_softmax_sample_among_top_moves(tree, root, 0.1f, 1.0f, mv, sizeof(mv)); break;
+      }
+      if (ok != 1 || e55_pos_policy_index(pos, mv) < 0 || e55_pos_do_move(pos, mv) != 0) return 17;
+      if (e55_pos_do_move(pos, "9z9z") == 0) return 18;        // nonsense must be refused
+      ++plies;
+    }
+    e55_pos_destroy(pos);
+  }
+  e55_mcts_destroy(tree);
+  printf("fuzz: %d games, %ld searched plies, %ld mate moves, %ld repetition ends: ok\n", games, plies, mates, reps);
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc > 1 && strcmp(argv[1], "fuzz") == 0) {
+    const int r = fuzz(argc > 2 ? atoi(argv[2]) : 20, argc > 3 ? atoi(argv[3]) : 64);
+    if (r) fprintf(stderr, "fuzz: check %d failed\n", r);
+    return r;
+  }
   const int threads = argc > 1 ? atoi(argv[1]) : 1;
   const long moves = argc > 2 ? atol(argv[2]) : 200;
   const int mate = argc > 3 ? atoi(argv[3]) : 7;
