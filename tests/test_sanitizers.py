@@ -13,11 +13,14 @@ SOURCES = ["tools/host_prof.cpp", "erweitern_55_b200/csrc/e55_game.cpp"]
 BASE = ["g++", "-O1", "-g", "-std=c++20", "-march=x86-64-v3", "-pthread", "-fno-omit-frame-pointer", "-I."]
 
 
-def _build(tmp_path, name, flags):
+PACKER_SOURCES = ["-Ierweitern_55_b200/csrc", "tools/pack_check.cpp", "erweitern_55_b200/csrc/e55_host.cpp"]
+
+
+def _build(tmp_path, name, flags, sources=SOURCES):
     if shutil.which("g++") is None:
         pytest.skip("no g++")
     exe = str(tmp_path / name)
-    r = subprocess.run(BASE + flags + SOURCES + ["-o", exe], cwd=ROOT, capture_output=True, text=True, timeout=300)
+    r = subprocess.run(BASE + flags + sources + ["-o", exe], cwd=ROOT, capture_output=True, text=True, timeout=300)
     if r.returncode != 0 and ("cannot find" in r.stderr or "unrecognized" in r.stderr):
         pytest.skip("sanitizer runtime not installed: " + r.stderr.strip().splitlines()[-1])
     assert r.returncode == 0, r.stderr[-2000:]
@@ -43,3 +46,11 @@ def test_selfplay_driver_under_tsan(tmp_path):
     exe = _build(tmp_path, "host_prof_tsan", ["-fsanitize=thread"])
     out = _run(exe, "4", "300", "7", "48", "3")                # 4 threads stealing games from each other
     assert "rc 0: 300 moves" in out
+
+
+@pytest.mark.parametrize("sanitizer", ["address,undefined", "thread"])
+def test_host_packer_under_sanitizers(tmp_path, sanitizer):
+    """The AVX2 plane packer and its thread pool (csrc/e55_host.cpp) against a scalar restatement: ragged batch, constant
+    planes, negative zeros, planes that cannot be packed, main thread lending a hand."""
+    exe = _build(tmp_path, "pack_check", ["-fsanitize=" + sanitizer], PACKER_SOURCES)
+    assert "0 mismatches: ok" in _run(exe, "5", "9")
