@@ -108,7 +108,7 @@ struct Params {
   Board* req_board;    // [n_games]
   uint32_t* req_seq;   // [n_games]: 0 = no request yet, else the number of the game's latest request
   const unsigned long long* ans;   // [n_games]: (request number << 16) | packed mate move, 0xFFFF = no mate
-  int n_games, game0, simulations, use_dirichlet, reuse_tree, sampling_moves, max_moves, record_cap, mate_depth;   // game0: index of the cohort's first game in the run
+  int n_games, game0, speculate, simulations, use_dirichlet, reuse_tree, sampling_moves, max_moves, record_cap, mate_depth;   // game0: index of the cohort's first game in the run
   long long move_budget;
   float c_puct, dirichlet_alpha, dirichlet_eps;
 };
@@ -432,7 +432,8 @@ __global__ void __launch_bounds__(64) select_kernel(Params p) {
   for (int k = 0; k < kLeaf; ++k) p.move_cnt[static_cast<size_t>(gi) * kLeaf + k] = 0;
   g.n_sel = 0;
   // selfplay.py:35-42: a mate within mate_depth plies is played at once, without a search (and the tree is dropped).
-  // The answer to the game's request comes from the host; until it is here the game sits the round out.
+  // The answer to the game's request comes from the host a round or two later.  Until then the game searches on
+  // regardless (p.speculate; a found mate drops that work, which is rare) -- only the end of a search waits for it.
   const unsigned long long answer = g.need_mate ? p.ans[gi] : 0ull;
   if (g.need_mate && static_cast<uint32_t>(answer >> 16) == g.req_seq) {
     const uint16_t mate = static_cast<uint16_t>(answer & 0xFFFFull);
@@ -446,7 +447,8 @@ __global__ void __launch_bounds__(64) select_kernel(Params p) {
       request_mate(g, p, gi);          // the next move starts with a mate search too
     }
   }
-  if (g.need_mate) return;
+  if (g.need_mate && (!p.speculate || g.sims_done >= p.simulations || (g.sims_done >= 0 && nodes[0].terminal))) return;
+  if (g.sims_done >= p.simulations) return;   // the answer was all that was missing: expand_kernel ends the search
   PathView pv;
   MoveList moves;
   // A round selects until the game's 16 network slots are filled (selections that end in an expanded, terminal or
@@ -557,7 +559,7 @@ __global__ void __launch_bounds__(64) expand_kernel(Params p) {
   GNode* nodes = p.nodes + (static_cast<size_t>(gi) * 2 + g.pool) * kMaxNodes;
   GEdge* edges = p.edges + (static_cast<size_t>(gi) * 2 + g.pool) * kMaxEdges;
   int32_t* child = p.child + (static_cast<size_t>(gi) * 2 + g.pool) * kMaxEdges;
-  if (g.n_sel == 0) return;            // the game spent this round on mate searches
+  if (g.n_sel == 0 && (g.need_mate || g.sims_done < p.simulations)) return;   // the game sat this round out
   const bool root_round = g.sims_done < 0;
   int evaluated = 0;
   // priors and values into the leaves evaluated this round (Mcts::expand_from_priors)
@@ -596,6 +598,7 @@ __global__ void __launch_bounds__(64) expand_kernel(Params p) {
   if (root_round) { g.sims_done = 0; if (!nodes[0].terminal) return; }   // the root evaluation is not a simulation (mcts.py:55-60)
   else g.sims_done += g.n_sel;
   if (g.sims_done < p.simulations && !nodes[0].terminal) return;
+  if (g.need_mate) return;             // a mate found by the host goes first (select_kernel)
 
   // ---- the search of this move is over: choose, play, look at the game (selfplay.py:63-78,17-31) -----------------
   const GNode& root = nodes[0];
