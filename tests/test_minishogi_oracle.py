@@ -1,0 +1,72 @@
+"""The rules oracle (oracle/minishogi_oracle.py, pure Python) pinned on the reference's own fixtures, then the native
+engine (csrc/minishogi.hpp behind erweitern_55_b200.minishogi.Position) held against it on random positions: same
+legal moves, same repetition verdicts, same mate-search answers."""
+import random
+
+import pytest
+
+from erweitern_55_b200.minishogi import Move, Position
+from oracle import minishogi_oracle as O
+from test_minishogi import CHECKMATE_KATS, REPETITION_KATS, START
+
+
+@pytest.mark.parametrize("sfen,expected", CHECKMATE_KATS)
+def test_oracle_checkmate_known_answers(sfen, expected):          # reference tests/test_checkmate.py:7-77
+    pos = O.Position(sfen)
+    found, move = pos.solve_checkmate_dfs(7)
+    assert found == expected
+    if found:
+        assert move in pos.generate_moves()
+
+
+@pytest.mark.parametrize("sfen,expected", REPETITION_KATS)
+def test_oracle_repetition_known_answers(sfen, expected):         # reference tests/test_repetition.py:7-59
+    assert O.Position(sfen).is_repetition() == expected
+
+
+def test_oracle_perft_start_position():
+    assert [O.perft(O.Position(START), d) for d in (1, 2, 3)] == [14, 181, 2512]
+
+
+def _playout_positions(seed, games, max_plies):
+    """(native position, oracle position) pairs along random games, both fed the same moves."""
+    rng = random.Random(seed)
+    for _ in range(games):
+        native, oracle = Position(), O.Position(START)
+        for _ in range(max_plies):
+            yield native, oracle
+            moves = sorted(m.sfen() for m in native.generate_moves())
+            if not moves or native.is_repetition()[0]:
+                break
+            # captures and drops more often than a uniform choice would: hands fill up, kings get chased
+            sharp = [m for m in moves if "*" in m or "+" in m]
+            mv = rng.choice(sharp) if sharp and rng.random() < 0.35 else rng.choice(moves)
+            native.do_move(Move(mv))
+            oracle.do_move(mv)
+
+
+def test_native_engine_generates_the_oracles_moves():
+    n = 0
+    for native, oracle in _playout_positions(seed=2024, games=14, max_plies=70):
+        assert sorted(m.sfen() for m in native.generate_moves()) == sorted(oracle.generate_moves()), native.sfen()
+        assert native.is_repetition() == oracle.is_repetition(), native.sfen(True)
+        assert native.sfen().rsplit(" ", 1)[0] == oracle.board_sfen()
+        n += 1
+    assert n > 300
+
+
+def test_native_mate_search_agrees_with_the_oracle():
+    checked = mates = 0
+    for i, (native, oracle) in enumerate(_playout_positions(seed=7, games=30, max_plies=60)):
+        if i % 3:
+            continue
+        found, move = native.solve_checkmate_dfs(3)
+        assert found == oracle.solve_checkmate_dfs(3)[0], native.sfen()
+        if found:                                                   # the native move is one the oracle accepts as mating
+            mates += 1
+            assert move.sfen() in oracle.generate_moves()
+            undo = oracle._apply(move.sfen())
+            assert oracle.in_check(oracle.side) and oracle._defend(2), native.sfen()
+            oracle._revert(undo)
+        checked += 1
+    assert checked > 150 and mates > 0
