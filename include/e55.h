@@ -249,13 +249,14 @@ int e55_selfplay_run(e55_ctx* ctx, int threads, long total_moves, int simulation
  * network, one thread per game, `games` games at once; nothing but counters crosses PCIe and the host cores do not
  * matter (csrc/e55_gpu_selfplay.cuh).  Same rules, encoding and search as the host driver (shared source; tree reuse
  * and Dirichlet noise as in client.py:27-35, mate search of mate_depth plies before every search as in
- * selfplay.py:35-42 -- that one, a divergent recursion, is answered by the host from the roots the games post), except that a round selects until a game's 16 network slots are filled (at most 24
- * selections) and an unevaluated root takes a round of its own.  simulations: a multiple of 16, at most 1024.
- * records (optional): the first record_cap finished games, 16384 uint16 words each: plies, winner, words used, 0, then
- * per ply what selfplay.run records (selfplay.py:80-92) -- move, sum_N, Q * 65535, k, and k (move, N) pairs of the
- * visited root children; moves are packed as from (31 = drop) | to << 5 | piece << 10 | promotes << 14.  records (optional): the first record_cap finished games as
- * uint16 [258] each -- plies, winner, then the moves packed as from (31 = drop) | to << 5 | piece << 10 |
- * promotes << 14.  stats_out->mean_gpu_batch is the positions per network launch (16 slots per game). */
+ * selfplay.py:35-42 -- that one, a divergent recursion, is answered by the host from the roots the games post),
+ * except that a round selects until a game's 16 network slots are filled (at most 24 selections) and an
+ * unevaluated root takes a round of its own.  From 2 048 games on, the games run as two cohorts on two streams so
+ * that one cohort's search overlaps the other's network launch.  simulations: a multiple of 16, at most 1024.
+ * records (optional): the first record_cap finished games, 16384 uint16 words each: plies, winner, words used, 0,
+ * then per ply what selfplay.run records (selfplay.py:80-92) -- move, sum_N, Q * 65535, k, and k (move, N) pairs of
+ * the visited root children; moves are packed as from (31 = drop) | to << 5 | piece << 10 | promotes << 14.
+ * stats_out->mean_gpu_batch is the positions per network launch (16 slots per game of a cohort). */
 int e55_gpu_selfplay_run(e55_ctx* ctx, int games, long total_moves, int simulations, int mate_depth, int reuse_tree,
                          int use_dirichlet, int sampling_moves, int max_moves, uint64_t seed, e55_selfplay_stats* stats_out,
                          uint16_t* records, int record_cap,
