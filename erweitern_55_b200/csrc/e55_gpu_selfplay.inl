@@ -294,7 +294,7 @@ int e55_gpu_selfplay_run(e55_ctx* c, int games, long total_moves, int simulation
   out->evals = static_cast<long>(h_shared->evals);
   out->games = static_cast<long>(h_shared->games);
   out->mean_game_plies = h_shared->games ? static_cast<double>(h_shared->plies_in_finished_games) / static_cast<double>(h_shared->games) : 0.0;
-  out->mean_gpu_batch = static_cast<double>(n);
+  out->mean_gpu_batch = static_cast<double>(n) / n_cohorts;   // slots per network launch
   if (timeline && rc == E55_OK) {
     for (long r = 0; r < kTlRounds; ++r)
       for (int k = 0; k < n_cohorts; ++k) {
