@@ -115,6 +115,7 @@ SIGNATURES.update({
     "e55_gpu_selfplay_run": (C.c_int, [_ctx, C.c_int, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.POINTER(SelfplayStats),
                                        C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "e55_selftest_engine": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int64)]),
+    "e55_selftest_encode": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "e55_selfplay_default_config": (None, [C.POINTER(SelfplayConfig)]),
     "e55_selfplay_run_ex": (C.c_int, [_ctx, C.POINTER(SelfplayConfig), C.POINTER(SelfplayStats)]),
     "e55_selfplay_run": (C.c_int, [_ctx, C.c_int, C.c_long, C.c_int, C.c_int, C.c_int, C.c_uint64, C.POINTER(SelfplayStats)]),

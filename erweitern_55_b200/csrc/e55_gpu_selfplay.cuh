@@ -642,6 +642,65 @@ __global__ void __launch_bounds__(64) expand_kernel(Params p) {
   request_mate(g, p, gi);              // selfplay.py:35-36: every move starts with the mate search
 }
 
+// Validation of the device-side history: every thread plays a random game with the game bookkeeping (game_play), walks
+// a random path below it with the descent's bookkeeping (path_push), encodes the position it arrives at
+// (path_encode) and judges it (path_repetition).  The host replays the moves on a Position and must get the same planes,
+// repetition verdict and number of legal moves (e55_selftest_encode).  Moves that take the previous one back are
+// preferred now and then, so that positions do repeat.
+constexpr int kSelftestMoves = 192;   // moves per thread: at most 128 of the game + 48 of the path
+__global__ void encode_selftest_kernel(Game* games, int n, uint64_t seed, uint32_t* bits, float* scale, uint16_t* moves_out, int32_t* info) {
+  const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= n) return;
+  Game& g = games[gi];
+  uint64_t rng = (seed + 0x9E3779B97F4A7C15ull * static_cast<uint64_t>(gi + 1)) | 1ull;
+  for (int i = 0; i < 8; ++i) next_u64(rng);
+  GNode scratch_root;
+  g.pool = 0;
+  start_game(g, &scratch_root);
+  MoveList moves;
+  uint16_t* out = moves_out + static_cast<size_t>(gi) * kSelftestMoves;
+  int n_out = 0;
+  auto pick = [&](const MoveList& l, int n_played) {
+    if (n_played >= 2 && (next_u64(rng) & 3) != 0) {        // take my previous move back, if that is legal
+      const Move prev = unpack_move(out[n_played - 2]);
+      if (!prev.is_drop() && !prev.promotes)
+        for (int i = 0; i < l.size(); ++i)
+          if (l.m[i].from == prev.to && l.m[i].to == prev.from && !l.m[i].promotes) return i;
+    }
+    return static_cast<int>(next_u64(rng) % static_cast<uint64_t>(l.size()));
+  };
+  const int game_plies = static_cast<int>(next_u64(rng) % 129), path_plies = static_cast<int>(next_u64(rng) % 49);
+  for (int i = 0; i < game_plies; ++i) {
+    g.root.generate_moves(moves);
+    if (moves.empty()) break;
+    const Move m = moves.m[pick(moves, n_out)];
+    out[n_out++] = pack_move(m);
+    game_play(g, m);
+  }
+  Board pos = g.root;
+  PathView pv;
+  pv.g = &g; pv.ply0 = pos.ply; pv.depth = 0;
+  for (int i = 0; i < path_plies; ++i) {
+    pos.generate_moves(moves);
+    if (moves.empty()) break;
+    Move m = moves.m[pick(moves, n_out)];
+    out[n_out++] = pack_move(m);
+    m.captured = static_cast<int8_t>(Board::type_of(pos.board[m.to]));      // as select_kernel plays a move
+    const uint64_t key = pos.hash_after(pv.key(pv.last()), m);
+    pos.apply(m);
+    ++pos.ply;
+    path_push(pv, pos, key, pos.in_check(pos.side));
+  }
+  path_encode(pv, pos, bits + static_cast<size_t>(gi) * kInputPlanes, scale + static_cast<size_t>(gi) * kInputPlanes);
+  bool rep, my_check, op_check;
+  path_repetition(pv, rep, my_check, op_check);
+  pos.generate_moves(moves);
+  info[gi * 4 + 0] = n_out;
+  info[gi * 4 + 1] = pv.depth;
+  info[gi * 4 + 2] = (rep ? 1 : 0) | (my_check ? 2 : 0) | (op_check ? 4 : 0) | (pv.rep_count(pv.last()) << 8);
+  info[gi * 4 + 3] = moves.size();
+}
+
 // Device perft from the start position (validation of the device build of the engine).
 __device__ long long perft_rec(Board& b, int depth) {
   MoveList l;

@@ -45,6 +45,70 @@ int e55_selftest_engine(int device, int depth, int64_t* nodes_out) {
   return E55_OK;
 }
 
+int e55_selftest_encode(int device, int n, uint64_t seed, int64_t* mismatches_out, int64_t* repetitions_out, int64_t* path_plies_out) {
+  namespace gs = e55::gs;
+  if (n < 1 || n > 65536 || !mismatches_out || !repetitions_out || !path_plies_out) return E55_ERR_INVALID;
+  if (cudaSetDevice(device) != cudaSuccess || device_engine_ready() != cudaSuccess) return E55_ERR_CUDA;
+  const size_t N = static_cast<size_t>(n);
+  gs::Game* d_games = nullptr;
+  uint32_t* d_bits = nullptr;
+  float* d_scale = nullptr;
+  uint16_t* d_moves = nullptr;
+  int32_t* d_info = nullptr;
+  cudaError_t e = cudaMalloc(&d_games, N * sizeof(gs::Game));
+  if (e == cudaSuccess) e = cudaMalloc(&d_bits, N * mshogi::kInputPlanes * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&d_scale, N * mshogi::kInputPlanes * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&d_moves, N * gs::kSelftestMoves * sizeof(uint16_t));
+  if (e == cudaSuccess) e = cudaMalloc(&d_info, N * 4 * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMemset(d_games, 0, N * sizeof(gs::Game));
+  std::vector<uint32_t> bits(N * mshogi::kInputPlanes);
+  std::vector<float> scale(N * mshogi::kInputPlanes);
+  std::vector<uint16_t> moves(N * gs::kSelftestMoves);
+  std::vector<int32_t> info(N * 4);
+  if (e == cudaSuccess) {
+    gs::encode_selftest_kernel<<<(n + 63) / 64, 64>>>(d_games, n, seed, d_bits, d_scale, d_moves, d_info);
+    e = cudaDeviceSynchronize();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(bits.data(), d_bits, bits.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(scale.data(), d_scale, scale.size() * sizeof(float), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(moves.data(), d_moves, moves.size() * sizeof(uint16_t), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(info.data(), d_info, info.size() * sizeof(int32_t), cudaMemcpyDeviceToHost);
+  cudaFree(d_games); cudaFree(d_bits); cudaFree(d_scale); cudaFree(d_moves); cudaFree(d_info);
+  if (e != cudaSuccess) { cudaGetLastError(); return E55_ERR_CUDA; }
+  int64_t bad = 0, reps = 0, path = 0;
+  uint32_t hb[mshogi::kInputPlanes];
+  float hs[mshogi::kInputPlanes];
+  for (size_t i = 0; i < N; ++i) {
+    mshogi::Position pos;
+    const int n_moves = info[i * 4];
+    bool legal = n_moves >= 0 && n_moves <= gs::kSelftestMoves;
+    for (int k = 0; legal && k < n_moves; ++k) {
+      const mshogi::Move mv = gs::unpack_move(moves[i * gs::kSelftestMoves + k]);
+      mshogi::MoveList l;
+      pos.generate_moves(l);
+      legal = std::find(l.begin(), l.end(), mv) != l.end();
+      if (legal) pos.do_move(mv);
+    }
+    if (!legal) { ++bad; continue; }
+    mshogi::encode_packed(pos, hb, hs);
+    bool rep, my_check, op_check;
+    pos.is_repetition(rep, my_check, op_check);
+    mshogi::MoveList l;
+    pos.generate_moves(l);
+    const int flags = (rep ? 1 : 0) | (my_check ? 2 : 0) | (op_check ? 4 : 0) | (pos.repetition_count() << 8);
+    const bool same = memcmp(hb, bits.data() + i * mshogi::kInputPlanes, sizeof(hb)) == 0 &&
+                      memcmp(hs, scale.data() + i * mshogi::kInputPlanes, sizeof(hs)) == 0 && flags == info[i * 4 + 2] &&
+                      l.size() == info[i * 4 + 3];
+    if (!same) ++bad;
+    if (pos.repetition_count() >= 2) ++reps;
+    path += info[i * 4 + 1];
+  }
+  *mismatches_out = bad;
+  *repetitions_out = reps;
+  *path_plies_out = path;
+  return E55_OK;
+}
+
 int e55_gpu_selfplay_run(e55_ctx* c, int games, long total_moves, int simulations, int mate_depth, int reuse_tree, int use_dirichlet,
                          int sampling_moves, int max_moves, uint64_t seed, e55_selfplay_stats* out, uint16_t* records, int record_cap,
                          int* n_records_out) {

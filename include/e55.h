@@ -263,6 +263,12 @@ int e55_gpu_selfplay_run(e55_ctx* ctx, int games, long total_moves, int simulati
                          int* n_records_out);
 /* Device build of the rules engine: perft from the start position computed on the GPU (14, 181, 2512, 35401, ...). */
 int e55_selftest_engine(int device, int depth, int64_t* nodes_out);
+/* Validation of the device-side game history: n threads each play a random game and a random path below it with the
+ * kernels' bookkeeping and encode the position they reach; the host replays the moves on a Position and compares
+ * the 266 packed planes, the repetition verdict and count and the number of legal moves.  mismatches_out must be 0;
+ * repetitions_out = positions that had occurred before (the walks are steered into repetitions), path_plies_out =
+ * plies walked below the game positions in total. */
+int e55_selftest_encode(int device, int n, uint64_t seed, int64_t* mismatches_out, int64_t* repetitions_out, int64_t* path_plies_out);
 
 /* Block until all work enqueued on the context stream has finished. */
 int e55_sync(e55_ctx* ctx);

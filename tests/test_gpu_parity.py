@@ -493,6 +493,20 @@ def test_host_side_packing_is_invisible(weights_perturbed):
     net.close()
 
 
+def test_device_history_and_encoding_equal_the_hosts():
+    """What the network sees in the GPU-resident self-play: random games plus random descents below them, played with the
+    kernels' own bookkeeping (game history ring, path view, Bloom-filtered repetition counts) and encoded on the device,
+    against the host Position replaying the same moves -- identical 266 packed planes, repetition verdicts and counts,
+    legal-move counts."""
+    import ctypes as C
+    from erweitern_55_b200 import _capi
+    lib = _capi.load()
+    bad, reps, path = C.c_int64(-1), C.c_int64(), C.c_int64()
+    assert lib.e55_selftest_encode(0, 8192, 2024, C.byref(bad), C.byref(reps), C.byref(path)) == 0
+    assert bad.value == 0, f"{bad.value} of 8192 positions differ"
+    assert reps.value > 500 and path.value > 8192 * 10           # repetitions and real descents were exercised
+
+
 @pytest.mark.parametrize("cohorts", ["1", "2"])
 def test_gpu_resident_selfplay(weights_default, monkeypatch, cohorts):
     """The search on the GPU (csrc/e55_gpu_selfplay.cuh): the device build of the rules engine counts the same perft
