@@ -11,7 +11,9 @@ two-pawn, last-rank and pawn-drop-mate restrictions, fourth occurrence of a posi
 loses.  PINNED on the reference's own fixtures -- the 9 known answers of ``tests/test_checkmate.py`` and the 8 of
 ``tests/test_repetition.py`` -- and on the published perft counts of the start position (14, 181, 2 512, 35 401);
 ``tests/test_minishogi_oracle.py`` checks those first and then holds the native engine against this file on random
-positions.
+positions.  ``to_alphazero_input`` / ``policy_index`` restate this repo's own plane and move layout (minishogilib's is
+not visible in the reference tree: "parity unpinned" for those two); they keep the native encoders honest to their
+documentation.
 
 Deliberately naive and independent of the engine's design: a mailbox board, pseudo-legal moves from step tables, legality
 by playing the move and looking for an attacker of the king.  Slow (a few thousand positions per second) and small.
@@ -84,6 +86,7 @@ class Position:
         self.ply = 0
         # history of (position key, the move into it gave check); entry 0 = the position set here
         self.history = [(self.key(), False)]
+        self.snapshots = [self._snapshot()]
         if "moves" in parts:
             for m in parts[parts.index("moves") + 1:]:
                 self.do_move(m)
@@ -246,11 +249,72 @@ class Position:
         self._apply(move)
         self.ply += 1
         self.history.append((self.key(), self.in_check(self.side)))
+        self.snapshots.append(self._snapshot())
 
     def undo_move(self, undo):
         self.history.pop()
+        self.snapshots.pop()
         self.ply -= 1
         self._revert(undo)
+
+    # ---- network input and policy index (this repo's own layout, documented in csrc/minishogi.hpp) ---------------------
+    def _snapshot(self):
+        key = self.history[-1][0]
+        return ([row[:] for row in self.board], [dict(h) for h in self.hands], sum(1 for k, _ in self.history if k == key))
+
+    def to_alphazero_input(self):
+        """[266][5][5] floats: 8 history steps (newest first) x 33 planes -- 10 piece kinds of the side to move, 10 of the
+        other side, 3 one-hot planes for the 1st / 2nd / 3rd+ occurrence, 5 + 5 hand counts / 2 -- then a plane of ones
+        if the second player is to move and a plane of ply / 512.  Everything is seen from the side to move: for the
+        second player the board is turned by 180 degrees."""
+        kinds = ["K", "G", "S", "B", "R", "P", "+S", "+B", "+R", "+P"]
+        me = self.side
+        x = [[[0.0] * N for _ in range(N)] for _ in range(266)]
+
+        def fill(plane, v):
+            for r in range(N):
+                for c in range(N):
+                    x[plane][r][c] = v
+        for t in range(8):
+            if t >= len(self.snapshots):
+                break
+            board, hands, occurrences = self.snapshots[-1 - t]
+            base = 33 * t
+            for r in range(N):
+                for c in range(N):
+                    piece = board[r][c]
+                    if piece is None:
+                        continue
+                    rr, cc = (r, c) if me == BLACK else (N - 1 - r, N - 1 - c)
+                    x[base + (0 if piece[0] == me else 10) + kinds.index(piece[1])][rr][cc] = 1.0
+            fill(base + 20 + min(occurrences, 3) - 1, 1.0)
+            for k, kind in enumerate(HAND_ORDER):
+                if hands[me][kind]:
+                    fill(base + 23 + k, hands[me][kind] / 2.0)
+                if hands[1 - me][kind]:
+                    fill(base + 28 + k, hands[1 - me][kind] / 2.0)
+        if me == WHITE:
+            fill(264, 1.0)
+        if self.ply > 0:
+            fill(265, min(self.ply, 512) / 512.0)
+        return x
+
+    def policy_index(self, move):
+        """Index of a move in the 69 x 25 policy: planes 0-31 = direction (N NE E SE S SW W NW, seen from the side to
+        move) x distance 1-4 at the origin square, 32-63 the same with promotion, 64-68 drops of G S B R P at the
+        destination square."""
+        def persp(r, c):
+            return (r, c) if self.side == BLACK else (N - 1 - r, N - 1 - c)
+        if move[1] == "*":
+            r, c = persp(*_parse_square(move[2:4]))
+            return (64 + HAND_ORDER.index(move[0])) * 25 + r * N + c
+        r, c = persp(*_parse_square(move[0:2]))
+        rr, cc = persp(*_parse_square(move[2:4]))
+        dr, dc = rr - r, cc - c
+        step = ((dr > 0) - (dr < 0), (dc > 0) - (dc < 0))
+        d = [(-1, 0), (-1, 1), (0, 1), (1, 1), (1, 0), (1, -1), (0, -1), (-1, -1)].index(step)
+        dist = max(abs(dr), abs(dc))
+        return ((32 if move.endswith("+") else 0) + d * 4 + dist - 1) * 25 + r * N + c
 
     # ---- repetition (tests/test_repetition.py) ---------------------------------------------------------------------
     def is_repetition(self):

@@ -70,3 +70,18 @@ def test_native_mate_search_agrees_with_the_oracle():
             oracle._revert(undo)
         checked += 1
     assert checked > 150 and mates > 0
+
+
+def test_native_input_planes_and_policy_index_follow_the_documented_layout():
+    import numpy as np
+    n = 0
+    for i, (native, oracle) in enumerate(_playout_positions(seed=99, games=8, max_plies=60)):
+        if i % 2:
+            continue
+        got = np.asarray(native.to_alphazero_input(), dtype=np.float32).reshape(266, 5, 5)
+        want = np.asarray(oracle.to_alphazero_input(), dtype=np.float32)
+        assert np.array_equal(got, want), (native.sfen(True), np.argwhere(got != want)[:5])
+        for m in native.generate_moves():
+            assert native.policy_index(m) == oracle.policy_index(m.sfen()), (native.sfen(), m.sfen())
+        n += 1
+    assert n > 100
