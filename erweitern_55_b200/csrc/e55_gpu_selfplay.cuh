@@ -5,15 +5,18 @@
 // of e55_game.cpp needs ~1.5 ms of a core per move; an 8-GPU box with four cores per GPU starves it).
 //
 // One round = what one iteration of MCTS.run's main loop does for every game (mcts.py:91-110):
-//   select_kernel   per game: kLeaf selections with virtual loss; each new leaf gets its terminal test, its legal
-//                   moves (stored as the node's edges straight away) and its bit-packed planes in a batch slot
-//   tower_kernel    all slots of all games in one launch (e55_tc.cuh), then legal_priors_strided_kernel
+//   select_kernel   per game: selections with virtual loss until kLeaf network slots are filled; each new leaf gets its
+//                   terminal test, its legal moves (stored as the node's edges straight away) and its bit-packed
+//                   planes in a batch slot
+//   tower_kernel    all slots of a cohort of games in one launch (e55_tc.cuh), then legal_priors_strided_kernel
 //   expand_kernel   per game: priors and values into the new nodes, back-up of every selection; after the last
 //                   simulation of a move: choose it (sampled from the visit counts for the first plies), play it,
 //                   test for the end of the game, start the next search (or the next game)
 // Rules, encoding and policy indexing are the very functions the host engine uses (minishogi.hpp, compiled for the
-// device); the search follows csrc/mcts.hpp.  Differences to the host driver: no tree reuse between moves and the
-// root evaluation takes a round of its own.  Included by e55_api.cu.
+// device); the search follows csrc/mcts.hpp, tree reuse included (keep_subtree).  Differences to the host driver: the
+// root evaluation takes a round of its own, and the mate search before every move is answered by the host
+// (request_mate) while the game already searches.  The host side (e55_gpu_selfplay.inl) runs the games as two cohorts
+// on two streams, so that one cohort's kernels here overlap the other's tower launch.  Included by e55_api.cu.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -104,7 +107,7 @@ struct Params {
   uint16_t* records;   // [record_cap][kRecordWords]: finished games, in the layout of finish_game
   uint16_t* rec_buf;   // [n_games][kRecordWords]: the record of the game in progress (null: no records wanted)
   // mate search (selfplay.py:35-42): divergent recursion with a long tail, so the host does it -- a game posts its root
-  // here, the driver answers a round or two later (e55_gpu_selfplay.inl); the game idles meanwhile
+  // here, the driver answers a round or two later (e55_gpu_selfplay.inl); the game searches on meanwhile (speculate)
   Board* req_board;    // [n_games]
   uint32_t* req_seq;   // [n_games]: 0 = no request yet, else the number of the game's latest request
   const unsigned long long* ans;   // [n_games]: (request number << 16) | packed mate move, 0xFFFF = no mate
