@@ -29,20 +29,30 @@ class Node:
 class Tree:
     def __init__(self, c_puct=1.25):
         self.c_puct = f32(c_puct)
+        self.forced_k = f32(2)
         self.root = Node()
 
-    def select_leaf(self, node, pos):
-        """PUCT descent from `node`; the moves are played on `pos` (an oracle Position); virtual loss on every edge taken."""
+    def select_leaf(self, node, pos, forced_playouts=False):
+        """PUCT descent from `node`; the moves are played on `pos` (an oracle Position); virtual loss on every edge taken.
+        forced_playouts (KataGo, used by mcts.py:97 during self-play): a child of the starting node that has been
+        visited is taken again while it has fewer than sqrt(k P N) playouts, k = 2."""
+        start = node
         while node.expanded and not node.terminal:
             total = sum(n + v for n, v in zip(node.n_edge, node.vloss))
             sq = np.sqrt(f32(total) + f32(1e-8))
-            best, best_score = 0, f32(-1e30)
-            for i in range(len(node.moves)):
+            best, best_score = None, f32(-1e30)
+            if forced_playouts and node is start:
+                for i in range(len(node.moves)):
+                    if node.n_edge[i] > 0 and f32(node.n_edge[i] + node.vloss[i]) < np.sqrt(self.forced_k * node.prior[i] * f32(total)):
+                        best = i
+                        break
+            for i in range(len(node.moves) if best is None else 0):
                 n = node.n_edge[i] + node.vloss[i]
                 q = node.w[i] / f32(n) if n > 0 else f32(0)
                 score = q + self.c_puct * node.prior[i] * sq / (f32(1) + f32(n))
                 if score > best_score:
                     best, best_score = i, score
+            best = best or 0
             node.vloss[best] += 1
             pos.do_move(node.moves[best])
             if node.child[best] is None:
@@ -96,6 +106,28 @@ class Tree:
             node = p
             node.n += 1
 
-    def visits(self, node=None):
+    def visits(self, node=None, target_pruning=False):
+        """Visit counts of the children.  target_pruning (KataGo; mcts.py:187 for the training targets): forced playouts
+        are taken back from every child but the most visited one while its PUCT score, with its utility held, stays
+        below the best child's; children left with one playout are dropped."""
         node = node or self.root
-        return {m: n for m, n in zip(node.moves, node.n_edge) if n > 0}
+        cnt = list(node.n_edge)
+        total = sum(cnt)
+        if target_pruning and total > 0:
+            best = max(range(len(cnt)), key=lambda i: (cnt[i], -i))
+            sq = np.sqrt(f32(total))
+
+            def puct(i, n):
+                q = node.w[i] / f32(node.n_edge[i]) if node.n_edge[i] > 0 else f32(0)
+                return q + self.c_puct * node.prior[i] * sq / (f32(1) + f32(n))
+            best_score = puct(best, cnt[best])
+            for i in range(len(cnt)):
+                if i == best or cnt[i] == 0:
+                    continue
+                forced = int(np.sqrt(self.forced_k * node.prior[i] * f32(total)))
+                while forced > 0 and cnt[i] > 0 and puct(i, cnt[i] - 1) < best_score:
+                    cnt[i] -= 1
+                    forced -= 1
+                if cnt[i] <= 1:
+                    cnt[i] = 0
+        return {m: n for m, n in zip(node.moves, cnt) if n > 0}

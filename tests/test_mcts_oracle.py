@@ -27,6 +27,7 @@ def _fake_network(key, moves):
 @pytest.mark.parametrize("sfen,simulations,batch,ends", [
     (START, 640, 1, False),
     (START, 640, 8, False),                                          # leaf batches: virtual loss spreads the selections
+    (START, 800, 16, None),                                          # as in self-play: forced playouts, pruned targets
     ("2k2/5/2B2/5/2K2 b GSBRgsr2p 1", 480, 8, True),                 # many drops, mates within reach
     ("2k2/5/5/5/2K2 b R 1 moves R*3c 3a2a 3c2c 2a3a 2c3c 3a2a 3c2c 2a3a 2c3c 3a2a 3c2c", 480, 4, True),   # perpetual check two plies below the root
 ])
@@ -47,6 +48,7 @@ def test_native_tree_walks_and_counts_like_the_oracle(sfen, simulations, batch, 
         native.evaluate(node_n, pos_n, policy, value)
         oracle.evaluate(node_o, pos_o, moves, logits, value)
 
+    forced = ends is None                                            # mcts.py:97: forced_playouts during self-play
     played = []                                                      # moves played at the root since `sfen`
 
     def oracle_position():
@@ -66,8 +68,8 @@ def test_native_tree_walks_and_counts_like_the_oracle(sfen, simulations, batch, 
             leaves = []
             for _ in range(batch):
                 pos_n, pos_o = native_root_pos.copy(True), oracle_position()
-                leaf_n = native.select_leaf(root, pos_n)
-                leaf_o = oracle.select_leaf(oracle.root, pos_o)
+                leaf_n = native.select_leaf(root, pos_n, forced)
+                leaf_o = oracle.select_leaf(oracle.root, pos_o, forced)
                 assert pos_n.sfen().rsplit(" ", 1)[0] == pos_o.board_sfen() and pos_n.get_ply() == pos_o.ply, (done, pos_n.sfen(True))
                 leaves.append((leaf_n, pos_n, leaf_o, pos_o))
             for leaf_n, pos_n, leaf_o, pos_o in leaves:
@@ -87,6 +89,10 @@ def test_native_tree_walks_and_counts_like_the_oracle(sfen, simulations, batch, 
     assert abs(q - w / simulations) < 1e-5
     if ends:
         assert terminals > 0                                         # the walk did run into ends of the game
+    if forced:                                                       # the training targets (mcts.py:187, selfplay.py:80-92)
+        pruned_sum, _, pruned = native.dump(root, True, True)
+        assert dict(pruned) == oracle.visits(target_pruning=True) and pruned_sum == sum(dict(pruned).values()) <= simulations
+        assert dict(pruned) != dict(visits)                          # (the pruning did take playouts back)
 
     # the game goes on: the most visited move is played and its subtree becomes the tree (set_root with reuse_tree,
     # mcts.py:50 / client.py:32) -- twice, the searches in between still in step
