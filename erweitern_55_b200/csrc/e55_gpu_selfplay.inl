@@ -174,7 +174,8 @@ int e55_gpu_selfplay_run(e55_ctx* c, int games, long total_moves, int simulation
     if (ready) cudaEventDestroy(ready);
   };
   if (e != cudaSuccess) { cleanup(); return fail(c, E55_ERR_CUDA, std::string("GPU self-play buffers: ") + cudaGetErrorString(e)); }
-  p.n_games = games; p.game0 = 0; p.speculate = !(getenv("E55_GPU_SPECULATE") && atoi(getenv("E55_GPU_SPECULATE")) == 0); p.simulations = simulations; p.use_dirichlet = use_dirichlet; p.reuse_tree = reuse_tree; p.mate_depth = mate_depth;
+  p.n_games = games; p.game0 = 0; p.simulations = simulations; p.use_dirichlet = use_dirichlet; p.reuse_tree = reuse_tree; p.mate_depth = mate_depth;
+  p.speculate = !(getenv("E55_GPU_SPECULATE") && atoi(getenv("E55_GPU_SPECULATE")) == 0);   // search on while the host looks for a mate
   p.sampling_moves = sampling_moves; p.max_moves = std::min(max_moves, gs::kMaxPly); p.record_cap = record_cap; p.move_budget = total_moves;
   p.c_puct = 1.25f; p.dirichlet_alpha = 0.15f; p.dirichlet_eps = 0.25f;
   // Two cohorts of games on two streams: while the network evaluates one cohort's leaves the search kernels of the other
