@@ -85,3 +85,28 @@ def test_native_input_planes_and_policy_index_follow_the_documented_layout():
             assert native.policy_index(m) == oracle.policy_index(m.sfen()), (native.sfen(), m.sfen())
         n += 1
     assert n > 100
+
+
+@pytest.mark.parametrize("depth,games,every", [(5, 30, 6), (7, 14, 8)])          # 7 = selfplay.py:36's depth
+def test_native_deep_mate_search_agrees_with_the_oracle(depth, games, every):
+    """Middle-game positions (pieces in hand, exposed kings): mate or no mate within `depth` plies, native against oracle."""
+    checked = mates = 0
+    rng = random.Random(11 * depth)
+    for _ in range(games):
+        native, oracle = Position(), O.Position(START)
+        for ply in range(70):
+            moves = sorted(m.sfen() for m in native.generate_moves())
+            if not moves or native.is_repetition()[0]:
+                break
+            if ply >= 16 and ply % every == 0:
+                found, move = native.solve_checkmate_dfs(depth)
+                assert found == oracle.solve_checkmate_dfs(depth)[0], (depth, native.sfen())
+                if found:
+                    assert move.sfen() in moves
+                checked += 1
+                mates += found
+            sharp = [m for m in moves if "*" in m or "+" in m]
+            mv = rng.choice(sharp) if sharp and rng.random() < 0.35 else rng.choice(moves)
+            native.do_move(Move(mv))
+            oracle.do_move(mv)
+    assert checked > 50 and mates > 5
