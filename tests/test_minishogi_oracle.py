@@ -110,3 +110,40 @@ def test_native_deep_mate_search_agrees_with_the_oracle(depth, games, every):
             native.do_move(Move(mv))
             oracle.do_move(mv)
     assert checked > 50 and mates > 5
+
+
+def test_native_repetition_verdicts_on_games_steered_into_repetitions():
+    """Both sides keep taking their last move back when they can: fourth occurrences and perpetual checks do happen,
+    and the native engine's (repetition, my_check, op_check) is the oracle's at every ply."""
+    rng = random.Random(5)
+    repetitions = perpetual = plies = 0
+    starts = [START, START, "2k2/5/5/5/2K2 b R 1", "3k1/5/2R2/5/2K2 b - 1"]      # the last two: a rook chasing a bare king
+    for game in range(48):
+        sfen = starts[game % 4]
+        native, oracle = Position(), O.Position(sfen)
+        native.set_sfen(sfen)
+        played = []
+        for _ in range(60):
+            verdict = native.is_repetition()
+            assert verdict == oracle.is_repetition(), native.sfen(True)
+            plies += 1
+            if verdict[0]:
+                repetitions += 1
+                perpetual += verdict[1] or verdict[2]
+                break
+            moves = sorted(m.sfen() for m in native.generate_moves())
+            if not moves:
+                break
+            back = played[-2][2:4] + played[-2][0:2] if len(played) >= 2 and "*" not in played[-2] and "+" not in played[-2] else None
+            checks = []
+            if rng.random() < 0.5:                                   # a checking move, if there is one: perpetual checks
+                for m in moves:
+                    undo = oracle._apply(m)
+                    if oracle.in_check(oracle.side):
+                        checks.append(m)
+                    oracle._revert(undo)
+            mv = back if back in moves and rng.random() < 0.8 else (rng.choice(checks) if checks else rng.choice(moves))
+            played.append(mv)
+            native.do_move(Move(mv))
+            oracle.do_move(mv)
+    assert repetitions >= 10 and perpetual >= 1 and plies > 500, (repetitions, perpetual, plies)
