@@ -93,8 +93,8 @@ struct e55_ctx {
   int host_threads = -1;           // -1: chosen from the core count on first use; 0: off
   bool host_auto = true;           // the caller left the choice to the library: measure both pipelines, use the faster
   int64_t pipe_calls = 0;
-  static constexpr int kSplitLevels = 6;
-  static constexpr int kSplitEighths[kSplitLevels] = {0, 1, 2, 3, 4, 8};   // eighths of a large batch that travel as float planes
+  static constexpr int kSplitLevels = 8;
+  static constexpr int kSplitEighths[kSplitLevels] = {0, 1, 2, 3, 4, 5, 6, 8};   // eighths of a large batch that travel as float planes
   double split_us[kSplitLevels] = {};        // running mean of microseconds per position at each split
   int split_samples[kSplitLevels] = {};
   int split_level = 0;                       // the split of the latest large call
@@ -102,6 +102,10 @@ struct e55_ctx {
   uint32_t* h_bits = nullptr;      // pinned [h_cap][in_planes]
   float* h_scale = nullptr;
   int h_cap = 0;
+  float* h_out_policy = nullptr;   // pinned staging of results for pageable caller buffers: [h_out_cap][1725], [h_out_cap]
+  float* h_out_value = nullptr;
+  int h_out_cap = 0;
+  std::vector<cudaEvent_t> chunk_ev;   // one per chunk of the host-buffer pipeline (grown on demand)
   // e55_predict_packed_moves: one pinned request block and one answer block per call, and their device twins
   uint8_t *h_req = nullptr, *h_ans = nullptr, *d_req = nullptr, *d_ans = nullptr;
   size_t req_cap = 0, ans_cap = 0;
@@ -369,32 +373,38 @@ int pipe_chunk(int left, int chunk) {
   return half >= left ? left : half;
 }
 
+constexpr int kSmallBatch = 64;   // below this a host-buffer predict is one copy in, one kernel, one copy out
+
+// Pinned staging of the packed form of `n` positions.
+int ensure_host_staging(e55_ctx* c, int n) {
+  if (n <= c->h_cap) return E55_OK;
+  cudaFreeHost(c->h_bits); cudaFreeHost(c->h_scale);
+  c->h_bits = nullptr; c->h_scale = nullptr; c->h_cap = 0;
+  int cap = 256;
+  while (cap < n) cap *= 2;
+  const size_t w = static_cast<size_t>(cap) * c->in_planes;
+  if (cudaMallocHost(&c->h_bits, w * sizeof(uint32_t)) != cudaSuccess || cudaMallocHost(&c->h_scale, w * sizeof(float)) != cudaSuccess) {
+    cudaFreeHost(c->h_bits); c->h_bits = nullptr; c->h_scale = nullptr;
+    return fail(c, E55_ERR_CUDA, std::string("pinned staging: ") + cudaGetErrorString(cudaGetLastError()));
+  }
+  c->h_cap = cap;
+  return E55_OK;
+}
+
 // The packing pool and pinned staging for `n` positions (null: compaction is off or unavailable).
 e55host::Packer* host_packer(e55_ctx* c, int n) {
   if (c->host_threads < 0) {
     cpu_set_t set;
     int hw = static_cast<int>(std::thread::hardware_concurrency());
     if (sched_getaffinity(0, sizeof(set), &set) == 0) hw = CPU_COUNT(&set);   // the cores this process may actually use
-    int t = hw - 2;
+    int t = hw - 1;                                                           // the calling thread packs too while it waits
     if (const char* env = getenv("E55_HOST_THREADS")) t = atoi(env);
-    c->host_threads = std::max(0, std::min(t, 14));
+    c->host_threads = std::max(0, std::min(t, 31));
   }
   if (c->host_threads == 0) return nullptr;
   if (c->packer && e55host::packer_threads(c->packer) != c->host_threads) { e55host::packer_destroy(c->packer); c->packer = nullptr; }
   if (!c->packer) c->packer = e55host::packer_create(c->host_threads);
-  if (c->packer && n > c->h_cap) {
-    cudaFreeHost(c->h_bits); cudaFreeHost(c->h_scale);
-    c->h_bits = nullptr; c->h_scale = nullptr; c->h_cap = 0;
-    int cap = 256;
-    while (cap < n) cap *= 2;
-    const size_t w = static_cast<size_t>(cap) * c->in_planes;
-    if (cudaMallocHost(&c->h_bits, w * sizeof(uint32_t)) != cudaSuccess || cudaMallocHost(&c->h_scale, w * sizeof(float)) != cudaSuccess) {
-      cudaFreeHost(c->h_bits); c->h_bits = nullptr; c->h_scale = nullptr;
-      cudaGetLastError();
-      return nullptr;
-    }
-    c->h_cap = cap;
-  }
+  if (c->packer && ensure_host_staging(c, n) != E55_OK) return nullptr;
   return c->packer;
 }
 
@@ -457,6 +467,8 @@ void e55_destroy(e55_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   e55host::packer_destroy(c->packer);
   cudaFreeHost(c->h_bits); cudaFreeHost(c->h_scale);
+  cudaFreeHost(c->h_out_policy); cudaFreeHost(c->h_out_value);
+  for (cudaEvent_t ev : c->chunk_ev) cudaEventDestroy(ev);
   cudaFreeHost(c->h_req); cudaFreeHost(c->h_ans); cudaFree(c->d_req); cudaFree(c->d_ans);
   free_weights(c);
   free_buffers(c);
@@ -588,22 +600,67 @@ namespace {
 
 constexpr int kPipeChunk = 256;
 
-// Host-buffer predict, compacting pipeline: the planes are bit-packed on the host chunk by chunk (exactly;
-// e55_host.cpp) while earlier chunks are already on the GPU, so 2 128 instead of 26 600 bytes per position cross
-// PCIe.  A chunk that is not exactly representable travels as float planes.  Results equal the float pipeline's.
-// n_float > 0: the last n_float positions are not packed at all but sent as float planes in between the packed
-// chunks -- the copy engine moves them while the cores pack the rest, so both the PCIe link and the host cores
-// are busy for the whole call.
-int predict_compacting(e55_ctx* c, e55host::Packer* packer, const float* planes, int n, int n_float, float* policy, float* value) {
+// True if `p` is page-locked host memory the copy engines can reach directly (cudaHostAlloc / cudaHostRegister).
+bool host_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+// Pinned staging of results for callers whose output buffers are pageable (numpy arrays, malloc).
+int ensure_out_staging(e55_ctx* c, int n) {
+  if (n <= c->h_out_cap) return E55_OK;
+  cudaFreeHost(c->h_out_policy); cudaFreeHost(c->h_out_value);
+  c->h_out_policy = c->h_out_value = nullptr; c->h_out_cap = 0;
+  int cap = 256;
+  while (cap < n) cap *= 2;
+  E55_CUDA(c, cudaMallocHost(&c->h_out_policy, static_cast<size_t>(cap) * kPolicyCh * kSq * sizeof(float)));
+  E55_CUDA(c, cudaMallocHost(&c->h_out_value, static_cast<size_t>(cap) * sizeof(float)));
+  c->h_out_cap = cap;
+  return E55_OK;
+}
+
+void sync_pipe_streams(e55_ctx* c) {
+  for (int i = 0; i < e55_ctx::kPipeStreams; ++i)
+    if (c->pipe_stream[i]) cudaStreamSynchronize(c->pipe_stream[i]);
+  cudaStreamSynchronize(c->stream);
+}
+
+// Host-buffer predict as a pipeline of chunks on rotating side streams: H2D -> tower kernel -> D2H, so that PCIe
+// transfers in both directions overlap each other and the kernels (which run side by side on disjoint SMs).
+//   * The first n - n_float positions are bit-packed on the host chunk by chunk (exactly; e55_host.cpp) while earlier
+//     chunks are already on the GPU, so 2 128 instead of 26 600 bytes per position cross PCIe.  A chunk that is not
+//     exactly representable travels as float planes.
+//   * The last n_float positions are not packed at all but sent as float planes in between the packed chunks -- the
+//     copy engine moves them while the cores pack the rest, so both the PCIe link and the host cores are busy for the
+//     whole call (pinned inputs only: a pageable buffer is read by the cores either way).  n_float == n is the plain
+//     float pipeline.
+//   * Results go straight into the caller's buffers when those are pinned; otherwise into the library's pinned staging,
+//     from where the pool copies each chunk out as soon as its event has fired, while later chunks are still on the GPU.
+// Results are identical whichever way a position travels.
+int predict_host_pipeline(e55_ctx* c, e55host::Packer* packer, const float* planes, int n, int n_float, float* policy, float* value,
+                          bool pol_pinned, bool val_pinned) {
   const int n_pack = n - n_float;
-  e55host::packer_start(packer, planes, n_pack, c->in_planes, c->h_bits, c->h_scale);
-  cudaError_t e = cudaEventRecord(c->pipe_start, c->stream);
   const size_t ip = static_cast<size_t>(c->in_planes), in_pp = ip * kSq, pol_pp = static_cast<size_t>(kPolicyCh) * kSq;
-  int used = 0, rc = E55_OK, chunk = 0;
-  auto send = [&](int off, int m, bool packed) {
+  int rc = E55_OK;
+  if (!(pol_pinned && val_pinned) && (rc = ensure_out_staging(c, n))) return rc;
+  float* out_policy = pol_pinned ? policy : c->h_out_policy;
+  float* out_value = val_pinned ? value : c->h_out_value;
+  if (n_pack > 0) e55host::packer_start(packer, planes, n_pack, c->in_planes, c->h_bits, c->h_scale);
+  cudaError_t e = cudaEventRecord(c->pipe_start, c->stream);
+  struct Sent { int off, m; };
+  std::vector<Sent> sent;
+  int used = 0;
+  auto send = [&](int off, int m, bool packed, bool full_chunk) {
+    const int chunk = static_cast<int>(sent.size());
     cudaStream_t st = c->pipe_stream[chunk % e55_ctx::kPipeStreams];
     if (chunk < e55_ctx::kPipeStreams) { e = cudaStreamWaitEvent(st, c->pipe_start, 0); used = chunk + 1; }
-    ++chunk;
+    while (e == cudaSuccess && static_cast<int>(c->chunk_ev.size()) <= chunk) {
+      cudaEvent_t ev = nullptr;
+      e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+      if (e == cudaSuccess) c->chunk_ev.push_back(ev);
+    }
+    c->tc.throughput_rounds = full_chunk;   // full chunks run side by side on few SMs each; a short tail spreads out
     if (packed) {
       if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_bits + off * ip, c->h_bits + off * ip, m * ip * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
       if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_scale + off * ip, c->h_scale + off * ip, m * ip * sizeof(float), cudaMemcpyHostToDevice, st);
@@ -612,62 +669,55 @@ int predict_compacting(e55_ctx* c, e55host::Packer* packer, const float* planes,
       if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_in + off * in_pp, planes + off * in_pp, m * in_pp * sizeof(float), cudaMemcpyHostToDevice, st);
       if (e == cudaSuccess) rc = forward_tc_on(c, st, c->d_in + off * in_pp, m, c->d_policy + off * pol_pp, c->d_value + off);
     }
-    if (e == cudaSuccess && rc == E55_OK) e = cudaMemcpyAsync(policy + off * pol_pp, c->d_policy + off * pol_pp, m * pol_pp * sizeof(float), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess && rc == E55_OK) e = cudaMemcpyAsync(value + off, c->d_value + off, m * sizeof(float), cudaMemcpyDeviceToHost, st);
+    c->tc.throughput_rounds = false;
+    if (e == cudaSuccess && rc == E55_OK) e = cudaMemcpyAsync(out_policy + off * pol_pp, c->d_policy + off * pol_pp, m * pol_pp * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && rc == E55_OK) e = cudaMemcpyAsync(out_value + off, c->d_value + off, m * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && rc == E55_OK) e = cudaEventRecord(c->chunk_ev[chunk], st);
+    sent.push_back(Sent{off, m});
   };
+  // packed chunks: 256 positions = a one-group-per-CTA kernel of 64 CTAs, two of which run side by side; smaller
+  // batches are cut in two so that the second half is packed while the first is on the GPU
+  const int pack_chunk = n_pack >= 2 * kPipeChunk ? kPipeChunk : std::max(64, ((n_pack / 2 + 63) / 64) * 64);
   constexpr int kFloatChunk = 128;   // 3.4 MB: ~65 us on the link, about what packing the next chunk takes
   int off = 0, foff = n_pack;
   while ((off < n_pack || foff < n) && e == cudaSuccess && rc == E55_OK) {
     // the float share keeps step with the packed share (and goes first: nothing has to be waited for)
     while (foff < n && e == cudaSuccess && rc == E55_OK &&
            (off >= n_pack || static_cast<int64_t>(foff - n_pack) * n_pack <= static_cast<int64_t>(off) * n_float)) {
-      const int m = std::min(kFloatChunk, n - foff);
-      send(foff, m, false);
+      // all floats: full chunks while much is left, then halving chunks, so that what remains after the last byte
+      // has arrived -- one kernel and one read-back -- is short
+      const int m = n_pack == 0 ? pipe_chunk(n - foff, kPipeChunk) : std::min(kFloatChunk, n - foff);
+      send(foff, m, false, m >= kPipeChunk);
       foff += m;
     }
     if (off < n_pack && e == cudaSuccess && rc == E55_OK) {
-      const int m = std::min(kPipeChunk, n_pack - off);   // a one-group-per-CTA kernel of 64 CTAs; two run side by side
-      send(off, m, e55host::packer_wait_range(packer, off, m));
+      const int m = std::min(pack_chunk, n_pack - off);
+      send(off, m, e55host::packer_wait_range(packer, off, m), n_pack >= 2 * kPipeChunk);
       off += m;
+    }
+  }
+  if (n_pack > 0) e55host::packer_finish(packer);   // the pool reads the caller's planes: it must be done before we return, whatever happened
+  if (rc != E55_OK || e != cudaSuccess) {
+    sync_pipe_streams(c);   // nothing of this call may still be in flight when the caller gets its buffers back
+    if (rc != E55_OK) return rc;
+    E55_CUDA(c, e);
+  }
+  if (!(pol_pinned && val_pinned)) {
+    for (size_t k = 0; k < sent.size() && e == cudaSuccess; ++k) {
+      e = cudaEventSynchronize(c->chunk_ev[k]);
+      if (e != cudaSuccess) break;
+      if (!pol_pinned)
+        e55host::packer_parallel_copy(packer, policy + sent[k].off * pol_pp, out_policy + sent[k].off * pol_pp, sent[k].m * pol_pp * sizeof(float));
+      if (!val_pinned) memcpy(value + sent[k].off, out_value + sent[k].off, sent[k].m * sizeof(float));
     }
   }
   for (int i = 0; i < used && e == cudaSuccess; ++i) {
     e = cudaEventRecord(c->pipe_done[i], c->pipe_stream[i]);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(c->stream, c->pipe_done[i], 0);
   }
-  e55host::packer_finish(packer);   // the pool reads the caller's planes: it must be done before we return, whatever happened
-  if (rc != E55_OK) return rc;
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess) sync_pipe_streams(c);
   E55_CUDA(c, e);
-  E55_CUDA(c, cudaStreamSynchronize(c->stream));
-  return E55_OK;
-}
-
-// Host-buffer predict, float pipeline: chunks travel H2D -> kernel -> D2H on rotating side streams, so PCIe
-// transfers in both directions overlap each other and the kernels (which run side by side on disjoint SMs).
-int predict_float_pipeline(e55_ctx* c, const float* planes, int n, float* policy, float* value) {
-  E55_CUDA(c, cudaEventRecord(c->pipe_start, c->stream));
-  const size_t in_pp = static_cast<size_t>(c->in_planes) * kSq, pol_pp = static_cast<size_t>(kPolicyCh) * kSq;
-  int used = 0;
-  for (int off = 0, i = 0; off < n; ++i) {
-    // The H2D copy is the serial resource (26.6 KB per position): full chunks while much is left, then halving
-    // chunks, so that what remains after the last byte has arrived -- one kernel and one read-back -- is short.
-    const int m = pipe_chunk(n - off, kPipeChunk);
-    cudaStream_t st = c->pipe_stream[i % e55_ctx::kPipeStreams];
-    if (i < e55_ctx::kPipeStreams) { E55_CUDA(c, cudaStreamWaitEvent(st, c->pipe_start, 0)); used = i + 1; }
-    E55_CUDA(c, cudaMemcpyAsync(c->d_in + off * in_pp, planes + off * in_pp, m * in_pp * sizeof(float), cudaMemcpyHostToDevice, st));
-    c->tc.throughput_rounds = m >= kPipeChunk;   // full chunks run side by side on few SMs each; the short tail spreads out
-    const int rc = forward_tc_on(c, st, c->d_in + off * in_pp, m, c->d_policy + off * pol_pp, c->d_value + off);
-    c->tc.throughput_rounds = false;
-    if (rc) return rc;
-    E55_CUDA(c, cudaMemcpyAsync(policy + off * pol_pp, c->d_policy + off * pol_pp, m * pol_pp * sizeof(float), cudaMemcpyDeviceToHost, st));
-    E55_CUDA(c, cudaMemcpyAsync(value + off, c->d_value + off, m * sizeof(float), cudaMemcpyDeviceToHost, st));
-    off += m;
-  }
-  for (int i = 0; i < used; ++i) {
-    E55_CUDA(c, cudaEventRecord(c->pipe_done[i], c->pipe_stream[i]));
-    E55_CUDA(c, cudaStreamWaitEvent(c->stream, c->pipe_done[i], 0));
-  }
-  E55_CUDA(c, cudaStreamSynchronize(c->stream));
   return E55_OK;
 }
 
@@ -679,14 +729,17 @@ int e55_predict(e55_ctx* c, const float* planes, int n, float* policy, float* va
   std::lock_guard<std::mutex> lk(c->mu);
   E55_CUDA(c, cudaSetDevice(c->device));
   if ((rc = ensure_capacity(c, n))) return rc;
-  if (c->precision == E55_PRECISION_BF16_TC && !c->timing && n >= 2 * kPipeChunk) {
-    // Large batch on the tensor-core path: the cores pack one part of the batch, the rest travels as floats meanwhile.
-    // Which split is fastest depends on the host (cores and memory bandwidth to spare against the PCIe link), so
-    // unless the caller fixed the thread count the first calls try them all and later ones take the fastest,
-    // looking at its neighbours again now and then.
+  const bool tc_path = c->precision == E55_PRECISION_BF16_TC && !c->timing;
+  if (tc_path && n >= kSmallBatch) {
+    // Larger batch on the tensor-core path: chunks travel as a pipeline.  The cores pack one part of the batch, the rest
+    // travels as floats meanwhile (pinned inputs).  Which split is fastest depends on the host (cores and memory bandwidth
+    // to spare against the PCIe link), so unless the caller fixed the thread count the first calls try them all and later
+    // ones take the fastest, looking at its neighbours again now and then.
+    const bool in_pinned = host_pinned(planes), pol_pinned = host_pinned(policy), val_pinned = host_pinned(value);
     e55host::Packer* packer = host_packer(c, n);
     int level = packer ? 0 : e55_ctx::kSplitLevels - 1;   // index into kSplitEighths: how much of the batch travels as floats
-    if (packer && c->host_auto) {
+    const bool adaptive = packer && c->host_auto && in_pinned && n >= 2 * kPipeChunk;
+    if (adaptive) {
       const int64_t k = c->pipe_calls++;
       int best = 0;
       for (int i = 1; i < e55_ctx::kSplitLevels; ++i)
@@ -695,22 +748,35 @@ int e55_predict(e55_ctx* c, const float* planes, int n, float* policy, float* va
       else if (k % 32 == 0) level = std::max(0, std::min(e55_ctx::kSplitLevels - 1, best + ((k / 32) % 2 ? 1 : -1)));   // ... a neighbour now and then, ...
       else level = best;                                                                                            // ... else the fastest
     }
-    if (const char* env = packer ? getenv("E55_HOST_SPLIT") : nullptr)   // fixed share (eighths of the batch as floats), for measurements
+    if (const char* env = (packer && in_pinned) ? getenv("E55_HOST_SPLIT") : nullptr)   // fixed share (eighths of the batch as floats), for measurements
       for (int i = 0; i < e55_ctx::kSplitLevels; ++i)
         if (e55_ctx::kSplitEighths[i] == atoi(env)) level = i;
     const int eighths = e55_ctx::kSplitEighths[level];
     const int n_float = eighths >= 8 ? n : (n / 8 * eighths) / 64 * 64;
     const auto t0 = std::chrono::steady_clock::now();
-    rc = n_float >= n ? predict_float_pipeline(c, planes, n, policy, value) : predict_compacting(c, packer, planes, n, n_float, policy, value);
-    const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / n;
-    double& avg = c->split_us[level];
-    avg = c->split_samples[level]++ < 2 ? us : 0.75 * avg + 0.25 * us;   // (the first call of a kind also pays for its set-up)
-    c->split_level = level;
+    rc = predict_host_pipeline(c, packer, planes, n, n_float, policy, value, pol_pinned, val_pinned);
+    if (adaptive) {
+      const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / n;
+      double& avg = c->split_us[level];
+      avg = c->split_samples[level]++ < 2 ? us : 0.75 * avg + 0.25 * us;   // (the first call of a kind also pays for its set-up)
+      c->split_level = level;
+    }
     return rc;
   }
-  const size_t in_bytes = static_cast<size_t>(n) * c->in_planes * kSq * sizeof(float);
-  E55_CUDA(c, cudaMemcpyAsync(c->d_in, planes, in_bytes, cudaMemcpyHostToDevice, c->stream));
-  if ((rc = forward(c, c->d_in, n, c->d_policy, c->d_value))) return rc;
+  // Small batch (the reference's own: root 1, leaves 16; mcts.py:57-58,101-102): one copy in, one kernel, one copy out.
+  // A pageable input is bit-packed by the calling thread into pinned staging on the way (2 KB instead of 26 KB per
+  // position for the copy engine, and no driver-side staging copy); anything not exactly representable goes as floats.
+  if (tc_path && c->host_threads != 0 && !host_pinned(planes) && ensure_host_staging(c, n) == E55_OK &&
+      e55host::pack_planes_inline(planes, n, c->in_planes, c->h_bits, c->h_scale)) {
+    const size_t w = static_cast<size_t>(n) * c->in_planes;
+    E55_CUDA(c, cudaMemcpyAsync(c->d_bits, c->h_bits, w * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    E55_CUDA(c, cudaMemcpyAsync(c->d_scale, c->h_scale, w * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    if ((rc = forward_packed_on(c, c->stream, c->d_bits, c->d_scale, n, 0, c->d_policy, c->d_value))) return rc;
+  } else {
+    const size_t in_bytes = static_cast<size_t>(n) * c->in_planes * kSq * sizeof(float);
+    E55_CUDA(c, cudaMemcpyAsync(c->d_in, planes, in_bytes, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = forward(c, c->d_in, n, c->d_policy, c->d_value))) return rc;
+  }
   E55_CUDA(c, cudaMemcpyAsync(policy, c->d_policy, static_cast<size_t>(n) * kPolicyCh * kSq * sizeof(float),
                               cudaMemcpyDeviceToHost, c->stream));
   E55_CUDA(c, cudaMemcpyAsync(value, c->d_value, static_cast<size_t>(n) * sizeof(float), cudaMemcpyDeviceToHost,
@@ -848,6 +914,18 @@ int e55_predict_masked(e55_ctx* c, const float* planes, const uint8_t* mask, int
   E55_CUDA(c, cudaMemcpyAsync(value, c->d_value, static_cast<size_t>(n) * sizeof(float), cudaMemcpyDeviceToHost,
                               c->stream));
   E55_CUDA(c, cudaStreamSynchronize(c->stream));
+  return E55_OK;
+}
+
+int e55_host_alloc(size_t bytes, void** out) {
+  if (!out || bytes == 0) return fail(nullptr, E55_ERR_INVALID, "bad host allocation request");
+  *out = nullptr;
+  E55_CUDA(nullptr, cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+  return E55_OK;
+}
+
+int e55_host_free(void* p) {
+  if (p) E55_CUDA(nullptr, cudaFreeHost(p));
   return E55_OK;
 }
 

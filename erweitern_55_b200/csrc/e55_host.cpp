@@ -4,15 +4,18 @@
 // 27 MB host->device copy that bounds the float path at batch 1024 shrinks 12.5x.  Exact by construction: a plane is
 // packed only if all its non-zero entries hold one and the same value (occupancy, repetition, hand-count, colour and
 // ply planes all do); anything else is reported and the caller sends that chunk as plain float planes.
-// Host-only translation unit (g++, AVX2).
+// The same pool copies results out of the library's pinned staging into pageable caller buffers (parallel_copy).
+// Host-only translation unit (g++): AVX2 baseline, AVX-512 kernels chosen at run time where the CPU has them.
 #include "e55_host.h"
 
 #include <immintrin.h>
+#include <pthread.h>
+#include <sched.h>
 
 #include <atomic>
-#include <condition_variable>
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
-#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -40,7 +43,7 @@ inline bool pack_plane(const float* q, uint32_t& bits, float& value) {
   return uniform(v0) == 0xFF && uniform(v1) == 0xFF && uniform(v2) == 0xFF && (uniform(v3) & 0x80);
 }
 
-bool pack_positions(const float* planes, int first, int count, int in_planes, uint32_t* bits, float* scale) {
+bool pack_positions_avx2(const float* planes, int first, int count, int in_planes, uint32_t* bits, float* scale) {
   bool exact = true;
   for (int p = first; p < first + count; ++p) {
     const float* src = planes + static_cast<size_t>(p) * in_planes * kSq;
@@ -51,38 +54,109 @@ bool pack_positions(const float* planes, int first, int count, int in_planes, ui
   return exact;
 }
 
+// AVX-512: a plane is one full and one 9-lane masked load, the occupancy word is the two compare masks, and the
+// uniformity test is one more compare per half -- branch-free, so the loop runs at the rate the planes stream in.
+__attribute__((target("avx512f,avx512vl,avx512bw,avx512dq")))
+bool pack_positions_avx512(const float* planes, int first, int count, int in_planes, uint32_t* bits, float* scale) {
+  const __m512 zero = _mm512_setzero_ps();
+  uint32_t bad = 0;
+  const size_t total = static_cast<size_t>(count) * in_planes;
+  const float* src = planes + static_cast<size_t>(first) * in_planes * kSq;
+  uint32_t* b = bits + static_cast<size_t>(first) * in_planes;
+  float* s = scale + static_cast<size_t>(first) * in_planes;
+  for (size_t c = 0; c < total; ++c) {
+    const float* q = src + c * kSq;
+    _mm_prefetch(reinterpret_cast<const char*>(q + 512), _MM_HINT_T0);
+    const __m512 lo = _mm512_loadu_ps(q);
+    const __m512 hi = _mm512_maskz_loadu_ps(0x1FF, q + 16);
+    const uint32_t k0 = _mm512_cmp_ps_mask(lo, zero, _CMP_NEQ_UQ), k1 = _mm512_cmp_ps_mask(hi, zero, _CMP_NEQ_UQ);
+    const uint32_t w = k0 | (k1 << 16);
+    float v = q[w ? __builtin_ctz(w) : 0];
+    v = w ? v : 1.f;
+    const __m512 sv = _mm512_set1_ps(v);
+    const uint32_t e0 = _mm512_cmp_ps_mask(lo, sv, _CMP_EQ_OQ), e1 = _mm512_cmp_ps_mask(hi, sv, _CMP_EQ_OQ);
+    bad |= (k0 & ~e0) | (k1 & ~e1);   // a non-zero entry that is not the value (NaN included)
+    b[c] = w;
+    s[c] = v;
+  }
+  return bad == 0;
+}
+
+using PackFn = bool (*)(const float*, int, int, int, uint32_t*, float*);
+
+PackFn choose_pack() {
+  const char* env = getenv("E55_HOST_ISA");
+  if (env && !strcmp(env, "avx2")) return pack_positions_avx2;
+  __builtin_cpu_init();
+  if (__builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512vl") && __builtin_cpu_supports("avx512bw") &&
+      __builtin_cpu_supports("avx512dq"))
+    return pack_positions_avx512;
+  return pack_positions_avx2;
+}
+
+const PackFn g_pack = choose_pack();
+
+inline bool pack_positions(const float* planes, int first, int count, int in_planes, uint32_t* bits, float* scale) {
+  return g_pack(planes, first, count, in_planes, bits, scale);
+}
+
 }  // namespace
 
 struct Packer {
   static constexpr int kBlock = 8;   // positions per work item
+  static constexpr size_t kCopyBlock = 128 << 10;   // bytes per copy work item
+  static constexpr int kSpinUs = 400;               // how long an idle worker polls before it sleeps
   std::vector<std::thread> threads;
-  std::mutex m;
-  std::condition_variable cv;
-  std::atomic<uint64_t> generation{0};
-  bool stop = false;
-  // the current job
+  std::atomic<uint32_t> generation{0};   // bumped per job; sleeping workers wait on it (a futex: no mutex hand-over on wake-up)
+  std::atomic<bool> stop{false};
+  // the current job: pack (planes != null) or copy (copy_src != null)
   const float* planes = nullptr;
   uint32_t* bits = nullptr;
   float* scale = nullptr;
   int n = 0, in_planes = 0, n_blocks = 0;
+  const uint8_t* copy_src = nullptr;
+  uint8_t* copy_dst = nullptr;
+  size_t copy_bytes = 0;
   std::atomic<int> next{0};
   std::atomic<int> idle{0};                       // workers that have left the current job
   std::vector<std::atomic<uint8_t>> block_state;  // 0 pending, 1 packed exactly, 2 not representable
 
   explicit Packer(int n_threads) : block_state(0) {
-    for (int i = 0; i < n_threads; ++i) threads.emplace_back([this] { work(); });
+    // Workers sit on the cores this process may use, one each, after the first (left to the calling thread): several
+    // ranks on one box each own a block of cores (bench.py / the launcher set the affinity), and a worker that
+    // migrates drags its share of the planes through another core's cache.
+    std::vector<int> cpus;
+    cpu_set_t set;
+    const char* pin = getenv("E55_PIN_THREADS");
+    if (!(pin && !strcmp(pin, "0")) && sched_getaffinity(0, sizeof(set), &set) == 0)
+      for (int c = 0; c < CPU_SETSIZE; ++c)
+        if (CPU_ISSET(c, &set)) cpus.push_back(c);
+    for (int i = 0; i < n_threads; ++i) {
+      threads.emplace_back([this] { work(); });
+      if (static_cast<int>(cpus.size()) > n_threads) {
+        cpu_set_t one;
+        CPU_ZERO(&one);
+        CPU_SET(cpus[1 + i], &one);
+        pthread_setaffinity_np(threads.back().native_handle(), sizeof(one), &one);
+      }
+    }
   }
   ~Packer() {
-    {
-      std::lock_guard<std::mutex> lk(m);
-      stop = true;
-      generation.fetch_add(1, std::memory_order_release);
-    }
-    cv.notify_all();
+    stop.store(true, std::memory_order_release);
+    generation.fetch_add(1, std::memory_order_release);
+    generation.notify_all();
     for (auto& t : threads) t.join();
   }
 
   void run_blocks() {
+    if (copy_src) {
+      for (;;) {
+        const int b = next.fetch_add(1, std::memory_order_relaxed);
+        if (b >= n_blocks) return;
+        const size_t o = static_cast<size_t>(b) * kCopyBlock;
+        memcpy(copy_dst + o, copy_src + o, std::min(kCopyBlock, copy_bytes - o));
+      }
+    }
     for (;;) {
       const int b = next.fetch_add(1, std::memory_order_relaxed);
       if (b >= n_blocks) return;
@@ -93,35 +167,41 @@ struct Packer {
   }
 
   void work() {
-    uint64_t seen = 0;
+    uint32_t seen = 0;
     for (;;) {
-      // spin a little for back-to-back calls, then sleep
-      uint64_t g = generation.load(std::memory_order_acquire);
-      for (int spin = 0; g == seen && spin < 2000; ++spin) { _mm_pause(); g = generation.load(std::memory_order_acquire); }
-      if (g == seen) {
-        std::unique_lock<std::mutex> lk(m);
-        cv.wait(lk, [&] { return generation.load(std::memory_order_acquire) != seen; });
+      // spin for a while (back-to-back calls of a search loop find the pool awake), then sleep on the counter
+      uint32_t g = generation.load(std::memory_order_acquire);
+      const auto t0 = std::chrono::steady_clock::now();
+      for (int spin = 0; g == seen; ++spin) {
+        _mm_pause();
+        g = generation.load(std::memory_order_acquire);
+        if ((spin & 255) == 255 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(kSpinUs)) break;
+      }
+      while (g == seen) {
+        generation.wait(seen, std::memory_order_acquire);
         g = generation.load(std::memory_order_acquire);
       }
       seen = g;
-      if (stop) return;
+      if (stop.load(std::memory_order_acquire)) return;
       run_blocks();
       idle.fetch_add(1, std::memory_order_release);
     }
   }
 
+  void publish() {
+    next.store(0, std::memory_order_relaxed);
+    idle.store(0, std::memory_order_relaxed);
+    generation.fetch_add(1, std::memory_order_release);
+    generation.notify_all();
+  }
+
   void start(const float* planes_, int n_, int in_planes_, uint32_t* bits_, float* scale_) {
+    copy_src = nullptr;
     planes = planes_; n = n_; in_planes = in_planes_; bits = bits_; scale = scale_;
     n_blocks = (n + kBlock - 1) / kBlock;
     if (static_cast<int>(block_state.size()) < n_blocks) block_state = std::vector<std::atomic<uint8_t>>(n_blocks);
     for (int b = 0; b < n_blocks; ++b) block_state[b].store(0, std::memory_order_relaxed);
-    next.store(0, std::memory_order_relaxed);
-    idle.store(0, std::memory_order_relaxed);
-    {
-      std::lock_guard<std::mutex> lk(m);
-      generation.fetch_add(1, std::memory_order_release);
-    }
-    cv.notify_all();
+    publish();
   }
 
   // Wait until positions [first, first + count) are packed; true if all of them were representable.
@@ -148,6 +228,17 @@ struct Packer {
     run_blocks();   // nothing left normally; covers a pool whose threads have not woken up yet
     while (idle.load(std::memory_order_acquire) < static_cast<int>(threads.size())) _mm_pause();
   }
+
+  // memcpy shared by the pool and the calling thread; returns when every byte is in place.
+  void parallel_copy(void* dst, const void* src, size_t bytes) {
+    if (bytes <= 2 * kCopyBlock) { memcpy(dst, src, bytes); return; }
+    planes = nullptr;
+    copy_src = static_cast<const uint8_t*>(src); copy_dst = static_cast<uint8_t*>(dst); copy_bytes = bytes;
+    n_blocks = static_cast<int>((bytes + kCopyBlock - 1) / kCopyBlock);
+    publish();
+    finish();
+    copy_src = nullptr;
+  }
 };
 
 Packer* packer_create(int threads) { return threads > 0 ? new (std::nothrow) Packer(threads) : nullptr; }
@@ -158,8 +249,12 @@ void packer_start(Packer* p, const float* planes, int n, int in_planes, uint32_t
 }
 bool packer_wait_range(Packer* p, int first, int count) { return p->wait_range(first, count); }
 void packer_finish(Packer* p) { p->finish(); }
+void packer_parallel_copy(Packer* p, void* dst, const void* src, size_t bytes) {
+  if (p) p->parallel_copy(dst, src, bytes); else memcpy(dst, src, bytes);
+}
 bool pack_planes_inline(const float* planes, int n, int in_planes, uint32_t* bits, float* scale) {
   return pack_positions(planes, 0, n, in_planes, bits, scale);
 }
+const char* pack_isa() { return g_pack == pack_positions_avx512 ? "avx512" : "avx2"; }
 
 }  // namespace e55host

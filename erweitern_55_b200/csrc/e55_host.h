@@ -1,5 +1,6 @@
 // Host-side helpers of libe55.so that are plain C++ (compiled by g++, see e55_host.cpp).
 #pragma once
+#include <cstddef>
 #include <cstdint>
 
 namespace e55host {
@@ -16,6 +17,10 @@ void packer_start(Packer* p, const float* planes, int n, int in_planes, uint32_t
 bool packer_wait_range(Packer* p, int first, int count);
 // Block until every worker has left the job started last.
 void packer_finish(Packer* p);
+// memcpy shared by the pool's threads and the caller (no pack job may be running); p may be null (plain memcpy).
+void packer_parallel_copy(Packer* p, void* dst, const void* src, size_t bytes);
+// "avx512" or "avx2": the packing kernel chosen for this CPU (E55_HOST_ISA=avx2 forces the baseline).
+const char* pack_isa();
 // Same packing on the calling thread.
 bool pack_planes_inline(const float* planes, int n, int in_planes, uint32_t* bits, float* scale);
 

@@ -14,7 +14,7 @@ import ctypes as C
 
 import numpy as np
 
-from . import _capi
+from . import _capi, hostmem
 from .weights import IN_PLANES, POLICY_SIZE, infer_arch, init_weights, weight_spec
 
 _PRECISIONS = {"fp32": _capi.PRECISION_FP32, "bf16": _capi.PRECISION_BF16_TC}
@@ -179,7 +179,9 @@ class Network:
         return ins
 
     def zero_inputs(self, batch_size):
-        return np.zeros([batch_size] + self.input_shape, dtype="float32")
+        ins = hostmem.empty([batch_size] + self.input_shape)   # page-locked when large: predict() can split it between cores and copy engine
+        ins.fill(0)
+        return ins
 
     # ---- evaluation (network.py:201-216) --------------------------------------------------------
     def _as_batch(self, images):
@@ -195,7 +197,7 @@ class Network:
         While the aggregation service runs (:meth:`start_service`) calls from many threads are coalesced."""
         x = self._as_batch(images)
         n = x.shape[0]
-        policy = np.empty((n, POLICY_SIZE), dtype=np.float32)
+        policy = hostmem.empty((n, POLICY_SIZE))        # page-locked from 38 positions up: the copy engine writes into it
         value = np.empty((n, 1), dtype=np.float32)
         fn = self._lib.e55_service_predict if (self._service_cap and n <= self._service_cap) else self._lib.e55_predict
         self._check(fn(self._ctx, x.ctypes.data, n, policy.ctypes.data, value.ctypes.data))

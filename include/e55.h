@@ -18,6 +18,7 @@
 #ifndef E55_H_
 #define E55_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -68,13 +69,15 @@ int e55_get_precision(const e55_ctx* ctx, int* precision);
 /* Replaces Network.predict (network.py:201-216) for HOST buffers: planes float32 [n,in_planes,5,5]
  * (NCHW) -> policy float32 [n,1725] raw logits (index c*25+y*5+x), value float32 [n,1] (tanh).
  * The whole input is one batch.  Includes H2D and D2H copies; returns after the outputs are in the
- * caller's buffers.  Batches of 256 and more are pipelined in chunks (host-side bit-packing of the planes by a
- * small thread pool -> copy -> kernel -> read-back overlap across chunks; see e55_set_host_threads). */
+ * caller's buffers, which may be pinned (e55_host_alloc, cudaHostAlloc) or ordinary pageable memory.  Batches of 64 and
+ * more are pipelined in chunks (host-side bit-packing of the planes by a small thread pool -> copy -> kernel ->
+ * read-back -> copy-out overlap across chunks; see e55_set_host_threads); smaller ones are one copy in, one kernel,
+ * one copy out, a pageable input being bit-packed by the calling thread on the way. */
 int e55_predict(e55_ctx* ctx, const float* planes, int n, float* policy, float* value);
 
 /* Host threads e55_predict may use to bit-pack large float-plane batches before the copy (exact: a chunk whose
  * planes are not "one value or zero" travels as floats; results are identical either way).  -1 (default) = the
- * library's choice: cores - 2 threads (at most 14; E55_HOST_THREADS overrides), and during the first calls it
+ * library's choice: cores - 1 threads, pinned to the process's cores (at most 31; E55_HOST_THREADS overrides), and during the first calls it
  * measures how much of the batch to pack and how much to send as floats meanwhile (e55_get_host_split) and keeps
  * the fastest; n > 0 = always pack with n threads; 0 = off: the planes cross PCIe as they
  * are. */
@@ -84,9 +87,17 @@ int e55_set_host_threads(e55_ctx* ctx, int threads);
 int e55_get_host_pipeline(e55_ctx* ctx, int* threads_out, double* compact_us_out, double* float_us_out);
 /* The compacting pipeline may leave a share of a large batch unpacked and send it as float planes in between the
  * packed chunks (link and cores both busy).  float_eighths_out: that share, in eighths of the batch, at the latest
- * large call (0 = all packed, 8 = the float pipeline); us_per_position_out (6 doubles, may be null): the running
- * mean at the shares 0, 1, 2, 3, 4 and 8 eighths (0 = not tried). */
+ * large call (0 = all packed, 8 = the float pipeline); us_per_position_out (8 doubles, may be null): the running
+ * mean at the shares 0, 1, 2, 3, 4, 5, 6 and 8 eighths (0 = not tried).  Pageable inputs are always packed whole (the
+ * cores have to read them either way). */
 int e55_get_host_split(e55_ctx* ctx, int* float_eighths_out, double* us_per_position_out);
+
+/* Page-locked host memory for the arrays handed to the host-buffer calls (any thread, any device: portable).  Buffers
+ * from here are read and written by the copy engines directly: no staging copy on either side of e55_predict.
+ * Network.predict (erweitern_55_b200/network.py) returns its numpy results in such blocks and recycles them when the
+ * arrays are garbage-collected.  Ordinary (pageable) buffers work everywhere too: the library stages them itself. */
+int e55_host_alloc(size_t bytes, void** out);
+int e55_host_free(void* p);
 
 /* Same computation on DEVICE buffers, enqueued on the context stream; returns without
  * synchronising (call e55_sync).  Buffers must stay valid until then. */

@@ -469,16 +469,27 @@ def test_host_side_packing_is_invisible(weights_perturbed):
     lib.e55_set_host_threads(net._ctx, 0)
     p0, v0 = net.predict(x)
     import ctypes as C
-    for threads in (1, 4, -1):
-        lib.e55_set_host_threads(net._ctx, threads)
-        shares = set()
-        for _ in range(14 if threads < 0 else 2):                      # the automatic mode tries every split of the batch
-            p1, v1 = net.predict(x)                                    # between packed chunks and float chunks first
-            assert np.array_equal(p0, p1) and np.array_equal(v0, v1)
-            eighths = C.c_int()
-            assert lib.e55_get_host_split(net._ctx, C.byref(eighths), None) == 0
-            shares.add(eighths.value)
-        assert shares == ({0, 1, 2, 3, 4, 8} if threads < 0 else {0})
+    from erweitern_55_b200 import hostmem
+    xp = hostmem.empty(x.shape)                                        # page-locked copy of the same planes: the copy engine
+    xp[...] = x                                                        # may take a share of them as floats
+    for planes, pinned in ((x, False), (xp, True)):
+        for threads in (1, 4, -1):
+            lib.e55_set_host_threads(net._ctx, threads)
+            shares = set()
+            for _ in range(18 if threads < 0 else 2):                  # the automatic mode tries every split of the batch
+                p1, v1 = net.predict(planes)                           # between packed chunks and float chunks first
+                assert np.array_equal(p0, p1) and np.array_equal(v0, v1)
+                eighths = C.c_int()
+                assert lib.e55_get_host_split(net._ctx, C.byref(eighths), None) == 0
+                shares.add(eighths.value)
+            assert shares == ({0, 1, 2, 3, 4, 5, 6, 8} if threads < 0 and pinned else {0})
+    # results land in the caller's arrays whatever memory those are: page-locked (Network.predict's own), pageable numpy
+    lib.e55_set_host_threads(net._ctx, -1)
+    for n in (64, 100, 300, 511, 1000):
+        for planes in (x[:n], xp[:n]):
+            pol, val = np.full((n, 1725), np.nan, dtype=np.float32), np.full((n, 1), np.nan, dtype=np.float32)
+            net._check(lib.e55_predict(net._ctx, planes.ctypes.data, n, pol.ctypes.data, val.ctypes.data))
+            assert np.array_equal(pol, p0[:n]) and np.array_equal(val, v0[:n])
     y = x.copy()
     y[300, 5, 2, 2], y[300, 5, 3, 3] = 0.25, 0.75                      # two different non-zero values in one plane
     y[999, 265] = np.linspace(0.0, 1.0, 25, dtype=np.float32).reshape(5, 5)

@@ -1,28 +1,52 @@
-"""Host-buffer predict throughput at batch 1024 (the bench's e2e) and the PCIe copy rates that bound it."""
-import sys, time
+"""The drop-in call itself -- Network.predict(numpy) -> numpy -- at the reference's batch sizes and at batch 1024, with
+pageable and with page-locked input arrays, plus the raw copy rates that bound it."""
+import ctypes as C
+import os
+import sys
+import time
+
 sys.path.insert(0, ".")
-import numpy as np, torch
-from erweitern_55_b200 import synth, weights as W, packing
+import numpy as np
+import torch
+
+from erweitern_55_b200 import hostmem, synth, weights as W
 from erweitern_55_b200.network import Network
-B = 1024
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 net = Network(precision="bf16", weights=W.init_weights(seed=55), max_batch=B)
-x = torch.from_numpy(synth.synthetic_planes(B, seed=1)).pin_memory()
-pol = torch.empty((B, 1725), dtype=torch.float32).pin_memory(); val = torch.empty((B, 1), dtype=torch.float32).pin_memory()
-d = torch.empty_like(x, device="cuda"); dp = torch.empty((B, 1725), device="cuda")
-def t(fn, n=30):
-    fn(); torch.cuda.synchronize(); t0 = time.perf_counter()
-    for _ in range(n): fn()
-    torch.cuda.synchronize(); return (time.perf_counter() - t0) / n
-h2d = t(lambda: d.copy_(x, non_blocking=True)); d2h = t(lambda: pol.copy_(dp, non_blocking=True))
-print(f"H2D {x.numel()*4/h2d/1e9:.1f} GB/s ({h2d*1e6:.0f} us for {x.numel()*4/1e6:.1f} MB); D2H {pol.numel()*4/d2h/1e9:.1f} GB/s ({d2h*1e6:.0f} us)")
 lib, ctx = net._lib, net._ctx
-e = t(lambda: lib.e55_predict(ctx, x.data_ptr(), B, pol.data_ptr(), val.data_ptr()), 50)
-print(f"e55_predict (fp32 planes): {e*1e6:.0f} us/step = {B/e/1e6:.2f} M evals/s")
-bits, scale = packing.pack_planes(x.numpy())
-bt = torch.from_numpy(bits.astype(np.int32)).pin_memory(); st = torch.from_numpy(scale).pin_memory()
-e = t(lambda: lib.e55_predict_packed(ctx, bt.data_ptr(), st.data_ptr(), B, pol.data_ptr(), val.data_ptr()), 50)
-print(f"e55_predict_packed: {e*1e6:.0f} us/step = {B/e/1e6:.2f} M evals/s")
-for threads in (0, 4, 8, 12, 14, 16):
-    lib.e55_set_host_threads(ctx, threads)
-    e = t(lambda: lib.e55_predict(ctx, x.data_ptr(), B, pol.data_ptr(), val.data_ptr()), 50)
-    print(f"e55_predict, {threads:2d} packing threads: {e*1e6:.0f} us/step = {B/e/1e6:.2f} M evals/s")
+print("cores", len(os.sched_getaffinity(0)))
+
+
+def t(fn, n):
+    for i in range(3):
+        fn(i)
+    t0 = time.perf_counter()
+    for i in range(n):
+        fn(i)
+    return (time.perf_counter() - t0) / n
+
+
+for nb in (1, 16, 64, 256, 1024, 1184):
+    xs = [synth.synthetic_planes(nb, seed=10 + i) for i in range(3)]
+    xp = []
+    for a in xs:
+        b = hostmem.empty(a.shape); b[...] = a; xp.append(b)
+    reps = 300 if nb <= 64 else 40
+    for name, arrs in (("pageable", xs), ("pinned", xp)):
+        lib.e55_set_host_threads(ctx, -1)
+        for i in range(20):
+            net.predict(arrs[i % 3])
+        c = t(lambda i: net.predict(arrs[i % 3]), reps)
+        extra = ""
+        if nb >= 512 and name == "pinned":
+            us = (C.c_double * 8)(); e8 = C.c_int()
+            lib.e55_get_host_split(ctx, C.byref(e8), us)
+            extra = " split us/pos " + " ".join(f"{s}:{u:.3f}" for s, u in zip((0, 1, 2, 3, 4, 5, 6, 8), us))
+        print(f"Network.predict batch {nb:5d} {name:8s} input: {c * 1e6:7.0f} us/call = {nb / c / 1e6:.3f} M evals/s{extra}", flush=True)
+    if nb >= 256:
+        for threads in (0, 3, 7, 15):
+            lib.e55_set_host_threads(ctx, threads)
+            c = t(lambda i: net.predict(xs[i % 3]), reps)
+            print(f"   pageable, {threads:2d} pool threads: {c * 1e6:7.0f} us/call = {nb / c / 1e6:.3f} M evals/s", flush=True)
+net.close()
