@@ -32,6 +32,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+import erweitern_55_b200  # noqa: E402,F401  (sets CUDA_DEVICE_MAX_CONNECTIONS before torch creates the CUDA context)
 
 METRIC = "policy+value evals/sec (batch 1024)"
 UNIT = "evals/s"

@@ -49,6 +49,7 @@ SIGNATURES = {
     "e55_stream": (C.c_int, [_ctx, C.POINTER(C.c_void_p)]),
     "e55_launch_count": (C.c_int, [_ctx, C.POINTER(C.c_int64)]),
     "e55_debug_activations": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "e55_debug_legal_priors": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "e55_set_kernel_timing": (C.c_int, [_ctx, C.c_int]),
     "e55_get_kernel_timing": (C.c_int, [_ctx, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "e55_debug_set_lag": (C.c_int, [_ctx, C.c_int]),

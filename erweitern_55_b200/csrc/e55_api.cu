@@ -99,12 +99,15 @@ struct e55_ctx {
   int split_samples[kSplitLevels] = {};
   int split_level = 0;                       // the split of the latest large call
   e55host::Packer* packer = nullptr;
-  uint32_t* h_bits = nullptr;      // pinned [h_cap][in_planes]
-  float* h_scale = nullptr;
+  uint32_t* h_pack = nullptr;      // pinned [h_cap][bits in_planes | scale in_planes]: one copy per chunk takes both
+  uint32_t* d_pack = nullptr;      // its device twin [d_pack_cap][2 * in_planes]
+  int d_pack_cap = 0;
   int h_cap = 0;
-  float* h_out_policy = nullptr;   // pinned staging of results for pageable caller buffers: [h_out_cap][1725], [h_out_cap]
-  float* h_out_value = nullptr;
+  float* h_out_policy = nullptr;   // pinned staging of logits for pageable caller buffers: [h_out_cap][1725]
   int h_out_cap = 0;
+  float* h_out_value = nullptr;    // pinned, device-mapped staging of values: the kernel writes them here directly
+  void* d_out_value_mapped = nullptr;
+  int h_out_value_cap = 0;
   std::vector<cudaEvent_t> chunk_ev;   // one per chunk of the host-buffer pipeline (grown on demand)
   // e55_predict_packed_moves: one pinned request block and one answer block per call, and their device twins
   uint8_t *h_req = nullptr, *h_ans = nullptr, *d_req = nullptr, *d_ans = nullptr;
@@ -313,11 +316,12 @@ int collect_timing(e55_ctx* c) {
   return E55_OK;
 }
 
-int forward_tc_on(e55_ctx* c, cudaStream_t stream, const float* d_planes, int n, float* d_policy, float* d_value) {
+int forward_tc_on(e55_ctx* c, cudaStream_t stream, const float* d_planes, int n, float* d_policy, float* d_value,
+                  e55::tc::PolicyTail tail = e55::tc::PolicyTail()) {
   std::string why;
   int launched = 0;
   c->tc.ev0 = c->tc.ev1 = nullptr;
-  cudaError_t e = e55::tc::forward(c->tc, d_planes, n, d_policy, d_value, stream, &launched, &why);
+  cudaError_t e = e55::tc::forward(c->tc, d_planes, n, d_policy, d_value, stream, &launched, &why, tail);
   c->launches += launched;
   if (e != cudaSuccess) return fail(c, E55_ERR_CUDA, "tensor-core forward: " + why + ": " + cudaGetErrorString(e));
   if (!why.empty()) return fail(c, E55_ERR_UNSUPPORTED, why);
@@ -346,8 +350,9 @@ int forward(e55_ctx* c, const float* d_planes, int n, float* d_policy, float* d_
 // Forward from packed device input on `stream`: the tcgen05 kernel expands the bits itself; the fp32 path
 // expands them into the context's plane buffer first (main stream only).
 int forward_packed_on(e55_ctx* c, cudaStream_t stream, const uint32_t* d_bits, const float* d_scale, int n, int plane_off,
-                      float* d_policy, float* d_value) {
+                      float* d_policy, float* d_value, int stride = 0, e55::tc::PolicyTail tail = e55::tc::PolicyTail()) {
   if (c->precision == E55_PRECISION_FP32) {
+    if (stride || tail.priors || tail.probs) return fail(c, E55_ERR_UNSUPPORTED, "interleaved packed input and the fused policy tail belong to the tensor-core path");
     const size_t total = static_cast<size_t>(n) * c->in_planes * kSq;
     float* planes = c->d_in + static_cast<size_t>(plane_off) * c->in_planes * kSq;
     e55::fp32::unpack_planes_kernel<<<static_cast<unsigned>(std::min<size_t>((total + 255) / 256, 4096)), 256, 0, stream>>>(
@@ -359,7 +364,7 @@ int forward_packed_on(e55_ctx* c, cudaStream_t stream, const uint32_t* d_bits, c
   std::string why;
   int launched = 0;
   c->tc.ev0 = c->tc.ev1 = nullptr;
-  cudaError_t e = e55::tc::forward_packed(c->tc, d_bits, d_scale, n, d_policy, d_value, stream, &launched, &why);
+  cudaError_t e = e55::tc::forward_packed(c->tc, d_bits, d_scale, n, d_policy, d_value, stream, &launched, &why, stride, tail);
   c->launches += launched;
   if (e != cudaSuccess) return fail(c, E55_ERR_CUDA, "tensor-core forward: " + why + ": " + cudaGetErrorString(e));
   if (!why.empty()) return fail(c, E55_ERR_UNSUPPORTED, why);
@@ -373,21 +378,30 @@ int pipe_chunk(int left, int chunk) {
   return half >= left ? left : half;
 }
 
+void sync_pipe_streams(e55_ctx* c) {
+  for (int i = 0; i < e55_ctx::kPipeStreams; ++i)
+    if (c->pipe_stream[i]) cudaStreamSynchronize(c->pipe_stream[i]);
+  cudaStreamSynchronize(c->stream);
+}
+
 constexpr int kSmallBatch = 64;   // below this a host-buffer predict is one copy in, one kernel, one copy out
 
-// Pinned staging of the packed form of `n` positions.
+// Pinned staging of the packed form of `n` positions, and its device twin.
 int ensure_host_staging(e55_ctx* c, int n) {
-  if (n <= c->h_cap) return E55_OK;
-  cudaFreeHost(c->h_bits); cudaFreeHost(c->h_scale);
-  c->h_bits = nullptr; c->h_scale = nullptr; c->h_cap = 0;
+  if (n <= c->h_cap && n <= c->d_pack_cap) return E55_OK;
+  sync_pipe_streams(c);
+  cudaFreeHost(c->h_pack); cudaFree(c->d_pack);
+  c->h_pack = nullptr; c->d_pack = nullptr; c->h_cap = 0; c->d_pack_cap = 0;
   int cap = 256;
   while (cap < n) cap *= 2;
-  const size_t w = static_cast<size_t>(cap) * c->in_planes;
-  if (cudaMallocHost(&c->h_bits, w * sizeof(uint32_t)) != cudaSuccess || cudaMallocHost(&c->h_scale, w * sizeof(float)) != cudaSuccess) {
-    cudaFreeHost(c->h_bits); c->h_bits = nullptr; c->h_scale = nullptr;
-    return fail(c, E55_ERR_CUDA, std::string("pinned staging: ") + cudaGetErrorString(cudaGetLastError()));
+  const size_t bytes = static_cast<size_t>(cap) * 2 * c->in_planes * sizeof(uint32_t);
+  if (cudaMallocHost(&c->h_pack, bytes) != cudaSuccess || cudaMalloc(&c->d_pack, bytes) != cudaSuccess) {
+    const std::string msg = std::string("packed staging: ") + cudaGetErrorString(cudaGetLastError());
+    cudaFreeHost(c->h_pack); cudaFree(c->d_pack);
+    c->h_pack = nullptr; c->d_pack = nullptr;
+    return fail(c, E55_ERR_CUDA, msg);
   }
-  c->h_cap = cap;
+  c->h_cap = cap; c->d_pack_cap = cap;
   return E55_OK;
 }
 
@@ -433,6 +447,10 @@ int e55_create(e55_ctx** out, int device, int blocks, int filters, int in_planes
   if (filters != 128 && filters != 256)
     return fail(nullptr, E55_ERR_UNSUPPORTED, "filters must be 128 or 256");
   int ndev = 0;
+  // the host-buffer pipeline keeps up to eight chunk streams busy: with the default of 8 hardware queues, streams share
+  // queues and a late chunk waits behind an early chunk's read-back (seen as ~100 us per batch-1024 call); only
+  // effective when this is the process's first CUDA use, hence also set by the Python package on import
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
     return fail(nullptr, E55_ERR_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e));
@@ -466,7 +484,7 @@ void e55_destroy(e55_ctx* c) {
   e55_service_stop(c);
   if (c->stream) cudaStreamSynchronize(c->stream);
   e55host::packer_destroy(c->packer);
-  cudaFreeHost(c->h_bits); cudaFreeHost(c->h_scale);
+  cudaFreeHost(c->h_pack); cudaFree(c->d_pack);
   cudaFreeHost(c->h_out_policy); cudaFreeHost(c->h_out_value);
   for (cudaEvent_t ev : c->chunk_ev) cudaEventDestroy(ev);
   cudaFreeHost(c->h_req); cudaFreeHost(c->h_ans); cudaFree(c->d_req); cudaFree(c->d_ans);
@@ -607,23 +625,38 @@ bool host_pinned(const void* p) {
   return a.type == cudaMemoryTypeHost;
 }
 
-// Pinned staging of results for callers whose output buffers are pageable (numpy arrays, malloc).
-int ensure_out_staging(e55_ctx* c, int n) {
-  if (n <= c->h_out_cap) return E55_OK;
-  cudaFreeHost(c->h_out_policy); cudaFreeHost(c->h_out_value);
-  c->h_out_policy = c->h_out_value = nullptr; c->h_out_cap = 0;
-  int cap = 256;
-  while (cap < n) cap *= 2;
-  E55_CUDA(c, cudaMallocHost(&c->h_out_policy, static_cast<size_t>(cap) * kPolicyCh * kSq * sizeof(float)));
-  E55_CUDA(c, cudaMallocHost(&c->h_out_value, static_cast<size_t>(cap) * sizeof(float)));
-  c->h_out_cap = cap;
-  return E55_OK;
+// Device-side address of page-locked host memory (null: not mapped, or direct writes are switched off).  The tower
+// kernel's policy tail writes whole 6.9 KB rows, so logits can go straight over PCIe into the caller's array: no
+// read-back copy, and nothing waits behind a copy engine.  E55_DIRECT_HOST=0 restores the copies (for comparison).
+float* mapped_device_pointer(void* host) {
+  static const bool direct = !(getenv("E55_DIRECT_HOST") && !strcmp(getenv("E55_DIRECT_HOST"), "0"));
+  void* d = nullptr;
+  if (!direct || cudaHostGetDevicePointer(&d, host, 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return static_cast<float*>(d);
 }
 
-void sync_pipe_streams(e55_ctx* c) {
-  for (int i = 0; i < e55_ctx::kPipeStreams; ++i)
-    if (c->pipe_stream[i]) cudaStreamSynchronize(c->pipe_stream[i]);
-  cudaStreamSynchronize(c->stream);
+// Pinned staging of results.  Values (4 bytes per position) always go through it: the kernel writes them straight into
+// this page-locked block (it is device-mapped: no read-back copy at all) and the call copies them to the caller's array
+// at the end.  Logits go through it only for callers whose policy buffer is pageable (malloc, plain numpy).
+int ensure_out_staging(e55_ctx* c, int n, bool need_policy) {
+  int cap = 256;
+  while (cap < n) cap *= 2;
+  if (n > c->h_out_value_cap) {
+    sync_pipe_streams(c);
+    cudaFreeHost(c->h_out_value);
+    c->h_out_value = nullptr; c->h_out_value_cap = 0;
+    E55_CUDA(c, cudaHostAlloc(&c->h_out_value, static_cast<size_t>(cap) * sizeof(float), cudaHostAllocMapped | cudaHostAllocPortable));
+    E55_CUDA(c, cudaHostGetDevicePointer(&c->d_out_value_mapped, c->h_out_value, 0));
+    c->h_out_value_cap = cap;
+  }
+  if (need_policy && n > c->h_out_cap) {
+    sync_pipe_streams(c);
+    cudaFreeHost(c->h_out_policy);
+    c->h_out_policy = nullptr; c->h_out_cap = 0;
+    E55_CUDA(c, cudaMallocHost(&c->h_out_policy, static_cast<size_t>(cap) * kPolicyCh * kSq * sizeof(float)));
+    c->h_out_cap = cap;
+  }
+  return E55_OK;
 }
 
 // Host-buffer predict as a pipeline of chunks on rotating side streams: H2D -> tower kernel -> D2H, so that PCIe
@@ -639,14 +672,31 @@ void sync_pipe_streams(e55_ctx* c) {
 //     from where the pool copies each chunk out as soon as its event has fired, while later chunks are still on the GPU.
 // Results are identical whichever way a position travels.
 int predict_host_pipeline(e55_ctx* c, e55host::Packer* packer, const float* planes, int n, int n_float, float* policy, float* value,
-                          bool pol_pinned, bool val_pinned) {
+                          bool pol_pinned) {
   const int n_pack = n - n_float;
   const size_t ip = static_cast<size_t>(c->in_planes), in_pp = ip * kSq, pol_pp = static_cast<size_t>(kPolicyCh) * kSq;
   int rc = E55_OK;
-  if (!(pol_pinned && val_pinned) && (rc = ensure_out_staging(c, n))) return rc;
+  if ((rc = ensure_out_staging(c, n, !pol_pinned))) return rc;
   float* out_policy = pol_pinned ? policy : c->h_out_policy;
-  float* out_value = val_pinned ? value : c->h_out_value;
-  if (n_pack > 0) e55host::packer_start(packer, planes, n_pack, c->in_planes, c->h_bits, c->h_scale);
+  float* direct_policy = mapped_device_pointer(out_policy);      // non-null: the kernels write the logits into it themselves
+  float* d_value = static_cast<float*>(c->d_out_value_mapped);   // written by the kernels over PCIe, 4 bytes per position
+  e55::tc::PolicyTail tail;
+  tail.rows = direct_policy != nullptr;
+  const size_t ip2 = 2 * ip;
+  static const bool trace = getenv("E55_HOST_TRACE") != nullptr;   // prints where a call's time goes (host clock, us)
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto now_us = [&] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_begin).count(); };
+  std::vector<double> t_sent;
+  std::vector<cudaEvent_t> tev;   // trace mode: [chunk][before H2D, after H2D, after kernel, after D2H] (+ one at the start)
+  auto mark = [&](cudaStream_t st) {
+    if (!trace) return;
+    cudaEvent_t ev = nullptr;
+    cudaEventCreate(&ev);
+    cudaEventRecord(ev, st);
+    tev.push_back(ev);
+  };
+  if (n_pack > 0) e55host::packer_start(packer, planes, n_pack, c->in_planes, c->h_pack, reinterpret_cast<float*>(c->h_pack) + ip, static_cast<int>(ip2));
+  mark(c->stream);
   cudaError_t e = cudaEventRecord(c->pipe_start, c->stream);
   struct Sent { int off, m; };
   std::vector<Sent> sent;
@@ -661,23 +711,31 @@ int predict_host_pipeline(e55_ctx* c, e55host::Packer* packer, const float* plan
       if (e == cudaSuccess) c->chunk_ev.push_back(ev);
     }
     c->tc.throughput_rounds = full_chunk;   // full chunks run side by side on few SMs each; a short tail spreads out
+    mark(st);
     if (packed) {
-      if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_bits + off * ip, c->h_bits + off * ip, m * ip * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
-      if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_scale + off * ip, c->h_scale + off * ip, m * ip * sizeof(float), cudaMemcpyHostToDevice, st);
-      if (e == cudaSuccess) rc = forward_packed_on(c, st, c->d_bits + off * ip, c->d_scale + off * ip, m, off, c->d_policy + off * pol_pp, c->d_value + off);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_pack + off * ip2, c->h_pack + off * ip2, m * ip2 * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
+      mark(st);
+      if (e == cudaSuccess) rc = forward_packed_on(c, st, c->d_pack + off * ip2, reinterpret_cast<const float*>(c->d_pack + off * ip2) + ip, m, off,
+                                                   (direct_policy ? direct_policy : c->d_policy) + off * pol_pp, d_value + off, static_cast<int>(ip2), tail);
     } else {
       if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_in + off * in_pp, planes + off * in_pp, m * in_pp * sizeof(float), cudaMemcpyHostToDevice, st);
-      if (e == cudaSuccess) rc = forward_tc_on(c, st, c->d_in + off * in_pp, m, c->d_policy + off * pol_pp, c->d_value + off);
+      mark(st);
+      if (e == cudaSuccess) rc = forward_tc_on(c, st, c->d_in + off * in_pp, m, (direct_policy ? direct_policy : c->d_policy) + off * pol_pp, d_value + off, tail);
     }
+    mark(st);
     c->tc.throughput_rounds = false;
-    if (e == cudaSuccess && rc == E55_OK) e = cudaMemcpyAsync(out_policy + off * pol_pp, c->d_policy + off * pol_pp, m * pol_pp * sizeof(float), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess && rc == E55_OK) e = cudaMemcpyAsync(out_value + off, c->d_value + off, m * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && rc == E55_OK && !direct_policy)
+      e = cudaMemcpyAsync(out_policy + off * pol_pp, c->d_policy + off * pol_pp, m * pol_pp * sizeof(float), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && rc == E55_OK) e = cudaEventRecord(c->chunk_ev[chunk], st);
+    mark(st);
     sent.push_back(Sent{off, m});
+    if (trace) t_sent.push_back(now_us());
   };
-  // packed chunks: 256 positions = a one-group-per-CTA kernel of 64 CTAs, two of which run side by side; smaller
-  // batches are cut in two so that the second half is packed while the first is on the GPU
-  const int pack_chunk = n_pack >= 2 * kPipeChunk ? kPipeChunk : std::max(64, ((n_pack / 2 + 63) / 64) * 64);
+  // Packed chunks.  The read-back of the logits (6.9 KB per position) is the longest stage of a large call, so results
+  // have to start flowing early and keep flowing: two chunks of 64 positions first, then chunks of 128, each a kernel in
+  // latency mode (one 4-position group per CTA: 16 / 32 CTAs, ~76 us), up to four of which run side by side.
+  static const int first_chunk = getenv("E55_FIRST_CHUNK") ? std::max(64, atoi(getenv("E55_FIRST_CHUNK"))) : 64;
+  static const int body_chunk = getenv("E55_BODY_CHUNK") ? std::max(64, atoi(getenv("E55_BODY_CHUNK"))) : 128;
   constexpr int kFloatChunk = 128;   // 3.4 MB: ~65 us on the link, about what packing the next chunk takes
   int off = 0, foff = n_pack;
   while ((off < n_pack || foff < n) && e == cudaSuccess && rc == E55_OK) {
@@ -687,28 +745,29 @@ int predict_host_pipeline(e55_ctx* c, e55host::Packer* packer, const float* plan
       // all floats: full chunks while much is left, then halving chunks, so that what remains after the last byte
       // has arrived -- one kernel and one read-back -- is short
       const int m = n_pack == 0 ? pipe_chunk(n - foff, kPipeChunk) : std::min(kFloatChunk, n - foff);
-      send(foff, m, false, m >= kPipeChunk);
+      send(foff, m, false, n_pack == 0 && m >= kPipeChunk);
       foff += m;
     }
     if (off < n_pack && e == cudaSuccess && rc == E55_OK) {
-      const int m = std::min(pack_chunk, n_pack - off);
-      send(off, m, e55host::packer_wait_range(packer, off, m), n_pack >= 2 * kPipeChunk);
+      const int left = n_pack - off;
+      int m = off < 2 * first_chunk ? first_chunk : body_chunk;
+      if (left < m + 32) m = left;   // no crumbs at the end
+      send(off, m, e55host::packer_wait_range(packer, off, m), false);
       off += m;
     }
   }
   if (n_pack > 0) e55host::packer_finish(packer);   // the pool reads the caller's planes: it must be done before we return, whatever happened
+  const double t_packed = trace ? now_us() : 0.0;
   if (rc != E55_OK || e != cudaSuccess) {
     sync_pipe_streams(c);   // nothing of this call may still be in flight when the caller gets its buffers back
     if (rc != E55_OK) return rc;
     E55_CUDA(c, e);
   }
-  if (!(pol_pinned && val_pinned)) {
+  if (!pol_pinned) {
     for (size_t k = 0; k < sent.size() && e == cudaSuccess; ++k) {
       e = cudaEventSynchronize(c->chunk_ev[k]);
       if (e != cudaSuccess) break;
-      if (!pol_pinned)
-        e55host::packer_parallel_copy(packer, policy + sent[k].off * pol_pp, out_policy + sent[k].off * pol_pp, sent[k].m * pol_pp * sizeof(float));
-      if (!val_pinned) memcpy(value + sent[k].off, out_value + sent[k].off, sent[k].m * sizeof(float));
+      e55host::packer_parallel_copy(packer, policy + sent[k].off * pol_pp, out_policy + sent[k].off * pol_pp, sent[k].m * pol_pp * sizeof(float));
     }
   }
   for (int i = 0; i < used && e == cudaSuccess; ++i) {
@@ -718,6 +777,22 @@ int predict_host_pipeline(e55_ctx* c, e55host::Packer* packer, const float* plan
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   if (e != cudaSuccess) sync_pipe_streams(c);
   E55_CUDA(c, e);
+  memcpy(value, c->h_out_value, static_cast<size_t>(n) * sizeof(float));
+  if (trace) {
+    fprintf(stderr, "[e55 host pipeline] n %d (%d as floats): chunks sent at", n, n_float);
+    for (size_t k = 0; k < sent.size(); ++k) fprintf(stderr, " %.0f(%d)", t_sent[k], sent[k].m);
+    fprintf(stderr, " us, pool done %.0f us, results home %.0f us\n", t_packed, now_us());
+    if (tev.size() == 1 + 4 * sent.size()) {
+      fprintf(stderr, "[e55 host pipeline]   device clock, us since the call's first event: chunk = H2D start..end, kernel end, D2H end:");
+      for (size_t k = 0; k < sent.size(); ++k) {
+        float t[4];
+        for (int j = 0; j < 4; ++j) cudaEventElapsedTime(&t[j], tev[0], tev[1 + 4 * k + j]);
+        fprintf(stderr, " [%d: %.0f..%.0f, %.0f, %.0f]", sent[k].m, t[0] * 1e3, t[1] * 1e3, t[2] * 1e3, t[3] * 1e3);
+      }
+      fprintf(stderr, "\n");
+    }
+    for (cudaEvent_t ev : tev) cudaEventDestroy(ev);
+  }
   return E55_OK;
 }
 
@@ -735,7 +810,7 @@ int e55_predict(e55_ctx* c, const float* planes, int n, float* policy, float* va
     // travels as floats meanwhile (pinned inputs).  Which split is fastest depends on the host (cores and memory bandwidth
     // to spare against the PCIe link), so unless the caller fixed the thread count the first calls try them all and later
     // ones take the fastest, looking at its neighbours again now and then.
-    const bool in_pinned = host_pinned(planes), pol_pinned = host_pinned(policy), val_pinned = host_pinned(value);
+    const bool in_pinned = host_pinned(planes), pol_pinned = host_pinned(policy);
     e55host::Packer* packer = host_packer(c, n);
     int level = packer ? 0 : e55_ctx::kSplitLevels - 1;   // index into kSplitEighths: how much of the batch travels as floats
     const bool adaptive = packer && c->host_auto && in_pinned && n >= 2 * kPipeChunk;
@@ -754,7 +829,7 @@ int e55_predict(e55_ctx* c, const float* planes, int n, float* policy, float* va
     const int eighths = e55_ctx::kSplitEighths[level];
     const int n_float = eighths >= 8 ? n : (n / 8 * eighths) / 64 * 64;
     const auto t0 = std::chrono::steady_clock::now();
-    rc = predict_host_pipeline(c, packer, planes, n, n_float, policy, value, pol_pinned, val_pinned);
+    rc = predict_host_pipeline(c, packer, planes, n, n_float, policy, value, pol_pinned);
     if (adaptive) {
       const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / n;
       double& avg = c->split_us[level];
@@ -766,17 +841,35 @@ int e55_predict(e55_ctx* c, const float* planes, int n, float* policy, float* va
   // Small batch (the reference's own: root 1, leaves 16; mcts.py:57-58,101-102): one copy in, one kernel, one copy out.
   // A pageable input is bit-packed by the calling thread into pinned staging on the way (2 KB instead of 26 KB per
   // position for the copy engine, and no driver-side staging copy); anything not exactly representable goes as floats.
-  if (tc_path && c->host_threads != 0 && !host_pinned(planes) && ensure_host_staging(c, n) == E55_OK &&
-      e55host::pack_planes_inline(planes, n, c->in_planes, c->h_bits, c->h_scale)) {
-    const size_t w = static_cast<size_t>(n) * c->in_planes;
-    E55_CUDA(c, cudaMemcpyAsync(c->d_bits, c->h_bits, w * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-    E55_CUDA(c, cudaMemcpyAsync(c->d_scale, c->h_scale, w * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    if ((rc = forward_packed_on(c, c->stream, c->d_bits, c->d_scale, n, 0, c->d_policy, c->d_value))) return rc;
-  } else {
-    const size_t in_bytes = static_cast<size_t>(n) * c->in_planes * kSq * sizeof(float);
-    E55_CUDA(c, cudaMemcpyAsync(c->d_in, planes, in_bytes, cudaMemcpyHostToDevice, c->stream));
-    if ((rc = forward(c, c->d_in, n, c->d_policy, c->d_value))) return rc;
+  // The logits come back through pinned staging, the values are written into mapped host memory by the kernel.
+  if (tc_path) {
+    const bool pol_pinned = host_pinned(policy);
+    if ((rc = ensure_out_staging(c, n, !pol_pinned))) return rc;
+    float* d_value = static_cast<float*>(c->d_out_value_mapped);
+    float* out_policy = pol_pinned ? policy : c->h_out_policy;
+    float* direct_policy = mapped_device_pointer(out_policy);   // the kernel writes the logits into host memory itself
+    e55::tc::PolicyTail tail;
+    tail.rows = direct_policy != nullptr;
+    float* k_policy = direct_policy ? direct_policy : c->d_policy;
+    const size_t ip = static_cast<size_t>(c->in_planes), ip2 = 2 * ip;
+    if (c->host_threads != 0 && !host_pinned(planes) && ensure_host_staging(c, n) == E55_OK &&
+        e55host::pack_planes_inline(planes, n, c->in_planes, c->h_pack, reinterpret_cast<float*>(c->h_pack) + ip, static_cast<int>(ip2))) {
+      E55_CUDA(c, cudaMemcpyAsync(c->d_pack, c->h_pack, n * ip2 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+      if ((rc = forward_packed_on(c, c->stream, c->d_pack, reinterpret_cast<const float*>(c->d_pack) + ip, n, 0, k_policy, d_value, static_cast<int>(ip2), tail))) return rc;
+    } else {
+      E55_CUDA(c, cudaMemcpyAsync(c->d_in, planes, static_cast<size_t>(n) * ip * kSq * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+      if ((rc = forward_tc_on(c, c->stream, c->d_in, n, k_policy, d_value, tail))) return rc;
+    }
+    const size_t pol_bytes = static_cast<size_t>(n) * kPolicyCh * kSq * sizeof(float);
+    if (!direct_policy) E55_CUDA(c, cudaMemcpyAsync(out_policy, c->d_policy, pol_bytes, cudaMemcpyDeviceToHost, c->stream));
+    E55_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (!pol_pinned) memcpy(policy, c->h_out_policy, pol_bytes);
+    memcpy(value, c->h_out_value, static_cast<size_t>(n) * sizeof(float));
+    return E55_OK;
   }
+  const size_t in_bytes = static_cast<size_t>(n) * c->in_planes * kSq * sizeof(float);
+  E55_CUDA(c, cudaMemcpyAsync(c->d_in, planes, in_bytes, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = forward(c, c->d_in, n, c->d_policy, c->d_value))) return rc;
   E55_CUDA(c, cudaMemcpyAsync(policy, c->d_policy, static_cast<size_t>(n) * kPolicyCh * kSq * sizeof(float),
                               cudaMemcpyDeviceToHost, c->stream));
   E55_CUDA(c, cudaMemcpyAsync(value, c->d_value, static_cast<size_t>(n) * sizeof(float), cudaMemcpyDeviceToHost,
@@ -867,12 +960,21 @@ int e55_predict_packed_moves(e55_ctx* c, const uint32_t* bits, const float* scal
   E55_CUDA(c, cudaMemcpyAsync(c->d_req, c->h_req, in_bytes, cudaMemcpyHostToDevice, c->stream));
   float* d_priors = reinterpret_cast<float*>(c->d_ans);
   float* d_value = reinterpret_cast<float*>(c->d_ans + o_value);
-  if ((rc = forward_packed_on(c, c->stream, reinterpret_cast<const uint32_t*>(c->d_req), reinterpret_cast<const float*>(c->d_req + o_scale), n, 0,
-                              c->d_policy, d_value))) return rc;
-  e55::legal_priors_kernel<<<(n + 7) / 8, 256, 0, c->stream>>>(c->d_policy, reinterpret_cast<const int32_t*>(c->d_req + o_off),
-                                                                    reinterpret_cast<const uint16_t*>(c->d_req + o_idx), d_priors, n, kPolicyCh * kSq);
-  ++c->launches;
-  E55_CUDA(c, cudaGetLastError());
+  const int32_t* d_off = reinterpret_cast<const int32_t*>(c->d_req + o_off);
+  const uint16_t* d_idx = reinterpret_cast<const uint16_t*>(c->d_req + o_idx);
+  if (c->precision == E55_PRECISION_BF16_TC) {
+    // the tower kernel soft-maxes the legal moves itself (policy tail): the 1725 logits never leave shared memory
+    e55::tc::PolicyTail tail;
+    tail.move_off = d_off; tail.move_idx = d_idx; tail.priors = d_priors;
+    if ((rc = forward_packed_on(c, c->stream, reinterpret_cast<const uint32_t*>(c->d_req), reinterpret_cast<const float*>(c->d_req + o_scale), n, 0,
+                                nullptr, d_value, 0, tail))) return rc;
+  } else {
+    if ((rc = forward_packed_on(c, c->stream, reinterpret_cast<const uint32_t*>(c->d_req), reinterpret_cast<const float*>(c->d_req + o_scale), n, 0,
+                                c->d_policy, d_value))) return rc;
+    e55::legal_priors_kernel<<<(n + 7) / 8, 256, 0, c->stream>>>(c->d_policy, d_off, d_idx, d_priors, n, kPolicyCh * kSq);
+    ++c->launches;
+    E55_CUDA(c, cudaGetLastError());
+  }
   E55_CUDA(c, cudaMemcpyAsync(c->h_ans, c->d_ans, out_bytes, cudaMemcpyDeviceToHost, c->stream));
   E55_CUDA(c, cudaStreamSynchronize(c->stream));
   memcpy(priors, c->h_ans, static_cast<size_t>(total) * 4);
@@ -888,6 +990,11 @@ int e55_predict_masked_device(e55_ctx* c, const float* d_planes, const uint8_t* 
   std::lock_guard<std::mutex> lk(c->mu);
   E55_CUDA(c, cudaSetDevice(c->device));
   if ((rc = ensure_capacity(c, n))) return rc;
+  if (c->precision == E55_PRECISION_BF16_TC) {   // masked softmax in the tower kernel's policy tail
+    e55::tc::PolicyTail tail;
+    tail.mask = d_mask; tail.probs = d_probs;
+    return forward_tc_on(c, c->stream, d_planes, n, nullptr, d_value, tail);
+  }
   if ((rc = forward(c, d_planes, n, c->d_policy, d_value))) return rc;
   e55::fp32::masked_softmax_kernel<<<n, 256, 0, c->stream>>>(c->d_policy, d_mask, d_probs, kPolicyCh * kSq);
   ++c->launches;
@@ -906,10 +1013,16 @@ int e55_predict_masked(e55_ctx* c, const float* planes, const uint8_t* mask, int
   E55_CUDA(c, cudaMemcpyAsync(c->d_in, planes, static_cast<size_t>(n) * c->in_planes * kSq * sizeof(float),
                               cudaMemcpyHostToDevice, c->stream));
   E55_CUDA(c, cudaMemcpyAsync(c->d_mask, mask, pol, cudaMemcpyHostToDevice, c->stream));
-  if ((rc = forward(c, c->d_in, n, c->d_policy, c->d_value))) return rc;
-  e55::fp32::masked_softmax_kernel<<<n, 256, 0, c->stream>>>(c->d_policy, c->d_mask, c->d_probs, kPolicyCh * kSq);
-  ++c->launches;
-  E55_CUDA(c, cudaGetLastError());
+  if (c->precision == E55_PRECISION_BF16_TC) {   // masked softmax in the tower kernel's policy tail
+    e55::tc::PolicyTail tail;
+    tail.mask = c->d_mask; tail.probs = c->d_probs;
+    if ((rc = forward_tc_on(c, c->stream, c->d_in, n, nullptr, c->d_value, tail))) return rc;
+  } else {
+    if ((rc = forward(c, c->d_in, n, c->d_policy, c->d_value))) return rc;
+    e55::fp32::masked_softmax_kernel<<<n, 256, 0, c->stream>>>(c->d_policy, c->d_mask, c->d_probs, kPolicyCh * kSq);
+    ++c->launches;
+    E55_CUDA(c, cudaGetLastError());
+  }
   E55_CUDA(c, cudaMemcpyAsync(probs, c->d_probs, pol * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   E55_CUDA(c, cudaMemcpyAsync(value, c->d_value, static_cast<size_t>(n) * sizeof(float), cudaMemcpyDeviceToHost,
                               c->stream));
@@ -920,7 +1033,7 @@ int e55_predict_masked(e55_ctx* c, const float* planes, const uint8_t* mask, int
 int e55_host_alloc(size_t bytes, void** out) {
   if (!out || bytes == 0) return fail(nullptr, E55_ERR_INVALID, "bad host allocation request");
   *out = nullptr;
-  E55_CUDA(nullptr, cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+  E55_CUDA(nullptr, cudaHostAlloc(out, bytes, cudaHostAllocPortable | cudaHostAllocMapped));
   return E55_OK;
 }
 
@@ -1022,6 +1135,26 @@ int e55_debug_activations(e55_ctx* c, const float* planes, int n, int n_convs, f
   }
   E55_CUDA(c, cudaMemcpyAsync(act_out, result, static_cast<size_t>(n) * c->filters * kSq * sizeof(float),
                               cudaMemcpyDeviceToHost, c->stream));
+  E55_CUDA(c, cudaStreamSynchronize(c->stream));
+  return E55_OK;
+}
+
+int e55_debug_legal_priors(e55_ctx* c, const float* logits, int n, const int32_t* move_offset, const uint16_t* move_index, float* priors) {
+  if (!c || !logits || !move_offset || !move_index || !priors || n <= 0) return fail(c, E55_ERR_INVALID, "bad arguments");
+  std::lock_guard<std::mutex> lk(c->mu);
+  E55_CUDA(c, cudaSetDevice(c->device));
+  int rc = ensure_capacity(c, n);
+  if (rc) return rc;
+  const int total = move_offset[n];
+  if (total < 0 || static_cast<size_t>(total) > static_cast<size_t>(c->capacity) * e55_ctx::kMovesPerPosition)
+    return fail(c, E55_ERR_INVALID, "too many moves");
+  E55_CUDA(c, cudaMemcpyAsync(c->d_policy, logits, static_cast<size_t>(n) * kPolicyCh * kSq * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  E55_CUDA(c, cudaMemcpyAsync(c->d_move_off, move_offset, (static_cast<size_t>(n) + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  E55_CUDA(c, cudaMemcpyAsync(c->d_move_idx, move_index, static_cast<size_t>(total) * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
+  e55::legal_priors_kernel<<<(n + 7) / 8, 256, 0, c->stream>>>(c->d_policy, c->d_move_off, c->d_move_idx, c->d_priors, n, kPolicyCh * kSq);
+  ++c->launches;
+  E55_CUDA(c, cudaGetLastError());
+  E55_CUDA(c, cudaMemcpyAsync(priors, c->d_priors, static_cast<size_t>(total) * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   E55_CUDA(c, cudaStreamSynchronize(c->stream));
   return E55_OK;
 }

@@ -125,7 +125,6 @@ int e55_gpu_selfplay_run(e55_ctx* c, int games, long total_moves, int simulation
   std::vector<void*> owned;
   gs::Params p{};
   const size_t G = static_cast<size_t>(games), slots = G * gs::kLeaf;
-  float* d_policy = nullptr;
   cudaError_t e = cudaSuccess;
   auto chain = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
   chain(dev_alloc(p.games, G, owned, c->stream));
@@ -140,7 +139,6 @@ int e55_gpu_selfplay_run(e55_ctx* c, int games, long total_moves, int simulation
   chain(dev_alloc(p.priors, slots * gs::kMoveStride, owned, c->stream));
   chain(dev_alloc(p.value, slots, owned, c->stream));
   chain(dev_alloc(p.shared, 1, owned, c->stream));
-  chain(dev_alloc(d_policy, slots * kPolicyCh * kSq, owned, c->stream));
   if (record_cap > 0) {
     chain(dev_alloc(p.records, static_cast<size_t>(record_cap) * gs::kRecordWords, owned, c->stream));
     chain(dev_alloc(p.rec_buf, G * gs::kRecordWords, owned, c->stream));
@@ -188,11 +186,9 @@ int e55_gpu_selfplay_run(e55_ctx* c, int games, long total_moves, int simulation
   const int n_cohorts = want_cohorts == 1 || games < 128 ? 1 : (want_cohorts == 2 || games >= 2048 ? 2 : 1);
   const int spare_sms = getenv("E55_GPU_SPARE_SMS") ? atoi(getenv("E55_GPU_SPARE_SMS")) : 24;
   if (n_cohorts == 2) c->tc.sms = std::max(2, sms_before - std::max(0, spare_sms));
-  const int pri_warps = getenv("E55_GPU_PRIORS_WARPS") ? std::max(1, std::min(8, atoi(getenv("E55_GPU_PRIORS_WARPS")))) : 8;
   struct Cohort {
     gs::Params p;
     cudaStream_t st;
-    float* policy;
     int g0, games, blocks, n;
   } co[2];
   for (int k = 0; k < n_cohorts; ++k) {
@@ -210,7 +206,6 @@ int e55_gpu_selfplay_run(e55_ctx* c, int games, long total_moves, int simulation
     q.p.move_idx += s0 * gs::kMoveStride; q.p.move_cnt += s0; q.p.priors += s0 * gs::kMoveStride; q.p.value += s0;
     if (q.p.rec_buf) q.p.rec_buf += g0 * gs::kRecordWords;
     q.p.req_board += g0; q.p.req_seq += g0; q.p.ans += g0;
-    q.policy = d_policy + s0 * kPolicyCh * kSq;
   }
   const int n = static_cast<int>(slots);
   std::vector<unsigned long long> answers(G, 0ull);   // the latest answer of every game (request number 0 = none)
@@ -281,15 +276,18 @@ int e55_gpu_selfplay_run(e55_ctx* c, int games, long total_moves, int simulation
       ++c->launches;
       if (timed) cudaEventRecord(te[1], st);
       if (tle) cudaEventRecord(tle[1], st);
-      rc = forward_packed_on(c, st, q.p.bits, q.p.scale, q.n, 0, q.policy, q.p.value);
+      {   // the tower kernel's policy tail soft-maxes each slot's legal moves: the logits never reach HBM
+        e55::tc::PolicyTail tail;
+        tail.move_off = q.p.move_cnt; tail.move_idx = q.p.move_idx; tail.priors = q.p.priors; tail.move_stride = gs::kMoveStride;
+        rc = forward_packed_on(c, st, q.p.bits, q.p.scale, q.n, 0, nullptr, q.p.value, 0, tail);
+      }
       if (rc) break;
       if (timed) cudaEventRecord(te[2], st);
       if (tle) cudaEventRecord(tle[2], st);
-      gs::legal_priors_strided_kernel<<<(q.n + pri_warps - 1) / pri_warps, pri_warps * 32, 0, st>>>(q.policy, q.p.move_cnt, q.p.move_idx, q.p.priors, q.n, kPolicyCh * kSq, gs::kMoveStride);
       if (timed) cudaEventRecord(te[3], st);
       if (tle) cudaEventRecord(tle[3], st);
       gs::expand_kernel<<<q.blocks, 64, 0, st>>>(q.p);
-      c->launches += 2;
+      ++c->launches;
       if (tle) cudaEventRecord(tle[4], st);
       if (timed) {
         cudaEventRecord(te[4], st);

@@ -43,12 +43,14 @@ inline bool pack_plane(const float* q, uint32_t& bits, float& value) {
   return uniform(v0) == 0xFF && uniform(v1) == 0xFF && uniform(v2) == 0xFF && (uniform(v3) & 0x80);
 }
 
-bool pack_positions_avx2(const float* planes, int first, int count, int in_planes, uint32_t* bits, float* scale) {
+// (bits / scale of position p start at word p * stride: stride = in_planes for two separate arrays, 2 * in_planes for
+// the interleaved staging the host-buffer predict copies to the device in one piece)
+bool pack_positions_avx2(const float* planes, int first, int count, int in_planes, uint32_t* bits, float* scale, int stride) {
   bool exact = true;
   for (int p = first; p < first + count; ++p) {
     const float* src = planes + static_cast<size_t>(p) * in_planes * kSq;
-    uint32_t* b = bits + static_cast<size_t>(p) * in_planes;
-    float* s = scale + static_cast<size_t>(p) * in_planes;
+    uint32_t* b = bits + static_cast<size_t>(p) * stride;
+    float* s = scale + static_cast<size_t>(p) * stride;
     for (int c = 0; c < in_planes; ++c) exact &= pack_plane(src + c * kSq, b[c], s[c]);   // (loads stay inside the plane)
   }
   return exact;
@@ -57,32 +59,33 @@ bool pack_positions_avx2(const float* planes, int first, int count, int in_plane
 // AVX-512: a plane is one full and one 9-lane masked load, the occupancy word is the two compare masks, and the
 // uniformity test is one more compare per half -- branch-free, so the loop runs at the rate the planes stream in.
 __attribute__((target("avx512f,avx512vl,avx512bw,avx512dq")))
-bool pack_positions_avx512(const float* planes, int first, int count, int in_planes, uint32_t* bits, float* scale) {
+bool pack_positions_avx512(const float* planes, int first, int count, int in_planes, uint32_t* bits, float* scale, int stride) {
   const __m512 zero = _mm512_setzero_ps();
   uint32_t bad = 0;
-  const size_t total = static_cast<size_t>(count) * in_planes;
-  const float* src = planes + static_cast<size_t>(first) * in_planes * kSq;
-  uint32_t* b = bits + static_cast<size_t>(first) * in_planes;
-  float* s = scale + static_cast<size_t>(first) * in_planes;
-  for (size_t c = 0; c < total; ++c) {
-    const float* q = src + c * kSq;
-    _mm_prefetch(reinterpret_cast<const char*>(q + 512), _MM_HINT_T0);
-    const __m512 lo = _mm512_loadu_ps(q);
-    const __m512 hi = _mm512_maskz_loadu_ps(0x1FF, q + 16);
-    const uint32_t k0 = _mm512_cmp_ps_mask(lo, zero, _CMP_NEQ_UQ), k1 = _mm512_cmp_ps_mask(hi, zero, _CMP_NEQ_UQ);
-    const uint32_t w = k0 | (k1 << 16);
-    float v = q[w ? __builtin_ctz(w) : 0];
-    v = w ? v : 1.f;
-    const __m512 sv = _mm512_set1_ps(v);
-    const uint32_t e0 = _mm512_cmp_ps_mask(lo, sv, _CMP_EQ_OQ), e1 = _mm512_cmp_ps_mask(hi, sv, _CMP_EQ_OQ);
-    bad |= (k0 & ~e0) | (k1 & ~e1);   // a non-zero entry that is not the value (NaN included)
-    b[c] = w;
-    s[c] = v;
+  for (int p = first; p < first + count; ++p) {
+    const float* src = planes + static_cast<size_t>(p) * in_planes * kSq;
+    uint32_t* b = bits + static_cast<size_t>(p) * stride;
+    float* s = scale + static_cast<size_t>(p) * stride;
+    for (int c = 0; c < in_planes; ++c) {
+      const float* q = src + c * kSq;
+      _mm_prefetch(reinterpret_cast<const char*>(q + 512), _MM_HINT_T0);
+      const __m512 lo = _mm512_loadu_ps(q);
+      const __m512 hi = _mm512_maskz_loadu_ps(0x1FF, q + 16);
+      const uint32_t k0 = _mm512_cmp_ps_mask(lo, zero, _CMP_NEQ_UQ), k1 = _mm512_cmp_ps_mask(hi, zero, _CMP_NEQ_UQ);
+      const uint32_t w = k0 | (k1 << 16);
+      float v = q[w ? __builtin_ctz(w) : 0];
+      v = w ? v : 1.f;
+      const __m512 sv = _mm512_set1_ps(v);
+      const uint32_t e0 = _mm512_cmp_ps_mask(lo, sv, _CMP_EQ_OQ), e1 = _mm512_cmp_ps_mask(hi, sv, _CMP_EQ_OQ);
+      bad |= (k0 & ~e0) | (k1 & ~e1);   // a non-zero entry that is not the value (NaN included)
+      b[c] = w;
+      s[c] = v;
+    }
   }
   return bad == 0;
 }
 
-using PackFn = bool (*)(const float*, int, int, int, uint32_t*, float*);
+using PackFn = bool (*)(const float*, int, int, int, uint32_t*, float*, int);
 
 PackFn choose_pack() {
   const char* env = getenv("E55_HOST_ISA");
@@ -96,8 +99,8 @@ PackFn choose_pack() {
 
 const PackFn g_pack = choose_pack();
 
-inline bool pack_positions(const float* planes, int first, int count, int in_planes, uint32_t* bits, float* scale) {
-  return g_pack(planes, first, count, in_planes, bits, scale);
+inline bool pack_positions(const float* planes, int first, int count, int in_planes, uint32_t* bits, float* scale, int stride) {
+  return g_pack(planes, first, count, in_planes, bits, scale, stride);
 }
 
 }  // namespace
@@ -113,7 +116,7 @@ struct Packer {
   const float* planes = nullptr;
   uint32_t* bits = nullptr;
   float* scale = nullptr;
-  int n = 0, in_planes = 0, n_blocks = 0;
+  int n = 0, in_planes = 0, stride = 0, n_blocks = 0;
   const uint8_t* copy_src = nullptr;
   uint8_t* copy_dst = nullptr;
   size_t copy_bytes = 0;
@@ -122,13 +125,14 @@ struct Packer {
   std::vector<std::atomic<uint8_t>> block_state;  // 0 pending, 1 packed exactly, 2 not representable
 
   explicit Packer(int n_threads) : block_state(0) {
-    // Workers sit on the cores this process may use, one each, after the first (left to the calling thread): several
-    // ranks on one box each own a block of cores (bench.py / the launcher set the affinity), and a worker that
-    // migrates drags its share of the planes through another core's cache.
+    // The workers inherit the process's affinity mask (several ranks on one box each own a block of cores: bench.py / the
+    // launcher set it), so they stay on this rank's cores.  Binding each worker to one core of the mask is optional
+    // (E55_PIN_THREADS=1): the calling thread is not bound, and when the scheduler leaves it on a core whose bound worker
+    // is polling, every call waits for time slices (measured: 3.4 ms instead of 0.34 ms per batch-1024 call, at random).
     std::vector<int> cpus;
     cpu_set_t set;
     const char* pin = getenv("E55_PIN_THREADS");
-    if (!(pin && !strcmp(pin, "0")) && sched_getaffinity(0, sizeof(set), &set) == 0)
+    if (pin && !strcmp(pin, "1") && sched_getaffinity(0, sizeof(set), &set) == 0)
       for (int c = 0; c < CPU_SETSIZE; ++c)
         if (CPU_ISSET(c, &set)) cpus.push_back(c);
     for (int i = 0; i < n_threads; ++i) {
@@ -161,7 +165,7 @@ struct Packer {
       const int b = next.fetch_add(1, std::memory_order_relaxed);
       if (b >= n_blocks) return;
       const int first = b * kBlock, count = std::min(kBlock, n - first);
-      const bool exact = pack_positions(planes, first, count, in_planes, bits, scale);
+      const bool exact = pack_positions(planes, first, count, in_planes, bits, scale, stride);
       block_state[b].store(exact ? 1 : 2, std::memory_order_release);
     }
   }
@@ -195,9 +199,9 @@ struct Packer {
     generation.notify_all();
   }
 
-  void start(const float* planes_, int n_, int in_planes_, uint32_t* bits_, float* scale_) {
+  void start(const float* planes_, int n_, int in_planes_, uint32_t* bits_, float* scale_, int stride_) {
     copy_src = nullptr;
-    planes = planes_; n = n_; in_planes = in_planes_; bits = bits_; scale = scale_;
+    planes = planes_; n = n_; in_planes = in_planes_; bits = bits_; scale = scale_; stride = stride_ ? stride_ : in_planes_;
     n_blocks = (n + kBlock - 1) / kBlock;
     if (static_cast<int>(block_state.size()) < n_blocks) block_state = std::vector<std::atomic<uint8_t>>(n_blocks);
     for (int b = 0; b < n_blocks; ++b) block_state[b].store(0, std::memory_order_relaxed);
@@ -213,7 +217,7 @@ struct Packer {
         const int mine = next.fetch_add(1, std::memory_order_relaxed);   // lend a hand instead of just waiting
         if (mine < n_blocks) {
           const int f = mine * kBlock;
-          block_state[mine].store(pack_positions(planes, f, std::min(kBlock, n - f), in_planes, bits, scale) ? 1 : 2, std::memory_order_release);
+          block_state[mine].store(pack_positions(planes, f, std::min(kBlock, n - f), in_planes, bits, scale, stride) ? 1 : 2, std::memory_order_release);
         } else {
           _mm_pause();
         }
@@ -244,16 +248,16 @@ struct Packer {
 Packer* packer_create(int threads) { return threads > 0 ? new (std::nothrow) Packer(threads) : nullptr; }
 void packer_destroy(Packer* p) { delete p; }
 int packer_threads(const Packer* p) { return p ? static_cast<int>(p->threads.size()) : 0; }
-void packer_start(Packer* p, const float* planes, int n, int in_planes, uint32_t* bits, float* scale) {
-  p->start(planes, n, in_planes, bits, scale);
+void packer_start(Packer* p, const float* planes, int n, int in_planes, uint32_t* bits, float* scale, int stride) {
+  p->start(planes, n, in_planes, bits, scale, stride);
 }
 bool packer_wait_range(Packer* p, int first, int count) { return p->wait_range(first, count); }
 void packer_finish(Packer* p) { p->finish(); }
 void packer_parallel_copy(Packer* p, void* dst, const void* src, size_t bytes) {
   if (p) p->parallel_copy(dst, src, bytes); else memcpy(dst, src, bytes);
 }
-bool pack_planes_inline(const float* planes, int n, int in_planes, uint32_t* bits, float* scale) {
-  return pack_positions(planes, 0, n, in_planes, bits, scale);
+bool pack_planes_inline(const float* planes, int n, int in_planes, uint32_t* bits, float* scale, int stride) {
+  return pack_positions(planes, 0, n, in_planes, bits, scale, stride ? stride : in_planes);
 }
 const char* pack_isa() { return g_pack == pack_positions_avx512 ? "avx512" : "avx2"; }
 

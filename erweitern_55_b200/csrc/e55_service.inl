@@ -112,13 +112,21 @@ int service_launch(e55_ctx* c, e55_service* s, ServiceBatch& b, int slot_index) 
         E55_CUDA(c, cudaMemcpyAsync(d.move_idx, b.move_idx, static_cast<size_t>(b.moves_reserved) * sizeof(uint16_t), cudaMemcpyHostToDevice, d.stream));
     }
     if (s->trace) cudaEventRecord(b.k0, d.stream);
-    rc = forward_packed_on(c, d.stream, d.bits, d.scale, n, 0, d.policy, d.value);
+    if (b.kind == 3 && async) {   // the tower kernel's policy tail soft-maxes the legal moves: no logits in HBM, one launch
+      e55::tc::PolicyTail tail;
+      tail.move_off = d.move_off; tail.move_idx = d.move_idx; tail.priors = d.priors;
+      rc = forward_packed_on(c, d.stream, d.bits, d.scale, n, 0, nullptr, d.value, 0, tail);
+    } else {
+      rc = forward_packed_on(c, d.stream, d.bits, d.scale, n, 0, d.policy, d.value);
+    }
   }
   if (rc) return rc;
   if (b.kind == 3) {   // only the legal moves' priors travel back
-    e55::legal_priors_kernel<<<(n + 7) / 8, 256, 0, d.stream>>>(d.policy, d.move_off, d.move_idx, d.priors, n, kPolicyCh * kSq);
-    ++c->launches;
-    E55_CUDA(c, cudaGetLastError());
+    if (!async) {
+      e55::legal_priors_kernel<<<(n + 7) / 8, 256, 0, d.stream>>>(d.policy, d.move_off, d.move_idx, d.priors, n, kPolicyCh * kSq);
+      ++c->launches;
+      E55_CUDA(c, cudaGetLastError());
+    }
     if (s->trace) cudaEventRecord(b.k1, d.stream);
     if (b.moves_reserved)
       E55_CUDA(c, cudaMemcpyAsync(b.priors, d.priors, static_cast<size_t>(b.moves_reserved) * sizeof(float), cudaMemcpyDeviceToHost, d.stream));

@@ -124,6 +124,7 @@ struct Params {
   const float* planes;       // [n][in_planes][25] fp32 NCHW, as Network.get_inputs builds them (or nullptr)
   const uint32_t* bits;      // packed input instead of `planes`: [n][in_planes] occupancy bit per square ...
   const float* scale;        // ... and [n][in_planes] value of the set squares of that plane
+  int packed_stride;         // words from one position's bits (scale) to the next one's: in_planes, or 2 * in_planes when interleaved
   int in_planes;
   int in_planes8;            // ceil(in_planes / 16) * 2: 8-channel planes incl. zero padding
   int nslices;
@@ -135,8 +136,17 @@ struct Params {
   int n;                     // positions
   int nrounds;               // ceil(n / pos_per_round)
   int pos_per_round;         // 8 (groups A and B), or 4 (group A only: latency mode for small batches)
-  float* policy;             // [n][1725]
+  float* policy;             // [n][1725] raw logits (device memory or mapped page-locked host memory), or nullptr
   float* value;              // [n]
+  // fused legal-move tail (mcts.py:60,105-106: softmax over the legal moves' logits), all optional:
+  const int32_t* move_off;   // CSR offsets [n+1] (move_stride == 0), or counts [n] (move_stride > 0), or nullptr
+  const uint16_t* move_idx;  // policy indices of the legal moves: [move_off[i], move_off[i+1]) or [i*stride, +count[i])
+  float* priors;             // softmax over exactly those logits, same indexing as move_idx
+  int move_stride;
+  const uint8_t* mask;       // dense form: [n][1725] legal mask -> probs [n][1725] (illegal entries 0), or nullptr
+  float* probs;
+  int tail;                  // 1: the logits are staged in shared memory and leave through the policy tail (priors / probs wanted,
+                             // or `policy` is to be written as whole rows: mapped host memory); 0: the epilogue warps write `policy` directly
   uint4* dbg;                // [rounds*2][16][128] packed activations after layer nlayers_run-1
   unsigned long long* prof;  // optional cycle counters / timeline of CTA 0 (kProf instantiation only)
 };
@@ -235,6 +245,91 @@ __device__ __forceinline__ float epilogue_half(uint32_t taddr, const float* __re
   return vacc;
 }
 
+// Policy tail of one 4-position group, run by the weight-producer warp once all eight epilogue warps have staged the
+// group's logits in its (by then idle) activation planes: the logits leave as one coalesced 27.6 KB piece (device memory
+// or mapped page-locked host memory) and/or the legal moves of each position are soft-maxed with warp shuffles -- what
+// minishogilib.MCTS.evaluate does with a policy row (mcts.py:60,105-106).  Then the planes go back to the next round's
+// input: the staging has overwritten the zero columns / rows that give the convolutions their padding, so those are
+// cleared first.
+// Staging layout of a group's logits in its activation planes: five policy channels per plane strip (128 rows x 16 B),
+// each a row of [4 positions][25 squares] floats -- for an epilogue thread (one position, one square) the channel is
+// the only variable, and its offset a compile-time constant of the unrolled loop.
+template <int F>
+__host__ __device__ constexpr int stage_offset(int c) { return (c / 5) * Geo<F>::kPlaneBytes + (c % 5) * (kPosPerGroup * kSq * 4); }
+
+template <int F>
+__device__ __forceinline__ void policy_tail(const Params& prm, uint8_t* s_act, uint64_t* bar_in_empty, int g, int pos0, int lane) {
+  constexpr int kPlaneBytes = Geo<F>::kPlaneBytes;
+  constexpr int kRow = kPolicyCh * kSq;
+  uint8_t* stage = s_act + group_origin_row(g) * 16;
+  auto staged = [&](int L) -> float {   // L = p * 1725 + c * 25 + sq
+    const int p = L / kRow, j = L - p * kRow, c = j / kSq, sq = j - c * kSq;
+    return *reinterpret_cast<const float*>(stage + stage_offset<F>(c) + (p * kSq + sq) * 4);
+  };
+  const int npos = min(kPosPerGroup, prm.n - pos0);   // <= 0: the whole group lies past the batch
+  if (npos > 0 && prm.policy != nullptr) {
+    // rows of consecutive positions are consecutive in memory: one coalesced piece of npos x 6 900 bytes.  The lane's
+    // element advances by 32 per step: (position, channel, square) are carried along instead of divided out.
+    float* dst = prm.policy + static_cast<size_t>(pos0) * kRow;
+    int c = lane / kSq, sq = lane - c * kSq, p = 0;
+    for (int i = lane; i < npos * kRow; i += 32) {
+      dst[i] = *reinterpret_cast<const float*>(stage + stage_offset<F>(c) + (p * kSq + sq) * 4);
+      sq += 32 - kSq; c += 1;
+      if (sq >= kSq) { sq -= kSq; c += 1; }
+      if (c >= kPolicyCh) { c -= kPolicyCh; p += 1; }
+    }
+  }
+  if (npos > 0 && prm.priors != nullptr) {
+    for (int p = 0; p < npos; ++p) {
+      const int pos = pos0 + p, base = p * kRow;
+      int beg, end;
+      if (prm.move_stride > 0) { beg = pos * prm.move_stride; end = beg + max(prm.move_off[pos], 0); }
+      else { beg = prm.move_off[pos]; end = prm.move_off[pos + 1]; }
+      float m = -INFINITY;
+      for (int j = beg + lane; j < end; j += 32) m = fmaxf(m, staged(base + prm.move_idx[j]));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      float sum = 0.f;
+      for (int j = beg + lane; j < end; j += 32) sum += __expf(staged(base + prm.move_idx[j]) - m);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float inv = sum > 0.f ? 1.f / sum : 0.f;
+      for (int j = beg + lane; j < end; j += 32) prm.priors[j] = __expf(staged(base + prm.move_idx[j]) - m) * inv;
+    }
+  }
+  if (npos > 0 && prm.probs != nullptr) {
+    for (int p = 0; p < npos; ++p) {
+      const int base = p * kRow;
+      const uint8_t* mk = prm.mask + static_cast<size_t>(pos0 + p) * kRow;
+      float* out = prm.probs + static_cast<size_t>(pos0 + p) * kRow;
+      float m = -INFINITY;
+      for (int i = lane; i < kRow; i += 32) if (mk[i]) m = fmaxf(m, staged(base + i));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      float sum = 0.f;
+      for (int i = lane; i < kRow; i += 32) if (mk[i]) sum += __expf(staged(base + i) - m);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float inv = sum > 0.f ? 1.f / sum : 0.f;
+      for (int i = lane; i < kRow; i += 32) out[i] = mk[i] ? __expf(staged(base + i) - m) * inv : 0.f;
+    }
+  }
+  __syncwarp();
+  constexpr int kStripsUsed = (kPolicyCh + 4) / 5;                       // 14 of the planes hold staged logits
+  constexpr int kPadRows = kRowsValid / 6 + (kTile - kRowsValid);        // 20 sixth-column rows + 8 rows past the board
+  for (int i = lane; i < kStripsUsed * kPadRows; i += 32) {
+    const int strip = i / kPadRows, k = i % kPadRows;
+    const int prow = k < kRowsValid / 6 ? k * 6 + 5 : kRowsValid + (k - kRowsValid / 6);
+    *reinterpret_cast<uint4*>(stage + strip * kPlaneBytes + prow * 16) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  ptx::fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    ptx::mbar_arrive(&bar_in_empty[g * 2 + 0]);
+    ptx::mbar_arrive(&bar_in_empty[g * 2 + 1]);
+  }
+}
+
 struct SmemLayout {
   static constexpr int ring = 0;
   __host__ __device__ static constexpr int act(int nstages) { return ring + nstages * kStageBytes; }
@@ -263,7 +358,8 @@ tower_kernel(const Params prm) {
   uint64_t* bar_in_full = bar_act_part + 8;           // [2 groups][2 plane halves] leader only: stem input slice written
   uint64_t* bar_in_empty = bar_in_full + 4;           // [2][2] that half of the planes may be overwritten
   uint64_t* bar_v = bar_in_empty + 4;                 // [2] value-conv partials of a group written by all 8 warps
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_v + 2);
+  uint64_t* bar_p = bar_v + 2;                        // [2] logits of a group staged in shared memory by all 8 warps
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_p + 2);
   volatile uint32_t* s_apos = s_tmem + 1;             // chunks issued so far by group A's issuer
 
   const int warp = threadIdx.x >> 5;
@@ -298,6 +394,7 @@ tower_kernel(const Params prm) {
         ptx::mbar_init(&bar_in_empty[g * 2 + hh], 1);
       }
       ptx::mbar_init(&bar_v[g], 8);
+      ptx::mbar_init(&bar_p[g], 8);
     }
     ptx::fence_mbar_init();
   }
@@ -318,11 +415,13 @@ tower_kernel(const Params prm) {
   if (kProf && blockIdx.x == 0 && threadIdx.x == 0) { prm.prof[12] = t_entry; prm.prof[13] = clock64(); }
 
   if (warp == 8) {
-    // ===== weight producer: this CTA's half (64 output channels) of every chunk ==================
-    if (lane == 0) {
-      uint32_t s = 0, ph = 1;
-      long long t_wait = 0;
-      for (int pr = pair0; pr < npair_rounds; pr += pair_stride) {
+    // ===== weight producer: this CTA's half (64 output channels) of every chunk; then, with the round's last chunk on
+    // its way, the policy tails of the round's groups (this warp holds no epilogue state, so the tail costs the epilogue
+    // warps neither registers nor time) ==================
+    uint32_t s = 0, ph = 1, round_seq = 0;
+    long long t_wait = 0;
+    for (int pr = pair0; pr < npair_rounds; pr += pair_stride, ++round_seq) {
+      if (lane == 0) {
         for (uint32_t c = 0; c < nchunks; ++c) {
           const Chunk ch = s_chunks[c];
           long long t0 = 0;
@@ -335,8 +434,17 @@ tower_kernel(const Params prm) {
           if (++s == nstages) { s = 0; ph ^= 1; }
         }
       }
-      if (kProf && blockIdx.x == 0) prm.prof[8] = t_wait;
+      __syncwarp();
+      if (prm.tail && nl == prm.nlayers) {
+        const int r = pr * 2 + static_cast<int>(rank);
+        const bool has_b = G::kGroups == 2 && prm.pos_per_round == kPosPerRound && pr * 2 * kPosPerRound + kPosPerGroup < prm.n;
+        for (int g = 0; g < (has_b ? 2 : 1); ++g) {
+          ptx::mbar_wait(&bar_p[g], round_seq & 1);
+          policy_tail<F>(prm, s_act, bar_in_empty, g, r * prm.pos_per_round + g * kPosPerGroup, lane);
+        }
+      }
     }
+    if (kProf && blockIdx.x == 0 && lane == 0) prm.prof[8] = t_wait;
   } else if (warp == 9 && rank == 1) {
     // ===== peer CTA: relay "my half of stage s has landed" to the leader's issuers ==================
     if (lane == 0) {
@@ -442,9 +550,9 @@ tower_kernel(const Params prm) {
             ptx::umma_commit_2sm(&bar_in_empty[g * 2 + (stem_idx & 1)], 3);   // a later slice reuses this half
           if (ch.flags & kLastOfLayer) {
             ptx::umma_commit_2sm(&bar_tmem_full[g], 3);
-            if (ch.layer == nl - 1) {   // round end: both halves are free for the next round's input
-              ptx::umma_commit_2sm(&bar_in_empty[g * 2 + 0], 3);
-              ptx::umma_commit_2sm(&bar_in_empty[g * 2 + 1], 3);
+            if (ch.layer == nl - 1 && !(prm.tail && nl == prm.nlayers)) {   // round end: both halves are free for the next
+              ptx::umma_commit_2sm(&bar_in_empty[g * 2 + 0], 3);              // round's input (when the policy tail runs, it
+              ptx::umma_commit_2sm(&bar_in_empty[g * 2 + 1], 3);              // stages the logits in these planes and releases them)
             }
           }
         }
@@ -594,7 +702,7 @@ tower_kernel(const Params prm) {
                   f[u][e] = (live && (pl0 + c8) * 8 + e < prm.in_planes) ? __ldg(src + e * kSq) : 0.f;
               } else {
                 // packed planes: x[c][sq] = bit sq of bits[c] ? scale[c] : 0
-                const size_t o = static_cast<size_t>(pos0 + p) * prm.in_planes + (pl0 + c8) * 8;
+                const size_t o = static_cast<size_t>(pos0 + p) * prm.packed_stride + (pl0 + c8) * 8;
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                   const bool ok = live && (pl0 + c8) * 8 + e < prm.in_planes;
@@ -660,23 +768,49 @@ tower_kernel(const Params prm) {
             if (lane == 0 && do_value) ptx::mbar_arrive(&bar_v[g]);
           }
         } else {
-          // policy 1x1 output: fp32 logits straight to HBM, index c*25 + sq (Flatten of NCHW)
-          const int pos = pos_base + bp;
-          const bool out_valid = row_valid && pos < prm.n;
-          float* dst = prm.policy + static_cast<size_t>(pos) * (kPolicyCh * kSq) + sq;
+          // policy 1x1 output: fp32 logits, index c*25 + sq (Flatten of NCHW)
+          if (!prm.tail) {
+            // ... straight to HBM from the accumulator registers
+            const int pos = pos_base + bp;
+            const bool out_valid = row_valid && pos < prm.n && prm.policy != nullptr;
+            float* dst = prm.policy + static_cast<size_t>(pos) * (kPolicyCh * kSq) + sq;
 #pragma unroll
-          for (int cb = 0; cb < G::kCb; ++cb) {
-            if (h * G::kHalfCh + cb * 32 >= kPolicyN) break;  // columns beyond the padded policy width do not exist
-            uint32_t v[32];
-            ptx::tmem_ld_32x32b_x32(taddr + cb * 32, v);
-            ptx::tmem_ld_wait();
-            if (out_valid) {
+            for (int cb = 0; cb < G::kCb; ++cb) {
+              if (h * G::kHalfCh + cb * 32 >= kPolicyN) break;  // columns beyond the padded policy width do not exist
+              uint32_t v[32];
+              ptx::tmem_ld_32x32b_x32(taddr + cb * 32, v);
+              ptx::tmem_ld_wait();
+              if (out_valid) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const int c = h * G::kHalfCh + cb * 32 + j;
-                if (c < kPolicyCh) dst[c * kSq] = __uint_as_float(v[j]) + bias[cb * 32 + j];
+                for (int j = 0; j < 32; ++j) {
+                  const int c = h * G::kHalfCh + cb * 32 + j;
+                  if (c < kPolicyCh) dst[c * kSq] = __uint_as_float(v[j]) + bias[cb * 32 + j];
+                }
               }
             }
+          } else {
+            // ... staged in the group's activation planes (nothing reads those any more: this layer's MMAs, their last
+            // readers, are complete) for the policy tail
+            uint8_t* stage_row = s_act + group_origin_row(g) * 16 + (bp * kSq + sq) * 4;
+#pragma unroll
+            for (int cb = 0; cb < G::kCb; ++cb) {
+              if (h * G::kHalfCh + cb * 32 >= kPolicyN) break;
+              uint32_t v[32];
+              ptx::tmem_ld_32x32b_x32(taddr + cb * 32, v);
+              ptx::tmem_ld_wait();
+              if (row_valid) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  // (h is 0 or 1: both offsets are compile-time constants, selected per thread)
+                  const int c0 = cb * 32 + j, c1 = G::kHalfCh + cb * 32 + j;
+                  if (h == 0 ? c0 < kPolicyCh : c1 < kPolicyCh)
+                    *reinterpret_cast<float*>(stage_row + (h == 0 ? stage_offset<F>(c0) : stage_offset<F>(c1 < kPolicyCh ? c1 : 0))) =
+                        __uint_as_float(v[j]) + bias[cb * 32 + j];
+                }
+              }
+            }
+            __syncwarp();
+            if (lane == 0 && do_value) ptx::mbar_arrive(&bar_p[g]);
           }
           // no activations written, but keep the per-layer barrier phases in step
           ptx::tc_fence_before_sync();
@@ -918,7 +1052,7 @@ inline cudaError_t set_weights(State& s, const std::vector<std::vector<float>>& 
 
   s.nchunks = static_cast<int>(chunks.size());
   const size_t fixed = geo.act_bytes + (geo.bias_in_smem ? static_cast<size_t>(s.nlayers) * F * 4 : 0) + F * 4 +
-                       4 * kPosPerGroup * kSq * 4 + chunks.size() * sizeof(Chunk) + (2 * kMaxStages + 22) * 8 + 16;
+                       4 * kPosPerGroup * kSq * 4 + chunks.size() * sizeof(Chunk) + (2 * kMaxStages + 24) * 8 + 16;
   s.nstages = static_cast<int>(std::min<size_t>(kMaxStages, (232448 - std::min<size_t>(fixed, 232448)) / kStageBytes));
   s.smem_bytes = fixed + static_cast<size_t>(s.nstages) * kStageBytes;
   s.attr_set = false;
@@ -926,10 +1060,17 @@ inline cudaError_t set_weights(State& s, const std::vector<std::vector<float>>& 
 }
 
 // nlayers_run < nlayers: stop after that many layers and leave the packed activations in d_dbg.
-struct PackedInput { const uint32_t* bits = nullptr; const float* scale = nullptr; };
+struct PackedInput { const uint32_t* bits = nullptr; const float* scale = nullptr; int stride = 0; };   // stride 0 = in_planes
+// What the fused policy tail produces besides (or instead of) the raw logits; see Params.
+struct PolicyTail {
+  const int32_t* move_off = nullptr; const uint16_t* move_idx = nullptr; float* priors = nullptr; int move_stride = 0;
+  const uint8_t* mask = nullptr; float* probs = nullptr;
+  bool rows = false;   // write `policy` through the tail as whole rows (for mapped host memory) even if nothing else is wanted
+};
 
 inline cudaError_t run(State& s, const float* d_planes, int n, float* d_policy, float* d_value, int nlayers_run,
-                       cudaStream_t stream, int* launched, std::string* why, PackedInput packed = PackedInput()) {
+                       cudaStream_t stream, int* launched, std::string* why, PackedInput packed = PackedInput(),
+                       PolicyTail tail = PolicyTail()) {
   if (!supported(s)) { *why = "the tcgen05 path supports 128 or 256 filters"; return cudaSuccess; }
   if (s.nstages < 3) { *why = "network too deep for the shared-memory layer tables"; return cudaSuccess; }
   if (!s.attr_set) {
@@ -950,10 +1091,13 @@ inline cudaError_t run(State& s, const float* d_planes, int n, float* d_policy, 
   p.wimg = s.d_wimg; p.chunks = s.d_chunks; p.layers = s.d_layers; p.bias = s.d_bias;
   p.value_w = s.heads.d_value_w; p.fc1_k = s.heads.d_fc1_k; p.fc1_b = s.heads.d_fc1_b; p.fc2_k = s.heads.d_fc2_k;
   p.value_b = s.heads.value_b; p.fc2_b = s.heads.fc2_b;
-  p.planes = d_planes; p.bits = packed.bits; p.scale = packed.scale; p.in_planes = s.in_planes; p.in_planes8 = s.in_planes8; p.nslices = s.nslices;
+  p.planes = d_planes; p.bits = packed.bits; p.scale = packed.scale; p.packed_stride = packed.stride ? packed.stride : s.in_planes; p.in_planes = s.in_planes; p.in_planes8 = s.in_planes8; p.nslices = s.nslices;
   p.nstages = s.nstages; p.nchunks_total = s.nchunks; p.lag = std::min(s.lag, s.nstages - 2);
   p.nlayers = s.nlayers; p.nlayers_run = nlayers_run; p.n = n; p.nrounds = rounds; p.pos_per_round = ppr;
   p.policy = d_policy; p.value = d_value;
+  p.move_off = tail.move_off; p.move_idx = tail.move_idx; p.priors = tail.priors; p.move_stride = tail.move_stride;
+  p.mask = tail.mask; p.probs = tail.probs;
+  p.tail = (tail.priors != nullptr || tail.probs != nullptr || tail.rows) ? 1 : 0;
   p.dbg = nlayers_run < s.nlayers ? s.d_dbg : nullptr;
   p.prof = s.d_prof;
   const int pairs = std::min((rounds + 1) / 2, std::max(1, s.sms / 2));
@@ -974,13 +1118,14 @@ inline cudaError_t run(State& s, const float* d_planes, int n, float* d_policy, 
 }
 
 inline cudaError_t forward(State& s, const float* d_planes, int n, float* d_policy, float* d_value,
-                           cudaStream_t stream, int* launched, std::string* why) {
-  return run(s, d_planes, n, d_policy, d_value, s.nlayers, stream, launched, why);
+                           cudaStream_t stream, int* launched, std::string* why, PolicyTail tail = PolicyTail()) {
+  return run(s, d_planes, n, d_policy, d_value, s.nlayers, stream, launched, why, PackedInput(), tail);
 }
 
 inline cudaError_t forward_packed(State& s, const uint32_t* d_bits, const float* d_scale, int n, float* d_policy,
-                                  float* d_value, cudaStream_t stream, int* launched, std::string* why) {
-  return run(s, nullptr, n, d_policy, d_value, s.nlayers, stream, launched, why, PackedInput{d_bits, d_scale});
+                                  float* d_value, cudaStream_t stream, int* launched, std::string* why, int stride = 0,
+                                  PolicyTail tail = PolicyTail()) {
+  return run(s, nullptr, n, d_policy, d_value, s.nlayers, stream, launched, why, PackedInput{d_bits, d_scale, stride}, tail);
 }
 
 // Activations after `nconv` 3x3 convolutions (1 = stem ... 1+2*blocks = trunk) as fp32 NCHW.

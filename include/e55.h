@@ -302,6 +302,12 @@ int e55_get_kernel_timing(e55_ctx* ctx, double* total_ms_out, int64_t* launches_
  * host, computed by the currently selected precision path. */
 int e55_debug_activations(e55_ctx* ctx, const float* planes, int n, int n_convs, float* act_out);
 
+/* Debug/verification: the stand-alone legal-move softmax kernel (the fp32 path's policy tail) on caller-supplied logits
+ * float32 [n,1725]; same arguments as e55_predict_packed_moves.  The tensor-core path computes the same priors inside
+ * the tower kernel (the logits never leave shared memory); tests hold the two against each other bit for bit. */
+int e55_debug_legal_priors(e55_ctx* ctx, const float* logits, int n, const int32_t* move_offset, const uint16_t* move_index,
+                           float* priors);
+
 /* Tuning: number of weight chunks the tower kernel keeps group A's MMA issuer ahead of group B's
  * (0 = free running; clamped to ring depth - 1). */
 int e55_debug_set_lag(e55_ctx* ctx, int lag);

@@ -327,6 +327,10 @@ def test_legal_move_priors_match_the_host_softmax(weights_perturbed):
                 continue
             e = np.exp(logits[b, l].astype(np.float64) - logits[b, l].max())
             assert np.abs(got - e / e.sum()).max() < 2e-6 and abs(got.sum() - 1) < 1e-5
+        # the tower kernel's fused tail == the stand-alone softmax kernel on the same logits, bit for bit
+        alone = np.empty_like(priors)
+        net._check(net._lib.e55_debug_legal_priors(net._ctx, logits.ctypes.data, len(lists), off.ctypes.data, idx.ctypes.data, alone.ctypes.data))
+        assert np.array_equal(alone, priors)
 
     check(*net.predict_packed_moves(bits, scale, off, idx))
     net.set_precision("fp32")
