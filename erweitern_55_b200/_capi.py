@@ -60,7 +60,9 @@ SIGNATURES = {
 
 class SelfplayStats(C.Structure):
     _fields_ = [("seconds", C.c_double), ("moves", C.c_long), ("evals", C.c_long), ("games", C.c_long),
-                ("mean_game_plies", C.c_double), ("mean_gpu_batch", C.c_double)]
+                ("mean_game_plies", C.c_double), ("mean_gpu_batch", C.c_double),
+                ("tree_overflows", C.c_long), ("searches_suspended", C.c_long), ("mate_searches", C.c_long),
+                ("mate_exhausted", C.c_long), ("records_truncated", C.c_long)]
 
 
 GAME_SINK = C.CFUNCTYPE(None, C.c_void_p, C.c_char_p)
@@ -117,6 +119,10 @@ SIGNATURES.update({
     "e55_mcts_search_batches": (C.c_int, [_mcts, _ctx, _pos, C.c_int, C.c_int, C.c_int, C.c_int]),
     "e55_gpu_selfplay_run": (C.c_int, [_ctx, C.c_int, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.POINTER(SelfplayStats),
                                        C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
+    "e55_gpu_search_open": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "e55_gpu_search_close": (None, [C.c_void_p]),
+    "e55_gpu_search_select": (C.c_int, [C.c_void_p] + [C.c_void_p] * 8),
+    "e55_gpu_search_expand": (C.c_int, [C.c_void_p] + [C.c_void_p] * 4),
     "e55_selftest_engine": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int64)]),
     "e55_selftest_encode": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "e55_selfplay_default_config": (None, [C.POINTER(SelfplayConfig)]),

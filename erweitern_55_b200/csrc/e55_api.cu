@@ -545,7 +545,11 @@ int e55_set_weights(e55_ctx* c, int n_tensors, const float* const* data, const i
     return fail(c, E55_ERR_INVALID, "a head layer is missing from the weight list");
 
   E55_CUDA(c, cudaSetDevice(c->device));
+  // nothing may still read the old weight images: the context stream, the host pipeline's chunk streams and (the
+  // service's batches run on streams of their own) the whole device
   E55_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < e55_ctx::kPipeStreams; ++i) E55_CUDA(c, cudaStreamSynchronize(c->pipe_stream[i]));
+  E55_CUDA(c, cudaDeviceSynchronize());
   free_weights(c);
 
   std::vector<float> w, b;
@@ -899,24 +903,26 @@ int e55_predict_packed(e55_ctx* c, const uint32_t* bits, const float* scale, int
   const size_t in_pp = static_cast<size_t>(c->in_planes), pol_pp = static_cast<size_t>(kPolicyCh) * kSq;
   constexpr int kChunk = kPipeChunk;
   const bool pipelined = c->precision == E55_PRECISION_BF16_TC && n >= 2 * kChunk;
-  if (pipelined) E55_CUDA(c, cudaEventRecord(c->pipe_start, c->stream));
+  cudaError_t e = pipelined ? cudaEventRecord(c->pipe_start, c->stream) : cudaSuccess;
   int used = 0;
-  for (int off = 0, i = 0, m = 0; off < n; off += m, ++i) {
+  for (int off = 0, i = 0, m = 0; off < n && e == cudaSuccess && rc == E55_OK; off += m, ++i) {
     m = pipelined ? pipe_chunk(n - off, kChunk) : n;   // one-group-per-CTA kernels of <= 256 positions, two at a time
     cudaStream_t st = pipelined ? c->pipe_stream[i % e55_ctx::kPipeStreams] : c->stream;
-    if (pipelined && i < e55_ctx::kPipeStreams) { E55_CUDA(c, cudaStreamWaitEvent(st, c->pipe_start, 0)); used = i + 1; }
-    E55_CUDA(c, cudaMemcpyAsync(c->d_bits + off * in_pp, bits + off * in_pp, m * in_pp * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    E55_CUDA(c, cudaMemcpyAsync(c->d_scale + off * in_pp, scale + off * in_pp, m * in_pp * sizeof(float), cudaMemcpyHostToDevice, st));
-    if ((rc = forward_packed_on(c, st, c->d_bits + off * in_pp, c->d_scale + off * in_pp, m, off, c->d_policy + off * pol_pp,
-                                c->d_value + off))) return rc;
-    E55_CUDA(c, cudaMemcpyAsync(policy + off * pol_pp, c->d_policy + off * pol_pp, m * pol_pp * sizeof(float), cudaMemcpyDeviceToHost, st));
-    E55_CUDA(c, cudaMemcpyAsync(value + off, c->d_value + off, m * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (pipelined && i < e55_ctx::kPipeStreams) { e = cudaStreamWaitEvent(st, c->pipe_start, 0); used = i + 1; }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_bits + off * in_pp, bits + off * in_pp, m * in_pp * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_scale + off * in_pp, scale + off * in_pp, m * in_pp * sizeof(float), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) rc = forward_packed_on(c, st, c->d_bits + off * in_pp, c->d_scale + off * in_pp, m, off, c->d_policy + off * pol_pp, c->d_value + off);
+    if (e == cudaSuccess && rc == E55_OK) e = cudaMemcpyAsync(policy + off * pol_pp, c->d_policy + off * pol_pp, m * pol_pp * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && rc == E55_OK) e = cudaMemcpyAsync(value + off, c->d_value + off, m * sizeof(float), cudaMemcpyDeviceToHost, st);
   }
-  for (int i = 0; i < used; ++i) {
-    E55_CUDA(c, cudaEventRecord(c->pipe_done[i], c->pipe_stream[i]));
-    E55_CUDA(c, cudaStreamWaitEvent(c->stream, c->pipe_done[i], 0));
+  for (int i = 0; i < used && e == cudaSuccess && rc == E55_OK; ++i) {
+    e = cudaEventRecord(c->pipe_done[i], c->pipe_stream[i]);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(c->stream, c->pipe_done[i], 0);
   }
-  E55_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (e == cudaSuccess && rc == E55_OK) e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess || rc != E55_OK) sync_pipe_streams(c);   // nothing of this call may still be in flight when the caller gets its buffers back
+  if (rc != E55_OK) return rc;
+  E55_CUDA(c, e);
   return E55_OK;
 }
 

@@ -657,6 +657,7 @@ int e55_selfplay_run_ex(e55_ctx* c, const e55_selfplay_config* cfg_in, e55_selfp
     th.emplace_back([&workers, i] { workers[i].run(); });
   }
   for (auto& t : th) t.join();
+  *out = e55_selfplay_stats{};
   out->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   if (getenv("E55_SERVICE_TRACE")) {
     rusage ru1{};

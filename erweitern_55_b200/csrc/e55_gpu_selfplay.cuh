@@ -32,7 +32,9 @@ using namespace mshogi;
 constexpr int kLeaf = 16;              // network slots per game per round (Config.batch_size, mcts.py:13)
 constexpr int kMaxSel = 24;            // selections per game per round: until the 16 slots are filled, at most this many
 constexpr int kMaxPly = 512;           // selfplay.run's max_moves
-constexpr int kMaxNodes = 1792;        // per game and pool: the subtree kept from the last search + one new node per simulation
+constexpr int kMaxNodes = 4096;        // per game and pool: the subtree kept from the last search + one new node per simulation
+constexpr int kNodesSuspend = kMaxNodes * 9 / 10 - kMaxSel;    // mcts.py:72: "if the memory is used over 90%, suspend the search"
+constexpr int kEdgesSuspend = 112 * 1024 * 9 / 10 - kMaxSel * 256;
 constexpr int kMaxEdges = 112 * 1024;  // per game and pool (late positions with pieces in hand have 100+ legal moves)
 constexpr int kMoveStride = 256;       // move-list slots per batch position (MoveList capacity: nothing is ever cut)
 constexpr int kMaxPath = 96;           // deepest descent below the root
@@ -82,12 +84,15 @@ struct Game {
   int32_t n_sel;
   int32_t games_finished;
   int32_t rec_words;                   // words of the game's record written so far
+  int32_t rec_truncated;               // the record buffer was too small: a ply or its visit list is missing
   int32_t need_mate;                   // the mate search of the move about to be searched is still to come (from the host)
   uint32_t req_seq;                    // number of the game's latest mate-search request
 };
 
 struct Shared {                        // counters of the whole run
   unsigned long long moves, evals, games, plies_in_finished_games, pool_overflows, selections, kept_nodes, mate_moves;
+  unsigned long long searches_suspended;   // searches ended early because a tree pool was over 90 % full (mcts.py:72)
+  unsigned long long records_truncated;    // finished games whose record did not fit the record buffer
   int n_records;
 };
 
@@ -325,28 +330,34 @@ __device__ inline void keep_subtree(Game& g, const Params& p, int gi, int new_ro
 
 // One ply of the game record, as selfplay.run keeps it (selfplay.py:80-92; gamerecord.py:5): the move, then
 // search.dump(root) = (sum_N, Q, [(move, N), ...]) -- four words (move, sum_N, Q * 65535, k) and k (move, N) pairs.
-// A mate-search move is (1, 1.0, [(move, 1)]).  A record that would not fit loses its visit lists (k = 0), not its moves.
+// A mate-search move is (1, 1.0, [(move, 1)]).  A record that does not fit its buffer (16 384 words: ~350 plies at 20
+// visited moves each) first loses visit lists (k = 0), then plies; either way the finished record carries a flag
+// (header word 3), its reader reports it as incomplete and keeps the plies without visits out of the learning targets.
 __device__ inline void record_ply(Game& g, const Params& p, int gi, uint16_t mv, const GNode* root, const GEdge* edges) {
   if (!p.rec_buf) return;
+  constexpr int kCap = kRecordWords - 4;            // finish_game puts a four-word header in front
   uint16_t* rec = p.rec_buf + static_cast<size_t>(gi) * kRecordWords;
   int w = g.rec_words;
-  if (w + 4 > kRecordWords - 4) return;
   int k = 0, sum_n = 0;
   float wsum = 0.f;
   if (root)
     for (int i = 0; i < root->n_edges; ++i) { const GEdge& e = edges[root->first_edge + i]; sum_n += e.n; wsum += e.w; k += e.n > 0; }
-  const bool fits = w + 4 + 2 * k <= kRecordWords - 4;
+  else
+    k = 1;                                          // a mate-search move: (1, 1.0, [(move, 1)])
+  if (w + 4 > kCap) { g.rec_truncated = 1; return; }   // not even the move fits: the record ends here (flagged)
+  const bool fits = w + 4 + 2 * k <= kCap;
+  if (!fits) g.rec_truncated = 1;                   // the move is kept, its visit list is not (k = 0)
   rec[w++] = mv;
   rec[w++] = static_cast<uint16_t>(root ? (sum_n > 65535 ? 65535 : sum_n) : 1);
   rec[w++] = static_cast<uint16_t>(root ? (sum_n > 0 ? wsum / static_cast<float>(sum_n) : root->value) * 65535.f + 0.5f : 65535.f);
-  if (!root) { rec[w++] = 1; rec[w++] = mv; rec[w++] = 1; }
-  else if (!fits) rec[w++] = 0;
-  else {
-    rec[w++] = static_cast<uint16_t>(k);
-    for (int i = 0; i < root->n_edges; ++i) {
-      const GEdge& e = edges[root->first_edge + i];
-      if (e.n > 0) { rec[w++] = e.mv; rec[w++] = static_cast<uint16_t>(e.n > 65535 ? 65535 : e.n); }
-    }
+  rec[w++] = static_cast<uint16_t>(fits ? k : 0);
+  if (fits) {
+    if (!root) { rec[w++] = mv; rec[w++] = 1; }
+    else
+      for (int i = 0; i < root->n_edges; ++i) {
+        const GEdge& e = edges[root->first_edge + i];
+        if (e.n > 0) { rec[w++] = e.mv; rec[w++] = static_cast<uint16_t>(e.n > 65535 ? 65535 : e.n); }
+      }
   }
   g.rec_words = w;
 }
@@ -378,12 +389,15 @@ __device__ inline void finish_game(Game& g, const Params& p, int gi, GNode* node
       const uint16_t* rec = p.rec_buf + static_cast<size_t>(gi) * kRecordWords;
       out[0] = static_cast<uint16_t>(g.root.ply);
       out[1] = static_cast<uint16_t>(winner);
-      out[2] = static_cast<uint16_t>(g.rec_words);
-      out[3] = 0;
-      for (int i = 0; i < g.rec_words; ++i) out[4 + i] = rec[i];
+      const int words = g.rec_words < kRecordWords - 4 ? g.rec_words : kRecordWords - 4;
+      out[2] = static_cast<uint16_t>(words);
+      out[3] = static_cast<uint16_t>(g.rec_truncated ? 1 : 0);
+      for (int i = 0; i < words; ++i) out[4 + i] = rec[i];
     }
+    if (g.rec_truncated) atomicAdd(&p.shared->records_truncated, 1ull);
   }
   g.rec_words = 0;
+  g.rec_truncated = 0;
   ++g.games_finished;
   start_game(g, nodes);
 }
@@ -409,7 +423,18 @@ __global__ void init_kernel(Params p, uint64_t seed) {
   g.pool = 0;
   g.req_seq = 0;
   g.rec_words = 0;
+  g.rec_truncated = 0;
   start_game(g, p.nodes + static_cast<size_t>(gi) * 2 * kMaxNodes);
+  request_mate(g, p, gi);
+}
+
+// Debug stepper (e55_gpu_search_*): the moves of `prefix` are played on every game before its first search.
+__global__ void prefix_kernel(Params p, const uint16_t* prefix, int n_prefix) {
+  const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= p.n_games) return;
+  Game& g = p.games[gi];
+  for (int i = 0; i < n_prefix; ++i) game_play(g, unpack_move(prefix[i]));
+  reset_tree(g, p.nodes + (static_cast<size_t>(gi) * 2 + g.pool) * kMaxNodes);
   request_mate(g, p, gi);
 }
 
@@ -452,6 +477,14 @@ __global__ void __launch_bounds__(64) select_kernel(Params p) {
   }
   if (g.need_mate && (!p.speculate || g.sims_done >= p.simulations || (g.sims_done >= 0 && nodes[0].terminal))) return;
   if (g.sims_done >= p.simulations) return;   // the answer was all that was missing: expand_kernel ends the search
+  // mcts.py:71-73: "If the memory is used over 90%, suspend the search" -- the tree pools of a game are its memory.  The
+  // search ends with the simulations done so far (expand_kernel chooses the move from them); nothing ever overflows.
+  if (g.sims_done >= 0 && (g.n_nodes > kNodesSuspend || g.n_edges > kEdgesSuspend)) {
+    atomicAdd(&p.shared->searches_suspended, 1ull);
+    g.sims_done = p.simulations;
+    g.n_sel = 0;
+    return;
+  }
   PathView pv;
   MoveList moves;
   // A round selects until the game's 16 network slots are filled (selections that end in an expanded, terminal or
@@ -472,13 +505,18 @@ __global__ void __launch_bounds__(64) select_kernel(Params p) {
       const uint4* raw = reinterpret_cast<const uint4*>(ed);
       int total = 0;
       for (int i = 0; i < nd.n_edges; ++i) { const uint4 r = raw[i]; total += static_cast<int>(r.z) + static_cast<int>(r.w >> 16); }
-      const float cs = p.c_puct * sqrtf(static_cast<float>(total) + 1e-8f);
+      // Q + c_puct P sqrt(sum N) / (1 + N), virtual losses counting as visits worth nothing: the very expression, in the
+      // very order of operations, of Mcts::select_leaf (csrc/mcts.hpp) and oracle/mcts_oracle.py -- the three trees take
+      // the same path bit for bit (tests/test_gpu_parity.py::test_gpu_search_walks_like_the_oracle)
+      const float sq = sqrtf(static_cast<float>(total) + 1e-8f);
       int best = 0;
       float best_score = -1e30f;
       for (int i = 0; i < nd.n_edges; ++i) {
         const uint4 r = raw[i];
-        const float nv = static_cast<float>(static_cast<int>(r.z) + static_cast<int>(r.w >> 16));
-        const float score = __uint_as_float(r.y) / fmaxf(nv, 1.f) + cs * __uint_as_float(r.x) / (1.f + nv);
+        const int nvi = static_cast<int>(r.z) + static_cast<int>(r.w >> 16);
+        const float nv = static_cast<float>(nvi);
+        const float q = nvi > 0 ? __fdiv_rn(__uint_as_float(r.y), nv) : 0.f;
+        const float score = __fadd_rn(q, __fdiv_rn(__fmul_rn(__fmul_rn(p.c_puct, __uint_as_float(r.x)), sq), __fadd_rn(1.f, nv)));
         if (score > best_score) { best_score = score; best = i; }
       }
       GEdge& e = ed[best];
@@ -492,7 +530,16 @@ __global__ void __launch_bounds__(64) select_kernel(Params p) {
       const bool check = ch >= 0 && nodes[ch].expanded ? nodes[ch].in_check != 0 : pos.in_check(pos.side);
       path_push(pv, pos, key, check);
       if (ch < 0) {
-        if (g.n_nodes >= kMaxNodes) { atomicAdd(&p.shared->pool_overflows, 1ull); node = -1; break; }
+        if (g.n_nodes >= kMaxNodes) {
+          // (cannot happen while searches are suspended at 90 %; kept as a safety net that leaves the tree consistent:
+          // the virtual loss of the abandoned descent is taken back, and expand_kernel does not count the selection)
+          atomicAdd(&p.shared->pool_overflows, 1ull);
+          --e.vloss;
+          for (int up = node; nodes[up].parent >= 0; up = nodes[up].parent)
+            if (edges[nodes[up].parent_edge].vloss > 0) --edges[nodes[up].parent_edge].vloss;
+          node = -1;
+          break;
+        }
         ch = g.n_nodes++;
         GNode& nn = nodes[ch];
         nn.parent = node; nn.parent_edge = nd.first_edge + best; nn.first_edge = 0; nn.n = 0; nn.value = 0.5f; nn.n_edges = 0;
@@ -581,9 +628,11 @@ __global__ void __launch_bounds__(64) expand_kernel(Params p) {
       root_noise(g, leaf, edges, p.priors + slot * kMoveStride, p.dirichlet_alpha, p.dirichlet_eps);
   }
   // back every selection up (Mcts::backpropagate)
+  int done = 0;
   for (int s = 0; s < g.n_sel; ++s) {
     int node = g.leaf[s];
-    if (node < 0) continue;
+    if (node < 0) continue;              // a descent abandoned for lack of room is not a simulation
+    ++done;
     float v = nodes[node].value;
     ++nodes[node].n;
     while (nodes[node].parent >= 0) {
@@ -599,7 +648,7 @@ __global__ void __launch_bounds__(64) expand_kernel(Params p) {
   if (evaluated) atomicAdd(&p.shared->evals, static_cast<unsigned long long>(evaluated));
   atomicAdd(&p.shared->selections, static_cast<unsigned long long>(g.n_sel));
   if (root_round) { g.sims_done = 0; if (!nodes[0].terminal) return; }   // the root evaluation is not a simulation (mcts.py:55-60)
-  else g.sims_done += g.n_sel;
+  else g.sims_done += done;
   if (g.sims_done < p.simulations && !nodes[0].terminal) return;
   if (g.need_mate) return;             // a mate found by the host goes first (select_kernel)
 

@@ -109,6 +109,152 @@ int e55_selftest_encode(int device, int n, uint64_t seed, int64_t* mismatches_ou
   return E55_OK;
 }
 
+// ---- debug stepper: ONE game's search, a round at a time, with the caller playing the network ---------------------------
+// (tests hold select_kernel / expand_kernel to oracle/mcts_oracle.py selection by selection with it)
+struct e55_gpu_search {
+  e55_ctx* c = nullptr;
+  e55::gs::Params p{};
+  std::vector<void*> owned;
+  std::vector<e55::gs::GNode> nodes;
+  std::vector<e55::gs::GEdge> edges;
+  e55::gs::Game game;
+};
+
+int e55_gpu_search_open(e55_ctx* c, const uint16_t* prefix, int n_prefix, int simulations, int reuse_tree, e55_gpu_search** out) {
+  namespace gs = e55::gs;
+  if (!c || !out || n_prefix < 0 || (n_prefix > 0 && !prefix) || simulations < gs::kLeaf || simulations > 1024 || simulations % gs::kLeaf != 0)
+    return E55_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  E55_CUDA(c, cudaSetDevice(c->device));
+  E55_CUDA(c, device_engine_ready());
+  e55_gpu_search* h = new e55_gpu_search();
+  h->c = c;
+  gs::Params& p = h->p;
+  cudaError_t e = cudaSuccess;
+  auto chain = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+  uint16_t* d_prefix = nullptr;
+  unsigned long long* d_ans = nullptr;
+  chain(dev_alloc(p.games, 1, h->owned, c->stream));
+  chain(dev_alloc(p.nodes, 2 * gs::kMaxNodes, h->owned, c->stream));
+  chain(dev_alloc(p.edges, 2 * gs::kMaxEdges, h->owned, c->stream));
+  chain(dev_alloc(p.child, 2 * gs::kMaxEdges, h->owned, c->stream));
+  chain(dev_alloc(p.old_of, gs::kMaxNodes, h->owned, c->stream));
+  chain(dev_alloc(p.bits, gs::kLeaf * mshogi::kInputPlanes, h->owned, c->stream));
+  chain(dev_alloc(p.scale, gs::kLeaf * mshogi::kInputPlanes, h->owned, c->stream));
+  chain(dev_alloc(p.move_idx, gs::kLeaf * gs::kMoveStride, h->owned, c->stream));
+  chain(dev_alloc(p.move_cnt, gs::kLeaf, h->owned, c->stream));
+  chain(dev_alloc(p.priors, gs::kLeaf * gs::kMoveStride, h->owned, c->stream));
+  chain(dev_alloc(p.value, gs::kLeaf, h->owned, c->stream));
+  chain(dev_alloc(p.shared, 1, h->owned, c->stream));
+  chain(dev_alloc(p.rec_buf, gs::kRecordWords, h->owned, c->stream));
+  chain(dev_alloc(p.records, gs::kRecordWords, h->owned, c->stream));
+  chain(dev_alloc(p.req_board, 1, h->owned, c->stream));
+  chain(dev_alloc(p.req_seq, 1, h->owned, c->stream));
+  chain(dev_alloc(d_ans, 1, h->owned, c->stream));
+  chain(dev_alloc(d_prefix, static_cast<size_t>(std::max(n_prefix, 1)), h->owned, c->stream));
+  p.ans = d_ans;
+  p.n_games = 1; p.game0 = 0; p.simulations = simulations; p.use_dirichlet = 0; p.reuse_tree = reuse_tree; p.mate_depth = 0;
+  p.speculate = 0; p.sampling_moves = 0; p.max_moves = gs::kMaxPly; p.record_cap = 1; p.move_budget = 1 << 30;
+  p.c_puct = 1.25f; p.dirichlet_alpha = 0.15f; p.dirichlet_eps = 0.25f;
+  if (e == cudaSuccess && n_prefix > 0) e = cudaMemcpyAsync(d_prefix, prefix, n_prefix * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) {
+    gs::init_kernel<<<1, 64, 0, c->stream>>>(p, 1);
+    gs::prefix_kernel<<<1, 64, 0, c->stream>>>(p, d_prefix, n_prefix);
+    e = cudaStreamSynchronize(c->stream);
+  }
+  if (e != cudaSuccess) {
+    for (void* q : h->owned) cudaFree(q);
+    delete h;
+    return fail(c, E55_ERR_CUDA, std::string("GPU search stepper: ") + cudaGetErrorString(e));
+  }
+  h->nodes.resize(gs::kMaxNodes);
+  h->edges.resize(gs::kMaxEdges);
+  *out = h;
+  return E55_OK;
+}
+
+void e55_gpu_search_close(e55_gpu_search* h) {
+  if (!h) return;
+  cudaSetDevice(h->c->device);
+  cudaStreamSynchronize(h->c->stream);
+  for (void* q : h->owned) cudaFree(q);
+  delete h;
+}
+
+// One select_kernel round.  info[8] = {plies played, sims_done, n_sel, n_nodes, n_edges, games_finished, rec_words, 0};
+// per selection s < n_sel: sel_leaf[s] (node, -1 = abandoned), sel_slot[s] (network slot or -1), sel_path_len[s] and
+// sel_path[s*96 ..] (the moves from the root, packed); per slot k < 16: slot_cnt[k] legal moves, slot_moves[k*256 ..]
+// (packed, in edge order) and slot_idx[k*256 ..] (their policy indices).
+int e55_gpu_search_select(e55_gpu_search* h, int32_t* info, int32_t* sel_leaf, int32_t* sel_slot, int32_t* sel_path_len, uint16_t* sel_path,
+                          int32_t* slot_cnt, uint16_t* slot_moves, uint16_t* slot_idx) {
+  namespace gs = e55::gs;
+  if (!h || !info || !sel_leaf || !sel_slot || !sel_path_len || !sel_path || !slot_cnt || !slot_moves || !slot_idx) return E55_ERR_INVALID;
+  e55_ctx* c = h->c;
+  std::lock_guard<std::mutex> lk(c->mu);
+  E55_CUDA(c, cudaSetDevice(c->device));
+  gs::select_kernel<<<1, 64, 0, c->stream>>>(h->p);
+  ++c->launches;
+  E55_CUDA(c, cudaGetLastError());
+  E55_CUDA(c, cudaMemcpyAsync(&h->game, h->p.games, sizeof(gs::Game), cudaMemcpyDeviceToHost, c->stream));
+  E55_CUDA(c, cudaStreamSynchronize(c->stream));
+  const gs::Game& g = h->game;
+  E55_CUDA(c, cudaMemcpy(h->nodes.data(), h->p.nodes + static_cast<size_t>(g.pool) * gs::kMaxNodes, gs::kMaxNodes * sizeof(gs::GNode), cudaMemcpyDeviceToHost));
+  E55_CUDA(c, cudaMemcpy(h->edges.data(), h->p.edges + static_cast<size_t>(g.pool) * gs::kMaxEdges, gs::kMaxEdges * sizeof(gs::GEdge), cudaMemcpyDeviceToHost));
+  E55_CUDA(c, cudaMemcpy(slot_cnt, h->p.move_cnt, gs::kLeaf * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  E55_CUDA(c, cudaMemcpy(slot_idx, h->p.move_idx, gs::kLeaf * gs::kMoveStride * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+  info[0] = g.root.ply; info[1] = g.sims_done; info[2] = g.n_sel; info[3] = g.n_nodes; info[4] = g.n_edges; info[5] = g.games_finished;
+  info[6] = g.rec_words; info[7] = 0;
+  memset(slot_moves, 0, gs::kLeaf * gs::kMoveStride * sizeof(uint16_t));
+  for (int s = 0; s < g.n_sel; ++s) {
+    sel_leaf[s] = g.leaf[s];
+    sel_slot[s] = g.leaf_slot[s];
+    int len = 0;
+    uint16_t rev[gs::kMaxPath + 1];
+    for (int node = g.leaf[s]; node >= 0 && h->nodes[node].parent >= 0 && len <= gs::kMaxPath; node = h->nodes[node].parent)
+      rev[len++] = h->edges[h->nodes[node].parent_edge].mv;
+    sel_path_len[s] = len;
+    for (int i = 0; i < len; ++i) sel_path[s * gs::kMaxPath + i] = rev[len - 1 - i];
+    if (g.leaf_slot[s] >= 0 && g.leaf[s] >= 0) {
+      const gs::GNode& leaf = h->nodes[g.leaf[s]];
+      for (int i = 0; i < leaf.n_edges && i < gs::kMoveStride; ++i) slot_moves[g.leaf_slot[s] * gs::kMoveStride + i] = h->edges[leaf.first_edge + i].mv;
+    }
+  }
+  return E55_OK;
+}
+
+// The network's answers for the round's slots (priors float32 [16][256] in edge order, value float32 [16] in [-1, 1]), then
+// one expand_kernel round.  info[8] as above, after the round; record receives the game's record so far (info[6] words:
+// per ply move, sum_N, Q * 65535, k and k (move, N) pairs), or, when the round has ended a game (info[5] counts them),
+// the finished game: its four header words first, info[6] = words behind them.
+int e55_gpu_search_expand(e55_gpu_search* h, const float* priors, const float* value, int32_t* info, uint16_t* record) {
+  namespace gs = e55::gs;
+  if (!h || !priors || !value || !info || !record) return E55_ERR_INVALID;
+  e55_ctx* c = h->c;
+  std::lock_guard<std::mutex> lk(c->mu);
+  E55_CUDA(c, cudaSetDevice(c->device));
+  const int finished_before = h->game.games_finished;
+  E55_CUDA(c, cudaMemcpyAsync(h->p.priors, priors, gs::kLeaf * gs::kMoveStride * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  E55_CUDA(c, cudaMemcpyAsync(h->p.value, value, gs::kLeaf * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  gs::expand_kernel<<<1, 64, 0, c->stream>>>(h->p);
+  ++c->launches;
+  E55_CUDA(c, cudaGetLastError());
+  E55_CUDA(c, cudaMemcpyAsync(&h->game, h->p.games, sizeof(gs::Game), cudaMemcpyDeviceToHost, c->stream));
+  E55_CUDA(c, cudaStreamSynchronize(c->stream));
+  const gs::Game& g = h->game;
+  info[0] = g.root.ply; info[1] = g.sims_done; info[2] = g.n_sel; info[3] = g.n_nodes; info[4] = g.n_edges; info[5] = g.games_finished;
+  info[6] = g.rec_words; info[7] = 0;
+  if (g.games_finished != finished_before) {
+    E55_CUDA(c, cudaMemcpy(record, h->p.records, gs::kRecordWords * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+    info[6] = record[2];
+    info[7] = 1;
+    gs::Shared zero{};
+    E55_CUDA(c, cudaMemcpy(h->p.shared, &zero, sizeof(zero), cudaMemcpyHostToDevice));   // (the next finished game is record 0 again)
+  } else {
+    E55_CUDA(c, cudaMemcpy(record, h->p.rec_buf, gs::kRecordWords * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+  }
+  return E55_OK;
+}
+
 int e55_gpu_selfplay_run(e55_ctx* c, int games, long total_moves, int simulations, int mate_depth, int reuse_tree, int use_dirichlet,
                          int sampling_moves, int max_moves, uint64_t seed, e55_selfplay_stats* out, uint16_t* records, int record_cap,
                          int* n_records_out) {
@@ -215,6 +361,8 @@ int e55_gpu_selfplay_run(e55_ctx* c, int games, long total_moves, int simulation
   if (sched_getaffinity(0, sizeof(cpus), &cpus) == 0) host_cores = CPU_COUNT(&cpus);
   const int mate_threads = std::max(1, std::min(8, host_cores - 1));
   long mate_searches = 0;
+  std::atomic<long> mate_exhausted{0};
+  static const long mate_budget = getenv("E55_MATE_BUDGET") ? atol(getenv("E55_MATE_BUDGET")) : 1000000;
   // The mate searches of the requests of games [g0, g0 + count) in snapshot `buf`: selfplay.py:35-36 on the host.
   auto answer_requests = [&](int buf, int g0, int count) {
     const mshogi::Board* boards = h_board + static_cast<size_t>(buf) * G;
@@ -229,7 +377,9 @@ int e55_gpu_selfplay_run(e55_ctx* c, int games, long total_moves, int simulation
         const int g = todo[i];
         mshogi::Board b = boards[g];
         mshogi::Move mv;
-        const bool found = b.solve_checkmate_dfs(mate_depth, mv, 200000);   // bounded: the loop below waits for these
+        bool exhausted = false;
+        const bool found = b.solve_checkmate_dfs(mate_depth, mv, mate_budget, &exhausted);   // bounded: the loop below waits for these
+        if (exhausted) mate_exhausted.fetch_add(1, std::memory_order_relaxed);
         answers[g] = (static_cast<unsigned long long>(seq[g]) << 16) | (found ? gs::pack_move(mv) : 0xFFFFu);
         answered[g] = seq[g];
       }
@@ -358,6 +508,11 @@ int e55_gpu_selfplay_run(e55_ctx* c, int games, long total_moves, int simulation
   out->games = static_cast<long>(h_shared->games);
   out->mean_game_plies = h_shared->games ? static_cast<double>(h_shared->plies_in_finished_games) / static_cast<double>(h_shared->games) : 0.0;
   out->mean_gpu_batch = static_cast<double>(n) / n_cohorts;   // slots per network launch
+  out->tree_overflows = static_cast<long>(h_shared->pool_overflows);
+  out->searches_suspended = static_cast<long>(h_shared->searches_suspended);
+  out->mate_searches = mate_searches;
+  out->mate_exhausted = mate_exhausted.load();
+  out->records_truncated = static_cast<long>(h_shared->records_truncated);
   if (timeline && rc == E55_OK) {
     for (long r = 0; r < kTlRounds; ++r)
       for (int k = 0; k < n_cohorts; ++k) {
@@ -380,7 +535,7 @@ int e55_gpu_selfplay_run(e55_ctx* c, int games, long total_moves, int simulation
             h_shared->moves, h_shared->mate_moves, mate_searches, mate_threads, h_shared->selections, h_shared->evals, h_shared->kept_nodes,
             h_shared->pool_overflows);
   if (rc == E55_OK && h_shared->pool_overflows)
-    fprintf(stderr, "[e55 gpu self-play] %llu tree-pool overflows (searches cut short)\n", h_shared->pool_overflows);
+    fprintf(stderr, "[e55 gpu self-play] %llu descents abandoned on a full tree pool (the 90 %% suspension should make this impossible)\n", h_shared->pool_overflows);
   cleanup();
   return rc;
 }

@@ -277,6 +277,13 @@ int service_submit(e55_ctx* c, int kind, const float* planes, const uint32_t* bi
   const int total = kind == 3 ? move_offset[n] : 0;
   if (kind == 3 && (move_offset[0] != 0 || total < 0 || total > s->cap * e55_ctx::kMovesPerPosition))
     return fail_locked(E55_ERR_INVALID, "bad move lists in service request");
+  if (kind == 3) {
+    // every list must lie inside this request's own range: the batch is shared with other callers' requests
+    for (int i = 0; i < n; ++i)
+      if (move_offset[i] > move_offset[i + 1]) return fail_locked(E55_ERR_INVALID, "move_offset must be non-decreasing");
+    for (int j = 0; j < total; ++j)
+      if (move_index[j] >= kPolicyCh * kSq) return fail_locked(E55_ERR_INVALID, "move index outside the 1725 policy entries");
+  }
   if (!c->has_weights) return fail_locked(E55_ERR_NO_WEIGHTS, "predict called before e55_set_weights");
   std::unique_lock<std::mutex> lk(s->m);
   ServiceBatch* b = nullptr;

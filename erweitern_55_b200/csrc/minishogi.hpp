@@ -320,9 +320,12 @@ struct Board {
   // Depth-limited AND/OR search over checking sequences: the side to move must check on every move.
   // node_budget > 0 bounds the work: when that many positions have been looked at the search gives up and reports
   // "no mate" (a few positions with many checking drops have trees of millions of nodes).
-  MS_HD bool solve_checkmate_dfs(int depth, Move& best, long node_budget = 0) {
+  // exhausted (optional) reports that the budget ran out before the search was complete (a "no mate" that is not proven).
+  MS_HD bool solve_checkmate_dfs(int depth, Move& best, long node_budget = 0, bool* exhausted = nullptr) {
     long left = node_budget > 0 ? node_budget : -1;
-    return depth > 0 && mate_attack(depth, &best, left);
+    const bool found = depth > 0 && mate_attack(depth, &best, left);
+    if (exhausted) *exhausted = !found && left == 0;
+    return found;
   }
 
   MS_HD uint64_t compute_hash() const {

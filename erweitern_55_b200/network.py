@@ -244,28 +244,29 @@ class Network:
                                                    records, C.byref(n_rec) if records else None))
         stats = {"seconds": st.seconds, "moves": st.moves, "evals": st.evals, "games": st.games,
                  "mean_game_plies": st.mean_game_plies, "slots_per_launch": st.mean_gpu_batch,
-                 "moves_per_s": st.moves / st.seconds, "evals_per_s": st.evals / st.seconds}
-        letters = " KGSBRP"
-
-        def sfen(mv):
-            frm, to, piece, promo = mv & 31, (mv >> 5) & 31, (mv >> 10) & 15, (mv >> 14) & 1
-            sq = lambda q: "%d%s" % (5 - q % 5, "abcde"[q // 5])
-            return letters[piece] + "*" + sq(to) if frm == 31 else sq(frm) + sq(to) + ("+" if promo else "")
+                 "moves_per_s": st.moves / st.seconds, "evals_per_s": st.evals / st.seconds,
+                 "tree_overflows": st.tree_overflows, "searches_suspended": st.searches_suspended,
+                 "mate_searches": st.mate_searches, "mate_exhausted": st.mate_exhausted, "records_truncated": st.records_truncated}
+        if st.tree_overflows:
+            raise RuntimeError(f"GPU self-play abandoned {st.tree_overflows} descents on a full tree pool: its searches are not the reference's")
+        sfen = packed_move_sfen
         out, now = [], int(time.time())
         for r in range(n_rec.value):
             row = buf[r]
             rec = GameRecord()
-            rec.winner, used, w = int(row[1]), int(row[2]), 4
+            rec.winner, used, truncated, w = int(row[1]), int(row[2]), int(row[3]), 4
             while w < 4 + used:
                 mv, sum_n, q, k = int(row[w]), int(row[w + 1]), int(row[w + 2]) / 65535.0, int(row[w + 3])
                 visits = [(sfen(int(row[w + 4 + 2 * i])), int(row[w + 5 + 2 * i])) for i in range(k)]
                 w += 4 + 2 * k
                 rec.sfen_kif.append(sfen(mv))
                 rec.mcts_result.append((sum_n, q, visits))
-                rec.learning_target_plys.append(rec.ply)
+                if k > 0:                              # a ply whose visit list did not fit the record is no learning target
+                    rec.learning_target_plys.append(rec.ply)
                 rec.ply += 1
             rec.timestamp = now
-            rec.complete = rec.ply == int(row[0])      # False if the record buffer was too small for this game
+            # False if the record buffer was too small for this game (plies or visit lists are missing: flagged by the kernel)
+            rec.complete = rec.ply == int(row[0]) and not truncated
             out.append(rec)
         return stats, out
 
@@ -370,6 +371,13 @@ class Network:
     def step(self, train_images, policy_labels, value_labels, assertion=False):
         raise NotImplementedError("training (network.py:148-199) is outside the accelerated path; "
                                   "train with the reference and hand the weights over with set_weights()")
+
+
+def packed_move_sfen(mv):
+    """USI string of a move as the GPU-resident search packs it: from (31 = drop) | to << 5 | piece << 10 | promotes << 14."""
+    frm, to, piece, promo = mv & 31, (mv >> 5) & 31, (mv >> 10) & 15, (mv >> 14) & 1
+    sq = lambda q: "%d%s" % (5 - q % 5, "abcde"[q // 5])
+    return " KGSBRP"[piece] + "*" + sq(to) if frm == 31 else sq(frm) + sq(to) + ("+" if promo else "")
 
 
 def expected_weight_shapes(blocks=7, filters=128, in_planes=IN_PLANES):

@@ -224,6 +224,12 @@ typedef struct e55_selfplay_stats {
   long games;              /* games finished */
   double mean_game_plies;
   double mean_gpu_batch;   /* positions per GPU forward as coalesced by the evaluation service */
+  /* GPU-resident self-play only (0 from the host driver): */
+  long tree_overflows;      /* descents abandoned because a game's tree pool was full: must be 0 (searches are suspended at 90 %) */
+  long searches_suspended;  /* searches ended early at 90 % pool usage, as mcts.py:71-73 does with its memory */
+  long mate_searches;       /* mate searches answered by the host */
+  long mate_exhausted;      /* ... of which gave up at their node budget ("no mate" not proven; the reference's search is unbounded) */
+  long records_truncated;   /* finished games whose record did not fit its buffer (flagged in the record) */
 } e55_selfplay_stats;
 
 /* Receives one finished game as text: "winner W ply P\n" then one line per ply
@@ -264,7 +270,7 @@ int e55_selfplay_run(e55_ctx* ctx, int threads, long total_moves, int simulation
  * except that a round selects until a game's 16 network slots are filled (at most 24 selections) and an
  * unevaluated root takes a round of its own.  From 2 048 games on, the games run as two cohorts on two streams so
  * that one cohort's search overlaps the other's network launch.  simulations: a multiple of 16, at most 1024.
- * records (optional): the first record_cap finished games, 16384 uint16 words each: plies, winner, words used, 0,
+ * records (optional): the first record_cap finished games, 16384 uint16 words each: plies, winner, words used, truncated (0/1),
  * then per ply what selfplay.run records (selfplay.py:80-92) -- move, sum_N, Q * 65535, k, and k (move, N) pairs of
  * the visited root children; moves are packed as from (31 = drop) | to << 5 | piece << 10 | promotes << 14.
  * stats_out->mean_gpu_batch is the positions per network launch (16 slots per game of a cohort). */
@@ -272,6 +278,22 @@ int e55_gpu_selfplay_run(e55_ctx* ctx, int games, long total_moves, int simulati
                          int use_dirichlet, int sampling_moves, int max_moves, uint64_t seed, e55_selfplay_stats* stats_out,
                          uint16_t* records, int record_cap,
                          int* n_records_out);
+/* Debug/verification: ONE game of the GPU-resident search, a round at a time, with the caller in the network's place
+ * (no Dirichlet noise, no sampling, no mate search): the moves of `prefix` (packed as in the game records) are played from
+ * the start position, then every select call runs one select_kernel round and reports its selections (leaf node, network
+ * slot, the path from the root as packed moves) and the legal moves of the slots to evaluate; every expand call takes the
+ * priors (in the slots' move order) and values, runs one expand_kernel round and reports the game's record so far.
+ * tests/test_gpu_parity.py walks oracle/mcts_oracle.py beside it: same path for every selection, same visit counts.
+ * info (8 ints): plies played, simulations done (-1: root not evaluated), selections of the round, nodes, edges, games
+ * finished, record words, 1 if `record` holds a finished game (with its 4-word header).  Array sizes: sel_* [24],
+ * sel_path [24][96], slot_cnt [16], slot_moves / slot_idx [16][256], priors [16][256], value [16], record [16384]. */
+typedef struct e55_gpu_search e55_gpu_search;
+int e55_gpu_search_open(e55_ctx* ctx, const uint16_t* prefix, int n_prefix, int simulations, int reuse_tree, e55_gpu_search** out);
+void e55_gpu_search_close(e55_gpu_search* h);
+int e55_gpu_search_select(e55_gpu_search* h, int32_t* info, int32_t* sel_leaf, int32_t* sel_slot, int32_t* sel_path_len,
+                          uint16_t* sel_path, int32_t* slot_cnt, uint16_t* slot_moves, uint16_t* slot_idx);
+int e55_gpu_search_expand(e55_gpu_search* h, const float* priors, const float* value, int32_t* info, uint16_t* record);
+
 /* Device build of the rules engine: perft from the start position computed on the GPU (14, 181, 2512, 35401, ...). */
 int e55_selftest_engine(int device, int depth, int64_t* nodes_out);
 /* Validation of the device-side game history: n threads each play a random game and a random path below it with the
