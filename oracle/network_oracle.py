@@ -135,8 +135,9 @@ def prepare_torch(weights, dtype=torch.float32):
     return prep
 
 
-def forward_prepared(prep, x):
-    """Forward pass on a prepared weight set; ``x`` torch tensor ``[N,C,5,5]``.  network.py:87-122."""
+def forward_prepared(prep, x, return_trunk=False):
+    """Forward pass on a prepared weight set; ``x`` torch tensor ``[N,C,5,5]``.  network.py:87-122.
+    return_trunk: also the trunk output ``[N,filters,5,5]`` (the input of both heads, network.py:99)."""
     def cb(x, c, b):
         y = F.conv2d(x, c[0], c[1], stride=1, padding=c[2])
         return y * b[0] + b[1]
@@ -156,16 +157,19 @@ def forward_prepared(prep, x):
         v = F.relu(cb(h, vc, vb)).reshape(h.shape[0], -1)
         v = F.relu(v @ k1 + b1_)
         value = torch.tanh(v @ k2 + b2_)
+    if return_trunk:
+        return policy, value, h
     return policy, value
 
 
-def forward_torch(weights, images, dtype=torch.float32):
-    """``Network.predict`` restated: ``images [N,266,5,5]`` -> ``(policy [N,1725], value [N,1])`` numpy."""
+def forward_torch(weights, images, dtype=torch.float32, return_trunk=False):
+    """``Network.predict`` restated: ``images [N,266,5,5]`` -> ``(policy [N,1725], value [N,1])`` numpy
+    (and the trunk output with ``return_trunk``)."""
     prep = prepare_torch(weights, dtype)
     x = torch.from_numpy(np.ascontiguousarray(np.asarray(images))).to(dtype)
-    p, v = forward_prepared(prep, x)
-    return p.to(torch.float64 if dtype == torch.float64 else torch.float32).numpy(), \
-        v.to(torch.float64 if dtype == torch.float64 else torch.float32).numpy()
+    out = forward_prepared(prep, x, return_trunk)
+    keep = torch.float64 if dtype == torch.float64 else torch.float32
+    return tuple(t.to(keep).numpy() for t in out)
 
 
 # --------------------------------------------------------------------------------------------------

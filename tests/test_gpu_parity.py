@@ -44,7 +44,14 @@ def nets(weights_default, weights_perturbed):
         n.close()
 
 
-def _check(p, v, po, vo, tol):
+def _check(p, v, po, vo, tol, min_decisive=None, label=""):
+    """Outputs against the oracle's: absolute tolerances, and the same top-1 move wherever the oracle's top-2 margin
+    exceeds twice the logit tolerance ("decisive" rows).  The share of decisive rows is asserted (min_decisive; from 16
+    rows on, by default at least 0.3: random-init networks have a median top-2 margin of 0.088 against the 0.06
+    threshold of the bf16 tolerance, BASELINE.md section 4, so 40-60 % of their rows are decisive; the trained-like set
+    asks for 0.5 and has ~0.9) and the tie rate -- rows too close to call -- is reported (pytest -s shows it).  From 64
+    rows on, top-1 must also agree on at least 95 % of ALL rows, near-ties included (BASELINE.md section 4 measured
+    99.1 % over 2 048 rows for bf16 rounding as such; 64 rows can lose two)."""
     assert p.shape == po.shape and v.shape == vo.shape and p.dtype == np.float32 and v.dtype == np.float32
     assert np.isfinite(p).all() and np.isfinite(v).all()
     assert np.abs(p - po).max() <= tol[0], np.abs(p - po).max()
@@ -52,7 +59,15 @@ def _check(p, v, po, vo, tol):
     top2 = np.sort(po, axis=1)[:, -2:]
     decisive = (top2[:, 1] - top2[:, 0]) > 2 * tol[0]
     assert (p.argmax(1)[decisive] == po.argmax(1)[decisive]).all()
-    return float(decisive.mean())
+    frac = float(decisive.mean())
+    if min_decisive is None:
+        min_decisive = 0.3 if len(p) >= 16 else 0.0
+    if len(p) >= 64:
+        assert float((p.argmax(1) == po.argmax(1)).mean()) >= 0.95
+    print(f"[parity{' ' + label if label else ''}] {len(p)} rows: max |dlogit| {np.abs(p - po).max():.2e}, max |dvalue| {np.abs(v - vo).max():.2e}, "
+          f"decisive {frac:.3f} (tie rate {1 - frac:.3f}), top-1 equal on all rows {float((p.argmax(1) == po.argmax(1)).mean()):.3f}")
+    assert frac >= min_decisive, (frac, min_decisive)
+    return frac
 
 
 @pytest.mark.parametrize("tag", ["default", "perturbed"])
@@ -77,9 +92,25 @@ def test_golden_fixture(nets, golden, tag):
     assert np.abs(p - golden[f"{tag}_policy_bf16"]).max() <= _bf16_tol(tag)[0]
 
 
-def test_trunk_activations_match_fp32_path(nets):
+def test_trunk_activations_match_the_oracle(nets, weights_perturbed):
+    """Per-layer parity against the CPU oracle, not against another CUDA path: the trunk output (after all 15 3x3
+    convolutions) of both precision paths against the oracle's fp32 trunk, and the tcgen05 path against the oracle's
+    bf16 emulation (same rounding points: folded bf16 weights, bf16 activations between layers, fp32 accumulation);
+    intermediate layers of the two CUDA paths are held against each other as before."""
+    O = _oracle()
     x = synth.synthetic_planes(11, seed=3)
-    for nconv in (1, 2, 3, 15):
+    _, _, trunk_emulated = O.forward_bf16_emulated(weights_perturbed, x, return_trunk=True)
+    _, _, trunk_fp32 = O.forward_torch(weights_perturbed, x, return_trunk=True)
+    a32 = nets["perturbed", "fp32"].debug_activations(x)
+    a16 = nets["perturbed", "bf16"].debug_activations(x)
+    scale = max(1.0, float(np.abs(trunk_fp32).max()))
+    assert np.abs(a32 - trunk_fp32).max() <= 1e-4 * scale
+    assert np.abs(a16 - trunk_fp32).max() <= 0.02 * scale
+    # against the emulation only accumulation order differs (a sum that lands on the other side of a bf16 rounding
+    # boundary moves an activation by one bf16 step, 2^-8 relative, and the layers after it follow)
+    assert np.abs(a16 - trunk_emulated).max() <= 0.008 * scale, np.abs(a16 - trunk_emulated).max()
+    assert np.mean(np.abs(a16 - trunk_emulated)) <= 5e-4 * scale, np.mean(np.abs(a16 - trunk_emulated))
+    for nconv in (1, 2, 3):
         a = nets["perturbed", "bf16"].debug_activations(x, nconv)
         b = nets["perturbed", "fp32"].debug_activations(x, nconv)
         assert np.abs(a - b).max() <= 0.02 * max(1.0, np.abs(b).max())
@@ -127,7 +158,71 @@ def test_large_batch_against_oracle_sample(nets, weights_default):
     p, v = net.predict(x)
     idx = np.arange(0, 4096, 97)
     po, vo = _oracle().forward_torch(weights_default, x[idx])
-    _check(p[idx], v[idx], po, vo, BF16_TOL)
+    _check(p[idx], v[idx], po, vo, BF16_TOL, label="4096 sample")
+
+
+@pytest.mark.parametrize("tag", ["default", "perturbed"])
+@pytest.mark.parametrize("n", [1024, 1184])
+def test_headline_batches_against_the_oracle(nets, weights_default, weights_perturbed, tag, n):
+    """Every row of the headline batch (1024) and of the full-machine batch (1184 = 148 SMs x 8 positions) against the
+    oracle directly, through Network.predict (host pipeline: packed chunks) and through the device-resident call."""
+    w = weights_default if tag == "default" else weights_perturbed
+    x = synth.synthetic_planes(n, seed=4000 + n)
+    po, vo = _oracle().forward_torch(w, x)
+    net = nets[tag, "bf16"]
+    p, v = net.predict(x)
+    _check(p, v, po, vo, _bf16_tol(tag), label=f"{tag} batch {n}")
+    xd = torch.from_numpy(x).cuda()
+    pd, vd = torch.empty((n, 1725), device="cuda"), torch.empty((n, 1), device="cuda")
+    net.predict_device(xd, pd, vd)
+    net.sync()
+    assert np.array_equal(pd.cpu().numpy(), p) and np.array_equal(vd.cpu().numpy(), v)   # one launch == the chunked pipeline
+
+
+def test_trained_like_dynamic_range(weights_trained_like):
+    """bf16 tolerance on a network with a trained network's dynamic range (tests/conftest.py::calibrate_trained_like:
+    BatchNorm statistics far from the identity, logits from -14 to +20 instead of +-2): the rounding error of bf16
+    operands scales with the magnitudes, so the tolerance is relative -- 1.5 % of the largest |logit| of the batch
+    (measured: 1.0 % for the oracle's own bf16 emulation) -- and top-1 must agree wherever the oracle's margin exceeds
+    twice that.  The fp32 path stays at 1e-4 relative."""
+    from erweitern_55_b200.network import Network
+    O = _oracle()
+    x = synth.synthetic_planes(512, seed=5)
+    po, vo = O.forward_torch(weights_trained_like, x)
+    scale = float(np.abs(po).max())
+    assert scale > 10.0
+    net = Network(precision="fp32", weights=weights_trained_like)
+    p, v = net.predict(x[:64])
+    _check(p, v, po[:64], vo[:64], (1e-4 * scale, 1e-4), label="trained-like fp32")
+    net.set_precision("bf16")
+    p, v = net.predict(x)
+    frac = _check(p, v, po, vo, (0.015 * scale, 0.05), min_decisive=0.5, label="trained-like bf16")
+    pe, ve = O.forward_bf16_emulated(weights_trained_like, x)
+    assert np.abs(p - pe).max() <= 0.008 * scale and np.abs(v - ve).max() <= 0.02      # same rounding points, other summation order
+    assert (p.argmax(1) == po.argmax(1)).mean() >= 0.95
+    net.close()
+
+
+def test_tf_golden_when_present(nets):
+    """Reference-side pin: tests/golden/tf_golden.npz is written by tools/make_tf_golden.py on a machine that has the
+    reference's TensorFlow 1.15 / Keras stack (it cannot be produced here) -- the reference's own Network with seeded
+    weights, model.get_weights() and predict() on the seeded synthetic inputs.  When the file is there, both CUDA
+    paths are held to the reference's outputs themselves, and the oracle with them."""
+    import os
+    path = os.path.join(os.path.dirname(__file__), "golden", "tf_golden.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/tf_golden.npz not present (produce it with tools/make_tf_golden.py on a TF-1.15 machine)")
+    from erweitern_55_b200.network import Network
+    z = np.load(path)
+    w = [z[f"w{i}"] for i in range(int(z["n_weights"]))]
+    x, po, vo = z["inputs"], z["policy"], z["value"]
+    p_or, v_or = _oracle().forward_torch(w, x)
+    assert np.abs(p_or - po).max() <= 1e-4 and np.abs(v_or - vo).max() <= 1e-5      # the oracle IS the reference's forward pass
+    net = Network(precision="fp32", weights=w)
+    _check(*net.predict(x), po, vo, FP32_TOL, label="TF golden fp32")
+    net.set_precision("bf16")
+    _check(*net.predict(x), po, vo, BF16_TOL, label="TF golden bf16")
+    net.close()
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])

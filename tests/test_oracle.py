@@ -94,3 +94,35 @@ def test_masked_softmax_oracle():
     assert np.allclose(pr[:2].sum(1), 1.0) and np.all(pr[2] == 0) and np.all(pr[m == 0] == 0)
     i = np.flatnonzero(m[0])
     np.testing.assert_allclose(pr[0, i], np.exp(p[0, i]) / np.exp(p[0, i]).sum(), rtol=1e-12)
+
+
+def test_tf_golden_pins_the_oracle():
+    """When tests/golden/tf_golden.npz exists (written by tools/make_tf_golden.py where the reference's TensorFlow 1.15
+    stack runs), the oracle must reproduce the reference's own predict() outputs: that is what pins it."""
+    import os
+    path = os.path.join(os.path.dirname(__file__), "golden", "tf_golden.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/tf_golden.npz not present: the forward-pass oracle stays 'parity unpinned'")
+    z = np.load(path)
+    w = [z[f"w{i}"] for i in range(int(z["n_weights"]))]
+    from oracle import network_oracle as O
+    p, v = O.forward_torch(w, z["inputs"])
+    assert np.abs(p - z["policy"]).max() <= 1e-4 and np.abs(v - z["value"]).max() <= 1e-5
+
+
+def test_make_tf_golden_generators_match_this_repo():
+    """tools/make_tf_golden.py carries its own copy of the synthetic-input generator (it must run without this package):
+    the copy and the original produce the same planes, and its weight perturbation keeps the reference's shapes."""
+    import importlib.util
+    import os
+    from erweitern_55_b200 import synth, weights as W
+    spec = importlib.util.spec_from_file_location("make_tf_golden", os.path.join(os.path.dirname(__file__), "..", "tools", "make_tf_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert np.array_equal(mod.synthetic_planes(7, seed=1007), synth.synthetic_planes(7, seed=1007))
+    w = W.init_weights(seed=1)
+    pw = mod.perturb(w, 55)
+    assert [a.shape for a in pw] == [a.shape for a in w] and W.infer_arch(pw) == (7, 128, 266)
+    from oracle import network_oracle as O
+    p, v = O.forward_torch(pw, synth.synthetic_planes(3, seed=2))
+    assert np.isfinite(p).all() and np.abs(v).max() < 1
