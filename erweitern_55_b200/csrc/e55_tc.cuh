@@ -609,29 +609,96 @@ tower_kernel(const Params prm) {
         for (size_t i = first + threadIdx.x * 32; i < last; i += 256 * 32)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(prm.planes + i));
       }
+      // ---- phase 1: the stem's input.  All slices of both groups are converted before any epilogue of the round is
+      // served (the stem epilogues need every slice anyway).  No residual of the previous round is live here, and
+      // saying so (the registers are cleared) gives the conversion the registers to keep all its loads in flight:
+      // with the residuals alive the compiler had serialised the four items of a pass into four dependent round trips
+      // to L2, and the stem was bound by them instead of by its MMAs.
+#pragma unroll
+      for (int i = 0; i < F / 4; ++i) res_a[i] = 0u;
+#pragma unroll
+      for (int i = 0; i < (G::kGroups == 2 ? F / 4 : 1); ++i) res_b[i] = 0u;
+      while (next_slice[0] < prm.nslices || next_slice[1] < prm.nslices) {
+        // slice k goes to plane half k&1 once the MMAs that read that half's previous slice are done (the group that is
+        // further behind with its input goes first, so neither starves the other)
+        int g = -1;
+        while (g < 0) {
+          const int g0 = next_slice[1] < next_slice[0] ? 1 : 0;
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int gg = g0 ^ k;
+            if (g < 0 && next_slice[gg] < prm.nslices) {
+              const int b = gg * 2 + (next_slice[gg] & 1);
+              if (conv_cnt[b] == 0 || ptx::mbar_test_wait(&bar_in_empty[b], (conv_cnt[b] - 1) & 1)) g = gg;
+            }
+          }
+        }
+        // fp32 NCHW planes -> bf16 wide-board planes of this group (network.py:255-274 built the input):
+        // one item = 8 consecutive channels of one square of one position = one 16-byte row entry
+        const int sl = next_slice[g];
+        constexpr int kSlicePlanes = kPlanes / 2;
+        const int hh = sl & 1;
+        const int pl0 = sl * kSlicePlanes;                       // first input plane (8 channels each) of the slice
+        const int npl = min(kSlicePlanes, prm.in_planes8 - pl0);
+        const int pos0 = r * prm.pos_per_round + g * kPosPerGroup;
+        // item -> (position, plane, square) with compile-time divisors only (the slice is always walked as if it had
+        // all kSlicePlanes planes; items of planes a short last slice does not have are skipped): this loop is
+        // instruction-bound, and a division by a run-time plane count cost more than the loads
+        constexpr int nitems = kPosPerGroup * kSlicePlanes * kSq;
+        for (int it0 = threadIdx.x; it0 < nitems; it0 += 256 * 4) {
+          float f[4][8];
+          // phase 1: issue every global load of up to 4 items before touching any result
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int it = it0 + u * 256;
+            const int q = it / kSq, s_ = it - q * kSq, c8 = q % kSlicePlanes, p = q / kSlicePlanes;
+            const bool live = it < nitems && c8 < npl && pos0 + p < prm.n;
+            const int ch0 = (pl0 + c8) * 8;
+            if (prm.bits == nullptr) {
+              const float* src = prm.planes + (static_cast<size_t>(pos0 + p) * prm.in_planes + ch0) * kSq + s_;
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                f[u][e] = (live && ch0 + e < prm.in_planes) ? __ldg(src + e * kSq) : 0.f;
+            } else {
+              // packed planes: x[c][sq] = bit sq of bits[c] ? scale[c] : 0
+              const size_t o = static_cast<size_t>(pos0 + p) * prm.packed_stride + ch0;
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const bool ok = live && ch0 + e < prm.in_planes;
+                const uint32_t wbits = ok ? __ldg(prm.bits + o + e) : 0u;
+                const float sc = ok ? __ldg(prm.scale + o + e) : 0.f;
+                f[u][e] = ((wbits >> s_) & 1u) ? sc : 0.f;
+              }
+            }
+          }
+          // phase 2: pack and store
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int it = it0 + u * 256;
+            const int q = it / kSq, s_ = it - q * kSq, c8 = q % kSlicePlanes, p = q / kSlicePlanes;
+            if (it < nitems && c8 < npl) {
+              const uint4 pk = make_uint4(ptx::pack_bf16x2(f[u][0], f[u][1]), ptx::pack_bf16x2(f[u][2], f[u][3]),
+                                          ptx::pack_bf16x2(f[u][4], f[u][5]), ptx::pack_bf16x2(f[u][6], f[u][7]));
+              const int rr = (s_ / 5) * kW + p * 6 + s_ % 5;
+              *reinterpret_cast<uint4*>(s_act + (hh * kSlicePlanes + c8) * kPlaneBytes + (group_origin_row(g) + rr) * 16) = pk;
+            }
+          }
+        }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) arrive_on_leader(&bar_in_full[g * 2 + hh], rank);
+        next_slice[g] = sl + 1;
+        ++conv_cnt[g * 2 + hh];
+      }
+      // ---- phase 2: epilogues, value tails ----
       while (next_layer[0] < nl || next_layer[1] < nl || fc_pending[0] || fc_pending[1]) {
         long long te0 = 0, te1 = 0;
         if (kProf) te0 = clock64();
         int g;
-        bool convert = false, value_fc = false;
+        bool value_fc = false;
         for (;;) {  // serve whichever event is ready first (group A preferred: it runs ahead)
           if (next_layer[0] < nl && ptx::mbar_test_wait(&bar_tmem_full[0], (round_seq * nl + next_layer[0]) & 1)) { g = 0; break; }
           if (next_layer[1] < nl && ptx::mbar_test_wait(&bar_tmem_full[1], (round_seq * nl + next_layer[1]) & 1)) { g = 1; break; }
-          // stem input: slice k goes to plane half k&1 once the MMAs that read that half's previous slice are done
-          // (the group that is further behind with its input goes first, so neither starves the other)
-          {
-            const int g0 = next_slice[1] < next_slice[0] ? 1 : 0;
-            bool found = false;
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              const int gg = g0 ^ k;
-              if (next_slice[gg] < prm.nslices) {
-                const int b = gg * 2 + (next_slice[gg] & 1);
-                if (conv_cnt[b] == 0 || ptx::mbar_test_wait(&bar_in_empty[b], (conv_cnt[b] - 1) & 1)) { g = gg; convert = true; found = true; break; }
-              }
-            }
-            if (found) break;
-          }
           if (fc_pending[0] && ptx::mbar_test_wait(&bar_v[0], round_seq & 1)) { g = 0; value_fc = true; break; }
           if (fc_pending[1] && ptx::mbar_test_wait(&bar_v[1], round_seq & 1)) { g = 1; value_fc = true; break; }
         }
@@ -675,61 +742,6 @@ tower_kernel(const Params prm) {
             const float t = lane == 0 ? part[0] : lane == 1 ? part[1] : lane == 2 ? part[2] : part[3];
             prm.value[pos] = tanhf(t + prm.fc2_b);
           }
-          continue;
-        }
-        if (convert) {
-          // fp32 NCHW planes -> bf16 wide-board planes of this group (network.py:255-274 built the input):
-          // one item = 8 consecutive channels of one square of one position = one 16-byte row entry
-          const int sl = next_slice[g];
-          constexpr int kSlicePlanes = kPlanes / 2;
-          const int hh = sl & 1;
-          const int pl0 = sl * kSlicePlanes;                       // first input plane (8 channels each) of the slice
-          const int npl = min(kSlicePlanes, prm.in_planes8 - pl0);
-          const int pos0 = r * prm.pos_per_round + g * kPosPerGroup;
-          const int nitems = kPosPerGroup * npl * kSq;
-          for (int it0 = threadIdx.x; it0 < nitems; it0 += 256 * 4) {
-            float f[4][8];
-            // phase 1: issue every global load of up to 4 items before touching any result
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int it = it0 + u * 256;
-              const int s_ = it % kSq, c8 = (it / kSq) % npl, p = it / (kSq * npl);
-              const bool live = it < nitems && pos0 + p < prm.n;
-              if (prm.bits == nullptr) {
-                const float* src = prm.planes + (static_cast<size_t>(pos0 + p) * prm.in_planes + (pl0 + c8) * 8) * kSq + s_;
-#pragma unroll
-                for (int e = 0; e < 8; ++e)
-                  f[u][e] = (live && (pl0 + c8) * 8 + e < prm.in_planes) ? __ldg(src + e * kSq) : 0.f;
-              } else {
-                // packed planes: x[c][sq] = bit sq of bits[c] ? scale[c] : 0
-                const size_t o = static_cast<size_t>(pos0 + p) * prm.packed_stride + (pl0 + c8) * 8;
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  const bool ok = live && (pl0 + c8) * 8 + e < prm.in_planes;
-                  const uint32_t wbits = ok ? __ldg(prm.bits + o + e) : 0u;
-                  const float sc = ok ? __ldg(prm.scale + o + e) : 0.f;
-                  f[u][e] = ((wbits >> s_) & 1u) ? sc : 0.f;
-                }
-              }
-            }
-            // phase 2: pack and store
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int it = it0 + u * 256;
-              if (it < nitems) {
-                const int s_ = it % kSq, c8 = (it / kSq) % npl, p = it / (kSq * npl);
-                const uint4 pk = make_uint4(ptx::pack_bf16x2(f[u][0], f[u][1]), ptx::pack_bf16x2(f[u][2], f[u][3]),
-                                            ptx::pack_bf16x2(f[u][4], f[u][5]), ptx::pack_bf16x2(f[u][6], f[u][7]));
-                const int rr = (s_ / 5) * kW + p * 6 + s_ % 5;
-                *reinterpret_cast<uint4*>(s_act + (hh * kSlicePlanes + c8) * kPlaneBytes + (group_origin_row(g) + rr) * 16) = pk;
-              }
-            }
-          }
-          ptx::fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) arrive_on_leader(&bar_in_full[g * 2 + hh], rank);
-          next_slice[g] = sl + 1;
-          ++conv_cnt[g * 2 + hh];
           continue;
         }
         ptx::tc_fence_after_sync();

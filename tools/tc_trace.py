@@ -39,3 +39,13 @@ ep = ep[np.argsort(ep[:, 0])]
 print("epilogue durations: median", np.median(ep[:,1]-ep[:,0]), "max", (ep[:,1]-ep[:,0]).max())
 for c in list(range(0, 24)) + list(range(36, 44)):
     print(f"c={c:3d} A t0={ia[c,0]-t0:7d} wF={ia[c,1]-ia[c,0]:5d} wA={ia[c,2]-ia[c,1]:5d} is={ia[c,3]-ia[c,2]:5d} | B t0={ib[c,0]-t0:7d} wF={ib[c,1]-ib[c,0]:5d} wA={ib[c,2]-ib[c,1]:5d} is={ib[c,3]-ib[c,2]:5d}")
+print("layer starts (first chunk of each layer), group A t0 / B t0, and period:")
+firsts = [0, 15] + list(range(21, len(ia), 6))
+prev = None
+for c in firsts:
+    if c < len(ia) and c < len(ib):
+        print(f"  c={c:3d} A={ia[c,0]-t0:7d} B={ib[c,0]-t0:7d}" + (f"  dA={ia[c,0]-prev[0]:6d} dB={ib[c,0]-prev[1]:6d}" if prev else ""))
+        prev = (ia[c,0], ib[c,0])
+print("epilogue events (start, duration, group, layer):")
+for e in ep[:40]:
+    print(f"  t={e[0]-t0:7d} dur={e[1]-e[0]:5d} g={e[2]} L={e[3]}")
