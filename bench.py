@@ -381,7 +381,15 @@ def main():
         xs = [synth.synthetic_planes(nb, seed=70 + i) for i in range(3)]
         rate, call_s = e2e_rate(xs, nb, 200)
         small[str(nb)] = {"us_per_call": call_s * 1e6, "evals_per_s": rate}
-    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": (B - n_float) * 266 * 8 + n_float * 266 * 25 * 4,
+    # the host-memory roofline of this number: all ranks read their 27 MB input arrays at once with their pool threads
+    # (nothing else: no packing, no copies); every position costs 26 600 bytes of such reads, by cores or copy engine
+    gbs = C.c_double()
+    barrier()
+    for a in host_pool:
+        net._check(lib.e55_host_read_bandwidth(ctx, a.ctypes.data, a.nbytes, 3, C.byref(gbs)))
+    barrier()
+    host_gbs, _ = sharding.aggregate(gbs.value, 1.0, device=dev)
+    e2e = {"value": e2e_value, "unit": UNIT, "host_read_gbs": host_gbs, "host_read_bound_evals_per_s": host_gbs * 1e9 / (266 * 25 * 4), "h2d_bytes_per_step": (B - n_float) * 266 * 8 + n_float * 266 * 25 * 4,
            "d2h_bytes_per_step": B * 1725 * 4 + B * 4, "call": "Network.predict(numpy)->numpy", "us_per_call": e2e_call_s * 1e6,
            "input_memory": "page-locked numpy, 3 arrays in rotation", "host_input_bytes_per_step": in_bytes,
            "float_eighths": best_share, "host_pack_threads": pk_threads.value,

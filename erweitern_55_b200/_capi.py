@@ -27,6 +27,7 @@ SIGNATURES = {
     "e55_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "e55_host_free": (C.c_int, [C.c_void_p]),
     "e55_set_host_threads": (C.c_int, [_ctx, C.c_int]),
+    "e55_host_read_bandwidth": (C.c_int, [_ctx, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_double)]),
     "e55_get_host_pipeline": (C.c_int, [_ctx, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "e55_get_host_split": (C.c_int, [_ctx, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "e55_predict_device": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),

@@ -1071,6 +1071,17 @@ int e55_set_host_threads(e55_ctx* c, int threads) {
   return E55_OK;
 }
 
+int e55_host_read_bandwidth(e55_ctx* c, const void* buf, size_t bytes, int passes, double* gbs_out) {
+  if (!c || !buf || bytes < (1u << 20) || passes < 1 || !gbs_out) return E55_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  e55host::Packer* packer = host_packer(c, 1);
+  if (!packer) return fail(c, E55_ERR_UNSUPPORTED, "the host thread pool is switched off (e55_set_host_threads)");
+  double best = 0.0;
+  for (int i = 0; i < passes; ++i) best = std::max(best, e55host::packer_read_bandwidth(packer, buf, bytes));
+  *gbs_out = best;
+  return E55_OK;
+}
+
 int e55_get_host_pipeline(e55_ctx* c, int* threads_out, double* compact_us_out, double* float_us_out) {
   if (!c || !threads_out || !compact_us_out || !float_us_out) return E55_ERR_INVALID;
   std::lock_guard<std::mutex> lk(c->mu);

@@ -118,8 +118,9 @@ struct Packer {
   float* scale = nullptr;
   int n = 0, in_planes = 0, stride = 0, n_blocks = 0;
   const uint8_t* copy_src = nullptr;
-  uint8_t* copy_dst = nullptr;
+  uint8_t* copy_dst = nullptr;         // null with copy_src set: read only (bandwidth probe)
   size_t copy_bytes = 0;
+  std::atomic<uint64_t> read_sink{0};
   std::atomic<int> next{0};
   std::atomic<int> idle{0};                       // workers that have left the current job
   std::vector<std::atomic<uint8_t>> block_state;  // 0 pending, 1 packed exactly, 2 not representable
@@ -157,8 +158,16 @@ struct Packer {
       for (;;) {
         const int b = next.fetch_add(1, std::memory_order_relaxed);
         if (b >= n_blocks) return;
-        const size_t o = static_cast<size_t>(b) * kCopyBlock;
-        memcpy(copy_dst + o, copy_src + o, std::min(kCopyBlock, copy_bytes - o));
+        const size_t o = static_cast<size_t>(b) * kCopyBlock, len = std::min(kCopyBlock, copy_bytes - o);
+        if (copy_dst) {
+          memcpy(copy_dst + o, copy_src + o, len);
+        } else {                       // stream the block through the core: 64-bit loads, four independent sums
+          const uint64_t* q = reinterpret_cast<const uint64_t*>(copy_src + o);
+          uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+          size_t i = 0;
+          for (; i + 4 <= len / 8; i += 4) { a0 += q[i]; a1 += q[i + 1]; a2 += q[i + 2]; a3 += q[i + 3]; }
+          read_sink.fetch_add(a0 + a1 + a2 + a3, std::memory_order_relaxed);
+        }
       }
     }
     for (;;) {
@@ -245,6 +254,19 @@ struct Packer {
   }
 };
 
+// Reads `bytes` at `src` once with the pool's threads and the caller (nothing is written): GB/s of the pass.
+double Packer_read_pass(Packer* p, const void* src, size_t bytes) {
+  const auto t0 = std::chrono::steady_clock::now();
+  p->planes = nullptr;
+  p->copy_src = static_cast<const uint8_t*>(src); p->copy_dst = nullptr; p->copy_bytes = bytes;
+  p->n_blocks = static_cast<int>((bytes + Packer::kCopyBlock - 1) / Packer::kCopyBlock);
+  p->publish();
+  p->finish();
+  p->copy_src = nullptr;
+  const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return static_cast<double>(bytes) / s / 1e9;
+}
+
 Packer* packer_create(int threads) { return threads > 0 ? new (std::nothrow) Packer(threads) : nullptr; }
 void packer_destroy(Packer* p) { delete p; }
 int packer_threads(const Packer* p) { return p ? static_cast<int>(p->threads.size()) : 0; }
@@ -259,6 +281,7 @@ void packer_parallel_copy(Packer* p, void* dst, const void* src, size_t bytes) {
 bool pack_planes_inline(const float* planes, int n, int in_planes, uint32_t* bits, float* scale, int stride) {
   return pack_positions(planes, 0, n, in_planes, bits, scale, stride ? stride : in_planes);
 }
+double packer_read_bandwidth(Packer* p, const void* src, size_t bytes) { return p ? Packer_read_pass(p, src, bytes) : 0.0; }
 const char* pack_isa() { return g_pack == pack_positions_avx512 ? "avx512" : "avx2"; }
 
 }  // namespace e55host

@@ -20,6 +20,9 @@ bool packer_wait_range(Packer* p, int first, int count);
 void packer_finish(Packer* p);
 // memcpy shared by the pool's threads and the caller (no pack job may be running); p may be null (plain memcpy).
 void packer_parallel_copy(Packer* p, void* dst, const void* src, size_t bytes);
+// One read-only pass over [src, src + bytes) by the pool's threads and the caller: GB/s (the host-memory roofline of
+// everything that has to read float planes: 26 600 bytes per position).
+double packer_read_bandwidth(Packer* p, const void* src, size_t bytes);
 // "avx512" or "avx2": the packing kernel chosen for this CPU (E55_HOST_ISA=avx2 forces the baseline).
 const char* pack_isa();
 // Same packing on the calling thread.

@@ -82,6 +82,11 @@ int e55_predict(e55_ctx* ctx, const float* planes, int n, float* policy, float* 
  * the fastest; n > 0 = always pack with n threads; 0 = off: the planes cross PCIe as they
  * are. */
 int e55_set_host_threads(e55_ctx* ctx, int threads);
+/* Measurement: the rate at which this context's host thread pool can merely READ `bytes` of host memory at `buf` (best of
+ * `passes` passes, GB/s).  Whatever e55_predict does with float32 planes, 26 600 bytes per position have to be read from
+ * host memory once, by the cores (packing) or by the copy engine: this is the roofline of the end-to-end number, and
+ * bench.py reports it beside it (summed over the ranks of a box, which share the host's memory system). */
+int e55_host_read_bandwidth(e55_ctx* ctx, const void* buf, size_t bytes, int passes, double* gbs_out);
 /* What e55_predict measured: packing threads in use, and the running mean of microseconds per position of the
  * compacting and of the float pipeline on large batches (0 = not tried yet). */
 int e55_get_host_pipeline(e55_ctx* ctx, int* threads_out, double* compact_us_out, double* float_us_out);
