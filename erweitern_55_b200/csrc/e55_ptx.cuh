@@ -81,6 +81,48 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank
       "r"(rank)
       : "memory");
 }
+// the same with cluster-scope release: what the arriving thread wrote before (also into the peer's shared memory) is
+// visible to whoever acquires the barrier at cluster scope
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
+// address of the same shared-memory location in CTA `rank` of the cluster (distributed shared memory)
+__device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(p)), "r"(rank));
+  return ra;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+// arrive on the mbarrier at this offset in CTA `rank` and add `bytes` to the transaction count it waits for
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint64_t* bar, uint32_t rank, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.expect_tx.shared::cluster.b64 _, [ra], %2;\n\t}\n" ::"r"(smem_u32(bar)),
+      "r"(rank), "r"(bytes)
+      : "memory");
+}
+// bulk copy own shared memory -> the same offset space of CTA `rank` (async proxy on both ends; completes, in bytes, on
+// the mbarrier `bar` of the destination CTA): how one CTA's epilogue output becomes a tensor-core operand of its peer
+__device__ __forceinline__ void bulk_s2s_cluster(const void* src, uint32_t dst_cluster_addr, uint32_t bytes, uint32_t bar_cluster_addr) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster_addr),
+               "r"(smem_u32(src)), "r"(bytes), "r"(bar_cluster_addr)
+               : "memory");
+}
+// generic-proxy writes (own and the peer's shared memory) -> visible to the async proxy, any state space
+__device__ __forceinline__ void fence_proxy_async_all() {
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
 // wait on a local mbarrier whose arrivals may come from the peer CTA (cluster-scope acquire)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;

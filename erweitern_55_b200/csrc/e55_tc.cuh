@@ -856,6 +856,12 @@ tower_kernel(const Params prm) {
   if (kProf && blockIdx.x == 0 && threadIdx.x == 0) prm.prof[15] = clock64();
 }
 
+}  // namespace tc
+}  // namespace e55
+#include "e55_tc_split.cuh"
+namespace e55 {
+namespace tc {
+
 // =================================================================================================
 // host side
 // =================================================================================================
@@ -871,6 +877,9 @@ struct State {
   int nstages = 0, nchunks = 0;
   int lag = 0;                      // free-running groups measured fastest (tools/tc_prof.py, E55_LAG)
   bool throughput_rounds = false;   // set by callers that run several chunk kernels concurrently: never use latency mode
+  bool no_split = false;            // set by callers that pipeline many small launches: throughput per SM matters more than latency
+  int split_max = 0;                // batches up to this size run on the channel-split kernel (e55_tc_split.cuh): an experiment that
+                                    // did NOT pay (98 us against 75 us at batch 16, see its header), off unless E55_SPLIT_MAX says so
   size_t smem_bytes = 0;
   uint8_t* d_wimg = nullptr;
   Chunk* d_chunks = nullptr;
@@ -882,12 +891,13 @@ struct State {
   unsigned long long* d_prof = nullptr;  // set by e55_debug_profile
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // when set, recorded around the tower kernel launch
   int capacity = 0;
-  bool attr_set = false;
+  bool attr_set = false, split_attr_set = false;
 };
 
 inline void init(State& s, int blocks, int filters, int in_planes, int sms) {
   s.blocks = blocks; s.filters = filters; s.in_planes = in_planes; s.sms = sms;
   s.nlayers = 1 + 2 * blocks + 2;
+  if (const char* env = getenv("E55_SPLIT_MAX")) s.split_max = atoi(env);   // 0 switches the latency kernel off
   s.in_planes8 = ((in_planes + 15) / 16) * 2;
   const int slice_planes = filters / 16;   // stem input slices fill half of the activation planes, alternating
   s.nslices = slice_planes > 0 ? (s.in_planes8 + slice_planes - 1) / slice_planes : 0;
@@ -1068,6 +1078,7 @@ inline cudaError_t set_weights(State& s, const std::vector<std::vector<float>>& 
   s.nstages = static_cast<int>(std::min<size_t>(kMaxStages, (232448 - std::min<size_t>(fixed, 232448)) / kStageBytes));
   s.smem_bytes = fixed + static_cast<size_t>(s.nstages) * kStageBytes;
   s.attr_set = false;
+  s.split_attr_set = false;
   return cudaSuccess;
 }
 
@@ -1095,6 +1106,37 @@ inline cudaError_t run(State& s, const float* d_planes, int n, float* d_policy, 
                            : cudaFuncSetAttribute(tower_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
     if (e != cudaSuccess) { *why = "cudaFuncSetAttribute"; return e; }
     s.attr_set = true;
+  }
+  // small batches (the reference's own: 1 and 16 positions): the channel-split latency kernel, one group per CTA pair
+  if (s.filters == 128 && !s.throughput_rounds && !s.no_split && n <= s.split_max && (s.d_prof == nullptr || getenv("E55_SPLIT_PROF"))) {
+    if (!s.split_attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(tower_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(s.smem_bytes));
+      if (e != cudaSuccess) { *why = "cudaFuncSetAttribute (split kernel)"; return e; }
+      s.split_attr_set = true;
+    }
+    Params p{};
+    p.wimg = s.d_wimg; p.chunks = s.d_chunks; p.layers = s.d_layers; p.bias = s.d_bias;
+    p.value_w = s.heads.d_value_w; p.fc1_k = s.heads.d_fc1_k; p.fc1_b = s.heads.d_fc1_b; p.fc2_k = s.heads.d_fc2_k;
+    p.value_b = s.heads.value_b; p.fc2_b = s.heads.fc2_b;
+    p.planes = d_planes; p.bits = packed.bits; p.scale = packed.scale; p.packed_stride = packed.stride ? packed.stride : s.in_planes;
+    p.in_planes = s.in_planes; p.in_planes8 = s.in_planes8; p.nslices = s.nslices;
+    p.nstages = s.nstages; p.nchunks_total = s.nchunks; p.nlayers = s.nlayers; p.nlayers_run = nlayers_run; p.n = n;
+    p.nrounds = (n + kPosPerGroup - 1) / kPosPerGroup; p.pos_per_round = kPosPerGroup;
+    p.policy = d_policy; p.value = d_value;
+    p.move_off = tail.move_off; p.move_idx = tail.move_idx; p.priors = tail.priors; p.move_stride = tail.move_stride;
+    p.mask = tail.mask; p.probs = tail.probs;
+    p.tail = (tail.priors != nullptr || tail.probs != nullptr || tail.rows) ? 1 : 0;
+    p.dbg = nlayers_run < s.nlayers ? s.d_dbg : nullptr;
+    p.lag = s.lag;
+    p.prof = s.d_prof;
+    const int clusters = std::min(p.nrounds, std::max(1, s.sms / 2));
+    if (s.ev0) cudaEventRecord(s.ev0, stream);
+    tower_split_kernel<<<2 * clusters, kSplitThreads, s.smem_bytes, stream>>>(p);
+    if (s.ev1) cudaEventRecord(s.ev1, stream);
+    ++*launched;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) *why = "tower_split_kernel launch";
+    return e;
   }
   // latency mode: while the batch fits the machine with one 4-position group per CTA, leave group B out
   const int ppr = (s.filters != 128 || (!s.throughput_rounds && n <= kPosPerGroup * 2 * std::max(1, s.sms / 2))) ? kPosPerGroup : kPosPerRound;

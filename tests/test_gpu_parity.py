@@ -875,3 +875,35 @@ def test_gpu_search_walks_like_the_oracle(weights_default, prefix, simulations, 
     assert len(played) - len(prefix) == search + (0 if info[7] else 1)    # every search ended in a move
     if prefix:
         assert terminals > 0                                          # the walk did run into fourth occurrences
+
+
+def test_channel_split_kernel_is_bit_identical(weights_perturbed):
+    """csrc/e55_tc_split.cuh (an experiment that did not pay and is off by default: E55_SPLIT_MAX switches it on): the two
+    CTAs of a cluster split every layer's output channels and exchange activations through distributed shared memory.
+    Its results must equal the throughput kernel's bit for bit -- logits, values, priors of the fused tail -- and its
+    trunk the fp32 path's within the bf16 tolerance."""
+    import os
+    from erweitern_55_b200 import packing
+    from erweitern_55_b200.network import Network
+    ref = Network(precision="bf16", weights=weights_perturbed)
+    os.environ["E55_SPLIT_MAX"] = "64"
+    try:
+        net = Network(precision="bf16", weights=weights_perturbed)
+    finally:
+        del os.environ["E55_SPLIT_MAX"]
+    rng = np.random.default_rng(5)
+    for n in (1, 3, 4, 5, 16, 37, 64):
+        x = synth.synthetic_planes(n, seed=700 + n)
+        p0, v0 = ref.predict(x)
+        p1, v1 = net.predict(x)
+        assert np.array_equal(p0, p1) and np.array_equal(v0, v1), n
+        bits, scale = packing.pack_planes(x)
+        counts = rng.integers(0, 50, size=n)
+        off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+        idx = rng.integers(0, 1725, size=int(off[-1])).astype(np.uint16)
+        q0, w0 = ref.predict_packed_moves(bits, scale, off, idx)
+        q1, w1 = net.predict_packed_moves(bits, scale, off, idx)
+        assert np.array_equal(q0, q1) and np.array_equal(w0, w1), n
+    x = synth.synthetic_planes(9, seed=3)
+    assert np.array_equal(ref.debug_activations(x, 5), net.debug_activations(x, 5))
+    ref.close(); net.close()

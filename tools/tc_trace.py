@@ -22,6 +22,8 @@ a = np.array(list(out), dtype=np.int64)
 np.save("gpurun_out/trace.npy", a)
 ia = a[16:16 + 4096].reshape(-1, 4); ib = a[16 + 4096:16 + 8192].reshape(-1, 4); ep = a[16 + 8192:].reshape(-1, 4)
 ia = ia[ia[:, 0] > 0]; ib = ib[ib[:, 0] > 0]; ep = ep[ep[:, 0] > 0]
+if len(ib) == 0:          # latency mode: one group per CTA
+    ib = ia
 t0 = min(ia[0, 0], ib[0, 0])
 print("chunks", len(ia), len(ib), "events", len(ep))
 print("issuer A: total", ia[-1, 3] - t0, " B:", ib[-1, 3] - t0)
