@@ -73,7 +73,8 @@ class SelfplayConfig(C.Structure):
     _fields_ = [("threads", C.c_int), ("games_per_thread", C.c_int), ("total_moves", C.c_long), ("simulations", C.c_int), ("leaf_batch", C.c_int),
                 ("mate_depth", C.c_int), ("reuse_tree", C.c_int), ("use_dirichlet", C.c_int),
                 ("sampling_moves", C.c_int), ("max_moves", C.c_int), ("seed", C.c_uint64),
-                ("sink", GAME_SINK), ("sink_user", C.c_void_p)]
+                ("sink", GAME_SINK), ("sink_user", C.c_void_p),
+                ("cap_enable", C.c_int), ("cap_full", C.c_int), ("cap_fast", C.c_int), ("cap_frac", C.c_float)]
 
 
 _pos = C.c_void_p
@@ -120,6 +121,7 @@ SIGNATURES.update({
     "e55_mcts_search_batches": (C.c_int, [_mcts, _ctx, _pos, C.c_int, C.c_int, C.c_int, C.c_int]),
     "e55_gpu_selfplay_run": (C.c_int, [_ctx, C.c_int, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.POINTER(SelfplayStats),
                                        C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
+    "e55_gpu_selfplay_set_cap": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, C.c_float]),
     "e55_gpu_search_open": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "e55_gpu_search_close": (None, [C.c_void_p]),
     "e55_gpu_search_select": (C.c_int, [C.c_void_p] + [C.c_void_p] * 8),

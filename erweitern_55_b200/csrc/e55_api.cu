@@ -117,6 +117,9 @@ struct e55_ctx {
   int32_t* d_move_off = nullptr;   // [capacity + 1]
   uint16_t* d_move_idx = nullptr;  // [capacity * kMovesPerPosition]
   float* d_priors = nullptr;       // [capacity * kMovesPerPosition]
+  // playout-cap oscillation of the GPU-resident self-play (e55_gpu_selfplay_set_cap; selfplay.py:45-61)
+  int gpu_cap_enable = 0, gpu_cap_full = 800, gpu_cap_fast = 128;
+  float gpu_cap_frac = 0.25f;
 };
 
 namespace {

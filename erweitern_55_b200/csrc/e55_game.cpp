@@ -196,6 +196,8 @@ struct SelfplayGame {
   uint64_t seq = 0;                  // order of the outstanding request among all games (batches complete in order)
   std::atomic_flag busy = ATOMIC_FLAG_INIT;   // a thread is working on this game
   int batches_left = 0, n_eval = 0, plies = 0, winner = 2;
+  bool full_search = true;           // playout-cap oscillation: this move's search is a full one (a learning target)
+  int sim_target = 0;                // simulations of this move's search
   std::string record;
   std::vector<std::pair<mshogi::Move, int>> visits;
   SelfplayGame() = default;
@@ -225,6 +227,7 @@ struct SelfplayWorker {
     if (sh->moves_left.load() > 0 && sh->failures.load() == 0) start_game(g);
     else g.state = SelfplayGame::kStopped;
   }
+  bool noise(const SelfplayGame& g) const { return sh->cfg.cap_enable ? g.full_search : sh->cfg.use_dirichlet != 0; }
   void play(SelfplayGame& g, const mshogi::Move& mv) {
     g.pos.do_move(mv);
     ++g.plies;
@@ -266,10 +269,20 @@ struct SelfplayWorker {
             play(g, mate_move);
             break;
           }
-          g.batches_left = (cfg.simulations + cfg.leaf_batch - 1) / cfg.leaf_batch;
-          const RootStatus rs = prepare_root(g.m.tree, s, g.pos, cfg.reuse_tree != 0);
+          // selfplay.py:45-61: under playout-cap oscillation a move is searched fully (N simulations, forced playouts,
+          // noise, fresh tree, pruned targets) with probability frac, else fast (n, counting the reused tree's visits)
+          g.full_search = true;
+          g.sim_target = cfg.simulations;
+          bool reuse = cfg.reuse_tree != 0;
+          if (cfg.cap_enable) {
+            g.full_search = std::uniform_real_distribution<float>(0.f, 1.f)(g.m.tree.rng) < cfg.cap_frac;
+            g.sim_target = g.full_search ? cfg.cap_full : cfg.cap_fast;
+            reuse = !g.full_search;
+          }
+          g.batches_left = (g.sim_target + cfg.leaf_batch - 1) / cfg.leaf_batch;
+          const RootStatus rs = prepare_root(g.m.tree, s, g.pos, reuse);
           if (rs == kRootNeedsEval) { g.state = SelfplayGame::kSubmitRoot; break; }
-          if (cfg.use_dirichlet) g.m.tree.add_noise(0);
+          if (noise(g)) g.m.tree.add_noise(0);
           g.state = SelfplayGame::kSelect;
           break;
         }
@@ -285,19 +298,22 @@ struct SelfplayWorker {
           if (rc != E55_OK) { sh->failures.fetch_add(1); g.state = SelfplayGame::kStopped; break; }
           progressed = true;
           finish_root(g.m.tree, s);
-          if (cfg.use_dirichlet) g.m.tree.add_noise(0);
+          if (noise(g)) g.m.tree.add_noise(0);
           g.state = SelfplayGame::kSelect;
           break;
         }
         case SelfplayGame::kSelect: {
           progressed = true;
+          // "immediate" (mcts.py:84-88, set for fast searches): the visits the reused tree already has count
+          if (cfg.cap_enable && !g.full_search && g.m.tree.playouts(0, true) >= g.sim_target) g.batches_left = 0;
           if (g.batches_left == 0) {                                             // selfplay.py:63-68
             const int chosen = g.pos.ply < cfg.sampling_moves ? g.m.tree.sample_edge(0, 1.f) : g.m.tree.best_edge(0);
             const Move next = g.m.tree.edge_move(0, chosen);
             if (cfg.sink) {                                                      // search.dump(root), selfplay.py:89
               int sum_n;
               float q;
-              g.m.tree.dump(0, false, true, sum_n, q, g.visits);
+              g.m.tree.dump(0, cfg.cap_enable && g.full_search, true, sum_n, q, g.visits);   // target pruning for full searches
+              if (cfg.cap_enable && !g.full_search) g.record += "~";                          // selfplay.py:90-91: not a learning target
               g.record += next.sfen() + " " + std::to_string(sum_n) + " " + std::to_string(q) + " " + std::to_string(g.visits.size());
               for (const auto& v : g.visits) g.record += " " + v.first.sfen() + " " + std::to_string(v.second);
               g.record += "\n";
@@ -306,7 +322,7 @@ struct SelfplayWorker {
             break;
           }
           --g.batches_left;
-          g.n_eval = prepare_batch(g.m.tree, s, g.pos, cfg.leaf_batch, false);
+          g.n_eval = prepare_batch(g.m.tree, s, g.pos, cfg.leaf_batch, cfg.cap_enable && g.full_search);   // forced playouts
           if (g.n_eval == 0) { finish_batch(g.m.tree, s, cfg.leaf_batch); break; }
           g.state = SelfplayGame::kSubmitBatch;
           break;
@@ -616,6 +632,7 @@ void e55_selfplay_default_config(e55_selfplay_config* cfg) {
   cfg->simulations = 800; cfg->leaf_batch = 16;          // client.py:28-29
   cfg->mate_depth = 7;                                   // selfplay.py:36
   cfg->reuse_tree = 1; cfg->use_dirichlet = 1;           // client.py:31-32
+  cfg->cap_enable = 0; cfg->cap_full = 800; cfg->cap_fast = 128; cfg->cap_frac = 0.25f;   // selfplay.py:10
   cfg->sampling_moves = 10; cfg->max_moves = 512;        // selfplay.py:10
   cfg->threads = 0; cfg->games_per_thread = 0;           // chosen from the core count
   cfg->seed = 1;
@@ -633,7 +650,8 @@ int e55_selfplay_run_ex(e55_ctx* c, const e55_selfplay_config* cfg_in, e55_selfp
   if (resolved.games_per_thread <= 0) resolved.games_per_thread = 12;   // enough to hide the GPU round trip, few enough to stay in cache
   const e55_selfplay_config* cfg = &resolved;
   if (cfg->total_moves < 1 || cfg->simulations < 1 || cfg->leaf_batch < 1 ||
-      cfg->leaf_batch > 256 || cfg->mate_depth < 0 || cfg->max_moves < 1)
+      cfg->leaf_batch > 256 || cfg->mate_depth < 0 || cfg->max_moves < 1 ||
+      (cfg->cap_enable && (cfg->cap_full < 1 || cfg->cap_fast < 1 || !(cfg->cap_frac >= 0.f && cfg->cap_frac <= 1.f))))
     return E55_ERR_INVALID;
   int64_t b0 = 0, p0 = 0, b1 = 0, p1 = 0;
   if (e55_service_stats(c, &b0, &p0) != E55_OK) return E55_ERR_INVALID;   // the evaluation service must be running

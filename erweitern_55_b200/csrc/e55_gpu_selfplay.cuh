@@ -79,6 +79,8 @@ struct Game {
   int32_t n_nodes, n_edges;
   int32_t pool;                        // which of the game's two tree pools holds the current tree
   int32_t sims_done;                   // simulations of the current search (-1: the root is not evaluated yet)
+  int32_t sim_target;                  // simulations this move's search gets (Params::simulations, or N / n under playout-cap oscillation)
+  int32_t full_search;                 // playout-cap oscillation: this move's search is a full one (forced playouts, noise, fresh tree, pruned targets)
   int32_t leaf[kMaxSel];               // this round's selections
   int8_t leaf_slot[kMaxSel];           // the network slot a selection is evaluated in (-1: none)
   int32_t n_sel;
@@ -119,6 +121,11 @@ struct Params {
   int n_games, game0, speculate, simulations, use_dirichlet, reuse_tree, sampling_moves, max_moves, record_cap, mate_depth;   // game0: index of the cohort's first game in the run
   long long move_budget;
   float c_puct, dirichlet_alpha, dirichlet_eps;
+  // playout-cap oscillation (selfplay.py:45-61,90-91; off as in client.py unless enabled): a move is searched fully (cap_full
+  // simulations, forced playouts, Dirichlet noise, fresh tree, pruned visit counts recorded as the learning target) with
+  // probability cap_frac, else fast (cap_fast simulations counting the visits the reused tree already has, no noise; no target)
+  int cap_enable, cap_full, cap_fast;
+  float cap_frac;
 };
 
 // ---- small device helpers ---------------------------------------------------------------------------------------
@@ -237,6 +244,17 @@ __device__ inline void path_encode(const PathView& pv, const Board& pos, uint32_
 }
 
 // ---- game bookkeeping ---------------------------------------------------------------------------------------------
+// What kind of search the move now on the board gets (selfplay.py:45-61).
+__device__ inline void begin_move(Game& g, const Params& p) {
+  g.full_search = 1;
+  g.sim_target = p.simulations;
+  if (p.cap_enable) {
+    g.full_search = next_unit(g.rng) < p.cap_frac ? 1 : 0;
+    g.sim_target = g.full_search ? p.cap_full : p.cap_fast;
+  }
+}
+__device__ inline bool noise_on(const Game& g, const Params& p) { return p.cap_enable ? g.full_search != 0 : p.use_dirichlet != 0; }
+
 __device__ inline void reset_tree(Game& g, GNode* nodes) {
   g.n_nodes = 1; g.n_edges = 0; g.sims_done = -1;
   GNode& r = nodes[0];
@@ -338,25 +356,52 @@ __device__ inline void record_ply(Game& g, const Params& p, int gi, uint16_t mv,
   constexpr int kCap = kRecordWords - 4;            // finish_game puts a four-word header in front
   uint16_t* rec = p.rec_buf + static_cast<size_t>(gi) * kRecordWords;
   int w = g.rec_words;
-  int k = 0, sum_n = 0;
-  float wsum = 0.f;
+  const bool prune = root && p.cap_enable && g.full_search;     // Mcts::dump with target_pruning (Wu 2019; mcts.py:187)
+  const bool target = !root || !p.cap_enable || g.full_search;  // selfplay.py:90-91
+  int k = 0, sum_n = 0, total = 0, best = 0;
+  float wsum = 0.f, sq = 0.f, best_score = 0.f;
+  if (root) {
+    for (int i = 0; i < root->n_edges; ++i) {
+      const GEdge& e = edges[root->first_edge + i];
+      total += e.n; wsum += e.w;
+      if (e.n > edges[root->first_edge + best].n) best = i;
+    }
+    sq = sqrtf(static_cast<float>(total));
+  }
+  // the count a child is recorded with: forced playouts are taken back from every child but the most visited one while
+  // its PUCT score, with its utility held, stays below the best child's; children left with one playout are dropped
+  auto puct = [&](const GEdge& e, int n) {
+    const float qi = e.n > 0 ? __fdiv_rn(e.w, static_cast<float>(e.n)) : 0.f;
+    return __fadd_rn(qi, __fdiv_rn(__fmul_rn(__fmul_rn(p.c_puct, e.prior), sq), __fadd_rn(1.f, static_cast<float>(n))));
+  };
+  if (prune && total > 0) best_score = puct(edges[root->first_edge + best], edges[root->first_edge + best].n);
+  auto count_of = [&](int i) {
+    const GEdge& e = edges[root->first_edge + i];
+    int c = e.n;
+    if (prune && total > 0 && i != best && c > 0) {
+      int forced = static_cast<int>(sqrtf(__fmul_rn(__fmul_rn(2.f, e.prior), static_cast<float>(total))));
+      while (forced > 0 && c > 0 && puct(e, c - 1) < best_score) { --c; --forced; }
+      if (c <= 1) c = 0;
+    }
+    return c;
+  };
   if (root)
-    for (int i = 0; i < root->n_edges; ++i) { const GEdge& e = edges[root->first_edge + i]; sum_n += e.n; wsum += e.w; k += e.n > 0; }
+    for (int i = 0; i < root->n_edges; ++i) { const int c = count_of(i); sum_n += c; k += c > 0; }
   else
     k = 1;                                          // a mate-search move: (1, 1.0, [(move, 1)])
   if (w + 4 > kCap) { g.rec_truncated = 1; return; }   // not even the move fits: the record ends here (flagged)
   const bool fits = w + 4 + 2 * k <= kCap;
   if (!fits) g.rec_truncated = 1;                   // the move is kept, its visit list is not (k = 0)
-  rec[w++] = mv;
+  rec[w++] = static_cast<uint16_t>(mv | (target ? 0u : 0x8000u));   // bit 15: not a learning target
   rec[w++] = static_cast<uint16_t>(root ? (sum_n > 65535 ? 65535 : sum_n) : 1);
-  rec[w++] = static_cast<uint16_t>(root ? (sum_n > 0 ? wsum / static_cast<float>(sum_n) : root->value) * 65535.f + 0.5f : 65535.f);
+  rec[w++] = static_cast<uint16_t>(root ? (total > 0 ? wsum / static_cast<float>(total) : root->value) * 65535.f + 0.5f : 65535.f);
   rec[w++] = static_cast<uint16_t>(fits ? k : 0);
   if (fits) {
     if (!root) { rec[w++] = mv; rec[w++] = 1; }
     else
       for (int i = 0; i < root->n_edges; ++i) {
-        const GEdge& e = edges[root->first_edge + i];
-        if (e.n > 0) { rec[w++] = e.mv; rec[w++] = static_cast<uint16_t>(e.n > 65535 ? 65535 : e.n); }
+        const int c = count_of(i);
+        if (c > 0) { rec[w++] = edges[root->first_edge + i].mv; rec[w++] = static_cast<uint16_t>(c > 65535 ? 65535 : c); }
       }
   }
   g.rec_words = w;
@@ -400,6 +445,7 @@ __device__ inline void finish_game(Game& g, const Params& p, int gi, GNode* node
   g.rec_truncated = 0;
   ++g.games_finished;
   start_game(g, nodes);
+  begin_move(g, p);
 }
 
 // Ask the host for the mate search of the position now on the board.
@@ -425,6 +471,7 @@ __global__ void init_kernel(Params p, uint64_t seed) {
   g.rec_words = 0;
   g.rec_truncated = 0;
   start_game(g, p.nodes + static_cast<size_t>(gi) * 2 * kMaxNodes);
+  begin_move(g, p);
   request_mate(g, p, gi);
 }
 
@@ -435,6 +482,7 @@ __global__ void prefix_kernel(Params p, const uint16_t* prefix, int n_prefix) {
   Game& g = p.games[gi];
   for (int i = 0; i < n_prefix; ++i) game_play(g, unpack_move(prefix[i]));
   reset_tree(g, p.nodes + (static_cast<size_t>(gi) * 2 + g.pool) * kMaxNodes);
+  begin_move(g, p);
   request_mate(g, p, gi);
 }
 
@@ -471,17 +519,17 @@ __global__ void __launch_bounds__(64) select_kernel(Params p) {
       int winner = 2;
       record_ply(g, p, gi, mate, nullptr, nullptr);
       if (play_and_judge(g, p, unpack_move(mate), winner)) finish_game(g, p, gi, nodes, winner);
-      else reset_tree(g, nodes);
+      else { reset_tree(g, nodes); begin_move(g, p); }
       request_mate(g, p, gi);          // the next move starts with a mate search too
     }
   }
-  if (g.need_mate && (!p.speculate || g.sims_done >= p.simulations || (g.sims_done >= 0 && nodes[0].terminal))) return;
-  if (g.sims_done >= p.simulations) return;   // the answer was all that was missing: expand_kernel ends the search
+  if (g.need_mate && (!p.speculate || g.sims_done >= g.sim_target || (g.sims_done >= 0 && nodes[0].terminal))) return;
+  if (g.sims_done >= g.sim_target) return;   // the answer was all that was missing: expand_kernel ends the search
   // mcts.py:71-73: "If the memory is used over 90%, suspend the search" -- the tree pools of a game are its memory.  The
   // search ends with the simulations done so far (expand_kernel chooses the move from them); nothing ever overflows.
   if (g.sims_done >= 0 && (g.n_nodes > kNodesSuspend || g.n_edges > kEdgesSuspend)) {
     atomicAdd(&p.shared->searches_suspended, 1ull);
-    g.sims_done = p.simulations;
+    g.sims_done = g.sim_target;
     g.n_sel = 0;
     return;
   }
@@ -490,6 +538,7 @@ __global__ void __launch_bounds__(64) select_kernel(Params p) {
   // A round selects until the game's 16 network slots are filled (selections that end in an expanded, terminal or
   // already claimed node need none), at most kMaxSel times; an unevaluated root takes a round of its own.
   const int max_sel = nodes[0].expanded ? kMaxSel : 1;
+  const bool forced = p.cap_enable && g.full_search;
   int used = 0, s = 0;
   for (; s < max_sel && used < kLeaf; ++s) {
     const size_t slot = static_cast<size_t>(gi) * kLeaf + used;
@@ -509,9 +558,18 @@ __global__ void __launch_bounds__(64) select_kernel(Params p) {
       // very order of operations, of Mcts::select_leaf (csrc/mcts.hpp) and oracle/mcts_oracle.py -- the three trees take
       // the same path bit for bit (tests/test_gpu_parity.py::test_gpu_search_walks_like_the_oracle)
       const float sq = sqrtf(static_cast<float>(total) + 1e-8f);
-      int best = 0;
+      int best = -1;
       float best_score = -1e30f;
-      for (int i = 0; i < nd.n_edges; ++i) {
+      if (forced && node == 0)   // forced playouts (Wu 2019; mcts.py:97): a visited root child gets at least sqrt(2 P N) playouts
+        for (int i = 0; i < nd.n_edges && best < 0; ++i) {
+          const uint4 r = raw[i];
+          const int nvi = static_cast<int>(r.z) + static_cast<int>(r.w >> 16);
+          if (static_cast<int>(r.z) > 0 &&
+              static_cast<float>(nvi) < sqrtf(__fmul_rn(__fmul_rn(2.f, __uint_as_float(r.x)), static_cast<float>(total))))
+            best = i;
+        }
+      const int n_scan = best < 0 ? nd.n_edges : 0;   // (no forced child: the PUCT scan)
+      for (int i = 0; i < n_scan; ++i) {
         const uint4 r = raw[i];
         const int nvi = static_cast<int>(r.z) + static_cast<int>(r.w >> 16);
         const float nv = static_cast<float>(nvi);
@@ -519,6 +577,7 @@ __global__ void __launch_bounds__(64) select_kernel(Params p) {
         const float score = __fadd_rn(q, __fdiv_rn(__fmul_rn(__fmul_rn(p.c_puct, __uint_as_float(r.x)), sq), __fadd_rn(1.f, nv)));
         if (score > best_score) { best_score = score; best = i; }
       }
+      if (best < 0) best = 0;
       GEdge& e = ed[best];
       if (e.vloss < 0xFFFF) ++e.vloss;
       Move m = unpack_move(e.mv);
@@ -609,7 +668,7 @@ __global__ void __launch_bounds__(64) expand_kernel(Params p) {
   GNode* nodes = p.nodes + (static_cast<size_t>(gi) * 2 + g.pool) * kMaxNodes;
   GEdge* edges = p.edges + (static_cast<size_t>(gi) * 2 + g.pool) * kMaxEdges;
   int32_t* child = p.child + (static_cast<size_t>(gi) * 2 + g.pool) * kMaxEdges;
-  if (g.n_sel == 0 && (g.need_mate || g.sims_done < p.simulations)) return;   // the game sat this round out
+  if (g.n_sel == 0 && (g.need_mate || g.sims_done < g.sim_target)) return;   // the game sat this round out
   const bool root_round = g.sims_done < 0;
   int evaluated = 0;
   // priors and values into the leaves evaluated this round (Mcts::expand_from_priors)
@@ -624,7 +683,7 @@ __global__ void __launch_bounds__(64) expand_kernel(Params p) {
     leaf.value = (p.value[slot] + 1.f) * 0.5f;      // mcts.py:59,103
     leaf.expanded = 1;
     leaf.claimed = 0;
-    if (g.leaf[s] == 0 && p.use_dirichlet)          // the freshly expanded root (the slot serves as scratch)
+    if (g.leaf[s] == 0 && noise_on(g, p))           // the freshly expanded root (the slot serves as scratch)
       root_noise(g, leaf, edges, p.priors + slot * kMoveStride, p.dirichlet_alpha, p.dirichlet_eps);
   }
   // back every selection up (Mcts::backpropagate)
@@ -649,7 +708,13 @@ __global__ void __launch_bounds__(64) expand_kernel(Params p) {
   atomicAdd(&p.shared->selections, static_cast<unsigned long long>(g.n_sel));
   if (root_round) { g.sims_done = 0; if (!nodes[0].terminal) return; }   // the root evaluation is not a simulation (mcts.py:55-60)
   else g.sims_done += done;
-  if (g.sims_done < p.simulations && !nodes[0].terminal) return;
+  if (p.cap_enable && !g.full_search && g.sims_done >= 0 && g.sims_done < g.sim_target) {
+    // "immediate" (mcts.py:84-88, set for fast searches): the visits the reused tree already has count
+    int visits = 0;
+    for (int i = 0; i < nodes[0].n_edges; ++i) visits += edges[nodes[0].first_edge + i].n;
+    if (visits >= g.sim_target) g.sims_done = g.sim_target;
+  }
+  if (g.sims_done < g.sim_target && !nodes[0].terminal) return;
   if (g.need_mate) return;             // a mate found by the host goes first (select_kernel)
 
   // ---- the search of this move is over: choose, play, look at the game (selfplay.py:63-78,17-31) -----------------
@@ -677,19 +742,30 @@ __global__ void __launch_bounds__(64) expand_kernel(Params p) {
   }
   if (over) {
     finish_game(g, p, gi, nodes, winner);
-  } else if (p.reuse_tree && kept_root >= 0 && nodes[kept_root].expanded && !nodes[kept_root].terminal) {
-    // Mcts::set_root with reuse_tree (mcts.py:50; client.py:32): the chosen move's subtree becomes the tree; its root is
-    // expanded already, so the next search starts with simulations at once -- after fresh noise on the root priors
-    keep_subtree(g, p, gi, kept_root);
-    atomicAdd(&p.shared->kept_nodes, static_cast<unsigned long long>(g.n_nodes));
-    g.sims_done = 0;
-    if (p.use_dirichlet) {
-      GNode* kn = p.nodes + (static_cast<size_t>(gi) * 2 + g.pool) * kMaxNodes;
-      root_noise(g, kn[0], p.edges + (static_cast<size_t>(gi) * 2 + g.pool) * kMaxEdges, p.priors + static_cast<size_t>(gi) * kLeaf * kMoveStride,
-                 p.dirichlet_alpha, p.dirichlet_eps);
-    }
   } else {
-    reset_tree(g, nodes);
+    begin_move(g, p);                    // the kind of search the next move gets decides whether its tree starts afresh
+    const bool reuse = p.cap_enable ? !g.full_search : p.reuse_tree != 0;
+    if (reuse && kept_root >= 0 && nodes[kept_root].expanded && !nodes[kept_root].terminal) {
+      // Mcts::set_root with reuse_tree (mcts.py:50; client.py:32): the chosen move's subtree becomes the tree; its root is
+      // expanded already, so the next search starts with simulations at once -- after fresh noise on the root priors
+      keep_subtree(g, p, gi, kept_root);
+      atomicAdd(&p.shared->kept_nodes, static_cast<unsigned long long>(g.n_nodes));
+      g.sims_done = 0;
+      if (p.cap_enable && !g.full_search) {   // "immediate": a kept tree with enough visits needs no search at all
+        const GNode* kn = p.nodes + (static_cast<size_t>(gi) * 2 + g.pool) * kMaxNodes;
+        const GEdge* ke = p.edges + (static_cast<size_t>(gi) * 2 + g.pool) * kMaxEdges;
+        int visits = 0;
+        for (int i = 0; i < kn[0].n_edges; ++i) visits += ke[kn[0].first_edge + i].n;
+        if (visits >= g.sim_target) g.sims_done = g.sim_target;
+      }
+      if (noise_on(g, p)) {
+        GNode* kn = p.nodes + (static_cast<size_t>(gi) * 2 + g.pool) * kMaxNodes;
+        root_noise(g, kn[0], p.edges + (static_cast<size_t>(gi) * 2 + g.pool) * kMaxEdges, p.priors + static_cast<size_t>(gi) * kLeaf * kMoveStride,
+                   p.dirichlet_alpha, p.dirichlet_eps);
+      }
+    } else {
+      reset_tree(g, nodes);
+    }
   }
   request_mate(g, p, gi);              // selfplay.py:35-36: every move starts with the mate search
 }

@@ -109,6 +109,16 @@ int e55_selftest_encode(int device, int n, uint64_t seed, int64_t* mismatches_ou
   return E55_OK;
 }
 
+int e55_gpu_selfplay_set_cap(e55_ctx* c, int enable, int full_simulations, int fast_simulations, float frac) {
+  namespace gs = e55::gs;
+  if (!c) return E55_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (enable && (full_simulations < gs::kLeaf || full_simulations > 1024 || fast_simulations < 1 || fast_simulations > 1024 || !(frac >= 0.f && frac <= 1.f)))
+    return fail(c, E55_ERR_INVALID, "playout-cap oscillation: simulations in [16, 1024] / [1, 1024], frac in [0, 1]");
+  c->gpu_cap_enable = enable != 0; c->gpu_cap_full = full_simulations; c->gpu_cap_fast = fast_simulations; c->gpu_cap_frac = frac;
+  return E55_OK;
+}
+
 // ---- debug stepper: ONE game's search, a round at a time, with the caller playing the network ---------------------------
 // (tests hold select_kernel / expand_kernel to oracle/mcts_oracle.py selection by selection with it)
 struct e55_gpu_search {
@@ -156,6 +166,8 @@ int e55_gpu_search_open(e55_ctx* c, const uint16_t* prefix, int n_prefix, int si
   p.n_games = 1; p.game0 = 0; p.simulations = simulations; p.use_dirichlet = 0; p.reuse_tree = reuse_tree; p.mate_depth = 0;
   p.speculate = 0; p.sampling_moves = 0; p.max_moves = gs::kMaxPly; p.record_cap = 1; p.move_budget = 1 << 30;
   p.c_puct = 1.25f; p.dirichlet_alpha = 0.15f; p.dirichlet_eps = 0.25f;
+  p.cap_enable = c->gpu_cap_enable; p.cap_full = c->gpu_cap_full; p.cap_fast = c->gpu_cap_fast; p.cap_frac = c->gpu_cap_frac;
+  if (p.cap_enable) p.dirichlet_eps = 0.f;   // (the stepper's searches are deterministic: noise of weight 0 leaves the priors alone)
   if (e == cudaSuccess && n_prefix > 0) e = cudaMemcpyAsync(d_prefix, prefix, n_prefix * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream);
   if (e == cudaSuccess) {
     gs::init_kernel<<<1, 64, 0, c->stream>>>(p, 1);
@@ -322,6 +334,7 @@ int e55_gpu_selfplay_run(e55_ctx* c, int games, long total_moves, int simulation
   p.speculate = !(getenv("E55_GPU_SPECULATE") && atoi(getenv("E55_GPU_SPECULATE")) == 0);   // search on while the host looks for a mate
   p.sampling_moves = sampling_moves; p.max_moves = std::min(max_moves, gs::kMaxPly); p.record_cap = record_cap; p.move_budget = total_moves;
   p.c_puct = 1.25f; p.dirichlet_alpha = 0.15f; p.dirichlet_eps = 0.25f;
+  p.cap_enable = c->gpu_cap_enable; p.cap_full = c->gpu_cap_full; p.cap_fast = c->gpu_cap_fast; p.cap_frac = c->gpu_cap_frac;
   // Two cohorts of games on two streams: while the network evaluates one cohort's leaves the search kernels of the other
   // run beside it.  The tower kernel is a persistent kernel with one CTA per SM that leaves no room for anything else
   // on its SMs, so for the run it gets 24 SMs fewer and the (latency-bound, small) search kernels get those

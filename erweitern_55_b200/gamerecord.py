@@ -26,9 +26,11 @@ class GameRecord:
         for line in lines[1:]:
             f = line.split()
             k = int(f[3])
-            rec.sfen_kif.append(f[0])
+            target = not f[0].startswith("~")       # fast searches under playout-cap oscillation (selfplay.py:90-91)
+            rec.sfen_kif.append(f[0].lstrip("~"))
             rec.mcts_result.append((int(f[1]), float(f[2]), [(f[4 + 2 * i], int(f[5 + 2 * i])) for i in range(k)]))
-            rec.learning_target_plys.append(rec.ply)
+            if target:
+                rec.learning_target_plys.append(rec.ply)
             rec.ply += 1
         rec.timestamp = timestamp
         return rec

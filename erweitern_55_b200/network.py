@@ -228,13 +228,15 @@ class Network:
         return stats
 
     def gpu_selfplay(self, games, total_moves, simulations=800, mate_depth=7, reuse_tree=True, use_dirichlet=True, num_sampling_moves=10,
-                     max_moves=512, seed=1, records=0):
+                     max_moves=512, seed=1, records=0, playout_cap_oscillation=None):
         """GPU-resident self-play (``csrc/e55_gpu_selfplay.cuh``): ``games`` games at once with tree search, move
         generation and input encoding on the GPU (the host only answers the mate searches), until ``total_moves`` plies
         were played.  Returns ``(stats, game_records)``; ``game_records`` holds the first ``records`` finished games as
         :class:`erweitern_55_b200.gamerecord.GameRecord` -- what ``selfplay.run`` returns (selfplay.py:10-113)."""
         import time
         from .gamerecord import GameRecord
+        cap = playout_cap_oscillation or {"enable": False, "N": 800, "n": 128, "frac": 0.25}     # selfplay.py:10
+        self._check(self._lib.e55_gpu_selfplay_set_cap(self._ctx, int(bool(cap["enable"])), int(cap["N"]), int(cap["n"]), float(cap["frac"])))
         st = _capi.SelfplayStats()
         words = 16384
         buf = np.zeros((max(records, 1), words), dtype=np.uint16)
@@ -256,12 +258,13 @@ class Network:
             rec = GameRecord()
             rec.winner, used, truncated, w = int(row[1]), int(row[2]), int(row[3]), 4
             while w < 4 + used:
-                mv, sum_n, q, k = int(row[w]), int(row[w + 1]), int(row[w + 2]) / 65535.0, int(row[w + 3])
+                mv, sum_n, q, k = int(row[w]) & 0x7FFF, int(row[w + 1]), int(row[w + 2]) / 65535.0, int(row[w + 3])
+                target = not (int(row[w]) >> 15)       # fast searches under playout-cap oscillation are no targets (selfplay.py:90-91)
                 visits = [(sfen(int(row[w + 4 + 2 * i])), int(row[w + 5 + 2 * i])) for i in range(k)]
                 w += 4 + 2 * k
                 rec.sfen_kif.append(sfen(mv))
                 rec.mcts_result.append((sum_n, q, visits))
-                if k > 0:                              # a ply whose visit list did not fit the record is no learning target
+                if k > 0 and target:                   # (nor is a ply whose visit list did not fit the record)
                     rec.learning_target_plys.append(rec.ply)
                 rec.ply += 1
             rec.timestamp = now

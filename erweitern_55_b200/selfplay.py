@@ -132,7 +132,8 @@ def random_play(max_moves=512, stop_with_checkmate=False, trim_checkmate=False):
 
 
 def run_many(nn, threads=0, total_moves=1000, simulations=800, leaf_batch=16, mate_depth=7, reuse_tree=True,
-             use_dirichlet=True, num_sampling_moves=10, max_moves=512, seed=1, records=True, games_per_thread=0):
+             use_dirichlet=True, num_sampling_moves=10, max_moves=512, seed=1, records=True, games_per_thread=0,
+             playout_cap_oscillation=None):
     """Play games on ``threads`` host threads (0: cores - 2) working through a pool of ``threads x games_per_thread``
     games (0: 12 per thread; a service batch of about 74 positions per thread suits that) kept in flight on the asynchronous evaluation service, until ``total_moves`` plies were played; the service of ``nn`` must be running
     (``nn.start_service``).  Returns ``(stats dict, [GameRecord of each finished game])``."""
@@ -143,6 +144,9 @@ def run_many(nn, threads=0, total_moves=1000, simulations=800, leaf_batch=16, ma
     cfg.games_per_thread = games_per_thread
     cfg.mate_depth, cfg.reuse_tree, cfg.use_dirichlet = mate_depth, int(reuse_tree), int(use_dirichlet)
     cfg.sampling_moves, cfg.max_moves, cfg.seed = num_sampling_moves, max_moves, seed
+    if playout_cap_oscillation and playout_cap_oscillation.get("enable"):     # selfplay.py:45-61
+        cap = playout_cap_oscillation
+        cfg.cap_enable, cfg.cap_full, cfg.cap_fast, cfg.cap_frac = 1, int(cap["N"]), int(cap["n"]), float(cap["frac"])
     games = []
     if records:
         def sink(_user, text):

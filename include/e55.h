@@ -238,7 +238,8 @@ typedef struct e55_selfplay_stats {
 } e55_selfplay_stats;
 
 /* Receives one finished game as text: "winner W ply P\n" then one line per ply
- * "<move> <sum_N> <Q> <k> <m1> <n1> ... <mk> <nk>" (gamerecord.py:3-9).  Calls are serialised. */
+ * "<move> <sum_N> <Q> <k> <m1> <n1> ... <mk> <nk>" (gamerecord.py:3-9); a ply that is not a learning target (a fast
+ * search under playout-cap oscillation) has '~' in front of its move.  Calls are serialised. */
 typedef void (*e55_game_sink)(void* user, const char* record);
 
 typedef struct e55_selfplay_config {
@@ -256,6 +257,14 @@ typedef struct e55_selfplay_config {
   uint64_t seed;
   e55_game_sink sink;      /* optional: game records */
   void* sink_user;
+  /* Playout-cap oscillation (selfplay.py:45-61,90-91; off by default as in client.py): with probability cap_frac a move
+   * gets a FULL search -- cap_full simulations, forced playouts, Dirichlet noise, a fresh tree, pruned visit counts as
+   * the training target -- otherwise a FAST one -- cap_fast simulations counting the visits the reused tree already has
+   * ("immediate"), no noise, no forced playouts -- whose ply is not a learning target (its record line starts with '~'). */
+  int cap_enable;
+  int cap_full;            /* N (selfplay.py:10: 800) */
+  int cap_fast;            /* n (128) */
+  float cap_frac;          /* 0.25 */
 } e55_selfplay_config;
 void e55_selfplay_default_config(e55_selfplay_config* cfg);
 
@@ -277,7 +286,8 @@ int e55_selfplay_run(e55_ctx* ctx, int threads, long total_moves, int simulation
  * that one cohort's search overlaps the other's network launch.  simulations: a multiple of 16, at most 1024.
  * records (optional): the first record_cap finished games, 16384 uint16 words each: plies, winner, words used, truncated (0/1),
  * then per ply what selfplay.run records (selfplay.py:80-92) -- move, sum_N, Q * 65535, k, and k (move, N) pairs of
- * the visited root children; moves are packed as from (31 = drop) | to << 5 | piece << 10 | promotes << 14.
+ * the visited root children; moves are packed as from (31 = drop) | to << 5 | piece << 10 | promotes << 14 (bit 15 of a
+ * ply's own move word: not a learning target -- a fast search under playout-cap oscillation).
  * stats_out->mean_gpu_batch is the positions per network launch (16 slots per game of a cohort). */
 int e55_gpu_selfplay_run(e55_ctx* ctx, int games, long total_moves, int simulations, int mate_depth, int reuse_tree,
                          int use_dirichlet, int sampling_moves, int max_moves, uint64_t seed, e55_selfplay_stats* stats_out,
@@ -298,6 +308,12 @@ void e55_gpu_search_close(e55_gpu_search* h);
 int e55_gpu_search_select(e55_gpu_search* h, int32_t* info, int32_t* sel_leaf, int32_t* sel_slot, int32_t* sel_path_len,
                           uint16_t* sel_path, int32_t* slot_cnt, uint16_t* slot_moves, uint16_t* slot_idx);
 int e55_gpu_search_expand(e55_gpu_search* h, const float* priors, const float* value, int32_t* info, uint16_t* record);
+
+/* Playout-cap oscillation for the GPU-resident self-play and its debug stepper (selfplay.py:45-61,90-91; off by default,
+ * as in client.py): with probability frac a move gets a full search (full_simulations, forced playouts, Dirichlet noise, a
+ * fresh tree, pruned visit counts in the record), otherwise a fast one (fast_simulations counting the reused tree's visits,
+ * no noise) whose ply is not a learning target (bit 15 of its move word in the record). */
+int e55_gpu_selfplay_set_cap(e55_ctx* ctx, int enable, int full_simulations, int fast_simulations, float frac);
 
 /* Device build of the rules engine: perft from the start position computed on the GPU (14, 181, 2512, 35401, ...). */
 int e55_selftest_engine(int device, int depth, int64_t* nodes_out);

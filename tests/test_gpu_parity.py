@@ -747,11 +747,12 @@ def test_umma_addressing_selftest():
         assert err.value == 0.0
 
 
-@pytest.mark.parametrize("prefix,simulations,searches", [
-    ([], 800, 3),                                                     # the opening, as self-play searches it; tree reuse twice
-    (["5e4d", "1a2b", "4d5e", "2b1a", "5e4d", "1a2b", "4d5e", "2b1a", "5e4d", "1a2b"], 480, 2),   # a repetition within reach of the search
-])
-def test_gpu_search_walks_like_the_oracle(weights_default, prefix, simulations, searches):
+@pytest.mark.parametrize("prefix,simulations,searches,full", [
+    ([], 800, 3, False),                                              # the opening, as self-play searches it; tree reuse twice
+    (["5e4d", "1a2b", "4d5e", "2b1a", "5e4d", "1a2b", "4d5e", "2b1a", "5e4d", "1a2b"], 480, 2, False),   # a repetition within reach of the search
+    ([], 640, 2, True),                                               # "full" searches of playout-cap oscillation (selfplay.py:47-53):
+])                                                                    # forced playouts, fresh tree per move, pruned targets
+def test_gpu_search_walks_like_the_oracle(weights_default, prefix, simulations, searches, full):
     """select_kernel / expand_kernel (GPU-resident self-play) against oracle/mcts_oracle.py, selection by selection: one
     game through the debug stepper with the test in the network's place (uniform priors over a pseudo-random subset of
     the legal moves, values k/8: exact in float32).  Every selection of every round must take the oracle's path, every
@@ -797,6 +798,7 @@ def test_gpu_search_walks_like_the_oracle(weights_default, prefix, simulations, 
 
     h = C.c_void_p()
     arr = (C.c_uint16 * max(1, len(packed_prefix)))(*packed_prefix)
+    net._check(lib.e55_gpu_selfplay_set_cap(net._ctx, int(full), simulations, 128, 1.0))     # frac 1: every search a full one
     net._check(lib.e55_gpu_search_open(net._ctx, arr, len(packed_prefix), simulations, 1, C.byref(h)))
     info = (C.c_int32 * 8)(); leaf = (C.c_int32 * 24)(); slot = (C.c_int32 * 24)(); plen = (C.c_int32 * 24)()
     path = (C.c_uint16 * (24 * 96))(); cnt = (C.c_int32 * 16)(); mvs = (C.c_uint16 * (16 * 256))(); idx = (C.c_uint16 * (16 * 256))()
@@ -815,7 +817,7 @@ def test_gpu_search_walks_like_the_oracle(weights_default, prefix, simulations, 
             sel = []
             for s in range(n_sel):                                    # the round's selections, virtual losses piling up
                 pos_o = oracle_position()
-                leaf_o = oracle.select_leaf(oracle.root, pos_o)
+                leaf_o = oracle.select_leaf(oracle.root, pos_o, full)
                 want = [packed_move_sfen(path[s * 96 + i]) for i in range(plen[s])]
                 node, walk = leaf_o, []
                 while node.parent is not None:
@@ -856,20 +858,24 @@ def test_gpu_search_walks_like_the_oracle(weights_default, prefix, simulations, 
         w, last = base, None
         while w < base + words:
             k = record[w + 3]
-            last = (record[w], record[w + 1], record[w + 2] / 65535.0, {packed_move_sfen(record[w + 4 + 2 * i]): record[w + 5 + 2 * i] for i in range(k)})
+            last = (record[w] & 0x7FFF, record[w + 1], record[w + 2] / 65535.0, {packed_move_sfen(record[w + 4 + 2 * i]): record[w + 5 + 2 * i] for i in range(k)})
+            assert not (record[w] >> 15)                              # (every ply here is a learning target)
             w += 4 + 2 * k
         mv, sum_n, q, visits = last
-        assert visits == oracle.visits() and sum_n == sum(oracle.root.n_edge)
-        assert abs(q - sum(float(x) for x in oracle.root.w) / sum_n) < 2e-5
+        assert visits == oracle.visits(target_pruning=full) and sum_n == sum(visits.values())
+        if full:
+            assert visits != oracle.visits()                          # (the pruning did take forced playouts back)
+        assert abs(q - sum(float(x) for x in oracle.root.w) / sum(oracle.root.n_edge)) < 2e-5
         best = max(range(len(oracle.root.moves)), key=lambda i: (oracle.root.n_edge[i], -i))
         assert packed_move_sfen(mv) == oracle.root.moves[best]
         if info[7]:
             break                                                     # the move ended the game
-        kept = oracle.root.child[best]
+        kept = oracle.root.child[best] if not full else None          # a full search starts from a fresh tree
         played.append(oracle.root.moves[best])
         oracle.root = kept if (kept is not None and kept.expanded and not kept.terminal) else Tree().root
         oracle.root.parent, oracle.root.parent_edge = None, -1
     lib.e55_gpu_search_close(h)
+    net._check(lib.e55_gpu_selfplay_set_cap(net._ctx, 0, 800, 128, 0.25))
     net.close()
     assert total_selections >= simulations * (search + 1) - 24 * (search + 1) or info[7]
     assert len(played) - len(prefix) == search + (0 if info[7] else 1)    # every search ended in a move
@@ -907,3 +913,46 @@ def test_channel_split_kernel_is_bit_identical(weights_perturbed):
     x = synth.synthetic_planes(9, seed=3)
     assert np.array_equal(ref.debug_activations(x, 5), net.debug_activations(x, 5))
     ref.close(); net.close()
+
+
+def test_playout_cap_oscillation_in_the_native_drivers(weights_default):
+    """selfplay.py:45-61,90-91 in the host driver (e55_selfplay_run_ex) and in the GPU-resident one: fast searches (n
+    simulations, reused tree) are no learning targets, full searches (N, forced playouts, fresh tree, pruned counts)
+    and mate moves are; the games stay legal."""
+    from erweitern_55_b200 import selfplay
+    from erweitern_55_b200.minishogi import Move, Position
+    from erweitern_55_b200.network import Network
+    net = Network(precision="bf16", weights=weights_default)
+    cap = {"enable": True, "N": 96, "n": 32, "frac": 0.4}
+
+    def check(games):
+        targets = plies = full_sum = 0
+        for rec in games:
+            p = Position()
+            for ply, (m, (sum_n, q, visits)) in enumerate(zip(rec.sfen_kif, rec.mcts_result)):
+                legal = {x.sfen() for x in p.generate_moves()}
+                assert m in legal and all(v in legal for v, _ in visits)
+                is_target = ply in rec.learning_target_plys
+                is_mate = (sum_n, visits) == (1, [(m, 1)])
+                if not is_mate:
+                    if is_target:
+                        assert sum_n <= cap["N"] + 24 and sum(n for _, n in visits) == sum_n   # pruned: only what is kept is counted
+                        full_sum += sum_n
+                    else:
+                        assert sum_n >= cap["n"]                                            # the reused tree's visits count
+                targets += is_target; plies += 1
+                p.do_move(Move(m))
+        assert 0.2 * plies < targets < 0.8 * plies, (targets, plies)
+        return targets, plies
+
+    stats, games = net.gpu_selfplay(games=256, total_moves=6000, simulations=96, records=128, seed=3, max_moves=60, mate_depth=3,
+                                    playout_cap_oscillation=cap)
+    assert stats["tree_overflows"] == 0 and len(games) >= 32
+    check(games)
+    net.start_service(max_batch=256, max_wait_us=200)
+    stats, games = selfplay.run_many(net, threads=2, total_moves=1500, simulations=96, leaf_batch=16, mate_depth=3, seed=5, max_moves=60,
+                                     playout_cap_oscillation=cap)
+    net.stop_service()
+    assert len(games) >= 10
+    check(games)
+    net.close()
