@@ -15,7 +15,7 @@ import ctypes as C
 import numpy as np
 
 from . import _capi, hostmem
-from .weights import IN_PLANES, POLICY_SIZE, infer_arch, init_weights, weight_spec
+from .weights import IN_PLANES, POLICY_SIZE, adapt_weights, infer_arch, init_weights, weight_spec
 
 _PRECISIONS = {"fp32": _capi.PRECISION_FP32, "bf16": _capi.PRECISION_BF16_TC}
 
@@ -60,6 +60,7 @@ class Network:
         self._ctx = C.c_void_p()
         self._iterations = 0
         self._weights = None
+        self._layout = None                             # (plane_perm, plane_scale, policy_perm) of set_layout_adapter
         self._service_cap = 0
         rc = self._lib.e55_create(C.byref(self._ctx), self._device, blocks, filters, in_planes, max_batch)
         if rc != _capi.E55_OK:
@@ -101,8 +102,19 @@ class Network:
     def get_weights(self):
         return [w.copy() for w in self._weights]
 
+    def set_layout_adapter(self, plane_perm=None, plane_scale=None, policy_perm=None):
+        """Declare that the weights handed to :meth:`set_weights` / :meth:`load` were trained on another input-plane /
+        policy-channel layout than this package's native engine produces (i.e. by the reference with minishogilib, whose
+        layout is not visible in the reference tree): see :func:`erweitern_55_b200.weights.adapt_weights` for the three
+        tables.  The permutation is folded into the first and last tensors when weights are installed -- predict() costs
+        the same -- and :meth:`get_weights` keeps returning the list in the checkpoint's own layout."""
+        self._layout = None if (plane_perm is None and plane_scale is None and policy_perm is None) else (plane_perm, plane_scale, policy_perm)
+        if self._weights is not None:
+            self.set_weights(self._weights)
+
     def set_weights(self, weights):
-        ws = [np.ascontiguousarray(np.asarray(w, dtype=np.float32)) for w in weights]
+        original = [np.ascontiguousarray(np.asarray(w, dtype=np.float32)) for w in weights]
+        ws = original if self._layout is None else adapt_weights(original, *self._layout)
         blocks, filters, in_planes = infer_arch(ws)
         if (blocks, filters, in_planes) != (self._blocks, self._filters, self._in_planes):
             raise ValueError(f"weight list describes a {blocks}x{filters} tower on {in_planes} planes, "
@@ -113,7 +125,7 @@ class Network:
         shapes = (C.POINTER(C.c_int64) * n)(*[C.cast(s, C.POINTER(C.c_int64)) for s in shape_arrays])
         ndims = (C.c_int * n)(*[w.ndim for w in ws])
         self._check(self._lib.e55_set_weights(self._ctx, n, data, shapes, ndims))
-        self._weights = ws
+        self._weights = original
 
     def load_pickled_weights(self, blob):
         """Install weights from the reference's wire format: ``_pickle.dumps(nn.get_weights(), protocol=4)``
@@ -136,6 +148,12 @@ class Network:
             return
         if path.endswith((".h5", ".hdf5", ".keras")):
             from . import hdf5
+            if self._layout is None:
+                import warnings
+                warnings.warn("loading a Keras checkpoint without a layout adapter: it matches this package's native engine "
+                              "(minishogi.Position / MCTS, GPU self-play) only if it was trained on this package's plane and "
+                              "policy-channel layout; for checkpoints trained by the reference with minishogilib call "
+                              "set_layout_adapter() first (predict() on the caller's own planes is unaffected)", stacklevel=2)
             self.set_weights(hdf5.read_keras_weights(filepath))
             return
         with np.load(filepath) as z:

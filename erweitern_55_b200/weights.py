@@ -135,3 +135,41 @@ def infer_arch(weights):
         raise ValueError(f"unexpected number of weight tensors: {n}")
     blocks = (n - 24) // 12
     return blocks, filters, in_planes
+
+
+def adapt_weights(weights, plane_perm=None, plane_scale=None, policy_perm=None):
+    """Weights trained on ANOTHER plane / policy-channel layout, re-expressed for this package's layout -- at no run-time
+    cost, by permuting the network's first and last tensors.
+
+    The 266 input planes and the 69 policy channels are defined inside minishogilib (``Position.to_alphazero_input``,
+    ``MCTS.evaluate``; network.py:258, mcts.py:60,105), which is not part of the reference tree; this package's native
+    engine uses its own, documented layout (csrc/minishogi.hpp).  A checkpoint trained by the reference therefore
+    matches the native encoder only through a layout table, which a maintainer who has minishogilib can write down:
+
+    * ``plane_perm[c]`` = index, in the checkpoint's layout, of the plane this package calls ``c``; ``plane_scale[c]`` =
+      factor between the two conventions (checkpoint's value = scale x ours, e.g. hand counts / 2 against raw counts):
+      the stem kernel becomes ``K'[:, :, c, :] = K[:, :, plane_perm[c], :] * plane_scale[c]``;
+    * ``policy_perm[k]`` = checkpoint's policy channel for this package's channel ``k`` (logit index ``k*25 + square``):
+      the policy 1x1 kernel and bias become ``K'[..., k] = K[..., policy_perm[k]]``.
+
+    Returns a new list; the input is not modified.  ``Network.set_layout_adapter`` applies it on every ``set_weights``."""
+    ws = [np.asarray(w, dtype=np.float32) for w in weights]
+    _, filters, in_planes = infer_arch(ws)
+    out = list(ws)
+    if plane_perm is not None or plane_scale is not None:
+        perm = np.arange(in_planes) if plane_perm is None else np.asarray(plane_perm, dtype=np.int64)
+        scale = np.ones(in_planes, dtype=np.float32) if plane_scale is None else np.asarray(plane_scale, dtype=np.float32)
+        if perm.shape != (in_planes,) or scale.shape != (in_planes,) or perm.min() < 0 or perm.max() >= in_planes:
+            raise ValueError(f"plane_perm / plane_scale must have {in_planes} entries in [0, {in_planes})")
+        out[0] = np.ascontiguousarray(ws[0][:, :, perm, :] * scale.reshape(1, 1, -1, 1))
+    if policy_perm is not None:
+        perm = np.asarray(policy_perm, dtype=np.int64)
+        if perm.shape != (POLICY_CHANNELS,) or sorted(perm.tolist()) != list(range(POLICY_CHANNELS)):
+            raise ValueError(f"policy_perm must be a permutation of range({POLICY_CHANNELS})")
+        hits = [i for i, w in enumerate(ws) if w.shape == (1, 1, filters, POLICY_CHANNELS)]
+        if len(hits) != 1 or ws[hits[0] + 1].shape != (POLICY_CHANNELS,):
+            raise ValueError("policy 1x1 convolution not found in the weight list")
+        i = hits[0]
+        out[i] = np.ascontiguousarray(ws[i][..., perm])
+        out[i + 1] = np.ascontiguousarray(ws[i + 1][perm])
+    return out

@@ -956,3 +956,26 @@ def test_playout_cap_oscillation_in_the_native_drivers(weights_default):
     assert len(games) >= 10
     check(games)
     net.close()
+
+
+def test_layout_adapter_on_the_gpu(weights_perturbed):
+    """Network.set_layout_adapter folds a foreign plane / policy-channel layout into the installed weights: same results
+    as installing the adapted list, get_weights() still the checkpoint's own list, and no effect once it is cleared."""
+    from erweitern_55_b200 import weights as W
+    from erweitern_55_b200.network import Network
+    rng = np.random.default_rng(2)
+    plane_perm, policy_perm = rng.permutation(266), rng.permutation(69)
+    plane_scale = rng.choice([1.0, 0.5], size=266).astype(np.float32)
+    x = synth.synthetic_planes(9, seed=4)
+    a = Network(precision="bf16", weights=weights_perturbed)
+    p_plain, v_plain = a.predict(x)
+    a.set_layout_adapter(plane_perm, plane_scale, policy_perm)
+    b = Network(precision="bf16", weights=W.adapt_weights(weights_perturbed, plane_perm, plane_scale, policy_perm))
+    pa, va = a.predict(x)
+    pb, vb = b.predict(x)
+    assert np.array_equal(pa, pb) and np.array_equal(va, vb) and not np.array_equal(pa, p_plain)
+    assert all(np.array_equal(u, v) for u, v in zip(a.get_weights(), weights_perturbed))
+    a.set_layout_adapter()
+    p2, v2 = a.predict(x)
+    assert np.array_equal(p2, p_plain) and np.array_equal(v2, v_plain)
+    a.close(); b.close()

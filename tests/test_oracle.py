@@ -126,3 +126,24 @@ def test_make_tf_golden_generators_match_this_repo():
     from oracle import network_oracle as O
     p, v = O.forward_torch(pw, synth.synthetic_planes(3, seed=2))
     assert np.isfinite(p).all() and np.abs(v).max() < 1
+
+
+def test_layout_adapter_algebra():
+    """weights.adapt_weights: a network trained on another plane order / plane scaling / policy-channel order, re-expressed
+    for this package's layout, gives the same outputs on correspondingly re-laid-out inputs (oracle arithmetic, fp64)."""
+    rng = np.random.default_rng(11)
+    w = W.init_weights(seed=3, perturbed=True)
+    plane_perm = rng.permutation(266)
+    plane_scale = rng.choice([1.0, 0.5, 2.0], size=266).astype(np.float32)
+    policy_perm = rng.permutation(69)
+    x_ours = synth.synthetic_planes(6, seed=9)
+    x_ref = np.zeros_like(x_ours)
+    x_ref[:, plane_perm] = x_ours * plane_scale.reshape(1, -1, 1, 1)          # what the checkpoint's own encoder would have produced
+    p_ref, v_ref = O.forward_torch(w, x_ref, dtype=torch.float64)
+    p_ours, v_ours = O.forward_torch(W.adapt_weights(w, plane_perm, plane_scale, policy_perm), x_ours, dtype=torch.float64)
+    assert np.abs(v_ours - v_ref).max() < 1e-6                                # (the adapted list is float32: 1e-7 rounding of scaled kernels)
+    want = p_ref.reshape(6, 69, 25)[:, policy_perm].reshape(6, 1725)          # our channel k = the checkpoint's channel policy_perm[k]
+    assert np.abs(p_ours - want).max() < 1e-5
+    assert all(a is b or np.array_equal(a, b) for a, b in zip(w, W.adapt_weights(w)))
+    with pytest.raises(ValueError):
+        W.adapt_weights(w, policy_perm=np.zeros(69, dtype=int))
