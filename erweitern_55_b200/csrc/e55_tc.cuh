@@ -267,9 +267,29 @@ __device__ __forceinline__ void policy_tail(const Params& prm, uint8_t* s_act, u
     return *reinterpret_cast<const float*>(stage + stage_offset<F>(c) + (p * kSq + sq) * 4);
   };
   const int npos = min(kPosPerGroup, prm.n - pos0);   // <= 0: the whole group lies past the batch
-  if (npos > 0 && prm.policy != nullptr) {
-    // rows of consecutive positions are consecutive in memory: one coalesced piece of npos x 6 900 bytes.  The lane's
-    // element advances by 32 per step: (position, channel, square) are carried along instead of divided out.
+  if (npos == kPosPerGroup && prm.policy != nullptr && !(prm.tail & 2)) {
+    // rows of consecutive positions are consecutive in memory, and a full group's four rows (27 600 bytes from a
+    // position index that is a multiple of four) start and end on 16-byte boundaries: 1 725 float4 stores, 512 bytes per
+    // warp instruction -- when the destination is mapped host memory the size of the PCIe write transactions follows.
+    // The lane's first element advances by 128 floats per step: (position, channel, square) are carried, not divided out.
+    float4* dst = reinterpret_cast<float4*>(prm.policy + static_cast<size_t>(pos0) * kRow);
+    int e0 = lane * 4;                                   // first of the lane's four consecutive elements
+    int c = e0 / kSq, sq = e0 - c * kSq, p = 0;          // (e0 < 128 < 1725: position 0)
+    for (int v = lane; v < kPosPerGroup * kRow / 4; v += 32) {
+      float x[4];
+      int cc = c, ss = sq, pp = p;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        x[k] = *reinterpret_cast<const float*>(stage + stage_offset<F>(cc) + (pp * kSq + ss) * 4);
+        if (++ss == kSq) { ss = 0; if (++cc == kPolicyCh) { cc = 0; ++pp; } }
+      }
+      dst[v] = make_float4(x[0], x[1], x[2], x[3]);
+      sq += 128 - 5 * kSq; c += 5;                       // + 128 elements = 5 channels and 3 squares
+      if (sq >= kSq) { sq -= kSq; c += 1; }
+      if (c >= kPolicyCh) { c -= kPolicyCh; p += 1; }
+    }
+  } else if (npos > 0 && prm.policy != nullptr) {
+    // a ragged last group: the same piece, element by element
     float* dst = prm.policy + static_cast<size_t>(pos0) * kRow;
     int c = lane / kSq, sq = lane - c * kSq, p = 0;
     for (int i = lane; i < npos * kRow; i += 32) {
@@ -1152,6 +1172,8 @@ inline cudaError_t run(State& s, const float* d_planes, int n, float* d_policy, 
   p.move_off = tail.move_off; p.move_idx = tail.move_idx; p.priors = tail.priors; p.move_stride = tail.move_stride;
   p.mask = tail.mask; p.probs = tail.probs;
   p.tail = (tail.priors != nullptr || tail.probs != nullptr || tail.rows) ? 1 : 0;
+  static const bool scalar_rows = getenv("E55_TAIL_VEC") && atoi(getenv("E55_TAIL_VEC")) == 0;   // A/B: element-wise row stores
+  if (p.tail && scalar_rows) p.tail |= 2;
   p.dbg = nlayers_run < s.nlayers ? s.d_dbg : nullptr;
   p.prof = s.d_prof;
   const int pairs = std::min((rounds + 1) / 2, std::max(1, s.sms / 2));
