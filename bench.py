@@ -363,7 +363,10 @@ def main():
         return units / t_max, med / steps
 
     net._check(lib.e55_set_host_threads(ctx, -1))      # the default: the library picks the thread count and the pipeline
-    e2e_value, e2e_call_s = e2e_rate(host_pool, B, K)
+    # the headline: ordinary (pageable) numpy arrays, what mcts.py hands to predict (mcts.py:101-102); page-locked inputs
+    # (Network.zero_inputs) are measured beside it -- there the library may send a share of the batch through the copy engine
+    e2e_value, e2e_call_s = e2e_rate(host_src, B, K)
+    e2e_pinned, _ = e2e_rate(host_pool, B, K)
     pk_threads, pk_us, fl_us = C.c_int(), C.c_double(), C.c_double()
     net._check(lib.e55_get_host_pipeline(ctx, C.byref(pk_threads), C.byref(pk_us), C.byref(fl_us)))
     split_us = (C.c_double * 8)()
@@ -371,8 +374,7 @@ def main():
     net._check(lib.e55_get_host_split(ctx, C.byref(eighths), split_us))
     shares = (0, 1, 2, 3, 4, 5, 6, 8)
     best_share = min((u, sh) for u, sh in zip(split_us, shares) if u > 0)[1] if any(u > 0 for u in split_us) else 0
-    n_float = B if best_share == 8 else (B // 8 * best_share) // 64 * 64
-    e2e_pageable, _ = e2e_rate(host_src, B, K)
+    n_float = 0                                        # pageable inputs are always packed whole (the cores read them either way)
     net._check(lib.e55_set_host_threads(ctx, 0))
     e2e_plain, _ = e2e_rate(host_pool, B, max(3, K // 4), warm=3)
     net._check(lib.e55_set_host_threads(ctx, -1))
@@ -391,10 +393,10 @@ def main():
     host_gbs, _ = sharding.aggregate(gbs.value, 1.0, device=dev)
     e2e = {"value": e2e_value, "unit": UNIT, "host_read_gbs": host_gbs, "host_read_bound_evals_per_s": host_gbs * 1e9 / (266 * 25 * 4), "h2d_bytes_per_step": (B - n_float) * 266 * 8 + n_float * 266 * 25 * 4,
            "d2h_bytes_per_step": B * 1725 * 4 + B * 4, "call": "Network.predict(numpy)->numpy", "us_per_call": e2e_call_s * 1e6,
-           "input_memory": "page-locked numpy, 3 arrays in rotation", "host_input_bytes_per_step": in_bytes,
-           "float_eighths": best_share, "host_pack_threads": pk_threads.value,
-           "us_per_position_by_float_eighths": {str(sh): round(u, 4) for sh, u in zip(shares, split_us)},
-           "value_pageable_input": e2e_pageable, "value_without_host_packing": e2e_plain, "small_batches": small}
+           "input_memory": "numpy arrays (pageable), 3 in rotation", "host_input_bytes_per_step": in_bytes,
+           "host_pack_threads": pk_threads.value, "value_pinned_input": e2e_pinned, "pinned_input_float_eighths": best_share,
+           "pinned_input_us_per_position_by_float_eighths": {str(sh): round(u, 4) for sh, u in zip(shares, split_us)},
+           "value_without_host_packing": e2e_plain, "small_batches": small}
 
     # ---- same call with the compact input format (e55_predict_packed; not the reference's format) ---
     packed = [packing.pack_planes(a) for a in host_src]

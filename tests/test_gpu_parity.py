@@ -78,16 +78,16 @@ def test_predict_matches_oracle(nets, weights_default, weights_perturbed, tag, p
     x = synth.synthetic_planes(n, seed=1000 + n)
     p, v = nets[tag, prec].predict(x)
     po, vo = _oracle().forward_torch(w, x)
-    _check(p, v, po, vo, FP32_TOL if prec == "fp32" else _bf16_tol(tag))
+    _check(p, v, po, vo, FP32_TOL if prec == "fp32" else _bf16_tol(tag), label=f"{tag} {prec} batch {n}")
 
 
 @pytest.mark.parametrize("tag", ["default", "perturbed"])
 def test_golden_fixture(nets, golden, tag):
     x = synth.synthetic_planes(int(golden["batch"]), seed=int(golden["input_seed"]))
     p, v = nets[tag, "fp32"].predict(x)
-    _check(p, v, golden[f"{tag}_policy_f64"].astype(np.float32), golden[f"{tag}_value_f64"].astype(np.float32), FP32_TOL)
+    _check(p, v, golden[f"{tag}_policy_f64"].astype(np.float32), golden[f"{tag}_value_f64"].astype(np.float32), FP32_TOL, label=f"golden {tag} fp32")
     p, v = nets[tag, "bf16"].predict(x)
-    _check(p, v, golden[f"{tag}_policy_f64"].astype(np.float32), golden[f"{tag}_value_f64"].astype(np.float32), _bf16_tol(tag))
+    _check(p, v, golden[f"{tag}_policy_f64"].astype(np.float32), golden[f"{tag}_value_f64"].astype(np.float32), _bf16_tol(tag), label=f"golden {tag} bf16")
     # the oracle's bf16 emulation (same rounding points, different accumulation order) stays as close
     assert np.abs(p - golden[f"{tag}_policy_bf16"]).max() <= _bf16_tol(tag)[0]
 

@@ -1,5 +1,5 @@
 """Short ncu target for the self-play path: a few hundred plies of real self-play on the evaluation service
-(tower_kernel + legal_priors_kernel per coalesced batch)."""
+(one tower_kernel per coalesced batch: the legal-move softmax is its policy tail)."""
 import sys
 sys.path.insert(0, ".")
 from erweitern_55_b200 import weights as W
