@@ -383,13 +383,14 @@ def main():
         xs = [synth.synthetic_planes(nb, seed=70 + i) for i in range(3)]
         rate, call_s = e2e_rate(xs, nb, 200)
         small[str(nb)] = {"us_per_call": call_s * 1e6, "evals_per_s": rate}
-    # the host-memory roofline of this number: all ranks read their 27 MB input arrays at once with their pool threads
-    # (nothing else: no packing, no copies); every position costs 26 600 bytes of such reads, by cores or copy engine
+    # the host-memory roofline of this number: all ranks at once read 256 MiB each with their pool threads (nothing else:
+    # no packing, no copies); every position costs 26 600 bytes of such reads, by cores or copy engine
     gbs = C.c_double()
+    probe = np.ones(256 << 20, dtype=np.uint8)         # 256 MiB per rank, written first: far beyond the host's caches
     barrier()
-    for a in host_pool:
-        net._check(lib.e55_host_read_bandwidth(ctx, a.ctypes.data, a.nbytes, 3, C.byref(gbs)))
+    net._check(lib.e55_host_read_bandwidth(ctx, probe.ctypes.data, probe.nbytes, 3, C.byref(gbs)))
     barrier()
+    del probe
     host_gbs, _ = sharding.aggregate(gbs.value, 1.0, device=dev)
     e2e = {"value": e2e_value, "unit": UNIT, "host_read_gbs": host_gbs, "host_read_bound_evals_per_s": host_gbs * 1e9 / (266 * 25 * 4), "h2d_bytes_per_step": (B - n_float) * 266 * 8 + n_float * 266 * 25 * 4,
            "d2h_bytes_per_step": B * 1725 * 4 + B * 4, "call": "Network.predict(numpy)->numpy", "us_per_call": e2e_call_s * 1e6,

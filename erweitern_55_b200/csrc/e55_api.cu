@@ -868,6 +868,10 @@ int e55_predict(e55_ctx* c, const float* planes, int n, float* policy, float* va
   // position for the copy engine, and no driver-side staging copy); anything not exactly representable goes as floats.
   // The logits come back through pinned staging, the values are written into mapped host memory by the kernel.
   if (tc_path) {
+    static const bool trace_small = getenv("E55_HOST_TRACE") != nullptr;
+    const auto ts0 = std::chrono::steady_clock::now();
+    auto us_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t).count(); };
+    double t_checks = 0, t_pack = 0, t_issue = 0, t_wait = 0;
     const bool pol_pinned = host_pinned(policy);
     if ((rc = ensure_out_staging(c, n, !pol_pinned))) return rc;
     float* d_value = static_cast<float*>(c->d_out_value_mapped);
@@ -877,8 +881,11 @@ int e55_predict(e55_ctx* c, const float* planes, int n, float* policy, float* va
     tail.rows = direct_policy != nullptr;
     float* k_policy = direct_policy ? direct_policy : c->d_policy;
     const size_t ip = static_cast<size_t>(c->in_planes), ip2 = 2 * ip;
-    if (c->host_threads != 0 && !host_pinned(planes) && ensure_host_staging(c, n) == E55_OK &&
+    const bool try_pack = c->host_threads != 0 && !host_pinned(planes) && ensure_host_staging(c, n) == E55_OK;
+    if (trace_small) t_checks = us_since(ts0);
+    if (try_pack &&
         e55host::pack_planes_inline(planes, n, c->in_planes, c->h_pack, reinterpret_cast<float*>(c->h_pack) + ip, static_cast<int>(ip2))) {
+      if (trace_small) t_pack = us_since(ts0);
       // The search sends the same few batch sizes over and over (1 and 16), so copy + kernel can be replayed as one CUDA
       // graph from the second call of a size on (every pointer in it is library-owned staging: the graph stays valid).
       // Measured (tools/small_batch_probe.py, B200): batch 16 124.5 us per call with the graph against 118.7 us with the
@@ -913,9 +920,14 @@ int e55_predict(e55_ctx* c, const float* planes, int n, float* policy, float* va
     }
     const size_t pol_bytes = static_cast<size_t>(n) * kPolicyCh * kSq * sizeof(float);
     if (!direct_policy) E55_CUDA(c, cudaMemcpyAsync(out_policy, c->d_policy, pol_bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (trace_small) t_issue = us_since(ts0);
     E55_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (trace_small) t_wait = us_since(ts0);
     if (!pol_pinned) memcpy(policy, c->h_out_policy, pol_bytes);
     memcpy(value, c->h_out_value, static_cast<size_t>(n) * sizeof(float));
+    if (trace_small)
+      fprintf(stderr, "[e55 small call] n %d: checks %.1f, packed %.1f, issued %.1f, GPU done %.1f, results copied %.1f us\n", n, t_checks, t_pack,
+              t_issue, t_wait, us_since(ts0));
     return E55_OK;
   }
   const size_t in_bytes = static_cast<size_t>(n) * c->in_planes * kSq * sizeof(float);
