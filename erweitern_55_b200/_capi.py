@@ -4,7 +4,8 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libe55.so")
+# (E55_LIB: another build of the same library, for A/B measurements of a kernel change within one GPU session)
+_LIB_PATH = os.environ.get("E55_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libe55.so")
 
 E55_OK = 0
 E55_PENDING = 1

@@ -350,6 +350,23 @@ __device__ __forceinline__ void policy_tail(const Params& prm, uint8_t* s_act, u
   }
 }
 
+// Packed network input is small (2 128 bytes per position): the positions of a CTA's round fit the little L1 that is left
+// beside 220 KB of shared memory, so they are pulled into it before the conversion loops ask for them word by word.
+__device__ __forceinline__ void prefetch_packed_l1(const Params& prm, int pos0, int npos, int tid, int nthreads) {
+  const int last = min(pos0 + npos, prm.n);
+  if (pos0 >= last) return;
+  const bool interleaved = prm.scale == reinterpret_cast<const float*>(prm.bits) + prm.in_planes;   // [bits | scale] per position
+  const char* b0 = reinterpret_cast<const char*>(prm.bits + static_cast<size_t>(pos0) * prm.packed_stride);
+  const size_t bytes = static_cast<size_t>(last - pos0) * prm.packed_stride * 4 - (interleaved ? 0 : (prm.packed_stride - prm.in_planes) * 4);
+  for (size_t o = static_cast<size_t>(tid) * 128; o < bytes; o += static_cast<size_t>(nthreads) * 128)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(b0 + o));
+  if (!interleaved) {
+    const char* s0 = reinterpret_cast<const char*>(prm.scale + static_cast<size_t>(pos0) * prm.packed_stride);
+    for (size_t o = static_cast<size_t>(tid) * 128; o < bytes; o += static_cast<size_t>(nthreads) * 128)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(s0 + o));
+  }
+}
+
 struct SmemLayout {
   static constexpr int ring = 0;
   __host__ __device__ static constexpr int act(int nstages) { return ring + nstages * kStageBytes; }
@@ -425,6 +442,7 @@ tower_kernel(const Params prm) {
     for (size_t i = first + threadIdx.x * 32; i < last; i += kThreads * 32)
       asm volatile("prefetch.global.L2 [%0];" ::"l"(prm.planes + i));
   }
+  if (prm.bits != nullptr) prefetch_packed_l1(prm, (pair0 * 2 + static_cast<int>(rank)) * prm.pos_per_round, prm.pos_per_round, threadIdx.x, kThreads);
   if (warp == 9) ptx::tmem_alloc_2sm<kTmemCols>(s_tmem);
   ptx::fence_proxy_async_smem();
   ptx::tc_fence_before_sync();
@@ -485,7 +503,7 @@ tower_kernel(const Params prm) {
     const uint32_t a_lo_base = ((ptx::smem_u32(s_act) + group_origin_row(g) * 16) >> 4) |
                                (static_cast<uint32_t>(kPlaneBytes >> 4) << 16);
     const uint32_t b_lo_base = ptx::smem_u32(s_ring) >> 4;
-    uint32_t s = 0, ph = 0, round_seq = 0, stem_idx = 0, stem_full[2] = {0u, 0u};
+    uint32_t s = 0, ph = 0, round_seq = 0, stem_idx = 0, stem_full0 = 0u, stem_full1 = 0u;   // (scalars: no local-memory arrays)
     long long t_start = 0, t_issue = 0, t_full = 0, t_act = 0;
     if (kProf) t_start = clock64();
     for (int pr = pair0; pr < npair_rounds; pr += pair_stride, ++round_seq) {
@@ -510,8 +528,8 @@ tower_kernel(const Params prm) {
           // stem input slices alternate between the two halves of the activation planes
           if (ch.flags & kFirstOfLayer) stem_idx = 0;
           const uint32_t hh = stem_idx & 1;
-          ptx::mbar_wait_cluster(&bar_in_full[g * 2 + hh], stem_full[hh] & 1);
-          ++stem_full[hh];
+          ptx::mbar_wait_cluster(&bar_in_full[g * 2 + hh], (hh ? stem_full1 : stem_full0) & 1);
+          if (hh) ++stem_full1; else ++stem_full0;
         }
         if (ch.need && epoch > 0) {
           // activation K blocks written by the previous layer's (progressive) epilogue in both CTAs
@@ -611,17 +629,21 @@ tower_kernel(const Params prm) {
 #pragma unroll
     for (int i = 0; i < (G::kGroups == 2 ? F / 4 : 1); ++i) res_b[i] = 0u;
     uint32_t round_seq = 0;
-    uint32_t conv_cnt[4] = {0u, 0u, 0u, 0u};             // input slices written so far per (group, plane half)
+    // input slices written so far per (group, plane half): four 8-bit counters in one register (only "none yet" and the
+    // parity matter; 255 wraps to 1).  Scalars, not arrays: a dynamically indexed array lives in local memory, and during
+    // the input phase, with the L1 full of streaming loads, every access to it was an ~600-cycle miss (tools/tc_trace.py).
+    uint32_t conv_cnt = 0u;
+    auto conv_count = [&](int b) -> uint32_t { return (conv_cnt >> (8 * b)) & 0xFFu; };
     long long t_wait = 0, t_work = 0;
 
     for (int pr = pair0; pr < npair_rounds; pr += pair_stride, ++round_seq) {
       const int r = pr * 2 + static_cast<int>(rank);     // this CTA's round (may lie past the batch: all absent)
       const bool has_b = G::kGroups == 2 && prm.pos_per_round == kPosPerRound && pr * 2 * kPosPerRound + kPosPerGroup < prm.n;
-      int next_layer[2] = {0, has_b ? 0 : nl};
-      int next_slice[2] = {0, has_b ? 0 : prm.nslices};
+      int next_layer0 = 0, next_layer1 = has_b ? 0 : nl;
+      int next_slice0 = 0, next_slice1 = has_b ? 0 : prm.nslices;
       // the value-head tail of group g is run by warp 4g once all 8 warps have written their partials
       const bool do_value = nl == prm.nlayers;
-      bool fc_pending[2] = {do_value && warp == 0, do_value && warp == 4 && has_b};
+      bool fc_pending0 = do_value && warp == 0, fc_pending1 = do_value && warp == 4 && has_b;
       if (prm.planes != nullptr && pr + pair_stride < npair_rounds) {  // pull the next round's network input into L2
         const int rn = (pr + pair_stride) * 2 + static_cast<int>(rank);
         const size_t first = static_cast<size_t>(rn) * prm.pos_per_round * prm.in_planes * kSq;
@@ -629,6 +651,7 @@ tower_kernel(const Params prm) {
         for (size_t i = first + threadIdx.x * 32; i < last; i += 256 * 32)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(prm.planes + i));
       }
+      if (prm.bits != nullptr && round_seq > 0) prefetch_packed_l1(prm, r * prm.pos_per_round, prm.pos_per_round, threadIdx.x, 256);
       // ---- phase 1: the stem's input.  All slices of both groups are converted before any epilogue of the round is
       // served (the stem epilogues need every slice anyway).  No residual of the previous round is live here, and
       // saying so (the registers are cleared) gives the conversion the registers to keep all its loads in flight:
@@ -638,53 +661,74 @@ tower_kernel(const Params prm) {
       for (int i = 0; i < F / 4; ++i) res_a[i] = 0u;
 #pragma unroll
       for (int i = 0; i < (G::kGroups == 2 ? F / 4 : 1); ++i) res_b[i] = 0u;
-      while (next_slice[0] < prm.nslices || next_slice[1] < prm.nslices) {
+      // One conversion item = 8 consecutive channels of one square of one position = one 16-byte row entry.  Which items
+      // a thread converts does not depend on the slice or the group, so the split of the item index into (position,
+      // plane, square), the source offset and the shared-memory offset are worked out once per round, not per event
+      // (the events had been bound by their instruction stream: ~60 instructions per item, each event a walk through
+      // cold instruction cache).
+      constexpr int kSlicePlanes = kPlanes / 2;
+      constexpr int kItems = kPosPerGroup * kSlicePlanes * kSq;
+      constexpr int kPasses = (kItems + 1023) / 1024;
+      int it_meta[kPasses][4], it_src[kPasses][4], it_dst[kPasses][4];
+#pragma unroll
+      for (int pass = 0; pass < kPasses; ++pass)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int it = static_cast<int>(threadIdx.x) + (pass * 4 + u) * 256;
+          const int q = it / kSq, s_ = it - q * kSq, c8 = q % kSlicePlanes, p = q / kSlicePlanes;
+          it_meta[pass][u] = s_ | (c8 << 8) | (p << 16) | ((it < kItems ? 1 : 0) << 24);
+          it_src[pass][u] = prm.bits == nullptr ? (p * prm.in_planes + c8 * 8) * kSq + s_ : p * prm.packed_stride + c8 * 8;
+          it_dst[pass][u] = c8 * kPlaneBytes + ((s_ / 5) * kW + p * 6 + s_ % 5) * 16;
+        }
+      while (next_slice0 < prm.nslices || next_slice1 < prm.nslices) {
         // slice k goes to plane half k&1 once the MMAs that read that half's previous slice are done (the group that is
         // further behind with its input goes first, so neither starves the other)
         int g = -1;
+        long long tl0 = 0;
+        if (kProf) tl0 = clock64();
         while (g < 0) {
-          const int g0 = next_slice[1] < next_slice[0] ? 1 : 0;
+          const int g0 = next_slice1 < next_slice0 ? 1 : 0;
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
             const int gg = g0 ^ k;
-            if (g < 0 && next_slice[gg] < prm.nslices) {
-              const int b = gg * 2 + (next_slice[gg] & 1);
-              if (conv_cnt[b] == 0 || ptx::mbar_test_wait(&bar_in_empty[b], (conv_cnt[b] - 1) & 1)) g = gg;
+            const int ns = gg ? next_slice1 : next_slice0;
+            if (g < 0 && ns < prm.nslices) {
+              const int b = gg * 2 + (ns & 1);
+              const uint32_t cnt = conv_count(b);
+              if (cnt == 0 || ptx::mbar_test_wait(&bar_in_empty[b], (cnt - 1) & 1)) g = gg;
             }
           }
         }
         // fp32 NCHW planes -> bf16 wide-board planes of this group (network.py:255-274 built the input):
         // one item = 8 consecutive channels of one square of one position = one 16-byte row entry
-        const int sl = next_slice[g];
-        constexpr int kSlicePlanes = kPlanes / 2;
+        const int sl = g ? next_slice1 : next_slice0;
+        long long tc0 = 0;
+        if (kProf) tc0 = clock64();
         const int hh = sl & 1;
         const int pl0 = sl * kSlicePlanes;                       // first input plane (8 channels each) of the slice
         const int npl = min(kSlicePlanes, prm.in_planes8 - pl0);
         const int pos0 = r * prm.pos_per_round + g * kPosPerGroup;
-        // item -> (position, plane, square) with compile-time divisors only (the slice is always walked as if it had
-        // all kSlicePlanes planes; items of planes a short last slice does not have are skipped): this loop is
-        // instruction-bound, and a division by a run-time plane count cost more than the loads
-        constexpr int nitems = kPosPerGroup * kSlicePlanes * kSq;
-        for (int it0 = threadIdx.x; it0 < nitems; it0 += 256 * 4) {
+        uint8_t* dst_base = s_act + hh * kSlicePlanes * kPlaneBytes + group_origin_row(g) * 16;
+#pragma unroll
+        for (int pass = 0; pass < kPasses; ++pass) {
           float f[4][8];
           // phase 1: issue every global load of up to 4 items before touching any result
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int it = it0 + u * 256;
-            const int q = it / kSq, s_ = it - q * kSq, c8 = q % kSlicePlanes, p = q / kSlicePlanes;
-            const bool live = it < nitems && c8 < npl && pos0 + p < prm.n;
-            const int ch0 = (pl0 + c8) * 8;
+            const int meta = it_meta[pass][u];
+            const int s_ = meta & 31, c8 = (meta >> 8) & 31, p = (meta >> 16) & 7;
+            const bool live = (meta >> 24) != 0 && c8 < npl && pos0 + p < prm.n;
+            const int nch = prm.in_planes - (pl0 + c8) * 8;      // channels of this 8-channel plane that exist (>= 8: all)
             if (prm.bits == nullptr) {
-              const float* src = prm.planes + (static_cast<size_t>(pos0 + p) * prm.in_planes + ch0) * kSq + s_;
+              const float* src = prm.planes + (static_cast<size_t>(pos0) * prm.in_planes + pl0 * 8) * kSq + it_src[pass][u];
 #pragma unroll
-              for (int e = 0; e < 8; ++e)
-                f[u][e] = (live && ch0 + e < prm.in_planes) ? __ldg(src + e * kSq) : 0.f;
+              for (int e = 0; e < 8; ++e) f[u][e] = (live && e < nch) ? __ldg(src + e * kSq) : 0.f;
             } else {
               // packed planes: x[c][sq] = bit sq of bits[c] ? scale[c] : 0
-              const size_t o = static_cast<size_t>(pos0 + p) * prm.packed_stride + ch0;
+              const size_t o = static_cast<size_t>(pos0) * prm.packed_stride + pl0 * 8 + it_src[pass][u];
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
-                const bool ok = live && ch0 + e < prm.in_planes;
+                const bool ok = live && e < nch;
                 const uint32_t wbits = ok ? __ldg(prm.bits + o + e) : 0u;
                 const float sc = ok ? __ldg(prm.scale + o + e) : 0.f;
                 f[u][e] = ((wbits >> s_) & 1u) ? sc : 0.f;
@@ -694,38 +738,45 @@ tower_kernel(const Params prm) {
           // phase 2: pack and store
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int it = it0 + u * 256;
-            const int q = it / kSq, s_ = it - q * kSq, c8 = q % kSlicePlanes, p = q / kSlicePlanes;
-            if (it < nitems && c8 < npl) {
+            const int meta = it_meta[pass][u];
+            if ((meta >> 24) != 0 && ((meta >> 8) & 31) < npl) {
               const uint4 pk = make_uint4(ptx::pack_bf16x2(f[u][0], f[u][1]), ptx::pack_bf16x2(f[u][2], f[u][3]),
                                           ptx::pack_bf16x2(f[u][4], f[u][5]), ptx::pack_bf16x2(f[u][6], f[u][7]));
-              const int rr = (s_ / 5) * kW + p * 6 + s_ % 5;
-              *reinterpret_cast<uint4*>(s_act + (hh * kSlicePlanes + c8) * kPlaneBytes + (group_origin_row(g) + rr) * 16) = pk;
+              *reinterpret_cast<uint4*>(dst_base + it_dst[pass][u]) = pk;
             }
           }
         }
+        long long tfence = 0;
+        if (kProf) tfence = clock64();
         ptx::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) arrive_on_leader(&bar_in_full[g * 2 + hh], rank);
-        next_slice[g] = sl + 1;
-        ++conv_cnt[g * 2 + hh];
+        if (kProf && blockIdx.x == 0 && threadIdx.x == 0 && round_seq == 0) {
+          unsigned long long* tr = prm.prof + 16 + 8192 + 512 + (g * 8 + sl) * 4;
+          tr[0] = tc0; tr[1] = clock64(); tr[2] = tl0; tr[3] = tfence;
+        }
+        if (g) next_slice1 = sl + 1; else next_slice0 = sl + 1;
+        {
+          const int b = g * 2 + hh;
+          conv_cnt = conv_count(b) == 255u ? (conv_cnt & ~(0xFFu << (8 * b))) | (1u << (8 * b)) : conv_cnt + (1u << (8 * b));
+        }
       }
       // ---- phase 2: epilogues, value tails ----
-      while (next_layer[0] < nl || next_layer[1] < nl || fc_pending[0] || fc_pending[1]) {
+      while (next_layer0 < nl || next_layer1 < nl || fc_pending0 || fc_pending1) {
         long long te0 = 0, te1 = 0;
         if (kProf) te0 = clock64();
         int g;
         bool value_fc = false;
         for (;;) {  // serve whichever event is ready first (group A preferred: it runs ahead)
-          if (next_layer[0] < nl && ptx::mbar_test_wait(&bar_tmem_full[0], (round_seq * nl + next_layer[0]) & 1)) { g = 0; break; }
-          if (next_layer[1] < nl && ptx::mbar_test_wait(&bar_tmem_full[1], (round_seq * nl + next_layer[1]) & 1)) { g = 1; break; }
-          if (fc_pending[0] && ptx::mbar_test_wait(&bar_v[0], round_seq & 1)) { g = 0; value_fc = true; break; }
-          if (fc_pending[1] && ptx::mbar_test_wait(&bar_v[1], round_seq & 1)) { g = 1; value_fc = true; break; }
+          if (next_layer0 < nl && ptx::mbar_test_wait(&bar_tmem_full[0], (round_seq * nl + next_layer0) & 1)) { g = 0; break; }
+          if (next_layer1 < nl && ptx::mbar_test_wait(&bar_tmem_full[1], (round_seq * nl + next_layer1) & 1)) { g = 1; break; }
+          if (fc_pending0 && ptx::mbar_test_wait(&bar_v[0], round_seq & 1)) { g = 0; value_fc = true; break; }
+          if (fc_pending1 && ptx::mbar_test_wait(&bar_v[1], round_seq & 1)) { g = 1; value_fc = true; break; }
         }
         if (value_fc) {
           // value head tail of group g on one warp: ReLU(conv1x1) -> Dense(25->128)+ReLU -> Dense(128->1)+tanh
           // (network.py:111-120).  Lane l owns hidden units l, l+32, l+64, l+96.
-          fc_pending[g] = false;
+          if (g) fc_pending1 = false; else fc_pending0 = false;
           float hsum[4][kPosPerGroup];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -766,9 +817,9 @@ tower_kernel(const Params prm) {
         }
         ptx::tc_fence_after_sync();
         if (kProf) te1 = clock64();
-        const int L = next_layer[g];
-        next_layer[g] = L + 1;
-        const uint32_t lf = prm.layers[L].flags;
+        const int L = g ? next_layer1 : next_layer0;
+        if (g) next_layer1 = L + 1; else next_layer0 = L + 1;
+        const uint32_t lf = prm.layers[L].flags;   // (L1-resident; a copy in shared memory measured 0.7 % slower)
         const float* bias = bias_base + L * F + h * G::kHalfCh;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (g * 2 + (L & 1)) * F + h * G::kHalfCh;
         uint64_t* bar_part = &bar_act_part[g * 4 + h * G::kCb];

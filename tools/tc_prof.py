@@ -12,12 +12,20 @@ from erweitern_55_b200.network import Network
 w = W.init_weights()
 net = Network(precision="bf16", weights=w)
 import os
+PACKED = os.environ.get("PACKED") == "1"      # device-resident bit-packed input (what the self-play paths and the host pipeline feed)
+from erweitern_55_b200 import packing
 lag = int(os.environ.get("E55_LAG", "-1"))
 if lag >= 0:
     net._check(net._lib.e55_debug_set_lag(net._ctx, lag))
 for n in [int(a) for a in sys.argv[1:]] or [8, 256, 1024]:
-    x = torch.from_numpy(synth.synthetic_planes(n, seed=5)).cuda()
+    xh = synth.synthetic_planes(n, seed=5)
+    x = torch.from_numpy(xh).cuda()
     pd = torch.empty((n, 1725), device="cuda"); vd = torch.empty((n, 1), device="cuda")
+    if PACKED:
+        bits, scale = packing.pack_planes(xh)
+        db, ds = torch.from_numpy(bits.view(np.int32)).cuda(), torch.from_numpy(scale).cuda()
+        fwd = lambda: net._check(net._lib.e55_predict_packed_device(net._ctx, db.data_ptr(), ds.data_ptr(), n, pd.data_ptr(), vd.data_ptr()))
+        net.predict_device = lambda *_: fwd()
     net.predict_device(x, pd, vd); net.sync()
     net._check(net._lib.e55_debug_profile(net._ctx, 1, None))
     net.predict_device(x, pd, vd); net.sync()

@@ -51,3 +51,8 @@ for c in firsts:
 print("epilogue events (start, duration, group, layer):")
 for e in ep[:40]:
     print(f"  t={e[0]-t0:7d} dur={e[1]-e[0]:5d} g={e[2]} L={e[3]}")
+cv = a[16 + 8192 + 512:16 + 8192 + 512 + 64].reshape(-1, 4)
+cv = cv[cv[:, 0] > 0]; cv = cv[np.argsort(cv[:, 0])]
+print("input conversions of thread 0: loop top, plane half free (+wait), loads+stores done (+), fence+arrive done (+)")
+for e in cv:
+    print(f"  top={e[2]-t0:7d} free={e[0]-t0:7d} (+{e[0]-e[2]:5d}) stored={e[3]-t0:7d} (+{e[3]-e[0]:5d}) arrived={e[1]-t0:7d} (+{e[1]-e[3]:5d})")
