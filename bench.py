@@ -257,6 +257,18 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def host_exchange(tag, payload, timeout_s=900):
+        """Every rank's `payload` (JSON-able), as a list by rank on every rank, through the rendezvous store: a meeting point
+        on the host that works whatever state the devices are in."""
+        if world == 1:
+            return [payload]
+        import datetime
+        store = dist.distributed_c10d._get_default_store()
+        store.set(f"e55/{tag}/{rank}", json.dumps(payload))
+        keys = [f"e55/{tag}/{i}" for i in range(world)]
+        store.wait(keys, datetime.timedelta(seconds=timeout_s))
+        return [json.loads(store.get(k)) for k in keys]
+
     def repeat_regions(region, est_s):
         """Runs `region()` (-> seconds of one K-step region) until MIN_TIMED_S have been timed; median, count, total."""
         reps = max(3, min(2000, int(math.ceil(MIN_TIMED_S / max(est_s, 1e-6)))))
@@ -484,28 +496,40 @@ def main():
         tot_mv, _ = sharding.aggregate(mv, 1.0, device=dev)
         selfplay = {"moves_per_s": tot_mv, "evals_per_s": tot_ev, "mean_gpu_batch_rank0": mb, "workers_per_gpu": sp_threads}
 
+    # ---- GPU-resident self-play: the last device work of the run, and none of it behind a device collective ------------
+    # (the ranks meet through the rendezvous store, on the host: a search kernel that ever hung would hang a NCCL
+    # barrier on every rank with it, and with the barrier the whole line; this way the line still carries everything
+    # measured above, and says what went wrong here)
     selfplay_gpu = None
+    device_hung = False
     if args.selfplay_workers > 0 and args.precision == "bf16" and default_net and args.gpu_games > 0:
-        gs, gpu_error = {"moves_per_s": 0.0, "evals_per_s": 0.0, "games": 0, "mean_game_plies": 0.0}, None
+        gs, gpu_error = {"moves_per_s": 0.0, "evals_per_s": 0.0, "games": 0, "mean_game_plies": 0.0, "moves": 0, "evals": 0, "seconds": 0.0}, None
         try:
             net.gpu_selfplay(games=args.gpu_games, total_moves=args.gpu_games, simulations=800, seed=77 + rank)   # warm-up
         except Exception as exc:
             gpu_error = str(exc)
-        barrier()
+        host_exchange("gpu_selfplay_warm", {"error": gpu_error})
         if gpu_error is None:
             try:
                 gs, _ = net.gpu_selfplay(games=args.gpu_games, total_moves=args.gpu_games * args.gpu_plies, simulations=800,
                                          mate_depth=7, seed=5 + rank)
             except Exception as exc:
                 gpu_error = str(exc)
-        barrier()
-        g_mv, _ = sharding.aggregate(gs["moves_per_s"], 1.0, device=dev)
-        g_ev, _ = sharding.aggregate(gs["evals_per_s"], 1.0, device=dev)
-        selfplay_gpu = {"moves_per_s": g_mv, "evals_per_s": g_ev, "driver": "GPU-resident search", "games_in_flight_per_gpu": args.gpu_games,
-                        "plies_per_game_slot": args.gpu_plies, "games_finished_rank0": gs["games"],
-                        "mean_game_plies_rank0": gs["mean_game_plies"], "simulations_per_move": 800, "mate_search_plies": 7,
-                        "tree_pool_overflows_rank0": gs.get("tree_overflows"), "mate_budget_exhausted_rank0": gs.get("mate_exhausted"),
-                        "error_rank0": gpu_error}
+        got = host_exchange("gpu_selfplay", {"moves": gs.get("moves", 0), "evals": gs.get("evals", 0), "seconds": gs.get("seconds", 0.0),
+                                             "error": gpu_error})
+        device_hung = any(x["error"] for x in got)       # any failure here: leave without touching the devices again
+        if rank == 0:
+            worst_s = max(float(x["seconds"]) for x in got)
+            errors = {str(i): x["error"] for i, x in enumerate(got) if x["error"]}
+            ok = not errors and worst_s > 0
+            selfplay_gpu = {"moves_per_s": sum(x["moves"] for x in got) / worst_s if ok else 0.0,
+                            "evals_per_s": sum(x["evals"] for x in got) / worst_s if ok else 0.0,
+                            "aggregate": "moves of all ranks / the slowest rank's seconds",
+                            "driver": "GPU-resident search", "games_in_flight_per_gpu": args.gpu_games,
+                            "plies_per_game_slot": args.gpu_plies, "games_finished_rank0": gs["games"],
+                            "mean_game_plies_rank0": gs["mean_game_plies"], "simulations_per_move": 800, "mate_search_plies": 7,
+                            "tree_pool_overflows_rank0": gs.get("tree_overflows"), "mate_budget_exhausted_rank0": gs.get("mate_exhausted"),
+                            "errors_by_rank": errors or None}
 
     # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------------
     cpu_baseline = None
@@ -536,6 +560,10 @@ def main():
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
         os.dup2(2, 1)
+    if device_hung:
+        sys.stderr.write("[bench] GPU self-play failed; leaving without device teardown\n")
+        sys.stderr.flush()
+        os._exit(0)
     net.close()
     if world > 1:
         dist.destroy_process_group()

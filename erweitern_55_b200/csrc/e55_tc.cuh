@@ -629,11 +629,11 @@ tower_kernel(const Params prm) {
 #pragma unroll
     for (int i = 0; i < (G::kGroups == 2 ? F / 4 : 1); ++i) res_b[i] = 0u;
     uint32_t round_seq = 0;
-    // input slices written so far per (group, plane half): four 8-bit counters in one register (only "none yet" and the
-    // parity matter; 255 wraps to 1).  Scalars, not arrays: a dynamically indexed array lives in local memory, and during
-    // the input phase, with the L1 full of streaming loads, every access to it was an ~600-cycle miss (tools/tc_trace.py).
-    uint32_t conv_cnt = 0u;
-    auto conv_count = [&](int b) -> uint32_t { return (conv_cnt >> (8 * b)) & 0xFFu; };
+    // input slices written so far per (group, plane half) b: bit b = their number is odd, bit 4+b = there was one.  Nothing
+    // that can overflow (a launch of 131072 positions on 124 SMs converts ~400 slices per buffer).  One scalar, not an
+    // array: a dynamically indexed array lives in local memory, and during the input phase, with the L1 full of
+    // streaming loads, every access to it was an ~600-cycle miss (tools/tc_trace.py).
+    uint32_t conv_state = 0u;
     long long t_wait = 0, t_work = 0;
 
     for (int pr = pair0; pr < npair_rounds; pr += pair_stride, ++round_seq) {
@@ -694,8 +694,8 @@ tower_kernel(const Params prm) {
             const int ns = gg ? next_slice1 : next_slice0;
             if (g < 0 && ns < prm.nslices) {
               const int b = gg * 2 + (ns & 1);
-              const uint32_t cnt = conv_count(b);
-              if (cnt == 0 || ptx::mbar_test_wait(&bar_in_empty[b], (cnt - 1) & 1)) g = gg;
+              // the release of the buffer's previous slice is phase (count - 1) of its barrier
+              if (!((conv_state >> (4 + b)) & 1u) || ptx::mbar_test_wait(&bar_in_empty[b], ((conv_state >> b) & 1u) ^ 1u)) g = gg;
             }
           }
         }
@@ -758,7 +758,7 @@ tower_kernel(const Params prm) {
         if (g) next_slice1 = sl + 1; else next_slice0 = sl + 1;
         {
           const int b = g * 2 + hh;
-          conv_cnt = conv_count(b) == 255u ? (conv_cnt & ~(0xFFu << (8 * b))) | (1u << (8 * b)) : conv_cnt + (1u << (8 * b));
+          conv_state = (conv_state ^ (1u << b)) | (16u << b);
         }
       }
       // ---- phase 2: epilogues, value tails ----
