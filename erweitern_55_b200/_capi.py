@@ -57,6 +57,7 @@ SIGNATURES = {
     "e55_debug_set_lag": (C.c_int, [_ctx, C.c_int]),
     "e55_debug_profile": (C.c_int, [_ctx, C.c_int, C.POINTER(C.c_uint64)]),
     "e55_selftest_umma": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "e55_selftest_slice_book": (C.c_int, [C.c_int64, C.c_uint64, C.POINTER(C.c_int64)]),
     "e55_bench_umma": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
 }
 

@@ -1282,6 +1282,27 @@ int e55_debug_profile(e55_ctx* c, int enable, uint64_t* counters_out) {
   return E55_OK;
 }
 
+int e55_selftest_slice_book(int64_t slices, uint64_t seed, int64_t* mismatches_out) {
+  if (!mismatches_out || slices < 0) return fail(nullptr, E55_ERR_INVALID, "bad selftest arguments");
+  // the kernel's bookkeeping against plain 64-bit counters, buffers visited in a pseudo-random order
+  e55::tc::SliceBook book;
+  uint64_t count[4] = {0, 0, 0, 0};
+  int64_t bad = 0;
+  uint64_t x = seed * 2862933555777941757ull + 3037000493ull;
+  for (int64_t i = 0; i < slices; ++i) {
+    x = x * 6364136223846793005ull + 1442695040888963407ull;
+    const int b = static_cast<int>(x >> 62);
+    for (int k = 0; k < 4; ++k) {
+      if (book.none_yet(k) != (count[k] == 0)) ++bad;
+      if (count[k] > 0 && book.release_parity(k) != static_cast<uint32_t>((count[k] - 1) & 1)) ++bad;
+    }
+    book.wrote(b);
+    ++count[b];
+  }
+  *mismatches_out = bad;
+  return E55_OK;
+}
+
 int e55_selftest_umma(int device, int row_shift, float* max_abs_err_out) {
   using namespace e55::ummatest;
   if (!max_abs_err_out || row_shift < 0 || row_shift > 64) return fail(nullptr, E55_ERR_INVALID, "bad selftest arguments");

@@ -111,6 +111,19 @@ struct LayerInfo {
   uint32_t flags;
 };
 
+// Which input slices the epilogue warps have written into the four stem-input buffers b = group * 2 + plane half, as much
+// as the barrier protocol needs of it: before slice number k >= 1 of a buffer is written, the MMAs that read slice k - 1
+// must have released it, which is phase k - 1 of the buffer's `bar_in_empty` barrier, i.e. a wait on parity (k - 1) & 1.
+// One register (bit b: slices written so far is odd; bit 4 + b: there was one) instead of four counters: nothing that can
+// overflow in a launch of any length, and no array for the compiler to put into local memory (section 4.1 of DESIGN.md).
+// Host-callable so that `e55_selftest_slice_book` can hold it to plain counters without a GPU.
+struct SliceBook {
+  uint32_t state = 0u;
+  __host__ __device__ __forceinline__ bool none_yet(int b) const { return ((state >> (4 + b)) & 1u) == 0u; }
+  __host__ __device__ __forceinline__ uint32_t release_parity(int b) const { return ((state >> b) & 1u) ^ 1u; }
+  __host__ __device__ __forceinline__ void wrote(int b) { state = (state ^ (1u << b)) | (16u << b); }
+};
+
 struct Params {
   const uint8_t* wimg;
   const Chunk* chunks;
@@ -629,11 +642,11 @@ tower_kernel(const Params prm) {
 #pragma unroll
     for (int i = 0; i < (G::kGroups == 2 ? F / 4 : 1); ++i) res_b[i] = 0u;
     uint32_t round_seq = 0;
-    // input slices written so far per (group, plane half) b: bit b = their number is odd, bit 4+b = there was one.  Nothing
-    // that can overflow (a launch of 131072 positions on 124 SMs converts ~400 slices per buffer).  One scalar, not an
-    // array: a dynamically indexed array lives in local memory, and during the input phase, with the L1 full of
-    // streaming loads, every access to it was an ~600-cycle miss (tools/tc_trace.py).
-    uint32_t conv_state = 0u;
+    // input slices written so far per (group, plane half): one register of parity/seen bits (a launch of 131072 positions
+    // on 124 SMs converts ~400 slices per buffer).  Not an array: a dynamically indexed array lives in local memory, and
+    // during the input phase, with the L1 full of streaming loads, every access to it was an ~600-cycle miss
+    // (tools/tc_trace.py).
+    SliceBook slices;
     long long t_wait = 0, t_work = 0;
 
     for (int pr = pair0; pr < npair_rounds; pr += pair_stride, ++round_seq) {
@@ -695,7 +708,7 @@ tower_kernel(const Params prm) {
             if (g < 0 && ns < prm.nslices) {
               const int b = gg * 2 + (ns & 1);
               // the release of the buffer's previous slice is phase (count - 1) of its barrier
-              if (!((conv_state >> (4 + b)) & 1u) || ptx::mbar_test_wait(&bar_in_empty[b], ((conv_state >> b) & 1u) ^ 1u)) g = gg;
+              if (slices.none_yet(b) || ptx::mbar_test_wait(&bar_in_empty[b], slices.release_parity(b))) g = gg;
             }
           }
         }
@@ -756,10 +769,7 @@ tower_kernel(const Params prm) {
           tr[0] = tc0; tr[1] = clock64(); tr[2] = tl0; tr[3] = tfence;
         }
         if (g) next_slice1 = sl + 1; else next_slice0 = sl + 1;
-        {
-          const int b = g * 2 + hh;
-          conv_state = (conv_state ^ (1u << b)) | (16u << b);
-        }
+        slices.wrote(g * 2 + hh);
       }
       // ---- phase 2: epilogues, value tails ----
       while (next_layer0 < nl || next_layer1 < nl || fc_pending0 || fc_pending1) {

@@ -368,6 +368,12 @@ int e55_debug_profile(e55_ctx* ctx, int enable, uint64_t* counters_out);
  * largest deviation. */
 int e55_selftest_umma(int device, int row_shift, float* max_abs_err_out);
 
+/* Host-only self-test (no device needed) of the tower kernel's input-slice bookkeeping (`e55::tc::SliceBook`,
+ * csrc/e55_tc.cuh): `slices` slices are written to the four stem-input buffers in a pseudo-random order and the
+ * barrier parity the kernel would wait on is compared with plain counters before each.  mismatches_out receives
+ * the number of disagreements (0 = correct at any launch length). */
+int e55_selftest_slice_book(int64_t slices, uint64_t seed, int64_t* mismatches_out);
+
 /* Tensor-pipe micro-benchmark: every SM issues `iters` rounds of 72 back-to-back 128 x n_dim x 16
  * UMMAs (n_dim 128 or 256) from shared memory; tflops_out receives the achieved dense bf16 rate. */
 int e55_bench_umma(int device, int n_dim, int iters, float* tflops_out);

@@ -58,3 +58,14 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle|#include[^\n]*oracle|oracle[./]_ref", src, re.M), f
+
+
+def test_slice_bookkeeping_of_the_tower_kernel_at_any_launch_length():
+    """`e55::tc::SliceBook` (host-callable part of csrc/e55_tc.cuh) against plain counters: the barrier parity the epilogue
+    warps wait on before re-using a stem-input buffer stays right past 255, 65535 and 2**20 slices per buffer (a packed
+    8-bit version of this bookkeeping once wrapped to the wrong parity and hung launches of more than ~85 rounds per CTA)."""
+    lib = _capi.load()
+    for slices, seed in ((0, 1), (7, 2), (4 * 256 + 3, 3), (4 * 70000, 4), (5_000_000, 5)):
+        bad = C.c_int64(-1)
+        assert lib.e55_selftest_slice_book(slices, seed, C.byref(bad)) == 0 and bad.value == 0, (slices, bad.value)
+    assert lib.e55_selftest_slice_book(-1, 0, C.byref(bad)) == _capi.E55_ERR_INVALID
