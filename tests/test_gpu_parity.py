@@ -690,6 +690,7 @@ def test_device_resident_api(nets):
     assert np.array_equal(pd.cpu().numpy(), p) and np.array_equal(vd.cpu().numpy(), v)
 
 
+@pytest.mark.timeout(300, method="thread")   # a launch that never ends must end the run, not hang it
 def test_one_launch_of_many_rounds(weights_perturbed):
     """A single launch far beyond the grid (120 rounds per CTA: what a GPU self-play round of 8192 games x 16 leaves is) gives
     every position the result it has in a one-round launch -- per-launch state that only shows after hundreds of input
@@ -720,6 +721,7 @@ def test_one_launch_of_many_rounds(weights_perturbed):
     torch.cuda.empty_cache()
 
 
+@pytest.mark.timeout(300, method="thread")   # a launch that never ends must end the run, not hang it
 def test_gpu_selfplay_at_the_bench_size(weights_default):
     """16384 games in flight (two cohorts, 131072 network slots per launch on 124 SMs): one move per game, no overflow."""
     from erweitern_55_b200.network import Network
