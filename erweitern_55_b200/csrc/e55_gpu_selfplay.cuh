@@ -32,13 +32,24 @@ using namespace mshogi;
 constexpr int kLeaf = 16;              // network slots per game per round (Config.batch_size, mcts.py:13)
 constexpr int kMaxSel = 24;            // selections per game per round: until the 16 slots are filled, at most this many
 constexpr int kMaxPly = 512;           // selfplay.run's max_moves
-constexpr int kMaxNodes = 4096;        // per game and pool: the subtree kept from the last search + one new node per simulation
+// (pool and record sizes can be overridden at compile time: the host build of these kernels for the sanitizer runs,
+// tests/native/gs_host.cpp, shrinks them so that the suspension, overflow and truncation paths are walked all the time)
+#ifndef E55_GS_MAX_NODES
+#define E55_GS_MAX_NODES 4096
+#endif
+#ifndef E55_GS_MAX_EDGES
+#define E55_GS_MAX_EDGES (112 * 1024)
+#endif
+#ifndef E55_GS_RECORD_WORDS
+#define E55_GS_RECORD_WORDS 16384
+#endif
+constexpr int kMaxNodes = E55_GS_MAX_NODES;   // per game and pool: the subtree kept from the last search + one new node per simulation
+constexpr int kMaxEdges = E55_GS_MAX_EDGES;   // per game and pool (late positions with pieces in hand have 100+ legal moves)
 constexpr int kNodesSuspend = kMaxNodes * 9 / 10 - kMaxSel;    // mcts.py:72: "if the memory is used over 90%, suspend the search"
-constexpr int kEdgesSuspend = 112 * 1024 * 9 / 10 - kMaxSel * 256;
-constexpr int kMaxEdges = 112 * 1024;  // per game and pool (late positions with pieces in hand have 100+ legal moves)
+constexpr int kEdgesSuspend = kMaxEdges * 9 / 10 - kMaxSel * 256;
 constexpr int kMoveStride = 256;       // move-list slots per batch position (MoveList capacity: nothing is ever cut)
 constexpr int kMaxPath = 96;           // deepest descent below the root
-constexpr int kRecordWords = 16384;    // uint16 words of one game record (see finish_game)
+constexpr int kRecordWords = E55_GS_RECORD_WORDS;   // uint16 words of one game record (see finish_game)
 
 struct GNode {
   int32_t parent, parent_edge, first_edge;

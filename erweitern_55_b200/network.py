@@ -252,7 +252,6 @@ class Network:
         were played.  Returns ``(stats, game_records)``; ``game_records`` holds the first ``records`` finished games as
         :class:`erweitern_55_b200.gamerecord.GameRecord` -- what ``selfplay.run`` returns (selfplay.py:10-113)."""
         import time
-        from .gamerecord import GameRecord
         cap = playout_cap_oscillation or {"enable": False, "N": 800, "n": 128, "frac": 0.25}     # selfplay.py:10
         self._check(self._lib.e55_gpu_selfplay_set_cap(self._ctx, int(bool(cap["enable"])), int(cap["N"]), int(cap["n"]), float(cap["frac"])))
         st = _capi.SelfplayStats()
@@ -269,27 +268,7 @@ class Network:
                  "mate_searches": st.mate_searches, "mate_exhausted": st.mate_exhausted, "records_truncated": st.records_truncated}
         if st.tree_overflows:
             raise RuntimeError(f"GPU self-play abandoned {st.tree_overflows} descents on a full tree pool: its searches are not the reference's")
-        sfen = packed_move_sfen
-        out, now = [], int(time.time())
-        for r in range(n_rec.value):
-            row = buf[r]
-            rec = GameRecord()
-            rec.winner, used, truncated, w = int(row[1]), int(row[2]), int(row[3]), 4
-            while w < 4 + used:
-                mv, sum_n, q, k = int(row[w]) & 0x7FFF, int(row[w + 1]), int(row[w + 2]) / 65535.0, int(row[w + 3])
-                target = not (int(row[w]) >> 15)       # fast searches under playout-cap oscillation are no targets (selfplay.py:90-91)
-                visits = [(sfen(int(row[w + 4 + 2 * i])), int(row[w + 5 + 2 * i])) for i in range(k)]
-                w += 4 + 2 * k
-                rec.sfen_kif.append(sfen(mv))
-                rec.mcts_result.append((sum_n, q, visits))
-                if k > 0 and target:                   # (nor is a ply whose visit list did not fit the record)
-                    rec.learning_target_plys.append(rec.ply)
-                rec.ply += 1
-            rec.timestamp = now
-            # False if the record buffer was too small for this game (plies or visit lists are missing: flagged by the kernel)
-            rec.complete = rec.ply == int(row[0]) and not truncated
-            out.append(rec)
-        return stats, out
+        return stats, decode_gpu_records(buf, n_rec.value, int(time.time()))
 
     def bench_selfplay(self, workers, moves, simulations=800, leaf_batch=16):
         """Synthetic self-play load on the running service -> (moves/s, evals/s, mean GPU batch)."""
@@ -392,6 +371,35 @@ class Network:
     def step(self, train_images, policy_labels, value_labels, assertion=False):
         raise NotImplementedError("training (network.py:148-199) is outside the accelerated path; "
                                   "train with the reference and hand the weights over with set_weights()")
+
+
+def decode_gpu_records(buf, n_records, timestamp=0):
+    """Finished games in the record layout of ``csrc/e55_gpu_selfplay.cuh`` (``finish_game`` / ``record_ply``: a four-word
+    header ``[plies, winner, words, truncated]``, then per ply ``move | not-a-target << 15, sum_N, Q * 65535, k`` and ``k``
+    ``(move, N)`` pairs) as :class:`erweitern_55_b200.gamerecord.GameRecord` objects -- what ``selfplay.run`` returns
+    (selfplay.py:80-113)."""
+    from .gamerecord import GameRecord
+    sfen = packed_move_sfen
+    out = []
+    for r in range(n_records):
+        row = buf[r]
+        rec = GameRecord()
+        rec.winner, used, truncated, w = int(row[1]), int(row[2]), int(row[3]), 4
+        while w < 4 + used:
+            mv, sum_n, q, k = int(row[w]) & 0x7FFF, int(row[w + 1]), int(row[w + 2]) / 65535.0, int(row[w + 3])
+            target = not (int(row[w]) >> 15)       # fast searches under playout-cap oscillation are no targets (selfplay.py:90-91)
+            visits = [(sfen(int(row[w + 4 + 2 * i])), int(row[w + 5 + 2 * i])) for i in range(k)]
+            w += 4 + 2 * k
+            rec.sfen_kif.append(sfen(mv))
+            rec.mcts_result.append((sum_n, q, visits))
+            if k > 0 and target:                   # (nor is a ply whose visit list did not fit the record)
+                rec.learning_target_plys.append(rec.ply)
+            rec.ply += 1
+        rec.timestamp = timestamp
+        # False if the record buffer was too small for this game (plies or visit lists are missing: flagged by the kernel)
+        rec.complete = rec.ply == int(row[0]) and not truncated
+        out.append(rec)
+    return out
 
 
 def packed_move_sfen(mv):
