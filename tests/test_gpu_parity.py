@@ -794,132 +794,14 @@ def test_umma_addressing_selftest():
     ([], 640, 2, True),                                               # "full" searches of playout-cap oscillation (selfplay.py:47-53):
 ])                                                                    # forced playouts, fresh tree per move, pruned targets
 def test_gpu_search_walks_like_the_oracle(weights_default, prefix, simulations, searches, full):
-    """select_kernel / expand_kernel (GPU-resident self-play) against oracle/mcts_oracle.py, selection by selection: one
-    game through the debug stepper with the test in the network's place (uniform priors over a pseudo-random subset of
-    the legal moves, values k/8: exact in float32).  Every selection of every round must take the oracle's path, every
-    network slot must hold the oracle position's legal moves, and the record of each search -- visit counts, Q, the move
-    played -- must be the oracle's, also after the chosen subtree has become the tree (reuse_tree)."""
-    import ctypes as C
-    import zlib
-    from erweitern_55_b200.network import Network, packed_move_sfen
-    from oracle import minishogi_oracle as MO
-    from oracle.mcts_oracle import Tree
-
+    """select_kernel / expand_kernel (GPU-resident self-play) against oracle/mcts_oracle.py, selection by selection, through
+    the debug stepper of the C ABI: tests/search_walk.py (the same walk runs on the host build of the kernels in the CPU
+    suite, tests/test_search_on_host.py)."""
+    from erweitern_55_b200.network import Network
+    from search_walk import CudaStepper, walk_like_the_oracle
     net = Network(precision="bf16", weights=weights_default)
-    lib = net._lib
-    START = "rbsgk/4p/5/P4/KGSBR b - 1"
-    # the prefix moves, packed: take them from the move lists of a device-side stepper opened on the shorter prefix
-    packed_prefix = []
-    for i, usi in enumerate(prefix):
-        h = C.c_void_p()
-        arr = (C.c_uint16 * max(1, len(packed_prefix)))(*packed_prefix)
-        net._check(lib.e55_gpu_search_open(net._ctx, arr, len(packed_prefix), 16, 0, C.byref(h)))
-        info = (C.c_int32 * 8)(); leaf = (C.c_int32 * 24)(); slot = (C.c_int32 * 24)(); plen = (C.c_int32 * 24)()
-        path = (C.c_uint16 * (24 * 96))(); cnt = (C.c_int32 * 16)(); mvs = (C.c_uint16 * (16 * 256))(); idx = (C.c_uint16 * (16 * 256))()
-        net._check(lib.e55_gpu_search_select(h, info, leaf, slot, plen, path, cnt, mvs, idx))
-        table = {packed_move_sfen(mvs[k]): mvs[k] for k in range(cnt[0])}
-        lib.e55_gpu_search_close(h)
-        assert usi in table, (usi, sorted(table))
-        packed_prefix.append(table[usi])
-
-    played = list(prefix)
-
-    def oracle_position():
-        pos = MO.Position(START)
-        for m in played:
-            pos.do_move(m)
-        return pos
-
-    def fake_network(key, n_moves):
-        hsh = zlib.crc32(key.encode())
-        keep = [((hsh >> (i % 24)) ^ i) & 3 != 0 for i in range(n_moves)]
-        if not any(keep):
-            keep[hsh % n_moves] = True
-        return keep, (hsh % 9) / 8.0
-
-    h = C.c_void_p()
-    arr = (C.c_uint16 * max(1, len(packed_prefix)))(*packed_prefix)
-    net._check(lib.e55_gpu_selfplay_set_cap(net._ctx, int(full), simulations, 128, 1.0))     # frac 1: every search a full one
-    net._check(lib.e55_gpu_search_open(net._ctx, arr, len(packed_prefix), simulations, 1, C.byref(h)))
-    info = (C.c_int32 * 8)(); leaf = (C.c_int32 * 24)(); slot = (C.c_int32 * 24)(); plen = (C.c_int32 * 24)()
-    path = (C.c_uint16 * (24 * 96))(); cnt = (C.c_int32 * 16)(); mvs = (C.c_uint16 * (16 * 256))(); idx = (C.c_uint16 * (16 * 256))()
-    priors = np.zeros((16, 256), dtype=np.float32); value = np.zeros(16, dtype=np.float32)
-    record = (C.c_uint16 * 16384)()
-    oracle = Tree()
-    total_selections = terminals = 0
-    for search in range(searches):
-        ply0 = len(played)
-        rec_words0 = None
-        for rnd in range(400):
-            net._check(lib.e55_gpu_search_select(h, info, leaf, slot, plen, path, cnt, mvs, idx))
-            assert info[0] == ply0
-            n_sel = info[2]
-            assert n_sel > 0
-            sel = []
-            for s in range(n_sel):                                    # the round's selections, virtual losses piling up
-                pos_o = oracle_position()
-                leaf_o = oracle.select_leaf(oracle.root, pos_o, full)
-                want = [packed_move_sfen(path[s * 96 + i]) for i in range(plen[s])]
-                node, walk = leaf_o, []
-                while node.parent is not None:
-                    walk.append(node.parent.moves[node.parent_edge]); node = node.parent
-                assert want == walk[::-1], (search, rnd, s, want, walk[::-1])
-                assert leaf[s] >= 0
-                sel.append((leaf_o, pos_o))
-            priors[:] = 0
-            for s, (leaf_o, pos_o) in enumerate(sel):                 # the network's answers (or the rules' verdict)
-                k = slot[s]
-                if leaf_o.expanded or leaf_o.terminal:
-                    assert k < 0
-                    continue
-                legal = sorted(pos_o.generate_moves())
-                if k < 0:                                             # the kernel found the game over at this leaf
-                    oracle.evaluate(leaf_o, pos_o, legal, [], 0.0)
-                    assert leaf_o.terminal, (search, rnd, s)
-                    terminals += 1
-                    continue
-                moves = [packed_move_sfen(mvs[k * 256 + i]) for i in range(cnt[k])]
-                assert sorted(moves) == legal
-                keep, v01 = fake_network(pos_o.board_sfen(), len(moves))
-                kept = np.float32(sum(keep))
-                priors[k, :len(moves)] = np.where(keep, np.float32(1) / kept, np.float32(0))
-                value[k] = 2 * v01 - 1
-                oracle.evaluate(leaf_o, pos_o, moves, [0.0 if kp else -1e30 for kp in keep], v01)
-                assert leaf_o.expanded
-            for leaf_o, _ in sel:
-                oracle.backpropagate(leaf_o)
-            total_selections += n_sel
-            net._check(lib.e55_gpu_search_expand(h, priors.ctypes.data, value.ctypes.data, info, record))
-            if info[0] != ply0 or info[7]:
-                break
-        else:
-            raise AssertionError("the search did not end")
-        # the ply the kernels recorded: move, sum_N, Q, visit counts == the oracle's tree
-        base, words = (4, info[6]) if info[7] else (0, info[6])
-        w, last = base, None
-        while w < base + words:
-            k = record[w + 3]
-            last = (record[w] & 0x7FFF, record[w + 1], record[w + 2] / 65535.0, {packed_move_sfen(record[w + 4 + 2 * i]): record[w + 5 + 2 * i] for i in range(k)})
-            assert not (record[w] >> 15)                              # (every ply here is a learning target)
-            w += 4 + 2 * k
-        mv, sum_n, q, visits = last
-        assert visits == oracle.visits(target_pruning=full) and sum_n == sum(visits.values())
-        if full:
-            assert visits != oracle.visits()                          # (the pruning did take forced playouts back)
-        assert abs(q - sum(float(x) for x in oracle.root.w) / sum(oracle.root.n_edge)) < 2e-5
-        best = max(range(len(oracle.root.moves)), key=lambda i: (oracle.root.n_edge[i], -i))
-        assert packed_move_sfen(mv) == oracle.root.moves[best]
-        if info[7]:
-            break                                                     # the move ended the game
-        kept = oracle.root.child[best] if not full else None          # a full search starts from a fresh tree
-        played.append(oracle.root.moves[best])
-        oracle.root = kept if (kept is not None and kept.expanded and not kept.terminal) else Tree().root
-        oracle.root.parent, oracle.root.parent_edge = None, -1
-    lib.e55_gpu_search_close(h)
-    net._check(lib.e55_gpu_selfplay_set_cap(net._ctx, 0, 800, 128, 0.25))
+    _, terminals, _, _ = walk_like_the_oracle(CudaStepper(net), prefix, simulations, searches, full)
     net.close()
-    assert total_selections >= simulations * (search + 1) - 24 * (search + 1) or info[7]
-    assert len(played) - len(prefix) == search + (0 if info[7] else 1)    # every search ended in a move
     if prefix:
         assert terminals > 0                                          # the walk did run into fourth occurrences
 
