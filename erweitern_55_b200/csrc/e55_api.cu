@@ -916,7 +916,10 @@ int e55_predict(e55_ctx* c, const float* planes, int n, float* policy, float* va
       }
     } else {
       E55_CUDA(c, cudaMemcpyAsync(c->d_in, planes, static_cast<size_t>(n) * ip * kSq * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-      if ((rc = forward_tc_on(c, c->stream, c->d_in, n, k_policy, d_value, tail))) return rc;
+      if ((rc = forward_tc_on(c, c->stream, c->d_in, n, k_policy, d_value, tail))) {
+        cudaStreamSynchronize(c->stream);   // the copy may still be reading the caller's (page-locked) planes
+        return rc;
+      }
     }
     const size_t pol_bytes = static_cast<size_t>(n) * kPolicyCh * kSq * sizeof(float);
     if (!direct_policy) E55_CUDA(c, cudaMemcpyAsync(out_policy, c->d_policy, pol_bytes, cudaMemcpyDeviceToHost, c->stream));
@@ -932,7 +935,10 @@ int e55_predict(e55_ctx* c, const float* planes, int n, float* policy, float* va
   }
   const size_t in_bytes = static_cast<size_t>(n) * c->in_planes * kSq * sizeof(float);
   E55_CUDA(c, cudaMemcpyAsync(c->d_in, planes, in_bytes, cudaMemcpyHostToDevice, c->stream));
-  if ((rc = forward(c, c->d_in, n, c->d_policy, c->d_value))) return rc;
+  if ((rc = forward(c, c->d_in, n, c->d_policy, c->d_value))) {
+    cudaStreamSynchronize(c->stream);
+    return rc;
+  }
   E55_CUDA(c, cudaMemcpyAsync(policy, c->d_policy, static_cast<size_t>(n) * kPolicyCh * kSq * sizeof(float),
                               cudaMemcpyDeviceToHost, c->stream));
   E55_CUDA(c, cudaMemcpyAsync(value, c->d_value, static_cast<size_t>(n) * sizeof(float), cudaMemcpyDeviceToHost,

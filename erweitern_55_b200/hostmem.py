@@ -18,7 +18,7 @@ from . import _capi
 _MIN_BYTES = 256 << 10          # smaller results are ordinary numpy arrays
 _MAX_CACHED_BYTES = 512 << 20   # free-list cap; beyond it blocks go back to the driver
 
-_lock = threading.Lock()
+_lock = threading.RLock()      # re-entrant: a garbage collection inside a locked section may run a block's __del__ on the same thread
 _free: dict[int, list[int]] = {}
 _cached_bytes = 0
 
