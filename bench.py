@@ -257,17 +257,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def host_exchange(tag, payload, timeout_s=900):
-        """Every rank's `payload` (JSON-able), as a list by rank on every rank, through the rendezvous store: a meeting point
-        on the host that works whatever state the devices are in."""
-        if world == 1:
-            return [payload]
-        import datetime
-        store = dist.distributed_c10d._get_default_store()
-        store.set(f"e55/{tag}/{rank}", json.dumps(payload))
-        keys = [f"e55/{tag}/{i}" for i in range(world)]
-        store.wait(keys, datetime.timedelta(seconds=timeout_s))
-        return [json.loads(store.get(k)) for k in keys]
+    host_exchange = sharding.exchange                  # all ranks' payloads through the rendezvous store (host side only)
 
     def repeat_regions(region, est_s):
         """Runs `region()` (-> seconds of one K-step region) until MIN_TIMED_S have been timed; median, count, total."""

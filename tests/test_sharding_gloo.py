@@ -21,7 +21,9 @@ def _worker(rank, world, port, q):
     a, b = sharding.shard_range(1001, rank, world)
     dist.barrier()
     total, secs = sharding.aggregate(b - a, 0.5 + rank)
-    q.put((rank, a, b, total, secs))
+    got = sharding.exchange("moves", {"moves": 10 * (rank + 1), "seconds": 1.5 - rank, "error": None if rank else "x"})
+    again = sharding.exchange("again", rank)
+    q.put((rank, a, b, total, secs, got, again))
     dist.destroy_process_group()
 
 
@@ -38,3 +40,7 @@ def test_two_rank_aggregation():
         assert p.exitcode == 0
     assert [(r[1], r[2]) for r in res] == [(0, 501), (501, 1001)]
     assert all(r[3] == 1001.0 and r[4] == 1.5 for r in res)
+    # the host-side meeting point bench.py uses around the GPU-resident self-play: every rank sees every rank's payload
+    want = [{"moves": 10, "seconds": 1.5, "error": "x"}, {"moves": 20, "seconds": 0.5, "error": None}]
+    assert all(r[5] == want and r[6] == [0, 1] for r in res)
+    assert sharding.exchange("alone", {"a": 1}) == [{"a": 1}]           # not distributed: identity
