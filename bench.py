@@ -11,8 +11,8 @@ is used only for the barrier and the max/sum of the results.
 
 What the ONE JSON line holds is described in DESIGN.md section 5 (the line itself carries numbers, not prose):
 `value` (device-resident inputs, CUDA events on the launching streams, K steps per timed region, regions repeated
-for >= 0.6 s, median region, max over ranks), `e2e` (the drop-in call Network.predict(numpy) -> numpy on page-locked
-host arrays, copies inside the timed region), `roofline`, `cpu_baseline`, and the other configs of BASELINE.json
+for >= 0.6 s, median region, max over ranks), `e2e` (the drop-in call Network.predict(numpy) -> numpy on ordinary
+pageable numpy arrays, copies inside the timed region), `roofline`, `cpu_baseline`, and the other configs of BASELINE.json
 (`selfplay*`: configs[3], `scaled_20x256`: configs[4], `e2e.small_batches`: configs[0]/[2]).
 `--impl reference` times the reference's CPU path stand-in (the oracle port; TensorFlow 1.15 cannot run here).
 """
@@ -334,8 +334,9 @@ def main():
                     "peak_burst": burst, "frac_of_burst": achieved / burst, "launches_timed": k_n}
 
     # ---- end to end: the drop-in call, Network.predict(numpy) -> numpy (network.py:201-216) ----------------------
-    # Inputs: three page-locked numpy arrays in rotation (81 MB: the planes come from DRAM, not from the host's cache),
-    # as Network.zero_inputs hands them out; results: the fresh numpy arrays predict returns.
+    # Inputs: three numpy arrays in rotation (81 MB: the planes come from DRAM, not from the host's cache) -- ordinary
+    # pageable ones for the headline, page-locked ones (as Network.zero_inputs hands them out) beside it; results: the
+    # fresh numpy arrays predict returns.
     def pinned_copy(a):
         b = hostmem.empty(a.shape)
         b[...] = a
