@@ -386,6 +386,41 @@ def main():
         xs = [synth.synthetic_planes(nb, seed=70 + i) for i in range(3)]
         rate, call_s = e2e_rate(xs, nb, 200)
         small[str(nb)] = {"us_per_call": call_s * 1e6, "evals_per_s": rate}
+    # ---- batch sweep (BASELINE.json configs[2]) on this rank: device-resident us per launch, Network.predict us per call ----
+    batch_sweep = None
+    if default_net and args.precision == "bf16":
+        try:
+            big = torch.cat(pool[:4])[:4096] if B * min(len(pool), 4) >= 4096 else None
+            sweep_p = torch.empty((4096, 1725), dtype=torch.float32, device=dev)
+            sweep_v = torch.empty((4096, 1), dtype=torch.float32, device=dev)
+            host_big = np.concatenate(host_src + [host_src[0]])[:4096] if 4 * B >= 4096 else None
+            batch_sweep = {}
+            for nb in (1, 16, 64, 256, 512, 1024, 1184, 2048, 4096):
+                if big is None or host_big is None or nb > big.shape[0]:
+                    continue
+                xs_d = big[:nb]
+                for _ in range(5):
+                    net.predict_device(xs_d, sweep_p[:nb], sweep_v[:nb])
+                net.sync()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                reps = 40 if nb <= 1184 else 12
+                e0.record(stream)
+                for _ in range(reps):
+                    net.predict_device(xs_d, sweep_p[:nb], sweep_v[:nb])
+                e1.record(stream)
+                net.sync()
+                dev_us = e0.elapsed_time(e1) * 1e3 / reps
+                xs_h = host_big[:nb]
+                for _ in range(3):
+                    net.predict(xs_h)
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    net.predict(xs_h)
+                call_us = (time.perf_counter() - t0) * 1e6 / reps
+                batch_sweep[str(nb)] = {"device_us": round(dev_us, 1), "predict_us": round(call_us, 1)}
+            del big, sweep_p, sweep_v, host_big
+        except Exception as exc:                       # an extra: never at the cost of the line
+            batch_sweep = {"error": str(exc)[:200]}
     # the host-memory roofline of this number: all ranks at once read 256 MiB each with their pool threads (nothing else:
     # no packing, no copies); every position costs 26 600 bytes of such reads, by cores or copy engine
     gbs = C.c_double()
@@ -400,7 +435,7 @@ def main():
            "input_memory": "numpy arrays (pageable), 3 in rotation", "host_input_bytes_per_step": in_bytes,
            "host_pack_threads": pk_threads.value, "value_pinned_input": e2e_pinned, "pinned_input_float_eighths": best_share,
            "pinned_input_us_per_position_by_float_eighths": {str(sh): round(u, 4) for sh, u in zip(shares, split_us)},
-           "value_without_host_packing": e2e_plain, "small_batches": small}
+           "value_without_host_packing": e2e_plain, "small_batches": small, "batch_sweep_rank0": batch_sweep}
 
     # ---- same call with the compact input format (e55_predict_packed; not the reference's format) ---
     packed = [packing.pack_planes(a) for a in host_src]
