@@ -9,6 +9,7 @@ and is handed out again by a later call, so a search loop keeps reusing the same
 from __future__ import annotations
 
 import ctypes as C
+import math
 import threading
 
 import numpy as np
@@ -56,7 +57,7 @@ def empty(shape, dtype=np.float32):
     """Uninitialised array like ``np.empty``; page-locked when it is large enough to matter."""
     global _cached_bytes
     dt = np.dtype(dtype)
-    nbytes = int(np.prod(shape)) * dt.itemsize
+    nbytes = math.prod(int(d) for d in shape) * dt.itemsize      # (np.prod costs 3 us: a third of a small call's Python time)
     if nbytes < _MIN_BYTES:
         return np.empty(shape, dtype=dt)
     size = _round(nbytes)
