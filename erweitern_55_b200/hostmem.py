@@ -19,6 +19,7 @@ from . import _capi
 _MIN_BYTES = 256 << 10          # smaller results are ordinary numpy arrays
 _MAX_CACHED_BYTES = 512 << 20   # free-list cap; beyond it blocks go back to the driver
 
+_F32 = np.dtype(np.float32)
 _lock = threading.RLock()      # re-entrant: a garbage collection inside a locked section may run a block's __del__ on the same thread
 _free: dict[int, list[int]] = {}
 _cached_bytes = 0
@@ -56,8 +57,8 @@ class _Block:
 def empty(shape, dtype=np.float32):
     """Uninitialised array like ``np.empty``; page-locked when it is large enough to matter."""
     global _cached_bytes
-    dt = np.dtype(dtype)
-    nbytes = math.prod(int(d) for d in shape) * dt.itemsize      # (np.prod costs 3 us: a third of a small call's Python time)
+    dt = _F32 if dtype is np.float32 else np.dtype(dtype)
+    nbytes = int(math.prod(shape)) * dt.itemsize      # (np.prod costs 3 us: a third of a small call's Python time)
     if nbytes < _MIN_BYTES:
         return np.empty(shape, dtype=dt)
     size = _round(nbytes)
