@@ -122,9 +122,22 @@ def test_gpu_search_kernels_on_the_host_under_asan_ubsan(tmp_path):
     assert mates > 0
     # sharper priors (deep, narrow trees), full-size searches, no mate search, no tree reuse, length limit, playout-cap oscillation
     _gs_clean(_gs_run(exe, games=8, moves=300, simulations=800, seed=3, sharp=20.0))
-    st = _gs_run(exe, games=16, moves=1200, simulations=160, mate_depth=5, noise=0, max_moves=40, seed=4, sharp=2.0, cap=(1, 160, 32, 0.25))
+    st = _gs_run(exe, games=16, moves=1200, simulations=160, mate_depth=5, noise=0, max_moves=40, seed=4, sharp=2.0, cap=(1, 160, 32, 0.25),
+                 records_out=rec_file)
     _gs_clean(st)
     assert st["ended_by_length"] > 0
+    # playout-cap oscillation in the records (selfplay.py:45-61,90-91): only the fully searched plies (about a quarter) and
+    # the mate-search moves are learning targets; a fast search records what its 32 simulations (or the reused tree) saw
+    buf = np.fromfile(rec_file, dtype=np.uint16).reshape(-1, 16384)
+    games = decode_gpu_records(buf, len(buf))
+    plies = sum(g.ply for g in games)
+    targets = sum(len(g.learning_target_plys) for g in games)
+    assert 0.1 * plies < targets < 0.6 * plies, (targets, plies)
+    for g in games:
+        assert g.complete and all(0 <= t < g.ply for t in g.learning_target_plys)
+        for t, (sum_n, _, visits) in enumerate(g.mcts_result):
+            if t in g.learning_target_plys and visits != [(g.sfen_kif[t], 1)]:
+                assert sum_n >= 100, (t, sum_n)                          # a full search of 160 simulations, pruned (Wu 2019)
     _gs_clean(_gs_run(exe, games=16, moves=800, simulations=160, mate_depth=0, reuse_tree=0, seed=5, sharp=0.0))
 
 
