@@ -94,3 +94,22 @@ def test_pack_planes_roundtrip_and_rejection():
         packing.pack_planes(bad)
     with pytest.raises(ValueError):
         packing.pack_planes(np.zeros((2, 3, 4, 5)))
+
+
+def test_result_array_pool_without_a_device():
+    """hostmem.empty is np.empty to its callers: right shape and dtype whatever the size, views keep their block alive,
+    and without a CUDA device (no page-locked memory to be had) it hands out ordinary arrays instead of failing."""
+    import gc
+    import torch
+    from erweitern_55_b200 import hostmem
+    for shape, dtype in (((16, 1725), np.float32), ((1024, 1725), np.float32), ([3, 266, 5, 5], np.float32), ((70000,), np.uint8)):
+        a = hostmem.empty(shape, dtype)
+        assert isinstance(a, np.ndarray) and a.shape == tuple(shape) and a.dtype == np.dtype(dtype) and a.flags.c_contiguous and a.flags.writeable
+        a[...] = 1
+        v = a[1:] if a.ndim > 1 else a[10:]
+        del a
+        gc.collect()
+        assert (v == 1).all()                                          # the view holds the memory
+    if not torch.cuda.is_available():
+        assert hostmem.empty((1024, 1725)).base is None                # pageable: nothing page-locked without a device
+    hostmem.trim()
