@@ -8,7 +8,8 @@
 //   select_kernel   per game: selections with virtual loss until kLeaf network slots are filled; each new leaf gets its
 //                   terminal test, its legal moves (stored as the node's edges straight away) and its bit-packed
 //                   planes in a batch slot
-//   tower_kernel    all slots of a cohort of games in one launch (e55_tc.cuh), then legal_priors_strided_kernel
+//   tower_kernel    all slots of a cohort of games in one launch (e55_tc.cuh); its policy tail soft-maxes each slot's
+//                   legal moves (fixed-stride lists) into the priors: no logits in HBM, no second kernel
 //   expand_kernel   per game: priors and values into the new nodes, back-up of every selection; after the last
 //                   simulation of a move: choose it (sampled from the visit counts for the first plies), play it,
 //                   test for the end of the game, start the next search (or the next game)
@@ -649,6 +650,8 @@ __global__ void __launch_bounds__(64) select_kernel(Params p) {
 }
 
 // legal_priors_kernel (e55_fp32.cuh) for fixed-stride move lists: position p owns index/priors [p*stride, +count[p]).
+// Not launched any more (round 2: the tower kernel's policy tail does this from shared memory); kept as the plain statement
+// of what the strided tail computes.
 __global__ void __launch_bounds__(256)
 legal_priors_strided_kernel(const float* __restrict__ logits, const int32_t* __restrict__ count, const uint16_t* __restrict__ index,
                             float* __restrict__ priors, int n, int width, int stride) {
