@@ -35,9 +35,10 @@ def main():
             prefix.append(m)
         if not pos.generate_moves() or pos.is_repetition()[0]:
             prefix = prefix[:-1]                                      # the game must not be over before the search
-        sims = rng.choice([16, 32, 64, 160, 320])
-        searches = rng.choice([1, 2, 3, 5])
-        full = rng.random() < 0.3
+        heavy = os.environ.get("WALK_FUZZ_HEAVY") == "1"             # larger searches, mostly "full" ones (forced playouts, pruning)
+        sims = rng.choice([320, 480, 800, 1024] if heavy else [16, 32, 64, 160, 320])
+        searches = rng.choice([1, 2] if heavy else [1, 2, 3, 5])
+        full = rng.random() < (0.7 if heavy else 0.3)
         try:
             s, t, played, ended = walk_like_the_oracle(stepper, prefix, sims, searches, full, expect_pruning=False)
         except AssertionError:
