@@ -690,47 +690,6 @@ def test_device_resident_api(nets):
     assert np.array_equal(pd.cpu().numpy(), p) and np.array_equal(vd.cpu().numpy(), v)
 
 
-@pytest.mark.timeout(300, method="thread")   # a launch that never ends must end the run, not hang it
-def test_one_launch_of_many_rounds(weights_perturbed):
-    """A single launch far beyond the grid (120 rounds per CTA: what a GPU self-play round of 8192 games x 16 leaves is) gives
-    every position the result it has in a one-round launch -- per-launch state that only shows after hundreds of input
-    slices per CTA (barrier phases, slice counters) has nowhere to hide."""
-    from erweitern_55_b200.network import Network
-    reps, nb = 120, 1184
-    net = Network(precision="bf16", weights=weights_perturbed, max_batch=nb)
-    xb = torch.from_numpy(synth.synthetic_planes(nb, seed=31)).cuda()
-    pb = torch.empty((nb, 1725), device="cuda")
-    vb = torch.empty((nb, 1), device="cuda")
-    net.predict_device(xb, pb, vb)
-    net.sync()
-    x = xb.repeat(reps, 1, 1, 1).contiguous()
-    p = torch.full((reps * nb, 1725), float("nan"), device="cuda")
-    v = torch.full((reps * nb, 1), float("nan"), device="cuda")
-    net.predict_device(x, p, v)
-    net.sync()
-    assert torch.equal(p.view(reps, nb, 1725), pb.unsqueeze(0).expand(reps, nb, 1725))
-    assert torch.equal(v.view(reps, nb, 1), vb.unsqueeze(0).expand(reps, nb, 1))
-    n_odd = 100 * nb + 5                                               # ragged: the last round is partly empty
-    p.fill_(float("nan")); v.fill_(float("nan"))
-    net.predict_device(x[:n_odd], p[:n_odd], v[:n_odd])
-    net.sync()
-    assert torch.equal(p[:n_odd], pb.repeat(101, 1)[:n_odd]) and torch.equal(v[:n_odd], vb.repeat(101, 1)[:n_odd])
-    assert bool(torch.isnan(p[n_odd:]).all()) and bool(torch.isnan(v[n_odd:]).all())
-    net.close()
-    del x, p, v
-    torch.cuda.empty_cache()
-
-
-@pytest.mark.timeout(300, method="thread")   # a launch that never ends must end the run, not hang it
-def test_gpu_selfplay_at_the_bench_size(weights_default):
-    """16384 games in flight (two cohorts, 131072 network slots per launch on 124 SMs): one move per game, no overflow."""
-    from erweitern_55_b200.network import Network
-    net = Network(precision="bf16", weights=weights_default)
-    stats, _ = net.gpu_selfplay(games=16384, total_moves=16384, simulations=32, seed=3)
-    assert stats["moves"] >= 16384 and stats["tree_overflows"] == 0 and stats["evals"] >= 16384 * 16
-    net.close()
-
-
 def test_small_and_scaled_architectures(weights_default):
     """Other tower shapes on both paths: 2 blocks x 128 filters on 40 input planes, 2 blocks x 256 filters
     (the width of BASELINE.json configs[4]; the tcgen05 kernel has a 256-filter instantiation)."""
@@ -902,3 +861,45 @@ def test_layout_adapter_on_the_gpu(weights_perturbed):
     p2, v2 = a.predict(x)
     assert np.array_equal(p2, p_plain) and np.array_equal(v2, v_plain)
     a.close(); b.close()
+
+
+# ---- launches far beyond the grid (last in the file: whatever happens here, every other test has run) --------------------
+@pytest.mark.timeout(300, method="thread")   # a launch that never ends must end the run, not hang it
+def test_one_launch_of_many_rounds(weights_perturbed):
+    """A single launch far beyond the grid (120 rounds per CTA: what a GPU self-play round of 8192 games x 16 leaves is) gives
+    every position the result it has in a one-round launch -- per-launch state that only shows after hundreds of input
+    slices per CTA (barrier phases, slice counters) has nowhere to hide."""
+    from erweitern_55_b200.network import Network
+    reps, nb = 120, 1184
+    net = Network(precision="bf16", weights=weights_perturbed, max_batch=nb)
+    xb = torch.from_numpy(synth.synthetic_planes(nb, seed=31)).cuda()
+    pb = torch.empty((nb, 1725), device="cuda")
+    vb = torch.empty((nb, 1), device="cuda")
+    net.predict_device(xb, pb, vb)
+    net.sync()
+    x = xb.repeat(reps, 1, 1, 1).contiguous()
+    p = torch.full((reps * nb, 1725), float("nan"), device="cuda")
+    v = torch.full((reps * nb, 1), float("nan"), device="cuda")
+    net.predict_device(x, p, v)
+    net.sync()
+    assert torch.equal(p.view(reps, nb, 1725), pb.unsqueeze(0).expand(reps, nb, 1725))
+    assert torch.equal(v.view(reps, nb, 1), vb.unsqueeze(0).expand(reps, nb, 1))
+    n_odd = 100 * nb + 5                                               # ragged: the last round is partly empty
+    p.fill_(float("nan")); v.fill_(float("nan"))
+    net.predict_device(x[:n_odd], p[:n_odd], v[:n_odd])
+    net.sync()
+    assert torch.equal(p[:n_odd], pb.repeat(101, 1)[:n_odd]) and torch.equal(v[:n_odd], vb.repeat(101, 1)[:n_odd])
+    assert bool(torch.isnan(p[n_odd:]).all()) and bool(torch.isnan(v[n_odd:]).all())
+    net.close()
+    del x, p, v
+    torch.cuda.empty_cache()
+
+
+@pytest.mark.timeout(300, method="thread")   # a launch that never ends must end the run, not hang it
+def test_gpu_selfplay_at_the_bench_size(weights_default):
+    """16384 games in flight (two cohorts, 131072 network slots per launch on 124 SMs): one move per game, no overflow."""
+    from erweitern_55_b200.network import Network
+    net = Network(precision="bf16", weights=weights_default)
+    stats, _ = net.gpu_selfplay(games=16384, total_moves=16384, simulations=32, seed=3)
+    assert stats["moves"] >= 16384 and stats["tree_overflows"] == 0 and stats["evals"] >= 16384 * 16
+    net.close()
