@@ -4,9 +4,9 @@
 # limit, prior sharpness, playout-cap oscillation), each on three builds -- ASan+UBSan with small pools (suspension and
 # record truncation all the time), ASan+UBSan with the real pool sizes, and an optimised build with more games.  Every
 # run audits every tree after every round and replays every finished game; the script stops at the first failure.
-#   tools/gs_host_fuzz.sh <seconds> [work dir]
+#   tools/gs_host_fuzz.sh <seconds> [work dir] [first seed]
 set -u
-SECS=${1:-600}; DIR=${2:-/tmp/gsfuzz}; ROOT=$(cd "$(dirname "$0")/.." && pwd)
+SECS=${1:-600}; DIR=${2:-/tmp/gsfuzz}; SEED0=${3:-1000}; ROOT=$(cd "$(dirname "$0")/.." && pwd)
 mkdir -p "$DIR"
 INC="-Wno-unknown-pragmas -Wno-attributes -I$ROOT/tests/native/shim -I$ROOT/erweitern_55_b200/csrc"
 SAN="g++ -O1 -g -std=c++20 -ffp-contract=off -fsanitize=address,undefined -fno-sanitize-recover=all -fno-omit-frame-pointer $INC"
@@ -16,7 +16,7 @@ g++ -O2 -std=c++20 -ffp-contract=off $INC -o "$DIR/fast" "$ROOT/tests/native/gs_
 pick() { python3 -c "import random,sys;random.seed($1);print(random.choice(sys.argv[1:]))" "${@:2}"; }
 T0=$(date +%s); i=0; runs=0
 while [ $(( $(date +%s) - T0 )) -lt "$SECS" ]; do
-  i=$((i+1)); seed=$((1000+i))
+  i=$((i+1)); seed=$((SEED0+i))
   sharp=$(pick $seed 0.0 1.0 3.0 6.0 12.0 30.0 100.0); sims=$(pick $((seed+1)) 16 32 160 480 800 1024)
   mate=$(pick $((seed+2)) 0 3 5 7); maxm=$(pick $((seed+3)) 30 80 512 512)
   reuse=$((i%3!=0)); noise=$((i%2)); cap=$((i%5==0))
