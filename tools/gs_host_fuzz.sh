@@ -24,7 +24,7 @@ while [ $(( $(date +%s) - T0 )) -lt "$SECS" ]; do
     games=16; moves=800; [ $bin = fast ] && games=64 && moves=6000
     out=$("$DIR/$bin" $games $moves $sims $mate $reuse $noise $maxm $seed $sharp $cap 800 128 0.25 64 - 2>&1); rc=$?
     runs=$((runs+1))
-    echo "$i $bin sims=$sims mate=$mate reuse=$reuse noise=$noise max=$maxm sharp=$sharp cap=$cap rc=$rc $(echo "$out" | tail -1 | cut -c1-400)" >> "$DIR/log.txt"
+    echo "$i $bin sims=$sims mate=$mate reuse=$reuse noise=$noise max=$maxm sharp=$sharp cap=$cap rc=$rc $(echo "$out" | tail -1)" >> "$DIR/log.txt"
     if [ $rc -ne 0 ]; then echo "FAILED: $bin seed $seed"; echo "$out" | tail -5; exit 1; fi
   done
 done
